@@ -1,0 +1,115 @@
+"""ctypes binding for the synthetic bubble-chain GBWT generator (synth/gbwt_synth.c).
+
+Test / benchmark input only: it produces Simple-SDS GBWT images and the
+query patterns of SURVEY.md 8(d). Not part of the product and not the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    path = os.path.join(_HERE, "libgbwt_synth.so")
+    src = [os.path.join(_HERE, f) for f in ("gbwt_synth.c", "Makefile")]
+    stale = (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return path
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        u64, p = C.c_uint64, C.c_void_p
+        L.synth_mix64.restype = u64
+        L.synth_mix64.argtypes = [u64]
+        L.synth_allele.restype = C.c_uint
+        L.synth_allele.argtypes = [u64, u64, u64, u64]
+        L.synth_bubble_chain_gbwt.restype = p
+        L.synth_bubble_chain_gbwt.argtypes = [u64, u64, u64, C.c_int, C.POINTER(u64)]
+        L.synth_gbwt_image.restype = p
+        L.synth_gbwt_image.argtypes = [u64, u64, u64, u64, u64, p, u64, p, u64, C.POINTER(u64)]
+        L.synth_bwt_section.restype = p
+        L.synth_bwt_section.argtypes = [p, u64, p, u64, C.POINTER(u64)]
+        L.synth_free.argtypes = [p]
+        L.synth_sequence.argtypes = [u64, u64, u64, u64, p]
+        L.synth_patterns.argtypes = [u64, u64, u64, u64, u64, u64, u64, p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+class Image:
+    """A malloc'd Simple-SDS GBWT image owned by the C library (zero-copy numpy view)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.ptr, self.nbytes = ptr, n
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr))
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self.ptr, self.nbytes)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().synth_free(self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def bubble_chain(sites: int, haplotypes: int, seed: int = 42, threads: int = 0) -> Image:
+    """Bubble chain with `sites` sites (N = 3*sites + 1 nodes) and `haplotypes` haplotypes."""
+    n = C.c_uint64(0)
+    ptr = lib().synth_bubble_chain_gbwt(sites, haplotypes, seed, threads, C.byref(n))
+    if not ptr:
+        raise ValueError("invalid bubble-chain parameters")
+    return Image(ptr, n.value)
+
+
+def gbwt_image(sequences, size, offset, alphabet_size, flags, rec_starts, data: bytes) -> bytes:
+    starts = np.ascontiguousarray(rec_starts, dtype=np.uint64)
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    n = C.c_uint64(0)
+    ptr = lib().synth_gbwt_image(sequences, size, offset, alphabet_size, flags, starts.ctypes.data_as(C.c_void_p),
+                                 len(starts), buf.ctypes.data_as(C.c_void_p), len(buf), C.byref(n))
+    out = C.string_at(ptr, n.value)
+    lib().synth_free(ptr)
+    return out
+
+
+def bwt_section(rec_starts, data: bytes) -> bytes:
+    starts = np.ascontiguousarray(rec_starts, dtype=np.uint64)
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    n = C.c_uint64(0)
+    ptr = lib().synth_bwt_section(starts.ctypes.data_as(C.c_void_p), len(starts), buf.ctypes.data_as(C.c_void_p),
+                                  len(buf), C.byref(n))
+    out = C.string_at(ptr, n.value)
+    lib().synth_free(ptr)
+    return out
+
+
+def sequence(sites: int, haplotypes: int, seed: int, seq_id: int) -> np.ndarray:
+    out = np.zeros(2 * sites + 1, dtype=np.uint64)
+    lib().synth_sequence(sites, haplotypes, seed, seq_id, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def patterns(sites: int, haplotypes: int, seed: int, n: int, k: int = 32, seed_q: int = 7, q0: int = 0,
+             threads: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+    if out is None:
+        out = np.empty((n, k), dtype=np.uint64)
+    assert out.dtype == np.uint64 and out.flags.c_contiguous and out.size == n * k
+    lib().synth_patterns(sites, haplotypes, seed, seed_q, q0, n, k, out.ctypes.data_as(C.c_void_p), threads)
+    return out
