@@ -1,0 +1,79 @@
+// layout.h -- the device-resident GBWT layout (shared by the host builder and the kernels).
+//
+// The reference keeps the BWT as one byte vector of variable-length ByteCode/RLE records located by
+// an Elias-Fano select (gbwt-rs src/bwt.rs:96-130) and re-decodes the edge list into a heap Vec on
+// every access (src/bwt.rs:378-395). Here every record gets
+//   * one 32-byte descriptor (= one HBM sector) holding what `find`, `edge_to` and the scan need, with
+//     the edge list inline when the outdegree is <= 2, and
+//   * a 16-byte-aligned body in one of five formats chosen per record at load time so that a rank query
+//     touches as few sectors as possible and never needs a serial varint decode.
+// All formats are semantically equal to the reference's run sequence: len / lf / follow / bd_follow
+// only depend on the sums of |run ∩ range| per symbol (src/bwt.rs:449-496, 595-656), which are invariant
+// under splitting a run, and on the symbol at a position.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GBWT_HD __host__ __device__ __forceinline__
+#define GBWT_UNROLL _Pragma("unroll")
+#else
+#define GBWT_HD inline
+#define GBWT_UNROLL
+#endif
+
+namespace gbwt_b200 {
+
+enum BodyFormat : uint8_t {
+    FMT_EMPTY = 0,   // sigma == 0: BWT::record() is None (src/bwt.rs:342, 381)
+    FMT_SINGLE = 1,  // sigma == 1: every position maps to edge 0, no body needed
+    FMT_DENSE2 = 2,  // sigma == 2: plain bitvector, 32-byte blocks {u32 ones_before, 224 bits}
+    FMT_RUN8 = 3,    // one byte per run: value + sigma * (len - 1), len <= max(1, 256 / sigma); no escapes
+    FMT_RUN32 = 4,   // one u32 per run: value | (len - 1) << 8, sigma <= 256, len <= 2^24
+    FMT_RUN64 = 5,   // two u32 per run: value, len
+    FMT_COUNT = 6
+};
+
+constexpr uint32_t DENSE_BITS = 224;        // payload bits per 32-byte dense block
+constexpr uint32_t DENSE_WORDS = 7;
+constexpr uint8_t DESC_INLINE_EDGES = 1;    // w[] = {node0, offset0, node1, offset1}
+constexpr uint32_t RUN32_MAX_LEN = 1u << 24;
+constexpr uint32_t NO_SYMBOL = 0xFFFFFFFFu;
+
+// One record. 32 bytes, 32-byte aligned: a single sector fetch gives everything but the body.
+struct alignas(32) RecordDesc {
+    uint32_t body;       // offset of the body in 16-byte units
+    uint32_t body_len;   // RUN8: bytes; RUN32 / RUN64: runs; DENSE2: 32-byte blocks
+    uint32_t total_len;  // Record::len(), src/bwt.rs:449-455
+    uint16_t sigma16;    // min(sigma, 65535)
+    uint8_t fmt;         // BodyFormat
+    uint8_t flags;
+    // DESC_INLINE_EDGES: {node0, offset0, node1, offset1} (node1 unused when sigma == 1)
+    // otherwise:         {first edge index into IndexView::edges, sigma, magic = 65536 / sigma + 1, 0}
+    uint32_t w[4];
+};
+static_assert(sizeof(RecordDesc) == 32, "descriptor must be one sector");
+
+// One 16-byte unit of body storage (loaded with a single 128-bit access on the device).
+struct alignas(16) Unit16 { uint32_t x, y, z, w; };
+
+// Edge (node, offset), src/bwt.rs:63-69, narrowed to 32 bits.
+struct Edge { uint32_t node, offset; };
+
+// Everything a kernel needs; passed by value.
+struct IndexView {
+    const RecordDesc* desc;   // [records]
+    const Unit16* bodies;     // 16-byte units
+    const Edge* edges;        // edge lists of records with sigma > 2
+    const Edge* endmarker;    // [endmarker_len] decompressed endmarker record (src/gbwt.rs:413-414)
+    uint64_t records;         // BWT::len()
+    uint64_t offset;          // alphabet offset (src/gbwt.rs:127-129)
+    uint64_t alphabet_size;
+    uint64_t sequences;
+    uint64_t endmarker_len;
+    uint32_t bidirectional;
+};
+
+// Magic multiplier for q = b / sigma, 0 <= b < 256, 1 <= sigma <= 256: q = (b * magic) >> 16.
+GBWT_HD uint32_t div_magic(uint32_t sigma) { return 65536u / sigma + 1u; }
+
+}  // namespace gbwt_b200

@@ -1,0 +1,283 @@
+// layout_builder.cpp -- see layout_builder.h and layout.h.
+#include "layout_builder.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+
+#include "../../include/gbwt_b200.h"
+
+namespace gbwt_b200 {
+namespace {
+
+// Decoder for one record in the reference encoding. Follows ByteCodeIter::next (src/support.rs:1151-1164)
+// and RLEIter::next (src/support.rs:1413-1430) with RLE::sanitize (src/support.rs:1292-1296).
+struct RecordReader {
+    const uint8_t* p;
+    uint64_t n, at = 0;
+    uint64_t sigma = 0, threshold = 0;
+    bool bad = false;
+
+    RecordReader(const uint8_t* bytes, uint64_t len) : p(bytes), n(len) {}
+
+    bool varint(uint64_t& v) {
+        v = 0;
+        for (unsigned shift = 0; at < n; shift += 7) {
+            uint8_t b = p[at++];
+            if (shift < 64) v += static_cast<uint64_t>(b & 0x7F) << shift;
+            if (!(b & 0x80)) return true;
+        }
+        return false;
+    }
+    void begin_runs(uint64_t s) {
+        sigma = s;
+        threshold = (s < 255) ? 256 / s : 0;
+    }
+    // One run of the reference's sequence; false at the end of the record (or on a truncated run).
+    bool run(uint64_t& value, uint64_t& len) {
+        if (at >= n) return false;
+        if (sigma >= 255) {
+            uint64_t l;
+            if (!varint(value) || !varint(l)) { bad = true; return false; }
+            len = l + 1;
+        } else {
+            uint8_t b = p[at++];
+            value = b % sigma;
+            len = b / sigma + 1;
+            if (len == threshold) {
+                uint64_t extra;
+                if (!varint(extra)) { bad = true; return false; }
+                len += extra;
+            }
+        }
+        return true;
+    }
+};
+
+struct Plan {
+    uint64_t sigma = 0, total = 0, runs = 0, run8 = 0, run32 = 0, header_end = 0;
+    uint8_t fmt = FMT_EMPTY;
+    uint32_t units = 0;   // body size in 16-byte units
+    int status = GBWT_B200_OK;
+};
+
+inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Pass 1: size every candidate format and pick one.
+Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
+    Plan pl;
+    if (len == 0) return pl;  // Record::new: empty slice -> None (src/bwt.rs:342)
+    RecordReader rd(bytes, len);
+    if (!rd.varint(pl.sigma)) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
+    if (pl.sigma == 0) return pl;  // decompress_edges: sigma == 0 -> None (src/bwt.rs:381)
+    if (pl.sigma > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
+    uint64_t node = 0;
+    for (uint64_t i = 0; i < pl.sigma; i++) {
+        uint64_t delta, off;
+        if (!rd.varint(delta) || !rd.varint(off)) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
+        node += delta;
+        if (node > 0xFFFFFFFFull || off > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
+    }
+    pl.header_end = rd.at;
+    rd.begin_runs(pl.sigma);
+    const uint64_t max8 = pl.sigma <= 256 ? std::max<uint64_t>(1, 256 / pl.sigma) : 0;
+    uint64_t value, rl;
+    while (rd.run(value, rl)) {
+        if (value >= pl.sigma) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
+        pl.total += rl;
+        pl.runs++;
+        if (max8) pl.run8 += ceil_div(rl, max8);
+        pl.run32 += ceil_div(rl, RUN32_MAX_LEN);
+        if (pl.total > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
+    }
+    if (rd.bad) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
+    if (pl.sigma == 1) { pl.fmt = FMT_SINGLE; return pl; }
+    uint64_t best = ~0ull;
+    if (pl.sigma <= 256) {
+        best = ceil_div(pl.run8, 16); pl.fmt = FMT_RUN8;
+        uint64_t u32 = ceil_div(pl.run32 * 4, 16);
+        if (u32 < best) { best = u32; pl.fmt = FMT_RUN32; }
+    } else {
+        best = ceil_div(pl.runs * 8, 16); pl.fmt = FMT_RUN64;
+    }
+    if (pl.sigma == 2 && policy == GBWT_B200_LAYOUT_AUTO) {
+        // A dense record answers rank with one 32-byte block however long it is, so it is preferred
+        // unless it would more than double the footprint of a body that already spans several sectors.
+        uint64_t dense = 2 * ceil_div(pl.total, DENSE_BITS);
+        if (dense <= std::max<uint64_t>(4, 2 * best)) { best = dense; pl.fmt = FMT_DENSE2; }
+    }
+    if (best > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
+    pl.units = static_cast<uint32_t>(best);
+    return pl;
+}
+
+// Pass 2: write the descriptor, edges and body of one record.
+void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t body_unit, uint64_t edge_index,
+                 RecordDesc& d, uint64_t* bodies, Edge* edges) {
+    std::memset(&d, 0, sizeof(d));
+    d.fmt = pl.fmt;
+    if (pl.fmt == FMT_EMPTY) return;
+    d.body = static_cast<uint32_t>(body_unit);
+    d.total_len = static_cast<uint32_t>(pl.total);
+    d.sigma16 = static_cast<uint16_t>(std::min<uint64_t>(pl.sigma, 65535));
+    RecordReader rd(bytes, len);
+    uint64_t sigma;
+    rd.varint(sigma);
+    uint64_t node = 0;
+    if (sigma <= 2) {
+        d.flags |= DESC_INLINE_EDGES;
+        for (uint64_t i = 0; i < sigma; i++) {
+            uint64_t delta, off;
+            rd.varint(delta); rd.varint(off);
+            node += delta;
+            d.w[2 * i] = static_cast<uint32_t>(node);
+            d.w[2 * i + 1] = static_cast<uint32_t>(off);
+        }
+    } else {
+        d.w[0] = static_cast<uint32_t>(edge_index);
+        d.w[1] = static_cast<uint32_t>(sigma);
+        d.w[2] = sigma <= 256 ? div_magic(static_cast<uint32_t>(sigma)) : 0;
+        for (uint64_t i = 0; i < sigma; i++) {
+            uint64_t delta, off;
+            rd.varint(delta); rd.varint(off);
+            node += delta;
+            edges[edge_index + i] = Edge{static_cast<uint32_t>(node), static_cast<uint32_t>(off)};
+        }
+    }
+    rd.begin_runs(sigma);
+    uint8_t* body = reinterpret_cast<uint8_t*>(bodies + 2 * body_unit);
+    uint64_t value, rl;
+    switch (pl.fmt) {
+    case FMT_SINGLE:
+        break;
+    case FMT_DENSE2: {
+        uint64_t blocks = ceil_div(pl.total, DENSE_BITS);
+        d.body_len = static_cast<uint32_t>(blocks);
+        uint32_t* words = reinterpret_cast<uint32_t*>(body);
+        uint64_t pos = 0;
+        while (rd.run(value, rl)) {
+            if (value == 1) {
+                for (uint64_t i = pos; i < pos + rl; i++) {
+                    uint64_t blk = i / DENSE_BITS, bit = i % DENSE_BITS;
+                    words[blk * 8 + 1 + bit / 32] |= 1u << (bit % 32);
+                }
+            }
+            pos += rl;
+        }
+        uint32_t ones = 0;
+        for (uint64_t b = 0; b < blocks; b++) {
+            words[b * 8] = ones;
+            for (uint32_t w = 1; w <= DENSE_WORDS; w++) ones += static_cast<uint32_t>(__builtin_popcount(words[b * 8 + w]));
+        }
+        break;
+    }
+    case FMT_RUN8: {
+        const uint64_t max8 = std::max<uint64_t>(1, 256 / sigma);
+        uint64_t n = 0;
+        while (rd.run(value, rl)) {
+            while (rl > 0) {
+                uint64_t piece = std::min(rl, max8);
+                body[n++] = static_cast<uint8_t>(value + sigma * (piece - 1));
+                rl -= piece;
+            }
+        }
+        d.body_len = static_cast<uint32_t>(n);
+        break;
+    }
+    case FMT_RUN32: {
+        uint32_t* out = reinterpret_cast<uint32_t*>(body);
+        uint64_t n = 0;
+        while (rd.run(value, rl)) {
+            while (rl > 0) {
+                uint64_t piece = std::min<uint64_t>(rl, RUN32_MAX_LEN);
+                out[n++] = static_cast<uint32_t>(value) | (static_cast<uint32_t>(piece - 1) << 8);
+                rl -= piece;
+            }
+        }
+        d.body_len = static_cast<uint32_t>(n);
+        break;
+    }
+    case FMT_RUN64: {
+        uint32_t* out = reinterpret_cast<uint32_t*>(body);
+        uint64_t n = 0;
+        while (rd.run(value, rl)) {
+            out[2 * n] = static_cast<uint32_t>(value);
+            out[2 * n + 1] = static_cast<uint32_t>(rl);
+            n++;
+        }
+        d.body_len = static_cast<uint32_t>(n);
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+}  // namespace
+
+int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string& err) {
+    if (policy != GBWT_B200_LAYOUT_AUTO && policy != GBWT_B200_LAYOUT_RUNS) {
+        err = "unknown layout policy"; return GBWT_B200_E_ARGUMENT;
+    }
+    const uint64_t R = in.record_starts.size();
+    if (in.alphabet_size > (1ull << 32) || R > 0xFFFFFFFFull) {
+        err = "alphabet does not fit the 32-bit device layout"; return GBWT_B200_E_RANGE;
+    }
+    // BWT::len() is the number of record starts; GBWT ids are mapped with node - offset (src/gbwt.rs:150-152).
+    auto rec_len = [&](uint64_t i) { return (i + 1 < R ? in.record_starts[i + 1] : in.bwt_len) - in.record_starts[i]; };
+
+    std::vector<Plan> plans(R);
+    std::atomic<int> status{GBWT_B200_OK};
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
+        plans[i] = plan_record(in.bwt + in.record_starts[i], rec_len(i), policy);
+        if (plans[i].status != GBWT_B200_OK) status.store(plans[i].status);
+    }
+    if (status.load() != GBWT_B200_OK) {
+        err = status.load() == GBWT_B200_E_RANGE ? "a record does not fit the 32-bit device layout" : "BWT: malformed record";
+        return status.load();
+    }
+    std::vector<uint64_t> body_at(R + 1, 0), edge_at(R + 1, 0);
+    for (uint64_t i = 0; i < R; i++) {
+        body_at[i + 1] = body_at[i] + plans[i].units;
+        edge_at[i + 1] = edge_at[i] + (plans[i].sigma > 2 ? plans[i].sigma : 0);
+        out.format_counts[plans[i].fmt]++;
+    }
+    if (body_at[R] > 0xFFFFFFFFull || edge_at[R] > 0xFFFFFFFFull) {
+        err = "index does not fit the 32-bit device layout"; return GBWT_B200_E_RANGE;
+    }
+    out.desc.assign(R, RecordDesc{});
+    out.bodies.assign(2 * body_at[R] + 2, 0);
+    out.edges.assign(edge_at[R] + 1, Edge{0, 0});
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
+        emit_record(in.bwt + in.record_starts[i], rec_len(i), plans[i], body_at[i], edge_at[i], out.desc[i],
+                    out.bodies.data(), out.edges.data());
+    }
+
+    // Endmarker: Record::decompress of record 0 (src/bwt.rs:465-475, src/gbwt.rs:413-414).
+    out.endmarker.clear();
+    if (R > 0) {
+        if (plans[0].fmt == FMT_EMPTY) { err = "GBWT: missing endmarker record"; return GBWT_B200_E_INVALID_DATA; }
+        RecordReader rd(in.bwt + in.record_starts[0], rec_len(0));
+        uint64_t sigma;
+        rd.varint(sigma);
+        std::vector<Edge> e(sigma);
+        uint64_t node = 0;
+        for (uint64_t i = 0; i < sigma; i++) {
+            uint64_t delta, off;
+            rd.varint(delta); rd.varint(off);
+            node += delta;
+            e[i] = Edge{static_cast<uint32_t>(node), static_cast<uint32_t>(off)};
+        }
+        rd.begin_runs(sigma);
+        out.endmarker.reserve(plans[0].total);
+        uint64_t value, rl;
+        while (rd.run(value, rl)) {
+            for (uint64_t j = 0; j < rl; j++) { out.endmarker.push_back(e[value]); e[value].offset++; }
+        }
+    }
+    return GBWT_B200_OK;
+}
+
+}  // namespace gbwt_b200

@@ -1,0 +1,24 @@
+// layout_builder.h -- K0: turns the reference's BWT byte stream into the device layout of layout.h.
+// Runs once at load time on the host (parallel over records); the result is copied to HBM verbatim.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "layout.h"
+#include "sds_loader.h"
+
+namespace gbwt_b200 {
+
+struct HostLayout {
+    std::vector<RecordDesc> desc;
+    std::vector<uint64_t> bodies;  // raw 16-byte units, two words each
+    std::vector<Edge> edges;       // edge lists of records with sigma > 2
+    std::vector<Edge> endmarker;   // Record::decompress() of record 0 (src/gbwt.rs:413-414)
+    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+};
+
+// `policy` is GBWT_B200_LAYOUT_AUTO or GBWT_B200_LAYOUT_RUNS. Returns a GBWT_B200_* status.
+int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string& err);
+
+}  // namespace gbwt_b200

@@ -1,0 +1,470 @@
+// record_scan.cuh -- per-record primitives on the device layout (layout.h): descriptor fetch, edge lookup,
+// rank of a symbol at one or two positions (the core of Record::follow / bd_follow / lf, gbwt-rs
+// src/bwt.rs:480-496, 595-656) and the GBWT-level steps built from them (src/gbwt.rs:213-229, 269-384).
+//
+// Everything here is one-lane code: one thread owns one query. The functions are __host__ __device__ so
+// that tests/hostsim can run exactly this logic on the CPU against the oracle when no GPU is present;
+// the product library only ever calls them from kernels (kernels.cu).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/gbwt_b200.h"
+#include "layout.h"
+
+namespace gbwt_b200 {
+
+#if defined(__CUDA_ARCH__)
+#define GBWT_LDG(p) __ldg(p)
+#define GBWT_POPC(x) __popc(x)
+#else
+#define GBWT_LDG(p) (*(p))
+#define GBWT_POPC(x) __builtin_popcount(x)
+#endif
+
+struct Quad { uint32_t x, y, z, w; };
+
+// One 128-bit read-only load (LDG.E.128.CONSTANT on the device).
+GBWT_HD Quad load_quad(const Unit16* p) {
+    Quad q;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
+#else
+    q.x = p->x; q.y = p->y; q.z = p->z; q.w = p->w;
+#endif
+    return q;
+}
+
+// A descriptor held in eight registers.
+struct Desc {
+    Quad a, b;
+    GBWT_HD uint32_t body() const { return a.x; }
+    GBWT_HD uint32_t body_len() const { return a.y; }
+    GBWT_HD uint32_t total_len() const { return a.z; }
+    GBWT_HD uint32_t fmt() const { return (a.w >> 16) & 0xFF; }
+    GBWT_HD bool inline_edges() const { return ((a.w >> 24) & DESC_INLINE_EDGES) != 0; }
+    GBWT_HD uint32_t sigma() const { return inline_edges() ? (a.w & 0xFFFF) : b.y; }
+    GBWT_HD uint32_t edge_base() const { return b.x; }
+};
+
+GBWT_HD Desc load_desc(const IndexView& ix, uint64_t rec) {
+    const Unit16* p = reinterpret_cast<const Unit16*>(ix.desc + rec);
+    Desc d;
+    d.a = load_quad(p);
+    d.b = load_quad(p + 1);
+    return d;
+}
+
+// GBWT::node_to_record + BWT::record (src/gbwt.rs:150-152, src/bwt.rs:124-130): false = None.
+GBWT_HD bool record_of(const IndexView& ix, uint64_t node, uint64_t& rec) {
+    if (node < ix.offset) return false;  // Rust's wrapping subtraction lands beyond BWT::len()
+    rec = node - ix.offset;
+    return rec < ix.records;
+}
+
+GBWT_HD Edge edge_at(const IndexView& ix, const Desc& d, uint32_t rank) {
+    Edge e;
+    if (d.inline_edges()) {
+        e.node = rank == 0 ? d.b.x : d.b.z;
+        e.offset = rank == 0 ? d.b.y : d.b.w;
+    } else {
+        const Edge* p = ix.edges + d.edge_base() + rank;
+        e.node = GBWT_LDG(&p->node);
+        e.offset = GBWT_LDG(&p->offset);
+    }
+    return e;
+}
+
+// The symbols that bd_follow counts towards the reverse range (src/bwt.rs:646-648): v with
+// flip(successor(v)) < flip(node). The edge list is sorted, so that set is {v < lt} plus possibly `extra`.
+struct FlipSet {
+    uint32_t lt, extra;
+    GBWT_HD bool has(uint32_t v) const { return v < lt || v == extra; }
+};
+
+// Record::edge_to (src/bwt.rs:543-555). Returns false when `node` is not a successor.
+template <bool BD>
+GBWT_HD bool find_edge(const IndexView& ix, const Desc& d, uint64_t node, uint32_t& rank, uint32_t& edge_offset,
+                       FlipSet& fs) {
+    const uint32_t sigma = d.sigma();
+    if (d.inline_edges()) {
+        if (node == d.b.x) { rank = 0; edge_offset = d.b.y; }
+        else if (sigma == 2 && node == d.b.z) { rank = 1; edge_offset = d.b.w; }
+        else return false;
+    } else {
+        uint32_t low = 0, high = sigma;
+        bool found = false;
+        while (low < high) {
+            uint32_t mid = low + (high - low) / 2;
+            Edge e = edge_at(ix, d, mid);
+            if (node < e.node) high = mid;
+            else if (node == e.node) { rank = mid; edge_offset = e.offset; found = true; break; }
+            else low = mid + 1;
+        }
+        if (!found) return false;
+    }
+    if (BD) {
+        fs.lt = rank;
+        fs.extra = NO_SYMBOL;
+        if ((node & 1) != 0 && rank > 0 && edge_at(ix, d, rank - 1).node == node - 1) fs.lt = rank - 1;
+        if ((node & 1) == 0 && rank + 1 < sigma && edge_at(ix, d, rank + 1).node == node + 1) fs.extra = rank + 1;
+    }
+    return true;
+}
+
+// |[off, off + len) ∩ [0, x)| = support::intersect(..).len() of src/bwt.rs:605-607.
+GBWT_HD uint32_t covered(uint32_t x, uint32_t off, uint32_t len) {
+    uint32_t t = x - (x < off ? x : off);
+    return t < len ? t : len;
+}
+
+struct Ranks {
+    uint32_t at_start, at_end;  // occurrences of the symbol in [0, start) and [0, end)
+    uint32_t flipped;           // positions of [start, end) whose symbol is in the FlipSet (bd only)
+};
+
+// ---- FMT_DENSE2 ---------------------------------------------------------------------------------
+// Ones in [0, i) of a dense body; i <= total_len. `bit` receives the symbol at position i (0 if i == total).
+GBWT_HD uint32_t dense_rank1(const Unit16* body, uint32_t blocks, uint32_t i, uint32_t& bit) {
+    uint32_t blk = i / DENSE_BITS;
+    if (blk >= blocks) blk = blocks - 1;
+    const uint32_t r = i - blk * DENSE_BITS;  // 0..224
+    const Quad lo = load_quad(body + 2 * blk), hi = load_quad(body + 2 * blk + 1);
+    const uint32_t w[7] = {lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t count = lo.x;
+    bit = 0;
+GBWT_UNROLL
+    for (uint32_t k = 0; k < 7; k++) {
+        const uint32_t base = 32 * k;
+        uint32_t mask;
+        if (r >= base + 32) mask = 0xFFFFFFFFu;
+        else if (r > base) mask = (1u << (r - base)) - 1u;
+        else mask = 0;
+        count += GBWT_POPC(w[k] & mask);
+        if (r >= base && r < base + 32) bit = (w[k] >> (r - base)) & 1u;
+    }
+    return count;
+}
+
+// ---- run formats ------------------------------------------------------------------------------------
+template <bool BD>
+GBWT_HD void add_run(uint32_t value, uint32_t len, uint32_t symbol, const FlipSet& fs, uint32_t start, uint32_t end,
+                     uint32_t& off, Ranks& r) {
+    const uint32_t cs = covered(start, off, len), ce = covered(end, off, len);
+    if (value == symbol) { r.at_start += cs; r.at_end += ce; }
+    if (BD) { if (fs.has(value)) r.flipped += ce - cs; }
+    off += len;
+}
+
+// Scans the runs of a RUN8 / RUN32 / RUN64 body up to `end` (the reference's early exit, src/bwt.rs:610-612).
+template <bool BD>
+GBWT_HD void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+                       uint32_t end, Ranks& r) {
+    const Unit16* body = ix.bodies + d.body();
+    const uint32_t n = d.body_len();
+    const uint32_t fmt = d.fmt();
+    uint32_t off = 0;
+    if (fmt == FMT_RUN8) {
+        const uint32_t sigma = d.sigma();
+        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;  // inline edges + runs => sigma == 2
+        for (uint32_t base = 0; base < n && off < end; base += 16) {
+            const Quad q = load_quad(body + (base >> 4));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 16 ? n - base : 16;
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 16; j++) {
+                if (j < nb) {
+                    const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                    const uint32_t quot = (b * magic) >> 16;
+                    add_run<BD>(b - quot * sigma, quot + 1, symbol, fs, start, end, off, r);
+                }
+            }
+        }
+    } else if (fmt == FMT_RUN32) {
+        for (uint32_t base = 0; base < n && off < end; base += 4) {
+            const Quad q = load_quad(body + (base >> 2));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 4 ? n - base : 4;
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 4; j++) {
+                if (j < nb) add_run<BD>(words[j] & 0xFF, (words[j] >> 8) + 1, symbol, fs, start, end, off, r);
+            }
+        }
+    } else {  // FMT_RUN64
+        for (uint32_t base = 0; base < n && off < end; base += 2) {
+            const Quad q = load_quad(body + (base >> 1));
+            add_run<BD>(q.x, q.y, symbol, fs, start, end, off, r);
+            if (base + 1 < n) add_run<BD>(q.z, q.w, symbol, fs, start, end, off, r);
+        }
+    }
+}
+
+// Symbol at position i (< total_len) of a run body: the first pass of Record::lf (src/bwt.rs:483-484).
+GBWT_HD uint32_t symbol_at_runs(const IndexView& ix, const Desc& d, uint32_t i) {
+    const Unit16* body = ix.bodies + d.body();
+    const uint32_t n = d.body_len();
+    const uint32_t fmt = d.fmt();
+    uint32_t off = 0, symbol = NO_SYMBOL;
+    if (fmt == FMT_RUN8) {
+        const uint32_t sigma = d.sigma();
+        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;  // inline edges + runs => sigma == 2
+        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 16) {
+            const Quad q = load_quad(body + (base >> 4));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 16 ? n - base : 16;
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 16; j++) {
+                if (j < nb) {
+                    const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                    const uint32_t quot = (b * magic) >> 16;
+                    if (symbol == NO_SYMBOL && i - off < quot + 1) symbol = b - quot * sigma;
+                    off += quot + 1;
+                }
+            }
+        }
+    } else if (fmt == FMT_RUN32) {
+        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 4) {
+            const Quad q = load_quad(body + (base >> 2));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 4 ? n - base : 4;
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 4; j++) {
+                if (j < nb) {
+                    const uint32_t len = (words[j] >> 8) + 1;
+                    if (symbol == NO_SYMBOL && i - off < len) symbol = words[j] & 0xFF;
+                    off += len;
+                }
+            }
+        }
+    } else {
+        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 2) {
+            const Quad q = load_quad(body + (base >> 1));
+            if (i - off < q.y) symbol = q.x;
+            off += q.y;
+            if (symbol == NO_SYMBOL && base + 1 < n) {
+                if (i - off < q.w) symbol = q.z;
+                off += q.w;
+            }
+        }
+    }
+    return symbol;
+}
+
+// rank_symbol(start), rank_symbol(end) and, for BD, the flipped count, for any body format.
+// `start` <= `end`; both are clamped to the record length (ranks saturate there).
+template <bool BD>
+GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+                        uint32_t end) {
+    Ranks r;
+    r.at_start = r.at_end = r.flipped = 0;
+    const uint32_t total = d.total_len();
+    if (start > total) start = total;
+    if (end > total) end = total;
+    const uint32_t fmt = d.fmt();
+    if (fmt == FMT_SINGLE) {
+        r.at_start = start; r.at_end = end;
+        if (BD) r.flipped = fs.has(0) ? end - start : 0;
+    } else if (fmt == FMT_DENSE2) {
+        const Unit16* body = ix.bodies + d.body();
+        uint32_t bit;
+        const uint32_t ones_s = dense_rank1(body, d.body_len(), start, bit);
+        const uint32_t ones_e = dense_rank1(body, d.body_len(), end, bit);
+        r.at_start = symbol ? ones_s : start - ones_s;
+        r.at_end = symbol ? ones_e : end - ones_e;
+        if (BD) {
+            const uint32_t ones = ones_e - ones_s, zeros = (end - start) - ones;
+            r.flipped = (fs.has(0) ? zeros : 0) + (fs.has(1) ? ones : 0);
+        }
+    } else {
+        rank_runs<BD>(ix, d, symbol, fs, start, end, r);
+    }
+    return r;
+}
+
+// ---- GBWT-level steps (on the ABI value types of include/gbwt_b200.h) ---------------------------------
+
+GBWT_HD void set_none(gbwt_b200_state& s) { s.node = 0; s.start = 0; s.end = 0; }
+GBWT_HD void set_none(gbwt_b200_bdstate& s) { set_none(s.forward); set_none(s.reverse); }
+GBWT_HD void set_none(gbwt_b200_pos& p) { p.node = 0; p.offset = 0; }
+
+// GBWT::find, src/gbwt.rs:269-281. The length comes from the descriptor instead of Record::len()'s scan.
+GBWT_HD bool gbwt_find(const IndexView& ix, uint64_t node, gbwt_b200_state& out) {
+    set_none(out);
+    uint64_t rec;
+    if (node < ix.offset + 1 || !record_of(ix, node, rec)) return false;
+    const Desc d = load_desc(ix, rec);
+    if (d.fmt() == FMT_EMPTY || d.total_len() == 0) return false;
+    out.node = node; out.end = d.total_len();
+    return true;
+}
+
+// Record::follow / bd_follow on the record of `from` (src/bwt.rs:595-656) as used by GBWT::extend and
+// bd_internal (src/gbwt.rs:292-304, 370-384). `flipped` is bd_follow's second return value.
+template <bool BD>
+GBWT_HD bool gbwt_follow(const IndexView& ix, uint64_t from, uint64_t start, uint64_t end, uint64_t node,
+                         gbwt_b200_state& out, uint64_t& flipped) {
+    set_none(out);
+    flipped = 0;
+    uint64_t rec;
+    if (node < ix.offset + 1 || start >= end || !record_of(ix, from, rec)) return false;
+    const Desc d = load_desc(ix, rec);
+    if (d.fmt() == FMT_EMPTY) return false;
+    uint32_t rank = 0, edge_offset = 0;
+    FlipSet fs;
+    fs.lt = 0; fs.extra = NO_SYMBOL;
+    if (!find_edge<BD>(ix, d, node, rank, edge_offset, fs)) return false;
+    const uint32_t total = d.total_len();
+    const uint32_t s = start > total ? total : static_cast<uint32_t>(start);
+    const uint32_t e = end > total ? total : static_cast<uint32_t>(end);
+    const Ranks r = rank_pair<BD>(ix, d, rank, fs, s, e);
+    if (r.at_start >= r.at_end) return false;
+    out.node = node;
+    out.start = static_cast<uint64_t>(edge_offset) + r.at_start;
+    out.end = static_cast<uint64_t>(edge_offset) + r.at_end;
+    flipped = r.flipped;
+    return true;
+}
+
+// GBWT::extend, src/gbwt.rs:292-304.
+GBWT_HD bool gbwt_extend(const IndexView& ix, const gbwt_b200_state& state, uint64_t node, gbwt_b200_state& out) {
+    uint64_t flipped;
+    return gbwt_follow<false>(ix, state.node, state.start, state.end, node, out, flipped);
+}
+
+// GBWT::bd_find, src/gbwt.rs:311-324.
+GBWT_HD bool gbwt_bd_find(const IndexView& ix, uint64_t node, gbwt_b200_bdstate& out) {
+    set_none(out);
+    gbwt_b200_state st;
+    if (!gbwt_find(ix, node, st)) return false;
+    out.forward = st;
+    out.reverse.node = node ^ 1; out.reverse.start = st.start; out.reverse.end = st.end;
+    return true;
+}
+
+// GBWT::extend_forward + bd_internal, src/gbwt.rs:339-347, 370-384. `out` may alias `state`.
+GBWT_HD bool gbwt_extend_forward(const IndexView& ix, const gbwt_b200_bdstate& state, uint64_t node,
+                                 gbwt_b200_bdstate& out) {
+    const gbwt_b200_state reverse = state.reverse;
+    gbwt_b200_state fwd;
+    uint64_t flipped;
+    if (!gbwt_follow<true>(ix, state.forward.node, state.forward.start, state.forward.end, node, fwd, flipped)) {
+        set_none(out);
+        return false;
+    }
+    out.forward = fwd;
+    out.reverse.node = reverse.node;
+    out.reverse.start = reverse.start + flipped;
+    out.reverse.end = out.reverse.start + (fwd.end - fwd.start);
+    return true;
+}
+
+// GBWT::extend_backward, src/gbwt.rs:362-367: flip, extend forward with the flipped node, flip back.
+GBWT_HD bool gbwt_extend_backward(const IndexView& ix, const gbwt_b200_bdstate& state, uint64_t node,
+                                  gbwt_b200_bdstate& out) {
+    gbwt_b200_bdstate flipped_state;
+    flipped_state.forward = state.reverse;
+    flipped_state.reverse = state.forward;
+    gbwt_b200_bdstate res;
+    if (!gbwt_extend_forward(ix, flipped_state, node ^ 1, res)) { set_none(out); return false; }
+    out.forward = res.reverse;
+    out.reverse = res.forward;
+    return true;
+}
+
+// GBWT::forward + Record::lf, src/gbwt.rs:222-229, src/bwt.rs:480-496. False = None.
+GBWT_HD bool gbwt_forward(const IndexView& ix, const gbwt_b200_pos& pos, gbwt_b200_pos& out) {
+    const uint64_t node = pos.node, offset = pos.offset;
+    set_none(out);
+    uint64_t rec;
+    if (node < ix.offset + 1 || !record_of(ix, node, rec)) return false;
+    const Desc d = load_desc(ix, rec);
+    const uint32_t fmt = d.fmt();
+    if (fmt == FMT_EMPTY || offset >= d.total_len()) return false;
+    const uint32_t i = static_cast<uint32_t>(offset);
+    uint32_t symbol, rank_i;
+    if (fmt == FMT_SINGLE) {
+        symbol = 0; rank_i = i;
+    } else if (fmt == FMT_DENSE2) {
+        const uint32_t ones = dense_rank1(ix.bodies + d.body(), d.body_len(), i, symbol);
+        rank_i = symbol ? ones : i - ones;
+    } else {
+        symbol = symbol_at_runs(ix, d, i);
+        if (symbol == NO_SYMBOL) return false;
+        FlipSet fs;
+        fs.lt = 0; fs.extra = NO_SYMBOL;
+        Ranks r;
+        r.at_start = r.at_end = r.flipped = 0;
+        rank_runs<false>(ix, d, symbol, fs, i, i, r);
+        rank_i = r.at_start;
+    }
+    const Edge e = edge_at(ix, d, symbol);
+    if (e.node == 0) return false;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+    out.node = e.node; out.offset = static_cast<uint64_t>(e.offset) + rank_i;
+    return true;
+}
+
+// GBWT::start, src/gbwt.rs:213-219.
+GBWT_HD bool gbwt_start(const IndexView& ix, uint64_t id, gbwt_b200_pos& out) {
+    set_none(out);
+    if (id >= ix.endmarker_len) return false;
+    const uint32_t node = GBWT_LDG(&ix.endmarker[id].node);
+    if (node == 0) return false;
+    out.node = node; out.offset = GBWT_LDG(&ix.endmarker[id].offset);
+    return true;
+}
+
+// ---- whole queries ---------------------------------------------------------------------------------
+
+// find(pattern[0]) followed by extend over pattern[1..k): the loop of src/bin/benchmark.rs:161-167.
+GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uint64_t k, gbwt_b200_state& out) {
+    set_none(out);
+    if (k == 0) return;
+    gbwt_b200_state st;
+    if (!gbwt_find(ix, GBWT_LDG(pattern), st)) return;
+    for (uint64_t i = 1; i < k; i++) {
+        gbwt_b200_state next;
+        if (!gbwt_extend(ix, st, GBWT_LDG(pattern + i), next)) return;
+        st = next;
+    }
+    out = st;
+}
+
+// bd_find(path[first]), extend_forward over path(first, end), extend_backward over path[start, first) in
+// descending order: the reference's test driver, src/gbwt/tests.rs:352-361.
+GBWT_HD void query_bd_search(const IndexView& ix, const uint64_t* path, uint64_t len, uint64_t first, uint64_t start,
+                             uint64_t end, gbwt_b200_bdstate& out) {
+    set_none(out);
+    if (!(start <= first && first < end && end <= len)) return;
+    gbwt_b200_bdstate st;
+    if (!gbwt_bd_find(ix, GBWT_LDG(path + first), st)) return;
+    for (uint64_t i = first + 1; i < end; i++) {
+        gbwt_b200_bdstate next;
+        if (!gbwt_extend_forward(ix, st, GBWT_LDG(path + i), next)) return;
+        st = next;
+    }
+    for (uint64_t i = first; i > start; i--) {
+        gbwt_b200_bdstate next;
+        if (!gbwt_extend_backward(ix, st, GBWT_LDG(path + i - 1), next)) return;
+        st = next;
+    }
+    out = st;
+}
+
+// GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568): writes at most `cap` nodes and returns the
+// full length, or UINT64_MAX when sequence() is None (id >= sequences()).
+GBWT_HD uint64_t walk_sequence(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap) {
+    if (id >= ix.sequences) return ~0ull;
+    uint64_t n = 0;
+    gbwt_b200_pos pos;
+    bool some = gbwt_start(ix, id, pos);
+    while (some) {
+        if (n < cap) out[n] = pos.node;
+        n++;
+        gbwt_b200_pos next;
+        some = gbwt_forward(ix, pos, next);
+        pos = next;
+    }
+    return n;
+}
+
+}  // namespace gbwt_b200

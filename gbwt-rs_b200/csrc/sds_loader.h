@@ -1,0 +1,24 @@
+// sds_loader.h -- host-side reader for Simple-SDS GBWT / GBZ images (boundary input, not accelerated).
+// Format: SURVEY.md App. A; field order from gbwt-rs src/gbwt.rs:402-438, src/bwt.rs:176-185,
+// src/gbz.rs:678-690, src/headers.rs:57-62, 190-234.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gbwt_b200 {
+
+struct ParsedGBWT {
+    uint64_t sequences = 0, size = 0, offset = 0, alphabet_size = 0, flags = 0;
+    std::vector<uint64_t> record_starts;  // start of every record in `bwt` (what the Elias-Fano index selects)
+    const uint8_t* bwt = nullptr;         // points into the caller's image
+    uint64_t bwt_len = 0;
+};
+
+constexpr uint64_t GBWT_FLAG_BIDIRECTIONAL = 1, GBWT_FLAG_METADATA = 2, GBWT_FLAG_SIMPLE_SDS = 4;
+
+// Returns a GBWT_B200_* status; on failure `err` holds the reference's error text where it has one.
+int parse_gbwt_image(const uint8_t* bytes, size_t len, ParsedGBWT& out, std::string& err);
+
+}  // namespace gbwt_b200
