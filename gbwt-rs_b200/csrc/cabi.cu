@@ -1,0 +1,671 @@
+// cabi.cu -- the extern "C" boundary of include/gbwt_b200.h: index construction (parse + K0 layout + upload),
+// kernel launches, and the chunked host<->device pipeline of the host entry points.
+//
+// There is no CPU implementation of any query behind this boundary: every entry point launches the kernels
+// of kernels.cuh on the index's device, and index construction fails with GBWT_B200_E_NO_DEVICE without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/gbwt_b200.h"
+#include "kernels.cuh"
+#include "layout_builder.h"
+#include "sds_loader.h"
+
+using namespace gbwt_b200;
+
+struct gbwt_b200_index {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t sequences = 0, size = 0, offset = 0, alphabet_size = 0, flags = 0;
+    IndexView view{};
+    void* d_desc = nullptr;
+    void* d_bodies = nullptr;
+    void* d_edges = nullptr;
+    void* d_endmarker = nullptr;
+    uint64_t bytes[4] = {0, 0, 0, 0};
+    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return GBWT_B200_E_CUDA;
+}
+
+#define CUDA_TRY(expr)                                        \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);   \
+    } while (0)
+
+// Selects the index's device for the calling thread and restores the previous one.
+struct DeviceScope {
+    int previous = -1;
+    bool ok = true;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&previous) != cudaSuccess) previous = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceScope() { if (previous >= 0) cudaSetDevice(previous); }
+};
+
+// Persistent grid: at most one resident wave (8 CTAs of 256 threads per SM), fewer when the batch is small.
+unsigned grid_for(const gbwt_b200_index* ix, size_t n, int block = BLOCK_THREADS) {
+    size_t blocks = (n + block - 1) / block;
+    size_t wave = static_cast<size_t>(ix->sm_count) * (2048 / block);
+    return static_cast<unsigned>(std::max<size_t>(1, std::min(blocks, wave)));
+}
+
+int launch_done(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return GBWT_B200_OK;
+}
+
+// ---- kernel launchers (device pointers) ------------------------------------------------------------
+
+int launch_find(const gbwt_b200_index* ix, const uint64_t* nodes, size_t n, gbwt_b200_state* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_find<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, n, out);
+    return launch_done("k_find");
+}
+int launch_extend(const gbwt_b200_index* ix, const gbwt_b200_state* st, const uint64_t* nodes, size_t n,
+                  gbwt_b200_state* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, st, nodes, n, out);
+    return launch_done("k_extend");
+}
+int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
+                       cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_find_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, patterns, n, k, out);
+    return launch_done("k_find_extend");
+}
+int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, uint64_t base,
+                              size_t n, gbwt_b200_state* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_find_extend_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, n, out);
+    return launch_done("k_find_extend_ragged");
+}
+int launch_bd_find(const gbwt_b200_index* ix, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_bd_find<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, n, out);
+    return launch_done("k_bd_find");
+}
+int launch_bd_extend(const gbwt_b200_index* ix, const gbwt_b200_bdstate* st, const uint64_t* nodes, size_t n, int backward,
+                     gbwt_b200_bdstate* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_bd_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, st, nodes, n, backward, out);
+    return launch_done("k_bd_extend");
+}
+int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, uint64_t base,
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, size_t n, gbwt_b200_bdstate* out,
+                     cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_bd_search<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, n, out);
+    return launch_done("k_bd_search");
+}
+int launch_start(const gbwt_b200_index* ix, const uint64_t* ids, size_t n, gbwt_b200_pos* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_start<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, ids, n, out);
+    return launch_done("k_start");
+}
+int launch_forward(const gbwt_b200_index* ix, const gbwt_b200_pos* pos, size_t n, gbwt_b200_pos* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_forward<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, pos, n, out);
+    return launch_done("k_forward");
+}
+int launch_backward(const gbwt_b200_index* ix, const gbwt_b200_pos* pos, size_t n, gbwt_b200_pos* out, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_backward<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, pos, n, out);
+    return launch_done("k_backward");
+}
+int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
+                   uint64_t* nodes, uint64_t* lengths, cudaStream_t s) {
+    if (m == 0) return GBWT_B200_OK;
+    const int block = 32;  // one warp per CTA spreads the chains over the SMs
+    k_extract<<<static_cast<unsigned>((m + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths);
+    return launch_done("k_extract");
+}
+
+// ---- host <-> device pipeline ----------------------------------------------------------------------
+
+// A fixed-size-per-item array on the host side of a batched call.
+struct HostArray {
+    const void* in;     // copied to the device before the kernel (may be null)
+    void* out;          // copied back after the kernel (may be null)
+    size_t item_bytes;
+};
+
+// Processes items [0, n) in chunks on two alternating streams: H2D of the chunk's inputs, the kernel(s), D2H
+// of its outputs. With page-locked host memory the copies of one chunk overlap the kernel of the other.
+// `launch(begin, count, device_ptrs, stream)` receives one device pointer per HostArray.
+template <class Launch>
+int run_chunked(const gbwt_b200_index* ix, size_t n, const std::vector<HostArray>& arrays, size_t chunk_items, Launch launch) {
+    if (n == 0) return GBWT_B200_OK;
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    const int n_streams = n > chunk_items ? 2 : 1;
+    for (int i = 0; i < n_streams; i++) CUDA_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    int rc = GBWT_B200_OK;
+    std::vector<void*> dptr(arrays.size(), nullptr);
+    size_t chunk_index = 0;
+    for (size_t begin = 0; begin < n && rc == GBWT_B200_OK; begin += chunk_items, chunk_index++) {
+        const size_t count = std::min(chunk_items, n - begin);
+        cudaStream_t s = streams[chunk_index % n_streams];
+        for (size_t a = 0; a < arrays.size() && rc == GBWT_B200_OK; a++) {
+            cudaError_t e = cudaMallocAsync(&dptr[a], std::max<size_t>(16, count * arrays[a].item_bytes), s);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync"); break; }
+            if (arrays[a].in != nullptr) {
+                e = cudaMemcpyAsync(dptr[a], static_cast<const char*>(arrays[a].in) + begin * arrays[a].item_bytes,
+                                    count * arrays[a].item_bytes, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+            }
+        }
+        if (rc == GBWT_B200_OK) rc = launch(begin, count, dptr, s);
+        for (size_t a = 0; a < arrays.size(); a++) {
+            if (dptr[a] == nullptr) continue;
+            if (rc == GBWT_B200_OK && arrays[a].out != nullptr) {
+                cudaError_t e = cudaMemcpyAsync(static_cast<char*>(arrays[a].out) + begin * arrays[a].item_bytes, dptr[a],
+                                                count * arrays[a].item_bytes, cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+            }
+            cudaFreeAsync(dptr[a], s);
+            dptr[a] = nullptr;
+        }
+    }
+    for (int i = 0; i < n_streams; i++) {
+        cudaError_t e = cudaStreamSynchronize(streams[i]);
+        if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+        cudaStreamDestroy(streams[i]);
+    }
+    return rc;
+}
+
+// Chunk size: about 64 MiB of the widest array per chunk, at least 16 Ki items.
+size_t chunk_for(size_t widest_item_bytes) {
+    const size_t target = size_t(64) << 20;
+    return std::max<size_t>(size_t(1) << 14, target / std::max<size_t>(1, widest_item_bytes));
+}
+
+// Ragged batches: items [q0, q1) such that offsets[q1] - offsets[q0] <= node_budget (at least one item).
+size_t ragged_chunk_end(const uint64_t* offsets, size_t n, size_t q0, size_t item_budget, uint64_t node_budget) {
+    size_t q1 = std::min(n, q0 + item_budget);
+    if (q1 > q0 + 1 && offsets[q1] - offsets[q0] > node_budget) {
+        size_t lo = q0 + 1, hi = q1;  // largest q1 within the node budget, but never fewer than one item
+        while (lo < hi) {
+            size_t mid = lo + (hi - lo + 1) / 2;
+            if (offsets[mid] - offsets[q0] <= node_budget) lo = mid; else hi = mid - 1;
+        }
+        q1 = lo;
+    }
+    return q1;
+}
+
+bool offsets_valid(const uint64_t* offsets, size_t n) {
+    for (size_t i = 0; i < n; i++) if (offsets[i + 1] < offsets[i]) return false;
+    return true;
+}
+
+// Uploads and launches a ragged (nodes, offsets) batch with optional per-item u64 side arrays and one output
+// array of `out_bytes` per item. `launch(d_nodes, d_offsets, base, d_side[], count, d_out, stream)`.
+template <class Launch>
+int run_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, size_t n,
+               const std::vector<const uint64_t*>& side, void* out, size_t out_bytes, Launch launch) {
+    if (n == 0) return GBWT_B200_OK;
+    if (!offsets_valid(offsets, n)) return fail(GBWT_B200_E_ARGUMENT, "offsets must be non-decreasing");
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    cudaStream_t streams[2];
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+    int rc = GBWT_B200_OK;
+    const size_t item_budget = size_t(1) << 20;
+    const uint64_t node_budget = uint64_t(8) << 20;
+    size_t chunk_index = 0;
+    for (size_t q0 = 0; q0 < n && rc == GBWT_B200_OK; chunk_index++) {
+        const size_t q1 = ragged_chunk_end(offsets, n, q0, item_budget, node_budget);
+        const size_t count = q1 - q0;
+        const uint64_t base = offsets[q0], n_nodes = offsets[q1] - base;
+        cudaStream_t s = streams[chunk_index % 2];
+        uint64_t *d_nodes = nullptr, *d_offsets = nullptr;
+        void* d_out = nullptr;
+        std::vector<uint64_t*> d_side(side.size(), nullptr);
+        auto alloc = [&](void** p, size_t bytes) {
+            cudaError_t e = cudaMallocAsync(p, std::max<size_t>(16, bytes), s);
+            if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaMallocAsync");
+        };
+        auto upload = [&](void* d, const void* h, size_t bytes) {
+            if (rc != GBWT_B200_OK || bytes == 0) return;
+            cudaError_t e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+        };
+        alloc(reinterpret_cast<void**>(&d_nodes), n_nodes * 8);
+        alloc(reinterpret_cast<void**>(&d_offsets), (count + 1) * 8);
+        alloc(&d_out, count * out_bytes);
+        for (size_t a = 0; a < side.size(); a++) alloc(reinterpret_cast<void**>(&d_side[a]), count * 8);
+        upload(d_nodes, nodes + base, n_nodes * 8);
+        upload(d_offsets, offsets + q0, (count + 1) * 8);
+        for (size_t a = 0; a < side.size(); a++) upload(d_side[a], side[a] + q0, count * 8);
+        if (rc == GBWT_B200_OK) rc = launch(d_nodes, d_offsets, base, d_side, count, d_out, s);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(static_cast<char*>(out) + q0 * out_bytes, d_out, count * out_bytes,
+                                            cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        if (d_nodes) cudaFreeAsync(d_nodes, s);
+        if (d_offsets) cudaFreeAsync(d_offsets, s);
+        if (d_out) cudaFreeAsync(d_out, s);
+        for (uint64_t* p : d_side) if (p) cudaFreeAsync(p, s);
+        q0 = q1;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaError_t e = cudaStreamSynchronize(streams[i]);
+        if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+        cudaStreamDestroy(streams[i]);
+    }
+    return rc;
+}
+
+int check_index(const gbwt_b200_index* ix) {
+    if (ix == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null index handle");
+    return GBWT_B200_OK;
+}
+
+int check_bidirectional(const gbwt_b200_index* ix) {
+    // assert!(self.is_bidirectional(), ...) at src/gbwt.rs:237, 312, 340
+    if (!(ix->flags & GBWT_FLAG_BIDIRECTIONAL)) return fail(GBWT_B200_E_NOT_BIDIRECTIONAL, "Bidirectional search requires a bidirectional GBWT");
+    return GBWT_B200_OK;
+}
+
+int upload(void** d, const void* h, size_t bytes, uint64_t& accounted) {
+    *d = nullptr;
+    accounted = bytes;
+    CUDA_TRY(cudaMalloc(d, std::max<size_t>(bytes, 256)));
+    if (bytes > 0) CUDA_TRY(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return GBWT_B200_OK;
+}
+
+int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_index** out) {
+    if (out == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output handle");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(GBWT_B200_E_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return fail(GBWT_B200_E_ARGUMENT, "invalid device ordinal");
+    HostLayout layout;
+    std::string err;
+    int rc = build_layout(parsed, policy, layout, err);
+    if (rc != GBWT_B200_OK) return fail(rc, err);
+
+    DeviceScope scope(device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    gbwt_b200_index* ix = new gbwt_b200_index();
+    ix->device = device;
+    cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ix->sequences = parsed.sequences; ix->size = parsed.size; ix->offset = parsed.offset;
+    ix->alphabet_size = parsed.alphabet_size; ix->flags = parsed.flags;
+    std::memcpy(ix->format_counts, layout.format_counts, sizeof(layout.format_counts));
+    rc = upload(&ix->d_desc, layout.desc.data(), layout.desc.size() * sizeof(RecordDesc), ix->bytes[0]);
+    if (rc == GBWT_B200_OK) rc = upload(&ix->d_bodies, layout.bodies.data(), layout.bodies.size() * 8, ix->bytes[1]);
+    if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
+    if (rc == GBWT_B200_OK) rc = upload(&ix->d_endmarker, layout.endmarker.data(), layout.endmarker.size() * sizeof(Edge), ix->bytes[3]);
+    if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+    // Keep the stream-ordered pool's memory between calls: the host entry points allocate their staging
+    // buffers from it on every call.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    IndexView& v = ix->view;
+    v.desc = static_cast<const RecordDesc*>(ix->d_desc);
+    v.bodies = static_cast<const Unit16*>(ix->d_bodies);
+    v.edges = static_cast<const Edge*>(ix->d_edges);
+    v.endmarker = static_cast<const Edge*>(ix->d_endmarker);
+    v.records = layout.desc.size();
+    v.offset = parsed.offset;
+    v.alphabet_size = parsed.alphabet_size;
+    v.sequences = parsed.sequences;
+    v.endmarker_len = layout.endmarker.size();
+    v.bidirectional = (parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
+    *out = ix;
+    return GBWT_B200_OK;
+}
+
+}  // namespace
+
+// ---- construction ------------------------------------------------------------------------------------
+
+extern "C" {
+
+int gbwt_b200_index_from_bytes(const void* bytes, size_t len, int device, int layout_policy, gbwt_b200_index** out) {
+    ParsedGBWT parsed;
+    std::string err;
+    int rc = parse_gbwt_image(static_cast<const uint8_t*>(bytes), len, parsed, err);
+    if (rc != GBWT_B200_OK) return fail(rc, err);
+    return create_index(parsed, device, layout_policy, out);
+}
+
+int gbwt_b200_index_load_file(const char* path, int device, int layout_policy, gbwt_b200_index** out) {
+    if (path == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null path");
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return fail(GBWT_B200_E_IO, std::string("cannot open ") + path);
+    std::streamsize n = f.tellg();
+    f.seekg(0);
+    std::vector<uint8_t> buf(static_cast<size_t>(n));
+    if (n > 0 && !f.read(reinterpret_cast<char*>(buf.data()), n)) return fail(GBWT_B200_E_IO, std::string("cannot read ") + path);
+    return gbwt_b200_index_from_bytes(buf.data(), buf.size(), device, layout_policy, out);
+}
+
+int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, uint64_t offset, uint64_t alphabet_size, uint64_t flags,
+                               const uint8_t* bwt_bytes, uint64_t bwt_len, const uint64_t* record_starts, uint64_t records,
+                               int device, int layout_policy, gbwt_b200_index** out) {
+    if ((bwt_len > 0 && bwt_bytes == nullptr) || (records > 0 && record_starts == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null input");
+    ParsedGBWT parsed;
+    parsed.sequences = sequences; parsed.size = size; parsed.offset = offset; parsed.alphabet_size = alphabet_size;
+    parsed.flags = flags | GBWT_FLAG_SIMPLE_SDS;
+    parsed.bwt = bwt_bytes; parsed.bwt_len = bwt_len;
+    parsed.record_starts.assign(record_starts, record_starts + records);
+    for (uint64_t i = 0; i < records; i++) {
+        if (record_starts[i] >= bwt_len || (i > 0 && record_starts[i] <= record_starts[i - 1]))
+            return fail(GBWT_B200_E_INVALID_DATA, "BWT: invalid index");
+    }
+    return create_index(parsed, device, layout_policy, out);
+}
+
+void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
+    if (ix == nullptr) return;
+    {
+        DeviceScope scope(ix->device);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker);
+    }
+    delete ix;
+}
+
+const char* gbwt_b200_last_error(void) { return g_last_error.c_str(); }
+
+// ---- statistics (src/gbwt.rs:105-175) ----------------------------------------------------------------
+
+uint64_t gbwt_b200_len(const gbwt_b200_index* ix) { return ix ? ix->size : 0; }
+uint64_t gbwt_b200_sequences(const gbwt_b200_index* ix) { return ix ? ix->sequences : 0; }
+uint64_t gbwt_b200_alphabet_size(const gbwt_b200_index* ix) { return ix ? ix->alphabet_size : 0; }
+uint64_t gbwt_b200_alphabet_offset(const gbwt_b200_index* ix) { return ix ? ix->offset : 0; }
+uint64_t gbwt_b200_effective_size(const gbwt_b200_index* ix) { return ix ? ix->alphabet_size - ix->offset : 0; }
+uint64_t gbwt_b200_first_node(const gbwt_b200_index* ix) { return ix ? ix->offset + 1 : 0; }
+int gbwt_b200_has_node(const gbwt_b200_index* ix, uint64_t id) { return ix && id > ix->offset && id < ix->alphabet_size; }
+int gbwt_b200_is_bidirectional(const gbwt_b200_index* ix) { return ix && (ix->flags & GBWT_FLAG_BIDIRECTIONAL) != 0; }
+int gbwt_b200_device(const gbwt_b200_index* ix) { return ix ? ix->device : -1; }
+
+uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* ix, uint64_t breakdown[10]) {
+    if (ix == nullptr) return 0;
+    if (breakdown != nullptr) {
+        for (int i = 0; i < 4; i++) breakdown[i] = ix->bytes[i];
+        for (int i = 0; i < FMT_COUNT; i++) breakdown[4 + i] = ix->format_counts[i];
+    }
+    return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3];
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------------------
+
+#define DEVICE_ENTRY_PROLOGUE(ix)                                              \
+    if (int _rc = check_index(ix)) return _rc;                                 \
+    DeviceScope _scope((ix)->device);                                          \
+    if (!_scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+
+int gbwt_b200_find_device(const gbwt_b200_index* ix, const uint64_t* d_nodes, size_t n, gbwt_b200_state* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_find(ix, d_nodes, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_extend_device(const gbwt_b200_index* ix, const gbwt_b200_state* d_states, const uint64_t* d_nodes, size_t n,
+                            gbwt_b200_state* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_extend(ix, d_states, d_nodes, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_find_extend_device(const gbwt_b200_index* ix, const uint64_t* d_patterns, size_t n, size_t k,
+                                 gbwt_b200_state* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_find_extend(ix, d_patterns, n, k, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_find_extend_ragged_device(const gbwt_b200_index* ix, const uint64_t* d_nodes, const uint64_t* d_offsets, size_t n,
+                                        gbwt_b200_state* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_find_extend_ragged(ix, d_nodes, d_offsets, 0, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_bd_find_device(const gbwt_b200_index* ix, const uint64_t* d_nodes, size_t n, gbwt_b200_bdstate* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_bidirectional(ix)) return rc;
+    return launch_bd_find(ix, d_nodes, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_bd_extend_device(const gbwt_b200_index* ix, const gbwt_b200_bdstate* d_states, const uint64_t* d_nodes, size_t n,
+                               int backward, gbwt_b200_bdstate* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_bidirectional(ix)) return rc;
+    return launch_bd_extend(ix, d_states, d_nodes, n, backward, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_bd_search_device(const gbwt_b200_index* ix, const uint64_t* d_nodes, const uint64_t* d_offsets,
+                               const uint64_t* d_first, const uint64_t* d_start, const uint64_t* d_end, size_t n,
+                               gbwt_b200_bdstate* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_bidirectional(ix)) return rc;
+    return launch_bd_search(ix, d_nodes, d_offsets, 0, d_first, d_start, d_end, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_forward_device(const gbwt_b200_index* ix, const gbwt_b200_pos* d_positions, size_t n, gbwt_b200_pos* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_forward(ix, d_positions, n, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_sequence_lengths_device(const gbwt_b200_index* ix, const uint64_t* d_seq_ids, size_t m, uint64_t* d_lengths, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_extract(ix, d_seq_ids, m, nullptr, 0, nullptr, d_lengths, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_extract_device(const gbwt_b200_index* ix, const uint64_t* d_seq_ids, size_t m, const uint64_t* d_out_offsets,
+                             uint64_t* d_nodes, uint64_t* d_lengths, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (d_nodes == nullptr || d_out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    return launch_extract(ix, d_seq_ids, m, d_out_offsets, 0, d_nodes, d_lengths, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host entry points -------------------------------------------------------------------------------
+
+int gbwt_b200_find(const gbwt_b200_index* ix, const uint64_t* nodes, size_t n, gbwt_b200_state* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && (nodes == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{nodes, nullptr, 8}, {nullptr, out, sizeof(gbwt_b200_state)}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_state)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_find(ix, static_cast<uint64_t*>(d[0]), count, static_cast<gbwt_b200_state*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_extend(const gbwt_b200_index* ix, const gbwt_b200_state* states, const uint64_t* nodes, size_t n, gbwt_b200_state* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && (states == nullptr || nodes == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{states, out, sizeof(gbwt_b200_state)}, {nodes, nullptr, 8}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_state)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        gbwt_b200_state* st = static_cast<gbwt_b200_state*>(d[0]);
+        return launch_extend(ix, st, static_cast<uint64_t*>(d[1]), count, st, s);
+    });
+}
+
+int gbwt_b200_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && ((k > 0 && patterns == nullptr) || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{k > 0 ? patterns : nullptr, nullptr, 8 * k}, {nullptr, out, sizeof(gbwt_b200_state)}};
+    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(8 * k, sizeof(gbwt_b200_state))),
+                       [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_find_extend(ix, static_cast<uint64_t*>(d[0]), count, k, static_cast<gbwt_b200_state*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, size_t n, gbwt_b200_state* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && (offsets == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    return run_ragged(ix, nodes, offsets, n, {}, out, sizeof(gbwt_b200_state),
+                      [&](uint64_t* d_nodes, uint64_t* d_offsets, uint64_t base, std::vector<uint64_t*>&, size_t count, void* d_out, cudaStream_t s) {
+        return launch_find_extend_ragged(ix, d_nodes, d_offsets, base, count, static_cast<gbwt_b200_state*>(d_out), s);
+    });
+}
+
+int gbwt_b200_bd_find(const gbwt_b200_index* ix, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_bidirectional(ix)) return rc;
+    if (n > 0 && (nodes == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{nodes, nullptr, 8}, {nullptr, out, sizeof(gbwt_b200_bdstate)}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_bdstate)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_bd_find(ix, static_cast<uint64_t*>(d[0]), count, static_cast<gbwt_b200_bdstate*>(d[1]), s);
+    });
+}
+
+static int bd_extend_host(const gbwt_b200_index* ix, const gbwt_b200_bdstate* states, const uint64_t* nodes, size_t n, int backward,
+                          gbwt_b200_bdstate* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_bidirectional(ix)) return rc;
+    if (n > 0 && (states == nullptr || nodes == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{states, out, sizeof(gbwt_b200_bdstate)}, {nodes, nullptr, 8}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_bdstate)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        gbwt_b200_bdstate* st = static_cast<gbwt_b200_bdstate*>(d[0]);
+        return launch_bd_extend(ix, st, static_cast<uint64_t*>(d[1]), count, backward, st, s);
+    });
+}
+
+int gbwt_b200_extend_forward(const gbwt_b200_index* ix, const gbwt_b200_bdstate* states, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out) {
+    return bd_extend_host(ix, states, nodes, n, 0, out);
+}
+int gbwt_b200_extend_backward(const gbwt_b200_index* ix, const gbwt_b200_bdstate* states, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out) {
+    return bd_extend_host(ix, states, nodes, n, 1, out);
+}
+
+int gbwt_b200_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, const uint64_t* first,
+                        const uint64_t* start, const uint64_t* end, size_t n, gbwt_b200_bdstate* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_bidirectional(ix)) return rc;
+    if (n > 0 && (offsets == nullptr || first == nullptr || start == nullptr || end == nullptr || out == nullptr))
+        return fail(GBWT_B200_E_ARGUMENT, "null array");
+    return run_ragged(ix, nodes, offsets, n, {first, start, end}, out, sizeof(gbwt_b200_bdstate),
+                      [&](uint64_t* d_nodes, uint64_t* d_offsets, uint64_t base, std::vector<uint64_t*>& side, size_t count, void* d_out, cudaStream_t s) {
+        return launch_bd_search(ix, d_nodes, d_offsets, base, side[0], side[1], side[2], count, static_cast<gbwt_b200_bdstate*>(d_out), s);
+    });
+}
+
+int gbwt_b200_start(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t n, gbwt_b200_pos* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && (seq_ids == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{seq_ids, nullptr, 8}, {nullptr, out, sizeof(gbwt_b200_pos)}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_pos)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_start(ix, static_cast<uint64_t*>(d[0]), count, static_cast<gbwt_b200_pos*>(d[1]), s);
+    });
+}
+
+static int step_host(const gbwt_b200_index* ix, const gbwt_b200_pos* positions, size_t n, gbwt_b200_pos* out, bool backward) {
+    if (int rc = check_index(ix)) return rc;
+    if (backward) {
+        // assert!(self.is_bidirectional(), ...) at src/gbwt.rs:237
+        if (!(ix->flags & GBWT_FLAG_BIDIRECTIONAL)) return fail(GBWT_B200_E_NOT_BIDIRECTIONAL, "Following sequences backward requires a bidirectional GBWT");
+    }
+    if (n > 0 && (positions == nullptr || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{positions, out, sizeof(gbwt_b200_pos)}};
+    return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_pos)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        gbwt_b200_pos* p = static_cast<gbwt_b200_pos*>(d[0]);
+        return backward ? launch_backward(ix, p, count, p, s) : launch_forward(ix, p, count, p, s);
+    });
+}
+
+int gbwt_b200_forward(const gbwt_b200_index* ix, const gbwt_b200_pos* positions, size_t n, gbwt_b200_pos* out) {
+    return step_host(ix, positions, n, out, false);
+}
+int gbwt_b200_backward(const gbwt_b200_index* ix, const gbwt_b200_pos* positions, size_t n, gbwt_b200_pos* out) {
+    return step_host(ix, positions, n, out, true);
+}
+
+int gbwt_b200_sequence_lengths(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t m, uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (m > 0 && (seq_ids == nullptr || lengths == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{seq_ids, nullptr, 8}, {nullptr, lengths, 8}};
+    // all chains of the batch in one launch: a path walk is latency-bound, so concurrency is everything
+    return run_chunked(ix, m, arrays, std::max<size_t>(m, 1), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_extract(ix, static_cast<uint64_t*>(d[0]), count, nullptr, 0, nullptr, static_cast<uint64_t*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_extract(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t m, const uint64_t* out_offsets, uint64_t* nodes,
+                      uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (m == 0) return GBWT_B200_OK;
+    if (seq_ids == nullptr || out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    if (!offsets_valid(out_offsets, m)) return fail(GBWT_B200_E_ARGUMENT, "out_offsets must be non-decreasing");
+    if (out_offsets[m] > out_offsets[0] && nodes == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    size_t free_bytes = 0, total_bytes = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_bytes, &total_bytes));
+    const uint64_t node_budget = std::max<uint64_t>(uint64_t(1) << 20, (free_bytes / 8) * 6 / 10);
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = GBWT_B200_OK;
+    for (size_t i0 = 0; i0 < m && rc == GBWT_B200_OK;) {
+        const size_t i1 = ragged_chunk_end(out_offsets, m, i0, m, node_budget);
+        const size_t count = i1 - i0;
+        const uint64_t base = out_offsets[i0], cap = out_offsets[i1] - base;
+        uint64_t *d_ids = nullptr, *d_offsets = nullptr, *d_nodes = nullptr, *d_lengths = nullptr;
+        auto alloc = [&](uint64_t** p, size_t words) {
+            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(16, words * 8), s);
+            if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaMallocAsync");
+        };
+        alloc(&d_ids, count); alloc(&d_offsets, count + 1); alloc(&d_nodes, cap); alloc(&d_lengths, count);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(d_ids, seq_ids + i0, count * 8, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, out_offsets + i0, (count + 1) * 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+        }
+        if (rc == GBWT_B200_OK) rc = launch_extract(ix, d_ids, count, d_offsets, base, d_nodes, d_lengths, s);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaSuccess;
+            if (cap > 0) e = cudaMemcpyAsync(nodes + base, d_nodes, cap * 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && lengths != nullptr) e = cudaMemcpyAsync(lengths + i0, d_lengths, count * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        if (d_ids) cudaFreeAsync(d_ids, s);
+        if (d_offsets) cudaFreeAsync(d_offsets, s);
+        if (d_nodes) cudaFreeAsync(d_nodes, s);
+        if (d_lengths) cudaFreeAsync(d_lengths, s);
+        i0 = i1;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+// ---- utilities ---------------------------------------------------------------------------------------
+
+void* gbwt_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void gbwt_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+uint64_t gbwt_b200_kernel_launches(void) { return g_launches.load(); }
+const char* gbwt_b200_version(void) { return "gbwt-rs_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

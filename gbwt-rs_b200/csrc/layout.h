@@ -15,9 +15,12 @@
 
 #if defined(__CUDACC__)
 #define GBWT_HD __host__ __device__ __forceinline__
-#define GBWT_UNROLL _Pragma("unroll")
 #else
 #define GBWT_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define GBWT_UNROLL _Pragma("unroll")
+#else
 #define GBWT_UNROLL
 #endif
 

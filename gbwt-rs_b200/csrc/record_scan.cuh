@@ -413,6 +413,144 @@ GBWT_HD bool gbwt_start(const IndexView& ix, uint64_t id, gbwt_b200_pos& out) {
     return true;
 }
 
+// ---- backward navigation (src/gbwt.rs:236-250, src/bwt.rs:502-584) ------------------------------------
+
+// Number of occurrences of `symbol` in the whole record.
+GBWT_HD uint32_t count_symbol(const IndexView& ix, const Desc& d, uint32_t symbol) {
+    FlipSet fs;
+    fs.lt = 0; fs.extra = NO_SYMBOL;
+    const uint32_t total = d.total_len();
+    return rank_pair<false>(ix, d, symbol, fs, total, total).at_end;
+}
+
+// Position of the k-th (0-based) occurrence of `symbol`; false if there are not that many.
+GBWT_HD bool select_symbol(const IndexView& ix, const Desc& d, uint32_t symbol, uint32_t k, uint32_t& pos) {
+    const uint32_t fmt = d.fmt();
+    const uint32_t total = d.total_len();
+    if (fmt == FMT_SINGLE) { pos = k; return k < total; }
+    const Unit16* body = ix.bodies + d.body();
+    const uint32_t n = d.body_len();
+    if (fmt == FMT_DENSE2) {
+        // last block whose prefix count of `symbol` is <= k
+        uint32_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            const uint32_t ones = load_quad(body + 2 * mid).x;
+            const uint32_t before = symbol ? ones : mid * DENSE_BITS - ones;
+            if (before <= k) lo = mid; else hi = mid;
+        }
+        const Quad a = load_quad(body + 2 * lo), b = load_quad(body + 2 * lo + 1);
+        const uint32_t w[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t need = k - (symbol ? a.x : lo * DENSE_BITS - a.x);
+        for (uint32_t j = 0; j < 7; j++) {
+            uint32_t bits = symbol ? w[j] : ~w[j];
+            const uint32_t c = GBWT_POPC(bits);
+            if (need < c) {
+                for (uint32_t t = 0; t < need; t++) bits &= bits - 1;
+                uint32_t bit = 0;
+                while (!((bits >> bit) & 1u)) bit++;
+                pos = lo * DENSE_BITS + 32 * j + bit;
+                return pos < total;
+            }
+            need -= c;
+        }
+        return false;
+    }
+    uint32_t off = 0, seen = 0;
+    if (fmt == FMT_RUN8) {
+        const uint32_t sigma = d.sigma();
+        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;
+        for (uint32_t base = 0; base < n; base += 16) {
+            const Quad q = load_quad(body + (base >> 4));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 16 ? n - base : 16;
+            for (uint32_t j = 0; j < nb; j++) {
+                const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                const uint32_t quot = (b * magic) >> 16;
+                if (b - quot * sigma == symbol) {
+                    if (k - seen < quot + 1) { pos = off + (k - seen); return true; }
+                    seen += quot + 1;
+                }
+                off += quot + 1;
+            }
+        }
+    } else if (fmt == FMT_RUN32) {
+        for (uint32_t base = 0; base < n; base += 4) {
+            const Quad q = load_quad(body + (base >> 2));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t nb = n - base < 4 ? n - base : 4;
+            for (uint32_t j = 0; j < nb; j++) {
+                const uint32_t len = (words[j] >> 8) + 1;
+                if ((words[j] & 0xFF) == symbol) {
+                    if (k - seen < len) { pos = off + (k - seen); return true; }
+                    seen += len;
+                }
+                off += len;
+            }
+        }
+    } else {
+        for (uint32_t base = 0; base < n; base++) {
+            const Quad q = load_quad(body + (base >> 1));
+            const uint32_t value = (base & 1) ? q.z : q.x, len = (base & 1) ? q.w : q.y;
+            if (value == symbol) {
+                if (k - seen < len) { pos = off + (k - seen); return true; }
+                seen += len;
+            }
+            off += len;
+        }
+    }
+    return false;
+}
+
+// Record::predecessor_at (src/bwt.rs:502-540) on the record of flip(node): walks the successors in the order
+// of the flipped nodes (adjacent edges to the two orientations of one node swap places, :521-525).
+GBWT_HD bool predecessor_at(const IndexView& ix, const Desc& d, uint32_t i, uint64_t& predecessor) {
+    const uint32_t sigma = d.sigma();
+    uint32_t offset = 0;
+    for (uint32_t j = 0; j < sigma;) {
+        const bool pair = j + 1 < sigma && edge_at(ix, d, j).node / 2 == edge_at(ix, d, j + 1).node / 2;
+        const uint32_t order[2] = {pair ? j + 1 : j, j};
+        const uint32_t steps = pair ? 2 : 1;
+        for (uint32_t t = 0; t < steps; t++) {
+            const uint32_t v = order[t];
+            offset += count_symbol(ix, d, v);
+            if (offset > i) {
+                const uint32_t node = edge_at(ix, d, v).node;
+                if (node == 0) return false;
+                predecessor = node ^ 1;
+                return true;
+            }
+        }
+        j += steps;
+    }
+    return false;
+}
+
+// GBWT::backward, src/gbwt.rs:236-250 (the caller has checked is_bidirectional()).
+GBWT_HD bool gbwt_backward(const IndexView& ix, const gbwt_b200_pos& pos, gbwt_b200_pos& out) {
+    const uint64_t node = pos.node, offset = pos.offset;
+    set_none(out);
+    uint64_t rec;
+    if (node <= ix.offset + 1 || !record_of(ix, node ^ 1, rec)) return false;
+    const Desc rev = load_desc(ix, rec);
+    if (rev.fmt() == FMT_EMPTY || offset >= rev.total_len()) return false;
+    uint64_t predecessor;
+    if (!predecessor_at(ix, rev, static_cast<uint32_t>(offset), predecessor)) return false;
+    if (!record_of(ix, predecessor, rec)) return false;
+    const Desc pred = load_desc(ix, rec);
+    if (pred.fmt() == FMT_EMPTY) return false;
+    // Record::offset_to, src/bwt.rs:558-584
+    uint32_t rank = 0, edge_offset = 0;
+    FlipSet fs;
+    if (!find_edge<false>(ix, pred, node, rank, edge_offset, fs)) return false;
+    if (edge_offset > offset) return false;
+    const uint64_t k = offset - edge_offset;
+    uint32_t where;
+    if (k > 0xFFFFFFFFull || !select_symbol(ix, pred, rank, static_cast<uint32_t>(k), where)) return false;
+    out.node = predecessor; out.offset = where;
+    return true;
+}
+
 // ---- whole queries ---------------------------------------------------------------------------------
 
 // find(pattern[0]) followed by extend over pattern[1..k): the loop of src/bin/benchmark.rs:161-167.

@@ -1038,3 +1038,90 @@ void orc_extract_batch(const orc_gbwt* g, const uint64_t* ids, uint64_t m, const
     for (int64_t i = 0; i < (int64_t)m; i++)
         (void)orc_sequence(g, ids[i], nodes + out_offsets[i], out_offsets[i + 1] - out_offsets[i]);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Algorithmic-byte accounting: measurement helper, not a query path          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Bytes of record `rid` the reference's loops consume: the header (decompress_edges decodes all of it,
+ * src/bwt.rs:378-395) plus the run bytes read until the loop exits. mode 0 = Record::len (whole record,
+ * src/bwt.rs:449-455); mode 1 = follow with early exit at offset >= end (src/bwt.rs:610-612), only when the
+ * edge exists; mode 2 = lf, through the run containing i (src/bwt.rs:484). */
+static uint64_t consumed_bytes(const orc_gbwt* g, uint64_t rid, int mode, uint64_t end_or_i, uint64_t node) {
+    orc_record rec;
+    if (!bwt_record(&g->bwt, rid, &rec)) {
+        uint64_t s, l;
+        if (rid >= bwt_len(&g->bwt)) return 0;
+        bwt_record_bytes(&g->bwt, rid, &s, &l);
+        return l - s; /* an empty record is still fetched and its sigma decoded */
+    }
+    uint64_t s, l;
+    bwt_record_bytes(&g->bwt, rid, &s, &l);
+    uint64_t header = (l - s) - rec.bwt_len;
+    uint64_t used = header;
+    if (mode == 1 && record_edge_to(&rec, node) < 0) { record_drop(&rec); return used; }
+    size_t pos = 0; orc_run run; uint64_t offset = 0;
+    while (orc_rle_next(rec.bwt, rec.bwt_len, &pos, rec.sigma, &run)) {
+        offset += run.len;
+        if (mode == 1 && offset >= end_or_i) break;
+        if (mode == 2 && offset > end_or_i) break;
+    }
+    used += pos;
+    record_drop(&rec);
+    return used;
+}
+
+/* Sum over queries of: per step 16 (two record boundaries) + 8 (pattern symbol) + consumed record bytes,
+ * plus 24 bytes of result per query. */
+uint64_t orc_find_extend_bytes(const orc_gbwt* g, const uint64_t* patterns, uint64_t n, uint64_t k, int threads) {
+    int t = pick_threads(threads); (void)t;
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(t) reduction(+:total)
+    for (int64_t q = 0; q < (int64_t)n; q++) {
+        const uint64_t* pat = patterns + (uint64_t)q * k;
+        uint64_t bytes = 24;
+        orc_state st;
+        uint64_t rid;
+        if (k > 0) {
+            bytes += 8;
+            if (pat[0] >= orc_first_node(g) && node_to_record(g, pat[0], &rid) && rid < bwt_len(&g->bwt))
+                bytes += 16 + consumed_bytes(g, rid, 0, 0, 0);
+            int some = orc_find(g, pat[0], &st);
+            for (uint64_t i = 1; i < k && some; i++) {
+                bytes += 8;
+                if (pat[i] >= orc_first_node(g) && node_to_record(g, st.node, &rid) && rid < bwt_len(&g->bwt))
+                    bytes += 16 + consumed_bytes(g, rid, 1, st.end, pat[i]);
+                orc_state nx;
+                some = orc_extend(g, &st, pat[i], &nx);
+                st = nx;
+            }
+        }
+        total += bytes;
+    }
+    return total;
+}
+
+/* Sum over sequences of: per forward() call 16 + consumed record bytes (lf), plus 8 bytes per extracted node. */
+uint64_t orc_extract_bytes(const orc_gbwt* g, const uint64_t* ids, uint64_t m, int threads) {
+    int t = pick_threads(threads); (void)t;
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(t) reduction(+:total)
+    for (int64_t j = 0; j < (int64_t)m; j++) {
+        uint64_t bytes = 0;
+        if (ids[j] < g->sequences) {
+            orc_pos pos;
+            int some = orc_start(g, ids[j], &pos);
+            while (some) {
+                bytes += 8;
+                uint64_t rid;
+                if (pos.node >= orc_first_node(g) && node_to_record(g, pos.node, &rid) && rid < bwt_len(&g->bwt))
+                    bytes += 16 + consumed_bytes(g, rid, 2, pos.offset, 0);
+                orc_pos next;
+                some = orc_forward(g, pos, &next);
+                pos = next;
+            }
+        }
+        total += bytes;
+    }
+    return total;
+}

@@ -128,6 +128,10 @@ void orc_extract_batch(const orc_gbwt* g, const uint64_t* ids, uint64_t m, const
                        uint64_t* nodes, int threads);
 int orc_max_threads(void);
 
+/* ---- algorithmic-byte accounting of SURVEY.md 8(d) (measurement helper for bench.py) ------------ */
+uint64_t orc_find_extend_bytes(const orc_gbwt* g, const uint64_t* patterns, uint64_t n, uint64_t k, int threads);
+uint64_t orc_extract_bytes(const orc_gbwt* g, const uint64_t* ids, uint64_t m, int threads);
+
 #ifdef __cplusplus
 }
 #endif

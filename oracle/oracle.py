@@ -115,6 +115,10 @@ def lib(native: bool = False) -> C.CDLL:
         L.orc_forward_batch.argtypes = [p, p, u64, p, C.c_int]
         L.orc_sequence_lengths.argtypes = [p, p, u64, p, C.c_int]
         L.orc_extract_batch.argtypes = [p, p, u64, p, p, C.c_int]
+        L.orc_find_extend_bytes.restype = u64
+        L.orc_find_extend_bytes.argtypes = [p, p, u64, u64, C.c_int]
+        L.orc_extract_bytes.restype = u64
+        L.orc_extract_bytes.argtypes = [p, p, u64, C.c_int]
         L.orc_bytecode_write.restype = C.c_size_t
         L.orc_bytecode_write.argtypes = [p, u64]
         L.orc_bytecode_next.argtypes = [p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(u64)]
@@ -426,6 +430,16 @@ class GBWT:
         out = np.zeros(len(ids), dtype=np.uint64)
         self._L.orc_sequence_lengths(self._h, _ptr(ids), len(ids), _ptr(out), threads)
         return out
+
+    def find_extend_bytes(self, patterns: np.ndarray, threads: int = 0) -> int:
+        """Algorithmic bytes of SURVEY.md 8(d) for these patterns (reference's compressed records)."""
+        patterns = _u64(patterns)
+        n, k = patterns.shape
+        return int(self._L.orc_find_extend_bytes(self._h, _ptr(patterns), n, k, threads))
+
+    def extract_bytes(self, ids, threads: int = 0) -> int:
+        ids = _u64(ids)
+        return int(self._L.orc_extract_bytes(self._h, _ptr(ids), len(ids), threads))
 
     def extract_batch(self, ids, threads: int = 0):
         ids = _u64(ids)

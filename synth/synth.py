@@ -113,3 +113,30 @@ def patterns(sites: int, haplotypes: int, seed: int, n: int, k: int = 32, seed_q
     assert out.dtype == np.uint64 and out.flags.c_contiguous and out.size == n * k
     lib().synth_patterns(sites, haplotypes, seed, seed_q, q0, n, k, out.ctypes.data_as(C.c_void_p), threads)
     return out
+
+
+# ---- device-side pattern generator (benchmark input only) --------------------------------------------
+
+_CUDA_LIB = None
+
+
+def build_cuda(force: bool = False) -> str:
+    path = os.path.join(_HERE, "libgbwt_synth_cuda.so")
+    src = os.path.join(_HERE, "gbwt_synth_cuda.cu")
+    if force or not os.path.exists(path) or os.path.getmtime(src) > os.path.getmtime(path):
+        subprocess.run(["make", "-C", _HERE, "-B", "libgbwt_synth_cuda.so"], check=True, capture_output=True)
+    return path
+
+
+def patterns_device(sites: int, haplotypes: int, seed: int, n: int, d_out: int, k: int = 32, seed_q: int = 7,
+                    q0: int = 0, stream: int = 0) -> None:
+    """Writes patterns q0 .. q0+n (row-major, k u64 each) to the device address `d_out`."""
+    global _CUDA_LIB
+    if _CUDA_LIB is None:
+        L = C.CDLL(build_cuda())
+        u64 = C.c_uint64
+        L.synth_patterns_device.argtypes = [u64, u64, u64, u64, u64, u64, u64, C.c_void_p, C.c_void_p]
+        _CUDA_LIB = L
+    rc = _CUDA_LIB.synth_patterns_device(sites, haplotypes, seed, seed_q, q0, n, k, d_out, stream)
+    if rc != 0:
+        raise RuntimeError(f"synth_patterns_device failed with CUDA error {rc}")

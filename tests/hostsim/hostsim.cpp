@@ -84,6 +84,11 @@ void hs_start(const HostSim* h, const uint64_t* ids, size_t n, gbwt_b200_pos* ou
 void hs_forward(const HostSim* h, const gbwt_b200_pos* in, size_t n, gbwt_b200_pos* out) {
     for (size_t i = 0; i < n; i++) { gbwt_b200_pos p = in[i]; gbwt_forward(h->view, p, out[i]); }
 }
+int hs_backward(const HostSim* h, const gbwt_b200_pos* in, size_t n, gbwt_b200_pos* out) {
+    if (!h->view.bidirectional) return GBWT_B200_E_NOT_BIDIRECTIONAL;
+    for (size_t i = 0; i < n; i++) { gbwt_b200_pos p = in[i]; gbwt_backward(h->view, p, out[i]); }
+    return 0;
+}
 void hs_sequence_lengths(const HostSim* h, const uint64_t* ids, size_t m, uint64_t* lengths) {
     for (size_t i = 0; i < m; i++) lengths[i] = walk_sequence(h->view, ids[i], nullptr, 0);
 }

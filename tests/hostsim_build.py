@@ -52,6 +52,7 @@ def lib():
         L.hs_bd_search.argtypes = [p, p, p, p, p, p, C.c_size_t, p]
         L.hs_start.argtypes = [p, p, C.c_size_t, p]
         L.hs_forward.argtypes = [p, p, C.c_size_t, p]
+        L.hs_backward.argtypes = [p, p, C.c_size_t, p]
         L.hs_sequence_lengths.argtypes = [p, p, C.c_size_t, p]
         L.hs_extract.argtypes = [p, p, C.c_size_t, p, p, p]
         _LIB = L
@@ -141,6 +142,12 @@ class HostSim:
     def forward(self, positions):
         positions = np.ascontiguousarray(positions, POS); out = np.zeros(len(positions), POS)
         self._L.hs_forward(self._h, _p(positions), len(positions), _p(out)); return out
+
+    def backward(self, positions):
+        positions = np.ascontiguousarray(positions, POS); out = np.zeros(len(positions), POS)
+        if self._L.hs_backward(self._h, _p(positions), len(positions), _p(out)) != 0:
+            raise AssertionError("Following sequences backward requires a bidirectional GBWT")
+        return out
 
     def sequence_lengths(self, ids):
         ids = _u64(ids); out = np.zeros(len(ids), np.uint64)

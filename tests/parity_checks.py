@@ -147,6 +147,12 @@ def check_navigation(engine, g):
     pos += [(2**33, 0), (5, 2**40)]
     pos = np.array(pos, dtype=orc.POS_DTYPE)
     assert states_equal(engine.forward(pos), g.forward_batch(pos))
+    if g.is_bidirectional():
+        # src/gbwt/tests.rs:191-214: backward() at every position (and past-the-end offsets)
+        want = np.zeros(len(pos), dtype=orc.POS_DTYPE)
+        for j, (node, off) in enumerate(pos):
+            want[j] = g.backward((int(node), int(off))) or (0, 0)
+        assert states_equal(engine.backward(pos), want)
     lengths = engine.sequence_lengths(ids)
     assert np.array_equal(lengths, g.sequence_lengths(ids))
     offsets, nodes, got = engine.extract(ids)

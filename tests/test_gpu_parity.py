@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA kernels, called through the C ABI (ctypes -> libgbwt_b200.so), against the CPU
+oracle on the same inputs, bit-exact. Mirrors the reference's own tests (src/bwt/tests.rs, src/gbwt/tests.rs)
+via tests/parity_checks.py and adds the synthetic configs of BASELINE.json."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import gbwt_builder as gb
+import golden_vectors as gv
+import parity_checks as pc
+from oracle import oracle as orc
+from synth import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = ["example.gbwt", "with-empty.gbwt", "translation.gbwt", "example.gbz", "translation.gbz",
+            "example-v1.gbz", "translation-v1.gbz"]
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import gbwt_rs_b200
+    return gbwt_rs_b200
+
+
+def image_of(b, bidirectional=True):
+    flags = 4 | (1 if bidirectional else 0)
+    return synth.gbwt_image(b["sequences"], b["size"], b["offset"], b["alphabet_size"], flags, b["starts"], b["data"])
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fixtures(b200, name, layout):
+    raw = open(os.path.join(GOLDEN, name), "rb").read()
+    g = orc.GBWT.load(raw)
+    e = b200.GBWT.from_bytes(raw, layout=layout)
+    s = gv.STATS.get(name)
+    if s:
+        assert (e.len(), e.sequences(), e.alphabet_size(), e.alphabet_offset()) == \
+               (s["len"], s["sequences"], s["alphabet_size"], s["alphabet_offset"])
+        assert e.effective_size() == s["alphabet_size"] - s["alphabet_offset"] and e.first_node() == s["alphabet_offset"] + 1
+        assert e.is_bidirectional() and not e.has_node(e.alphabet_offset()) and e.has_node(e.first_node())
+    pc.check_everything(e, g)
+
+
+def test_config1_example_gbz(b200):
+    # BASELINE.json configs[0]: find() of every length-4 subpath of every stored path + full path extraction
+    path = os.path.join(GOLDEN, "example.gbz")
+    e, g = b200.GBWT.load(path), orc.GBWT.load(path)
+    seqs = [list(e.sequence(i)) for i in range(e.sequences())]
+    assert seqs[:12:2] == gv.true_paths(False) and seqs[7] == gv.SEQ7
+    pats = np.array(pc.subpath_patterns(seqs, 4), dtype=np.uint64)
+    out = e.find_extend(pats)
+    assert len(pats) == 20 and int((out["end"] - out["start"]).sum()) == 32
+    assert pc.states_equal(out, g.find_extend_batch(pats))
+    assert e.sequence(e.sequences()) is None
+
+
+def test_config2_translation_bidirectional(b200):
+    # BASELINE.json configs[1]: bd_find + extend_forward/backward over all (first, start, end) of all paths
+    path = os.path.join(GOLDEN, "translation.gbz")
+    e, g = b200.GBWT.load(path), orc.GBWT.load(path)
+    assert pc.check_bd(e, g) == 504
+
+
+def test_scalar_reference_api(b200):
+    # the doc-test of src/gbwt.rs:55-83 through the scalar mirror (a batch of one per call)
+    e = b200.GBWT.load(os.path.join(GOLDEN, "example.gbwt"))
+    st = e.find(24)
+    st = e.extend(st, 28)
+    st = e.extend(st, 30)
+    assert st == b200.SearchState(30, range(0, 2)) and st.len() == 2
+    bd = e.bd_find(28)
+    bd = e.extend_backward(bd, 24)
+    bd = e.extend_forward(bd, 30)
+    assert bd.forward.node == 30 and bd.reverse.node == 25 and bd.len() == 2
+    assert bd.from_() == (12, False) and bd.to() == (15, False)
+    assert e.find(0) is None and e.find(36) is None and e.extend(st, 22) is None
+    pos, last = e.start(4), None
+    while pos is not None:
+        last, pos = pos, e.forward(pos)
+    assert e.backward(last).node == 30
+    assert e.start(12) is None and e.forward(b200.Pos(0, 0)) is None
+
+
+def test_unidirectional_index_rejects_bd(b200):
+    paths = [[3, 5, 7, 9]] * 700 + [[3, 6, 7, 9]] * 300 + [[3, 5, 8]] * 5 + [[4, 5, 7]]
+    img = image_of(gb.build_bwt([list(p) for p in paths]), bidirectional=False)
+    for layout in ("auto", "runs"):
+        e, g = b200.GBWT.from_bytes(img, layout=layout), orc.GBWT.load(img)
+        assert not e.is_bidirectional()
+        pc.check_find_all_nodes(e, g)
+        pc.check_find_extend_subpaths(e, g)
+        pc.check_find_extend_random(e, g)
+        pc.check_navigation(e, g)
+        for call in (lambda: e.bd_find(3), lambda: e.bd_find(np.array([3], dtype=np.uint64)),
+                     lambda: e.backward(b200.Pos(5, 0)),
+                     lambda: e.extend_forward(np.zeros(1, b200.BDSTATE_DTYPE), np.array([3], dtype=np.uint64))):
+            with pytest.raises(AssertionError):
+                call()
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_graphs(b200, seed, layout):
+    from test_hostsim_layout import random_paths
+    rng = random.Random(seed)
+    paths = random_paths(rng, n_nodes=rng.choice([2, 3, 6, 12]), n_paths=rng.choice([3, 10, 40]), max_len=rng.choice([3, 8, 20]))
+    if not any(paths):
+        paths.append([2, 4])
+    img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths)))
+    pc.check_everything(b200.GBWT.from_bytes(img, layout=layout), orc.GBWT.load(img))
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_paper_and_bidirectional_examples(b200, layout):
+    from test_hostsim_layout import records_image
+    for edges, runs, bidir in [(gv.PAPER_EDGES, gv.PAPER_RUNS, False), (gv.BIDIR_EDGES, gv.BIDIR_RUNS, True)]:
+        img, _ = records_image(edges, runs, sequences=3 if not bidir else 6, size=17, offset=0 if not bidir else 1,
+                               bidirectional=bidir)
+        pc.check_everything(b200.GBWT.from_bytes(img, layout=layout), orc.GBWT.load(img))
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+@pytest.mark.parametrize("sigma,bits", [(2, (1, 3)), (2, (9, 12)), (3, (1, 4, 10)), (7, (2, 8)), (64, (1, 5)), (200, (1, 3, 9)),
+                                        (254, (1, 2)), (255, (1, 9)), (256, (1, 4)), (300, (1, 12)), (1000, (1, 3))])
+def test_wide_records(b200, sigma, bits, layout):
+    from test_hostsim_layout import records_image, wide_record_index
+    rng = random.Random(sigma * 31 + len(bits))
+    edges, runs, total = wide_record_index(sigma, rng, bits)
+    img, _ = records_image(edges, runs, sequences=total, size=3 * total, offset=0)
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, layout=layout)
+    st, nx = [], []
+    cuts = sorted(set([0, 1, 2, total // 3, total // 2, total - 1, total, total + 5] + [rng.randrange(total + 1) for _ in range(12)]))
+    for a in cuts:
+        for b_ in cuts:
+            if a < b_:
+                for node in range(0, sigma + 4):
+                    st.append((1, a, b_)); nx.append(node)
+    st = np.array(st, dtype=orc.STATE_DTYPE); nx = np.array(nx, dtype=np.uint64)
+    assert pc.states_equal(e.extend(st, nx), g.extend_batch(st, nx))
+    pos = np.array([(1, i) for i in sorted(set(cuts + [rng.randrange(total) for _ in range(300)]))], dtype=orc.POS_DTYPE)
+    assert pc.states_equal(e.forward(pos), g.forward_batch(pos))
+    pc.check_find_all_nodes(e, g)
+    ids = np.array(sorted(set(rng.randrange(total) for _ in range(50))), dtype=np.uint64)
+    assert np.array_equal(e.sequence_lengths(ids), g.sequence_lengths(ids))
+
+
+def from_parts_of(b200, g, layout="auto"):
+    return b200.GBWT.from_parts(g.sequences(), g.len(), g.alphabet_offset(), g.alphabet_size(), g.flags(),
+                                g.bwt_data(), g.record_starts(), layout=layout)
+
+
+def test_from_parts_matches_from_bytes(b200):
+    raw = open(os.path.join(GOLDEN, "example.gbwt"), "rb").read()
+    g = orc.GBWT.load(raw)
+    pc.check_everything(from_parts_of(b200, g), g)
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_config3_shape_small(b200, layout):
+    # bubble chain like configs[2] (fewer sites so the oracle finishes in seconds): every query matches
+    S, H, seed = 4000, 64, 42
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)
+    pats = synth.patterns(S, H, seed, n=300_000, k=32)   # crosses the host pipeline's chunk boundary
+    out = e.find_extend(pats)
+    assert pc.states_equal(out, g.find_extend_batch(pats))
+    assert np.all(out["end"] > out["start"]) and np.array_equal(out["node"], pats[:, -1])
+    pc.check_find_extend_random(e, g, n=20000, k=8, seed=5)
+    # ragged view of the same patterns with varying lengths
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 33, size=50_000)
+    offsets = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    nodes = np.concatenate([pats[i, :lens[i]] for i in range(len(lens))]) if offsets[-1] else np.zeros(0, np.uint64)
+    assert pc.states_equal(e.find_extend_ragged(nodes, offsets), g.find_extend_ragged(nodes, offsets))
+    # bidirectional searches sampled from the haplotypes
+    first = rng.integers(0, 32, size=20_000).astype(np.uint64)
+    start = (first * rng.random(20_000)).astype(np.uint64)
+    end = (first + 1 + ((32 - first - 1) * rng.random(20_000)).astype(np.uint64)).astype(np.uint64)
+    offs = (np.arange(20_001, dtype=np.uint64) * 32)
+    flat = pats[:20_000].reshape(-1)
+    got = e.bd_search(flat, offs, first, start, end)
+    assert pc.states_equal(got, g.bd_search_batch(flat, offs, first, start, end))
+    assert np.all(got["forward"]["end"] > got["forward"]["start"])
+    # extraction of every haplotype, both strands
+    ids = np.arange(2 * H, dtype=np.uint64)
+    offsets, nodes, lengths = e.extract(ids)
+    assert np.all(lengths == 2 * S + 1)
+    for i in range(2 * H):
+        assert np.array_equal(nodes[int(offsets[i]):int(offsets[i + 1])], synth.sequence(S, H, seed, i))
+
+
+def test_config4_shape_small(b200):
+    # 1024 haplotypes like configs[3]/[4]: long anchor records (dense under "auto", ~512 runs under "runs")
+    S, H, seed = 600, 1024, 42
+    img = synth.bubble_chain(S, H, seed)
+    g = orc.GBWT.load(img.array)
+    pats = synth.patterns(S, H, seed, n=100_000, k=32)
+    want = g.find_extend_batch(pats)
+    for layout in ("auto", "runs"):
+        e = b200.GBWT.from_bytes(img.array, layout=layout)
+        assert pc.states_equal(e.find_extend(pats), want)
+        stats = e.device_bytes()
+        assert (stats["records_dense"] > 0) == (layout == "auto")
+        ids = np.arange(0, 2 * H, 37, dtype=np.uint64)
+        offsets, nodes, lengths = e.extract(ids)
+        for j, i in enumerate(ids):
+            assert np.array_equal(nodes[int(offsets[j]):int(offsets[j + 1])], synth.sequence(S, H, seed, int(i)))
+
+
+def test_full_size_config3_properties(b200):
+    # BASELINE.json configs[2] at full size (100k nodes x 64 haplotypes, 10M patterns): size-independent
+    # properties + exact comparison with the oracle on a sample.
+    S, H, seed = 33333, 64, 42
+    img = synth.bubble_chain(S, H, seed)
+    e = b200.GBWT.from_bytes(img.array)
+    n = 10_000_000
+    pats = synth.patterns(S, H, seed, n=n, k=32)
+    out = e.find_extend(pats)
+    assert np.all(out["end"] > out["start"])                 # every sampled pattern occurs at least once
+    assert np.array_equal(out["node"], pats[:, -1])          # SearchState.node is the last pattern node
+    occ = (out["end"] - out["start"]).astype(np.int64)
+    assert occ.max() <= H and 1.0 <= occ.mean() < 1.01
+    g = orc.GBWT.load(img.array)
+    idx = np.random.default_rng(0).choice(n, size=200_000, replace=False)
+    assert pc.states_equal(out[idx], g.find_extend_batch(pats[idx]))
+    # idempotence: the same batch again gives the same bytes; a permuted batch gives the permuted result
+    perm = np.random.default_rng(1).permutation(1_000_000)
+    assert pc.states_equal(e.find_extend(pats[:1_000_000][perm]), out[:1_000_000][perm])
+
+
+def test_device_pointer_entry_points(b200):
+    import torch
+    S, H, seed = 2000, 64, 42
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    pats = synth.patterns(S, H, seed, n=50_000, k=32)
+    d_pats = torch.from_numpy(pats.view(np.int64)).cuda()
+    d_out = torch.zeros((len(pats), 3), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    before = b200.kernel_launches()
+    e.find_extend_device(d_pats.data_ptr(), len(pats), 32, d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert b200.kernel_launches() == before + 1
+    got = d_out.cpu().numpy().view(np.uint64).reshape(-1, 3)
+    want = g.find_extend_batch(pats)
+    assert np.array_equal(got, want.view(np.uint64).reshape(-1, 3))
+    ids = torch.arange(2 * H, dtype=torch.int64, device="cuda")
+    lens = torch.zeros(2 * H, dtype=torch.int64, device="cuda")
+    e.sequence_lengths_device(ids.data_ptr(), 2 * H, lens.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert torch.all(lens == 2 * S + 1)
+    offs = torch.arange(2 * H + 1, dtype=torch.int64, device="cuda") * (2 * S + 1)
+    nodes = torch.zeros(2 * H * (2 * S + 1), dtype=torch.int64, device="cuda")
+    e.extract_device(ids.data_ptr(), 2 * H, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
+    torch.cuda.synchronize()
+    host = nodes.cpu().numpy().view(np.uint64).reshape(2 * H, 2 * S + 1)
+    for i in range(0, 2 * H, 9):
+        assert np.array_equal(host[i], synth.sequence(S, H, seed, i))
+
+
+def test_pinned_host_buffers_and_threads(b200):
+    import ctypes
+    import threading
+    S, H, seed = 2000, 64, 42
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    n = 400_000
+    lib = b200.library()
+    p_in, p_out = lib.gbwt_b200_host_alloc(n * 32 * 8), lib.gbwt_b200_host_alloc(n * 24)
+    assert p_in and p_out
+    pats = np.ctypeslib.as_array((ctypes.c_uint64 * (n * 32)).from_address(p_in)).reshape(n, 32)
+    synth.patterns(S, H, seed, n=n, k=32, out=pats)
+    out = np.ctypeslib.as_array((ctypes.c_uint64 * (n * 3)).from_address(p_out)).reshape(n, 3)
+    assert lib.gbwt_b200_find_extend(e._h, p_in, n, 32, p_out) == 0
+    want = g.find_extend_batch(pats).view(np.uint64).reshape(-1, 3)
+    assert np.array_equal(out, want)
+    # the handle is usable from several host threads at once (the reference type is Sync)
+    results = [None] * 4
+    def work(t):
+        results[t] = e.find_extend(pats[t * 50_000:(t + 1) * 50_000])
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    for t in range(4):
+        assert np.array_equal(results[t].view(np.uint64).reshape(-1, 3), want[t * 50_000:(t + 1) * 50_000])
+    del pats, out
+    lib.gbwt_b200_host_free(p_in); lib.gbwt_b200_host_free(p_out)
+
+
+def test_load_errors_match_reference(b200):
+    data = bytearray(open(os.path.join(GOLDEN, "example.gbwt"), "rb").read())
+    for mutate in (lambda d: d.__setitem__(0, d[0] ^ 0xFF), lambda d: d.__setitem__(4, 4),
+                   lambda d: d.__setitem__(40, d[40] & ~4 & 0xFF), lambda d: d.__setitem__(40, d[40] & ~2 & 0xFF)):
+        bad = bytearray(data)
+        mutate(bad)
+        with pytest.raises(IOError):
+            b200.GBWT.from_bytes(bytes(bad))
+    with pytest.raises(IOError):
+        b200.GBWT.from_bytes(bytes(data[:200]))
+    with pytest.raises(IOError):
+        b200.GBWT.load("/nonexistent/file.gbwt")
+    empty = b200.GBWT.from_bytes(synth.gbwt_image(0, 0, 0, 0, 4, [], b""))
+    assert empty.find(np.arange(4, dtype=np.uint64))["end"].sum() == 0 and empty.start(0) is None
