@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -92,12 +93,71 @@ int launch_extend(const gbwt_b200_index* ix, const gbwt_b200_state* st, const ui
     k_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, st, nodes, n, out);
     return launch_done("k_extend");
 }
+// Development knobs (tuning experiments only; the defaults are the product configuration):
+//   GBWT_B200_FIND_VARIANT  bit 0 = rounds loop, bit 1 = chunked pattern reader (default: chosen from the index)
+//   GBWT_B200_LOCALITY      0 = never bucket the batch, 1 = always, unset = by batch and index size
+int env_int(const char* name, int fallback) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : fallback;
+}
+
+constexpr size_t LOCALITY_MIN_QUERIES = size_t(1) << 16;  // below this the sort costs more than it saves
+constexpr uint64_t LOCALITY_MIN_INDEX_BYTES = uint64_t(48) << 20;  // an index that lives in L2 gains nothing
+
+template <bool PERMUTED>
+void launch_find_extend_variant(const gbwt_b200_index* ix, int variant, const uint64_t* patterns, const uint32_t* perm, size_t n,
+                                size_t k, gbwt_b200_state* out, cudaStream_t s) {
+    const unsigned grid = grid_for(ix, n);
+    switch (variant & 3) {
+    case 0: k_find_extend<PERMUTED, false, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+    case 1: k_find_extend<PERMUTED, true, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+    case 2: k_find_extend<PERMUTED, false, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+    default: k_find_extend<PERMUTED, true, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+    }
+}
+
 int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
                        cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
-    k_find_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, patterns, n, k, out);
-    return launch_done("k_find_extend");
+    // Measured on B200 (tools/exp_find.py): the rounds loop with the chunked pattern reader is the fastest
+    // arrangement for dense and single-edge records and within 3% of the best for run-length bodies.
+    const int default_variant = 3;
+    const int variant = env_int("GBWT_B200_FIND_VARIANT", default_variant);
+    const uint64_t index_bytes = ix->bytes[0] + ix->bytes[1] + ix->bytes[2];
+    const int locality = env_int("GBWT_B200_LOCALITY", -1);
+    const bool bucket = k >= 2 && ix->view.records > 0 &&
+                        (locality == 1 || (locality != 0 && n >= LOCALITY_MIN_QUERIES && index_bytes >= LOCALITY_MIN_INDEX_BYTES));
+    if (!bucket) {
+        launch_find_extend_variant<false>(ix, variant, patterns, nullptr, n, k, out, s);
+        return launch_done("k_find_extend");
+    }
+    // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time
+    uint32_t shift = 0;
+    while (((ix->view.records - 1) >> shift) >= MAX_BUCKETS) shift++;
+    const uint32_t buckets = static_cast<uint32_t>(((ix->view.records - 1) >> shift) + 1);
+    const size_t max_part = 0xFFFFFFFFull;
+    for (size_t begin = 0; begin < n; begin += max_part) {
+        const size_t count = std::min(max_part, n - begin);
+        uint32_t *counts = nullptr, *perm = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counts), (buckets + 1) * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm), count * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMemsetAsync(counts, 0, (buckets + 1) * sizeof(uint32_t), s));
+        const uint64_t* part = patterns + begin * k;
+        k_bucket_count<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts);
+        launch_done("k_bucket_count");
+        k_bucket_scan<<<1, 1024, 0, s>>>(counts, buckets + 1);
+        launch_done("k_bucket_scan");
+        k_bucket_scatter<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts, perm);
+        launch_done("k_bucket_scatter");
+        launch_find_extend_variant<true>(ix, variant, part, perm, count, k, out + begin, s);
+        int rc = launch_done("k_find_extend");
+        cudaFreeAsync(counts, s);
+        cudaFreeAsync(perm, s);
+        if (rc != GBWT_B200_OK) return rc;
+    }
+    return GBWT_B200_OK;
 }
+
 int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, uint64_t base,
                               size_t n, gbwt_b200_state* out, cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
@@ -330,6 +390,12 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_endmarker, layout.endmarker.data(), layout.endmarker.size() * sizeof(Edge), ix->bytes[3]);
     if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+    // Records are fetched as isolated 32-byte sectors; ask L2 not to widen the DRAM fetches (a hint).
+    {
+        const char* e = std::getenv("GBWT_B200_L2_FETCH");
+        size_t granularity = e ? static_cast<size_t>(std::atoi(e)) : 32;
+        if (granularity > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, granularity) != cudaSuccess) cudaGetLastError();
+    }
     // Keep the stream-ordered pool's memory between calls: the host entry points allocate their staging
     // buffers from it on every call.
     cudaMemPool_t pool;

@@ -42,12 +42,124 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend(IndexView ix, const gb
     }
 }
 
+// Reads the pattern one 32-byte sector (four nodes) at a time with two 128-bit loads.
+struct ChunkReader {
+    const uint64_t* p;
+    uint64_t k, base;
+    uint64_t c0, c1, c2, c3;
+    bool vec;
+    __device__ __forceinline__ ChunkReader(const uint64_t* pattern, uint64_t len)
+        : p(pattern), k(len), base(~0ull), c0(0), c1(0), c2(0), c3(0), vec((reinterpret_cast<uintptr_t>(pattern) & 15) == 0) {}
+    __device__ __forceinline__ uint64_t node(uint64_t i) {
+        const uint64_t b = i & ~3ull;
+        if (b != base) {
+            base = b;
+            if (vec && k - b >= 4) {
+                const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(p + b));
+                const ulonglong2 hi = __ldg(reinterpret_cast<const ulonglong2*>(p + b) + 1);
+                c0 = lo.x; c1 = lo.y; c2 = hi.x; c3 = hi.y;
+            } else {
+                c0 = __ldg(p + b);
+                c1 = b + 1 < k ? __ldg(p + b + 1) : 0;
+                c2 = b + 2 < k ? __ldg(p + b + 2) : 0;
+                c3 = b + 3 < k ? __ldg(p + b + 3) : 0;
+            }
+        }
+        const uint32_t j = static_cast<uint32_t>(i) & 3u;
+        return j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+    }
+};
+
+// K1: find(p[0]) + extends, one thread per pattern. PERMUTED: the thread takes the query perm[i] (locality
+// schedule below; results always go to out[q]). ROUNDS / CHUNKED select the loop arrangement and the pattern
+// reader (record_scan.cuh); all combinations give identical results.
+template <bool PERMUTED, bool ROUNDS, bool CHUNKED>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
-                                                                size_t n, size_t k, gbwt_b200_state* __restrict__ out) {
-    GBWT_GRID_STRIDE(q, n) {
+                                                                const uint32_t* __restrict__ perm, size_t n, size_t k,
+                                                                gbwt_b200_state* __restrict__ out) {
+    GBWT_GRID_STRIDE(i, n) {
+        const size_t q = PERMUTED ? __ldg(perm + i) : i;
         gbwt_b200_state st;
-        query_find_extend(ix, patterns + q * k, k, st);
+        if (CHUNKED) {
+            ChunkReader rd(patterns + q * k, k);
+            if (ROUNDS) query_find_extend_rounds(ix, rd, k, st);
+            else query_find_extend_chain(ix, rd, k, st);
+        } else {
+            PlainReader rd;
+            rd.p = patterns + q * k;
+            if (ROUNDS) query_find_extend_rounds(ix, rd, k, st);
+            else query_find_extend_chain(ix, rd, k, st);
+        }
         store_state(out + q, st);
+    }
+}
+
+// ---- locality schedule ------------------------------------------------------------------------------
+// A batch of random queries touches ~65 isolated 32-byte sectors per query; HBM serves such accesses at a
+// fraction of its streaming bandwidth (every access opens a new DRAM row). The records a pattern needs lie
+// next to the record of its first node (node ids follow the graph's topological order), so the batch is
+// bucketed by the record of pattern[0] with a counting sort, and threads take queries in bucket order:
+// the queries in flight at any moment then share a few MB of the index, which stays in L1/L2, and HBM
+// only streams each part of the index once per batch.
+
+constexpr uint32_t MAX_BUCKETS = 1u << 16;
+
+__device__ __forceinline__ uint32_t bucket_of(const IndexView& ix, uint64_t node, uint32_t shift) {
+    uint64_t rec;
+    if (!record_of(ix, node, rec)) return 0;
+    return static_cast<uint32_t>(rec >> shift);
+}
+
+// counts[b + 1] += 1 for the bucket b of every query (counts[0] stays 0 for the exclusive scan).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
+                                                                 size_t k, uint32_t shift, uint32_t* __restrict__ counts) {
+    GBWT_GRID_STRIDE(q, n) {
+        atomicAdd(counts + 1 + bucket_of(ix, __ldg(patterns + q * k), shift), 1u);
+    }
+}
+
+// In-place inclusive scan of counts[0 .. m) by one CTA (m <= MAX_BUCKETS + 1): counts[b] becomes the first
+// slot of bucket b.
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t* __restrict__ counts, uint32_t m) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < m ? counts[i] : 0;
+        uint32_t x = v;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (warp > 0 ? warp_sums[warp - 1] : 0);
+        if (i < m) counts[i] = before + x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + x;
+        __syncthreads();
+    }
+}
+
+// perm[slot] = q, slots handed out per bucket by atomics (the order inside a bucket does not matter).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_scatter(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
+                                                                   size_t k, uint32_t shift, uint32_t* __restrict__ cursor,
+                                                                   uint32_t* __restrict__ perm) {
+    GBWT_GRID_STRIDE(q, n) {
+        const uint32_t slot = atomicAdd(cursor + bucket_of(ix, __ldg(patterns + q * k), shift), 1u);
+        perm[slot] = static_cast<uint32_t>(q);
     }
 }
 

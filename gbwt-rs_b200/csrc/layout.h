@@ -29,30 +29,35 @@ namespace gbwt_b200 {
 enum BodyFormat : uint8_t {
     FMT_EMPTY = 0,   // sigma == 0: BWT::record() is None (src/bwt.rs:342, 381)
     FMT_SINGLE = 1,  // sigma == 1: every position maps to edge 0, no body needed
-    FMT_DENSE2 = 2,  // sigma == 2: plain bitvector, 32-byte blocks {u32 ones_before, 224 bits}
+    FMT_DENSE2 = 2,  // sigma == 2: plain bitvector, 32-byte blocks {u32 ones_before, u32 sub-counts, 192 bits}
     FMT_RUN8 = 3,    // one byte per run: value + sigma * (len - 1), len <= max(1, 256 / sigma); no escapes
     FMT_RUN32 = 4,   // one u32 per run: value | (len - 1) << 8, sigma <= 256, len <= 2^24
     FMT_RUN64 = 5,   // two u32 per run: value, len
     FMT_COUNT = 6
 };
 
-constexpr uint32_t DENSE_BITS = 224;        // payload bits per 32-byte dense block
-constexpr uint32_t DENSE_WORDS = 7;
+// Dense block = one 32-byte sector: word 0 = ones before the block, word 1 = ones in payload bits [0, 64) in
+// bits 0-7 and ones in [0, 128) in bits 8-15, words 2-7 = 192 payload bits (position p -> word 2 + p / 32,
+// bit p % 32). rank needs the block, one sub-count and ONE masked 64-bit popcount.
+constexpr uint32_t DENSE_BITS = 192;
+constexpr uint32_t DENSE_WORDS = 6;
 constexpr uint8_t DESC_INLINE_EDGES = 1;    // w[] = {node0, offset0, node1, offset1}
 constexpr uint32_t RUN32_MAX_LEN = 1u << 24;
 constexpr uint32_t NO_SYMBOL = 0xFFFFFFFFu;
 
-// One record. 32 bytes, 32-byte aligned: a single sector fetch gives everything but the body.
+// One record. 32 bytes, 32-byte aligned: a single sector fetch gives everything but the body. The first
+// 16 bytes are all a single-edge record or `find` needs, so those steps issue one 128-bit load.
 struct alignas(32) RecordDesc {
-    uint32_t body;       // offset of the body in 16-byte units
-    uint32_t body_len;   // RUN8: bytes; RUN32 / RUN64: runs; DENSE2: 32-byte blocks
     uint32_t total_len;  // Record::len(), src/bwt.rs:449-455
     uint16_t sigma16;    // min(sigma, 65535)
     uint8_t fmt;         // BodyFormat
     uint8_t flags;
-    // DESC_INLINE_EDGES: {node0, offset0, node1, offset1} (node1 unused when sigma == 1)
-    // otherwise:         {first edge index into IndexView::edges, sigma, magic = 65536 / sigma + 1, 0}
-    uint32_t w[4];
+    // DESC_INLINE_EDGES: w = {node0, offset0, node1, offset1} (node1 unused when sigma == 1)
+    // otherwise:         w = {first edge index into IndexView::edges, sigma, magic = 65536 / sigma + 1, 0}
+    uint32_t w01[2];
+    uint32_t body;       // offset of the body in 16-byte units
+    uint32_t body_len;   // RUN8: bytes; RUN32 / RUN64: runs; DENSE2: 32-byte blocks
+    uint32_t w23[2];
 };
 static_assert(sizeof(RecordDesc) == 32, "descriptor must be one sector");
 

@@ -130,13 +130,14 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
             uint64_t delta, off;
             rd.varint(delta); rd.varint(off);
             node += delta;
-            d.w[2 * i] = static_cast<uint32_t>(node);
-            d.w[2 * i + 1] = static_cast<uint32_t>(off);
+            uint32_t* w = i == 0 ? d.w01 : d.w23;
+            w[0] = static_cast<uint32_t>(node);
+            w[1] = static_cast<uint32_t>(off);
         }
     } else {
-        d.w[0] = static_cast<uint32_t>(edge_index);
-        d.w[1] = static_cast<uint32_t>(sigma);
-        d.w[2] = sigma <= 256 ? div_magic(static_cast<uint32_t>(sigma)) : 0;
+        d.w01[0] = static_cast<uint32_t>(edge_index);
+        d.w01[1] = static_cast<uint32_t>(sigma);
+        d.w23[0] = sigma <= 256 ? div_magic(static_cast<uint32_t>(sigma)) : 0;
         for (uint64_t i = 0; i < sigma; i++) {
             uint64_t delta, off;
             rd.varint(delta); rd.varint(off);
@@ -159,15 +160,19 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
             if (value == 1) {
                 for (uint64_t i = pos; i < pos + rl; i++) {
                     uint64_t blk = i / DENSE_BITS, bit = i % DENSE_BITS;
-                    words[blk * 8 + 1 + bit / 32] |= 1u << (bit % 32);
+                    words[blk * 8 + 2 + bit / 32] |= 1u << (bit % 32);
                 }
             }
             pos += rl;
         }
         uint32_t ones = 0;
         for (uint64_t b = 0; b < blocks; b++) {
-            words[b * 8] = ones;
-            for (uint32_t w = 1; w <= DENSE_WORDS; w++) ones += static_cast<uint32_t>(__builtin_popcount(words[b * 8 + w]));
+            uint32_t* w = words + b * 8;
+            w[0] = ones;
+            const uint32_t c0 = static_cast<uint32_t>(__builtin_popcount(w[2]) + __builtin_popcount(w[3]));
+            const uint32_t c1 = c0 + static_cast<uint32_t>(__builtin_popcount(w[4]) + __builtin_popcount(w[5]));
+            w[1] = c0 | (c1 << 8);
+            ones += c1 + static_cast<uint32_t>(__builtin_popcount(w[6]) + __builtin_popcount(w[7]));
         }
         break;
     }

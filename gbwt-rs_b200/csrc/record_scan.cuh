@@ -35,23 +35,34 @@ GBWT_HD Quad load_quad(const Unit16* p) {
     return q;
 }
 
-// A descriptor held in eight registers.
+// A descriptor held in eight registers: a = {total_len, meta, w0, w1}, b = {body, body_len, w2, w3}.
 struct Desc {
     Quad a, b;
-    GBWT_HD uint32_t body() const { return a.x; }
-    GBWT_HD uint32_t body_len() const { return a.y; }
-    GBWT_HD uint32_t total_len() const { return a.z; }
-    GBWT_HD uint32_t fmt() const { return (a.w >> 16) & 0xFF; }
-    GBWT_HD bool inline_edges() const { return ((a.w >> 24) & DESC_INLINE_EDGES) != 0; }
-    GBWT_HD uint32_t sigma() const { return inline_edges() ? (a.w & 0xFFFF) : b.y; }
-    GBWT_HD uint32_t edge_base() const { return b.x; }
+    GBWT_HD uint32_t total_len() const { return a.x; }
+    GBWT_HD uint32_t fmt() const { return (a.y >> 16) & 0xFF; }
+    GBWT_HD bool inline_edges() const { return ((a.y >> 24) & DESC_INLINE_EDGES) != 0; }
+    GBWT_HD uint32_t sigma() const { return inline_edges() ? (a.y & 0xFFFF) : a.w; }
+    GBWT_HD uint32_t edge_base() const { return a.z; }
+    GBWT_HD uint32_t node0() const { return a.z; }
+    GBWT_HD uint32_t offset0() const { return a.w; }
+    GBWT_HD uint32_t node1() const { return b.z; }
+    GBWT_HD uint32_t offset1() const { return b.w; }
+    GBWT_HD uint32_t magic() const { return b.z; }
+    GBWT_HD uint32_t body() const { return b.x; }
+    GBWT_HD uint32_t body_len() const { return b.y; }
 };
 
+// First half: enough for `find` and for single-edge records. Second half: body location and the second edge.
+GBWT_HD void load_desc_head(const IndexView& ix, uint64_t rec, Desc& d) {
+    d.a = load_quad(reinterpret_cast<const Unit16*>(ix.desc + rec));
+}
+GBWT_HD void load_desc_tail(const IndexView& ix, uint64_t rec, Desc& d) {
+    d.b = load_quad(reinterpret_cast<const Unit16*>(ix.desc + rec) + 1);
+}
 GBWT_HD Desc load_desc(const IndexView& ix, uint64_t rec) {
-    const Unit16* p = reinterpret_cast<const Unit16*>(ix.desc + rec);
     Desc d;
-    d.a = load_quad(p);
-    d.b = load_quad(p + 1);
+    load_desc_head(ix, rec, d);
+    load_desc_tail(ix, rec, d);
     return d;
 }
 
@@ -65,8 +76,8 @@ GBWT_HD bool record_of(const IndexView& ix, uint64_t node, uint64_t& rec) {
 GBWT_HD Edge edge_at(const IndexView& ix, const Desc& d, uint32_t rank) {
     Edge e;
     if (d.inline_edges()) {
-        e.node = rank == 0 ? d.b.x : d.b.z;
-        e.offset = rank == 0 ? d.b.y : d.b.w;
+        e.node = rank == 0 ? d.node0() : d.node1();
+        e.offset = rank == 0 ? d.offset0() : d.offset1();
     } else {
         const Edge* p = ix.edges + d.edge_base() + rank;
         e.node = GBWT_LDG(&p->node);
@@ -88,8 +99,8 @@ GBWT_HD bool find_edge(const IndexView& ix, const Desc& d, uint64_t node, uint32
                        FlipSet& fs) {
     const uint32_t sigma = d.sigma();
     if (d.inline_edges()) {
-        if (node == d.b.x) { rank = 0; edge_offset = d.b.y; }
-        else if (sigma == 2 && node == d.b.z) { rank = 1; edge_offset = d.b.w; }
+        if (node == d.node0()) { rank = 0; edge_offset = d.offset0(); }
+        else if (sigma == 2 && node == d.node1()) { rank = 1; edge_offset = d.offset1(); }
         else return false;
     } else {
         uint32_t low = 0, high = sigma;
@@ -124,26 +135,53 @@ struct Ranks {
 };
 
 // ---- FMT_DENSE2 ---------------------------------------------------------------------------------
+struct DenseBlock { Quad lo, hi; };
+
+GBWT_HD DenseBlock load_dense_block(const Unit16* body, uint32_t blk) {
+    DenseBlock b;
+    b.lo = load_quad(body + 2 * blk);
+    b.hi = load_quad(body + 2 * blk + 1);
+    return b;
+}
+
+// Ones in the block's payload bits [0, r), r <= 192, plus the ones before the block; `bit` = payload bit r
+// (0 when r == 192). One sub-count and one masked 64-bit popcount (layout.h).
+GBWT_HD uint32_t dense_block_rank1(const DenseBlock& b, uint32_t r, uint32_t& bit) {
+    uint32_t j = r >> 6;
+    if (j > 2) j = 2;
+    const uint32_t p = r - 64 * j;  // 0..64 bits of 64-bit word j
+    const uint32_t w_lo = j == 0 ? b.lo.z : (j == 1 ? b.hi.x : b.hi.z);
+    const uint32_t w_hi = j == 0 ? b.lo.w : (j == 1 ? b.hi.y : b.hi.w);
+    const uint32_t sub = j == 0 ? 0u : (j == 1 ? (b.lo.y & 0xFFu) : ((b.lo.y >> 8) & 0xFFu));
+    const uint32_t m_lo = p >= 32 ? 0xFFFFFFFFu : ((1u << p) - 1u);
+    const uint32_t m_hi = p <= 32 ? 0u : (p >= 64 ? 0xFFFFFFFFu : ((1u << (p - 32)) - 1u));
+    bit = p < 32 ? ((w_lo >> p) & 1u) : (p < 64 ? ((w_hi >> (p - 32)) & 1u) : 0u);
+    return b.lo.x + sub + GBWT_POPC(w_lo & m_lo) + GBWT_POPC(w_hi & m_hi);
+}
+
 // Ones in [0, i) of a dense body; i <= total_len. `bit` receives the symbol at position i (0 if i == total).
 GBWT_HD uint32_t dense_rank1(const Unit16* body, uint32_t blocks, uint32_t i, uint32_t& bit) {
     uint32_t blk = i / DENSE_BITS;
     if (blk >= blocks) blk = blocks - 1;
-    const uint32_t r = i - blk * DENSE_BITS;  // 0..224
-    const Quad lo = load_quad(body + 2 * blk), hi = load_quad(body + 2 * blk + 1);
-    const uint32_t w[7] = {lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint32_t count = lo.x;
-    bit = 0;
-GBWT_UNROLL
-    for (uint32_t k = 0; k < 7; k++) {
-        const uint32_t base = 32 * k;
-        uint32_t mask;
-        if (r >= base + 32) mask = 0xFFFFFFFFu;
-        else if (r > base) mask = (1u << (r - base)) - 1u;
-        else mask = 0;
-        count += GBWT_POPC(w[k] & mask);
-        if (r >= base && r < base + 32) bit = (w[k] >> (r - base)) & 1u;
+    const DenseBlock b = load_dense_block(body, blk);
+    return dense_block_rank1(b, i - blk * DENSE_BITS, bit);
+}
+
+// rank1(start) and rank1(end), start <= end <= total_len; one block load when both fall in the same block.
+GBWT_HD void dense_rank1_pair(const Unit16* body, uint32_t blocks, uint32_t start, uint32_t end, uint32_t& ones_s,
+                              uint32_t& ones_e) {
+    uint32_t blk_s = start / DENSE_BITS, blk_e = end / DENSE_BITS;
+    if (blk_s >= blocks) blk_s = blocks - 1;
+    if (blk_e >= blocks) blk_e = blocks - 1;
+    uint32_t bit;
+    const DenseBlock bs = load_dense_block(body, blk_s);
+    ones_s = dense_block_rank1(bs, start - blk_s * DENSE_BITS, bit);
+    if (blk_e == blk_s) {
+        ones_e = dense_block_rank1(bs, end - blk_e * DENSE_BITS, bit);
+    } else {
+        const DenseBlock be = load_dense_block(body, blk_e);
+        ones_e = dense_block_rank1(be, end - blk_e * DENSE_BITS, bit);
     }
-    return count;
 }
 
 // ---- run formats ------------------------------------------------------------------------------------
@@ -166,7 +204,7 @@ GBWT_HD void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, cons
     uint32_t off = 0;
     if (fmt == FMT_RUN8) {
         const uint32_t sigma = d.sigma();
-        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;  // inline edges + runs => sigma == 2
+        const uint32_t magic = d.inline_edges() ? 32769u : d.magic();  // inline edges + runs => sigma == 2
         for (uint32_t base = 0; base < n && off < end; base += 16) {
             const Quad q = load_quad(body + (base >> 4));
             const uint32_t words[4] = {q.x, q.y, q.z, q.w};
@@ -207,7 +245,7 @@ GBWT_HD uint32_t symbol_at_runs(const IndexView& ix, const Desc& d, uint32_t i) 
     uint32_t off = 0, symbol = NO_SYMBOL;
     if (fmt == FMT_RUN8) {
         const uint32_t sigma = d.sigma();
-        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;  // inline edges + runs => sigma == 2
+        const uint32_t magic = d.inline_edges() ? 32769u : d.magic();  // inline edges + runs => sigma == 2
         for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 16) {
             const Quad q = load_quad(body + (base >> 4));
             const uint32_t words[4] = {q.x, q.y, q.z, q.w};
@@ -265,10 +303,8 @@ GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, con
         r.at_start = start; r.at_end = end;
         if (BD) r.flipped = fs.has(0) ? end - start : 0;
     } else if (fmt == FMT_DENSE2) {
-        const Unit16* body = ix.bodies + d.body();
-        uint32_t bit;
-        const uint32_t ones_s = dense_rank1(body, d.body_len(), start, bit);
-        const uint32_t ones_e = dense_rank1(body, d.body_len(), end, bit);
+        uint32_t ones_s, ones_e;
+        dense_rank1_pair(ix.bodies + d.body(), d.body_len(), start, end, ones_s, ones_e);
         r.at_start = symbol ? ones_s : start - ones_s;
         r.at_end = symbol ? ones_e : end - ones_e;
         if (BD) {
@@ -440,9 +476,9 @@ GBWT_HD bool select_symbol(const IndexView& ix, const Desc& d, uint32_t symbol, 
             if (before <= k) lo = mid; else hi = mid;
         }
         const Quad a = load_quad(body + 2 * lo), b = load_quad(body + 2 * lo + 1);
-        const uint32_t w[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const uint32_t w[6] = {a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t need = k - (symbol ? a.x : lo * DENSE_BITS - a.x);
-        for (uint32_t j = 0; j < 7; j++) {
+        for (uint32_t j = 0; j < 6; j++) {
             uint32_t bits = symbol ? w[j] : ~w[j];
             const uint32_t c = GBWT_POPC(bits);
             if (need < c) {
@@ -459,7 +495,7 @@ GBWT_HD bool select_symbol(const IndexView& ix, const Desc& d, uint32_t symbol, 
     uint32_t off = 0, seen = 0;
     if (fmt == FMT_RUN8) {
         const uint32_t sigma = d.sigma();
-        const uint32_t magic = d.inline_edges() ? 32769u : d.b.z;
+        const uint32_t magic = d.inline_edges() ? 32769u : d.magic();
         for (uint32_t base = 0; base < n; base += 16) {
             const Quad q = load_quad(body + (base >> 4));
             const uint32_t words[4] = {q.x, q.y, q.z, q.w};
@@ -553,18 +589,111 @@ GBWT_HD bool gbwt_backward(const IndexView& ix, const gbwt_b200_pos& pos, gbwt_b
 
 // ---- whole queries ---------------------------------------------------------------------------------
 
-// find(pattern[0]) followed by extend over pattern[1..k): the loop of src/bin/benchmark.rs:161-167.
-GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uint64_t k, gbwt_b200_state& out) {
+// ---- find + extends for one pattern -------------------------------------------------------------------
+// The loop of src/bin/benchmark.rs:161-167, i.e. GBWT::find (src/gbwt.rs:269-281) then GBWT::extend /
+// Record::follow (src/gbwt.rs:292-304, src/bwt.rs:595-616) per node. Same results as chaining gbwt_find /
+// gbwt_extend, arranged for the GPU: the range lives in two 32-bit registers, every descriptor is loaded once
+// and its second half only when the record has a body.
+
+struct PlainReader {
+    const uint64_t* p;
+    GBWT_HD uint64_t node(uint64_t i) { return GBWT_LDG(p + i); }
+};
+
+// Step on a single-edge record (head loaded): every position maps to edge 0.
+GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
+    const uint32_t total = d.total_len();
+    const uint32_t s = d.offset0() + (start < total ? start : total), e = d.offset0() + (end < total ? end : total);
+    if (next != d.node0() || s >= e) return false;
+    start = s; end = e;
+    return true;
+}
+
+// Step on a record with a body (head loaded; loads the tail).
+GBWT_HD bool follow_body(const IndexView& ix, uint64_t rec, Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
+    load_desc_tail(ix, rec, d);
+    uint32_t rank = 0, edge_offset = 0;
+    FlipSet fs;
+    fs.lt = 0; fs.extra = NO_SYMBOL;
+    if (!find_edge<false>(ix, d, next, rank, edge_offset, fs)) return false;
+    const Ranks r = rank_pair<false>(ix, d, rank, fs, start, end);
+    if (r.at_start >= r.at_end) return false;
+    start = edge_offset + r.at_start; end = edge_offset + r.at_end;
+    return true;
+}
+
+// GBWT::find on pattern node 0: leaves the head of its descriptor in `d`.
+GBWT_HD bool find_first(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d, uint32_t& start, uint32_t& end) {
+    if (node < ix.offset + 1 || !record_of(ix, node, rec)) return false;
+    load_desc_head(ix, rec, d);
+    if (d.fmt() == FMT_EMPTY || d.total_len() == 0) return false;
+    start = 0; end = d.total_len();
+    return true;
+}
+
+// Descriptor head of the record that the next step starts from; false = BWT::record() is None.
+GBWT_HD bool next_record(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d) {
+    if (!record_of(ix, node, rec)) return false;
+    load_desc_head(ix, rec, d);
+    return d.fmt() != FMT_EMPTY;
+}
+
+// Straight chain of steps. Lanes of a warp diverge on the record format; when the steps are cheap and
+// memory-bound (dense / single-edge records) that is what keeps more loads in flight.
+template <class Reader>
+GBWT_HD void query_find_extend_chain(const IndexView& ix, Reader& rd, uint64_t k, gbwt_b200_state& out) {
     set_none(out);
     if (k == 0) return;
-    gbwt_b200_state st;
-    if (!gbwt_find(ix, GBWT_LDG(pattern), st)) return;
+    const uint64_t first_node = ix.offset + 1;
+    uint64_t node = rd.node(0), rec = 0;
+    Desc d;
+    uint32_t start = 0, end = 0;
+    if (!find_first(ix, node, rec, d, start, end)) return;
     for (uint64_t i = 1; i < k; i++) {
-        gbwt_b200_state next;
-        if (!gbwt_extend(ix, st, GBWT_LDG(pattern + i), next)) return;
-        st = next;
+        const uint64_t next = rd.node(i);
+        if (next < first_node) return;
+        const bool ok = d.fmt() == FMT_SINGLE ? follow_single(d, next, start, end) : follow_body(ix, rec, d, next, start, end);
+        if (!ok) return;
+        node = next;
+        if (i + 1 < k && !next_record(ix, node, rec, d)) return;
     }
-    out = st;
+    out.node = node; out.start = start; out.end = end;
+}
+
+// Rounds: any number of single-edge records, then one record with a body, so that the lanes of a warp meet
+// again at the expensive step. This is the form for run-length bodies, where the scan dominates.
+template <class Reader>
+GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t k, gbwt_b200_state& out) {
+    set_none(out);
+    if (k == 0) return;
+    const uint64_t first_node = ix.offset + 1;
+    uint64_t node = rd.node(0), rec = 0;
+    Desc d;
+    uint32_t start = 0, end = 0;
+    if (!find_first(ix, node, rec, d, start, end)) return;
+    uint64_t i = 1;
+    while (i < k) {
+        bool dead = false;
+        while (i < k && d.fmt() == FMT_SINGLE) {
+            const uint64_t next = rd.node(i);
+            if (next < first_node || !follow_single(d, next, start, end)) { dead = true; break; }
+            node = next; i++;
+            if (i < k && !next_record(ix, node, rec, d)) { dead = true; break; }
+        }
+        if (dead) return;
+        if (i >= k) break;
+        const uint64_t next = rd.node(i);
+        if (next < first_node || !follow_body(ix, rec, d, next, start, end)) return;
+        node = next; i++;
+        if (i < k && !next_record(ix, node, rec, d)) return;
+    }
+    out.node = node; out.start = start; out.end = end;
+}
+
+GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uint64_t k, gbwt_b200_state& out) {
+    PlainReader rd;
+    rd.p = pattern;
+    query_find_extend_rounds(ix, rd, k, out);
 }
 
 // bd_find(path[first]), extend_forward over path(first, end), extend_backward over path[start, first) in

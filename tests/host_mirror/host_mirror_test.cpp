@@ -1,0 +1,72 @@
+// Exercises gbwt-rs_b200/host/gbwt.hpp like the reference's GBWT doc-test (gbwt-rs src/gbwt.rs:46-92) and
+// its extract / bd_extend tests (src/gbwt/tests.rs:164-189, 393-462). Exit code 0 = all assertions hold,
+// 77 = no CUDA device (the mirror refuses to run; there is no CPU fallback), anything else = failure.
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../gbwt-rs_b200/host/gbwt.hpp"
+
+using namespace gbwt_b200_host;
+
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        if (!(cond)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } \
+    } while (0)
+
+static std::size_t encode_node(std::size_t id, bool reverse) { return 2 * id + (reverse ? 1 : 0); }  // support.rs:155
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    const std::string dir = argv[1];
+    try {
+        GBWT index = GBWT::load(dir + "/example.gbwt");
+        // Statistics (gbwt.rs:54-58)
+        CHECK(index.len() == 68 && index.sequences() == 12 && index.alphabet_size() == 52 && index.is_bidirectional());
+        CHECK(index.alphabet_offset() == 21 && index.first_node() == 22 && index.effective_size() == 31);
+        CHECK(!index.has_node(21) && index.has_node(22) && !index.has_node(52));
+        // second-to-last node of path 2 forward (gbwt.rs:60-68)
+        auto pos = index.start(4);
+        std::optional<Pos> last;
+        while (pos) { last = pos; pos = index.forward(*pos); }
+        CHECK(last.has_value());
+        auto prev = index.backward(*last);
+        CHECK(prev && prev->node == encode_node(15, false));
+        // unidirectional search (gbwt.rs:70-75)
+        auto state = index.find(encode_node(12, false));
+        CHECK(state.has_value());
+        state = index.extend(*state, encode_node(14, false));
+        CHECK(state.has_value());
+        state = index.extend(*state, encode_node(15, false));
+        CHECK(state && state->node == encode_node(15, false) && state->len() == 2);
+        CHECK(!index.extend(*state, encode_node(11, false)) && !index.find(0) && !index.find(36));
+        // bidirectional search (gbwt.rs:77-83)
+        auto bd = index.bd_find(encode_node(14, false));
+        CHECK(bd.has_value());
+        bd = index.extend_backward(*bd, encode_node(12, false));
+        CHECK(bd.has_value());
+        bd = index.extend_forward(*bd, encode_node(15, false));
+        CHECK(bd && bd->forward.node == encode_node(15, false) && bd->reverse.node == encode_node(12, true) && bd->len() == 2);
+        CHECK(bd->from() == std::make_pair(std::size_t(12), false) && bd->to() == std::make_pair(std::size_t(15), false));
+        // sequence iterator (gbwt.rs:546-548)
+        auto path = index.sequence(7);
+        CHECK(path && *path == (std::vector<std::size_t>{35, 33, 29, 27, 23}));
+        CHECK(!index.sequence(12).has_value() && !index.start(12).has_value());
+        // batch: every length-4 window of every sequence (BASELINE.json configs[0]): 20 queries, 32 occurrences
+        std::vector<uint64_t> patterns;
+        for (std::size_t i = 0; i < index.sequences(); i++) {
+            auto p = *index.sequence(i);
+            for (std::size_t j = 0; j + 4 <= p.size(); j++) patterns.insert(patterns.end(), p.begin() + j, p.begin() + j + 4);
+        }
+        auto out = index.find_extend_batch(patterns, 4);
+        std::size_t occ = 0;
+        for (auto& s : out) occ += s.end - s.start;
+        CHECK(out.size() == 20 && occ == 32);
+    } catch (const std::runtime_error& e) {
+        if (std::string(e.what()).find("error 7") != std::string::npos) { std::fprintf(stderr, "%s\n", e.what()); return 77; }
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 3;
+    }
+    std::puts("host mirror ok");
+    return 0;
+}
