@@ -399,6 +399,4 @@ class GBWT:
         self._check(_lib.gbwt_b200_extract_device(self._h, d_ids, m, d_out_offsets, d_nodes, d_lengths, stream))
 
 
-def shard_range(n: int, rank: int, world: int) -> tuple:
-    """Contiguous block [lo, hi) of n queries / sequences owned by `rank`."""
-    return (n * rank) // world, (n * (rank + 1)) // world
+from .distributed import gather_states, shard_range  # noqa: E402,F401

@@ -112,7 +112,13 @@ void launch_find_extend_variant(const gbwt_b200_index* ix, int variant, const ui
     case 0: k_find_extend<PERMUTED, false, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
     case 1: k_find_extend<PERMUTED, true, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
     case 2: k_find_extend<PERMUTED, false, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-    default: k_find_extend<PERMUTED, true, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+    default:
+        switch (env_int("GBWT_B200_MINBLOCKS", 1)) {
+        case 5: k_find_extend<PERMUTED, true, true, 5><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+        case 6: k_find_extend<PERMUTED, true, true, 6><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+        default: k_find_extend<PERMUTED, true, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
+        }
+        break;
     }
 }
 

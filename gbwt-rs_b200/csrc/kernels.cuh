@@ -42,22 +42,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend(IndexView ix, const gb
     }
 }
 
-// Reads the pattern one 32-byte sector (four nodes) at a time with two 128-bit loads.
+// Reads the pattern one 32-byte sector (four nodes) at a time with one 256-bit load.
 struct ChunkReader {
     const uint64_t* p;
     uint64_t k, base;
     uint64_t c0, c1, c2, c3;
     bool vec;
     __device__ __forceinline__ ChunkReader(const uint64_t* pattern, uint64_t len)
-        : p(pattern), k(len), base(~0ull), c0(0), c1(0), c2(0), c3(0), vec((reinterpret_cast<uintptr_t>(pattern) & 15) == 0) {}
+        : p(pattern), k(len), base(~0ull), c0(0), c1(0), c2(0), c3(0), vec((reinterpret_cast<uintptr_t>(pattern) & 31) == 0) {}
     __device__ __forceinline__ uint64_t node(uint64_t i) {
         const uint64_t b = i & ~3ull;
         if (b != base) {
             base = b;
             if (vec && k - b >= 4) {
-                const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(p + b));
-                const ulonglong2 hi = __ldg(reinterpret_cast<const ulonglong2*>(p + b) + 1);
-                c0 = lo.x; c1 = lo.y; c2 = hi.x; c3 = hi.y;
+                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(c0), "=l"(c1), "=l"(c2), "=l"(c3) : "l"(p + b));
             } else {
                 c0 = __ldg(p + b);
                 c1 = b + 1 < k ? __ldg(p + b + 1) : 0;
@@ -73,8 +71,8 @@ struct ChunkReader {
 // K1: find(p[0]) + extends, one thread per pattern. PERMUTED: the thread takes the query perm[i] (locality
 // schedule below; results always go to out[q]). ROUNDS / CHUNKED select the loop arrangement and the pattern
 // reader (record_scan.cuh); all combinations give identical results.
-template <bool PERMUTED, bool ROUNDS, bool CHUNKED>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
+template <bool PERMUTED, bool ROUNDS, bool CHUNKED, int MIN_BLOCKS = 1>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
                                                                 const uint32_t* __restrict__ perm, size_t n, size_t k,
                                                                 gbwt_b200_state* __restrict__ out) {
     GBWT_GRID_STRIDE(i, n) {

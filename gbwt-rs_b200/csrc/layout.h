@@ -45,8 +45,8 @@ constexpr uint8_t DESC_INLINE_EDGES = 1;    // w[] = {node0, offset0, node1, off
 constexpr uint32_t RUN32_MAX_LEN = 1u << 24;
 constexpr uint32_t NO_SYMBOL = 0xFFFFFFFFu;
 
-// One record. 32 bytes, 32-byte aligned: a single sector fetch gives everything but the body. The first
-// 16 bytes are all a single-edge record or `find` needs, so those steps issue one 128-bit load.
+// One record. 32 bytes, 32-byte aligned: a single sector, fetched with one 256-bit load, gives everything
+// but the body.
 struct alignas(32) RecordDesc {
     uint32_t total_len;  // Record::len(), src/bwt.rs:449-455
     uint16_t sigma16;    // min(sigma, 65535)
@@ -55,7 +55,7 @@ struct alignas(32) RecordDesc {
     // DESC_INLINE_EDGES: w = {node0, offset0, node1, offset1} (node1 unused when sigma == 1)
     // otherwise:         w = {first edge index into IndexView::edges, sigma, magic = 65536 / sigma + 1, 0}
     uint32_t w01[2];
-    uint32_t body;       // offset of the body in 16-byte units
+    uint32_t body;       // offset of the body in 16-byte units (always even: bodies are 32-byte aligned)
     uint32_t body_len;   // RUN8: bytes; RUN32 / RUN64: runs; DENSE2: 32-byte blocks
     uint32_t w23[2];
 };

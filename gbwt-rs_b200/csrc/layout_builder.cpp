@@ -106,6 +106,7 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
         uint64_t dense = 2 * ceil_div(pl.total, DENSE_BITS);
         if (dense <= std::max<uint64_t>(4, 2 * best)) { best = dense; pl.fmt = FMT_DENSE2; }
     }
+    best = (best + 1) & ~1ull;  // every body starts on a 32-byte sector boundary (256-bit loads)
     if (best > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
     pl.units = static_cast<uint32_t>(best);
     return pl;

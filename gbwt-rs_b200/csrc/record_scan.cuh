@@ -35,6 +35,19 @@ GBWT_HD Quad load_quad(const Unit16* p) {
     return q;
 }
 
+// One 256-bit read-only load of a 32-byte-aligned sector (LDG.E.256.CONSTANT on sm_100a): descriptors and
+// dense blocks are exactly one sector, so each costs a single load instruction and a single L1 wavefront.
+GBWT_HD void load_sector(const Unit16* p, Quad& lo, Quad& hi) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+#else
+    lo = load_quad(p);
+    hi = load_quad(p + 1);
+#endif
+}
+
 // A descriptor held in eight registers: a = {total_len, meta, w0, w1}, b = {body, body_len, w2, w3}.
 struct Desc {
     Quad a, b;
@@ -52,17 +65,9 @@ struct Desc {
     GBWT_HD uint32_t body_len() const { return b.y; }
 };
 
-// First half: enough for `find` and for single-edge records. Second half: body location and the second edge.
-GBWT_HD void load_desc_head(const IndexView& ix, uint64_t rec, Desc& d) {
-    d.a = load_quad(reinterpret_cast<const Unit16*>(ix.desc + rec));
-}
-GBWT_HD void load_desc_tail(const IndexView& ix, uint64_t rec, Desc& d) {
-    d.b = load_quad(reinterpret_cast<const Unit16*>(ix.desc + rec) + 1);
-}
 GBWT_HD Desc load_desc(const IndexView& ix, uint64_t rec) {
     Desc d;
-    load_desc_head(ix, rec, d);
-    load_desc_tail(ix, rec, d);
+    load_sector(reinterpret_cast<const Unit16*>(ix.desc + rec), d.a, d.b);
     return d;
 }
 
@@ -139,8 +144,7 @@ struct DenseBlock { Quad lo, hi; };
 
 GBWT_HD DenseBlock load_dense_block(const Unit16* body, uint32_t blk) {
     DenseBlock b;
-    b.lo = load_quad(body + 2 * blk);
-    b.hi = load_quad(body + 2 * blk + 1);
+    load_sector(body + 2 * blk, b.lo, b.hi);
     return b;
 }
 
@@ -592,15 +596,15 @@ GBWT_HD bool gbwt_backward(const IndexView& ix, const gbwt_b200_pos& pos, gbwt_b
 // ---- find + extends for one pattern -------------------------------------------------------------------
 // The loop of src/bin/benchmark.rs:161-167, i.e. GBWT::find (src/gbwt.rs:269-281) then GBWT::extend /
 // Record::follow (src/gbwt.rs:292-304, src/bwt.rs:595-616) per node. Same results as chaining gbwt_find /
-// gbwt_extend, arranged for the GPU: the range lives in two 32-bit registers, every descriptor is loaded once
-// and its second half only when the record has a body.
+// gbwt_extend, arranged for the GPU: the range lives in two 32-bit registers and every descriptor is loaded
+// once, with a single 256-bit load.
 
 struct PlainReader {
     const uint64_t* p;
     GBWT_HD uint64_t node(uint64_t i) { return GBWT_LDG(p + i); }
 };
 
-// Step on a single-edge record (head loaded): every position maps to edge 0.
+// Step on a single-edge record: every position maps to edge 0.
 GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
     const uint32_t total = d.total_len();
     const uint32_t s = d.offset0() + (start < total ? start : total), e = d.offset0() + (end < total ? end : total);
@@ -609,9 +613,8 @@ GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32
     return true;
 }
 
-// Step on a record with a body (head loaded; loads the tail).
-GBWT_HD bool follow_body(const IndexView& ix, uint64_t rec, Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
-    load_desc_tail(ix, rec, d);
+// Step on a record with a body.
+GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
     uint32_t rank = 0, edge_offset = 0;
     FlipSet fs;
     fs.lt = 0; fs.extra = NO_SYMBOL;
@@ -622,19 +625,19 @@ GBWT_HD bool follow_body(const IndexView& ix, uint64_t rec, Desc& d, uint64_t ne
     return true;
 }
 
-// GBWT::find on pattern node 0: leaves the head of its descriptor in `d`.
+// GBWT::find on pattern node 0: leaves its descriptor in `d`.
 GBWT_HD bool find_first(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d, uint32_t& start, uint32_t& end) {
     if (node < ix.offset + 1 || !record_of(ix, node, rec)) return false;
-    load_desc_head(ix, rec, d);
+    d = load_desc(ix, rec);
     if (d.fmt() == FMT_EMPTY || d.total_len() == 0) return false;
     start = 0; end = d.total_len();
     return true;
 }
 
-// Descriptor head of the record that the next step starts from; false = BWT::record() is None.
+// Descriptor of the record that the next step starts from; false = BWT::record() is None.
 GBWT_HD bool next_record(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d) {
     if (!record_of(ix, node, rec)) return false;
-    load_desc_head(ix, rec, d);
+    d = load_desc(ix, rec);
     return d.fmt() != FMT_EMPTY;
 }
 
@@ -652,7 +655,7 @@ GBWT_HD void query_find_extend_chain(const IndexView& ix, Reader& rd, uint64_t k
     for (uint64_t i = 1; i < k; i++) {
         const uint64_t next = rd.node(i);
         if (next < first_node) return;
-        const bool ok = d.fmt() == FMT_SINGLE ? follow_single(d, next, start, end) : follow_body(ix, rec, d, next, start, end);
+        const bool ok = d.fmt() == FMT_SINGLE ? follow_single(d, next, start, end) : follow_body(ix, d, next, start, end);
         if (!ok) return;
         node = next;
         if (i + 1 < k && !next_record(ix, node, rec, d)) return;
@@ -683,7 +686,7 @@ GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t 
         if (dead) return;
         if (i >= k) break;
         const uint64_t next = rd.node(i);
-        if (next < first_node || !follow_body(ix, rec, d, next, start, end)) return;
+        if (next < first_node || !follow_body(ix, d, next, start, end)) return;
         node = next; i++;
         if (i < k && !next_record(ix, node, rec, d)) return;
     }

@@ -14,6 +14,7 @@ ap.add_argument("--sites", type=int, default=3_333_333)
 ap.add_argument("--haplotypes", type=int, default=1024)
 ap.add_argument("--variants", default="0,1,2,3")
 ap.add_argument("--locality", default="0,1")
+ap.add_argument("--minblocks", default="1")
 ap.add_argument("--l2", default="32")
 ap.add_argument("--layout", default="auto")
 args = ap.parse_args()
@@ -29,7 +30,8 @@ ref = None
 for l2 in args.l2.split(","):
     os.environ["GBWT_B200_L2_FETCH"] = l2
     index = gb.GBWT.from_bytes(img.array, layout=args.layout)
-    for v, loc in [(v, loc) for loc in args.locality.split(",") for v in args.variants.split(",")]:
+    for v, loc, mb in [(v, loc, mb) for loc in args.locality.split(",") for v in args.variants.split(",") for mb in args.minblocks.split(",")]:
+        os.environ["GBWT_B200_MINBLOCKS"] = mb
         os.environ["GBWT_B200_FIND_VARIANT"] = v
         os.environ["GBWT_B200_LOCALITY"] = loc
         for _ in range(2):
@@ -43,5 +45,5 @@ for l2 in args.l2.split(","):
         ms = e0.elapsed_time(e1) / 3
         chk = int((d_out[:, 2] - d_out[:, 1]).sum().item())
         if ref is None: ref = chk
-        print(json.dumps({"locality": loc, "variant": v, "ms": ms, "mqps": Q / ms / 1e3, "checksum_ok": chk == ref}), flush=True)
+        print(json.dumps({"locality": loc, "variant": v, "minblocks": mb, "ms": ms, "mqps": Q / ms / 1e3, "checksum_ok": chk == ref}), flush=True)
     del index
