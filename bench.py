@@ -333,15 +333,26 @@ def main():
         if not np.array_equal(got, want.view(np.uint64).reshape(-1, 3)):
             raise SystemExit("parity failure against the oracle on the sampled queries")
         peak, peak_src = measured_peak_gbs()
+        traffic = None
+        try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this very step
+            with open(os.path.join(ROOT, "profiles", "find_extend_traffic.json")) as f:
+                prof = json.load(f)
+            if prof["queries_per_launch"] == Q and prof["layout"] == args.layout and args.workload == "find":
+                traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+        except Exception:
+            traffic = None
         launch_s = statistics.mean(step_ms) / 1e3
         achieved = bytes_per_query * Q / launch_s / 1e9
         roofline = {"bound": "hbm", "kernel": "k_find_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (of measured)",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
                     "algorithmic_bytes_per_query": bytes_per_query, "algorithmic_bytes_per_lf_step": bytes_per_query / K_LEN,
-                    "launch_ms": launch_s * 1e3,
-                    "note": "algorithmic bytes are counted on the reference's compressed records (SURVEY.md 8(d)); the device "
-                            "layout answers a rank query from one 32-byte descriptor plus at most two 32-byte blocks, so a "
-                            "fraction above 1 means fewer bytes moved than the reference's scan reads, not skipped work"}
+                    "launch_ms": launch_s * 1e3, "launches_per_step": launches // max(1, args.steps),
+                    "note": "achieved = algorithmic bytes of SURVEY.md 8(d) (counted on the reference's compressed records: "
+                            "~330 B of a 518 B record per anchor step) / device time of the whole step (bucket pre-pass + "
+                            "k_find_extend). It exceeds the HBM peak because the work is not done by moving those bytes: the dense "
+                            "device layout answers a rank from one 32-byte block, and the locality schedule makes the batch share "
+                            "records through L1/L2, so measured DRAM traffic (`traffic`, ncu) is ~0.45 KB/query against 5.7 KB/query "
+                            "algorithmic. The kernel is bound by L1 wavefronts / latency (profiles/README.md), not by HBM"}
         log(f"[bench] oracle sample + cpu baseline took {time.time() - t:.1f} s")
 
     if rank == 0:
