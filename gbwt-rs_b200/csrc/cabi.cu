@@ -93,9 +93,8 @@ int launch_extend(const gbwt_b200_index* ix, const gbwt_b200_state* st, const ui
     k_extend<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, st, nodes, n, out);
     return launch_done("k_extend");
 }
-// Development knobs (tuning experiments only; the defaults are the product configuration):
-//   GBWT_B200_FIND_VARIANT  bit 0 = rounds loop, bit 1 = chunked pattern reader (default: chosen from the index)
-//   GBWT_B200_LOCALITY      0 = never bucket the batch, 1 = always, unset = by batch and index size
+// Development / test knob: GBWT_B200_LOCALITY = 0 never bucket the batch, 1 always (lets the tests drive the
+// permuted path on tiny indexes); unset = decided by batch and index size.
 int env_int(const char* name, int fallback) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : fallback;
@@ -105,36 +104,23 @@ constexpr size_t LOCALITY_MIN_QUERIES = size_t(1) << 16;  // below this the sort
 constexpr uint64_t LOCALITY_MIN_INDEX_BYTES = uint64_t(48) << 20;  // an index that lives in L2 gains nothing
 
 template <bool PERMUTED>
-void launch_find_extend_variant(const gbwt_b200_index* ix, int variant, const uint64_t* patterns, const uint32_t* perm, size_t n,
-                                size_t k, gbwt_b200_state* out, cudaStream_t s) {
+void launch_find_extend_kernel(const gbwt_b200_index* ix, const uint64_t* patterns, const uint32_t* perm, size_t n, size_t k,
+                               gbwt_b200_state* out, cudaStream_t s) {
     const unsigned grid = grid_for(ix, n);
-    switch (variant & 3) {
-    case 0: k_find_extend<PERMUTED, false, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-    case 1: k_find_extend<PERMUTED, true, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-    case 2: k_find_extend<PERMUTED, false, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-    default:
-        switch (env_int("GBWT_B200_MINBLOCKS", 1)) {
-        case 5: k_find_extend<PERMUTED, true, true, 5><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-        case 6: k_find_extend<PERMUTED, true, true, 6><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-        default: k_find_extend<PERMUTED, true, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out); break;
-        }
-        break;
-    }
+    const uint64_t run_records = ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64];
+    if (run_records == 0) k_find_extend<PERMUTED, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out);
+    else k_find_extend<PERMUTED, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out);
 }
 
 int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
                        cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
-    // Measured on B200 (tools/exp_find.py): the rounds loop with the chunked pattern reader is the fastest
-    // arrangement for dense and single-edge records and within 3% of the best for run-length bodies.
-    const int default_variant = 3;
-    const int variant = env_int("GBWT_B200_FIND_VARIANT", default_variant);
     const uint64_t index_bytes = ix->bytes[0] + ix->bytes[1] + ix->bytes[2];
     const int locality = env_int("GBWT_B200_LOCALITY", -1);
     const bool bucket = k >= 2 && ix->view.records > 0 &&
                         (locality == 1 || (locality != 0 && n >= LOCALITY_MIN_QUERIES && index_bytes >= LOCALITY_MIN_INDEX_BYTES));
     if (!bucket) {
-        launch_find_extend_variant<false>(ix, variant, patterns, nullptr, n, k, out, s);
+        launch_find_extend_kernel<false>(ix, patterns, nullptr, n, k, out, s);
         return launch_done("k_find_extend");
     }
     // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time
@@ -155,7 +141,7 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
         launch_done("k_bucket_scan");
         k_bucket_scatter<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts, perm);
         launch_done("k_bucket_scatter");
-        launch_find_extend_variant<true>(ix, variant, part, perm, count, k, out + begin, s);
+        launch_find_extend_kernel<true>(ix, part, perm, count, k, out + begin, s);
         int rc = launch_done("k_find_extend");
         cudaFreeAsync(counts, s);
         cudaFreeAsync(perm, s);

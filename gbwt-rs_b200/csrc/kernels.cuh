@@ -69,25 +69,17 @@ struct ChunkReader {
 };
 
 // K1: find(p[0]) + extends, one thread per pattern. PERMUTED: the thread takes the query perm[i] (locality
-// schedule below; results always go to out[q]). ROUNDS / CHUNKED select the loop arrangement and the pattern
-// reader (record_scan.cuh); all combinations give identical results.
-template <bool PERMUTED, bool ROUNDS, bool CHUNKED, int MIN_BLOCKS = 1>
-__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
+// schedule below; results always go to out[q]). RUNS = false is the instantiation for indexes without
+// run-length bodies (record_scan.cuh: rank_pair).
+template <bool PERMUTED, bool RUNS>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
                                                                 const uint32_t* __restrict__ perm, size_t n, size_t k,
                                                                 gbwt_b200_state* __restrict__ out) {
     GBWT_GRID_STRIDE(i, n) {
         const size_t q = PERMUTED ? __ldg(perm + i) : i;
         gbwt_b200_state st;
-        if (CHUNKED) {
-            ChunkReader rd(patterns + q * k, k);
-            if (ROUNDS) query_find_extend_rounds(ix, rd, k, st);
-            else query_find_extend_chain(ix, rd, k, st);
-        } else {
-            PlainReader rd;
-            rd.p = patterns + q * k;
-            if (ROUNDS) query_find_extend_rounds(ix, rd, k, st);
-            else query_find_extend_chain(ix, rd, k, st);
-        }
+        ChunkReader rd(patterns + q * k, k);
+        query_find_extend_rounds<RUNS>(ix, rd, k, st);
         store_state(out + q, st);
     }
 }

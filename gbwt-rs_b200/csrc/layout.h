@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define GBWT_HD __host__ __device__ __forceinline__
+#define GBWT_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define GBWT_HD inline
+#define GBWT_HD_NOINLINE inline
 #endif
 #if defined(__CUDA_ARCH__)
 #define GBWT_UNROLL _Pragma("unroll")

@@ -198,15 +198,85 @@ GBWT_HD void add_run(uint32_t value, uint32_t len, uint32_t symbol, const FlipSe
     off += len;
 }
 
-// Scans the runs of a RUN8 / RUN32 / RUN64 body up to `end` (the reference's early exit, src/bwt.rs:610-612).
+// Sum of the four byte products a_i * b_i (IDP4A on the device).
+GBWT_HD uint32_t dot4(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, 0u);
+#else
+    uint32_t s = 0;
+    for (int i = 0; i < 4; i++) s += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+    return s;
+#endif
+}
+
+// 0x01 in every byte of x that is zero; exact for bytes <= 0x7F.
+GBWT_HD uint32_t zero_bytes(uint32_t x) { return (((x + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u) >> 7; }
+
+// RUN8 body whose alphabet size is a power of two <= 128 (the common outdegree 2 and 4): four runs are decoded
+// per 32-bit word with byte-parallel arithmetic -- lengths L = (w >> t) + 1 and values V = w & (sigma - 1) per
+// byte, sums with dot products. A word that lies entirely before `start` or entirely inside [start, end) only
+// adds its totals; the at most two words that straddle a boundary take the byte-by-byte path.
 template <bool BD>
-GBWT_HD void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+GBWT_HD void rank_runs8_pow2(const Unit16* body, uint32_t n, uint32_t sigma, uint32_t symbol, const FlipSet& fs,
+                             uint32_t start, uint32_t end, Ranks& r) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t t = 31u - static_cast<uint32_t>(__clz(sigma));
+#else
+    const uint32_t t = 31u - static_cast<uint32_t>(__builtin_clz(sigma));
+#endif
+    const uint32_t len_mask = (0xFFu >> t) * 0x01010101u, val_mask = (sigma - 1u) * 0x01010101u;
+    const uint32_t sym_bytes = symbol * 0x01010101u;
+    const uint32_t lt_add = (0x80u - (fs.lt < 128u ? fs.lt : 128u)) * 0x01010101u;
+    const uint32_t extra_bytes = (fs.extra < 128u ? fs.extra : 0x7Fu) * 0x01010101u;
+    const bool has_extra = fs.extra < sigma;
+    uint32_t off = 0;
+    for (uint32_t base = 0; base < n && off < end; base += 16) {
+        const Quad q = load_quad(body + (base >> 4));
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+GBWT_UNROLL
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t first = base + 4 * j;
+            if (first < n && off < end) {
+                const uint32_t w = words[j];
+                const uint32_t lens = ((w >> t) & len_mask) + 0x01010101u, vals = w & val_mask;
+                const uint32_t total = dot4(lens, 0x01010101u);
+                const bool whole = n - first >= 4;
+                if (whole && (off + total <= start || (off >= start && off + total <= end))) {
+                    const uint32_t count = dot4(lens, zero_bytes(vals ^ sym_bytes));
+                    r.at_end += count;
+                    if (off + total <= start) {
+                        r.at_start += count;
+                    } else if (BD) {
+                        uint32_t in_set = (((vals + lt_add) & 0x80808080u) ^ 0x80808080u) >> 7;
+                        if (has_extra) in_set |= zero_bytes(vals ^ extra_bytes);
+                        r.flipped += dot4(lens, in_set);
+                    }
+                    off += total;
+                } else {
+                    const uint32_t nb = n - first < 4 ? n - first : 4;
+                    for (uint32_t b = 0; b < nb; b++) {
+                        const uint32_t byte = (w >> (8 * b)) & 0xFF;
+                        add_run<BD>(byte & (sigma - 1u), (byte >> t) + 1u, symbol, fs, start, end, off, r);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Scans the runs of a RUN8 / RUN32 / RUN64 body up to `end` (the reference's early exit, src/bwt.rs:610-612).
+// Not inlined on the device: the scan loops would otherwise set the register budget (and the occupancy) of
+// the kernels whose common case is the register-light dense / single-edge step.
+template <bool BD>
+GBWT_HD_NOINLINE void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
                        uint32_t end, Ranks& r) {
     const Unit16* body = ix.bodies + d.body();
     const uint32_t n = d.body_len();
     const uint32_t fmt = d.fmt();
     uint32_t off = 0;
-    if (fmt == FMT_RUN8) {
+    if (fmt == FMT_RUN8 && d.sigma() <= 128 && (d.sigma() & (d.sigma() - 1)) == 0) {
+        rank_runs8_pow2<BD>(body, n, d.sigma(), symbol, fs, start, end, r);
+    } else if (fmt == FMT_RUN8) {
         const uint32_t sigma = d.sigma();
         const uint32_t magic = d.inline_edges() ? 32769u : d.magic();  // inline edges + runs => sigma == 2
         for (uint32_t base = 0; base < n && off < end; base += 16) {
@@ -294,7 +364,9 @@ GBWT_UNROLL
 
 // rank_symbol(start), rank_symbol(end) and, for BD, the flipped count, for any body format.
 // `start` <= `end`; both are clamped to the record length (ranks saturate there).
-template <bool BD>
+// RUNS = false compiles the run-length formats out: the host picks that instantiation for indexes that hold
+// none (IndexView::run_records == 0), so the scan loops do not set the register budget of the dense path.
+template <bool BD, bool RUNS = true>
 GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
                         uint32_t end) {
     Ranks r;
@@ -315,7 +387,7 @@ GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, con
             const uint32_t ones = ones_e - ones_s, zeros = (end - start) - ones;
             r.flipped = (fs.has(0) ? zeros : 0) + (fs.has(1) ? ones : 0);
         }
-    } else {
+    } else if (RUNS) {
         rank_runs<BD>(ix, d, symbol, fs, start, end, r);
     }
     return r;
@@ -614,12 +686,13 @@ GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32
 }
 
 // Step on a record with a body.
+template <bool RUNS>
 GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
     uint32_t rank = 0, edge_offset = 0;
     FlipSet fs;
     fs.lt = 0; fs.extra = NO_SYMBOL;
     if (!find_edge<false>(ix, d, next, rank, edge_offset, fs)) return false;
-    const Ranks r = rank_pair<false>(ix, d, rank, fs, start, end);
+    const Ranks r = rank_pair<false, RUNS>(ix, d, rank, fs, start, end);
     if (r.at_start >= r.at_end) return false;
     start = edge_offset + r.at_start; end = edge_offset + r.at_end;
     return true;
@@ -641,31 +714,11 @@ GBWT_HD bool next_record(const IndexView& ix, uint64_t node, uint64_t& rec, Desc
     return d.fmt() != FMT_EMPTY;
 }
 
-// Straight chain of steps. Lanes of a warp diverge on the record format; when the steps are cheap and
-// memory-bound (dense / single-edge records) that is what keeps more loads in flight.
-template <class Reader>
-GBWT_HD void query_find_extend_chain(const IndexView& ix, Reader& rd, uint64_t k, gbwt_b200_state& out) {
-    set_none(out);
-    if (k == 0) return;
-    const uint64_t first_node = ix.offset + 1;
-    uint64_t node = rd.node(0), rec = 0;
-    Desc d;
-    uint32_t start = 0, end = 0;
-    if (!find_first(ix, node, rec, d, start, end)) return;
-    for (uint64_t i = 1; i < k; i++) {
-        const uint64_t next = rd.node(i);
-        if (next < first_node) return;
-        const bool ok = d.fmt() == FMT_SINGLE ? follow_single(d, next, start, end) : follow_body(ix, d, next, start, end);
-        if (!ok) return;
-        node = next;
-        if (i + 1 < k && !next_record(ix, node, rec, d)) return;
-    }
-    out.node = node; out.start = start; out.end = end;
-}
-
-// Rounds: any number of single-edge records, then one record with a body, so that the lanes of a warp meet
-// again at the expensive step. This is the form for run-length bodies, where the scan dominates.
-template <class Reader>
+// The loop runs in rounds: any number of single-edge records (a few instructions each), then one record with
+// a body, so that the lanes of a warp meet again at the expensive rank step instead of diverging on the record
+// format (measured on B200 with tools/exp_find.py: 1.2x for dense bodies, 1.9x for run-length bodies over
+// the straight per-node chain).
+template <bool RUNS, class Reader>
 GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t k, gbwt_b200_state& out) {
     set_none(out);
     if (k == 0) return;
@@ -686,7 +739,7 @@ GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t 
         if (dead) return;
         if (i >= k) break;
         const uint64_t next = rd.node(i);
-        if (next < first_node || !follow_body(ix, d, next, start, end)) return;
+        if (next < first_node || !follow_body<RUNS>(ix, d, next, start, end)) return;
         node = next; i++;
         if (i < k && !next_record(ix, node, rec, d)) return;
     }
@@ -696,7 +749,7 @@ GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t 
 GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uint64_t k, gbwt_b200_state& out) {
     PlainReader rd;
     rd.p = pattern;
-    query_find_extend_rounds(ix, rd, k, out);
+    query_find_extend_rounds<true>(ix, rd, k, out);
 }
 
 // bd_find(path[first]), extend_forward over path(first, end), extend_backward over path[start, first) in

@@ -62,13 +62,6 @@ void hs_extend(const HostSim* h, const gbwt_b200_state* in, const uint64_t* node
 void hs_find_extend(const HostSim* h, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out) {
     for (size_t i = 0; i < n; i++) query_find_extend(h->view, patterns + i * k, k, out[i]);
 }
-void hs_find_extend_chain(const HostSim* h, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out) {
-    for (size_t i = 0; i < n; i++) {
-        PlainReader rd;
-        rd.p = patterns + i * k;
-        query_find_extend_chain(h->view, rd, k, out[i]);
-    }
-}
 void hs_bd_find(const HostSim* h, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out) {
     for (size_t i = 0; i < n; i++) gbwt_bd_find(h->view, nodes[i], out[i]);
 }

@@ -12,7 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--queries", type=int, default=1 << 25)
 ap.add_argument("--sites", type=int, default=3_333_333)
 ap.add_argument("--haplotypes", type=int, default=1024)
-ap.add_argument("--variants", default="0,1,2,3")
+ap.add_argument("--variants", default="3")
 ap.add_argument("--locality", default="0,1")
 ap.add_argument("--minblocks", default="1")
 ap.add_argument("--l2", default="32")
