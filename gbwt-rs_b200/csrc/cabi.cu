@@ -124,8 +124,11 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
         return launch_done("k_find_extend");
     }
     // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time
+    // About 256 queries per bucket (one CTA's worth), at most MAX_BUCKETS: small batches get few buckets so
+    // that the single-CTA scan stays negligible.
+    const uint64_t want_buckets = std::min<uint64_t>(MAX_BUCKETS, std::max<uint64_t>(256, n / 256));
     uint32_t shift = 0;
-    while (((ix->view.records - 1) >> shift) >= MAX_BUCKETS) shift++;
+    while (((ix->view.records - 1) >> shift) >= want_buckets) shift++;
     const uint32_t buckets = static_cast<uint32_t>(((ix->view.records - 1) >> shift) + 1);
     const size_t max_part = 0xFFFFFFFFull;
     for (size_t begin = 0; begin < n; begin += max_part) {

@@ -149,6 +149,27 @@ def test_wide_records(b200, sigma, bits, layout):
     assert np.array_equal(e.sequence_lengths(ids), g.sequence_lengths(ids))
 
 
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_locality_schedule_on_small_inputs(b200, layout, monkeypatch):
+    # The bucket pre-pass and the permuted kernel with tiny batches, non-matching patterns, out-of-range first
+    # nodes, batches that are not a multiple of anything, and more buckets than queries.
+    monkeypatch.setenv("GBWT_B200_LOCALITY", "1")
+    for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw, layout=layout)
+        pc.check_find_extend_subpaths(e, g)
+        pc.check_find_extend_random(e, g, n=4001, k=4, seed=11)
+        pats = np.array([[2**40, 22], [0, 0], [22, 2**63]], dtype=np.uint64)
+        assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
+    S, H, seed = 700, 300, 5
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)
+    for n in (1, 2, 255, 257, 70_001):
+        pats = synth.patterns(S, H, seed, n=n, k=32, q0=n)
+        assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
+    pc.check_find_extend_random(e, g, n=30_000, k=7, seed=2)
+
+
 def from_parts_of(b200, g, layout="auto"):
     return b200.GBWT.from_parts(g.sequences(), g.len(), g.alphabet_offset(), g.alphabet_size(), g.flags(),
                                 g.bwt_data(), g.record_starts(), layout=layout)
@@ -160,9 +181,14 @@ def test_from_parts_matches_from_bytes(b200):
     pc.check_everything(from_parts_of(b200, g), g)
 
 
+@pytest.mark.parametrize("locality", [None, "1"])
 @pytest.mark.parametrize("layout", ["auto", "runs"])
-def test_config3_shape_small(b200, layout):
-    # bubble chain like configs[2] (fewer sites so the oracle finishes in seconds): every query matches
+def test_config3_shape_small(b200, layout, locality, monkeypatch):
+    # bubble chain like configs[2] (fewer sites so the oracle finishes in seconds): every query matches.
+    # locality = "1" forces the bucketed schedule (counting sort by first record + permuted kernel), which
+    # the library otherwise only uses for indexes that do not fit L2.
+    if locality:
+        monkeypatch.setenv("GBWT_B200_LOCALITY", locality)
     S, H, seed = 4000, 64, 42
     img = synth.bubble_chain(S, H, seed)
     g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)
