@@ -77,7 +77,7 @@ def get_image(sites, haplotypes, rank, world, barrier):
     path = f"/dev/shm/gbwt_b200_bench_{sites}_{haplotypes}_{SEED}_{os.environ.get('MASTER_PORT', '0')}.gbwt"
     if rank == 0:
         t = time.time()
-        img = synth.bubble_chain(sites, haplotypes, SEED)
+        img = synth.bubble_chain(sites, haplotypes, SEED, threads=os.cpu_count() or 0)  # the other ranks wait
         img.array.tofile(path + ".tmp")
         os.replace(path + ".tmp", path)
         log(f"[bench] generated index image: {img.nbytes / 1e9:.2f} GB in {time.time() - t:.1f} s")
@@ -93,46 +93,61 @@ def get_image(sites, haplotypes, rank, world, barrier):
 # ---- clocks ---------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons while the timed region runs (B200_PROFILING.md)."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML every few milliseconds while the timed region
+    runs (the same fields as the nvidia-smi line of B200_PROFILING.md, without the process start-up latency,
+    so that even a 100 ms timed region gets samples)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.lines, self.proc = [], None
+    def __init__(self, cuda_index):
+        self.samples, self.handle, self.nv = [], None, None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.nv = pynvml
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as exc:
+            self.error = str(exc)
+            self.handle = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+    def _run(self):
+        nv, h = self.nv, self.handle
+        while not self._stop.is_set():
+            try:
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
-                continue
-            try:
-                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "error", "?")]}
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": float(self.sm_max), "reasons": ["no samples inside the timed region"]}
+        reasons = set()
+        for s in inside:
+            for bit, name in self.REASONS.items():
+                if s[3] & bit:
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": float(statistics.median(s[1] for s in inside)), "sm_max_mhz": float(self.sm_max),
+                "power_w_max": max(s[2] for s in inside), "samples": len(inside), "reasons": sorted(reasons),
+                "how": "NVML, 4 ms period, samples with timestamps inside the timed region only"}
 
 
 def measured_peak_gbs():
@@ -235,7 +250,7 @@ def main():
     import gbwt_rs_b200 as gb
     from synth import synth
     ncpu = os.cpu_count() or 8
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, ncpu // max(1, world))))
+    os.environ["GBWT_B200_BUILD_THREADS"] = str(max(1, ncpu // max(1, world)))  # K0 runs on every rank at once
 
     sites, haplotypes, Q = resolve_workload(args)
     image, keep = get_image(sites, haplotypes, rank, world, barrier)

@@ -229,6 +229,76 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_backward(IndexView ix, const 
     }
 }
 
+// Descriptor of the record of `node`, or an empty one when BWT::record() would be None.
+__device__ __forceinline__ Desc load_desc_of(const IndexView& ix, uint64_t node) {
+    Desc d;
+    d.a.x = d.a.y = d.a.z = d.a.w = d.b.x = d.b.y = d.b.z = d.b.w = 0;  // fmt() == FMT_EMPTY
+    uint64_t rec;
+    if (node >= ix.offset + 1 && record_of(ix, node, rec)) d = load_desc(ix, rec);
+    return d;
+}
+
+// GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568; Record::lf, src/bwt.rs:480-496): same results as
+// walk_sequence(), arranged so that a step costs one memory round trip instead of two or three. A walk is a
+// dependent chain, so its speed is 1 / (latency per step): the descriptor of the current record is always in
+// registers, and as soon as it arrives the descriptors of BOTH successors of an outdegree-2 record are
+// requested together with the body block that decides between them.
+__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap) {
+    if (id >= ix.sequences) return ~0ull;
+    gbwt_b200_pos pos;
+    if (!gbwt_start(ix, id, pos)) return 0;
+    uint64_t node = pos.node, offset = pos.offset, n = 0;
+    Desc d = load_desc_of(ix, node);
+    for (;;) {
+        if (n < cap) out[n] = node;
+        n++;
+        const uint32_t fmt = d.fmt();
+        if (fmt == FMT_EMPTY || offset >= d.total_len()) break;  // GBWT::forward -> None
+        const uint32_t i = static_cast<uint32_t>(offset);
+        uint32_t symbol, rank_i;
+        Edge e;
+        if (fmt == FMT_SINGLE) {
+            e.node = d.node0(); e.offset = d.offset0();
+            if (e.node == 0) break;
+            offset = static_cast<uint64_t>(e.offset) + i;
+            node = e.node;
+            d = load_desc_of(ix, node);
+            continue;
+        }
+        if (d.inline_edges()) {
+            // outdegree 2: both candidate descriptors are requested before the body decides
+            const Desc d0 = load_desc_of(ix, d.node0());
+            const Desc d1 = load_desc_of(ix, d.node1());
+            if (fmt == FMT_DENSE2) {
+                const uint32_t ones = dense_rank1(ix.bodies + d.body(), d.body_len(), i, symbol);
+                rank_i = symbol ? ones : i - ones;
+            } else {
+                symbol = symbol_at_runs(ix, d, i);
+                if (symbol == NO_SYMBOL) break;
+                FlipSet fs;
+                fs.lt = 0; fs.extra = NO_SYMBOL;
+                Ranks r;
+                r.at_start = r.at_end = r.flipped = 0;
+                rank_runs<false>(ix, d, symbol, fs, i, i, r);
+                rank_i = r.at_start;
+            }
+            e.node = symbol ? d.node1() : d.node0();
+            e.offset = symbol ? d.offset1() : d.offset0();
+            if (e.node == 0) break;
+            offset = static_cast<uint64_t>(e.offset) + rank_i;
+            node = e.node;
+            d = symbol ? d1 : d0;
+            continue;
+        }
+        gbwt_b200_pos cur, next;
+        cur.node = node; cur.offset = offset;
+        if (!gbwt_forward(ix, cur, next)) break;
+        node = next.node; offset = next.offset;
+        d = load_desc_of(ix, node);
+    }
+    return n;
+}
+
 // K3. A path walk is a dependent chain of LF steps (src/gbwt.rs:557-568): one thread per sequence, all
 // sequences of the batch in flight at once. Paths of a pangenome move through the same records at about the
 // same time, so after the first chain has pulled a record into L2 the others hit there.
@@ -244,7 +314,7 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
             dst = nodes + (lo - base);
             cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence(ix, __ldg(ids + i), dst, cap);
+        const uint64_t len = walk_sequence_device(ix, __ldg(ids + i), dst, cap);
         if (lengths != nullptr) lengths[i] = len;
     }
 }

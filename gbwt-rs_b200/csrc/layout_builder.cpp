@@ -3,7 +3,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../../include/gbwt_b200.h"
 
@@ -232,9 +236,17 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
     // BWT::len() is the number of record starts; GBWT ids are mapped with node - offset (src/gbwt.rs:150-152).
     auto rec_len = [&](uint64_t i) { return (i + 1 < R ? in.record_starts[i + 1] : in.bwt_len) - in.record_starts[i]; };
 
+    // Load-time work: use the host's processors (GBWT_B200_BUILD_THREADS overrides), not OMP_NUM_THREADS, which
+    // launchers such as torchrun pin to 1.
+    int threads = 1;
+#ifdef _OPENMP
+    threads = omp_get_num_procs();
+#endif
+    if (const char* e = std::getenv("GBWT_B200_BUILD_THREADS")) threads = std::max(1, std::atoi(e));
+    (void)threads;
     std::vector<Plan> plans(R);
     std::atomic<int> status{GBWT_B200_OK};
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
     for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
         plans[i] = plan_record(in.bwt + in.record_starts[i], rec_len(i), policy);
         if (plans[i].status != GBWT_B200_OK) status.store(plans[i].status);
@@ -255,7 +267,7 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
     out.desc.assign(R, RecordDesc{});
     out.bodies.assign(2 * body_at[R] + 2, 0);
     out.edges.assign(edge_at[R] + 1, Edge{0, 0});
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
     for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
         emit_record(in.bwt + in.record_starts[i], rec_len(i), plans[i], body_at[i], edge_at[i], out.desc[i],
                     out.bodies.data(), out.edges.data());

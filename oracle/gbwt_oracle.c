@@ -910,17 +910,17 @@ int64_t orc_sequence(const orc_gbwt* g, uint64_t id, uint64_t* out, uint64_t cap
 /* Batch drivers: dynamic scheduling over queries = the rayon par_iter analogue               */
 /* ------------------------------------------------------------------------------------------ */
 
+/* All processors of the host, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1). */
 int orc_max_threads(void) {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif
 }
 
 static int pick_threads(int threads) {
-    int m = orc_max_threads();
-    if (threads <= 0 || threads > m) return m;
+    if (threads <= 0) return orc_max_threads();
     return threads;
 }
 

@@ -302,8 +302,8 @@ static void emit_site(chunk_buf* cb, uint64_t seed, uint64_t S, uint64_t H, uint
 uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int threads, uint64_t* out_len) {
     if (S == 0 || H == 0 || H > 0xFFFFFFFFULL) return NULL;
 #ifdef _OPENMP
-    int maxt = omp_get_max_threads();
-    if (threads <= 0 || threads > maxt) threads = maxt;
+    /* all processors unless told otherwise: launchers such as torchrun export OMP_NUM_THREADS=1 */
+    if (threads <= 0) threads = omp_get_num_procs();
 #else
     threads = 1;
 #endif
@@ -444,8 +444,8 @@ void synth_sequence(uint64_t S, uint64_t H, uint64_t seed, uint64_t seq, uint64_
 void synth_patterns(uint64_t S, uint64_t H, uint64_t seed, uint64_t seed_q, uint64_t q0, uint64_t n, uint64_t k,
                     uint64_t* out, int threads) {
 #ifdef _OPENMP
-    int maxt = omp_get_max_threads();
-    if (threads <= 0 || threads > maxt) threads = maxt;
+    /* all processors unless told otherwise: launchers such as torchrun export OMP_NUM_THREADS=1 */
+    if (threads <= 0) threads = omp_get_num_procs();
 #else
     threads = 1;
 #endif
