@@ -195,8 +195,14 @@ int launch_backward(const gbwt_b200_index* ix, const gbwt_b200_pos* pos, size_t 
 int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
                    uint64_t* nodes, uint64_t* lengths, cudaStream_t s) {
     if (m == 0) return GBWT_B200_OK;
-    const int block = 32;  // one warp per CTA spreads the chains over the SMs
-    k_extract<<<static_cast<unsigned>((m + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths);
+    // One warp per CTA (spreads the chains over the SMs) and, up to 64 Ki chains, one chain per warp.
+    const int block = 32;
+    uint32_t stride = static_cast<uint32_t>(env_int("GBWT_B200_EXTRACT_STRIDE", m <= (size_t(1) << 16) ? 32 : 1));
+    if (stride != 1 && stride != 2 && stride != 4 && stride != 8 && stride != 16 && stride != 32) stride = 1;
+    const size_t threads = m * stride;
+    // How far ahead (in records) the walks ask L2 for the records they are heading to; 0 disables it.
+    const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
+    k_extract<<<static_cast<unsigned>((threads + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, stride, ahead);
     return launch_done("k_extract");
 }
 

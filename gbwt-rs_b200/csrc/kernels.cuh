@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_backward(IndexView ix, const 
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Descriptor of the record of `node`, or an empty one when BWT::record() would be None.
 __device__ __forceinline__ Desc load_desc_of(const IndexView& ix, uint64_t node) {
     Desc d;
@@ -243,18 +245,42 @@ __device__ __forceinline__ Desc load_desc_of(const IndexView& ix, uint64_t node)
 // dependent chain, so its speed is 1 / (latency per step): the descriptor of the current record is always in
 // registers, and as soon as it arrives the descriptors of BOTH successors of an outdegree-2 record are
 // requested together with the body block that decides between them.
-__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap) {
+__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap,
+                                                         uint32_t ahead) {
     if (id >= ix.sequences) return ~0ull;
     gbwt_b200_pos pos;
     if (!gbwt_start(ix, id, pos)) return 0;
     uint64_t node = pos.node, offset = pos.offset, n = 0;
     Desc d = load_desc_of(ix, node);
+    Desc pf;
+    pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
+    uint64_t prev_node = node;
     for (;;) {
         if (n < cap) out[n] = node;
         n++;
         const uint32_t fmt = d.fmt();
         if (fmt == FMT_EMPTY || offset >= d.total_len()) break;  // GBWT::forward -> None
         const uint32_t i = static_cast<uint32_t>(offset);
+        if (ahead != 0) {
+            // Sequences that walk the graph together arrive at a record together and would all wait for the
+            // same HBM miss. Node ids follow the graph's topological order, so the records a walk will need
+            // shortly lie a few records further in the direction it is moving: ask L2 for the descriptors
+            // 2 * ahead records away, and for the body of the descriptor `ahead` records away (loaded during the
+            // previous step, so reading its body offset does not wait).
+            const uint64_t rec = node - ix.offset;
+            const bool up = node >= prev_node;
+            prev_node = node;
+            const uint32_t pf_fmt = pf.fmt();
+            if (pf_fmt == FMT_DENSE2 || pf_fmt >= FMT_RUN8) {
+                prefetch_l2(ix.bodies + pf.body());
+                prefetch_l2(ix.bodies + pf.body() + 8);
+            }
+            const uint64_t near = up ? (rec + ahead < ix.records ? rec + ahead : ix.records - 1) : (rec > ahead ? rec - ahead : 0);
+            const uint64_t far = up ? (rec + 2 * ahead < ix.records ? rec + 2 * ahead : ix.records - 1)
+                                    : (rec > 2 * ahead ? rec - 2 * ahead : 0);
+            prefetch_l2(ix.desc + far);
+            pf = load_desc(ix, near);
+        }
         uint32_t symbol, rank_i;
         Edge e;
         if (fmt == FMT_SINGLE) {
@@ -303,10 +329,15 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
 // sequences of the batch in flight at once. Paths of a pangenome move through the same records at about the
 // same time, so after the first chain has pulled a record into L2 the others hit there.
 // `nodes == nullptr` only counts (GBWT::sequence(id).count()).
+// `stride` threads per chain (only the first of them walks): with one chain per warp a step waits for its own
+// loads only, not for the slowest of 32 unrelated chains, and the warp does not serialise 32 divergent paths.
 __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
                                                  const uint64_t* __restrict__ out_offsets, uint64_t base,
-                                                 uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
-    GBWT_GRID_STRIDE(i, m) {
+                                                 uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t stride,
+                                                 uint32_t ahead) {
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid % stride != 0) return;
+    for (size_t i = tid / stride; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / stride) {
         uint64_t* dst = nullptr;
         uint64_t cap = 0;
         if (nodes != nullptr) {
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
             dst = nodes + (lo - base);
             cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_device(ix, __ldg(ids + i), dst, cap);
+        const uint64_t len = walk_sequence_device(ix, __ldg(ids + i), dst, cap, ahead);
         if (lengths != nullptr) lengths[i] = len;
     }
 }

@@ -49,3 +49,7 @@ nodes = torch.empty(m * L, dtype=torch.int64, device=dev)
 lens = torch.empty(m, dtype=torch.int64, device=dev)
 ms = timed(lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream), reps=2)
 print(json.dumps({"op": f"extract {m} paths", "ms": ms, "steps_per_s": m * L / ms * 1e3, "ok": bool(torch.all(lens == L).item())}), flush=True)
+for ahead in ("0", "12", "48", "192", "768"):
+    os.environ["GBWT_B200_EXTRACT_AHEAD"] = ahead
+    ms = timed(lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream), reps=1)
+    print(json.dumps({"op": f"extract {m} paths, ahead {ahead}", "ms": ms, "steps_per_s": m * L / ms * 1e3}), flush=True)
