@@ -69,6 +69,8 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_extend_forward": (i, [p, p, p, sz, p]),
         "gbwt_b200_extend_backward": (i, [p, p, p, sz, p]),
         "gbwt_b200_bd_search": (i, [p, p, p, p, p, p, sz, p]),
+        "gbwt_b200_follow": (i, [p, p, sz, i, p, p, p]),
+        "gbwt_b200_follow_device": (i, [p, p, sz, i, p, p, p, p]),
         "gbwt_b200_start": (i, [p, p, sz, p]),
         "gbwt_b200_forward": (i, [p, p, sz, p]),
         "gbwt_b200_backward": (i, [p, p, sz, p]),
@@ -333,6 +335,34 @@ class GBWT:
         out = np.zeros(n, BDSTATE_DTYPE)
         self._check(_lib.gbwt_b200_bd_search(self._h, _ptr(nodes), _ptr(offsets), _ptr(first), _ptr(start), _ptr(end), n, _ptr(out)))
         return out
+
+    def follow(self, states, backward: bool = False):
+        """All non-empty single-node extensions of each state (GBZ::follow_forward / follow_backward,
+        src/gbz.rs:519-544): returns (offsets, extensions, counts), counts[i] = 2^64-1 where the reference is None."""
+        states = np.ascontiguousarray(states, dtype=BDSTATE_DTYPE)
+        n = len(states)
+        counts = np.zeros(n, np.uint64)
+        self._check(_lib.gbwt_b200_follow(self._h, _ptr(states), n, int(backward), None, None, _ptr(counts)))
+        sizes = np.where(counts == _U64MAX, np.uint64(0), counts)
+        offsets = np.zeros(n + 1, np.uint64)
+        np.cumsum(sizes, out=offsets[1:])
+        out = np.zeros(int(offsets[-1]), BDSTATE_DTYPE)
+        self._check(_lib.gbwt_b200_follow(self._h, _ptr(states), n, int(backward), _ptr(offsets), _ptr(out), _ptr(counts)))
+        return offsets, out, counts
+
+    def follow_forward(self, state):
+        """GBZ::follow_forward for one state: list of BidirectionalState, or None."""
+        return self._follow_one(state, False)
+
+    def follow_backward(self, state):
+        return self._follow_one(state, True)
+
+    def _follow_one(self, state: "BidirectionalState", backward: bool):
+        st = np.array([(_state_rec(state.forward), _state_rec(state.reverse))], dtype=BDSTATE_DTYPE)
+        _, out, counts = self.follow(st, backward)
+        if counts[0] == _U64MAX:
+            return None
+        return [_bd_obj(o) for o in out]
 
     # -- sequence navigation (src/gbwt.rs:213-261) --
     def start(self, seq_id):

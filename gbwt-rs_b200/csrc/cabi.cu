@@ -177,6 +177,12 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
     k_bd_search<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, n, out);
     return launch_done("k_bd_search");
 }
+int launch_follow(const gbwt_b200_index* ix, const gbwt_b200_bdstate* st, size_t n, int backward, const uint64_t* out_offsets,
+                  uint64_t base, gbwt_b200_bdstate* out, uint64_t* counts, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_follow<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, st, n, backward, out_offsets, base, out, counts);
+    return launch_done("k_follow");
+}
 int launch_start(const gbwt_b200_index* ix, const uint64_t* ids, size_t n, gbwt_b200_pos* out, cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
     k_start<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, ids, n, out);
@@ -536,6 +542,13 @@ int gbwt_b200_bd_search_device(const gbwt_b200_index* ix, const uint64_t* d_node
     if (int rc = check_bidirectional(ix)) return rc;
     return launch_bd_search(ix, d_nodes, d_offsets, 0, d_first, d_start, d_end, n, d_out, static_cast<cudaStream_t>(stream));
 }
+int gbwt_b200_follow_device(const gbwt_b200_index* ix, const gbwt_b200_bdstate* d_states, size_t n, int backward,
+                            const uint64_t* d_out_offsets, gbwt_b200_bdstate* d_out, uint64_t* d_counts, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_bidirectional(ix)) return rc;
+    if (d_out != nullptr && d_out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null out_offsets");
+    return launch_follow(ix, d_states, n, backward, d_out_offsets, 0, d_out, d_counts, static_cast<cudaStream_t>(stream));
+}
 int gbwt_b200_forward_device(const gbwt_b200_index* ix, const gbwt_b200_pos* d_positions, size_t n, gbwt_b200_pos* d_out, void* stream) {
     DEVICE_ENTRY_PROLOGUE(ix);
     return launch_forward(ix, d_positions, n, d_out, static_cast<cudaStream_t>(stream));
@@ -630,6 +643,64 @@ int gbwt_b200_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const 
                       [&](uint64_t* d_nodes, uint64_t* d_offsets, uint64_t base, std::vector<uint64_t*>& side, size_t count, void* d_out, cudaStream_t s) {
         return launch_bd_search(ix, d_nodes, d_offsets, base, side[0], side[1], side[2], count, static_cast<gbwt_b200_bdstate*>(d_out), s);
     });
+}
+
+int gbwt_b200_follow(const gbwt_b200_index* ix, const gbwt_b200_bdstate* states, size_t n, int backward, const uint64_t* out_offsets,
+                     gbwt_b200_bdstate* out, uint64_t* counts) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_bidirectional(ix)) return rc;
+    if (n == 0) return GBWT_B200_OK;
+    if (states == nullptr || (out != nullptr && out_offsets == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    if (out == nullptr) {
+        if (counts == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null array");
+        std::vector<HostArray> arrays = {{states, nullptr, sizeof(gbwt_b200_bdstate)}, {nullptr, counts, 8}};
+        return run_chunked(ix, n, arrays, chunk_for(sizeof(gbwt_b200_bdstate)), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+            return launch_follow(ix, static_cast<gbwt_b200_bdstate*>(d[0]), count, backward, nullptr, 0, nullptr, static_cast<uint64_t*>(d[1]), s);
+        });
+    }
+    if (!offsets_valid(out_offsets, n)) return fail(GBWT_B200_E_ARGUMENT, "out_offsets must be non-decreasing");
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = GBWT_B200_OK;
+    const uint64_t out_budget = uint64_t(4) << 20;  // extensions per chunk
+    for (size_t i0 = 0; i0 < n && rc == GBWT_B200_OK;) {
+        const size_t i1 = ragged_chunk_end(out_offsets, n, i0, size_t(1) << 20, out_budget);
+        const size_t count = i1 - i0;
+        const uint64_t base = out_offsets[i0], cap = out_offsets[i1] - base;
+        gbwt_b200_bdstate *d_states = nullptr, *d_out = nullptr;
+        uint64_t *d_offsets = nullptr, *d_counts = nullptr;
+        auto alloc = [&](void** p, size_t bytes) {
+            cudaError_t e = cudaMallocAsync(p, std::max<size_t>(16, bytes), s);
+            if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaMallocAsync");
+        };
+        alloc(reinterpret_cast<void**>(&d_states), count * sizeof(gbwt_b200_bdstate));
+        alloc(reinterpret_cast<void**>(&d_out), cap * sizeof(gbwt_b200_bdstate));
+        alloc(reinterpret_cast<void**>(&d_offsets), (count + 1) * 8);
+        alloc(reinterpret_cast<void**>(&d_counts), count * 8);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(d_states, states + i0, count * sizeof(gbwt_b200_bdstate), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, out_offsets + i0, (count + 1) * 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+        }
+        if (rc == GBWT_B200_OK) rc = launch_follow(ix, d_states, count, backward, d_offsets, base, d_out, d_counts, s);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaSuccess;
+            if (cap > 0) e = cudaMemcpyAsync(out + base, d_out, cap * sizeof(gbwt_b200_bdstate), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && counts != nullptr) e = cudaMemcpyAsync(counts + i0, d_counts, count * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        if (d_states) cudaFreeAsync(d_states, s);
+        if (d_out) cudaFreeAsync(d_out, s);
+        if (d_offsets) cudaFreeAsync(d_offsets, s);
+        if (d_counts) cudaFreeAsync(d_counts, s);
+        i0 = i1;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(s);
+    return rc;
 }
 
 int gbwt_b200_start(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t n, gbwt_b200_pos* out) {

@@ -200,6 +200,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_search(IndexView ix, const
     }
 }
 
+// All extensions of a state (GBZ::follow_forward / follow_backward): one thread per state; `out == nullptr` only counts.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_follow(IndexView ix, const gbwt_b200_bdstate* __restrict__ states, size_t n,
+                                                           int backward, const uint64_t* __restrict__ out_offsets, uint64_t base,
+                                                           gbwt_b200_bdstate* __restrict__ out, uint64_t* __restrict__ counts) {
+    GBWT_GRID_STRIDE(q, n) {
+        gbwt_b200_bdstate* dst = nullptr;
+        uint64_t cap = 0;
+        if (out != nullptr) {
+            const uint64_t lo = __ldg(out_offsets + q), hi = __ldg(out_offsets + q + 1);
+            dst = out + (lo - base);
+            cap = hi > lo ? hi - lo : 0;
+        }
+        const gbwt_b200_bdstate st = states[q];
+        const uint64_t c = gbwt_follow_all(ix, st, backward != 0, dst, cap);
+        if (counts != nullptr) counts[q] = c;
+    }
+}
+
 __global__ void __launch_bounds__(BLOCK_THREADS) k_start(IndexView ix, const uint64_t* __restrict__ ids, size_t n,
                                                           gbwt_b200_pos* __restrict__ out) {
     GBWT_GRID_STRIDE(q, n) {

@@ -663,6 +663,53 @@ GBWT_HD bool gbwt_backward(const IndexView& ix, const gbwt_b200_pos& pos, gbwt_b
     return true;
 }
 
+// ---- all extensions of a state (GBZ::follow_forward / follow_backward, src/gbz.rs:519-544, 1223-1231) --------
+
+// Every non-empty single-node extension of `state` in edge order (EdgeIter, src/gbz.rs:835-861: an edge to the
+// endmarker is skipped), each computed like GBWT::bd_internal (src/gbwt.rs:370-384); backward = the same on the
+// flipped state with the results flipped back. Writes at most `cap` states and returns their number, or
+// UINT64_MAX where the reference returns None (GBZ::has_node fails or the record does not exist).
+GBWT_HD uint64_t gbwt_follow_all(const IndexView& ix, const gbwt_b200_bdstate& state, bool backward,
+                                 gbwt_b200_bdstate* out, uint64_t cap) {
+    const gbwt_b200_state fwd = backward ? state.reverse : state.forward;
+    const gbwt_b200_state rev = backward ? state.forward : state.reverse;
+    // GBZ::has_node (src/gbz.rs:286-289): the forward orientation is in the alphabet and has a record
+    const uint64_t forward_node = fwd.node & ~1ull;
+    uint64_t rec;
+    if (!(forward_node > ix.offset && forward_node < ix.alphabet_size) || !record_of(ix, forward_node, rec)) return ~0ull;
+    if (load_desc(ix, rec).fmt() == FMT_EMPTY) return ~0ull;
+    if (!record_of(ix, fwd.node, rec)) return ~0ull;
+    const Desc d = load_desc(ix, rec);
+    if (d.fmt() == FMT_EMPTY) return ~0ull;
+    const uint32_t sigma = d.sigma();
+    const uint32_t total = d.total_len();
+    uint64_t n = 0;
+    if (fwd.start >= fwd.end) return 0;  // bd_follow: an empty range has no extensions
+    const uint32_t s = fwd.start > total ? total : static_cast<uint32_t>(fwd.start);
+    const uint32_t e = fwd.end > total ? total : static_cast<uint32_t>(fwd.end);
+    for (uint32_t rank = 0; rank < sigma; rank++) {
+        const Edge edge = edge_at(ix, d, rank);
+        if (edge.node == 0) continue;  // EdgeIter::new skips the endmarker (always rank 0); bd_follow rejects it too
+        FlipSet fs;
+        fs.lt = rank; fs.extra = NO_SYMBOL;
+        if ((edge.node & 1) != 0 && rank > 0 && edge_at(ix, d, rank - 1).node == edge.node - 1) fs.lt = rank - 1;
+        if ((edge.node & 1) == 0 && rank + 1 < sigma && edge_at(ix, d, rank + 1).node == edge.node + 1) fs.extra = rank + 1;
+        const Ranks r = rank_pair<true>(ix, d, rank, fs, s, e);
+        if (r.at_start >= r.at_end) continue;
+        gbwt_b200_bdstate next;
+        next.forward.node = edge.node;
+        next.forward.start = static_cast<uint64_t>(edge.offset) + r.at_start;
+        next.forward.end = static_cast<uint64_t>(edge.offset) + r.at_end;
+        next.reverse.node = rev.node;
+        next.reverse.start = rev.start + r.flipped;
+        next.reverse.end = next.reverse.start + (r.at_end - r.at_start);
+        if (backward) { const gbwt_b200_state t = next.forward; next.forward = next.reverse; next.reverse = t; }
+        if (n < cap) out[n] = next;
+        n++;
+    }
+    return n;
+}
+
 // ---- whole queries ---------------------------------------------------------------------------------
 
 // ---- find + extends for one pattern -------------------------------------------------------------------

@@ -136,6 +136,11 @@ public:
         return to_bd(out);
     }
 
+    // GBZ::follow_forward / follow_backward (src/gbz.rs:519-544): all non-empty single-node extensions of a state
+    // in edge order; nullopt where the reference returns None (the node does not exist).
+    std::optional<std::vector<BidirectionalState>> follow_forward(const BidirectionalState& state) const { return follow(state, 0); }
+    std::optional<std::vector<BidirectionalState>> follow_backward(const BidirectionalState& state) const { return follow(state, 1); }
+
     // Batched forms (what the kernels are for). Results use the C ABI value types; None = empty range.
     std::vector<gbwt_b200_state> find_extend_batch(const std::vector<uint64_t>& patterns, std::size_t k) const {
         std::size_t n = k ? patterns.size() / k : 0;
@@ -161,6 +166,18 @@ public:
     }
 
 private:
+    std::optional<std::vector<BidirectionalState>> follow(const BidirectionalState& state, int backward) const {
+        gbwt_b200_bdstate in{from_state(state.forward), from_state(state.reverse)};
+        uint64_t count = 0;
+        check(gbwt_b200_follow(h_, &in, 1, backward, nullptr, nullptr, &count));
+        if (count == UINT64_MAX) return std::nullopt;
+        std::vector<gbwt_b200_bdstate> raw(count);
+        const uint64_t offsets[2] = {0, count};
+        check(gbwt_b200_follow(h_, &in, 1, backward, offsets, raw.data(), &count));
+        std::vector<BidirectionalState> out;
+        for (const auto& r : raw) out.push_back(*to_bd(r));
+        return out;
+    }
     explicit GBWT(gbwt_b200_index* h) : h_(h) {}
     void reset() { if (h_) gbwt_b200_index_destroy(h_); h_ = nullptr; }
     static void check(int rc) {

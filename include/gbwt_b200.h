@@ -127,6 +127,14 @@ GBWT_B200_API int gbwt_b200_bd_search(const gbwt_b200_index* index, const uint64
                                      const uint64_t* first, const uint64_t* start, const uint64_t* end, size_t n,
                                      gbwt_b200_bdstate* out);
 
+/* GBZ::follow_forward / follow_backward with StateIter (src/gbz.rs:519-544, 1211-1249), at the GBWT level: all
+ * non-empty single-node extensions of each state, in edge order (EdgeIter, src/gbz.rs:835-861). counts[i] receives
+ * the number of extensions of state i, UINT64_MAX where the reference returns None (no such node). When `out` is
+ * not NULL the extensions of state i are written to out[out_offsets[i] ..], at most
+ * out_offsets[i+1] - out_offsets[i] of them; call once with out == NULL to size the output. */
+GBWT_B200_API int gbwt_b200_follow(const gbwt_b200_index* index, const gbwt_b200_bdstate* states, size_t n, int backward,
+                                  const uint64_t* out_offsets, gbwt_b200_bdstate* out, uint64_t* counts);
+
 /* ---- sequence navigation ---------------------------------------------------------------------- */
 /* GBWT::start (src/gbwt.rs:213-219). */
 GBWT_B200_API int gbwt_b200_start(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t n, gbwt_b200_pos* out);
@@ -164,6 +172,9 @@ GBWT_B200_API int gbwt_b200_bd_extend_device(const gbwt_b200_index* index, const
 GBWT_B200_API int gbwt_b200_bd_search_device(const gbwt_b200_index* index, const uint64_t* d_nodes,
                                             const uint64_t* d_offsets, const uint64_t* d_first, const uint64_t* d_start,
                                             const uint64_t* d_end, size_t n, gbwt_b200_bdstate* d_out, void* stream);
+GBWT_B200_API int gbwt_b200_follow_device(const gbwt_b200_index* index, const gbwt_b200_bdstate* d_states, size_t n,
+                                         int backward, const uint64_t* d_out_offsets, gbwt_b200_bdstate* d_out,
+                                         uint64_t* d_counts, void* stream);
 GBWT_B200_API int gbwt_b200_forward_device(const gbwt_b200_index* index, const gbwt_b200_pos* d_positions, size_t n,
                                           gbwt_b200_pos* d_out, void* stream);
 GBWT_B200_API int gbwt_b200_sequence_lengths_device(const gbwt_b200_index* index, const uint64_t* d_seq_ids, size_t m,

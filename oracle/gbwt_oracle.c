@@ -1125,3 +1125,58 @@ uint64_t orc_extract_bytes(const orc_gbwt* g, const uint64_t* ids, uint64_t m, i
     }
     return total;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* All extensions of a state: GBZ::follow_forward / follow_backward    */
+/* ------------------------------------------------------------------------------------------ */
+
+/* GBZ::has_node, src/gbz.rs:286-289: the forward GBWT node is in the alphabet and its record is non-empty
+ * (the real_nodes bit set at load from BWT::id_iter, src/gbz.rs:695-704, src/bwt.rs:310-316). */
+static int gbz_has_node(const orc_gbwt* g, uint64_t node_id) {
+    uint64_t gbwt_node = 2 * node_id;
+    if (!orc_has_node(g, gbwt_node)) return 0;
+    uint64_t start, limit;
+    bwt_record_bytes(&g->bwt, gbwt_node - g->offset, &start, &limit);
+    return limit > start && g->bwt.data[start] != 0;
+}
+
+/* GBZ::follow_forward / follow_backward + StateIter::next (src/gbz.rs:519-544, 1223-1231) over
+ * EdgeIter (src/gbz.rs:835-861): every successor of the last node in edge order, skipping an edge to the
+ * endmarker, extended with GBWT::bd_internal; backward = the same on the flipped state, results flipped back.
+ * Writes at most cap states; returns their number, or -1 where the reference returns None. */
+int64_t orc_follow(const orc_gbwt* g, const orc_bdstate* state, int backward, orc_bdstate* out, uint64_t cap) {
+    orc_bdstate st = *state;
+    if (backward) { st.forward = state->reverse; st.reverse = state->forward; }
+    if (!gbz_has_node(g, st.forward.node / 2)) return -1;        /* GBZ::successors, src/gbz.rs:327-335 */
+    orc_record rec;
+    uint64_t rid;
+    if (!node_to_record(g, st.forward.node, &rid) || !bwt_record(&g->bwt, rid, &rec)) return -1;
+    uint64_t n = 0;
+    uint64_t rank = (rec.sigma > 0 && rec.edges[0].node == ORC_ENDMARKER) ? 1 : 0; /* EdgeIter::new */
+    for (; rank < rec.sigma; rank++) {
+        orc_bdstate next;
+        if (!bd_internal(&rec, &st, rec.edges[rank].node, &next)) continue;
+        if (backward) { orc_state t = next.forward; next.forward = next.reverse; next.reverse = t; }
+        if (n < cap) out[n] = next;
+        n++;
+    }
+    record_drop(&rec);
+    return (int64_t)n;
+}
+
+void orc_follow_counts(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, int backward, uint64_t* counts, int threads) {
+    int t = pick_threads(threads); (void)t;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(t)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        int64_t c = orc_follow(g, &states[i], backward, NULL, 0);
+        counts[i] = c < 0 ? UINT64_MAX : (uint64_t)c;
+    }
+}
+
+void orc_follow_batch(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, int backward, const uint64_t* offsets,
+                      orc_bdstate* out, int threads) {
+    int t = pick_threads(threads); (void)t;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(t)
+    for (int64_t i = 0; i < (int64_t)n; i++)
+        (void)orc_follow(g, &states[i], backward, out + offsets[i], offsets[i + 1] - offsets[i]);
+}

@@ -128,6 +128,12 @@ void orc_extract_batch(const orc_gbwt* g, const uint64_t* ids, uint64_t m, const
                        uint64_t* nodes, int threads);
 int orc_max_threads(void);
 
+/* ---- all extensions of a state: GBZ::follow_forward / follow_backward + StateIter (src/gbz.rs:519-544, 1223-1231) */
+int64_t orc_follow(const orc_gbwt* g, const orc_bdstate* state, int backward, orc_bdstate* out, uint64_t cap);
+void orc_follow_counts(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, int backward, uint64_t* counts, int threads);
+void orc_follow_batch(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, int backward, const uint64_t* offsets,
+                      orc_bdstate* out, int threads);
+
 /* ---- algorithmic-byte accounting of SURVEY.md 8(d) (measurement helper for bench.py) ------------ */
 uint64_t orc_find_extend_bytes(const orc_gbwt* g, const uint64_t* patterns, uint64_t n, uint64_t k, int threads);
 uint64_t orc_extract_bytes(const orc_gbwt* g, const uint64_t* ids, uint64_t m, int threads);

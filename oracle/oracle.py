@@ -115,6 +115,10 @@ def lib(native: bool = False) -> C.CDLL:
         L.orc_forward_batch.argtypes = [p, p, u64, p, C.c_int]
         L.orc_sequence_lengths.argtypes = [p, p, u64, p, C.c_int]
         L.orc_extract_batch.argtypes = [p, p, u64, p, p, C.c_int]
+        L.orc_follow.restype = C.c_int64
+        L.orc_follow.argtypes = [p, C.POINTER(BDState), C.c_int, p, u64]
+        L.orc_follow_counts.argtypes = [p, p, u64, C.c_int, p, C.c_int]
+        L.orc_follow_batch.argtypes = [p, p, u64, C.c_int, p, p, C.c_int]
         L.orc_find_extend_bytes.restype = u64
         L.orc_find_extend_bytes.argtypes = [p, p, u64, u64, C.c_int]
         L.orc_extract_bytes.restype = u64
@@ -418,6 +422,30 @@ class GBWT:
         if rc < 0:
             raise AssertionError("Bidirectional search requires a bidirectional GBWT")
         return out
+
+    def follow(self, state, backward: bool = False):
+        """GBZ::follow_forward / follow_backward (src/gbz.rs:519-544): list of extensions, or None."""
+        s = BDState(State(*state[0]), State(*state[1]))
+        n = self._L.orc_follow(self._h, C.byref(s), 1 if backward else 0, None, 0)
+        if n < 0:
+            return None
+        out = np.zeros(n, dtype=BDSTATE_DTYPE)
+        self._L.orc_follow(self._h, C.byref(s), 1 if backward else 0, _ptr(out), n)
+        return [((int(o["forward"]["node"]), int(o["forward"]["start"]), int(o["forward"]["end"])),
+                 (int(o["reverse"]["node"]), int(o["reverse"]["start"]), int(o["reverse"]["end"]))) for o in out]
+
+    def follow_batch(self, states: np.ndarray, backward: bool = False, threads: int = 0):
+        """Returns (offsets, extensions, counts); counts[i] = 2^64-1 where the reference returns None."""
+        states = np.ascontiguousarray(states, dtype=BDSTATE_DTYPE)
+        n = len(states)
+        counts = np.zeros(n, dtype=np.uint64)
+        self._L.orc_follow_counts(self._h, _ptr(states), n, 1 if backward else 0, _ptr(counts), threads)
+        sizes = np.where(counts == np.uint64(2**64 - 1), np.uint64(0), counts)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=offsets[1:])
+        out = np.zeros(int(offsets[-1]), dtype=BDSTATE_DTYPE)
+        self._L.orc_follow_batch(self._h, _ptr(states), n, 1 if backward else 0, _ptr(offsets), _ptr(out), threads)
+        return offsets, out, counts
 
     def forward_batch(self, positions: np.ndarray, threads: int = 0) -> np.ndarray:
         positions = np.ascontiguousarray(positions, dtype=POS_DTYPE)

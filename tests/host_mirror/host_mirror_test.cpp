@@ -48,6 +48,19 @@ int main(int argc, char** argv) {
         bd = index.extend_forward(*bd, encode_node(15, false));
         CHECK(bd && bd->forward.node == encode_node(15, false) && bd->reverse.node == encode_node(12, true) && bd->len() == 2);
         CHECK(bd->from() == std::make_pair(std::size_t(12), false) && bd->to() == std::make_pair(std::size_t(15), false));
+        // all extensions of a state (StateIter doc-test, gbz.rs:1189-1208)
+        auto st14 = index.bd_find(encode_node(14, false));
+        auto successors = index.follow_forward(*st14);
+        CHECK(successors && successors->size() == 2);
+        std::size_t preds = 0;
+        for (const auto& s : *successors) {
+            auto p = index.follow_backward(s);
+            CHECK(p && p->size() == 1);
+            preds += p->size();
+            if (s.forward.node == encode_node(15, false)) CHECK((*p)[0].from() == std::make_pair(std::size_t(12), false) && (*p)[0].len() == 2);
+            else CHECK((*p)[0].from() == std::make_pair(std::size_t(13), false) && (*p)[0].to() == std::make_pair(std::size_t(16), false) && (*p)[0].len() == 1);
+        }
+        CHECK(preds == 2);
         // sequence iterator (gbwt.rs:546-548)
         auto path = index.sequence(7);
         CHECK(path && *path == (std::vector<std::size_t>{35, 33, 29, 27, 23}));

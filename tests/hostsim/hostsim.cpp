@@ -78,6 +78,14 @@ void hs_bd_search(const HostSim* h, const uint64_t* nodes, const uint64_t* offse
     for (size_t i = 0; i < n; i++)
         query_bd_search(h->view, nodes + offsets[i], offsets[i + 1] - offsets[i], first[i], start[i], end[i], out[i]);
 }
+void hs_follow(const HostSim* h, const gbwt_b200_bdstate* states, size_t n, int backward, const uint64_t* offsets,
+               gbwt_b200_bdstate* out, uint64_t* counts) {
+    for (size_t i = 0; i < n; i++) {
+        gbwt_b200_bdstate* dst = out ? out + offsets[i] : nullptr;
+        uint64_t cap = out ? offsets[i + 1] - offsets[i] : 0;
+        counts[i] = gbwt_follow_all(h->view, states[i], backward != 0, dst, cap);
+    }
+}
 void hs_start(const HostSim* h, const uint64_t* ids, size_t n, gbwt_b200_pos* out) {
     for (size_t i = 0; i < n; i++) gbwt_start(h->view, ids[i], out[i]);
 }

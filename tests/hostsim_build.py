@@ -50,6 +50,7 @@ def lib():
         L.hs_bd_find.argtypes = [p, p, C.c_size_t, p]
         L.hs_bd_extend.argtypes = [p, p, p, C.c_size_t, C.c_int, p]
         L.hs_bd_search.argtypes = [p, p, p, p, p, p, C.c_size_t, p]
+        L.hs_follow.argtypes = [p, p, C.c_size_t, C.c_int, p, p, p]
         L.hs_start.argtypes = [p, p, C.c_size_t, p]
         L.hs_forward.argtypes = [p, p, C.c_size_t, p]
         L.hs_backward.argtypes = [p, p, C.c_size_t, p]
@@ -134,6 +135,18 @@ class HostSim:
         out = np.zeros(len(first), BDSTATE)
         self._L.hs_bd_search(self._h, _p(nodes), _p(offsets), _p(first), _p(start), _p(end), len(first), _p(out))
         return out
+
+    def follow(self, states, backward=False):
+        states = np.ascontiguousarray(states, BDSTATE); n = len(states)
+        counts = np.zeros(n, np.uint64)
+        self._L.hs_follow(self._h, _p(states), n, int(backward), None, None, _p(counts))
+        sizes = np.where(counts == np.uint64(2**64 - 1), np.uint64(0), counts)
+        offsets = np.zeros(n + 1, np.uint64); np.cumsum(sizes, out=offsets[1:])
+        out = np.zeros(int(offsets[-1]), BDSTATE)
+        again = np.zeros(n, np.uint64)
+        self._L.hs_follow(self._h, _p(states), n, int(backward), _p(offsets), _p(out), _p(again))
+        assert np.array_equal(again, counts)
+        return offsets, out, counts
 
     def start(self, ids):
         ids = _u64(ids); out = np.zeros(len(ids), POS)

@@ -161,6 +161,49 @@ def check_navigation(engine, g):
     assert np.all(got[g.sequences():] == U64MAX)
 
 
+def check_follow(engine, g, max_rounds=6):
+    """src/gbz/tests.rs:100-168 (check_states): breadth-first over the states reachable from every node, all
+    forward and backward extensions of every state against the oracle, and the oracle's follow() against
+    extend_forward / extend_backward over the successors (the reference test's own truth)."""
+    nodes = np.arange(g.alphabet_size() + 2, dtype=np.uint64)
+    frontier = g.bd_find_batch(nodes)
+    seen = set()
+    total = 0
+    for _ in range(max_rounds):
+        if len(frontier) == 0:
+            break
+        nxt = []
+        for backward in (False, True):
+            offsets, want, counts = g.follow_batch(frontier, backward=backward)
+            got_offsets, got, got_counts = engine.follow(frontier, backward)
+            assert np.array_equal(got_counts, counts) and np.array_equal(got_offsets, offsets)
+            assert states_equal(got, want)
+            total += len(want)
+            nxt.append(want)
+        # the reference's own truth on a sample: follow == non-empty extend_* over every node id
+        for st in frontier[:: max(1, len(frontier) // 8)]:
+            tup = ((int(st["forward"]["node"]), int(st["forward"]["start"]), int(st["forward"]["end"])),
+                   (int(st["reverse"]["node"]), int(st["reverse"]["start"]), int(st["reverse"]["end"])))
+            if tup[0][2] <= tup[0][1]:
+                continue
+            found = g.follow(tup)
+            if found is None:
+                continue
+            truth = [x for x in (g.extend_forward(tup, int(v)) for v in range(g.alphabet_size())) if x is not None]
+            assert sorted(found) == sorted(truth)
+        new = np.concatenate(nxt) if nxt else np.zeros(0, orc.BDSTATE_DTYPE)
+        keep = []
+        for row in new:
+            key = row.tobytes()
+            if key not in seen:
+                seen.add(key)
+                keep.append(row)
+        frontier = np.array(keep, dtype=orc.BDSTATE_DTYPE) if keep else np.zeros(0, orc.BDSTATE_DTYPE)
+        if len(frontier) > 3000:
+            frontier = frontier[:3000]
+    return total
+
+
 def check_everything(engine, g):
     check_find_all_nodes(engine, g)
     check_extend_all_pairs(engine, g)
@@ -168,4 +211,5 @@ def check_everything(engine, g):
     check_find_extend_random(engine, g)
     if g.is_bidirectional():
         check_bd(engine, g)
+        check_follow(engine, g)
     check_navigation(engine, g)

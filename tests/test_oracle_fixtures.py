@@ -202,6 +202,45 @@ def test_doc_examples():
     assert g.backward(last)[0] == gv.encode_node(15)
 
 
+def test_follow_doc_example():
+    # StateIter doc-test, src/gbz.rs:1189-1208, and the probe values of SURVEY.md App. B.6
+    g = load("example.gbz")
+    d = gv.DOC_STATEITER
+    state = g.bd_find(gv.encode_node(d["node"]))
+    assert state[0][2] - state[0][1] == d["len"]
+    successors = g.follow(state)
+    assert len(successors) == d["successors"]
+    assert successors == [((30, 0, 2), (29, 0, 2)), ((32, 0, 1), (29, 2, 3))]
+    predecessors = []
+    for s in successors:
+        for p in g.follow(s, backward=True):
+            frm, to = p[1][0] ^ 1, p[0][0]
+            predecessors.append(((frm // 2, bool(frm & 1)), (to // 2, bool(to & 1)), p[0][2] - p[0][1]))
+    assert predecessors == d["predecessors"]
+    assert g.follow(((36, 0, 1), (37, 0, 1))) is None      # node 18 does not exist in example.gbz
+    assert g.follow(((2**40, 0, 1), (2**40 + 1, 0, 1))) is None
+
+
+def test_check_states_like_reference():
+    # src/gbz/tests.rs:100-168 on both GBZ fixtures: follow() == extend_*() over the graph successors
+    for name in ("example.gbz", "translation.gbz"):
+        g = load(name)
+        stack = [s for s in (g.bd_find(v) for v in range(g.alphabet_size() + 2)) if s is not None]
+        visited = set(stack)
+        while stack:
+            state = stack.pop()
+            for backward in (False, True):
+                found = g.follow(state, backward=backward)
+                assert found is not None
+                ext = g.extend_backward if backward else g.extend_forward
+                truth = {x for x in (ext(state, v) for v in range(g.alphabet_size())) if x is not None}
+                assert set(found) == truth and len(found) == len(truth)
+                for s in found:
+                    if s not in visited:
+                        visited.add(s); stack.append(s)
+        assert len(visited) > 20
+
+
 def test_raw_record_bytes():
     # SURVEY.md App. B.7 (bytes of the C++-built fixture)
     g = load("example.gbwt")
