@@ -123,30 +123,41 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
         launch_find_extend_kernel<false>(ix, patterns, nullptr, n, k, out, s);
         return launch_done("k_find_extend");
     }
-    // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time
-    // About 256 queries per bucket (one CTA's worth), at most MAX_BUCKETS: small batches get few buckets so
-    // that the single-CTA scan stays negligible.
-    const uint64_t want_buckets = std::min<uint64_t>(MAX_BUCKETS, std::max<uint64_t>(256, n / 256));
+    // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time.
+    // About 256 queries per bucket and at most 2^18 buckets (GBWT_B200_BUCKETS overrides): measured on config 4,
+    // a full sort (one bucket per record) makes the search kernel 11% faster but the sort itself twice as
+    // expensive (20 M counters and fully scattered slot writes), a net loss.
+    const uint64_t max_buckets = static_cast<uint64_t>(std::max(1, env_int("GBWT_B200_BUCKETS", 1 << 18)));
+    const uint64_t want_buckets = std::min<uint64_t>(max_buckets, std::max<uint64_t>(256, n / 256));
     uint32_t shift = 0;
-    while (((ix->view.records - 1) >> shift) >= want_buckets) shift++;
-    const uint32_t buckets = static_cast<uint32_t>(((ix->view.records - 1) >> shift) + 1);
+    while (bucket_count(ix->view.records, shift) > want_buckets) shift++;
+    const uint32_t buckets = static_cast<uint32_t>(bucket_count(ix->view.records, shift));
+    const uint32_t m = buckets + 1, tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     const size_t max_part = 0xFFFFFFFFull;
     for (size_t begin = 0; begin < n; begin += max_part) {
         const size_t count = std::min(max_part, n - begin);
-        uint32_t *counts = nullptr, *perm = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counts), (buckets + 1) * sizeof(uint32_t), s));
+        uint32_t *counts = nullptr, *perm = nullptr, *tile_sums = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counts), m * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tile_sums), tiles * sizeof(uint32_t), s));
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm), count * sizeof(uint32_t), s));
-        CUDA_TRY(cudaMemsetAsync(counts, 0, (buckets + 1) * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMemsetAsync(counts, 0, m * sizeof(uint32_t), s));
         const uint64_t* part = patterns + begin * k;
         k_bucket_count<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts);
         launch_done("k_bucket_count");
-        k_bucket_scan<<<1, 1024, 0, s>>>(counts, buckets + 1);
-        launch_done("k_bucket_scan");
+        k_scan_tiles<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+        launch_done("k_scan_tiles");
+        if (tiles > 1) {
+            k_scan_single<<<1, 1024, 0, s>>>(tile_sums, tiles);
+            launch_done("k_scan_single");
+            k_scan_add<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+            launch_done("k_scan_add");
+        }
         k_bucket_scatter<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts, perm);
         launch_done("k_bucket_scatter");
         launch_find_extend_kernel<true>(ix, part, perm, count, k, out + begin, s);
         int rc = launch_done("k_find_extend");
         cudaFreeAsync(counts, s);
+        cudaFreeAsync(tile_sums, s);
         cudaFreeAsync(perm, s);
         if (rc != GBWT_B200_OK) return rc;
     }

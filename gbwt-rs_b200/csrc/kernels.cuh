@@ -75,12 +75,28 @@ template <bool PERMUTED, bool RUNS>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
                                                                 const uint32_t* __restrict__ perm, size_t n, size_t k,
                                                                 gbwt_b200_state* __restrict__ out) {
-    GBWT_GRID_STRIDE(i, n) {
-        const size_t q = PERMUTED ? __ldg(perm + i) : i;
-        gbwt_b200_state st;
-        ChunkReader rd(patterns + q * k, k);
-        query_find_extend_rounds<RUNS>(ix, rd, k, st);
-        store_state(out + q, st);
+    if (PERMUTED) {
+        // Bucket order: every CTA takes one contiguous span of the sorted batch, so the queries it runs one
+        // after the other come from the same and then the neighbouring buckets and find their records in its
+        // SM's L1; at any moment the CTAs of the grid work on gridDim.x separate windows of the index (L2).
+        size_t span = (n + gridDim.x - 1) / gridDim.x;
+        span = (span + blockDim.x - 1) / blockDim.x * blockDim.x;
+        const size_t begin = static_cast<size_t>(blockIdx.x) * span;
+        const size_t end = begin + span < n ? begin + span : n;
+        for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+            const size_t q = __ldg(perm + i);
+            gbwt_b200_state st;
+            ChunkReader rd(patterns + q * k, k);
+            query_find_extend_rounds<RUNS>(ix, rd, k, st);
+            store_state(out + q, st);
+        }
+    } else {
+        GBWT_GRID_STRIDE(q, n) {
+            gbwt_b200_state st;
+            ChunkReader rd(patterns + q * k, k);
+            query_find_extend_rounds<RUNS>(ix, rd, k, st);
+            store_state(out + q, st);
+        }
     }
 }
 
@@ -92,13 +108,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, con
 // the queries in flight at any moment then share a few MB of the index, which stays in L1/L2, and HBM
 // only streams each part of the index once per batch.
 
-constexpr uint32_t MAX_BUCKETS = 1u << 16;
-
+// Sort key of a query: the record of its first node, coarsened by `shift`. (Moving the orientation bit to the
+// top, so that walks heading the same way sit together, was measured 16% slower: the two orientations of a node
+// share a 64-byte descriptor pair, and a bucket that uses only one of them needs twice the lines.)
 __device__ __forceinline__ uint32_t bucket_of(const IndexView& ix, uint64_t node, uint32_t shift) {
     uint64_t rec;
     if (!record_of(ix, node, rec)) return 0;
     return static_cast<uint32_t>(rec >> shift);
 }
+
+__host__ __device__ inline uint64_t bucket_count(uint64_t records, uint32_t shift) { return ((records - 1) >> shift) + 1; }
 
 // counts[b + 1] += 1 for the bucket b of every query (counts[0] stays 0 for the exclusive scan).
 __global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
@@ -108,39 +127,66 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(IndexView ix, co
     }
 }
 
-// In-place inclusive scan of counts[0 .. m) by one CTA (m <= MAX_BUCKETS + 1): counts[b] becomes the first
-// slot of bucket b.
-__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t* __restrict__ counts, uint32_t m) {
+// Inclusive scan of counts[0 .. m) in three launches: every CTA scans one tile of SCAN_TILE entries in place and
+// records its total, one CTA scans the tile totals, every CTA adds the total of the tiles before it. After the
+// scan counts[b] is the first slot of bucket b.
+constexpr uint32_t SCAN_TILE = 4096;  // 1024 threads x 4 entries
+
+__device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t x, uint32_t* warp_sums) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t result = x + (warp > 0 ? warp_sums[warp - 1] : 0);
+    __syncthreads();
+    return result;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* __restrict__ counts, uint32_t m, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    uint32_t v[4];
+    for (uint32_t j = 0; j < 4; j++) v[j] = base + j < m ? counts[base + j] : 0;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    const uint32_t before = block_inclusive_scan(v[3], warp_sums) - v[3];
+    for (uint32_t j = 0; j < 4; j++) if (base + j < m) counts[base + j] = before + v[j];
+    if (threadIdx.x == 1023) tile_sums[blockIdx.x] = before + v[3];
+}
+
+// In-place inclusive scan of a short array by one CTA (the tile totals).
+__global__ void __launch_bounds__(1024) k_scan_single(uint32_t* __restrict__ a, uint32_t m) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t base = 0; base < m; base += 1024) {
         const uint32_t i = base + threadIdx.x;
-        uint32_t v = i < m ? counts[i] : 0;
-        uint32_t x = v;
-        for (uint32_t d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-            if (lane >= d) x += y;
-        }
-        if (lane == 31) warp_sums[warp] = x;
+        const uint32_t x = block_inclusive_scan(i < m ? a[i] : 0, warp_sums);
+        const uint32_t c = carry;
+        if (i < m) a[i] = c + x;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-            for (uint32_t d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d);
-                if (lane >= d) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t before = carry + (warp > 0 ? warp_sums[warp - 1] : 0);
-        if (i < m) counts[i] = before + x;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + x;
+        if (threadIdx.x == 1023) carry = c + x;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ counts, uint32_t m, const uint32_t* __restrict__ tile_sums) {
+    if (blockIdx.x == 0) return;
+    const uint32_t add = tile_sums[blockIdx.x - 1];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    for (uint32_t j = 0; j < 4; j++) if (base + j < m) counts[base + j] += add;
 }
 
 // perm[slot] = q, slots handed out per bucket by atomics (the order inside a bucket does not matter).
