@@ -115,6 +115,7 @@ void launch_find_extend_kernel(const gbwt_b200_index* ix, const uint64_t* patter
 int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
                        cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
+    if (k > 0xFFFFFFFFull) return fail(GBWT_B200_E_ARGUMENT, "pattern length must be below 2^32");
     const uint64_t index_bytes = ix->bytes[0] + ix->bytes[1] + ix->bytes[2];
     const int locality = env_int("GBWT_B200_LOCALITY", -1);
     const bool bucket = k >= 2 && ix->view.records > 0 &&

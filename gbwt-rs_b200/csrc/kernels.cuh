@@ -42,29 +42,35 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend(IndexView ix, const gb
     }
 }
 
-// Reads the pattern one 32-byte sector (four nodes) at a time with one 256-bit load.
+// Reads the pattern one 32-byte sector (four nodes) at a time with one 256-bit load and keeps the nodes as
+// 32-bit values plus a "does not fit 32 bits" mask (see PlainReader).
 struct ChunkReader {
     const uint64_t* p;
-    uint64_t k, base;
-    uint64_t c0, c1, c2, c3;
+    uint32_t k, base;
+    uint32_t c0, c1, c2, c3, bad;
     bool vec;
-    __device__ __forceinline__ ChunkReader(const uint64_t* pattern, uint64_t len)
-        : p(pattern), k(len), base(~0ull), c0(0), c1(0), c2(0), c3(0), vec((reinterpret_cast<uintptr_t>(pattern) & 31) == 0) {}
-    __device__ __forceinline__ uint64_t node(uint64_t i) {
-        const uint64_t b = i & ~3ull;
+    __device__ __forceinline__ ChunkReader(const uint64_t* pattern, uint32_t len)
+        : p(pattern), k(len), base(0xFFFFFFFFu), c0(0), c1(0), c2(0), c3(0), bad(0), vec((reinterpret_cast<uintptr_t>(pattern) & 31) == 0) {}
+    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
+        const uint32_t b = i & ~3u;
         if (b != base) {
             base = b;
+            uint64_t v0, v1 = 0, v2 = 0, v3 = 0;
             if (vec && k - b >= 4) {
-                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(c0), "=l"(c1), "=l"(c2), "=l"(c3) : "l"(p + b));
+                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p + b));
             } else {
-                c0 = __ldg(p + b);
-                c1 = b + 1 < k ? __ldg(p + b + 1) : 0;
-                c2 = b + 2 < k ? __ldg(p + b + 2) : 0;
-                c3 = b + 3 < k ? __ldg(p + b + 3) : 0;
+                v0 = __ldg(p + b);
+                if (b + 1 < k) v1 = __ldg(p + b + 1);
+                if (b + 2 < k) v2 = __ldg(p + b + 2);
+                if (b + 3 < k) v3 = __ldg(p + b + 3);
             }
+            c0 = static_cast<uint32_t>(v0); c1 = static_cast<uint32_t>(v1);
+            c2 = static_cast<uint32_t>(v2); c3 = static_cast<uint32_t>(v3);
+            bad = ((v0 >> 32) != 0 ? 1u : 0u) | ((v1 >> 32) != 0 ? 2u : 0u) | ((v2 >> 32) != 0 ? 4u : 0u) | ((v3 >> 32) != 0 ? 8u : 0u);
         }
-        const uint32_t j = static_cast<uint32_t>(i) & 3u;
-        return j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+        const uint32_t j = i & 3u;
+        out = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+        return ((bad >> j) & 1u) == 0;
     }
 };
 
@@ -86,15 +92,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, con
         for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
             const size_t q = __ldg(perm + i);
             gbwt_b200_state st;
-            ChunkReader rd(patterns + q * k, k);
-            query_find_extend_rounds<RUNS>(ix, rd, k, st);
+            ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
+            query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
             store_state(out + q, st);
         }
     } else {
         GBWT_GRID_STRIDE(q, n) {
             gbwt_b200_state st;
-            ChunkReader rd(patterns + q * k, k);
-            query_find_extend_rounds<RUNS>(ix, rd, k, st);
+            ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
+            query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
             store_state(out + q, st);
         }
     }

@@ -718,13 +718,19 @@ GBWT_HD uint64_t gbwt_follow_all(const IndexView& ix, const gbwt_b200_bdstate& s
 // gbwt_extend, arranged for the GPU: the range lives in two 32-bit registers and every descriptor is loaded
 // once, with a single 256-bit load.
 
+// Pattern readers hand out node i as 32 bits plus a validity flag: every node of a loaded index is below 2^32
+// (layout.h), so a pattern node above that can never match and the hot loop never touches 64-bit node ids.
 struct PlainReader {
     const uint64_t* p;
-    GBWT_HD uint64_t node(uint64_t i) { return GBWT_LDG(p + i); }
+    GBWT_HD bool node(uint32_t i, uint32_t& out) {
+        const uint64_t v = GBWT_LDG(p + i);
+        out = static_cast<uint32_t>(v);
+        return (v >> 32) == 0;
+    }
 };
 
 // Step on a single-edge record: every position maps to edge 0.
-GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
+GBWT_HD bool follow_single(const Desc& d, uint32_t next, uint32_t& start, uint32_t& end) {
     const uint32_t total = d.total_len();
     const uint32_t s = d.offset0() + (start < total ? start : total), e = d.offset0() + (end < total ? end : total);
     if (next != d.node0() || s >= e) return false;
@@ -734,7 +740,7 @@ GBWT_HD bool follow_single(const Desc& d, uint64_t next, uint32_t& start, uint32
 
 // Step on a record with a body.
 template <bool RUNS>
-GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint64_t next, uint32_t& start, uint32_t& end) {
+GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint32_t next, uint32_t& start, uint32_t& end) {
     uint32_t rank = 0, edge_offset = 0;
     FlipSet fs;
     fs.lt = 0; fs.extra = NO_SYMBOL;
@@ -745,18 +751,11 @@ GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint64_t next, uint
     return true;
 }
 
-// GBWT::find on pattern node 0: leaves its descriptor in `d`.
-GBWT_HD bool find_first(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d, uint32_t& start, uint32_t& end) {
-    if (node < ix.offset + 1 || !record_of(ix, node, rec)) return false;
-    d = load_desc(ix, rec);
-    if (d.fmt() == FMT_EMPTY || d.total_len() == 0) return false;
-    start = 0; end = d.total_len();
-    return true;
-}
-
-// Descriptor of the record that the next step starts from; false = BWT::record() is None.
-GBWT_HD bool next_record(const IndexView& ix, uint64_t node, uint64_t& rec, Desc& d) {
-    if (!record_of(ix, node, rec)) return false;
+// Descriptor of the record of `node` (32-bit arithmetic; the caller has checked node >= first_node); false =
+// BWT::record() is None.
+GBWT_HD bool record_desc32(const IndexView& ix, uint32_t node, Desc& d) {
+    const uint32_t rec = node - static_cast<uint32_t>(ix.offset);
+    if (rec >= ix.records) return false;
     d = load_desc(ix, rec);
     return d.fmt() != FMT_EMPTY;
 }
@@ -764,39 +763,42 @@ GBWT_HD bool next_record(const IndexView& ix, uint64_t node, uint64_t& rec, Desc
 // The loop runs in rounds: any number of single-edge records (a few instructions each), then one record with
 // a body, so that the lanes of a warp meet again at the expensive rank step instead of diverging on the record
 // format (measured on B200 with tools/exp_find.py: 1.2x for dense bodies, 1.9x for run-length bodies over
-// the straight per-node chain).
+// the straight per-node chain). Counters, nodes and ranges are all 32-bit.
 template <bool RUNS, class Reader>
-GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint64_t k, gbwt_b200_state& out) {
+GBWT_HD void query_find_extend_rounds(const IndexView& ix, Reader& rd, uint32_t k, gbwt_b200_state& out) {
     set_none(out);
     if (k == 0) return;
     const uint64_t first_node = ix.offset + 1;
-    uint64_t node = rd.node(0), rec = 0;
+    uint32_t node;
     Desc d;
-    uint32_t start = 0, end = 0;
-    if (!find_first(ix, node, rec, d, start, end)) return;
-    uint64_t i = 1;
+    // GBWT::find on pattern node 0 (src/gbwt.rs:269-281)
+    if (!rd.node(0, node) || node < first_node || !record_desc32(ix, node, d) || d.total_len() == 0) return;
+    uint32_t start = 0, end = d.total_len();
+    uint32_t i = 1;
     while (i < k) {
         bool dead = false;
         while (i < k && d.fmt() == FMT_SINGLE) {
-            const uint64_t next = rd.node(i);
-            if (next < first_node || !follow_single(d, next, start, end)) { dead = true; break; }
+            uint32_t next;
+            if (!rd.node(i, next) || next < first_node || !follow_single(d, next, start, end)) { dead = true; break; }
             node = next; i++;
-            if (i < k && !next_record(ix, node, rec, d)) { dead = true; break; }
+            if (i < k && !record_desc32(ix, node, d)) { dead = true; break; }
         }
         if (dead) return;
         if (i >= k) break;
-        const uint64_t next = rd.node(i);
-        if (next < first_node || !follow_body<RUNS>(ix, d, next, start, end)) return;
+        uint32_t next;
+        if (!rd.node(i, next) || next < first_node || !follow_body<RUNS>(ix, d, next, start, end)) return;
         node = next; i++;
-        if (i < k && !next_record(ix, node, rec, d)) return;
+        if (i < k && !record_desc32(ix, node, d)) return;
     }
     out.node = node; out.start = start; out.end = end;
 }
 
+// Patterns of 2^32 nodes or more cannot be stored anywhere near a GPU; they are reported as None.
 GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uint64_t k, gbwt_b200_state& out) {
     PlainReader rd;
     rd.p = pattern;
-    query_find_extend_rounds<true>(ix, rd, k, out);
+    if (k > 0xFFFFFFFFull) { set_none(out); return; }
+    query_find_extend_rounds<true>(ix, rd, static_cast<uint32_t>(k), out);
 }
 
 // bd_find(path[first]), extend_forward over path(first, end), extend_backward over path[start, first) in
