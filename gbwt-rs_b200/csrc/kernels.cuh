@@ -42,31 +42,41 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_extend(IndexView ix, const gb
     }
 }
 
-// Reads the pattern one 32-byte sector (four nodes) at a time with one 256-bit load and keeps the nodes as
-// 32-bit values plus a "does not fit 32 bits" mask (see PlainReader).
+// Reads the pattern one 32-byte sector (four nodes) at a time with one 256-bit load, keeps the nodes as 32-bit
+// values plus a "does not fit 32 bits" mask (see PlainReader), and always has the NEXT sector in flight: the
+// pattern rows of a bucketed batch are scattered over HBM, so this is the one load of the loop that pays full
+// DRAM latency, and nothing depends on it for four steps.
 struct ChunkReader {
     const uint64_t* p;
     uint32_t k, base;
     uint32_t c0, c1, c2, c3, bad;
+    uint64_t n0, n1, n2, n3;  // the sector after `base`, requested one chunk early
     bool vec;
+    __device__ __forceinline__ void fetch(uint32_t b, uint64_t& v0, uint64_t& v1, uint64_t& v2, uint64_t& v3) const {
+        v0 = v1 = v2 = v3 = 0;
+        if (b >= k) return;
+        if (vec && k - b >= 4) {
+            asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p + b));
+        } else {
+            v0 = __ldg(p + b);
+            if (b + 1 < k) v1 = __ldg(p + b + 1);
+            if (b + 2 < k) v2 = __ldg(p + b + 2);
+            if (b + 3 < k) v3 = __ldg(p + b + 3);
+        }
+    }
     __device__ __forceinline__ ChunkReader(const uint64_t* pattern, uint32_t len)
-        : p(pattern), k(len), base(0xFFFFFFFFu), c0(0), c1(0), c2(0), c3(0), bad(0), vec((reinterpret_cast<uintptr_t>(pattern) & 31) == 0) {}
+        : p(pattern), k(len), base(0xFFFFFFFFu), c0(0), c1(0), c2(0), c3(0), bad(0), vec((reinterpret_cast<uintptr_t>(pattern) & 31) == 0) {
+        fetch(0, n0, n1, n2, n3);
+    }
+    // Nodes are read in increasing order of i (the search loop), so a new chunk is always the prefetched one.
     __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
         const uint32_t b = i & ~3u;
         if (b != base) {
             base = b;
-            uint64_t v0, v1 = 0, v2 = 0, v3 = 0;
-            if (vec && k - b >= 4) {
-                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(p + b));
-            } else {
-                v0 = __ldg(p + b);
-                if (b + 1 < k) v1 = __ldg(p + b + 1);
-                if (b + 2 < k) v2 = __ldg(p + b + 2);
-                if (b + 3 < k) v3 = __ldg(p + b + 3);
-            }
-            c0 = static_cast<uint32_t>(v0); c1 = static_cast<uint32_t>(v1);
-            c2 = static_cast<uint32_t>(v2); c3 = static_cast<uint32_t>(v3);
-            bad = ((v0 >> 32) != 0 ? 1u : 0u) | ((v1 >> 32) != 0 ? 2u : 0u) | ((v2 >> 32) != 0 ? 4u : 0u) | ((v3 >> 32) != 0 ? 8u : 0u);
+            c0 = static_cast<uint32_t>(n0); c1 = static_cast<uint32_t>(n1);
+            c2 = static_cast<uint32_t>(n2); c3 = static_cast<uint32_t>(n3);
+            bad = ((n0 >> 32) != 0 ? 1u : 0u) | ((n1 >> 32) != 0 ? 2u : 0u) | ((n2 >> 32) != 0 ? 4u : 0u) | ((n3 >> 32) != 0 ? 8u : 0u);
+            fetch(b + 4, n0, n1, n2, n3);
         }
         const uint32_t j = i & 3u;
         out = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
