@@ -103,63 +103,78 @@ int env_int(const char* name, int fallback) {
 constexpr size_t LOCALITY_MIN_QUERIES = size_t(1) << 16;  // below this the sort costs more than it saves
 constexpr uint64_t LOCALITY_MIN_INDEX_BYTES = uint64_t(48) << 20;  // an index that lives in L2 gains nothing
 
-template <bool PERMUTED>
-void launch_find_extend_kernel(const gbwt_b200_index* ix, const uint64_t* patterns, const uint32_t* perm, size_t n, size_t k,
-                               gbwt_b200_state* out, cudaStream_t s) {
-    const unsigned grid = grid_for(ix, n);
-    const uint64_t run_records = ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64];
-    if (run_records == 0) k_find_extend<PERMUTED, false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out);
-    else k_find_extend<PERMUTED, true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, patterns, perm, n, k, out);
+bool has_run_records(const gbwt_b200_index* ix) {
+    return ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64] != 0;
 }
 
-int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
-                       cudaStream_t s) {
-    if (n == 0) return GBWT_B200_OK;
-    if (k > 0xFFFFFFFFull) return fail(GBWT_B200_E_ARGUMENT, "pattern length must be below 2^32");
+// Whether a batch of n queries gets the locality schedule (GBWT_B200_LOCALITY overrides).
+bool wants_locality(const gbwt_b200_index* ix, size_t n) {
     const uint64_t index_bytes = ix->bytes[0] + ix->bytes[1] + ix->bytes[2];
     const int locality = env_int("GBWT_B200_LOCALITY", -1);
-    const bool bucket = k >= 2 && ix->view.records > 0 &&
-                        (locality == 1 || (locality != 0 && n >= LOCALITY_MIN_QUERIES && index_bytes >= LOCALITY_MIN_INDEX_BYTES));
-    if (!bucket) {
-        launch_find_extend_kernel<false>(ix, patterns, nullptr, n, k, out, s);
-        return launch_done("k_find_extend");
-    }
-    // locality schedule: counting sort of the queries by the record of pattern[0], 2^32 - 1 queries at a time.
-    // About 256 queries per bucket and at most 2^18 buckets (GBWT_B200_BUCKETS overrides): measured on config 4,
-    // a full sort (one bucket per record) makes the search kernel 11% faster but the sort itself twice as
-    // expensive (20 M counters and fully scattered slot writes), a net loss.
+    if (ix->view.records == 0 || n > 0xFFFFFFFFull) return false;
+    return locality == 1 || (locality != 0 && n >= LOCALITY_MIN_QUERIES && index_bytes >= LOCALITY_MIN_INDEX_BYTES);
+}
+
+// Locality schedule: counting sort of the batch by the record of each query's first node. `write_keys(shift, keys)`
+// launches the kernel that fills keys[q] = bucket of query q; on success *perm holds the sorted order and the
+// caller frees it with cudaFreeAsync on the same stream once the search kernel is enqueued.
+// About 256 queries per bucket and at most 2^18 buckets (GBWT_B200_BUCKETS overrides): measured on config 4,
+// a full sort (one bucket per record) makes the search kernel 11% faster but the sort itself twice as
+// expensive (20 M counters and fully scattered slot writes), a net loss.
+template <class WriteKeys>
+int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, WriteKeys write_keys, uint32_t** perm) {
     const uint64_t max_buckets = static_cast<uint64_t>(std::max(1, env_int("GBWT_B200_BUCKETS", 1 << 18)));
     const uint64_t want_buckets = std::min<uint64_t>(max_buckets, std::max<uint64_t>(256, n / 256));
     uint32_t shift = 0;
     while (bucket_count(ix->view.records, shift) > want_buckets) shift++;
     const uint32_t buckets = static_cast<uint32_t>(bucket_count(ix->view.records, shift));
     const uint32_t m = buckets + 1, tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    const size_t max_part = 0xFFFFFFFFull;
+    uint32_t *counts = nullptr, *tile_sums = nullptr, *keys = nullptr;
+    *perm = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counts), m * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tile_sums), tiles * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&keys), n * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(perm), n * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(counts, 0, m * sizeof(uint32_t), s));
+    write_keys(shift, keys);
+    launch_done("k_keys");
+    k_bucket_count<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts);
+    launch_done("k_bucket_count");
+    k_scan_tiles<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+    launch_done("k_scan_tiles");
+    if (tiles > 1) {
+        k_scan_single<<<1, 1024, 0, s>>>(tile_sums, tiles);
+        launch_done("k_scan_single");
+        k_scan_add<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+        launch_done("k_scan_add");
+    }
+    k_bucket_scatter<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts, *perm);
+    int rc = launch_done("k_bucket_scatter");
+    cudaFreeAsync(counts, s);
+    cudaFreeAsync(tile_sums, s);
+    cudaFreeAsync(keys, s);
+    return rc;
+}
+
+int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
+                       cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    if (k > 0xFFFFFFFFull) return fail(GBWT_B200_E_ARGUMENT, "pattern length must be below 2^32");
+    const size_t max_part = 0xFFFFFFFFull;  // the permutation is 32-bit
     for (size_t begin = 0; begin < n; begin += max_part) {
         const size_t count = std::min(max_part, n - begin);
-        uint32_t *counts = nullptr, *perm = nullptr, *tile_sums = nullptr;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counts), m * sizeof(uint32_t), s));
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tile_sums), tiles * sizeof(uint32_t), s));
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm), count * sizeof(uint32_t), s));
-        CUDA_TRY(cudaMemsetAsync(counts, 0, m * sizeof(uint32_t), s));
         const uint64_t* part = patterns + begin * k;
-        k_bucket_count<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts);
-        launch_done("k_bucket_count");
-        k_scan_tiles<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
-        launch_done("k_scan_tiles");
-        if (tiles > 1) {
-            k_scan_single<<<1, 1024, 0, s>>>(tile_sums, tiles);
-            launch_done("k_scan_single");
-            k_scan_add<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
-            launch_done("k_scan_add");
+        uint32_t* perm = nullptr;
+        if (k >= 2 && wants_locality(ix, count)) {
+            int rc = build_locality_perm(ix, count, s, [&](uint32_t shift, uint32_t* keys) {
+                k_keys_fixed<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, keys);
+            }, &perm);
+            if (rc != GBWT_B200_OK) return rc;
         }
-        k_bucket_scatter<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, counts, perm);
-        launch_done("k_bucket_scatter");
-        launch_find_extend_kernel<true>(ix, part, perm, count, k, out + begin, s);
+        if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+        else k_find_extend<false><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
         int rc = launch_done("k_find_extend");
-        cudaFreeAsync(counts, s);
-        cudaFreeAsync(tile_sums, s);
-        cudaFreeAsync(perm, s);
+        if (perm != nullptr) cudaFreeAsync(perm, s);
         if (rc != GBWT_B200_OK) return rc;
     }
     return GBWT_B200_OK;
@@ -168,8 +183,17 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
 int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t* offsets, uint64_t base,
                               size_t n, gbwt_b200_state* out, cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
-    k_find_extend_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, n, out);
-    return launch_done("k_find_extend_ragged");
+    uint32_t* perm = nullptr;
+    if (wants_locality(ix, n)) {
+        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys) {
+            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, nullptr, n, shift, keys);
+        }, &perm);
+        if (rc != GBWT_B200_OK) return rc;
+    }
+    k_find_extend_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);
+    int rc = launch_done("k_find_extend_ragged");
+    if (perm != nullptr) cudaFreeAsync(perm, s);
+    return rc;
 }
 int launch_bd_find(const gbwt_b200_index* ix, const uint64_t* nodes, size_t n, gbwt_b200_bdstate* out, cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
@@ -186,8 +210,17 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
                      const uint64_t* first, const uint64_t* start, const uint64_t* end, size_t n, gbwt_b200_bdstate* out,
                      cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
-    k_bd_search<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, n, out);
-    return launch_done("k_bd_search");
+    uint32_t* perm = nullptr;
+    if (wants_locality(ix, n)) {
+        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys) {
+            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys);
+        }, &perm);
+        if (rc != GBWT_B200_OK) return rc;
+    }
+    k_bd_search<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, perm, n, out);
+    int rc = launch_done("k_bd_search");
+    if (perm != nullptr) cudaFreeAsync(perm, s);
+    return rc;
 }
 int launch_follow(const gbwt_b200_index* ix, const gbwt_b200_bdstate* st, size_t n, int backward, const uint64_t* out_offsets,
                   uint64_t base, gbwt_b200_bdstate* out, uint64_t* counts, cudaStream_t s) {

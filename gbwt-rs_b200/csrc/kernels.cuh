@@ -18,6 +18,17 @@ constexpr int BLOCK_THREADS = 256;
 #define GBWT_GRID_STRIDE(i, n) \
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < (n); i += static_cast<size_t>(gridDim.x) * blockDim.x)
 
+// Work assignment of the search kernels: item i of the batch, or, with a permutation (locality schedule), one
+// contiguous span of the sorted batch per CTA, so that the queries a CTA runs one after the other come from the
+// same and then the neighbouring buckets.
+#define GBWT_FOR_EACH_QUERY(q, n, perm)                                                                              \
+    const size_t _stride = (perm) != nullptr ? blockDim.x : static_cast<size_t>(gridDim.x) * blockDim.x;            \
+    size_t _span = ((n) + gridDim.x - 1) / gridDim.x;                                                                \
+    _span = (_span + blockDim.x - 1) / blockDim.x * blockDim.x;                                                      \
+    const size_t _begin = (perm) != nullptr ? static_cast<size_t>(blockIdx.x) * _span : static_cast<size_t>(blockIdx.x) * blockDim.x; \
+    const size_t _end = (perm) != nullptr ? (_begin + _span < (n) ? _begin + _span : (n)) : (n);                      \
+    for (size_t _i = _begin + threadIdx.x, q = 0; _i < _end && ((q = (perm) != nullptr ? (perm)[_i] : _i), true); _i += _stride)
+
 // 24-byte / 48-byte results are written with 8-byte stores; neighbouring threads write neighbouring
 // records, so every warp store covers whole sectors.
 __device__ __forceinline__ void store_state(gbwt_b200_state* out, const gbwt_b200_state& s) { *out = s; }
@@ -84,35 +95,18 @@ struct ChunkReader {
     }
 };
 
-// K1: find(p[0]) + extends, one thread per pattern. PERMUTED: the thread takes the query perm[i] (locality
-// schedule below; results always go to out[q]). RUNS = false is the instantiation for indexes without
-// run-length bodies (record_scan.cuh: rank_pair).
-template <bool PERMUTED, bool RUNS>
+// K1: find(p[0]) + extends, one thread per pattern. With `perm` the threads take the queries in bucket order
+// (locality schedule below; results always go to out[q]). RUNS = false is the instantiation for indexes
+// without run-length bodies (record_scan.cuh: rank_pair).
+template <bool RUNS>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, const uint64_t* __restrict__ patterns,
                                                                 const uint32_t* __restrict__ perm, size_t n, size_t k,
                                                                 gbwt_b200_state* __restrict__ out) {
-    if (PERMUTED) {
-        // Bucket order: every CTA takes one contiguous span of the sorted batch, so the queries it runs one
-        // after the other come from the same and then the neighbouring buckets and find their records in its
-        // SM's L1; at any moment the CTAs of the grid work on gridDim.x separate windows of the index (L2).
-        size_t span = (n + gridDim.x - 1) / gridDim.x;
-        span = (span + blockDim.x - 1) / blockDim.x * blockDim.x;
-        const size_t begin = static_cast<size_t>(blockIdx.x) * span;
-        const size_t end = begin + span < n ? begin + span : n;
-        for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-            const size_t q = __ldg(perm + i);
-            gbwt_b200_state st;
-            ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
-            query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
-            store_state(out + q, st);
-        }
-    } else {
-        GBWT_GRID_STRIDE(q, n) {
-            gbwt_b200_state st;
-            ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
-            query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
-            store_state(out + q, st);
-        }
+    GBWT_FOR_EACH_QUERY(q, n, perm) {
+        gbwt_b200_state st;
+        ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
+        query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
+        store_state(out + q, st);
     }
 }
 
@@ -135,12 +129,28 @@ __device__ __forceinline__ uint32_t bucket_of(const IndexView& ix, uint64_t node
 
 __host__ __device__ inline uint64_t bucket_count(uint64_t records, uint32_t shift) { return ((records - 1) >> shift) + 1; }
 
-// counts[b + 1] += 1 for the bucket b of every query (counts[0] stays 0 for the exclusive scan).
-__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
-                                                                 size_t k, uint32_t shift, uint32_t* __restrict__ counts) {
+// keys[q] = bucket of query q: its first node is pattern row q, column 0 ...
+__global__ void __launch_bounds__(BLOCK_THREADS) k_keys_fixed(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
+                                                               size_t k, uint32_t shift, uint32_t* __restrict__ keys) {
+    GBWT_GRID_STRIDE(q, n) { keys[q] = bucket_of(ix, __ldg(patterns + q * k), shift); }
+}
+
+// ... or nodes[offsets[q] - base + first[q]] for ragged batches (first == nullptr: the first node of the pattern).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_keys_ragged(IndexView ix, const uint64_t* __restrict__ nodes,
+                                                                const uint64_t* __restrict__ offsets, uint64_t base,
+                                                                const uint64_t* __restrict__ first, size_t n, uint32_t shift,
+                                                                uint32_t* __restrict__ keys) {
     GBWT_GRID_STRIDE(q, n) {
-        atomicAdd(counts + 1 + bucket_of(ix, __ldg(patterns + q * k), shift), 1u);
+        const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
+        const uint64_t at = first != nullptr ? __ldg(first + q) : 0;
+        keys[q] = (hi > lo && at < hi - lo) ? bucket_of(ix, __ldg(nodes + (lo - base) + at), shift) : 0;
     }
+}
+
+// counts[b + 1] += 1 for the bucket b of every query (counts[0] stays 0 for the exclusive scan).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(const uint32_t* __restrict__ keys, size_t n,
+                                                                 uint32_t* __restrict__ counts) {
+    GBWT_GRID_STRIDE(q, n) { atomicAdd(counts + 1 + __ldg(keys + q), 1u); }
 }
 
 // Inclusive scan of counts[0 .. m) in three launches: every CTA scans one tile of SCAN_TILE entries in place and
@@ -206,11 +216,10 @@ __global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ counts
 }
 
 // perm[slot] = q, slots handed out per bucket by atomics (the order inside a bucket does not matter).
-__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_scatter(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
-                                                                   size_t k, uint32_t shift, uint32_t* __restrict__ cursor,
-                                                                   uint32_t* __restrict__ perm) {
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_scatter(const uint32_t* __restrict__ keys, size_t n,
+                                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
     GBWT_GRID_STRIDE(q, n) {
-        const uint32_t slot = atomicAdd(cursor + bucket_of(ix, __ldg(patterns + q * k), shift), 1u);
+        const uint32_t slot = atomicAdd(cursor + __ldg(keys + q), 1u);
         perm[slot] = static_cast<uint32_t>(q);
     }
 }
@@ -218,8 +227,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_scatter(IndexView ix, 
 // `base` = offsets[0] of the chunk that `nodes` starts at (host entry points upload node chunks).
 __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend_ragged(IndexView ix, const uint64_t* __restrict__ nodes,
                                                                        const uint64_t* __restrict__ offsets, uint64_t base,
-                                                                       size_t n, gbwt_b200_state* __restrict__ out) {
-    GBWT_GRID_STRIDE(q, n) {
+                                                                       const uint32_t* __restrict__ perm, size_t n,
+                                                                       gbwt_b200_state* __restrict__ out) {
+    GBWT_FOR_EACH_QUERY(q, n, perm) {
         const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
         gbwt_b200_state st;
         query_find_extend(ix, nodes + (lo - base), hi > lo ? hi - lo : 0, st);
@@ -252,9 +262,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_search(IndexView ix, const
                                                               const uint64_t* __restrict__ offsets, uint64_t base,
                                                               const uint64_t* __restrict__ first,
                                                               const uint64_t* __restrict__ start,
-                                                              const uint64_t* __restrict__ end, size_t n,
+                                                              const uint64_t* __restrict__ end,
+                                                              const uint32_t* __restrict__ perm, size_t n,
                                                               gbwt_b200_bdstate* __restrict__ out) {
-    GBWT_GRID_STRIDE(q, n) {
+    GBWT_FOR_EACH_QUERY(q, n, perm) {
         const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
         gbwt_b200_bdstate st;
         query_bd_search(ix, nodes + (lo - base), hi > lo ? hi - lo : 0, __ldg(first + q), __ldg(start + q), __ldg(end + q), st);
