@@ -217,7 +217,8 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
         }, &perm);
         if (rc != GBWT_B200_OK) return rc;
     }
-    k_bd_search<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, perm, n, out);
+    if (has_run_records(ix)) k_bd_search<true><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, perm, n, out);
+    else k_bd_search<false><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, start, end, perm, n, out);
     int rc = launch_done("k_bd_search");
     if (perm != nullptr) cudaFreeAsync(perm, s);
     return rc;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_extend(IndexView ix, const
     }
 }
 
+template <bool RUNS>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_search(IndexView ix, const uint64_t* __restrict__ nodes,
                                                               const uint64_t* __restrict__ offsets, uint64_t base,
                                                               const uint64_t* __restrict__ first,
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_search(IndexView ix, const
     GBWT_FOR_EACH_QUERY(q, n, perm) {
         const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
         gbwt_b200_bdstate st;
-        query_bd_search(ix, nodes + (lo - base), hi > lo ? hi - lo : 0, __ldg(first + q), __ldg(start + q), __ldg(end + q), st);
+        query_bd_search_fast<RUNS>(ix, nodes + (lo - base), hi > lo ? hi - lo : 0, __ldg(first + q), __ldg(start + q), __ldg(end + q), st);
         out[q] = st;
     }
 }

@@ -803,23 +803,86 @@ GBWT_HD void query_find_extend(const IndexView& ix, const uint64_t* pattern, uin
 
 // bd_find(path[first]), extend_forward over path(first, end), extend_backward over path[start, first) in
 // descending order: the reference's test driver, src/gbwt/tests.rs:352-361.
+// Same results as chaining gbwt_bd_find / gbwt_extend_forward / gbwt_extend_backward, arranged like
+// query_find_extend_rounds: 32-bit nodes and ranges, one descriptor load per step, rounds of single-edge records
+// followed by one record with a body. A backward extension by `node` is a forward extension of the flipped state
+// by flip(node) (src/gbwt.rs:362-367), so both phases run the same loop on swapped halves of the state.
+struct Half32 { uint32_t node, start, end; };
+
+// Extends `a` (the half being extended; `d` is the descriptor of a.node) by `x` and moves `b` (the other half)
+// like bd_internal (src/gbwt.rs:370-384). False = None.
+template <bool RUNS>
+GBWT_HD bool bd_step(const IndexView& ix, const Desc& d, uint32_t x, Half32& a, Half32& b) {
+    uint32_t flipped = 0;
+    if (d.fmt() == FMT_SINGLE) {
+        // the only edge has rank 0; no other symbol can precede it, so the reverse range keeps its start
+        if (!follow_single(d, x, a.start, a.end)) return false;
+    } else {
+        uint32_t rank = 0, edge_offset = 0;
+        FlipSet fs;
+        fs.lt = 0; fs.extra = NO_SYMBOL;
+        if (!find_edge<true>(ix, d, x, rank, edge_offset, fs)) return false;
+        const Ranks r = rank_pair<true, RUNS>(ix, d, rank, fs, a.start, a.end);
+        if (r.at_start >= r.at_end) return false;
+        a.start = edge_offset + r.at_start; a.end = edge_offset + r.at_end;
+        flipped = r.flipped;
+    }
+    a.node = x;
+    b.start += flipped;
+    b.end = b.start + (a.end - a.start);
+    return true;
+}
+
+// Runs `count` extensions of `a` by the nodes path[from], path[from + step], ... (xor `flip` for the backward
+// phase). Rounds: single-edge records, then one record with a body.
+template <bool RUNS>
+GBWT_HD bool bd_run(const IndexView& ix, const uint64_t* path, uint32_t from, int32_t step, uint32_t count, uint32_t flip,
+                    Half32& a, Half32& b) {
+    if (count == 0) return true;
+    const uint64_t first_node = ix.offset + 1;
+    Desc d;
+    if (!record_desc32(ix, a.node, d)) return false;  // like BWT::record(node_to_record(..)), no first_node test here
+    uint32_t at = from, left = count;
+    while (left > 0) {
+        bool dead = false;
+        while (left > 0 && d.fmt() == FMT_SINGLE) {
+            const uint64_t v = GBWT_LDG(path + at) ^ flip;
+            if ((v >> 32) != 0 || v < first_node || !bd_step<RUNS>(ix, d, static_cast<uint32_t>(v), a, b)) { dead = true; break; }
+            at += step; left--;
+            if (left > 0 && !record_desc32(ix, a.node, d)) { dead = true; break; }
+        }
+        if (dead) return false;
+        if (left == 0) break;
+        const uint64_t v = GBWT_LDG(path + at) ^ flip;
+        if ((v >> 32) != 0 || v < first_node || !bd_step<RUNS>(ix, d, static_cast<uint32_t>(v), a, b)) return false;
+        at += step; left--;
+        if (left > 0 && !record_desc32(ix, a.node, d)) return false;
+    }
+    return true;
+}
+
+template <bool RUNS>
+GBWT_HD void query_bd_search_fast(const IndexView& ix, const uint64_t* path, uint64_t len, uint64_t first, uint64_t start,
+                                  uint64_t end, gbwt_b200_bdstate& out) {
+    set_none(out);
+    if (!(start <= first && first < end && end <= len) || len > 0xFFFFFFFFull) return;
+    const uint64_t v = GBWT_LDG(path + first);
+    Desc d;
+    // bd_find (src/gbwt.rs:311-324)
+    if ((v >> 32) != 0 || v < ix.offset + 1 || !record_desc32(ix, static_cast<uint32_t>(v), d) || d.total_len() == 0) return;
+    Half32 fwd, rev;
+    fwd.node = static_cast<uint32_t>(v); fwd.start = 0; fwd.end = d.total_len();
+    rev.node = fwd.node ^ 1u; rev.start = 0; rev.end = fwd.end;
+    const uint32_t f = static_cast<uint32_t>(first);
+    if (!bd_run<RUNS>(ix, path, f + 1, 1, static_cast<uint32_t>(end - first - 1), 0u, fwd, rev)) return;
+    if (f > start && !bd_run<RUNS>(ix, path, f - 1, -1, static_cast<uint32_t>(first - start), 1u, rev, fwd)) return;
+    out.forward.node = fwd.node; out.forward.start = fwd.start; out.forward.end = fwd.end;
+    out.reverse.node = rev.node; out.reverse.start = rev.start; out.reverse.end = rev.end;
+}
+
 GBWT_HD void query_bd_search(const IndexView& ix, const uint64_t* path, uint64_t len, uint64_t first, uint64_t start,
                              uint64_t end, gbwt_b200_bdstate& out) {
-    set_none(out);
-    if (!(start <= first && first < end && end <= len)) return;
-    gbwt_b200_bdstate st;
-    if (!gbwt_bd_find(ix, GBWT_LDG(path + first), st)) return;
-    for (uint64_t i = first + 1; i < end; i++) {
-        gbwt_b200_bdstate next;
-        if (!gbwt_extend_forward(ix, st, GBWT_LDG(path + i), next)) return;
-        st = next;
-    }
-    for (uint64_t i = first; i > start; i--) {
-        gbwt_b200_bdstate next;
-        if (!gbwt_extend_backward(ix, st, GBWT_LDG(path + i - 1), next)) return;
-        st = next;
-    }
-    out = st;
+    query_bd_search_fast<true>(ix, path, len, first, start, end, out);
 }
 
 // GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568): writes at most `cap` nodes and returns the
