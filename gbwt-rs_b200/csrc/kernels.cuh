@@ -332,13 +332,114 @@ __device__ __forceinline__ Desc load_desc_of(const IndexView& ix, uint64_t node)
     return d;
 }
 
+// Record::lf (src/bwt.rs:480-496) on a RUN8 body by a whole warp: every lane calls it with the same arguments.
+// Each lane takes one 16-byte unit of the body (512 bytes per round, ONE memory round trip for a whole anchor
+// record instead of one per unit), decodes its runs, and a shuffle prefix sum over the per-lane run totals plus a
+// ballot locate the lane whose unit covers position i; that lane finds the run and its symbol, the lanes before
+// it count that symbol, and a warp reduction adds the counts up. Returns symbol == NO_SYMBOL if i is past the end.
+__device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d, uint32_t i, uint32_t& symbol, uint32_t& rank_i) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const Unit16* body = ix.bodies + d.body();
+    const uint32_t n = d.body_len(), sigma = d.sigma();
+    const uint32_t magic = d.inline_edges() ? 32769u : d.magic();
+    symbol = NO_SYMBOL; rank_i = 0;
+    uint32_t off = 0, found_base = 0;
+    for (uint32_t base = 0; base < n; base += 512) {
+        const uint32_t at = base + 16 * lane;
+        Quad q;
+        q.x = q.y = q.z = q.w = 0;
+        if (at < n) q = load_quad(body + (at >> 4));
+        const uint32_t nb = at < n ? (n - at < 16 ? n - at : 16) : 0;
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+        uint32_t total = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+            if (j < nb) total += (((words[j >> 2] >> (8 * (j & 3))) & 0xFF) * magic >> 16) + 1;
+        }
+        uint32_t incl = total;
+#pragma unroll
+        for (uint32_t dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, incl, dlt);
+            if (lane >= dlt) incl += y;
+        }
+        const uint32_t before = off + incl - total;
+        const uint32_t hit = __ballot_sync(FULL, total != 0 && i >= before && i - before < total);
+        if (hit != 0) {
+            const uint32_t owner = __ffs(hit) - 1;
+            uint32_t sym = 0, part = 0;
+            if (lane == owner) {
+                uint32_t o = before;
+                bool have = false;
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j++) {
+                    if (j < nb && !have) {
+                        const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                        const uint32_t quot = (b * magic) >> 16;
+                        if (i - o < quot + 1) { sym = b - quot * sigma; have = true; }
+                        else o += quot + 1;
+                    }
+                }
+                o = before;
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j++) {
+                    if (j < nb && o < i) {
+                        const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                        const uint32_t quot = (b * magic) >> 16;
+                        if (b - quot * sigma == sym) part += (i - o < quot + 1) ? i - o : quot + 1;
+                        o += quot + 1;
+                    }
+                }
+            }
+            sym = __shfl_sync(FULL, sym, owner);
+            part = __shfl_sync(FULL, part, owner);
+            uint32_t cnt = 0;
+            if (lane < owner) {
+#pragma unroll
+                for (uint32_t j = 0; j < 16; j++) {
+                    if (j < nb) {
+                        const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                        const uint32_t quot = (b * magic) >> 16;
+                        if (b - quot * sigma == sym) cnt += quot + 1;
+                    }
+                }
+            }
+            symbol = sym;
+            rank_i = __reduce_add_sync(FULL, cnt) + part;
+            found_base = base;
+            break;
+        }
+        off += __shfl_sync(FULL, incl, 31);
+    }
+    if (symbol == NO_SYMBOL) return;
+    // bodies longer than one round: the symbol's runs in the rounds before the one that holds position i
+    for (uint32_t base = 0; base < found_base; base += 512) {
+        const Quad q = load_quad(body + ((base + 16 * lane) >> 4));
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+        uint32_t cnt = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+            const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+            const uint32_t quot = (b * magic) >> 16;
+            if (b - quot * sigma == symbol) cnt += quot + 1;
+        }
+        rank_i += __reduce_add_sync(FULL, cnt);
+    }
+}
+
 // GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568; Record::lf, src/bwt.rs:480-496): same results as
 // walk_sequence(), arranged so that a step costs one memory round trip instead of two or three. A walk is a
 // dependent chain, so its speed is 1 / (latency per step): the descriptor of the current record is always in
 // registers, and as soon as it arrives the descriptors of BOTH successors of an outdegree-2 record are
 // requested together with the body block that decides between them.
+// WARP: all 32 lanes of a warp walk the same sequence with identical state (loads of one address are a single
+// broadcast wavefront); run-length bodies are then scanned by the whole warp (warp_lf_runs8) and the output is
+// written 32 nodes at a time, one per lane, as full 256-byte lines.
+template <bool WARP>
 __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap,
                                                          uint32_t ahead) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t mine = 0;
     if (id >= ix.sequences) return ~0ull;
     gbwt_b200_pos pos;
     if (!gbwt_start(ix, id, pos)) return 0;
@@ -348,8 +449,14 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
     pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
     uint64_t prev_node = node;
     for (;;) {
-        if (n < cap) out[n] = node;
-        n++;
+        if (WARP) {
+            if ((n & 31u) == lane) mine = node;
+            n++;
+            if ((n & 31u) == 0 && n - 32 + lane < cap) out[n - 32 + lane] = mine;
+        } else {
+            if (n < cap) out[n] = node;
+            n++;
+        }
         const uint32_t fmt = d.fmt();
         if (fmt == FMT_EMPTY || offset >= d.total_len()) break;  // GBWT::forward -> None
         const uint32_t i = static_cast<uint32_t>(offset);
@@ -390,6 +497,9 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
             if (fmt == FMT_DENSE2) {
                 const uint32_t ones = dense_rank1(ix.bodies + d.body(), d.body_len(), i, symbol);
                 rank_i = symbol ? ones : i - ones;
+            } else if (WARP && fmt == FMT_RUN8) {
+                warp_lf_runs8(ix, d, i, symbol, rank_i);
+                if (symbol == NO_SYMBOL) break;
             } else {
                 symbol = symbol_at_runs(ix, d, i);
                 if (symbol == NO_SYMBOL) break;
@@ -408,11 +518,26 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
             d = symbol ? d1 : d0;
             continue;
         }
+        if (WARP && fmt == FMT_RUN8) {
+            // outdegree > 2 with a byte-per-run body: the warp scans, then one edge lookup
+            warp_lf_runs8(ix, d, i, symbol, rank_i);
+            if (symbol == NO_SYMBOL) break;
+            e = edge_at(ix, d, symbol);
+            if (e.node == 0) break;
+            offset = static_cast<uint64_t>(e.offset) + rank_i;
+            node = e.node;
+            d = load_desc_of(ix, node);
+            continue;
+        }
         gbwt_b200_pos cur, next;
         cur.node = node; cur.offset = offset;
         if (!gbwt_forward(ix, cur, next)) break;
         node = next.node; offset = next.offset;
         d = load_desc_of(ix, node);
+    }
+    if (WARP) {
+        const uint64_t rem = n & 31u;
+        if (rem != 0 && lane < rem && n - rem + lane < cap) out[n - rem + lane] = mine;
     }
     return n;
 }
@@ -428,6 +553,20 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
                                                  uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t stride,
                                                  uint32_t ahead) {
     const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (stride == 32) {
+        for (size_t i = tid / 32; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / 32) {
+            uint64_t* dst = nullptr;
+            uint64_t cap = 0;
+            if (nodes != nullptr) {
+                const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+                dst = nodes + (lo - base);
+                cap = hi > lo ? hi - lo : 0;
+            }
+            const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), dst, cap, ahead);
+            if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
+        }
+        return;
+    }
     if (tid % stride != 0) return;
     for (size_t i = tid / stride; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / stride) {
         uint64_t* dst = nullptr;
@@ -437,7 +576,7 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
             dst = nodes + (lo - base);
             cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_device(ix, __ldg(ids + i), dst, cap, ahead);
+        const uint64_t len = walk_sequence_device<false>(ix, __ldg(ids + i), dst, cap, ahead);
         if (lengths != nullptr) lengths[i] = len;
     }
 }
