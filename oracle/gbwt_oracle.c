@@ -315,6 +315,11 @@ struct orc_gbwt {
     orc_bwt bwt;
     orc_pos* endmarker; /* src/gbwt.rs:99, 413-414 */
     uint64_t endmarker_len;
+    /* Graph::sequences (src/graph.rs:84-89) when loaded from a GBZ file: concatenated node labels. */
+    int has_graph;
+    uint64_t graph_nodes, n_seq;
+    uint64_t* seq_starts; /* n_seq + 1 */
+    uint8_t* seq_bytes;
 };
 
 #define GBWT_TAG 0x6B376B37u
@@ -557,6 +562,8 @@ void orc_free(orc_gbwt* g) {
     if (!g) return;
     bwt_free(&g->bwt);
     free(g->endmarker);
+    free(g->seq_starts);
+    free(g->seq_bytes);
     free(g);
 }
 
@@ -616,6 +623,8 @@ fail:
     return NULL;
 }
 
+static int load_graph(orc_reader* r, orc_gbwt* g, char* err, size_t errlen);
+
 orc_gbwt* orc_load_bytes(const uint8_t* bytes, size_t len, char* err, size_t errlen) {
     orc_reader r = { bytes, len, 0, 1 };
     if (len < 8) { set_err(err, errlen, "file too short"); return NULL; }
@@ -633,6 +642,7 @@ orc_gbwt* orc_load_bytes(const uint8_t* bytes, size_t len, char* err, size_t err
             set_err(err, errlen, "GBZ: The GBWT index is not bidirectional");
             orc_free(g); return NULL;
         }
+        if (g && !load_graph(&r, g, err, errlen)) { orc_free(g); return NULL; }
         return g;
     }
     return load_gbwt(&r, err, errlen);
@@ -1179,4 +1189,179 @@ void orc_follow_batch(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, 
 #pragma omp parallel for schedule(dynamic, 256) num_threads(t)
     for (int64_t i = 0; i < (int64_t)n; i++)
         (void)orc_follow(g, &states[i], backward, out + offsets[i], offsets[i + 1] - offsets[i]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Graph: node sequences of a GBZ file                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+#include <dlfcn.h>
+
+#define GRAPH_TAG 0x6B3764AFu
+
+/* zstd 0.13 crate = libzstd; the shared library is present without headers, so the two stable entry points
+ * are declared here and resolved with dlopen. */
+static int zstd_decompress(uint8_t* dst, uint64_t dst_len, const uint8_t* src, uint64_t src_len, uint64_t* got) {
+    typedef size_t (*decompress_fn)(void*, size_t, const void*, size_t);
+    typedef unsigned (*iserror_fn)(size_t);
+    static decompress_fn decompress = NULL;
+    static iserror_fn iserror = NULL;
+    if (!decompress) {
+        void* h = dlopen("libzstd.so.1", RTLD_NOW);
+        if (!h) return 0;
+        decompress = (decompress_fn)dlsym(h, "ZSTD_decompress");
+        iserror = (iserror_fn)dlsym(h, "ZSTD_isError");
+        if (!decompress || !iserror) return 0;
+    }
+    size_t n = decompress(dst, (size_t)dst_len, src, (size_t)src_len);
+    if (iserror(n)) return 0;
+    *got = n;
+    return 1;
+}
+
+/* All values of a serialized SparseVector (string start offsets). */
+static uint64_t* rd_sparse_values(orc_reader* r, uint64_t* count) {
+    orc_sparse sv;
+    if (!rd_sparse(r, &sv)) { sparse_free(&sv); return NULL; }
+    uint64_t* out = (uint64_t*)malloc((size_t)(sv.ones + 1) * 8);
+    for (uint64_t i = 0; i < sv.ones; i++) {
+        uint64_t v, dummy;
+        sparse_select_pair(&sv, i, &v, 0, &dummy);
+        out[i] = v;
+    }
+    *count = sv.ones;
+    sparse_free(&sv);
+    return out;
+}
+
+/* Graph::load, src/graph.rs:295-330: header, node sequences (StringArray::decompress for version >= 4,
+ * src/support.rs:545-571; StringArray::load otherwise, src/support.rs:619-643). The segment names and the
+ * node-to-segment mapping that follow are not on the path and are left unread. */
+static int load_graph(orc_reader* r, orc_gbwt* g, char* err, size_t errlen) {
+    uint64_t tv = rd_u64(r);
+    uint32_t tag = (uint32_t)tv, version = (uint32_t)(tv >> 32);
+    g->graph_nodes = rd_u64(r);
+    uint64_t flags = rd_u64(r);
+    if (!r->ok || tag != GRAPH_TAG) { set_err(err, errlen, "GraphHeader: Invalid tag"); return 0; }
+    if (version < 3 || version > 4) { set_err(err, errlen, "GraphHeader: Invalid version"); return 0; }
+    if (flags & ~3ULL) { set_err(err, errlen, "GraphHeader: Invalid flags"); return 0; }
+    if (!(flags & 2ULL)) { set_err(err, errlen, "GraphHeader: SDSL format is not supported"); return 0; }
+    uint64_t n = 0;
+    uint64_t* starts = rd_sparse_values(r, &n);
+    if (!starts) { set_err(err, errlen, "StringArray: invalid index"); return 0; }
+    uint64_t total = 0;
+    uint8_t* bytes = NULL;
+    if (version >= 4) {
+        total = rd_u64(r);
+        uint64_t clen = rd_u64(r);
+        if (!r->ok || (clen + 7) / 8 > (r->len - r->pos) / 8) { free(starts); set_err(err, errlen, "StringArray: invalid data"); return 0; }
+        bytes = (uint8_t*)malloc((size_t)total + 8);
+        uint64_t got = 0;
+        int ok = zstd_decompress(bytes, total, r->p + r->pos, clen, &got);
+        r->pos += (size_t)((clen + 7) / 8) * 8;
+        if (!ok || got != total) {
+            free(starts); free(bytes);
+            set_err(err, errlen, "StringArray: Decompressed string length does not match the expected length");
+            return 0;
+        }
+    } else {
+        uint64_t alen = rd_u64(r);
+        if (!r->ok || (alen + 7) / 8 > (r->len - r->pos) / 8) { free(starts); set_err(err, errlen, "StringArray: invalid alphabet"); return 0; }
+        const uint8_t* alphabet = r->p + r->pos;
+        r->pos += (size_t)((alen + 7) / 8) * 8;
+        total = rd_u64(r);
+        uint64_t width = rd_u64(r), bits = 0, nwords = 0;
+        uint64_t* packed = rd_rawvector(r, &bits, &nwords);
+        if (!r->ok || !packed || width == 0 || width > 64 || bits != total * width) { free(starts); free(packed); set_err(err, errlen, "StringArray: invalid strings"); return 0; }
+        bytes = (uint8_t*)malloc((size_t)total + 8);
+        for (uint64_t i = 0; i < total; i++) {
+            uint64_t bit = i * width, w = bit / 64, off = bit % 64;
+            uint64_t v = packed[w] >> off;
+            if (off + width > 64) v |= packed[w + 1] << (64 - off);
+            if (width < 64) v &= (1ULL << width) - 1;
+            bytes[i] = v < alen ? alphabet[v] : 0;
+        }
+        free(packed);
+    }
+    if (n > 0 && starts[0] != 0) { free(starts); free(bytes); set_err(err, errlen, "StringArray: First string does not start at offset 0"); return 0; }
+    starts[n] = total;
+    /* GBZ::load, src/gbz.rs:690-694 */
+    if (n != (g->alphabet_size - (g->offset + 1)) / 2) {
+        free(starts); free(bytes);
+        set_err(err, errlen, "GBZ: Mismatch between GBWT alphabet size and Graph sequence count");
+        return 0;
+    }
+    g->has_graph = 1; g->n_seq = n; g->seq_starts = starts; g->seq_bytes = bytes;
+    return 1;
+}
+
+int orc_has_graph(const orc_gbwt* g) { return g->has_graph; }
+uint64_t orc_graph_sequences(const orc_gbwt* g) { return g->n_seq; }
+
+/* GBZ::sequence(node_id), src/gbz.rs:292-298 with Graph::sequence (src/graph.rs:124-126). Returns the length
+ * and sets *seq, or -1 for None. */
+int64_t orc_node_sequence(const orc_gbwt* g, uint64_t node_id, const uint8_t** seq) {
+    if (!g->has_graph || !gbz_has_node(g, node_id)) return -1;
+    uint64_t sequence_id = (2 * node_id - (g->offset + 1)) / 2; /* gbwt_node_to_sequence, src/gbz.rs:253-255 */
+    if (sequence_id >= g->n_seq) return -1;
+    *seq = g->seq_bytes + g->seq_starts[sequence_id];
+    return (int64_t)(g->seq_starts[sequence_id + 1] - g->seq_starts[sequence_id]);
+}
+
+/* support::COMPLEMENT, src/support.rs:87-98: upper-case complement, anything else -> 'N'. */
+static uint8_t complement(uint8_t c) {
+    switch (c) {
+    case 'A': case 'a': return 'T';
+    case 'C': case 'c': return 'G';
+    case 'G': case 'g': return 'C';
+    case 'T': case 't': return 'A';
+    default: return 'N';
+    }
+}
+
+/* support::reverse_complement, src/support.rs:104-110. */
+void orc_reverse_complement(const uint8_t* seq, uint64_t len, uint8_t* out) {
+    for (uint64_t i = 0; i < len; i++) out[i] = complement(seq[len - 1 - i]);
+}
+
+/* extract_sequence, src/bin/gbz-extract.rs:173-189, for GBWT sequence `seq_id` (= encode_path(path, orientation)):
+ * the labels of the nodes on the path, reverse-complemented for reverse-oriented nodes, then the endmarker
+ * byte. Writes at most cap bytes and returns the full length, or -1 where gbz.path() is None. */
+int64_t orc_extract_dna(const orc_gbwt* g, uint64_t seq_id, uint8_t endmarker, uint8_t* out, uint64_t cap) {
+    if (!g->has_graph || seq_id >= g->sequences) return -1;
+    uint64_t n = 0;
+    orc_pos pos;
+    int some = orc_start(g, seq_id, &pos);
+    while (some) {
+        const uint8_t* seq = NULL;
+        int64_t len = orc_node_sequence(g, pos.node / 2, &seq); /* the reference unwrap()s */
+        for (int64_t j = 0; j < len; j++) {
+            uint8_t c = (pos.node & 1) ? complement(seq[len - 1 - j]) : seq[j];
+            if (out && n < cap) out[n] = c;
+            n++;
+        }
+        orc_pos next;
+        some = orc_forward(g, pos, &next);
+        pos = next;
+    }
+    if (out && n < cap) out[n] = endmarker;
+    n++;
+    return (int64_t)n;
+}
+
+void orc_dna_lengths(const orc_gbwt* g, const uint64_t* ids, uint64_t m, uint64_t* lengths, int threads) {
+    int t = pick_threads(threads); (void)t;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(t)
+    for (int64_t i = 0; i < (int64_t)m; i++) {
+        int64_t n = orc_extract_dna(g, ids[i], 0, NULL, 0);
+        lengths[i] = n < 0 ? UINT64_MAX : (uint64_t)n;
+    }
+}
+
+void orc_extract_dna_batch(const orc_gbwt* g, const uint64_t* ids, uint64_t m, uint8_t endmarker, const uint64_t* offsets,
+                           uint8_t* out, int threads) {
+    int t = pick_threads(threads); (void)t;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(t)
+    for (int64_t i = 0; i < (int64_t)m; i++)
+        (void)orc_extract_dna(g, ids[i], endmarker, out + offsets[i], offsets[i + 1] - offsets[i]);
 }

@@ -134,6 +134,17 @@ void orc_follow_counts(const orc_gbwt* g, const orc_bdstate* states, uint64_t n,
 void orc_follow_batch(const orc_gbwt* g, const orc_bdstate* states, uint64_t n, int backward, const uint64_t* offsets,
                       orc_bdstate* out, int threads);
 
+/* ---- node sequences and DNA-level extraction (GBZ files; src/graph.rs:295-330, src/gbz.rs:286-298,
+ *      src/support.rs:87-110, src/bin/gbz-extract.rs:173-189) ------------------------------------------- */
+int orc_has_graph(const orc_gbwt* g);
+uint64_t orc_graph_sequences(const orc_gbwt* g);
+int64_t orc_node_sequence(const orc_gbwt* g, uint64_t node_id, const uint8_t** seq);
+void orc_reverse_complement(const uint8_t* seq, uint64_t len, uint8_t* out);
+int64_t orc_extract_dna(const orc_gbwt* g, uint64_t seq_id, uint8_t endmarker, uint8_t* out, uint64_t cap);
+void orc_dna_lengths(const orc_gbwt* g, const uint64_t* ids, uint64_t m, uint64_t* lengths, int threads);
+void orc_extract_dna_batch(const orc_gbwt* g, const uint64_t* ids, uint64_t m, uint8_t endmarker, const uint64_t* offsets,
+                           uint8_t* out, int threads);
+
 /* ---- algorithmic-byte accounting of SURVEY.md 8(d) (measurement helper for bench.py) ------------ */
 uint64_t orc_find_extend_bytes(const orc_gbwt* g, const uint64_t* patterns, uint64_t n, uint64_t k, int threads);
 uint64_t orc_extract_bytes(const orc_gbwt* g, const uint64_t* ids, uint64_t m, int threads);

@@ -119,6 +119,16 @@ def lib(native: bool = False) -> C.CDLL:
         L.orc_follow.argtypes = [p, C.POINTER(BDState), C.c_int, p, u64]
         L.orc_follow_counts.argtypes = [p, p, u64, C.c_int, p, C.c_int]
         L.orc_follow_batch.argtypes = [p, p, u64, C.c_int, p, p, C.c_int]
+        L.orc_has_graph.argtypes = [p]
+        L.orc_graph_sequences.restype = u64
+        L.orc_graph_sequences.argtypes = [p]
+        L.orc_node_sequence.restype = C.c_int64
+        L.orc_node_sequence.argtypes = [p, u64, C.POINTER(C.c_void_p)]
+        L.orc_reverse_complement.argtypes = [p, u64, p]
+        L.orc_extract_dna.restype = C.c_int64
+        L.orc_extract_dna.argtypes = [p, u64, C.c_uint8, p, u64]
+        L.orc_dna_lengths.argtypes = [p, p, u64, p, C.c_int]
+        L.orc_extract_dna_batch.argtypes = [p, p, u64, C.c_uint8, p, p, C.c_int]
         L.orc_find_extend_bytes.restype = u64
         L.orc_find_extend_bytes.argtypes = [p, p, u64, u64, C.c_int]
         L.orc_extract_bytes.restype = u64
@@ -186,6 +196,14 @@ def rle_decode(sigma: int, data: bytes) -> list:
 
 
 # ---- the index ----------------------------------------------------------------------------
+
+def reverse_complement(seq: bytes) -> bytes:
+    """support::reverse_complement, src/support.rs:104-110."""
+    src = np.frombuffer(bytes(seq), dtype=np.uint8).copy()
+    out = np.zeros(len(src), dtype=np.uint8)
+    lib().orc_reverse_complement(_ptr(src), len(src), _ptr(out))
+    return out.tobytes()
+
 
 def _state(s: State) -> tuple:
     return (s.node, s.start, s.end)
@@ -446,6 +464,36 @@ class GBWT:
         out = np.zeros(int(offsets[-1]), dtype=BDSTATE_DTYPE)
         self._L.orc_follow_batch(self._h, _ptr(states), n, 1 if backward else 0, _ptr(offsets), _ptr(out), threads)
         return offsets, out, counts
+
+    # node sequences / DNA (GBZ files)
+    def has_graph(self): return bool(self._L.orc_has_graph(self._h))
+    def graph_sequences(self): return self._L.orc_graph_sequences(self._h)
+
+    def node_sequence(self, node_id):
+        """GBZ::sequence(node_id), src/gbz.rs:292-298."""
+        ptr = C.c_void_p()
+        n = self._L.orc_node_sequence(self._h, node_id, C.byref(ptr))
+        return None if n < 0 else C.string_at(ptr.value, n)
+
+    def extract_dna(self, seq_id, endmarker=0):
+        """extract_sequence of src/bin/gbz-extract.rs:173-189 for GBWT sequence `seq_id`."""
+        n = self._L.orc_extract_dna(self._h, seq_id, endmarker, None, 0)
+        if n < 0:
+            return None
+        out = np.zeros(n, dtype=np.uint8)
+        self._L.orc_extract_dna(self._h, seq_id, endmarker, _ptr(out), n)
+        return out.tobytes()
+
+    def extract_dna_batch(self, ids, endmarker=0, threads: int = 0):
+        ids = _u64(ids)
+        lengths = np.zeros(len(ids), dtype=np.uint64)
+        self._L.orc_dna_lengths(self._h, _ptr(ids), len(ids), _ptr(lengths), threads)
+        sizes = np.where(lengths == np.uint64(2**64 - 1), np.uint64(0), lengths)
+        offsets = np.zeros(len(ids) + 1, dtype=np.uint64)
+        np.cumsum(sizes, out=offsets[1:])
+        out = np.zeros(int(offsets[-1]), dtype=np.uint8)
+        self._L.orc_extract_dna_batch(self._h, _ptr(ids), len(ids), endmarker, _ptr(offsets), _ptr(out), threads)
+        return offsets, out, lengths
 
     def forward_batch(self, positions: np.ndarray, threads: int = 0) -> np.ndarray:
         positions = np.ascontiguousarray(positions, dtype=POS_DTYPE)

@@ -148,3 +148,28 @@ TRANSLATION_PATHS = [
 # src/gbz.rs:1189-1208 (StateIter doc-test on example.gbz): (from, to, len), F = forward
 DOC_STATEITER = dict(node=14, len=3, successors=2,
                      predecessors=[((12, False), (15, False), 2), ((13, False), (16, False), 1)])
+
+# src/graph/tests.rs:21-34 (example.gg; the same Graph is embedded in example.gbz) and :66-79 (translation).
+GRAPH_SEQUENCES = ["G", "A", "T", "T", "A", "C", "A", "", "", "", "G", "A", "T", "T", "A"]
+GRAPH_SEQUENCES_TRANSLATION = ["GA", "T", "T", "A", "CA", "G", "", "", "A", "T", "TA"]
+# src/support/tests.rs:13-42
+REVERSE_COMPLEMENTS = [(b"", b""), (b"C", b"G"), (b"GATTACA", b"TGTAATC"), (b"GATTACAT", b"ATGTAATC")]
+
+
+def complement_table():
+    """support::COMPLEMENT, src/support.rs:87-98 (restated as data for the tests)."""
+    table = bytearray(b"N" * 256)
+    for a, b in (("A", "T"), ("C", "G"), ("G", "C"), ("T", "A")):
+        table[ord(a)] = ord(b)
+        table[ord(a.lower())] = ord(b)
+    return bytes(table)
+
+
+def true_dna(node_sequence, path, endmarker=b"\x00"):
+    """extract_sequence of src/bin/gbz-extract.rs:173-189 over a list of GBWT node identifiers."""
+    table = complement_table()
+    out = bytearray()
+    for node in path:
+        seq = node_sequence(node // 2)
+        out += seq[::-1].translate(table) if node & 1 else seq
+    return bytes(out) + endmarker
