@@ -86,6 +86,14 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_forward_device": (i, [p, p, sz, p, p]),
         "gbwt_b200_sequence_lengths_device": (i, [p, p, sz, p, p]),
         "gbwt_b200_extract_device": (i, [p, p, sz, p, p, p, p]),
+        "gbwt_b200_index_attach_graph": (i, [p, u64, p, p]),
+        "gbwt_b200_has_graph": (i, [p]), "gbwt_b200_graph_sequences": (u64, [p]), "gbwt_b200_graph_bytes": (u64, [p]),
+        "gbwt_b200_node_sequence_lengths": (i, [p, p, sz, p]),
+        "gbwt_b200_node_sequences": (i, [p, p, sz, p, p, p]),
+        "gbwt_b200_dna_lengths": (i, [p, p, sz, p]),
+        "gbwt_b200_extract_dna": (i, [p, p, sz, C.c_uint8, p, p, p]),
+        "gbwt_b200_dna_lengths_device": (i, [p, p, sz, p, p]),
+        "gbwt_b200_extract_dna_device": (i, [p, p, sz, C.c_uint8, p, p, p, p]),
         "gbwt_b200_host_alloc": (p, [sz]), "gbwt_b200_host_free": (None, [p]),
         "gbwt_b200_kernel_launches": (u64, []), "gbwt_b200_version": (C.c_char_p, []),
     }
@@ -232,6 +240,16 @@ class GBWT:
         cls._check(_lib.gbwt_b200_index_from_parts(sequences, size, offset, alphabet_size, flags, _ptr(data), data.nbytes,
                                                    _ptr(starts), len(starts), device, _LAYOUTS[layout], C.byref(h)))
         return cls(h.value)
+
+    def attach_graph(self, label_starts, label_bytes) -> "GBWT":
+        """Node labels for an index built from parts (the Graph half of a GBZ): label i = bytes[starts[i]:starts[i+1]]."""
+        starts = _u64(label_starts)
+        data = np.ascontiguousarray(np.frombuffer(bytes(label_bytes), dtype=np.uint8)) if not isinstance(label_bytes, np.ndarray) \
+            else np.ascontiguousarray(label_bytes, dtype=np.uint8)
+        if len(starts) == 0 or int(starts[-1]) != data.nbytes:
+            raise ValueError("label_starts must hold one entry per label plus the total length")
+        self._check(_lib.gbwt_b200_index_attach_graph(self._h, len(starts) - 1, _ptr(starts), _ptr(data)))
+        return self
 
     def close(self):
         if getattr(self, "_h", None):
@@ -414,6 +432,68 @@ class GBWT:
             return None
         _, nodes, _ = self.extract(np.array([seq_id], dtype=np.uint64))
         return iter(int(x) for x in nodes)
+
+    # -- node sequences and DNA-level extraction (GBZ files; src/gbz.rs:286-306, src/bin/gbz-extract.rs:173-189) --
+    def has_graph(self) -> bool: return bool(_lib.gbwt_b200_has_graph(self._h))
+    def graph_sequences(self) -> int: return _lib.gbwt_b200_graph_sequences(self._h)
+
+    def node_sequence_lengths(self, node_ids) -> np.ndarray:
+        ids = _u64(node_ids)
+        out = np.zeros(len(ids), np.uint64)
+        self._check(_lib.gbwt_b200_node_sequence_lengths(self._h, _ptr(ids), len(ids), _ptr(out)))
+        return out
+
+    def node_sequences(self, node_ids):
+        """GBZ::sequence for many original-graph node ids: (offsets, bytes, lengths); UINT64_MAX length = None."""
+        ids = _u64(node_ids)
+        lengths = self.node_sequence_lengths(ids)
+        offsets = np.zeros(len(ids) + 1, np.uint64)
+        np.cumsum(np.where(lengths == _U64MAX, np.uint64(0), lengths), out=offsets[1:])
+        data = np.zeros(int(offsets[-1]), np.uint8)
+        got = np.zeros(len(ids), np.uint64)
+        self._check(_lib.gbwt_b200_node_sequences(self._h, _ptr(ids), len(ids), _ptr(offsets), _ptr(data), _ptr(got)))
+        return offsets, data, got
+
+    def sequence_len(self, node_id: int) -> Optional[int]:
+        """GBZ::sequence_len (src/gbz.rs:301-306)."""
+        n = int(self.node_sequence_lengths([node_id])[0])
+        return None if n == int(_U64MAX) else n
+
+    def node_sequence(self, node_id: int) -> Optional[bytes]:
+        """GBZ::sequence (src/gbz.rs:292-298)."""
+        _, data, got = self.node_sequences([node_id])
+        return None if got[0] == _U64MAX else data.tobytes()
+
+    def dna_lengths(self, seq_ids) -> np.ndarray:
+        ids = _u64(seq_ids)
+        out = np.zeros(len(ids), np.uint64)
+        self._check(_lib.gbwt_b200_dna_lengths(self._h, _ptr(ids), len(ids), _ptr(out)))
+        return out
+
+    def extract_dna(self, seq_ids, endmarker: int = 0, lengths=None):
+        """extract_sequence of gbz-extract for many GBWT sequence ids: (offsets, bytes, lengths)."""
+        ids = _u64(seq_ids)
+        if lengths is None:
+            lengths = self.dna_lengths(ids)
+        offsets = np.zeros(len(ids) + 1, np.uint64)
+        np.cumsum(np.where(lengths == _U64MAX, np.uint64(0), lengths), out=offsets[1:])
+        data = np.zeros(int(offsets[-1]), np.uint8)
+        got = np.zeros(len(ids), np.uint64)
+        self._check(_lib.gbwt_b200_extract_dna(self._h, _ptr(ids), len(ids), endmarker, _ptr(offsets), _ptr(data), _ptr(got)))
+        return offsets, data, got
+
+    def path_dna(self, seq_id: int, endmarker: int = 0) -> Optional[bytes]:
+        """extract_sequence(gbz, path_id, orientation) with seq_id = encode_path(path_id, orientation); None if no such path."""
+        if seq_id >= self.sequences():
+            return None
+        _, data, _ = self.extract_dna([seq_id], endmarker)
+        return data.tobytes()
+
+    def dna_lengths_device(self, d_ids: int, m: int, d_lengths: int, stream: int = 0):
+        self._check(_lib.gbwt_b200_dna_lengths_device(self._h, d_ids, m, d_lengths, stream))
+
+    def extract_dna_device(self, d_ids: int, m: int, endmarker: int, d_out_offsets: int, d_bytes: int, d_lengths: int, stream: int = 0):
+        self._check(_lib.gbwt_b200_extract_dna_device(self._h, d_ids, m, endmarker, d_out_offsets, d_bytes, d_lengths, stream))
 
     # -- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr(); stream = cudaStream_t) --
     def find_extend_device(self, d_patterns: int, n: int, k: int, d_out: int, stream: int = 0):

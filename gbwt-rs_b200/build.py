@@ -30,7 +30,7 @@ def nvcc_path() -> str:
 def command(out: str = OUT, extra=()):
     return [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O3,-fvisibility=hidden,-Wall", "-Xptxas", "-v",
-            "-shared", "-o", out, *extra, *SOURCES, "-lgomp"]
+            "-shared", "-o", out, *extra, *SOURCES, "-lgomp", "-ldl"]
 
 
 def is_stale() -> bool:

@@ -30,6 +30,11 @@ struct gbwt_b200_index {
     void* d_bodies = nullptr;
     void* d_edges = nullptr;
     void* d_endmarker = nullptr;
+    void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
+    void* d_label_bytes = nullptr;
+    bool has_graph = false;
+    GraphView graph{};
+    uint64_t graph_bytes = 0;
     uint64_t bytes[4] = {0, 0, 0, 0};
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
 };
@@ -258,6 +263,25 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
     return launch_done("k_extract");
 }
 
+int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
+                       uint8_t endmarker, uint8_t* bytes, uint64_t* lengths, cudaStream_t s) {
+    if (m == 0) return GBWT_B200_OK;
+    // One warp per sequence. One-warp CTAs spread few chains over all SMs; with more chains than the SMs hold
+    // that way (32 CTAs each), four warps per CTA double the chains in flight.
+    const int block = m > static_cast<size_t>(ix->sm_count) * 32 ? 128 : 32;
+    const size_t ctas = (m * 32 + block - 1) / block;
+    const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
+    k_extract_dna<<<static_cast<unsigned>(std::min<size_t>(ctas, size_t(1) << 30)), block, 0, s>>>(
+        ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
+    return launch_done("k_extract_dna");
+}
+int launch_node_sequences(const gbwt_b200_index* ix, const uint64_t* node_ids, size_t n, const uint64_t* out_offsets, uint64_t base,
+                          uint8_t* bytes, uint64_t* lengths, cudaStream_t s) {
+    if (n == 0) return GBWT_B200_OK;
+    k_node_sequences<<<grid_for(ix, n * 32), BLOCK_THREADS, 0, s>>>(ix->view, ix->graph, node_ids, n, out_offsets, base, bytes, lengths);
+    return launch_done("k_node_sequences");
+}
+
 // ---- host <-> device pipeline ----------------------------------------------------------------------
 
 // A fixed-size-per-item array on the host side of a batched call.
@@ -397,6 +421,60 @@ int run_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, const uint64_t*
     return rc;
 }
 
+// Batches whose item i produces a variable number of `elem_bytes`-sized elements into out[offsets[i] .. offsets[i+1]):
+// ids up, results down, in chunks bounded by free HBM. `launch(d_ids, count, d_offsets, base, d_out, d_lengths, stream)`.
+template <class Launch>
+int run_ragged_output(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, void* out,
+                      size_t elem_bytes, uint64_t* lengths, Launch launch) {
+    if (m == 0) return GBWT_B200_OK;
+    if (ids == nullptr || out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    if (!offsets_valid(out_offsets, m)) return fail(GBWT_B200_E_ARGUMENT, "out_offsets must be non-decreasing");
+    if (out_offsets[m] > out_offsets[0] && out == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    size_t free_bytes = 0, total_bytes = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_bytes, &total_bytes));
+    const uint64_t elem_budget = std::max<uint64_t>(uint64_t(1) << 20, (free_bytes / elem_bytes) * 6 / 10);
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = GBWT_B200_OK;
+    for (size_t i0 = 0; i0 < m && rc == GBWT_B200_OK;) {
+        // all chains of the chunk in one launch: a path walk is latency-bound, so concurrency is everything
+        const size_t i1 = ragged_chunk_end(out_offsets, m, i0, m, elem_budget);
+        const size_t count = i1 - i0;
+        const uint64_t base = out_offsets[i0], cap = out_offsets[i1] - base;
+        uint64_t *d_ids = nullptr, *d_offsets = nullptr, *d_lengths = nullptr;
+        void* d_out = nullptr;
+        auto alloc = [&](void** p, size_t bytes) {
+            cudaError_t e = cudaMallocAsync(p, std::max<size_t>(16, bytes), s);
+            if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaMallocAsync");
+        };
+        alloc(reinterpret_cast<void**>(&d_ids), count * 8); alloc(reinterpret_cast<void**>(&d_offsets), (count + 1) * 8);
+        alloc(&d_out, cap * elem_bytes); alloc(reinterpret_cast<void**>(&d_lengths), count * 8);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaMemcpyAsync(d_ids, ids + i0, count * 8, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, out_offsets + i0, (count + 1) * 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
+        }
+        if (rc == GBWT_B200_OK) rc = launch(d_ids, count, d_offsets, base, d_out, d_lengths, s);
+        if (rc == GBWT_B200_OK) {
+            cudaError_t e = cudaSuccess;
+            if (cap > 0) e = cudaMemcpyAsync(static_cast<char*>(out) + base * elem_bytes, d_out, cap * elem_bytes, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && lengths != nullptr) e = cudaMemcpyAsync(lengths + i0, d_lengths, count * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
+        }
+        if (d_ids) cudaFreeAsync(d_ids, s);
+        if (d_offsets) cudaFreeAsync(d_offsets, s);
+        if (d_out) cudaFreeAsync(d_out, s);
+        if (d_lengths) cudaFreeAsync(d_lengths, s);
+        i0 = i1;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(s);
+    return rc;
+}
+
 int check_index(const gbwt_b200_index* ix) {
     if (ix == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null index handle");
     return GBWT_B200_OK;
@@ -413,6 +491,30 @@ int upload(void** d, const void* h, size_t bytes, uint64_t& accounted) {
     accounted = bytes;
     CUDA_TRY(cudaMalloc(d, std::max<size_t>(bytes, 256)));
     if (bytes > 0) CUDA_TRY(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return GBWT_B200_OK;
+}
+
+// Node labels into HBM: starts[0 .. sequences] and the concatenated bytes (the caller has validated them).
+int attach_graph(gbwt_b200_index* ix, const uint64_t* starts, uint64_t sequences, const uint8_t* label_bytes) {
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
+    ix->d_label_starts = ix->d_label_bytes = nullptr;
+    ix->has_graph = false;
+    uint64_t a = 0, b = 0;
+    int rc = upload(&ix->d_label_starts, starts, (sequences + 1) * 8, a);
+    if (rc == GBWT_B200_OK) rc = upload(&ix->d_label_bytes, label_bytes, starts[sequences], b);
+    if (rc != GBWT_B200_OK) return rc;
+    ix->graph.starts = static_cast<const uint64_t*>(ix->d_label_starts);
+    ix->graph.bytes = static_cast<const uint8_t*>(ix->d_label_bytes);
+    ix->graph.sequences = sequences;
+    ix->graph_bytes = a + b;
+    ix->has_graph = true;
+    return GBWT_B200_OK;
+}
+
+int check_graph(const gbwt_b200_index* ix) {
+    if (!ix->has_graph) return fail(GBWT_B200_E_NO_GRAPH, "the index was not loaded from a GBZ file: no node sequences");
     return GBWT_B200_OK;
 }
 
@@ -467,6 +569,10 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     v.sequences = parsed.sequences;
     v.endmarker_len = layout.endmarker.size();
     v.bidirectional = (parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
+    if (parsed.has_graph) {
+        rc = attach_graph(ix, parsed.label_starts.data(), parsed.label_starts.size() - 1, parsed.label_bytes.data());
+        if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+    }
     *out = ix;
     return GBWT_B200_OK;
 }
@@ -517,9 +623,26 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     {
         DeviceScope scope(ix->device);
         cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker);
+        cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;
 }
+
+int gbwt_b200_index_attach_graph(gbwt_b200_index* ix, uint64_t sequences, const uint64_t* label_starts, const uint8_t* label_bytes) {
+    if (int rc = check_index(ix)) return rc;
+    if (label_starts == nullptr || (label_starts[sequences] > 0 && label_bytes == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null input");
+    if (label_starts[0] != 0) return fail(GBWT_B200_E_INVALID_DATA, "StringArray: First string does not start at offset 0");
+    if (!offsets_valid(label_starts, sequences)) return fail(GBWT_B200_E_INVALID_DATA, "StringArray: invalid index");
+    // GBZ::load, src/gbz.rs:686-694
+    if (!(ix->flags & GBWT_FLAG_BIDIRECTIONAL)) return fail(GBWT_B200_E_INVALID_DATA, "GBZ: The GBWT index is not bidirectional");
+    if (sequences != (ix->alphabet_size - (ix->offset + 1)) / 2)
+        return fail(GBWT_B200_E_INVALID_DATA, "GBZ: Mismatch between GBWT alphabet size and Graph sequence count");
+    return attach_graph(ix, label_starts, sequences, label_bytes);
+}
+
+int gbwt_b200_has_graph(const gbwt_b200_index* ix) { return ix && ix->has_graph; }
+uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* ix) { return ix && ix->has_graph ? ix->graph.sequences : 0; }
+uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* ix) { return ix ? ix->graph_bytes : 0; }
 
 const char* gbwt_b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -608,6 +731,19 @@ int gbwt_b200_extract_device(const gbwt_b200_index* ix, const uint64_t* d_seq_id
     DEVICE_ENTRY_PROLOGUE(ix);
     if (d_nodes == nullptr || d_out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
     return launch_extract(ix, d_seq_ids, m, d_out_offsets, 0, d_nodes, d_lengths, static_cast<cudaStream_t>(stream));
+}
+
+int gbwt_b200_dna_lengths_device(const gbwt_b200_index* ix, const uint64_t* d_seq_ids, size_t m, uint64_t* d_lengths, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_graph(ix)) return rc;
+    return launch_extract_dna(ix, d_seq_ids, m, nullptr, 0, 0, nullptr, d_lengths, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_extract_dna_device(const gbwt_b200_index* ix, const uint64_t* d_seq_ids, size_t m, uint8_t endmarker,
+                                 const uint64_t* d_out_offsets, uint8_t* d_bytes, uint64_t* d_lengths, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    if (int rc = check_graph(ix)) return rc;
+    if (d_bytes == nullptr || d_out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    return launch_extract_dna(ix, d_seq_ids, m, d_out_offsets, 0, endmarker, d_bytes, d_lengths, static_cast<cudaStream_t>(stream));
 }
 
 // ---- host entry points -------------------------------------------------------------------------------
@@ -792,50 +928,50 @@ int gbwt_b200_sequence_lengths(const gbwt_b200_index* ix, const uint64_t* seq_id
 int gbwt_b200_extract(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t m, const uint64_t* out_offsets, uint64_t* nodes,
                       uint64_t* lengths) {
     if (int rc = check_index(ix)) return rc;
-    if (m == 0) return GBWT_B200_OK;
-    if (seq_ids == nullptr || out_offsets == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null array");
-    if (!offsets_valid(out_offsets, m)) return fail(GBWT_B200_E_ARGUMENT, "out_offsets must be non-decreasing");
-    if (out_offsets[m] > out_offsets[0] && nodes == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
-    DeviceScope scope(ix->device);
-    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
-    size_t free_bytes = 0, total_bytes = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_bytes, &total_bytes));
-    const uint64_t node_budget = std::max<uint64_t>(uint64_t(1) << 20, (free_bytes / 8) * 6 / 10);
-    cudaStream_t s;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    int rc = GBWT_B200_OK;
-    for (size_t i0 = 0; i0 < m && rc == GBWT_B200_OK;) {
-        const size_t i1 = ragged_chunk_end(out_offsets, m, i0, m, node_budget);
-        const size_t count = i1 - i0;
-        const uint64_t base = out_offsets[i0], cap = out_offsets[i1] - base;
-        uint64_t *d_ids = nullptr, *d_offsets = nullptr, *d_nodes = nullptr, *d_lengths = nullptr;
-        auto alloc = [&](uint64_t** p, size_t words) {
-            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(16, words * 8), s);
-            if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaMallocAsync");
-        };
-        alloc(&d_ids, count); alloc(&d_offsets, count + 1); alloc(&d_nodes, cap); alloc(&d_lengths, count);
-        if (rc == GBWT_B200_OK) {
-            cudaError_t e = cudaMemcpyAsync(d_ids, seq_ids + i0, count * 8, cudaMemcpyHostToDevice, s);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, out_offsets + i0, (count + 1) * 8, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
-        }
-        if (rc == GBWT_B200_OK) rc = launch_extract(ix, d_ids, count, d_offsets, base, d_nodes, d_lengths, s);
-        if (rc == GBWT_B200_OK) {
-            cudaError_t e = cudaSuccess;
-            if (cap > 0) e = cudaMemcpyAsync(nodes + base, d_nodes, cap * 8, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess && lengths != nullptr) e = cudaMemcpyAsync(lengths + i0, d_lengths, count * 8, cudaMemcpyDeviceToHost, s);
-            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
-        }
-        if (d_ids) cudaFreeAsync(d_ids, s);
-        if (d_offsets) cudaFreeAsync(d_offsets, s);
-        if (d_nodes) cudaFreeAsync(d_nodes, s);
-        if (d_lengths) cudaFreeAsync(d_lengths, s);
-        i0 = i1;
-    }
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess && rc == GBWT_B200_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
-    cudaStreamDestroy(s);
-    return rc;
+    return run_ragged_output(ix, seq_ids, m, out_offsets, nodes, sizeof(uint64_t), lengths,
+                             [&](const uint64_t* d_ids, size_t count, const uint64_t* d_offsets, uint64_t base, void* d_out, uint64_t* d_lengths, cudaStream_t s) {
+                                 return launch_extract(ix, d_ids, count, d_offsets, base, static_cast<uint64_t*>(d_out), d_lengths, s);
+                             });
+}
+
+int gbwt_b200_dna_lengths(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t m, uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_graph(ix)) return rc;
+    if (m > 0 && (seq_ids == nullptr || lengths == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{seq_ids, nullptr, 8}, {nullptr, lengths, 8}};
+    return run_chunked(ix, m, arrays, std::max<size_t>(m, 1), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_extract_dna(ix, static_cast<uint64_t*>(d[0]), count, nullptr, 0, 0, nullptr, static_cast<uint64_t*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_extract_dna(const gbwt_b200_index* ix, const uint64_t* seq_ids, size_t m, uint8_t endmarker, const uint64_t* out_offsets,
+                          uint8_t* bytes, uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_graph(ix)) return rc;
+    return run_ragged_output(ix, seq_ids, m, out_offsets, bytes, 1, lengths,
+                             [&](const uint64_t* d_ids, size_t count, const uint64_t* d_offsets, uint64_t base, void* d_out, uint64_t* d_lengths, cudaStream_t s) {
+                                 return launch_extract_dna(ix, d_ids, count, d_offsets, base, endmarker, static_cast<uint8_t*>(d_out), d_lengths, s);
+                             });
+}
+
+int gbwt_b200_node_sequence_lengths(const gbwt_b200_index* ix, const uint64_t* node_ids, size_t n, uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_graph(ix)) return rc;
+    if (n > 0 && (node_ids == nullptr || lengths == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{node_ids, nullptr, 8}, {nullptr, lengths, 8}};
+    return run_chunked(ix, n, arrays, chunk_for(16), [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_node_sequences(ix, static_cast<uint64_t*>(d[0]), count, nullptr, 0, nullptr, static_cast<uint64_t*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_node_sequences(const gbwt_b200_index* ix, const uint64_t* node_ids, size_t n, const uint64_t* out_offsets, uint8_t* bytes,
+                             uint64_t* lengths) {
+    if (int rc = check_index(ix)) return rc;
+    if (int rc = check_graph(ix)) return rc;
+    return run_ragged_output(ix, node_ids, n, out_offsets, bytes, 1, lengths,
+                             [&](const uint64_t* d_ids, size_t count, const uint64_t* d_offsets, uint64_t base, void* d_out, uint64_t* d_lengths, cudaStream_t s) {
+                                 return launch_node_sequences(ix, d_ids, count, d_offsets, base, static_cast<uint8_t*>(d_out), d_lengths, s);
+                             });
 }
 
 // ---- utilities ---------------------------------------------------------------------------------------

@@ -427,6 +427,101 @@ __device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d
     }
 }
 
+// ---- what a walk does with the nodes it visits -------------------------------------------------------
+// A warp-mode walk parks node n in lane n % 32 and hands the sink 32 nodes at a time (`count` < 32 only for
+// the last group); a one-lane walk hands over every node as it is visited.
+
+// GBWT::sequence(id): the node identifiers themselves, one full 256-byte line per group.
+struct NodeSink {
+    uint64_t* out;
+    uint64_t cap;
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (lane < count && first + lane < cap) out[first + lane] = mine;
+    }
+    __device__ __forceinline__ void one(uint64_t node, uint64_t n) {
+        if (n < cap) out[n] = node;
+    }
+};
+
+// Node labels of the graph in HBM: label i = bytes[starts[i] .. starts[i + 1]) (Graph::sequence, src/graph.rs:124-126).
+struct GraphView {
+    const uint64_t* starts;  // [sequences + 1]
+    const uint8_t* bytes;
+    uint64_t sequences;
+};
+
+// support::COMPLEMENT, src/support.rs:87-98, as arithmetic (a 256-entry table indexed per lane would serialise in
+// the constant cache): both cases of A/C/G/T map to the upper-case complement, every other byte to 'N'.
+__device__ __forceinline__ uint32_t complement_base(uint32_t c) {
+    const uint32_t u = c & 0xDFu;  // 'a'..'z' -> 'A'..'Z'; no other byte lands on A, C, G or T
+    uint32_t r = 'N';
+    r = (u == 'A') ? 'T' : r;
+    r = (u == 'C') ? 'G' : r;
+    r = (u == 'G') ? 'C' : r;
+    r = (u == 'T') ? 'A' : r;
+    return r;
+}
+
+// extract_sequence (src/bin/gbz-extract.rs:173-189): the labels of the visited nodes, reverse-complemented for
+// reverse-oriented nodes (support::reverse_complement, src/support.rs:104-110). Per group of 32 nodes: every lane
+// fetches the label range of its node (32 independent loads instead of one per step of the chain), a warp scan
+// turns the lengths into output offsets, and the warp then writes the group's bytes as consecutive 32-byte
+// rows, each lane finding the node that owns its byte by a 5-step search over the scanned lengths.
+struct DnaSink {
+    GraphView graph;
+    uint64_t node_base;  // alphabet offset + 1: GBZ::gbwt_node_to_sequence, src/gbz.rs:253-255
+    uint8_t* out;        // nullptr: count only
+    uint64_t cap;
+    uint64_t written;
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t) {
+        constexpr unsigned FULL = 0xFFFFFFFFu;
+        const uint32_t lane = threadIdx.x & 31u;
+        uint64_t lo = 0;
+        uint32_t len = 0;
+        if (lane < count) {
+            const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
+            if (sid < graph.sequences) {
+                lo = __ldg(graph.starts + sid);
+                len = static_cast<uint32_t>(__ldg(graph.starts + sid + 1) - lo);
+            }
+        }
+        uint32_t incl = len;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (out != nullptr) {
+            const uint32_t lo_lo = static_cast<uint32_t>(lo), lo_hi = static_cast<uint32_t>(lo >> 32);
+            const uint32_t rev = static_cast<uint32_t>(mine & 1u);
+            for (uint32_t row = 0; row < total; row += 32) {
+                const uint32_t b = row + lane;
+                // owner = number of nodes that end at or before byte b (incl is non-decreasing over the lanes)
+                uint32_t owner = 0;
+#pragma unroll
+                for (uint32_t step = 16; step != 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, incl, (owner + step - 1) & 31u);
+                    if (v <= b) owner += step;
+                }
+                const uint32_t src = owner & 31u;
+                const uint32_t o_incl = __shfl_sync(FULL, incl, src), o_len = __shfl_sync(FULL, len, src);
+                const uint64_t o_lo = (static_cast<uint64_t>(__shfl_sync(FULL, lo_hi, src)) << 32) | __shfl_sync(FULL, lo_lo, src);
+                const uint32_t o_rev = __shfl_sync(FULL, rev, src);
+                if (b < total && written + b < cap) {
+                    const uint32_t within = b - (o_incl - o_len);
+                    uint32_t c;
+                    if (o_rev) c = complement_base(__ldg(graph.bytes + o_lo + (o_len - 1 - within)));
+                    else c = __ldg(graph.bytes + o_lo + within);
+                    out[written + b] = static_cast<uint8_t>(c);
+                }
+            }
+        }
+        written += total;
+    }
+};
+
 // GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568; Record::lf, src/bwt.rs:480-496): same results as
 // walk_sequence(), arranged so that a step costs one memory round trip instead of two or three. A walk is a
 // dependent chain, so its speed is 1 / (latency per step): the descriptor of the current record is always in
@@ -435,9 +530,8 @@ __device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d
 // WARP: all 32 lanes of a warp walk the same sequence with identical state (loads of one address are a single
 // broadcast wavefront); run-length bodies are then scanned by the whole warp (warp_lf_runs8) and the output is
 // written 32 nodes at a time, one per lane, as full 256-byte lines.
-template <bool WARP>
-__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap,
-                                                         uint32_t ahead) {
+template <bool WARP, class Sink>
+__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t mine = 0;
     if (id >= ix.sequences) return ~0ull;
@@ -449,12 +543,12 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
     pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
     uint64_t prev_node = node;
     for (;;) {
-        if (WARP) {
+        if constexpr (WARP) {
             if ((n & 31u) == lane) mine = node;
             n++;
-            if ((n & 31u) == 0 && n - 32 + lane < cap) out[n - 32 + lane] = mine;
+            if ((n & 31u) == 0) sink.group(mine, 32, n - 32);
         } else {
-            if (n < cap) out[n] = node;
+            sink.one(node, n);
             n++;
         }
         const uint32_t fmt = d.fmt();
@@ -536,8 +630,8 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
         d = load_desc_of(ix, node);
     }
     if (WARP) {
-        const uint64_t rem = n & 31u;
-        if (rem != 0 && lane < rem && n - rem + lane < cap) out[n - rem + lane] = mine;
+        const uint32_t rem = static_cast<uint32_t>(n & 31u);
+        if (rem != 0) sink.group(mine, rem, n - rem);
     }
     return n;
 }
@@ -555,29 +649,83 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
     const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (stride == 32) {
         for (size_t i = tid / 32; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / 32) {
-            uint64_t* dst = nullptr;
-            uint64_t cap = 0;
+            NodeSink sink{nullptr, 0};
             if (nodes != nullptr) {
                 const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
-                dst = nodes + (lo - base);
-                cap = hi > lo ? hi - lo : 0;
+                sink.out = nodes + (lo - base);
+                sink.cap = hi > lo ? hi - lo : 0;
             }
-            const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), dst, cap, ahead);
+            const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), sink, ahead);
             if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
         }
         return;
     }
     if (tid % stride != 0) return;
     for (size_t i = tid / stride; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / stride) {
-        uint64_t* dst = nullptr;
-        uint64_t cap = 0;
+        NodeSink sink{nullptr, 0};
         if (nodes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
-            dst = nodes + (lo - base);
-            cap = hi > lo ? hi - lo : 0;
+            sink.out = nodes + (lo - base);
+            sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_device<false>(ix, __ldg(ids + i), dst, cap, ahead);
+        const uint64_t len = walk_sequence_device<false>(ix, __ldg(ids + i), sink, ahead);
         if (lengths != nullptr) lengths[i] = len;
+    }
+}
+
+// K4. extract_sequence of src/bin/gbz-extract.rs:173-189 for many GBWT sequences: one warp per sequence walks the
+// path (K3) and spells the node labels as it goes, then appends the endmarker byte. lengths[i] = bytes of the
+// full result (endmarker included), UINT64_MAX where GBZ::path is None; `bytes == nullptr` only measures.
+__global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView graph, const uint64_t* __restrict__ ids, size_t m,
+                                                      const uint64_t* __restrict__ out_offsets, uint64_t base, uint32_t endmarker,
+                                                      uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths, uint32_t ahead) {
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
+    for (size_t i = warp; i < m; i += warps) {
+        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0};
+        if (bytes != nullptr) {
+            const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+            sink.out = bytes + (lo - base);
+            sink.cap = hi > lo ? hi - lo : 0;
+        }
+        const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), sink, ahead);
+        if ((threadIdx.x & 31u) != 0) continue;
+        if (len == ~0ull) {
+            if (lengths != nullptr) lengths[i] = ~0ull;
+            continue;
+        }
+        if (sink.out != nullptr && sink.written < sink.cap) sink.out[sink.written] = static_cast<uint8_t>(endmarker);
+        if (lengths != nullptr) lengths[i] = sink.written + 1;
+    }
+}
+
+// GBZ::sequence(node_id) for a batch of original-graph node identifiers (src/gbz.rs:286-298): lengths[i] = label
+// length, UINT64_MAX where the reference returns None (no such node: outside the alphabet or an empty record);
+// with `bytes`, label i is copied to bytes[out_offsets[i] - base ..), truncated to its slot. One warp per node.
+__global__ void k_node_sequences(IndexView ix, GraphView graph, const uint64_t* __restrict__ node_ids, size_t n,
+                                 const uint64_t* __restrict__ out_offsets, uint64_t base, uint8_t* __restrict__ bytes,
+                                 uint64_t* __restrict__ lengths) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
+    for (size_t i = warp; i < n; i += warps) {
+        const uint64_t id = __ldg(node_ids + i);
+        uint64_t len = ~0ull, lo = 0;
+        // GBZ::has_node: inside the alphabet and a non-empty record
+        if (id <= (~0ull >> 1) && 2 * id > ix.offset && 2 * id < ix.alphabet_size) {
+            const uint64_t sid = (2 * id - (ix.offset + 1)) >> 1;
+            const Desc d = load_desc_of(ix, 2 * id);
+            if (d.fmt() != FMT_EMPTY && sid < graph.sequences) {
+                lo = __ldg(graph.starts + sid);
+                len = __ldg(graph.starts + sid + 1) - lo;
+            }
+        }
+        if (lane == 0 && lengths != nullptr) lengths[i] = len;
+        if (bytes == nullptr || len == ~0ull) continue;
+        const uint64_t o_lo = __ldg(out_offsets + i), o_hi = __ldg(out_offsets + i + 1);
+        const uint64_t cap = o_hi > o_lo ? o_hi - o_lo : 0;
+        const uint64_t count = len < cap ? len : cap;
+        for (uint64_t j = lane; j < count; j += 32) bytes[o_lo - base + j] = __ldg(graph.bytes + lo + j);
     }
 }
 

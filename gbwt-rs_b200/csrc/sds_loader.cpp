@@ -1,6 +1,8 @@
 // sds_loader.cpp -- see sds_loader.h.
 #include "sds_loader.h"
 
+#include <dlfcn.h>
+
 #include <cstring>
 
 #include "../../include/gbwt_b200.h"
@@ -8,7 +10,7 @@
 namespace gbwt_b200 {
 namespace {
 
-constexpr uint32_t TAG_GBWT = 0x6B376B37u, TAG_GBZ = 0x205A4247u;
+constexpr uint32_t TAG_GBWT = 0x6B376B37u, TAG_GBZ = 0x205A4247u, TAG_GRAPH = 0x6B3764AFu;
 
 // Sequential reader over 64-bit little-endian "elements"; every structure in the format is a whole
 // number of elements and most can be skipped by their declared size.
@@ -129,6 +131,119 @@ int parse_gbwt(Cursor& c, ParsedGBWT& out, std::string& err) {
     return GBWT_B200_OK;
 }
 
+// The reference decompresses node labels with the zstd crate (= libzstd). The image has the shared library
+// but not its headers, so the two stable entry points are resolved at run time; a GBZ file with compressed
+// labels fails to load with a clear message when the library is missing.
+struct ZstdApi {
+    size_t (*decompress)(void*, size_t, const void*, size_t) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    ZstdApi() {
+        void* lib = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (lib == nullptr) lib = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+        if (lib == nullptr) return;
+        decompress = reinterpret_cast<decltype(decompress)>(dlsym(lib, "ZSTD_decompress"));
+        is_error = reinterpret_cast<decltype(is_error)>(dlsym(lib, "ZSTD_isError"));
+    }
+};
+
+bool zstd_decompress(uint8_t* dst, size_t dst_len, const uint8_t* src, size_t src_len, size_t& produced, std::string& err) {
+    static const ZstdApi api;  // resolved once (thread-safe initialisation)
+    if (api.decompress == nullptr || api.is_error == nullptr) { err = "StringArray: libzstd is not available"; return false; }
+    produced = api.decompress(dst, dst_len, src, src_len);
+    if (api.is_error(produced)) { err = "StringArray: Zstandard decompression failed"; return false; }
+    return true;
+}
+
+// Graph::load, src/graph.rs:295-330, as far as the node labels: header, then the sequences as a compressed
+// (version 4, StringArray::decompress) or packed (version 3, StringArray::load) string array. Segment names and
+// the node-to-segment mapping follow in the image and are not needed on the path.
+int parse_graph(Cursor& c, ParsedGBWT& out, std::string& err) {
+    const uint64_t tv = c.word();
+    const uint64_t nodes = c.word();
+    const uint64_t flags = c.word();
+    if (!c.ok()) { err = "GraphHeader: unexpected end of data"; return GBWT_B200_E_INVALID_DATA; }
+    const uint32_t tag = static_cast<uint32_t>(tv), version = static_cast<uint32_t>(tv >> 32);
+    if (tag != TAG_GRAPH) { err = "GraphHeader: Invalid tag"; return GBWT_B200_E_INVALID_DATA; }
+    if (version < 3 || version > 4) { err = "GraphHeader: Invalid version (expected 3 to 4)"; return GBWT_B200_E_INVALID_DATA; }
+    if (flags & ~3ull) { err = "GraphHeader: Invalid flags"; return GBWT_B200_E_INVALID_DATA; }
+    if (!(flags & 2ull)) { err = "GraphHeader: SDSL format is not supported"; return GBWT_B200_E_INVALID_DATA; }
+    uint64_t universe = 0;
+    if (!read_sparse_values(c, universe, out.label_starts)) { err = "StringArray: invalid index"; return GBWT_B200_E_INVALID_DATA; }
+    uint64_t total = 0;
+    if (version >= 4) {
+        total = c.word();
+        const uint64_t compressed_len = c.word();
+        const uint8_t* compressed = c.here();
+        c.skip_words((compressed_len + 7) / 8);
+        if (!c.ok() || total > (uint64_t(1) << 48)) { err = "StringArray: invalid data"; return GBWT_B200_E_INVALID_DATA; }
+        out.label_bytes.resize(total);
+        size_t produced = 0;
+        uint8_t scratch = 0;
+        if (!zstd_decompress(total ? out.label_bytes.data() : &scratch, total, compressed, compressed_len, produced, err))
+            return GBWT_B200_E_INVALID_DATA;
+        if (produced != total) {
+            err = "StringArray: Decompressed string length does not match the expected length";
+            return GBWT_B200_E_INVALID_DATA;
+        }
+    } else {
+        const uint64_t alphabet_len = c.word();
+        const uint8_t* alphabet = c.here();
+        c.skip_words((alphabet_len + 7) / 8);
+        total = c.word();
+        const uint64_t width = c.word(), bits = c.word(), words = c.word();
+        const uint8_t* packed = c.here();
+        c.skip_words(words);
+        if (!c.ok() || width == 0 || width > 64 || words != (bits + 63) / 64 || total > bits || bits != total * width) {
+            err = "StringArray: invalid strings"; return GBWT_B200_E_INVALID_DATA;
+        }
+        out.label_bytes.resize(total);
+        const uint64_t mask = width >= 64 ? ~0ull : ((1ull << width) - 1);
+        for (uint64_t i = 0; i < total; i++) {
+            const uint64_t bit = i * width, w = bit / 64, sh = bit % 64;
+            uint64_t v = load_word(packed, w) >> sh;
+            if (sh + width > 64) v |= load_word(packed, w + 1) << (64 - sh);
+            v &= mask;
+            if (v >= alphabet_len) { err = "StringArray: invalid strings"; return GBWT_B200_E_INVALID_DATA; }
+            out.label_bytes[i] = alphabet[v];
+        }
+    }
+    if (!out.label_starts.empty() && out.label_starts[0] != 0) {
+        err = "StringArray: First string does not start at offset 0"; return GBWT_B200_E_INVALID_DATA;
+    }
+    for (size_t i = 0; i < out.label_starts.size(); i++) {
+        if (out.label_starts[i] > total || (i > 0 && out.label_starts[i] < out.label_starts[i - 1])) {
+            err = "StringArray: invalid index"; return GBWT_B200_E_INVALID_DATA;
+        }
+    }
+    // GBZ::load, src/gbz.rs:690-694
+    if (out.label_starts.size() != (out.alphabet_size - (out.offset + 1)) / 2) {
+        err = "GBZ: Mismatch between GBWT alphabet size and Graph sequence count"; return GBWT_B200_E_INVALID_DATA;
+    }
+    // Segment names and the node-to-segment mapping are not needed on the path; they are stepped over with the
+    // reference's consistency checks (src/graph.rs:309-328) so that a damaged file is rejected like it is there.
+    c.word();  // universe of the segment-name index
+    const uint64_t segments = c.word();
+    c.skip_raw_vector(); c.skip_option(); c.skip_option(); c.skip_option();
+    c.skip_int_vector();
+    c.skip_byte_vector(); c.skip_int_vector();
+    const uint64_t mapping_len = c.word(), mapping_ones = c.word();
+    c.skip_raw_vector(); c.skip_option(); c.skip_option(); c.skip_option();
+    c.skip_int_vector();
+    if (!c.ok()) { err = "Graph: unexpected end of data"; return GBWT_B200_E_INVALID_DATA; }
+    const bool translation = (flags & 1ull) != 0;
+    if (translation == (segments == 0)) {
+        err = "Graph: Translation flag does not match the presence of segment names"; return GBWT_B200_E_INVALID_DATA;
+    }
+    if (translation) {
+        if (mapping_len <= nodes) { err = "Graph: Node-to-segment mapping does not match the number of nodes"; return GBWT_B200_E_INVALID_DATA; }
+        if (mapping_len != out.label_starts.size() + 1) { err = "Graph: Node-to-segment mapping does not match the number of sequences"; return GBWT_B200_E_INVALID_DATA; }
+        if (mapping_ones != segments) { err = "Graph: Node-to-segment mapping does not match the number of segments"; return GBWT_B200_E_INVALID_DATA; }
+    }
+    out.label_starts.push_back(total);
+    out.has_graph = true;
+    return GBWT_B200_OK;
+}
+
 }  // namespace
 
 int parse_gbwt_image(const uint8_t* bytes, size_t len, ParsedGBWT& out, std::string& err) {
@@ -137,7 +252,7 @@ int parse_gbwt_image(const uint8_t* bytes, size_t len, ParsedGBWT& out, std::str
     uint32_t tag;
     std::memcpy(&tag, bytes, 4);
     if (tag == TAG_GBZ) {
-        // GBZ::load, src/gbz.rs:678-690: header {tag|version, flags}, tags, GBWT, graph (ignored).
+        // GBZ::load, src/gbz.rs:678-696: header {tag|version, flags}, tags, GBWT, graph.
         uint64_t tv = c.word(), flags = c.word();
         uint32_t version = static_cast<uint32_t>(tv >> 32);
         if (version < 1 || version > 2) { err = "GBZHeader: Invalid version (expected 1 to 2)"; return GBWT_B200_E_INVALID_DATA; }
@@ -146,7 +261,7 @@ int parse_gbwt_image(const uint8_t* bytes, size_t len, ParsedGBWT& out, std::str
         int rc = parse_gbwt(c, out, err);
         if (rc != GBWT_B200_OK) return rc;
         if (!(out.flags & GBWT_FLAG_BIDIRECTIONAL)) { err = "GBZ: The GBWT index is not bidirectional"; return GBWT_B200_E_INVALID_DATA; }
-        return GBWT_B200_OK;
+        return parse_graph(c, out, err);
     }
     return parse_gbwt(c, out, err);
 }

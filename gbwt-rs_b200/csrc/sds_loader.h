@@ -1,6 +1,6 @@
 // sds_loader.h -- host-side reader for Simple-SDS GBWT / GBZ images (boundary input, not accelerated).
 // Format: SURVEY.md App. A; field order from gbwt-rs src/gbwt.rs:402-438, src/bwt.rs:176-185,
-// src/gbz.rs:678-690, src/headers.rs:57-62, 190-234.
+// src/gbz.rs:678-696, src/graph.rs:295-330, src/support.rs:545-571, 619-643, src/headers.rs:57-62, 190-280.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -14,6 +14,11 @@ struct ParsedGBWT {
     std::vector<uint64_t> record_starts;  // start of every record in `bwt` (what the Elias-Fano index selects)
     const uint8_t* bwt = nullptr;         // points into the caller's image
     uint64_t bwt_len = 0;
+    // Node labels of a GBZ image (Graph::sequences, src/graph.rs:84-89): label i is
+    // label_bytes[label_starts[i] .. label_starts[i + 1]); sequence id = node id - first node id.
+    bool has_graph = false;
+    std::vector<uint64_t> label_starts;
+    std::vector<uint8_t> label_bytes;
 };
 
 constexpr uint64_t GBWT_FLAG_BIDIRECTIONAL = 1, GBWT_FLAG_METADATA = 2, GBWT_FLAG_SIMPLE_SDS = 4;

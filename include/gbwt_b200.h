@@ -48,7 +48,8 @@ enum {
     GBWT_B200_E_NOT_BIDIRECTIONAL = 4, /* the reference's assert! at src/gbwt.rs:237, 312, 340 */
     GBWT_B200_E_CUDA = 5,              /* CUDA runtime error; see gbwt_b200_last_error() */
     GBWT_B200_E_ARGUMENT = 6,          /* NULL handle / pointer, bad layout policy, ... */
-    GBWT_B200_E_NO_DEVICE = 7          /* no CUDA device: there is deliberately no CPU fallback */
+    GBWT_B200_E_NO_DEVICE = 7,         /* no CUDA device: there is deliberately no CPU fallback */
+    GBWT_B200_E_NO_GRAPH = 8           /* node sequences requested from an index that has no graph (not a GBZ) */
 };
 
 /* ---- value types ------------------------------------------------------------------------------ */
@@ -79,6 +80,12 @@ GBWT_B200_API int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, 
                                             uint64_t flags, const uint8_t* bwt_bytes, uint64_t bwt_len,
                                             const uint64_t* record_starts, uint64_t records, int device,
                                             int layout_policy, gbwt_b200_index** out);
+/* Node labels for an index built from parts (the Graph half of a GBZ, src/gbz.rs:678-696; Graph::sequences,
+ * src/graph.rs:84-89): label i = label_bytes[label_starts[i] .. label_starts[i+1]) belongs to original-graph node
+ * first_node / 2 + i. Checks what GBZ::load checks (bidirectional index, sequence count). Not thread-safe
+ * against queries running on the same handle. Indexes loaded from a GBZ image have their graph already. */
+GBWT_B200_API int gbwt_b200_index_attach_graph(gbwt_b200_index* index, uint64_t sequences, const uint64_t* label_starts,
+                                              const uint8_t* label_bytes);
 GBWT_B200_API void gbwt_b200_index_destroy(gbwt_b200_index* index);
 /* Message of the last failure on the calling thread (never NULL). */
 GBWT_B200_API const char* gbwt_b200_last_error(void);
@@ -93,6 +100,9 @@ GBWT_B200_API uint64_t gbwt_b200_first_node(const gbwt_b200_index* index);      
 GBWT_B200_API int gbwt_b200_has_node(const gbwt_b200_index* index, uint64_t id); /* GBWT::has_node */
 GBWT_B200_API int gbwt_b200_is_bidirectional(const gbwt_b200_index* index);     /* GBWT::is_bidirectional */
 GBWT_B200_API int gbwt_b200_device(const gbwt_b200_index* index);
+GBWT_B200_API int gbwt_b200_has_graph(const gbwt_b200_index* index);            /* loaded from a GBZ / graph attached */
+GBWT_B200_API uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* index); /* Graph::sequences, src/graph.rs:112-114 */
+GBWT_B200_API uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* index);     /* HBM held by the node labels */
 /* Bytes of HBM held by the index, and a breakdown: [0] descriptors, [1] bodies, [2] edge lists,
  * [3] endmarker; [4..9] number of records per body format (empty, single-edge, dense, run8, run32, run64). */
 GBWT_B200_API uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* index, uint64_t breakdown[10]);
@@ -154,6 +164,24 @@ GBWT_B200_API int gbwt_b200_sequence_lengths(const gbwt_b200_index* index, const
 GBWT_B200_API int gbwt_b200_extract(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m,
                                    const uint64_t* out_offsets, uint64_t* nodes, uint64_t* lengths);
 
+/* ---- node sequences (GBZ files only; GBWT_B200_E_NO_GRAPH otherwise) ------------------------------ */
+/* GBZ::sequence_len / GBZ::sequence (src/gbz.rs:292-306) for n original-graph node identifiers: lengths[i] is the
+ * label length, UINT64_MAX where the reference returns None (GBZ::has_node is false, src/gbz.rs:286-289). */
+GBWT_B200_API int gbwt_b200_node_sequence_lengths(const gbwt_b200_index* index, const uint64_t* node_ids, size_t n,
+                                                 uint64_t* lengths);
+/* Label i is written to bytes[out_offsets[i] ..], at most out_offsets[i+1] - out_offsets[i] bytes. */
+GBWT_B200_API int gbwt_b200_node_sequences(const gbwt_b200_index* index, const uint64_t* node_ids, size_t n,
+                                          const uint64_t* out_offsets, uint8_t* bytes, uint64_t* lengths);
+/* extract_sequence (src/bin/gbz-extract.rs:173-189) over GBZ::path (src/gbz.rs:461-466) for m GBWT sequence ids
+ * (= support::encode_path(path_id, orientation), src/support.rs:247-249): the labels of the nodes on the path,
+ * reverse-complemented for reverse-oriented nodes (support::reverse_complement, src/support.rs:104-110), then
+ * the `endmarker` byte. lengths[i] = length of the full result including the endmarker, UINT64_MAX where
+ * GBZ::path is None (id >= sequences()). */
+GBWT_B200_API int gbwt_b200_dna_lengths(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m, uint64_t* lengths);
+/* Result i is written to bytes[out_offsets[i] ..], at most out_offsets[i+1] - out_offsets[i] bytes. */
+GBWT_B200_API int gbwt_b200_extract_dna(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m, uint8_t endmarker,
+                                       const uint64_t* out_offsets, uint8_t* bytes, uint64_t* lengths);
+
 /* ---- device-pointer entry points (inputs and outputs already resident in HBM) ------------------- */
 GBWT_B200_API int gbwt_b200_find_extend_device(const gbwt_b200_index* index, const uint64_t* d_patterns, size_t n,
                                               size_t k, gbwt_b200_state* d_out, void* stream);
@@ -185,6 +213,11 @@ GBWT_B200_API int gbwt_b200_extract_device(const gbwt_b200_index* index, const u
 
 /* ---- utilities -------------------------------------------------------------------------------- */
 /* Page-locked host buffers for the host entry points (cudaHostAlloc / cudaFreeHost). */
+GBWT_B200_API int gbwt_b200_dna_lengths_device(const gbwt_b200_index* index, const uint64_t* d_seq_ids, size_t m,
+                                              uint64_t* d_lengths, void* stream);
+GBWT_B200_API int gbwt_b200_extract_dna_device(const gbwt_b200_index* index, const uint64_t* d_seq_ids, size_t m,
+                                              uint8_t endmarker, const uint64_t* d_out_offsets, uint8_t* d_bytes,
+                                              uint64_t* d_lengths, void* stream);
 GBWT_B200_API void* gbwt_b200_host_alloc(size_t bytes);
 GBWT_B200_API void gbwt_b200_host_free(void* p);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */

@@ -1292,6 +1292,28 @@ static int load_graph(orc_reader* r, orc_gbwt* g, char* err, size_t errlen) {
         return 0;
     }
     g->has_graph = 1; g->n_seq = n; g->seq_starts = starts; g->seq_bytes = bytes;
+    /* Segment names (StringArray::load) and the node-to-segment mapping (SparseVector) are not used on the
+     * path; they are walked so that a truncated file fails like it does in the reference (src/graph.rs:309-328). */
+    uint64_t segments = 0;
+    {
+        (void)rd_u64(r);                    /* universe */
+        segments = rd_u64(r);               /* BitVector::ones = number of segment names */
+        rd_skip_rawvector(r); rd_skip_option(r); rd_skip_option(r); rd_skip_option(r);
+        rd_skip_intvector(r);
+        rd_skip_bytes(r); rd_skip_intvector(r);
+    }
+    uint64_t mapping_len = rd_u64(r), mapping_ones = rd_u64(r);
+    rd_skip_rawvector(r); rd_skip_option(r); rd_skip_option(r); rd_skip_option(r);
+    rd_skip_intvector(r);
+    if (!r->ok) { set_err(err, errlen, "Graph: unexpected end of data"); return 0; }
+    if (((flags & 1ULL) != 0) == (segments == 0)) {
+        set_err(err, errlen, "Graph: Translation flag does not match the presence of segment names"); return 0;
+    }
+    if (flags & 1ULL) {
+        if (mapping_len <= g->graph_nodes) { set_err(err, errlen, "Graph: Node-to-segment mapping does not match the number of nodes"); return 0; }
+        if (mapping_len != n + 1) { set_err(err, errlen, "Graph: Node-to-segment mapping does not match the number of sequences"); return 0; }
+        if (mapping_ones != segments) { set_err(err, errlen, "Graph: Node-to-segment mapping does not match the number of segments"); return 0; }
+    }
     return 1;
 }
 

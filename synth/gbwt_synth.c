@@ -182,6 +182,76 @@ uint8_t* synth_bwt_section(const uint64_t* rec_starts, uint64_t records, const u
     return w.p;
 }
 
+/* ---- GBZ container with node labels (gbwt-rs src/gbz.rs:650-696, src/graph.rs:284-294) ------------ */
+
+#include <dlfcn.h>
+
+/* StringArray::serialize body after the index (src/support.rs:592-610): alphabet + packed characters. */
+static void wb_packed_strings(wbuf* w, const uint8_t* bytes, uint64_t total) {
+    int present[256] = {0};
+    for (uint64_t i = 0; i < total; i++) present[bytes[i]] = 1;
+    uint8_t alphabet[256] = {0}; uint8_t pack[256] = {0}; size_t sigma = 0;
+    for (int c = 0; c < 256; c++) if (present[c]) { pack[c] = (uint8_t)sigma; alphabet[sigma++] = (uint8_t)c; }
+    wb_bytes_padded(w, alphabet, sigma);
+    uint64_t width = 1;
+    while (sigma > 1 && ((sigma - 1) >> width) != 0) width++;
+    uint64_t bits = total * width, words = (bits + 63) / 64;
+    uint64_t* packed = (uint64_t*)calloc(words + 1, 8);
+    for (uint64_t i = 0; i < total; i++) {
+        uint64_t v = pack[bytes[i]], bit = i * width;
+        packed[bit / 64] |= v << (bit % 64);
+        if ((bit % 64) + width > 64) packed[bit / 64 + 1] |= v >> (64 - bit % 64);
+    }
+    wb_u64(w, total); wb_u64(w, width); wb_u64(w, bits); wb_u64(w, words); wb_words(w, packed, words);
+    free(packed);
+}
+
+/* A GBZ image around an existing GBWT image: header, tags, GBWT, Graph {header, node labels, no segment
+ * names, empty node-to-segment mapping}. graph_version 3 writes the labels as a packed StringArray
+ * (GBZ version 1 files), 4 as a Zstandard frame (GBZ version 2; libzstd is resolved with dlopen and NULL is
+ * returned without it). starts has n_labels + 1 entries. */
+uint8_t* synth_gbz_image(const uint8_t* gbwt, uint64_t gbwt_len, uint64_t nodes, uint64_t n_labels, const uint64_t* starts,
+                         const uint8_t* labels, int graph_version, uint64_t* out_len) {
+    if (graph_version != 3 && graph_version != 4) return NULL;
+    uint64_t total = starts[n_labels];
+    wbuf w = {0, 0, 0};
+    wb_u64(&w, 0x205A4247ULL | ((uint64_t)(graph_version == 4 ? 2 : 1) << 32));
+    wb_u64(&w, 0);
+    const char* tags[2] = {"source", "jltsiren/gbwt-rs"};
+    wb_tags(&w, tags, 2);
+    wb_reserve(&w, gbwt_len);
+    memcpy(w.p + w.len, gbwt, gbwt_len);
+    w.len += gbwt_len;
+    wb_u64(&w, 0x6B3764AFULL | ((uint64_t)graph_version << 32));
+    wb_u64(&w, nodes);
+    wb_u64(&w, 2); /* FLAG_SIMPLE_SDS, no translation */
+    wb_sparse(&w, n_labels ? starts[n_labels - 1] + 1 : 0, starts, n_labels);
+    if (graph_version == 4) {
+        typedef size_t (*bound_fn)(size_t);
+        typedef size_t (*compress_fn)(void*, size_t, const void*, size_t, int);
+        typedef unsigned (*iserror_fn)(size_t);
+        void* h = dlopen("libzstd.so.1", RTLD_NOW);
+        bound_fn bound = h ? (bound_fn)dlsym(h, "ZSTD_compressBound") : NULL;
+        compress_fn compress = h ? (compress_fn)dlsym(h, "ZSTD_compress") : NULL;
+        iserror_fn iserror = h ? (iserror_fn)dlsym(h, "ZSTD_isError") : NULL;
+        if (!bound || !compress || !iserror) { free(w.p); return NULL; }
+        size_t cap = bound((size_t)total);
+        uint8_t* tmp = (uint8_t*)malloc(cap + 8);
+        size_t n = compress(tmp, cap, labels, (size_t)total, 3);
+        if (iserror(n)) { free(tmp); free(w.p); return NULL; }
+        wb_u64(&w, total);
+        wb_bytes_padded(&w, tmp, n);
+        free(tmp);
+    } else {
+        wb_packed_strings(&w, labels, total);
+    }
+    wb_sparse(&w, 0, NULL, 0);          /* segments: empty StringArray */
+    wb_packed_strings(&w, NULL, 0);
+    wb_sparse(&w, 0, NULL, 0);          /* mapping */
+    *out_len = w.len;
+    return w.p;
+}
+
 void synth_free(void* p) { free(p); }
 
 /* ---- bubble chain ------------------------------------------------------------------------------- */

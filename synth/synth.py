@@ -39,6 +39,8 @@ def lib() -> C.CDLL:
         L.synth_gbwt_image.argtypes = [u64, u64, u64, u64, u64, p, u64, p, u64, C.POINTER(u64)]
         L.synth_bwt_section.restype = p
         L.synth_bwt_section.argtypes = [p, u64, p, u64, C.POINTER(u64)]
+        L.synth_gbz_image.restype = p
+        L.synth_gbz_image.argtypes = [p, u64, u64, u64, p, p, C.c_int, C.POINTER(u64)]
         L.synth_free.argtypes = [p]
         L.synth_sequence.argtypes = [u64, u64, u64, u64, p]
         L.synth_patterns.argtypes = [u64, u64, u64, u64, u64, u64, u64, p, C.c_int]
@@ -84,6 +86,44 @@ def gbwt_image(sequences, size, offset, alphabet_size, flags, rec_starts, data: 
     n = C.c_uint64(0)
     ptr = lib().synth_gbwt_image(sequences, size, offset, alphabet_size, flags, starts.ctypes.data_as(C.c_void_p),
                                  len(starts), buf.ctypes.data_as(C.c_void_p), len(buf), C.byref(n))
+    out = C.string_at(ptr, n.value)
+    lib().synth_free(ptr)
+    return out
+
+
+def node_labels(n_labels: int, seed: int = 42, max_anchor: int = 32, first_node_id: int = 1):
+    """Deterministic node labels for a bubble chain: (starts[n_labels + 1], bytes). Node ids 1, 4, 7, ... are the
+    anchors between sites (1..max_anchor random bases), the two nodes after each anchor are the alleles of a site
+    (single bases, SNP-like). Sprinkles lower-case bases and 'N' so that reverse complements exercise the whole
+    COMPLEMENT table."""
+    rng = np.random.default_rng(seed)
+    ids = np.arange(n_labels, dtype=np.int64) + first_node_id
+    lengths = np.where(ids % 3 == 1, rng.integers(1, max_anchor + 1, n_labels), 1).astype(np.uint64)
+    starts = np.zeros(n_labels + 1, dtype=np.uint64)
+    np.cumsum(lengths, out=starts[1:])
+    total = int(starts[-1])
+    data = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, total)].copy()
+    odd = rng.integers(0, 64, total)
+    data[odd == 0] |= 0x20          # lower case
+    data[odd == 1] = ord("N")
+    return starts, data
+
+
+def gbz_image(gbwt_image, label_starts, label_bytes, graph_version: int = 4, nodes: int = 0) -> bytes:
+    """A GBZ image around a GBWT image (bytes or Image) with the given node labels; graph_version 3 = packed
+    labels (GBZ v1 files), 4 = Zstandard (GBZ v2)."""
+    if isinstance(gbwt_image, Image):
+        src_ptr, src_len = gbwt_image.ptr, gbwt_image.nbytes
+    else:
+        keep = np.frombuffer(bytes(gbwt_image), dtype=np.uint8)
+        src_ptr, src_len = keep.ctypes.data, len(keep)
+    starts = np.ascontiguousarray(label_starts, dtype=np.uint64)
+    data = np.ascontiguousarray(label_bytes, dtype=np.uint8)
+    n = C.c_uint64(0)
+    ptr = lib().synth_gbz_image(src_ptr, src_len, nodes, len(starts) - 1, starts.ctypes.data_as(C.c_void_p),
+                                data.ctypes.data_as(C.c_void_p), graph_version, C.byref(n))
+    if not ptr:
+        raise RuntimeError("could not write the GBZ image (libzstd missing?)")
     out = C.string_at(ptr, n.value)
     lib().synth_free(ptr)
     return out

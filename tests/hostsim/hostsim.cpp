@@ -49,6 +49,12 @@ HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t
 
 void hs_free(HostSim* h) { delete h; }
 
+// Node labels as the product's loader parsed them (sds_loader.cpp parse_graph): has_graph, count, starts, bytes.
+int hs_has_graph(const HostSim* h) { return h->parsed.has_graph ? 1 : 0; }
+uint64_t hs_label_count(const HostSim* h) { return h->parsed.has_graph ? h->parsed.label_starts.size() - 1 : 0; }
+const uint64_t* hs_label_starts(const HostSim* h) { return h->parsed.label_starts.data(); }
+const uint8_t* hs_label_bytes(const HostSim* h) { return h->parsed.label_bytes.data(); }
+
 void hs_format_counts(const HostSim* h, uint64_t* out) { std::memcpy(out, h->layout.format_counts, sizeof(h->layout.format_counts)); }
 uint64_t hs_body_bytes(const HostSim* h) { return h->layout.bodies.size() * 8; }
 int hs_record_format(const HostSim* h, uint64_t rec) { return h->layout.desc[rec].fmt; }

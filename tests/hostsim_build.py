@@ -34,12 +34,19 @@ def lib():
         stale = (not os.path.exists(OUT)) or any(os.path.getmtime(s) > os.path.getmtime(OUT) for s in DEPS)
         if stale:
             subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                            "-o", OUT] + SRC, check=True, capture_output=True)
+                            "-o", OUT] + SRC + ["-ldl"], check=True, capture_output=True)
         L = C.CDLL(OUT)
         p, u64 = C.c_void_p, C.c_uint64
         L.hs_load.restype = p
         L.hs_load.argtypes = [p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.hs_free.argtypes = [p]
+        L.hs_has_graph.argtypes = [p]
+        L.hs_label_count.restype = u64
+        L.hs_label_count.argtypes = [p]
+        L.hs_label_starts.restype = p
+        L.hs_label_starts.argtypes = [p]
+        L.hs_label_bytes.restype = p
+        L.hs_label_bytes.argtypes = [p]
         L.hs_format_counts.argtypes = [p, p]
         L.hs_body_bytes.restype = u64
         L.hs_body_bytes.argtypes = [p]
@@ -88,6 +95,17 @@ class HostSim:
                 self._h = None
         except Exception:
             pass
+
+    def labels(self):
+        """(starts, bytes) of the node labels the product loader parsed from a GBZ image, or None for a plain GBWT."""
+        if not self._L.hs_has_graph(self._h):
+            return None
+        n = self._L.hs_label_count(self._h)
+        starts = np.ctypeslib.as_array(C.cast(self._L.hs_label_starts(self._h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+        total = int(starts[-1])
+        data = np.ctypeslib.as_array(C.cast(self._L.hs_label_bytes(self._h), C.POINTER(C.c_uint8)), (total,)).copy() \
+            if total else np.zeros(0, np.uint8)
+        return starts, data
 
     def format_counts(self):
         out = np.zeros(6, dtype=np.uint64)

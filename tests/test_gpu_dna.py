@@ -1,0 +1,179 @@
+"""GPU parity for node sequences and DNA-level path extraction: the CUDA path through the
+C ABI against the oracle and the reference's literals (src/graph/tests.rs:21-34, 66-79; src/support/tests.rs:13-42;
+extract_sequence of src/bin/gbz-extract.rs:173-189), bit-exact."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import gbwt_builder as gb
+import golden_vectors as gv
+from oracle import oracle as orc
+from synth import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+U64MAX = np.uint64(2**64 - 1)
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import gbwt_rs_b200
+    return gbwt_rs_b200
+
+
+def check_dna(e, g, endmarker=0, ids=None):
+    """extract_dna of the product against the oracle for the given sequence ids (default: all + one past the end)."""
+    if ids is None:
+        ids = np.arange(g.sequences() + 1, dtype=np.uint64)
+    want_offsets, want, want_lengths = g.extract_dna_batch(ids, endmarker)
+    lengths = e.dna_lengths(ids)
+    assert np.array_equal(lengths, want_lengths)
+    offsets, data, got_lengths = e.extract_dna(ids, endmarker)
+    assert np.array_equal(offsets, want_offsets) and np.array_equal(got_lengths, want_lengths)
+    assert np.array_equal(data, want)
+    return int(offsets[-1])
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+@pytest.mark.parametrize("name,truth,first", [("example.gbz", gv.GRAPH_SEQUENCES, 11), ("example-v1.gbz", gv.GRAPH_SEQUENCES, 11),
+                                              ("translation.gbz", gv.GRAPH_SEQUENCES_TRANSLATION, 1),
+                                              ("translation-v1.gbz", gv.GRAPH_SEQUENCES_TRANSLATION, 1)])
+def test_fixture_node_sequences(b200, name, truth, first, layout):
+    path = os.path.join(GOLDEN, name)
+    e, g = b200.GBWT.load(path, layout=layout), orc.GBWT.load(path)
+    assert e.has_graph() and e.graph_sequences() == len(truth)
+    ids = np.arange(0, first + len(truth) + 3, dtype=np.uint64)
+    offsets, data, lengths = e.node_sequences(ids)
+    for i, node_id in enumerate(ids):
+        k = int(node_id) - first
+        label = truth[k] if 0 <= k < len(truth) else ""
+        if label:
+            assert data[int(offsets[i]):int(offsets[i + 1])].tobytes() == label.encode() and lengths[i] == len(label)
+            assert e.node_sequence(int(node_id)) == label.encode() == g.node_sequence(int(node_id))
+            assert e.sequence_len(int(node_id)) == len(label)
+        else:
+            assert lengths[i] == U64MAX and e.node_sequence(int(node_id)) is None and g.node_sequence(int(node_id)) is None
+    check_dna(e, g)
+    check_dna(e, g, endmarker=ord("$"))
+
+
+def test_example_dna_literals(b200):
+    e = b200.GBWT.load(os.path.join(GOLDEN, "example.gbz"))
+    labels = {11 + i: s.encode() for i, s in enumerate(gv.GRAPH_SEQUENCES)}
+    for path_id, path in enumerate(gv.true_paths(False)):
+        assert e.path_dna(2 * path_id, ord("$")) == gv.true_dna(lambda n: labels[n], path, b"$")
+        assert e.path_dna(2 * path_id + 1, ord("$")) == gv.true_dna(lambda n: labels[n], gv.reverse_path(path), b"$")
+    assert e.path_dna(0, ord("$")) == b"GATAA$" and e.path_dna(e.sequences()) is None
+
+
+def test_reverse_complement_table(b200):
+    # one node whose label is every byte value, walked in both orientations: the reverse path spells
+    # support::reverse_complement of the label (src/support.rs:87-110, literals of src/support/tests.rs:13-42)
+    img = synth.gbwt_image(**image_args(gb.build_bwt(gb.bidirectional_sequences([[2], [2, 4], [4, 2]]))))
+    labels = [bytes(range(256)), b"GATTACAT"]
+    starts = np.cumsum([0] + [len(x) for x in labels]).astype(np.uint64)
+    data = np.frombuffer(b"".join(labels), dtype=np.uint8)
+    for version in (3, 4):
+        gbz = synth.gbz_image(img, starts, data, version)
+        e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
+        assert e.path_dna(0)[:-1] == labels[0] and e.path_dna(1)[:-1] == labels[0][::-1].translate(gv.complement_table())
+        assert e.path_dna(3)[:-1] == b"ATGTAATC" + labels[0][::-1].translate(gv.complement_table())
+        check_dna(e, g)
+
+
+def image_args(b, bidirectional=True):
+    return dict(sequences=b["sequences"], size=b["size"], offset=b["offset"], alphabet_size=b["alphabet_size"],
+                flags=4 | (1 if bidirectional else 0), rec_starts=b["starts"], data=b["data"])
+
+
+def random_labels(rng, n, max_len):
+    labels = [bytes(rng.choice(b"ACGTacgtN") for _ in range(rng.choice([0, 1, 1, 2, 5, max_len]))) for _ in range(n)]
+    starts = np.cumsum([0] + [len(x) for x in labels]).astype(np.uint64)
+    return starts, np.frombuffer(b"".join(labels) or b"", dtype=np.uint8)
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_graphs_with_labels(b200, seed, layout):
+    from test_hostsim_layout import random_paths
+    rng = random.Random(100 + seed)
+    paths = random_paths(rng, n_nodes=rng.choice([2, 3, 6, 12]), n_paths=rng.choice([3, 10, 40]), max_len=rng.choice([3, 8, 20, 90]))
+    if not any(paths):
+        paths.append([2, 4])
+    b = gb.build_bwt(gb.bidirectional_sequences(paths))
+    img = synth.gbwt_image(**image_args(b))
+    n_labels = (b["alphabet_size"] - (b["offset"] + 1)) // 2
+    starts, data = random_labels(rng, n_labels, rng.choice([3, 40, 700, 3000]))
+    gbz = synth.gbz_image(img, starts, data, rng.choice([3, 4]))
+    e, g = b200.GBWT.from_bytes(gbz, layout=layout), orc.GBWT.load(gbz)
+    check_dna(e, g, endmarker=rng.choice([0, ord("$"), 255]))
+    # the same graph attached to an index built from parts
+    e2 = b200.GBWT.from_parts(g.sequences(), g.len(), g.alphabet_offset(), g.alphabet_size(), g.flags(), g.bwt_data(),
+                              g.record_starts(), layout=layout).attach_graph(starts, data)
+    check_dna(e2, g)
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_bubble_chain_dna(b200, layout):
+    # long paths (4001 nodes: many 32-node groups per walk), all haplotypes in both orientations
+    S, H, seed = 2000, 48, 11
+    img = synth.bubble_chain(S, H, seed)
+    starts, data = synth.node_labels(3 * S + 1, seed=5, max_anchor=48)
+    gbz = synth.gbz_image(img, starts, data, 4)
+    e, g = b200.GBWT.from_bytes(gbz, layout=layout), orc.GBWT.load(gbz)
+    total = check_dna(e, g, endmarker=ord("\n"))
+    assert total > 2 * H * 2 * S
+    # forward and reverse orientations of a path are reverse complements of each other
+    offsets, out, _ = e.extract_dna(np.arange(2 * H, dtype=np.uint64))
+    for p in range(0, H, 7):
+        fw = out[int(offsets[2 * p]):int(offsets[2 * p + 1]) - 1].tobytes()
+        rv = out[int(offsets[2 * p + 1]):int(offsets[2 * p + 2]) - 1].tobytes()
+        assert rv == fw[::-1].translate(gv.complement_table())
+
+
+def test_truncated_slots_and_device_pointers(b200):
+    import torch
+    S, H, seed = 500, 16, 4
+    img = synth.bubble_chain(S, H, seed)
+    starts, data = synth.node_labels(3 * S + 1, seed=9)
+    e = b200.GBWT.from_bytes(img.array).attach_graph(starts, data)
+    g = orc.GBWT.load(synth.gbz_image(img, starts, data, 3))
+    ids = np.arange(2 * H, dtype=np.uint64)
+    want_offsets, want, want_lengths = g.extract_dna_batch(ids, 7)
+    # slots shorter than the results: each result is cut to its slot, lengths still report the full size
+    cut = np.minimum(want_lengths, np.uint64(1000)) - np.arange(2 * H, dtype=np.uint64) % np.uint64(3)
+    offsets = np.zeros(2 * H + 1, np.uint64)
+    np.cumsum(cut, out=offsets[1:])
+    d_ids = torch.from_numpy(ids.view(np.int64)).cuda()
+    d_offsets = torch.from_numpy(offsets.view(np.int64)).cuda()
+    d_bytes = torch.full((int(offsets[-1]) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    d_lengths = torch.zeros(2 * H, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    before = b200.kernel_launches()
+    e.extract_dna_device(d_ids.data_ptr(), 2 * H, 7, d_offsets.data_ptr(), d_bytes.data_ptr(), d_lengths.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert b200.kernel_launches() == before + 1
+    got = d_bytes.cpu().numpy()
+    assert np.array_equal(d_lengths.cpu().numpy().view(np.uint64), want_lengths)
+    for i in range(2 * H):
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        assert np.array_equal(got[lo:hi], want[int(want_offsets[i]):int(want_offsets[i]) + hi - lo])
+    assert np.all(got[int(offsets[-1]):] == 0xEE)  # nothing written past the last slot
+    e.dna_lengths_device(d_ids.data_ptr(), 2 * H, d_lengths.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_lengths.cpu().numpy().view(np.uint64), want_lengths)
+
+
+def test_no_graph_is_an_error(b200):
+    e = b200.GBWT.load(os.path.join(GOLDEN, "example.gbwt"))
+    assert not e.has_graph() and e.graph_sequences() == 0
+    for call in (lambda: e.dna_lengths([0]), lambda: e.extract_dna([0]), lambda: e.node_sequence_lengths([11])):
+        with pytest.raises(b200.GBWTError) as err:
+            call()
+        assert err.value.code == 8
+    # GBZ::load checks (src/gbz.rs:686-694)
+    with pytest.raises(b200.GBWTError, match="Mismatch between GBWT alphabet size and Graph sequence count"):
+        e.attach_graph(np.array([0, 1], dtype=np.uint64), b"A")
