@@ -34,6 +34,7 @@ WORKLOADS = {
     "find": (3_333_333, 1024, 1 << 26),
     "find-c3": (33_333, 64, 10_000_000),
     "extract": (3_333_333, 1024, 0),
+    "extract-dna": (3_333_333, 1024, 0),
 }
 SEED, SEED_Q, K_LEN = 42, 7, 32
 
@@ -261,6 +262,11 @@ def main():
         log(f"[bench] device index built in {time.time() - t:.1f} s: {stats}")
     stream = torch.cuda.current_stream().cuda_stream
 
+    if args.workload == "extract-dna":
+        line = bench_extract_dna(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, stats)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
     if args.workload == "extract":
         line = bench_extract(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, stats)
         if rank == 0:
@@ -444,6 +450,85 @@ def bench_extract(args, index, image, sites, haplotypes, rank, world, local_rank
                        "paths_per_gpu": m, "layout": args.layout},
             "gpu_launches": gb.kernel_launches() - launches0, "roofline": roofline, "clocks": clocks,
             "extra": {"index_device_bytes": stats}}
+
+
+def bench_extract_dna(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, stats):
+    """DNA-level extraction (extract_sequence of src/bin/gbz-extract.rs:173-189) of all forward
+    haplotype paths of the configs[4] graph with synthetic node labels, partitioned by path."""
+    import torch
+    import gbwt_rs_b200 as gb
+    from synth import synth
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    starts, labels = synth.node_labels(3 * sites + 1, seed=SEED, max_anchor=32)
+    index.attach_graph(starts, labels)
+    lo, hi = gb.shard_range(haplotypes, rank, world)
+    m = hi - lo
+    length = 2 * sites + 1
+    ids = (torch.arange(lo, hi, dtype=torch.int64, device=dev) * 2)
+    lens = torch.empty(m, dtype=torch.int64, device=dev)
+    index.dna_lengths_device(ids.data_ptr(), m, lens.data_ptr(), stream)
+    torch.cuda.synchronize()
+    offs = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+    offs[1:] = torch.cumsum(lens, 0)
+    total_bytes = int(offs[-1].item())
+    out = torch.empty(total_bytes, dtype=torch.uint8, device=dev)
+    got = torch.empty(m, dtype=torch.int64, device=dev)
+
+    def step():
+        index.extract_dna_device(ids.data_ptr(), m, 0, offs.data_ptr(), out.data_ptr(), got.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    launches0 = gb.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    t1 = time.time()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t0, t1)
+    assert bool(torch.all(got == lens).item())
+    # the same walks without the byte copy (label ranges and lengths only), for the cost split
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    index.dna_lengths_device(ids.data_ptr(), m, got.data_ptr(), stream)
+    l1.record()
+    torch.cuda.synchronize()
+    lengths_only_ms = l0.elapsed_time(l1)
+    all_bytes = max_over_ranks(float(total_bytes)) * world if world > 1 else float(total_bytes)
+    value = all_bytes * args.steps / (total_ms / 1e3)
+    cpu_baseline = None
+    if rank == 0:
+        # parity of the first and last path of this rank against the oracle, and the CPU baseline on a sample
+        from oracle import oracle as orc
+        gbz = synth.gbz_image(image, starts, labels, 3, as_image=True)
+        g = orc.GBWT.load(gbz.array, native=True)
+        sample = np.array([2 * lo, 2 * (hi - 1)], dtype=np.uint64)
+        t = time.time()
+        w_offsets, w_bytes, _ = g.extract_dna_batch(sample, 0, threads=2)
+        dt = time.time() - t
+        for j, i in enumerate((0, m - 1)):
+            a, b = int(offs[i].item()), int(offs[i + 1].item())
+            assert np.array_equal(out[a:b].cpu().numpy(), w_bytes[int(w_offsets[j]):int(w_offsets[j + 1])])
+        cpu_baseline = {"value": float(w_offsets[-1]) / dt, "unit": "bases/s", "cores": 2, "kind": "port",
+                        "sample": "2 of the paths, one thread each"}
+    return {"metric": "gbz_extract_dna_bases_per_s", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"DNA sequences of all {haplotypes} forward haplotype paths ({length} nodes, "
+                                   f"{total_bytes // max(1, m)} bases each) of the {3 * sites + 1}-node bubble-chain GBZ",
+                       "paths_per_gpu": m, "layout": args.layout, "label_bytes": int(starts[-1])},
+            "gpu_launches": gb.kernel_launches() - launches0, "clocks": clocks, "cpu_baseline": cpu_baseline,
+            "extra": {"lf_steps_per_s": haplotypes * length * args.steps / (total_ms / 1e3), "lengths_only_ms": lengths_only_ms,
+                      "index_device_bytes": stats,
+                      "output_bytes_per_gpu": total_bytes}}
 
 
 if __name__ == "__main__":

@@ -442,6 +442,7 @@ struct NodeSink {
     __device__ __forceinline__ void one(uint64_t node, uint64_t n) {
         if (n < cap) out[n] = node;
     }
+    __device__ __forceinline__ void finish() {}
 };
 
 // Node labels of the graph in HBM: label i = bytes[starts[i] .. starts[i + 1]) (Graph::sequence, src/graph.rs:124-126).
@@ -464,28 +465,29 @@ __device__ __forceinline__ uint32_t complement_base(uint32_t c) {
 }
 
 // extract_sequence (src/bin/gbz-extract.rs:173-189): the labels of the visited nodes, reverse-complemented for
-// reverse-oriented nodes (support::reverse_complement, src/support.rs:104-110). Per group of 32 nodes: every lane
+// reverse-oriented nodes (support::reverse_complement, src/support.rs:104-110). Per group of 32 nodes every lane
 // fetches the label range of its node (32 independent loads instead of one per step of the chain), a warp scan
-// turns the lengths into output offsets, and the warp then writes the group's bytes as consecutive 32-byte
-// rows, each lane finding the node that owns its byte by a 5-step search over the scanned lengths.
+// turns the lengths into output offsets, and the warp writes the group's bytes as consecutive 32-byte rows, each
+// lane finding the node that owns its byte by a 5-step search over the scanned lengths.
+// The walk is a latency-bound dependent chain, so the sink must not add round trips to it: the label ranges
+// requested for one group are only consumed when the next group arrives (32 steps later, long since landed),
+// and label bytes are fetched four rows at a time before any of them is stored.
 struct DnaSink {
     GraphView graph;
     uint64_t node_base;  // alphabet offset + 1: GBZ::gbwt_node_to_sequence, src/gbz.rs:253-255
     uint8_t* out;        // nullptr: count only
     uint64_t cap;
     uint64_t written;
-    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t) {
+    // the group whose label ranges are in flight
+    uint64_t pend_lo, pend_hi;
+    uint32_t pend_rev;
+    bool pending;
+
+    __device__ __forceinline__ void copy_pending() {
         constexpr unsigned FULL = 0xFFFFFFFFu;
+        constexpr uint32_t ROWS = 4;
         const uint32_t lane = threadIdx.x & 31u;
-        uint64_t lo = 0;
-        uint32_t len = 0;
-        if (lane < count) {
-            const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
-            if (sid < graph.sequences) {
-                lo = __ldg(graph.starts + sid);
-                len = static_cast<uint32_t>(__ldg(graph.starts + sid + 1) - lo);
-            }
-        }
+        const uint32_t len = static_cast<uint32_t>(pend_hi - pend_lo);
         uint32_t incl = len;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -494,31 +496,56 @@ struct DnaSink {
         }
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         if (out != nullptr) {
-            const uint32_t lo_lo = static_cast<uint32_t>(lo), lo_hi = static_cast<uint32_t>(lo >> 32);
-            const uint32_t rev = static_cast<uint32_t>(mine & 1u);
-            for (uint32_t row = 0; row < total; row += 32) {
-                const uint32_t b = row + lane;
-                // owner = number of nodes that end at or before byte b (incl is non-decreasing over the lanes)
-                uint32_t owner = 0;
+            // byte b of the group comes from label byte key + b (forward node) or key - b (reverse node); the keys
+            // carry a bias of 2^32 so that they stay positive (bit 63 is the orientation)
+            constexpr uint64_t BIAS = 1ull << 32;
+            const uint32_t excl = incl - len;
+            const uint64_t key = BIAS + (pend_rev ? pend_lo + len - 1 + excl : pend_lo - excl);
+            const uint32_t key_lo = static_cast<uint32_t>(key), key_hi = static_cast<uint32_t>(key >> 32) | (pend_rev << 31);
+            for (uint32_t row = 0; row < total; row += 32 * ROWS) {
+                uint32_t c[ROWS], rev[ROWS];
 #pragma unroll
-                for (uint32_t step = 16; step != 0; step >>= 1) {
-                    const uint32_t v = __shfl_sync(FULL, incl, (owner + step - 1) & 31u);
-                    if (v <= b) owner += step;
+                for (uint32_t j = 0; j < ROWS; j++) {
+                    const uint32_t b = row + 32 * j + lane;
+                    // owner = number of nodes that end at or before byte b (incl is non-decreasing over the lanes)
+                    uint32_t owner = 0;
+#pragma unroll
+                    for (uint32_t step = 16; step != 0; step >>= 1) {
+                        const uint32_t v = __shfl_sync(FULL, incl, (owner + step - 1) & 31u);
+                        if (v <= b) owner += step;
+                    }
+                    const uint32_t k_lo = __shfl_sync(FULL, key_lo, owner & 31u), k_hi = __shfl_sync(FULL, key_hi, owner & 31u);
+                    const uint64_t k = (static_cast<uint64_t>(k_hi & 0x7FFFFFFFu) << 32) | k_lo;
+                    rev[j] = k_hi >> 31;
+                    c[j] = 0;
+                    if (b < total && written + b < cap) c[j] = __ldg(graph.bytes + ((rev[j] ? k - b : k + b) - BIAS));
                 }
-                const uint32_t src = owner & 31u;
-                const uint32_t o_incl = __shfl_sync(FULL, incl, src), o_len = __shfl_sync(FULL, len, src);
-                const uint64_t o_lo = (static_cast<uint64_t>(__shfl_sync(FULL, lo_hi, src)) << 32) | __shfl_sync(FULL, lo_lo, src);
-                const uint32_t o_rev = __shfl_sync(FULL, rev, src);
-                if (b < total && written + b < cap) {
-                    const uint32_t within = b - (o_incl - o_len);
-                    uint32_t c;
-                    if (o_rev) c = complement_base(__ldg(graph.bytes + o_lo + (o_len - 1 - within)));
-                    else c = __ldg(graph.bytes + o_lo + within);
-                    out[written + b] = static_cast<uint8_t>(c);
+#pragma unroll
+                for (uint32_t j = 0; j < ROWS; j++) {
+                    const uint32_t b = row + 32 * j + lane;
+                    if (b < total && written + b < cap) out[written + b] = static_cast<uint8_t>(rev[j] ? complement_base(c[j]) : c[j]);
                 }
             }
         }
         written += total;
+    }
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (pending) copy_pending();
+        pend_lo = pend_hi = 0;
+        if (lane < count) {
+            const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
+            if (sid < graph.sequences) {
+                pend_lo = __ldg(graph.starts + sid);
+                pend_hi = __ldg(graph.starts + sid + 1);
+            }
+        }
+        pend_rev = static_cast<uint32_t>(mine & 1u);
+        pending = true;
+    }
+    __device__ __forceinline__ void finish() {
+        if (pending) copy_pending();
+        pending = false;
     }
 };
 
@@ -633,7 +660,142 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
         const uint32_t rem = static_cast<uint32_t>(n & 31u);
         if (rem != 0) sink.group(mine, rem, n - rem);
     }
+    sink.finish();
     return n;
+}
+
+// ---- warp-mode walk: the lean chain ------------------------------------------------------------------
+// ncu on the first version of the warp-mode walk showed the chain was not waiting for memory most of the time: a
+// step was 186 instructions (64-bit positions, per-step prefetch arithmetic, descriptors spilled to the stack
+// around non-inlined calls), and with one warp per chain every dependent instruction costs its full latency.
+// This walk keeps a step of the two formats that make up a dense-policy pangenome index (SINGLE and DENSE2) to a
+// few dozen 32-bit instructions, moves everything else off the per-step path, and uses the 31 lanes that would
+// otherwise repeat lane 0's work: once per 32 steps the warp hands its 32 parked nodes to the sink and issues ONE
+// warp-wide round of prefetches for the records it is heading to (one address per lane).
+
+// A step on any other format, by value so that the caller's descriptor never has its address taken (which would
+// put it on the stack). Returns (offset << 32) | node, 0 = GBWT::forward is None.
+__device__ __forceinline__ uint64_t forward_slow(const IndexView& ix, uint32_t node, uint32_t offset) {
+    gbwt_b200_pos cur, next;
+    cur.node = node; cur.offset = offset;
+    if (!gbwt_forward(ix, cur, next)) return 0;
+    return (static_cast<uint64_t>(next.offset) << 32) | static_cast<uint32_t>(next.node);
+}
+
+// rank1 of position r < 192 inside one dense block and the bit at r (layout.h: {ones_before, c0 | c1 << 8, 192 bits}).
+__device__ __forceinline__ uint32_t dense_block_rank_lean(const Quad& lo, const Quad& hi, uint32_t r, uint32_t& bit) {
+    const uint32_t j = r >> 6, p = r & 63u;
+    const uint32_t w_lo = j == 0 ? lo.z : (j == 1 ? hi.x : hi.z);
+    const uint32_t w_hi = j == 0 ? lo.w : (j == 1 ? hi.y : hi.w);
+    const uint64_t w = (static_cast<uint64_t>(w_hi) << 32) | w_lo;
+    const uint32_t sub = ((lo.y << 8) >> (8 * j)) & 0xFFu;  // 0, c0, c1
+    bit = static_cast<uint32_t>(w >> p) & 1u;
+    return lo.x + sub + static_cast<uint32_t>(__popcll(w & ((1ull << p) - 1ull)));
+}
+
+// Descriptor of node v, empty (fmt 0) where BWT::record() is None; 32-bit arithmetic throughout.
+__device__ __forceinline__ Desc desc_of_node(const RecordDesc* descs, uint32_t base, uint32_t records, uint32_t v) {
+    Desc r;
+    r.a.x = r.a.y = r.a.z = r.a.w = r.b.x = r.b.y = r.b.z = r.b.w = 0;
+    const uint32_t rec = v - base;
+    if (rec - 1u < records - 1u) load_sector(reinterpret_cast<const Unit16*>(descs + rec), r.a, r.b);
+    return r;
+}
+
+template <class Sink>
+__device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (id >= ix.sequences) return ~0ull;
+    gbwt_b200_pos pos;
+    if (!gbwt_start(ix, id, pos)) { sink.finish(); return 0; }
+    // the device layout holds node identifiers, offsets and record counts in 32 bits (GBWT_B200_E_RANGE at load)
+    const RecordDesc* const descs = ix.desc;
+    const Unit16* const bodies = ix.bodies;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    uint32_t node = static_cast<uint32_t>(pos.node), offset = static_cast<uint32_t>(pos.offset);
+    uint32_t mine = 0, in_group = 0, flush_node = node;
+    uint64_t groups = 0;
+    Desc pf;  // this lane's look-ahead descriptor, requested one flush ago
+    pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
+#define desc_of(v) desc_of_node(descs, base, records, (v))
+    Desc d = desc_of(node);
+    for (;;) {
+        if (in_group == lane) mine = node;
+        in_group++;
+        if (in_group == 32) {
+            sink.group(static_cast<uint64_t>(mine), 32, groups * 32);
+            groups++;
+            in_group = 0;
+            if (ahead != 0) {
+                // Sequences that walk the graph together arrive at a record together and would all wait for the same
+                // HBM miss. Node ids follow the graph's topological order, so the records the walk needs next lie a
+                // little further in the direction it is moving: lane l asks for the line of descriptors
+                // `ahead + 4 l` records away (a real load: its body offset is used at the next flush, 32 steps
+                // later), and for the first lines of the bodies of the descriptors it asked for last time.
+                const uint32_t pf_fmt = pf.fmt();
+                if (pf_fmt == FMT_DENSE2 || pf_fmt >= FMT_RUN8) {
+                    const Unit16* body = bodies + pf.body();
+                    prefetch_l2(body); prefetch_l2(body + 8); prefetch_l2(body + 16);
+                }
+                const uint32_t rec = node - base, step = ahead + 4u * lane;
+                const bool up = node >= flush_node;
+                flush_node = node;
+                uint32_t target = up ? rec + step : rec - step;
+                if (up ? (target < rec || target >= records) : (target > rec)) target = up ? records - 1u : 0u;
+                load_sector(reinterpret_cast<const Unit16*>(descs + target), pf.a, pf.b);
+            }
+        }
+        const uint32_t fmt = d.fmt(), i = offset;
+        if (i >= d.total_len()) break;  // GBWT::forward -> None (an empty record has length 0)
+        if (fmt == FMT_SINGLE) {
+            const uint32_t next = d.node0();
+            if (next == 0) break;
+            offset = d.offset0() + i;
+            node = next;
+            d = desc_of(node);
+            continue;
+        }
+        if (fmt == FMT_DENSE2) {
+            // outdegree 2: both candidate descriptors are requested before the body decides
+            const Desc d0 = desc_of(d.node0()), d1 = desc_of(d.node1());
+            const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
+            Quad lo, hi;
+            load_sector(bodies + d.body() + 2u * blk, lo, hi);
+            uint32_t bit;
+            const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, bit);
+            const uint32_t next = bit ? d.node1() : d.node0();
+            if (next == 0) break;
+            offset = bit ? d.offset1() + ones : d.offset0() + (i - ones);
+            node = next;
+            d.a.x = bit ? d1.a.x : d0.a.x; d.a.y = bit ? d1.a.y : d0.a.y; d.a.z = bit ? d1.a.z : d0.a.z; d.a.w = bit ? d1.a.w : d0.a.w;
+            d.b.x = bit ? d1.b.x : d0.b.x; d.b.y = bit ? d1.b.y : d0.b.y; d.b.z = bit ? d1.b.z : d0.b.z; d.b.w = bit ? d1.b.w : d0.b.w;
+            continue;
+        }
+        if (fmt == FMT_RUN8) {
+            // byte-per-run body: the whole warp scans it; with two inline edges the successors are requested first
+            const bool two = d.inline_edges();
+            const Desc d0 = desc_of(two ? d.node0() : base), d1 = desc_of(two ? d.node1() : base);  // `base` has no record
+            uint32_t symbol, rank_i;
+            warp_lf_runs8(ix, d, i, symbol, rank_i);
+            if (symbol == NO_SYMBOL) break;
+            const Edge e = edge_at(ix, d, symbol);
+            if (e.node == 0) break;
+            offset = e.offset + rank_i;
+            node = e.node;
+            if (two) d = symbol ? d1 : d0;
+            else d = desc_of(node);
+            continue;
+        }
+        const uint64_t next = forward_slow(ix, node, offset);
+        if (next == 0) break;
+        node = static_cast<uint32_t>(next);
+        offset = static_cast<uint32_t>(next >> 32);
+        d = desc_of(node);
+    }
+    if (in_group != 0) sink.group(static_cast<uint64_t>(mine), in_group, groups * 32);
+    sink.finish();
+    return groups * 32 + in_group;
+#undef desc_of
 }
 
 // K3. A path walk is a dependent chain of LF steps (src/gbwt.rs:557-568): one thread per sequence, all
@@ -655,7 +817,7 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
                 sink.out = nodes + (lo - base);
                 sink.cap = hi > lo ? hi - lo : 0;
             }
-            const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), sink, ahead);
+            const uint64_t len = walk_sequence_warp(ix, __ldg(ids + i), sink, ahead);
             if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
         }
         return;
@@ -682,13 +844,13 @@ __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView gra
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t i = warp; i < m; i += warps) {
-        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0};
+        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0, 0, 0, 0, false};
         if (bytes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
             sink.out = bytes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_device<true>(ix, __ldg(ids + i), sink, ahead);
+        const uint64_t len = walk_sequence_warp(ix, __ldg(ids + i), sink, ahead);
         if ((threadIdx.x & 31u) != 0) continue;
         if (len == ~0ull) {
             if (lengths != nullptr) lengths[i] = ~0ull;

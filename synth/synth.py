@@ -109,13 +109,15 @@ def node_labels(n_labels: int, seed: int = 42, max_anchor: int = 32, first_node_
     return starts, data
 
 
-def gbz_image(gbwt_image, label_starts, label_bytes, graph_version: int = 4, nodes: int = 0) -> bytes:
+def gbz_image(gbwt_image, label_starts, label_bytes, graph_version: int = 4, nodes: int = 0, as_image: bool = False):
     """A GBZ image around a GBWT image (bytes or Image) with the given node labels; graph_version 3 = packed
-    labels (GBZ v1 files), 4 = Zstandard (GBZ v2)."""
+    labels (GBZ v1 files), 4 = Zstandard (GBZ v2). Returns bytes, or with as_image the malloc'd Image (no copy;
+    needed above 2 GiB)."""
     if isinstance(gbwt_image, Image):
         src_ptr, src_len = gbwt_image.ptr, gbwt_image.nbytes
     else:
-        keep = np.frombuffer(bytes(gbwt_image), dtype=np.uint8)
+        keep = np.ascontiguousarray(gbwt_image, dtype=np.uint8) if isinstance(gbwt_image, np.ndarray) \
+            else np.frombuffer(bytes(gbwt_image), dtype=np.uint8)
         src_ptr, src_len = keep.ctypes.data, len(keep)
     starts = np.ascontiguousarray(label_starts, dtype=np.uint64)
     data = np.ascontiguousarray(label_bytes, dtype=np.uint8)
@@ -124,6 +126,8 @@ def gbz_image(gbwt_image, label_starts, label_bytes, graph_version: int = 4, nod
                                 data.ctypes.data_as(C.c_void_p), graph_version, C.byref(n))
     if not ptr:
         raise RuntimeError("could not write the GBZ image (libzstd missing?)")
+    if as_image:
+        return Image(ptr, n.value)
     out = C.string_at(ptr, n.value)
     lib().synth_free(ptr)
     return out
