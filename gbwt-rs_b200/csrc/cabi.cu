@@ -30,6 +30,8 @@ struct gbwt_b200_index {
     void* d_bodies = nullptr;
     void* d_edges = nullptr;
     void* d_endmarker = nullptr;
+    void* d_skips = nullptr;
+    uint64_t skip_bytes = 0;
     void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
     void* d_label_bytes = nullptr;
     bool has_graph = false;
@@ -252,17 +254,24 @@ int launch_backward(const gbwt_b200_index* ix, const gbwt_b200_pos* pos, size_t 
 int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
                    uint64_t* nodes, uint64_t* lengths, cudaStream_t s) {
     if (m == 0) return GBWT_B200_OK;
-    // One warp per CTA (spreads the chains over the SMs) and, up to 64 Ki chains, one chain per warp.
-    const int block = 32;
+    // Up to 64 Ki sequences: one warp each (GBWT_B200_EXTRACT_STRIDE overrides: threads per sequence, 32 = warp mode).
     uint32_t stride = static_cast<uint32_t>(env_int("GBWT_B200_EXTRACT_STRIDE", m <= (size_t(1) << 16) ? 32 : 1));
     if (stride != 1 && stride != 2 && stride != 4 && stride != 8 && stride != 16 && stride != 32) stride = 1;
+    if (stride == 32) {
+        // One-warp CTAs spread few chains over all SMs; beyond 32 CTAs per SM, four warps per CTA.
+        const int block = m > static_cast<size_t>(ix->sm_count) * 32 ? 128 : 32;
+        const unsigned ctas = static_cast<unsigned>((m * 32 + block - 1) / block);
+        // How far ahead (in records) the walks ask L2 for the records they are heading to; 0 disables it.
+        const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
+        if (ix->view.edges_valid) k_extract<false><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, ahead);
+        else k_extract<true><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, ahead);
+        return launch_done("k_extract");
+    }
+    const int block = 32;
     const size_t threads = m * stride;
-    // How far ahead (in records) the walks ask L2 for the records they are heading to; 0 disables it.
-    const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
-    k_extract<<<static_cast<unsigned>((threads + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, stride, ahead);
-    return launch_done("k_extract");
+    k_extract_lanes<<<static_cast<unsigned>((threads + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, stride);
+    return launch_done("k_extract_lanes");
 }
-
 int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
                        uint8_t endmarker, uint8_t* bytes, uint64_t* lengths, cudaStream_t s) {
     if (m == 0) return GBWT_B200_OK;
@@ -271,8 +280,9 @@ int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m,
     const int block = m > static_cast<size_t>(ix->sm_count) * 32 ? 128 : 32;
     const size_t ctas = (m * 32 + block - 1) / block;
     const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
-    k_extract_dna<<<static_cast<unsigned>(std::min<size_t>(ctas, size_t(1) << 30)), block, 0, s>>>(
-        ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>(ctas, size_t(1) << 30));
+    if (ix->view.edges_valid) k_extract_dna<false><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
+    else k_extract_dna<true><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
     return launch_done("k_extract_dna");
 }
 int launch_node_sequences(const gbwt_b200_index* ix, const uint64_t* node_ids, size_t n, const uint64_t* out_offsets, uint64_t base,
@@ -544,6 +554,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_bodies, layout.bodies.data(), layout.bodies.size() * 8, ix->bytes[1]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_endmarker, layout.endmarker.data(), layout.endmarker.size() * sizeof(Edge), ix->bytes[3]);
+    if (rc == GBWT_B200_OK) rc = upload(&ix->d_skips, layout.skips.data(), layout.skips.size() * 8, ix->skip_bytes);
     if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
     // Records are fetched as isolated 32-byte sectors; ask L2 not to widen the DRAM fetches (a hint).
     {
@@ -569,6 +580,8 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     v.sequences = parsed.sequences;
     v.endmarker_len = layout.endmarker.size();
     v.bidirectional = (parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
+    v.skips = static_cast<const Unit16*>(ix->d_skips);
+    v.edges_valid = layout.edges_valid ? 1 : 0;
     if (parsed.has_graph) {
         rc = attach_graph(ix, parsed.label_starts.data(), parsed.label_starts.size() - 1, parsed.label_bytes.data());
         if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
@@ -622,7 +635,7 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;
     {
         DeviceScope scope(ix->device);
-        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips);
         cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;
@@ -643,6 +656,7 @@ int gbwt_b200_index_attach_graph(gbwt_b200_index* ix, uint64_t sequences, const 
 int gbwt_b200_has_graph(const gbwt_b200_index* ix) { return ix && ix->has_graph; }
 uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* ix) { return ix && ix->has_graph ? ix->graph.sequences : 0; }
 uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* ix) { return ix ? ix->graph_bytes : 0; }
+uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* ix) { return ix ? ix->skip_bytes : 0; }
 
 const char* gbwt_b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -664,7 +678,7 @@ uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* ix, uint64_t breakdown[10
         for (int i = 0; i < 4; i++) breakdown[i] = ix->bytes[i];
         for (int i = 0; i < FMT_COUNT; i++) breakdown[4 + i] = ix->format_counts[i];
     }
-    return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3];
+    return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3] + ix->skip_bytes + ix->graph_bytes;
 }
 
 // ---- device-pointer entry points ---------------------------------------------------------------------

@@ -428,19 +428,16 @@ __device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d
 }
 
 // ---- what a walk does with the nodes it visits -------------------------------------------------------
-// A warp-mode walk parks node n in lane n % 32 and hands the sink 32 nodes at a time (`count` < 32 only for
-// the last group); a one-lane walk hands over every node as it is visited.
+// A warp-mode walk parks the nodes it visits one per lane and hands the sink a group of up to 32 of them at a
+// time: `count` nodes, the first of which is number `first` of the sequence.
 
-// GBWT::sequence(id): the node identifiers themselves, one full 256-byte line per group.
+// GBWT::sequence(id): the node identifiers themselves, up to 256 contiguous bytes per group.
 struct NodeSink {
     uint64_t* out;
     uint64_t cap;
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
         if (lane < count && first + lane < cap) out[first + lane] = mine;
-    }
-    __device__ __forceinline__ void one(uint64_t node, uint64_t n) {
-        if (n < cap) out[n] = node;
     }
     __device__ __forceinline__ void finish() {}
 };
@@ -471,7 +468,7 @@ __device__ __forceinline__ uint32_t complement_base(uint32_t c) {
 // lane finding the node that owns its byte by a 5-step search over the scanned lengths.
 // The walk is a latency-bound dependent chain, so the sink must not add round trips to it: the label ranges
 // requested for one group are only consumed when the next group arrives (32 steps later, long since landed),
-// and label bytes are fetched four rows at a time before any of them is stored.
+// and label bytes are fetched eight rows (256 bytes, a typical group) at a time before any of them is stored.
 struct DnaSink {
     GraphView graph;
     uint64_t node_base;  // alphabet offset + 1: GBZ::gbwt_node_to_sequence, src/gbz.rs:253-255
@@ -481,13 +478,13 @@ struct DnaSink {
     // the group whose label ranges are in flight
     uint64_t pend_lo, pend_hi;
     uint32_t pend_rev;
-    bool pending;
+    bool pend_valid, pending;
 
     __device__ __forceinline__ void copy_pending() {
         constexpr unsigned FULL = 0xFFFFFFFFu;
-        constexpr uint32_t ROWS = 4;
+        constexpr uint32_t ROWS = 8;
         const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t len = static_cast<uint32_t>(pend_hi - pend_lo);
+        const uint32_t len = pend_valid ? static_cast<uint32_t>(pend_hi - pend_lo) : 0u;
         uint32_t incl = len;
 #pragma unroll
         for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -532,14 +529,13 @@ struct DnaSink {
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t) {
         const uint32_t lane = threadIdx.x & 31u;
         if (pending) copy_pending();
-        pend_lo = pend_hi = 0;
-        if (lane < count) {
-            const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
-            if (sid < graph.sequences) {
-                pend_lo = __ldg(graph.starts + sid);
-                pend_hi = __ldg(graph.starts + sid + 1);
-            }
-        }
+        // the loads are unconditional (clamped index) and nothing here reads their results: a select between the
+        // loaded value and zero would make this group wait for them
+        const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
+        pend_valid = lane < count && sid < graph.sequences;
+        const uint64_t at = sid < graph.sequences ? sid : 0;
+        pend_lo = __ldg(graph.starts + at);
+        pend_hi = __ldg(graph.starts + at + 1);
         pend_rev = static_cast<uint32_t>(mine & 1u);
         pending = true;
     }
@@ -549,105 +545,39 @@ struct DnaSink {
     }
 };
 
-// GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568; Record::lf, src/bwt.rs:480-496): same results as
-// walk_sequence(), arranged so that a step costs one memory round trip instead of two or three. A walk is a
-// dependent chain, so its speed is 1 / (latency per step): the descriptor of the current record is always in
-// registers, and as soon as it arrives the descriptors of BOTH successors of an outdegree-2 record are
-// requested together with the body block that decides between them.
-// WARP: all 32 lanes of a warp walk the same sequence with identical state (loads of one address are a single
-// broadcast wavefront); run-length bodies are then scanned by the whole warp (warp_lf_runs8) and the output is
-// written 32 nodes at a time, one per lane, as full 256-byte lines.
-template <bool WARP, class Sink>
-__device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
-    const uint32_t lane = threadIdx.x & 31u;
-    uint64_t mine = 0;
+// GBWT::sequence(id).collect() (src/gbwt.rs:253-261, 557-568; Record::lf, src/bwt.rs:480-496) by ONE lane: same
+// results as walk_sequence(), with the descriptors of both successors of an outdegree-2 record requested together
+// with the body block that decides between them. Used when a batch has more sequences than warps worth running
+// (one sequence per thread); the warp-mode walk below is the fast path.
+__device__ __forceinline__ uint64_t walk_sequence_lane(const IndexView& ix, uint64_t id, uint64_t* out, uint64_t cap) {
     if (id >= ix.sequences) return ~0ull;
     gbwt_b200_pos pos;
     if (!gbwt_start(ix, id, pos)) return 0;
     uint64_t node = pos.node, offset = pos.offset, n = 0;
     Desc d = load_desc_of(ix, node);
-    Desc pf;
-    pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
-    uint64_t prev_node = node;
     for (;;) {
-        if constexpr (WARP) {
-            if ((n & 31u) == lane) mine = node;
-            n++;
-            if ((n & 31u) == 0) sink.group(mine, 32, n - 32);
-        } else {
-            sink.one(node, n);
-            n++;
-        }
+        if (n < cap) out[n] = node;
+        n++;
         const uint32_t fmt = d.fmt();
         if (fmt == FMT_EMPTY || offset >= d.total_len()) break;  // GBWT::forward -> None
         const uint32_t i = static_cast<uint32_t>(offset);
-        if (ahead != 0) {
-            // Sequences that walk the graph together arrive at a record together and would all wait for the
-            // same HBM miss. Node ids follow the graph's topological order, so the records a walk will need
-            // shortly lie a few records further in the direction it is moving: ask L2 for the descriptors
-            // 2 * ahead records away, and for the body of the descriptor `ahead` records away (loaded during the
-            // previous step, so reading its body offset does not wait).
-            const uint64_t rec = node - ix.offset;
-            const bool up = node >= prev_node;
-            prev_node = node;
-            const uint32_t pf_fmt = pf.fmt();
-            if (pf_fmt == FMT_DENSE2 || pf_fmt >= FMT_RUN8) {
-                prefetch_l2(ix.bodies + pf.body());
-                prefetch_l2(ix.bodies + pf.body() + 8);
-            }
-            const uint64_t near = up ? (rec + ahead < ix.records ? rec + ahead : ix.records - 1) : (rec > ahead ? rec - ahead : 0);
-            const uint64_t far = up ? (rec + 2 * ahead < ix.records ? rec + 2 * ahead : ix.records - 1)
-                                    : (rec > 2 * ahead ? rec - 2 * ahead : 0);
-            prefetch_l2(ix.desc + far);
-            pf = load_desc(ix, near);
-        }
-        uint32_t symbol, rank_i;
-        Edge e;
         if (fmt == FMT_SINGLE) {
-            e.node = d.node0(); e.offset = d.offset0();
-            if (e.node == 0) break;
-            offset = static_cast<uint64_t>(e.offset) + i;
-            node = e.node;
+            if (d.node0() == 0) break;
+            offset = static_cast<uint64_t>(d.offset0()) + i;
+            node = d.node0();
             d = load_desc_of(ix, node);
             continue;
         }
-        if (d.inline_edges()) {
-            // outdegree 2: both candidate descriptors are requested before the body decides
+        if (fmt == FMT_DENSE2) {
             const Desc d0 = load_desc_of(ix, d.node0());
             const Desc d1 = load_desc_of(ix, d.node1());
-            if (fmt == FMT_DENSE2) {
-                const uint32_t ones = dense_rank1(ix.bodies + d.body(), d.body_len(), i, symbol);
-                rank_i = symbol ? ones : i - ones;
-            } else if (WARP && fmt == FMT_RUN8) {
-                warp_lf_runs8(ix, d, i, symbol, rank_i);
-                if (symbol == NO_SYMBOL) break;
-            } else {
-                symbol = symbol_at_runs(ix, d, i);
-                if (symbol == NO_SYMBOL) break;
-                FlipSet fs;
-                fs.lt = 0; fs.extra = NO_SYMBOL;
-                Ranks r;
-                r.at_start = r.at_end = r.flipped = 0;
-                rank_runs<false>(ix, d, symbol, fs, i, i, r);
-                rank_i = r.at_start;
-            }
-            e.node = symbol ? d.node1() : d.node0();
-            e.offset = symbol ? d.offset1() : d.offset0();
-            if (e.node == 0) break;
-            offset = static_cast<uint64_t>(e.offset) + rank_i;
-            node = e.node;
+            uint32_t symbol;
+            const uint32_t ones = dense_rank1(ix.bodies + d.body(), d.body_len(), i, symbol);
+            const uint32_t next = symbol ? d.node1() : d.node0();
+            if (next == 0) break;
+            offset = static_cast<uint64_t>(symbol ? d.offset1() : d.offset0()) + (symbol ? ones : i - ones);
+            node = next;
             d = symbol ? d1 : d0;
-            continue;
-        }
-        if (WARP && fmt == FMT_RUN8) {
-            // outdegree > 2 with a byte-per-run body: the warp scans, then one edge lookup
-            warp_lf_runs8(ix, d, i, symbol, rank_i);
-            if (symbol == NO_SYMBOL) break;
-            e = edge_at(ix, d, symbol);
-            if (e.node == 0) break;
-            offset = static_cast<uint64_t>(e.offset) + rank_i;
-            node = e.node;
-            d = load_desc_of(ix, node);
             continue;
         }
         gbwt_b200_pos cur, next;
@@ -656,11 +586,6 @@ __device__ __forceinline__ uint64_t walk_sequence_device(const IndexView& ix, ui
         node = next.node; offset = next.offset;
         d = load_desc_of(ix, node);
     }
-    if (WARP) {
-        const uint32_t rem = static_cast<uint32_t>(n & 31u);
-        if (rem != 0) sink.group(mine, rem, n - rem);
-    }
-    sink.finish();
     return n;
 }
 
@@ -693,16 +618,40 @@ __device__ __forceinline__ uint32_t dense_block_rank_lean(const Quad& lo, const 
     return lo.x + sub + static_cast<uint32_t>(__popcll(w & ((1ull << p) - 1ull)));
 }
 
-// Descriptor of node v, empty (fmt 0) where BWT::record() is None; 32-bit arithmetic throughout.
-__device__ __forceinline__ Desc desc_of_node(const RecordDesc* descs, uint32_t base, uint32_t records, uint32_t v) {
-    Desc r;
-    r.a.x = r.a.y = r.a.z = r.a.w = r.b.x = r.b.y = r.b.z = r.b.w = 0;
+// Record index of node v for a load that must be safe but whose result is only used when v has a record: edge
+// targets were validated when the layout was built (IndexView::edges_valid), so clamping is enough.
+__device__ __forceinline__ uint32_t record_clamped(uint32_t base, uint32_t records, uint32_t v) {
     const uint32_t rec = v - base;
-    if (rec - 1u < records - 1u) load_sector(reinterpret_cast<const Unit16*>(descs + rec), r.a, r.b);
-    return r;
+    return rec < records ? rec : records - 1u;
 }
 
-template <class Sink>
+// Descriptor and two-hop shortcut of node v. CHECKED: empty (fmt 0, no shortcut) where BWT::record() is None.
+template <bool CHECKED>
+__device__ __forceinline__ void load_landing(const RecordDesc* descs, const Unit16* skips, uint32_t base, uint32_t records,
+                                             uint32_t v, Desc& d, Quad& k) {
+    if (CHECKED) {
+        d.a.x = d.a.y = d.a.z = d.a.w = d.b.x = d.b.y = d.b.z = d.b.w = 0;
+        k.x = k.y = k.z = k.w = 0;
+        const uint32_t rec = v - base;
+        if (rec - 1u < records - 1u) {
+            load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
+            k = load_quad(skips + rec);
+        }
+    } else {
+        const uint32_t rec = record_clamped(base, records, v);
+        load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
+        k = load_quad(skips + rec);
+    }
+}
+
+// GBWT::sequence(id) by one warp (all lanes hold the same state). Per iteration: one record u with inline edges
+// (outdegree <= 2), the edge b the sequence takes and the rank r of b before its offset (no body for SINGLE, one
+// 32-byte block for DENSE2, a warp scan for RUN8). If the successor v_b is a single-edge record, the shortcut of u
+// gives LF(LF(u, i)) directly, so v_b is emitted without its record being read and the walk lands two nodes
+// further. The descriptors and shortcuts of both possible landing nodes are requested at the top of the iteration,
+// next to the body block that decides between them: ONE memory round trip per iteration.
+// CHECKED = false relies on IndexView::edges_valid (no bounds tests on edge targets).
+template <bool CHECKED, class Sink>
 __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
     const uint32_t lane = threadIdx.x & 31u;
     if (id >= ix.sequences) return ~0ull;
@@ -711,126 +660,150 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
     // the device layout holds node identifiers, offsets and record counts in 32 bits (GBWT_B200_E_RANGE at load)
     const RecordDesc* const descs = ix.desc;
     const Unit16* const bodies = ix.bodies;
+    const Unit16* const skips = ix.skips;
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
     uint32_t node = static_cast<uint32_t>(pos.node), offset = static_cast<uint32_t>(pos.offset);
     uint32_t mine = 0, in_group = 0, flush_node = node;
-    uint64_t groups = 0;
+    uint64_t flushed = 0;
     Desc pf;  // this lane's look-ahead descriptor, requested one flush ago
     pf.a.x = pf.a.y = pf.a.z = pf.a.w = pf.b.x = pf.b.y = pf.b.z = pf.b.w = 0;
-#define desc_of(v) desc_of_node(descs, base, records, (v))
-    Desc d = desc_of(node);
+    Desc d;
+    Quad k;
+    load_landing<true>(descs, skips, base, records, node, d, k);
     for (;;) {
-        if (in_group == lane) mine = node;
-        in_group++;
-        if (in_group == 32) {
-            sink.group(static_cast<uint64_t>(mine), 32, groups * 32);
-            groups++;
+        if (in_group >= 31) {  // an iteration parks up to two nodes
+            sink.group(static_cast<uint64_t>(mine), in_group, flushed);
+            flushed += in_group;
             in_group = 0;
             if (ahead != 0) {
                 // Sequences that walk the graph together arrive at a record together and would all wait for the same
                 // HBM miss. Node ids follow the graph's topological order, so the records the walk needs next lie a
-                // little further in the direction it is moving: lane l asks for the line of descriptors
-                // `ahead + 4 l` records away (a real load: its body offset is used at the next flush, 32 steps
-                // later), and for the first lines of the bodies of the descriptors it asked for last time.
-                const uint32_t pf_fmt = pf.fmt();
-                if (pf_fmt == FMT_DENSE2 || pf_fmt >= FMT_RUN8) {
-                    const Unit16* body = bodies + pf.body();
-                    prefetch_l2(body); prefetch_l2(body + 8); prefetch_l2(body + 16);
-                }
+                // little further in the direction it is moving: lane l asks for the lines of descriptors and
+                // shortcuts `ahead + 4 l` records away (the descriptor also as a real load: its body offset is used
+                // at the next flush, some 32 nodes later), and for the bodies of the four records it asked for last
+                // time.
+                // bodies lie in record order: this lane's four records own [its body offset, the next lane's)
+                const uint32_t body_at = pf.body(), body_next = __shfl_down_sync(0xFFFFFFFFu, body_at, 1);
+                uint32_t span = body_next > body_at ? body_next - body_at : body_at - body_next;
+                if (lane == 31 || span > 64u) span = span > 64u ? 64u : 24u;  // at most 1 KiB per lane
+                for (uint32_t unit = 0; unit < span; unit += 8) prefetch_l2(bodies + body_at + unit);
                 const uint32_t rec = node - base, step = ahead + 4u * lane;
                 const bool up = node >= flush_node;
                 flush_node = node;
                 uint32_t target = up ? rec + step : rec - step;
                 if (up ? (target < rec || target >= records) : (target > rec)) target = up ? records - 1u : 0u;
                 load_sector(reinterpret_cast<const Unit16*>(descs + target), pf.a, pf.b);
+                prefetch_l2(descs + target);  // the whole line: the descriptors of this lane's four records
+                prefetch_l2(skips + target);
             }
         }
+        if (in_group == lane) mine = node;
+        in_group++;
         const uint32_t fmt = d.fmt(), i = offset;
         if (i >= d.total_len()) break;  // GBWT::forward -> None (an empty record has length 0)
-        if (fmt == FMT_SINGLE) {
-            const uint32_t next = d.node0();
-            if (next == 0) break;
-            offset = d.offset0() + i;
-            node = next;
-            d = desc_of(node);
+        if (!d.inline_edges()) {
+            // outdegree > 2: the warp scans a byte-per-run body, anything else takes the general one-lane step
+            uint32_t next_node, next_offset;
+            if (fmt == FMT_RUN8) {
+                uint32_t symbol, rank_i;
+                warp_lf_runs8(ix, d, i, symbol, rank_i);
+                if (symbol == NO_SYMBOL) break;
+                const Edge e = edge_at(ix, d, symbol);
+                next_node = e.node; next_offset = e.offset + rank_i;
+            } else {
+                const uint64_t next = forward_slow(ix, node, offset);
+                next_node = static_cast<uint32_t>(next); next_offset = static_cast<uint32_t>(next >> 32);
+            }
+            if (next_node == 0) break;
+            node = next_node; offset = next_offset;
+            load_landing<CHECKED>(descs, skips, base, records, node, d, k);
             continue;
         }
-        if (fmt == FMT_DENSE2) {
-            // outdegree 2: both candidate descriptors are requested before the body decides
-            const Desc d0 = desc_of(d.node0()), d1 = desc_of(d.node1());
-            const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
-            Quad lo, hi;
-            load_sector(bodies + d.body() + 2u * blk, lo, hi);
-            uint32_t bit;
-            const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, bit);
-            const uint32_t next = bit ? d.node1() : d.node0();
-            if (next == 0) break;
-            offset = bit ? d.offset1() + ones : d.offset0() + (i - ones);
-            node = next;
-            d.a.x = bit ? d1.a.x : d0.a.x; d.a.y = bit ? d1.a.y : d0.a.y; d.a.z = bit ? d1.a.z : d0.a.z; d.a.w = bit ? d1.a.w : d0.a.w;
-            d.b.x = bit ? d1.b.x : d0.b.x; d.b.y = bit ? d1.b.y : d0.b.y; d.b.z = bit ? d1.b.z : d0.b.z; d.b.w = bit ? d1.b.w : d0.b.w;
-            continue;
+        // where the walk lands over edge 0 / edge 1: two nodes further when the shortcut applies
+        const uint32_t land0 = k.x != 0 ? k.x : d.node0(), land1 = k.z != 0 ? k.z : d.node1();
+        Desc t0, t1;
+        Quad s0, s1;
+        // both landings are always requested (for a SINGLE record the second one is a dummy): copying t0 into t1
+        // instead would make the copy wait for the first load before the body block is even requested
+        load_landing<CHECKED>(descs, skips, base, records, land0, t0, s0);
+        load_landing<CHECKED>(descs, skips, base, records, land1, t1, s1);
+        uint32_t b = 0, r = i;  // SINGLE: every position maps to edge 0
+        if (fmt != FMT_SINGLE) {
+            if (fmt == FMT_DENSE2) {
+                const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
+                Quad lo, hi;
+                load_sector(bodies + d.body() + 2u * blk, lo, hi);
+                const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, b);
+                r = b ? ones : i - ones;
+            } else if (fmt == FMT_RUN8) {
+                warp_lf_runs8(ix, d, i, b, r);
+                if (b == NO_SYMBOL) break;
+            } else {
+                const uint64_t next = forward_slow(ix, node, offset);
+                if (next == 0) break;
+                b = static_cast<uint32_t>(next) == d.node1() && d.node1() != d.node0() ? 1u : 0u;
+                r = static_cast<uint32_t>(next >> 32) - (b ? d.offset1() : d.offset0());
+            }
         }
-        if (fmt == FMT_RUN8) {
-            // byte-per-run body: the whole warp scans it; with two inline edges the successors are requested first
-            const bool two = d.inline_edges();
-            const Desc d0 = desc_of(two ? d.node0() : base), d1 = desc_of(two ? d.node1() : base);  // `base` has no record
-            uint32_t symbol, rank_i;
-            warp_lf_runs8(ix, d, i, symbol, rank_i);
-            if (symbol == NO_SYMBOL) break;
-            const Edge e = edge_at(ix, d, symbol);
-            if (e.node == 0) break;
-            offset = e.offset + rank_i;
-            node = e.node;
-            if (two) d = symbol ? d1 : d0;
-            else d = desc_of(node);
-            continue;
+        const uint32_t v = b ? d.node1() : d.node0();
+        if (v == 0) break;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+        const uint32_t w = b ? k.z : k.x;
+        if (w != 0) {
+            if (in_group == lane) mine = v;
+            in_group++;
+            node = w;
+            offset = (b ? k.w : k.y) + r;
+        } else {
+            node = v;
+            offset = (b ? d.offset1() : d.offset0()) + r;
         }
-        const uint64_t next = forward_slow(ix, node, offset);
-        if (next == 0) break;
-        node = static_cast<uint32_t>(next);
-        offset = static_cast<uint32_t>(next >> 32);
-        d = desc_of(node);
+        d.a.x = b ? t1.a.x : t0.a.x; d.a.y = b ? t1.a.y : t0.a.y; d.a.z = b ? t1.a.z : t0.a.z; d.a.w = b ? t1.a.w : t0.a.w;
+        d.b.x = b ? t1.b.x : t0.b.x; d.b.y = b ? t1.b.y : t0.b.y; d.b.z = b ? t1.b.z : t0.b.z; d.b.w = b ? t1.b.w : t0.b.w;
+        k.x = b ? s1.x : s0.x; k.y = b ? s1.y : s0.y; k.z = b ? s1.z : s0.z; k.w = b ? s1.w : s0.w;
     }
-    if (in_group != 0) sink.group(static_cast<uint64_t>(mine), in_group, groups * 32);
+    if (in_group != 0) sink.group(static_cast<uint64_t>(mine), in_group, flushed);
     sink.finish();
-    return groups * 32 + in_group;
-#undef desc_of
+    return flushed + in_group;
 }
 
-// K3. A path walk is a dependent chain of LF steps (src/gbwt.rs:557-568): one thread per sequence, all
-// sequences of the batch in flight at once. Paths of a pangenome move through the same records at about the
-// same time, so after the first chain has pulled a record into L2 the others hit there.
-// `nodes == nullptr` only counts (GBWT::sequence(id).count()).
-// `stride` threads per chain (only the first of them walks): with one chain per warp a step waits for its own
-// loads only, not for the slowest of 32 unrelated chains, and the warp does not serialise 32 divergent paths.
-__global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
-                                                 const uint64_t* __restrict__ out_offsets, uint64_t base,
-                                                 uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t stride,
-                                                 uint32_t ahead) {
-    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (stride == 32) {
-        for (size_t i = tid / 32; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / 32) {
-            NodeSink sink{nullptr, 0};
-            if (nodes != nullptr) {
-                const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
-                sink.out = nodes + (lo - base);
-                sink.cap = hi > lo ? hi - lo : 0;
-            }
-            const uint64_t len = walk_sequence_warp(ix, __ldg(ids + i), sink, ahead);
-            if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
-        }
-        return;
-    }
-    if (tid % stride != 0) return;
-    for (size_t i = tid / stride; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / stride) {
+// K3. GBWT::sequence(id) for a batch (src/gbwt.rs:253-261, 557-568). A path walk is a dependent chain of LF steps,
+// so its speed is chains in flight / time per step; paths of a pangenome move through the same records at about
+// the same time, so after the first chain has pulled a record into L2 the others hit there.
+// k_extract: one warp per sequence (walk_sequence_warp). `nodes == nullptr` only counts.
+template <bool CHECKED>
+__global__ void __launch_bounds__(128) k_extract(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
+                                                  const uint64_t* __restrict__ out_offsets, uint64_t base,
+                                                  uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t ahead) {
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
+    for (size_t i = warp; i < m; i += warps) {
         NodeSink sink{nullptr, 0};
         if (nodes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
             sink.out = nodes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_device<false>(ix, __ldg(ids + i), sink, ahead);
+        const uint64_t len = walk_sequence_warp<CHECKED>(ix, __ldg(ids + i), sink, ahead);
+        if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
+    }
+}
+
+// k_extract_lanes: `stride` threads per sequence, the first of them walks (stride 1 = one sequence per thread, for
+// batches with far more sequences than the device has warp slots).
+__global__ void __launch_bounds__(64) k_extract_lanes(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
+                                                       const uint64_t* __restrict__ out_offsets, uint64_t base,
+                                                       uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t stride) {
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid % stride != 0) return;
+    for (size_t i = tid / stride; i < m; i += (static_cast<size_t>(gridDim.x) * blockDim.x) / stride) {
+        uint64_t* out = nullptr;
+        uint64_t cap = 0;
+        if (nodes != nullptr) {
+            const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+            out = nodes + (lo - base);
+            cap = hi > lo ? hi - lo : 0;
+        }
+        const uint64_t len = walk_sequence_lane(ix, __ldg(ids + i), out, cap);
         if (lengths != nullptr) lengths[i] = len;
     }
 }
@@ -838,19 +811,20 @@ __global__ void __launch_bounds__(64) k_extract(IndexView ix, const uint64_t* __
 // K4. extract_sequence of src/bin/gbz-extract.rs:173-189 for many GBWT sequences: one warp per sequence walks the
 // path (K3) and spells the node labels as it goes, then appends the endmarker byte. lengths[i] = bytes of the
 // full result (endmarker included), UINT64_MAX where GBZ::path is None; `bytes == nullptr` only measures.
+template <bool CHECKED>
 __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView graph, const uint64_t* __restrict__ ids, size_t m,
                                                       const uint64_t* __restrict__ out_offsets, uint64_t base, uint32_t endmarker,
                                                       uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths, uint32_t ahead) {
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t i = warp; i < m; i += warps) {
-        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0, 0, 0, 0, false};
+        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0, 0, 0, 0, false, false};
         if (bytes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
             sink.out = bytes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_warp(ix, __ldg(ids + i), sink, ahead);
+        const uint64_t len = walk_sequence_warp<CHECKED>(ix, __ldg(ids + i), sink, ahead);
         if ((threadIdx.x & 31u) != 0) continue;
         if (len == ~0ull) {
             if (lengths != nullptr) lengths[i] = ~0ull;

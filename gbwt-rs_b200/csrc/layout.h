@@ -81,6 +81,11 @@ struct IndexView {
     uint64_t sequences;
     uint64_t endmarker_len;
     uint32_t bidirectional;
+    // Path-walk accelerator (K0 pass 3), one 16-byte unit per record with inline edges: {n0, o0, n1, o1}. When the
+    // successor v_b over edge b is a single-edge record (LF(v_b, j) = (w, p + j)), n_b = w and o_b = offset_b + p,
+    // so LF(LF(u, i)) = (n_b, o_b + rank_b(i)) without touching v_b's record; n_b = 0 where that does not apply.
+    const Unit16* skips;
+    uint32_t edges_valid;     // every edge of every record leads to the endmarker or to a node with a record
 };
 
 // Magic multiplier for q = b / sigma, 0 <= b < 256, 1 <= sigma <= 256: q = (b * magic) >> 16.

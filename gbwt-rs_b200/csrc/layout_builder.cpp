@@ -273,6 +273,37 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
                     out.bodies.data(), out.edges.data());
     }
 
+    // Pass 3: edge targets are checked once here so that a path walk can follow them without bounds tests, and the
+    // two-hop shortcuts over single-edge successors are filled in (layout.h, IndexView::skips).
+    out.skips.assign(2 * R + 2, 0);
+    std::atomic<bool> edges_valid{true};
+    auto has_record = [&](uint64_t node) { return node > in.offset && node - in.offset < R; };
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
+    for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
+        const RecordDesc& d = out.desc[i];
+        if (d.fmt == FMT_EMPTY) continue;
+        if (!(d.flags & DESC_INLINE_EDGES)) {
+            for (uint64_t e = 0; e < plans[i].sigma; e++) {
+                const uint32_t node = out.edges[edge_at[i] + e].node;
+                if (node != 0 && !has_record(node)) edges_valid.store(false);
+            }
+            continue;
+        }
+        uint32_t* skip = reinterpret_cast<uint32_t*>(out.skips.data() + 2 * i);
+        for (uint64_t b = 0; b < plans[i].sigma; b++) {
+            const uint32_t* w = b == 0 ? d.w01 : d.w23;
+            if (w[0] == 0) continue;
+            if (!has_record(w[0])) { edges_valid.store(false); continue; }
+            const RecordDesc& v = out.desc[w[0] - in.offset];
+            if (v.fmt != FMT_SINGLE || v.w01[0] == 0 || !has_record(v.w01[0])) continue;
+            const uint64_t offset = static_cast<uint64_t>(w[1]) + v.w01[1];
+            if (offset > 0xFFFFFFFFull) continue;
+            skip[2 * b] = v.w01[0];
+            skip[2 * b + 1] = static_cast<uint32_t>(offset);
+        }
+    }
+    out.edges_valid = edges_valid.load();
+
     // Endmarker: Record::decompress of record 0 (src/bwt.rs:465-475, src/gbwt.rs:413-414).
     out.endmarker.clear();
     if (R > 0) {

@@ -15,6 +15,8 @@ struct HostLayout {
     std::vector<uint64_t> bodies;  // raw 16-byte units, two words each
     std::vector<Edge> edges;       // edge lists of records with sigma > 2
     std::vector<Edge> endmarker;   // Record::decompress() of record 0 (src/gbwt.rs:413-414)
+    std::vector<uint64_t> skips;   // two words per record (IndexView::skips)
+    bool edges_valid = true;
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 

@@ -38,7 +38,14 @@ GBWT_HD Quad load_quad(const Unit16* p) {
 // One 256-bit read-only load of a 32-byte-aligned sector (LDG.E.256.CONSTANT on sm_100a): descriptors and
 // dense blocks are exactly one sector, so each costs a single load instruction and a single L1 wavefront.
 GBWT_HD void load_sector(const Unit16* p, Quad& lo, Quad& hi) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(GBWT_EXP_LD128)
+    lo = load_quad(p);
+    hi = load_quad(p + 1);
+#elif defined(__CUDA_ARCH__) && defined(GBWT_EXP_CG)
+    asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+#elif defined(__CUDA_ARCH__)
     asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));

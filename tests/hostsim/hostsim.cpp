@@ -43,11 +43,20 @@ HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t
     v.sequences = h->parsed.sequences;
     v.endmarker_len = h->layout.endmarker.size();
     v.bidirectional = (h->parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
+    v.skips = reinterpret_cast<const Unit16*>(h->layout.skips.data());
+    v.edges_valid = h->layout.edges_valid ? 1 : 0;
     h->parsed.bwt = nullptr;  // the image may go away
     return h;
 }
 
 void hs_free(HostSim* h) { delete h; }
+
+// Path-walk shortcuts of K0 pass 3 (layout.h, IndexView::skips): 4 x u32 per record; and the descriptor words the
+// shortcuts are derived from: out[0..7] = {total_len, meta, w0, w1, body, body_len, w2, w3}.
+const uint32_t* hs_skips(const HostSim* h) { return reinterpret_cast<const uint32_t*>(h->layout.skips.data()); }
+int hs_edges_valid(const HostSim* h) { return h->layout.edges_valid ? 1 : 0; }
+uint64_t hs_records(const HostSim* h) { return h->layout.desc.size(); }
+void hs_desc_words(const HostSim* h, uint64_t rec, uint32_t* out) { std::memcpy(out, &h->layout.desc[rec], 32); }
 
 // Node labels as the product's loader parsed them (sds_loader.cpp parse_graph): has_graph, count, starts, bytes.
 int hs_has_graph(const HostSim* h) { return h->parsed.has_graph ? 1 : 0; }

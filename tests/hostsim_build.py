@@ -40,6 +40,12 @@ def lib():
         L.hs_load.restype = p
         L.hs_load.argtypes = [p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.hs_free.argtypes = [p]
+        L.hs_skips.restype = p
+        L.hs_skips.argtypes = [p]
+        L.hs_edges_valid.argtypes = [p]
+        L.hs_records.restype = u64
+        L.hs_records.argtypes = [p]
+        L.hs_desc_words.argtypes = [p, u64, p]
         L.hs_has_graph.argtypes = [p]
         L.hs_label_count.restype = u64
         L.hs_label_count.argtypes = [p]
@@ -95,6 +101,22 @@ class HostSim:
                 self._h = None
         except Exception:
             pass
+
+    def records(self):
+        return self._L.hs_records(self._h)
+
+    def edges_valid(self):
+        return bool(self._L.hs_edges_valid(self._h))
+
+    def skips(self):
+        """(records, 4) uint32: {n0, o0, n1, o1} per record (IndexView::skips)."""
+        n = self.records()
+        return np.ctypeslib.as_array(C.cast(self._L.hs_skips(self._h), C.POINTER(C.c_uint32)), (n, 4)).copy()
+
+    def desc_words(self, rec):
+        out = np.zeros(8, dtype=np.uint32)
+        self._L.hs_desc_words(self._h, rec, _p(out))
+        return out
 
     def labels(self):
         """(starts, bytes) of the node labels the product loader parsed from a GBZ image, or None for a plain GBWT."""

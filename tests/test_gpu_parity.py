@@ -332,3 +332,20 @@ def test_load_errors_match_reference(b200):
         b200.GBWT.load("/nonexistent/file.gbwt")
     empty = b200.GBWT.from_bytes(synth.gbwt_image(0, 0, 0, 0, 4, [], b""))
     assert empty.find(np.arange(4, dtype=np.uint64))["end"].sum() == 0 and empty.start(0) is None
+
+
+def test_extraction_with_invalid_edge_targets(b200):
+    # An edge to a node beyond the alphabet: GBWT::forward returns None there, so the sequence ends after that node.
+    # The layout flags such an index (edges_valid = false) and extraction runs its bounds-checked kernel.
+    edges = [[(1, 0)], [(2, 0), (40, 0)], [(0, 0)]]
+    runs = [[(0, 2)], [(1, 1), (0, 1)], [(0, 1)]]
+    g0 = orc.GBWT.from_records(edges, runs, sequences=2, size=6, offset=0)
+    img = synth.gbwt_image(2, 6, 0, 3, 4, g0.record_starts(), g0.bwt_data())
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+    ids = np.arange(3, dtype=np.uint64)
+    offsets, nodes, lengths = e.extract(ids)
+    for i in range(2):
+        want = [int(x) for x in g.sequence(i)]
+        assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == want
+    assert sorted(len(list(g.sequence(i))) for i in range(2)) == [2, 2] and lengths[2] == np.uint64(2**64 - 1)
+    assert {tuple(int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]) for i in range(2)} == {(1, 40), (1, 2)}

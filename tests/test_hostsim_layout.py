@@ -186,3 +186,61 @@ def test_load_errors():
             HostSim(bytes(bad))
     with pytest.raises(IOError):
         HostSim(bytes(data[:200]))
+
+
+def check_shortcuts(e, g):
+    """K0 pass 3 (IndexView::skips) against the oracle's records: a shortcut over edge b of record u exists exactly
+    when the successor is a single-edge record that does not end the path, and then LF(LF(u, i)) = (n_b, o_b + rank)."""
+    skips = e.skips()
+    offset = g.alphabet_offset()
+    checked = 0
+    for rec in range(e.records()):
+        edges = g.record_edges(rec)
+        if edges is None or len(edges) > 2:
+            assert not skips[rec].any()
+            continue
+        for b, (node, off) in enumerate(edges):
+            n_b, o_b = int(skips[rec][2 * b]), int(skips[rec][2 * b + 1])
+            succ = g.record_edges(node - offset) if node != 0 else None
+            if succ is not None and len(succ) == 1 and succ[0][0] != 0:
+                assert (n_b, o_b) == (succ[0][0], off + succ[0][1])
+                # spot check with LF: the first position of u that maps to edge b
+                for i in range(g.record_len(rec)):
+                    first = g.record_lf(rec, i)
+                    if first is not None and first[0] == node:
+                        second = g.record_lf(node - offset, first[1])
+                        assert second == (n_b, o_b + (first[1] - off))
+                        checked += 1
+                        break
+            else:
+                assert (n_b, o_b) == (0, 0)
+        for b in range(len(edges), 2):
+            assert not skips[rec][2 * b:2 * b + 2].any()
+    return checked
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_path_walk_shortcuts(layout):
+    assert HostSim(open(os.path.join(GOLDEN, "example.gbz"), "rb").read(), layout).edges_valid()
+    total = 0
+    for name in FIXTURES:
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        e = HostSim(raw, layout)
+        assert e.edges_valid()
+        total += check_shortcuts(e, orc.GBWT.load(raw))
+    img = synth.bubble_chain(40, 9, 5)
+    total += check_shortcuts(HostSim(img.array, layout), orc.GBWT.load(img.array))
+    rng = random.Random(77)
+    for _ in range(4):
+        paths = random_paths(rng, n_nodes=rng.choice([3, 6, 12]), n_paths=rng.choice([3, 10, 40]), max_len=rng.choice([3, 8, 20]))
+        img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths + [[2, 4]])))
+        total += check_shortcuts(HostSim(img, layout), orc.GBWT.load(img))
+    assert total > 100
+
+
+def test_invalid_edge_targets_are_flagged():
+    # an edge to a node beyond the alphabet: queries still answer None like the reference, and the layout says so
+    # (the extraction kernels then use their bounds-checked variant)
+    img, _ = records_image([[(0, 0), (40, 0)], [(0, 0)], [(0, 0)]], [[(0, 1), (1, 1)], [(0, 1)], [(0, 1)]], sequences=2, size=4, offset=0)
+    e = HostSim(img)
+    assert not e.edges_valid() and not e.skips().any()

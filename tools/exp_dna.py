@@ -14,6 +14,7 @@ ap.add_argument("--layout", default="auto")
 ap.add_argument("--max-anchor", type=int, default=32)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--skip-nodes", action="store_true")
+ap.add_argument("--nodes-only", action="store_true")
 args = ap.parse_args()
 S, H = args.sites, args.haplotypes
 img = synth.bubble_chain(S, H, 42)
@@ -42,6 +43,10 @@ if not args.skip_nodes:
     ms = timed(lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream))
     print(json.dumps({"op": "extract nodes", "ms": ms, "steps_per_s": m * L / ms * 1e3}), flush=True)
     del nodes
+ms = timed(lambda: index.sequence_lengths_device(ids.data_ptr(), m, lens.data_ptr(), stream))
+print(json.dumps({"op": "sequence lengths (no output)", "ms": ms, "steps_per_s": m * L / ms * 1e3}), flush=True)
+if args.nodes_only:
+    sys.exit(0)
 ms = timed(lambda: index.dna_lengths_device(ids.data_ptr(), m, lens.data_ptr(), stream))
 print(json.dumps({"op": "dna lengths", "ms": ms, "steps_per_s": m * L / ms * 1e3}), flush=True)
 offs = torch.zeros(m + 1, dtype=torch.int64, device=dev)
