@@ -653,7 +653,8 @@ __device__ __forceinline__ void load_landing(const RecordDesc* descs, const Unit
 // CHECKED = false relies on IndexView::edges_valid (no bounds tests on edge targets).
 template <bool CHECKED, class Sink>
 __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
-    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // read once: the compiler would re-read the special register per step
     if (id >= ix.sequences) return ~0ull;
     gbwt_b200_pos pos;
     if (!gbwt_start(ix, id, pos)) { sink.finish(); return 0; }
@@ -721,12 +722,15 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
         }
         // where the walk lands over edge 0 / edge 1: two nodes further when the shortcut applies
         const uint32_t land0 = k.x != 0 ? k.x : d.node0(), land1 = k.z != 0 ? k.z : d.node1();
+        // A single-edge record, or a bubble whose alleles rejoin at one node (SNPs, indels: most of a pangenome
+        // graph): the landing record does not depend on the edge taken, so it is requested once and used as it is.
+        const bool same = fmt == FMT_SINGLE || land0 == land1;
         Desc t0, t1;
         Quad s0, s1;
-        // both landings are always requested (for a SINGLE record the second one is a dummy): copying t0 into t1
-        // instead would make the copy wait for the first load before the body block is even requested
         load_landing<CHECKED>(descs, skips, base, records, land0, t0, s0);
-        load_landing<CHECKED>(descs, skips, base, records, land1, t1, s1);
+        // (copying t0 into t1 instead of a second request would make the copy wait for the first load before the
+        // body block is even requested)
+        if (!same) load_landing<CHECKED>(descs, skips, base, records, land1, t1, s1);
         uint32_t b = 0, r = i;  // SINGLE: every position maps to edge 0
         if (fmt != FMT_SINGLE) {
             if (fmt == FMT_DENSE2) {
@@ -757,9 +761,8 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
             node = v;
             offset = (b ? d.offset1() : d.offset0()) + r;
         }
-        d.a.x = b ? t1.a.x : t0.a.x; d.a.y = b ? t1.a.y : t0.a.y; d.a.z = b ? t1.a.z : t0.a.z; d.a.w = b ? t1.a.w : t0.a.w;
-        d.b.x = b ? t1.b.x : t0.b.x; d.b.y = b ? t1.b.y : t0.b.y; d.b.z = b ? t1.b.z : t0.b.z; d.b.w = b ? t1.b.w : t0.b.w;
-        k.x = b ? s1.x : s0.x; k.y = b ? s1.y : s0.y; k.z = b ? s1.z : s0.z; k.w = b ? s1.w : s0.w;
+        if (same || b == 0) { d = t0; k = s0; }
+        else { d = t1; k = s1; }
     }
     if (in_group != 0) sink.group(static_cast<uint64_t>(mine), in_group, flushed);
     sink.finish();

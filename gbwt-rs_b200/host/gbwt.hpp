@@ -141,6 +141,39 @@ public:
     std::optional<std::vector<BidirectionalState>> follow_forward(const BidirectionalState& state) const { return follow(state, 0); }
     std::optional<std::vector<BidirectionalState>> follow_backward(const BidirectionalState& state) const { return follow(state, 1); }
 
+    // Node sequences and DNA-level extraction (GBZ files). GBZ::sequence / sequence_len (src/gbz.rs:292-306):
+    // nullopt where the graph has no such node; throws std::runtime_error for an index without a graph.
+    bool has_graph() const { return gbwt_b200_has_graph(h_) != 0; }
+    std::optional<std::size_t> sequence_len(std::size_t node_id) const {
+        uint64_t id = node_id, len = 0;
+        check(gbwt_b200_node_sequence_lengths(h_, &id, 1, &len));
+        if (len == UINT64_MAX) return std::nullopt;
+        return static_cast<std::size_t>(len);
+    }
+    std::optional<std::string> node_sequence(std::size_t node_id) const {
+        auto len = sequence_len(node_id);
+        if (!len) return std::nullopt;
+        std::string out(*len, '\0');
+        uint64_t id = node_id, got = 0;
+        const uint64_t offsets[2] = {0, *len};
+        check(gbwt_b200_node_sequences(h_, &id, 1, offsets, reinterpret_cast<uint8_t*>(out.data()), &got));
+        return out;
+    }
+    // extract_sequence of src/bin/gbz-extract.rs:173-189 for GBWT sequence ids (= encode_path(path, orientation)):
+    // (offsets, bytes); every result ends with `endmarker`; a None path contributes an empty slice.
+    std::pair<std::vector<uint64_t>, std::string> extract_dna(const std::vector<uint64_t>& ids, uint8_t endmarker = 0) const {
+        std::vector<uint64_t> lengths(ids.size()), offsets(ids.size() + 1, 0);
+        check(gbwt_b200_dna_lengths(h_, ids.data(), ids.size(), lengths.data()));
+        for (std::size_t i = 0; i < ids.size(); i++) offsets[i + 1] = offsets[i] + (lengths[i] == UINT64_MAX ? 0 : lengths[i]);
+        std::string bytes(offsets.back(), '\0');
+        check(gbwt_b200_extract_dna(h_, ids.data(), ids.size(), endmarker, offsets.data(), reinterpret_cast<uint8_t*>(bytes.data()), lengths.data()));
+        return {std::move(offsets), std::move(bytes)};
+    }
+    std::optional<std::string> path_dna(std::size_t seq_id, uint8_t endmarker = 0) const {
+        if (seq_id >= sequences()) return std::nullopt;
+        return extract_dna({static_cast<uint64_t>(seq_id)}, endmarker).second;
+    }
+
     // Batched forms (what the kernels are for). Results use the C ABI value types; None = empty range.
     std::vector<gbwt_b200_state> find_extend_batch(const std::vector<uint64_t>& patterns, std::size_t k) const {
         std::size_t n = k ? patterns.size() / k : 0;

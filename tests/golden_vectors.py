@@ -173,3 +173,8 @@ def true_dna(node_sequence, path, endmarker=b"\x00"):
         seq = node_sequence(node // 2)
         out += seq[::-1].translate(table) if node & 1 else seq
     return bytes(out) + endmarker
+
+# src/gbz/tests.rs:237-247 (example.gbz) and :332-342 (translation.gbz): (node id, sequence) of every node.
+GBZ_NODES = [(11, "G"), (12, "A"), (13, "T"), (14, "T"), (15, "A"), (16, "C"), (17, "A"),
+             (21, "G"), (22, "A"), (23, "T"), (24, "T"), (25, "A")]
+GBZ_NODES_TRANSLATION = [(1, "GA"), (2, "T"), (3, "T"), (4, "A"), (5, "CA"), (6, "G"), (9, "A"), (10, "T"), (11, "TA")]

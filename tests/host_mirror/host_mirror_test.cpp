@@ -75,6 +75,17 @@ int main(int argc, char** argv) {
         std::size_t occ = 0;
         for (auto& s : out) occ += s.end - s.start;
         CHECK(out.size() == 20 && occ == 32);
+        // node sequences and DNA of a GBZ (src/gbz/tests.rs:237-247; extract_sequence, src/bin/gbz-extract.rs:173-189)
+        CHECK(!index.has_graph());
+        GBWT gbz = GBWT::load(dir + "/example.gbz");
+        CHECK(gbz.has_graph() && gbz.node_sequence(11) == std::string("G") && gbz.node_sequence(16) == std::string("C"));
+        CHECK(gbz.sequence_len(13) == std::size_t(1) && !gbz.node_sequence(18) && !gbz.sequence_len(10) && !gbz.node_sequence(26));
+        CHECK(gbz.path_dna(0, '$') == std::string("GATAA$") && gbz.path_dna(1, '$') == std::string("TTATC$") && !gbz.path_dna(12));
+        auto dna = gbz.extract_dna({0, 1, 2, 3}, '$');
+        CHECK(dna.second == "GATAA$TTATC$GATA$TATC$" && dna.first == (std::vector<uint64_t>{0, 6, 12, 17, 22}));
+        bool refused = false;
+        try { index.path_dna(0); } catch (const std::runtime_error&) { refused = true; }
+        CHECK(refused);
     } catch (const std::runtime_error& e) {
         if (std::string(e.what()).find("error 7") != std::string::npos) { std::fprintf(stderr, "%s\n", e.what()); return 77; }
         std::fprintf(stderr, "exception: %s\n", e.what());

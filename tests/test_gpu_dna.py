@@ -60,6 +60,22 @@ def test_fixture_node_sequences(b200, name, truth, first, layout):
     check_dna(e, g, endmarker=ord("$"))
 
 
+@pytest.mark.parametrize("name,nodes", [("example.gbz", gv.GBZ_NODES), ("example-v1.gbz", gv.GBZ_NODES),
+                                        ("translation.gbz", gv.GBZ_NODES_TRANSLATION), ("translation-v1.gbz", gv.GBZ_NODES_TRANSLATION)])
+def test_check_nodes_like_reference(b200, name, nodes):
+    # check_nodes of src/gbz/tests.rs:11-34 (random access part) in one batch: sequence / sequence_len of every id
+    e = b200.GBWT.load(os.path.join(GOLDEN, name))
+    truth = dict(nodes)
+    ids = np.arange(max(truth) + 2, dtype=np.uint64)
+    offsets, data, lengths = e.node_sequences(ids)
+    for node_id in range(len(ids)):
+        if node_id in truth:
+            assert data[int(offsets[node_id]):int(offsets[node_id + 1])].tobytes() == truth[node_id].encode()
+            assert lengths[node_id] == len(truth[node_id]) == e.sequence_len(node_id)
+        else:
+            assert lengths[node_id] == U64MAX and e.sequence_len(node_id) is None and e.node_sequence(node_id) is None
+
+
 def test_example_dna_literals(b200):
     e = b200.GBWT.load(os.path.join(GOLDEN, "example.gbz"))
     labels = {11 + i: s.encode() for i, s in enumerate(gv.GRAPH_SEQUENCES)}

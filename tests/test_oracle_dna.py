@@ -75,3 +75,14 @@ def test_v1_and_v2_files_agree():
 def test_gbwt_file_has_no_graph():
     g = load("example.gbwt")
     assert not g.has_graph() and g.extract_dna(0) is None and g.node_sequence(11) is None
+
+
+@pytest.mark.parametrize("name,nodes", [("example.gbz", gv.GBZ_NODES), ("example-v1.gbz", gv.GBZ_NODES),
+                                        ("translation.gbz", gv.GBZ_NODES_TRANSLATION), ("translation-v1.gbz", gv.GBZ_NODES_TRANSLATION)])
+def test_check_nodes_like_reference(name, nodes):
+    # check_nodes of src/gbz/tests.rs:11-34 (random access part): has_node / sequence for every id up to max_node + 1
+    g = load(name)
+    truth = dict(nodes)
+    for node_id in range(max(truth) + 2):
+        got = g.node_sequence(node_id)
+        assert got == (truth[node_id].encode() if node_id in truth else None)

@@ -54,11 +54,11 @@ __global__ void chase256(const uint4* __restrict__ next, uint32_t start_stride, 
 }
 
 int main(int argc, char** argv) {
-    size_t mb = argc > 1 ? atol(argv[1]) : 32;
+    double mbf = argc > 1 ? atof(argv[1]) : 32; size_t mb = (size_t)mbf;
     int blocks = argc > 2 ? atoi(argv[2]) : 148;
     int same = argc > 3 ? atoi(argv[3]) : 0;   // 1: all blocks start at the same element
     int steps = 20000;
-    size_t n = mb * 1024 * 1024 / 16;          // 16-byte elements
+    size_t n = (size_t)(mbf * 1024 * 1024) / 16;
     std::vector<uint32_t> perm(n);
     for (size_t i = 0; i < n; i++) perm[i] = i;
     std::mt19937_64 rng(1);
