@@ -644,6 +644,32 @@ __device__ __forceinline__ void load_landing(const RecordDesc* descs, const Unit
     }
 }
 
+// The steady state of a walk through a chain of bubbles, as tight as it gets: `cur` is a DENSE2 record whose two
+// successors are single-edge records that rejoin at one node L (shortcuts on both edges, same landing). One
+// iteration emits cur's node and the allele taken, and lands on L, whose descriptor and shortcut are requested into
+// `nxt` before the body block of `cur` is. Returns false (nothing done) when `cur` is anything else, or when the
+// lanes are full. The caller alternates (cur, nxt) so that no register is copied.
+template <bool CHECKED>
+__device__ __forceinline__ bool walk_bubble_step(Desc& cur_d, Quad& cur_k, Desc& nxt_d, Quad& nxt_k, const RecordDesc* descs,
+                                                 const Unit16* bodies, const Unit16* skips, uint32_t base, uint32_t records,
+                                                 uint32_t lane, uint32_t& node, uint32_t& offset, uint32_t& mine, uint32_t& in_group) {
+    const uint32_t land = cur_k.x, i = offset;
+    if (cur_d.fmt() != FMT_DENSE2 || land == 0 || land != cur_k.z || i >= cur_d.total_len() || in_group >= 31) return false;
+    load_landing<CHECKED>(descs, skips, base, records, land, nxt_d, nxt_k);
+    const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
+    Quad lo, hi;
+    load_sector(bodies + cur_d.body() + 2u * blk, lo, hi);
+    if (in_group == lane) mine = node;
+    uint32_t b;
+    const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, b);
+    const uint32_t v = b ? cur_d.node1() : cur_d.node0();
+    if (in_group + 1 == lane) mine = v;
+    in_group += 2;
+    node = land;
+    offset = b ? cur_k.w + ones : cur_k.y + (i - ones);
+    return true;
+}
+
 // GBWT::sequence(id) by one warp (all lanes hold the same state). Per iteration: one record u with inline edges
 // (outdegree <= 2), the edge b the sequence takes and the rank r of b before its offset (no body for SINGLE, one
 // 32-byte block for DENSE2, a warp scan for RUN8). If the successor v_b is a single-edge record, the shortcut of u
@@ -697,6 +723,19 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
                 prefetch_l2(descs + target);  // the whole line: the descriptors of this lane's four records
                 prefetch_l2(skips + target);
             }
+        }
+        // chains of bubbles run here, two register sets alternating; everything else takes the general iteration
+        {
+            Desc e;
+            Quad f;
+            bool moved = false;
+            for (;;) {
+                if (!walk_bubble_step<CHECKED>(d, k, e, f, descs, bodies, skips, base, records, lane, node, offset, mine, in_group)) break;
+                if (!walk_bubble_step<CHECKED>(e, f, d, k, descs, bodies, skips, base, records, lane, node, offset, mine, in_group)) { d = e; k = f; break; }
+                moved = true;
+            }
+            (void)moved;
+            if (in_group >= 31) continue;
         }
         if (in_group == lane) mine = node;
         in_group++;
