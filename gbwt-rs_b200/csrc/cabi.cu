@@ -32,6 +32,7 @@ struct gbwt_b200_index {
     void* d_endmarker = nullptr;
     void* d_skips = nullptr;
     uint64_t skip_bytes = 0;
+    void* d_seq_len = nullptr;  // length of every sequence once some walk has measured it (SEQ_LEN_UNKNOWN before)
     void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
     void* d_label_bytes = nullptr;
     bool has_graph = false;
@@ -263,8 +264,17 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
         const unsigned ctas = static_cast<unsigned>((m * 32 + block - 1) / block);
         // How far ahead (in records) the walks ask L2 for the records they are heading to; 0 disables it.
         const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
-        if (ix->view.edges_valid) k_extract<false><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, ahead);
-        else k_extract<true><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, ahead);
+        uint64_t* seq_len = static_cast<uint64_t*>(ix->d_seq_len);
+        // With an output to fill and a bidirectional index, sequences whose length is already known are walked from
+        // both ends by two warps (GBWT_B200_EXTRACT_SPLIT=0 disables it).
+        if (nodes != nullptr && ix->view.bidirectional && seq_len != nullptr && env_int("GBWT_B200_EXTRACT_SPLIT", 1) != 0) {
+            const unsigned grid = static_cast<unsigned>(std::min<size_t>(m, size_t(1) << 30));
+            if (ix->view.edges_valid) k_extract_split<false><<<grid, 64, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, seq_len, ahead);
+            else k_extract_split<true><<<grid, 64, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, seq_len, ahead);
+            return launch_done("k_extract_split");
+        }
+        if (ix->view.edges_valid) k_extract<false><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, seq_len, ahead);
+        else k_extract<true><<<ctas, block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, seq_len, ahead);
         return launch_done("k_extract");
     }
     const int block = 32;
@@ -555,6 +565,12 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_endmarker, layout.endmarker.data(), layout.endmarker.size() * sizeof(Edge), ix->bytes[3]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_skips, layout.skips.data(), layout.skips.size() * 8, ix->skip_bytes);
+    if (rc == GBWT_B200_OK) {
+        const size_t bytes = std::max<size_t>(256, parsed.sequences * sizeof(uint64_t));
+        if (cudaMalloc(&ix->d_seq_len, bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, bytes) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
+        }
+    }
     if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
     // Records are fetched as isolated 32-byte sectors; ask L2 not to widen the DRAM fetches (a hint).
     {
@@ -635,7 +651,7 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;
     {
         DeviceScope scope(ix->device);
-        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_seq_len);
         cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;

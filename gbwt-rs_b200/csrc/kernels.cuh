@@ -442,6 +442,26 @@ struct NodeSink {
     __device__ __forceinline__ void finish() {}
 };
 
+// One half of a sequence walked from either end. Forward: node j of the walk is position j. Reverse: the walk is on
+// the other strand of a bidirectional index, where node j of sequence id ^ 1 is the flipped node at position
+// len - 1 - j of sequence id (support::reverse_path, src/support.rs:310-314). Positions [lo, hi) are written; the
+// node at position `probe` is also kept in `value` (all lanes) so that the two halves can be compared where they meet.
+struct HalfSink {
+    uint64_t* out;
+    uint64_t cap, len, lo, hi, probe, value;
+    bool reverse;
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint64_t j = first + lane;
+        const uint64_t p = reverse ? len - 1 - j : j, node = reverse ? mine ^ 1ull : mine;
+        const bool valid = lane < count && (!reverse || j < len);
+        if (valid && p >= lo && p < hi && p < cap) out[p] = node;
+        const unsigned hit = __ballot_sync(0xFFFFFFFFu, valid && p == probe);
+        if (hit != 0) value = __shfl_sync(0xFFFFFFFFu, node, __ffs(static_cast<int>(hit)) - 1);
+    }
+    __device__ __forceinline__ void finish() {}
+};
+
 // Node labels of the graph in HBM: label i = bytes[starts[i] .. starts[i + 1]) (Graph::sequence, src/graph.rs:124-126).
 struct GraphView {
     const uint64_t* starts;  // [sequences + 1]
@@ -677,8 +697,11 @@ __device__ __forceinline__ bool walk_bubble_step(Desc& cur_d, Quad& cur_k, Desc&
 // further. The descriptors and shortcuts of both possible landing nodes are requested at the top of the iteration,
 // next to the body block that decides between them: ONE memory round trip per iteration.
 // CHECKED = false relies on IndexView::edges_valid (no bounds tests on edge targets).
+// `limit`: stop once at least that many nodes have been handed to the sink (checked when the lanes are flushed, so
+// the walk may run up to 32 nodes further; the sink clips).
 template <bool CHECKED, class Sink>
-__device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead) {
+__device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint64_t id, Sink& sink, uint32_t ahead,
+                                                       uint64_t limit = ~0ull) {
     uint32_t lane;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // read once: the compiler would re-read the special register per step
     if (id >= ix.sequences) return ~0ull;
@@ -702,6 +725,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
             sink.group(static_cast<uint64_t>(mine), in_group, flushed);
             flushed += in_group;
             in_group = 0;
+            if (flushed >= limit) break;
             if (ahead != 0) {
                 // Sequences that walk the graph together arrive at a record together and would all wait for the same
                 // HBM miss. Node ids follow the graph's topological order, so the records the walk needs next lie a
@@ -815,7 +839,8 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
 template <bool CHECKED>
 __global__ void __launch_bounds__(128) k_extract(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
                                                   const uint64_t* __restrict__ out_offsets, uint64_t base,
-                                                  uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths, uint32_t ahead) {
+                                                  uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths,
+                                                  uint64_t* __restrict__ seq_len, uint32_t ahead) {
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t i = warp; i < m; i += warps) {
@@ -825,8 +850,63 @@ __global__ void __launch_bounds__(128) k_extract(IndexView ix, const uint64_t* _
             sink.out = nodes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_warp<CHECKED>(ix, __ldg(ids + i), sink, ahead);
-        if (lengths != nullptr && (threadIdx.x & 31u) == 0) lengths[i] = len;
+        const uint64_t id = __ldg(ids + i);
+        const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
+        if ((threadIdx.x & 31u) == 0) {
+            if (lengths != nullptr) lengths[i] = len;
+            if (seq_len != nullptr && id < ix.sequences) seq_len[id] = len;  // remembered for k_extract_split
+        }
+    }
+}
+
+constexpr uint64_t SEQ_LEN_UNKNOWN = 0xFEFEFEFEFEFEFEFEull;  // what cudaMemset(0xFE) leaves in the length cache
+
+// k_extract_split: a walk is a dependent chain, and a bidirectional index offers a second way in: sequence id ^ 1 is
+// the same path on the other strand, so it starts where sequence id ends. Once the length of a sequence is known
+// (any earlier k_extract, e.g. the sequence_lengths call that sized the output, leaves it in `seq_len`), two warps
+// of one CTA walk it from both ends and meet in the middle: twice the chains in flight, half the chain length.
+// Both produce the node at the meeting position; if they disagree (an index whose strands are not mirror images),
+// the first warp redoes the sequence from the front alone, which is what the reference does. One call site of the
+// walk serves all three cases, so the kernel stays at the register count of the plain one.
+template <bool CHECKED>
+__global__ void __launch_bounds__(64) k_extract_split(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
+                                                       const uint64_t* __restrict__ out_offsets, uint64_t base,
+                                                       uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths,
+                                                       uint64_t* __restrict__ seq_len, uint32_t ahead) {
+    __shared__ uint64_t meet[2];
+    const uint32_t half = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (size_t i = blockIdx.x; i < m; i += gridDim.x) {
+        const uint64_t id = __ldg(ids + i);
+        const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+        const uint64_t cap = hi > lo ? hi - lo : 0;
+        const uint64_t known = id < ix.sequences ? seq_len[id] : SEQ_LEN_UNKNOWN;
+        bool split = known != SEQ_LEN_UNKNOWN && known >= 128;  // a short sequence is not worth two warps
+        uint64_t len = known;
+        // at most two rounds: the halves, then (only if they disagree where they meet) the whole sequence from the front
+        for (;;) {
+            const uint64_t mid = known / 2;  // both halves produce position `mid`; the far half writes it
+            HalfSink sink;
+            sink.out = nodes + (lo - base); sink.cap = cap; sink.value = ~0ull;
+            if (!split) { sink.len = 0; sink.lo = 0; sink.hi = ~0ull; sink.probe = ~0ull; sink.reverse = false; }
+            else if (half == 0) { sink.len = known; sink.lo = 0; sink.hi = mid; sink.probe = mid; sink.reverse = false; }
+            else { sink.len = known; sink.lo = mid; sink.hi = known; sink.probe = mid; sink.reverse = true; }
+            if (split || half == 0) {
+                const uint64_t walked = walk_sequence_warp<CHECKED>(ix, split && half == 1 ? id ^ 1ull : id, sink, ahead,
+                                                                    !split ? ~0ull : (half == 0 ? mid + 1 : known - mid));
+                if (!split) {
+                    len = walked;
+                    if (lane == 0 && id < ix.sequences) seq_len[id] = walked;
+                } else if (lane == 0) {
+                    meet[half] = sink.value;
+                }
+            }
+            __syncthreads();
+            const bool agree = !split || (meet[0] == meet[1] && meet[0] != ~0ull);
+            __syncthreads();
+            if (agree) break;
+            split = false;
+        }
+        if (threadIdx.x == 0 && lengths != nullptr) lengths[i] = len;
     }
 }
 

@@ -160,8 +160,11 @@ GBWT_B200_API int gbwt_b200_backward(const gbwt_b200_index* index, const gbwt_b2
 GBWT_B200_API int gbwt_b200_sequence_lengths(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m,
                                             uint64_t* lengths);
 /* GBWT::sequence(id).collect() for m sequences: sequence i is written to nodes[out_offsets[i] ..], at most
- * out_offsets[i+1] - out_offsets[i] nodes; lengths[i] receives the full length (UINT64_MAX for None), so
- * a caller that does not know the lengths can size the output with gbwt_b200_sequence_lengths first. */
+ * out_offsets[i+1] - out_offsets[i] nodes (what is left of a longer slot is unspecified); lengths[i] receives the
+ * full length (UINT64_MAX for None), so a caller that does not know the lengths can size the output with
+ * gbwt_b200_sequence_lengths first. On a bidirectional index, sequences whose length an earlier call has measured
+ * are walked from both ends at once (sequence id ^ 1 is the same path on the other strand); the two halves are
+ * compared at the node where they meet and a sequence is redone from the front if they differ. */
 GBWT_B200_API int gbwt_b200_extract(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m,
                                    const uint64_t* out_offsets, uint64_t* nodes, uint64_t* lengths);
 

@@ -349,3 +349,58 @@ def test_extraction_with_invalid_edge_targets(b200):
         assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == want
     assert sorted(len(list(g.sequence(i))) for i in range(2)) == [2, 2] and lengths[2] == np.uint64(2**64 - 1)
     assert {tuple(int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]) for i in range(2)} == {(1, 40), (1, 2)}
+
+
+def test_two_ended_extraction(b200, monkeypatch):
+    # Long sequences of a bidirectional index are walked from both ends once their length is known (k_extract_split):
+    # same result as the one-ended walk and the oracle, for exact, short and over-long output slots.
+    S, H, seed = 700, 24, 9
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    ids = np.arange(2 * H + 1, dtype=np.uint64)
+    first = e.extract(ids)                      # lengths measured here (sequence_lengths) -> two-ended walks
+    again = e.extract(ids)
+    monkeypatch.setenv("GBWT_B200_EXTRACT_SPLIT", "0")
+    plain = e.extract(ids)
+    for a, b in zip(first, plain):
+        assert np.array_equal(a, b)
+    for a, b in zip(again, plain):
+        assert np.array_equal(a, b)
+    monkeypatch.delenv("GBWT_B200_EXTRACT_SPLIT")
+    for i in range(0, 2 * H, 5):
+        assert np.array_equal(first[1][int(first[0][i]):int(first[0][i + 1])], np.array(list(g.sequence(i)), dtype=np.uint64))
+    # slots that are too short / too long: every result is cut to its slot, lengths report the full size
+    import ctypes as C
+    lib = b200.library()
+    L = 2 * S + 1
+    for slot in (L - 1, L // 2, L // 2 + 1, 3, 0, L + 7):
+        offsets = (np.arange(len(ids) + 1, dtype=np.uint64) * np.uint64(slot))
+        nodes = np.full(int(offsets[-1]) + 8, 0xABCD, dtype=np.uint64)
+        lengths = np.zeros(len(ids), dtype=np.uint64)
+        rc = lib.gbwt_b200_extract(e._h, ids.ctypes.data_as(C.c_void_p), len(ids), offsets.ctypes.data_as(C.c_void_p),
+                                   nodes.ctypes.data_as(C.c_void_p), lengths.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert np.all(lengths[:-1] == L) and lengths[-1] == np.uint64(2**64 - 1)
+        for i in range(2 * H):
+            want = plain[1][int(plain[0][i]):int(plain[0][i + 1])][:slot]
+            got = nodes[i * slot:(i + 1) * slot]
+            assert np.array_equal(got[:len(want)], want)   # (the rest of an over-long slot is unspecified)
+        assert np.all(nodes[int(offsets[-1]):] == 0xABCD)
+
+
+def test_two_ended_extraction_checks_where_the_halves_meet(b200):
+    # An index flagged bidirectional whose odd sequences are NOT the reverse strands of the even ones: the halves
+    # disagree at the meeting node and every sequence is redone from the front, like the reference walks it.
+    rng = random.Random(6)
+    paths = [[2 * rng.randint(1, 40) + rng.randint(0, 1) for _ in range(rng.choice([150, 200, 333]))] for _ in range(8)]
+    for i, p in enumerate(paths):  # the check is one node: make sure no pair agrees there by chance
+        other, at = paths[i ^ 1], len(p) - 1 - len(p) // 2
+        assert at >= len(other) or other[at] ^ 1 != p[len(p) // 2]
+    b = gb.build_bwt(paths)
+    img = image_of(b, bidirectional=True)
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+    ids = np.arange(len(paths), dtype=np.uint64)
+    for _ in range(2):
+        offsets, nodes, lengths = e.extract(ids)
+        for i, p in enumerate(paths):
+            assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == p == [int(x) for x in g.sequence(i)]

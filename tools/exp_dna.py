@@ -15,6 +15,7 @@ ap.add_argument("--max-anchor", type=int, default=32)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--skip-nodes", action="store_true")
 ap.add_argument("--nodes-only", action="store_true")
+ap.add_argument("--reverse", action="store_true", help="walk the reverse-strand sequences")
 args = ap.parse_args()
 S, H = args.sites, args.haplotypes
 img = synth.bubble_chain(S, H, 42)
@@ -35,7 +36,7 @@ def timed(fn, reps=args.reps):
 
 
 m, L = H, 2 * S + 1
-ids = torch.arange(m, dtype=torch.int64, device=dev) * 2
+ids = torch.arange(m, dtype=torch.int64, device=dev) * 2 + (1 if args.reverse else 0)
 lens = torch.empty(m, dtype=torch.int64, device=dev)
 if not args.skip_nodes:
     offs = torch.arange(m + 1, dtype=torch.int64, device=dev) * L
