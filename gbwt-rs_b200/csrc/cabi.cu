@@ -33,6 +33,7 @@ struct gbwt_b200_index {
     void* d_skips = nullptr;
     uint64_t skip_bytes = 0;
     void* d_seq_len = nullptr;  // length of every sequence once some walk has measured it (SEQ_LEN_UNKNOWN before)
+    void* d_dna_len = nullptr;  // the same for the DNA of every sequence (valid for the attached graph)
     void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
     void* d_label_bytes = nullptr;
     bool has_graph = false;
@@ -291,8 +292,16 @@ int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m,
     const size_t ctas = (m * 32 + block - 1) / block;
     const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
     const unsigned grid = static_cast<unsigned>(std::min<size_t>(ctas, size_t(1) << 30));
-    if (ix->view.edges_valid) k_extract_dna<false><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
-    else k_extract_dna<true><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, ahead);
+    uint64_t *seq_len = static_cast<uint64_t*>(ix->d_seq_len), *dna_len = static_cast<uint64_t*>(ix->d_dna_len);
+    // sequences whose lengths are known are spelled from both ends by two warps (see launch_extract)
+    if (bytes != nullptr && ix->view.bidirectional && env_int("GBWT_B200_EXTRACT_SPLIT", 1) != 0) {
+        const unsigned pairs = static_cast<unsigned>(std::min<size_t>(m, size_t(1) << 30));
+        if (ix->view.edges_valid) k_extract_dna_split<false><<<pairs, 64, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
+        else k_extract_dna_split<true><<<pairs, 64, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
+        return launch_done("k_extract_dna_split");
+    }
+    if (ix->view.edges_valid) k_extract_dna<false><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
+    else k_extract_dna<true><<<grid, block, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
     return launch_done("k_extract_dna");
 }
 int launch_node_sequences(const gbwt_b200_index* ix, const uint64_t* node_ids, size_t n, const uint64_t* out_offsets, uint64_t base,
@@ -521,6 +530,8 @@ int attach_graph(gbwt_b200_index* ix, const uint64_t* starts, uint64_t sequences
     cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     ix->d_label_starts = ix->d_label_bytes = nullptr;
     ix->has_graph = false;
+    // DNA lengths measured with another graph are void
+    if (ix->d_dna_len != nullptr) CUDA_TRY(cudaMemset(ix->d_dna_len, 0xFE, std::max<size_t>(256, ix->sequences * sizeof(uint64_t))));
     uint64_t a = 0, b = 0;
     int rc = upload(&ix->d_label_starts, starts, (sequences + 1) * 8, a);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_label_bytes, label_bytes, starts[sequences], b);
@@ -567,7 +578,8 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_skips, layout.skips.data(), layout.skips.size() * 8, ix->skip_bytes);
     if (rc == GBWT_B200_OK) {
         const size_t bytes = std::max<size_t>(256, parsed.sequences * sizeof(uint64_t));
-        if (cudaMalloc(&ix->d_seq_len, bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, bytes) != cudaSuccess) {
+        if (cudaMalloc(&ix->d_seq_len, bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, bytes) != cudaSuccess ||
+            cudaMalloc(&ix->d_dna_len, bytes) != cudaSuccess || cudaMemset(ix->d_dna_len, 0xFE, bytes) != cudaSuccess) {
             rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
         }
     }
@@ -651,7 +663,7 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;
     {
         DeviceScope scope(ix->device);
-        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_seq_len);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_seq_len); cudaFree(ix->d_dna_len);
         cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;

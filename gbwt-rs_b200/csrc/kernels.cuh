@@ -499,6 +499,13 @@ struct DnaSink {
     uint64_t pend_lo, pend_hi;
     uint32_t pend_rev;
     bool pend_valid, pending;
+    // Walking one half of a sequence (k_extract_dna split mode): only nodes with index < node_limit are spelled; the
+    // node with index `probe` is kept in `value`. mirror: the walk is on the other strand (sequence id ^ 1), whose DNA
+    // is the reverse complement of this sequence's, so byte t of the walk is byte end - 1 - t of the result: the same
+    // label bytes in the same order within the group, written downwards, and complemented exactly when the node is
+    // forward on the walked strand (= reverse on the requested one).
+    uint64_t node_limit, probe, value, end;
+    bool mirror;
 
     __device__ __forceinline__ void copy_pending() {
         constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -535,24 +542,31 @@ struct DnaSink {
                     const uint64_t k = (static_cast<uint64_t>(k_hi & 0x7FFFFFFFu) << 32) | k_lo;
                     rev[j] = k_hi >> 31;
                     c[j] = 0;
-                    if (b < total && written + b < cap) c[j] = __ldg(graph.bytes + ((rev[j] ? k - b : k + b) - BIAS));
+                    const uint64_t t = written + b;
+                    const bool wanted = b < total && (mirror ? t < end && end - 1 - t < cap : t < cap);
+                    if (wanted) c[j] = __ldg(graph.bytes + ((rev[j] ? k - b : k + b) - BIAS));
                 }
 #pragma unroll
                 for (uint32_t j = 0; j < ROWS; j++) {
                     const uint32_t b = row + 32 * j + lane;
-                    if (b < total && written + b < cap) out[written + b] = static_cast<uint8_t>(rev[j] ? complement_base(c[j]) : c[j]);
+                    const uint64_t t = written + b;
+                    const bool wanted = b < total && (mirror ? t < end && end - 1 - t < cap : t < cap);
+                    const bool comp = (rev[j] != 0) != mirror;
+                    if (wanted) out[mirror ? end - 1 - t : t] = static_cast<uint8_t>(comp ? complement_base(c[j]) : c[j]);
                 }
             }
         }
         written += total;
     }
-    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t) {
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
         if (pending) copy_pending();
+        const unsigned hit = __ballot_sync(0xFFFFFFFFu, lane < count && first + lane == probe);
+        if (hit != 0) value = __shfl_sync(0xFFFFFFFFu, mirror ? mine ^ 1ull : mine, __ffs(static_cast<int>(hit)) - 1);
         // the loads are unconditional (clamped index) and nothing here reads their results: a select between the
         // loaded value and zero would make this group wait for them
         const uint64_t sid = ((mine & ~1ull) - node_base) >> 1;
-        pend_valid = lane < count && sid < graph.sequences;
+        pend_valid = lane < count && first + lane < node_limit && sid < graph.sequences;
         const uint64_t at = sid < graph.sequences ? sid : 0;
         pend_lo = __ldg(graph.starts + at);
         pend_hi = __ldg(graph.starts + at + 1);
@@ -936,17 +950,19 @@ __global__ void __launch_bounds__(64) k_extract_lanes(IndexView ix, const uint64
 template <bool CHECKED>
 __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView graph, const uint64_t* __restrict__ ids, size_t m,
                                                       const uint64_t* __restrict__ out_offsets, uint64_t base, uint32_t endmarker,
-                                                      uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths, uint32_t ahead) {
+                                                      uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths,
+                                                      uint64_t* __restrict__ seq_len, uint64_t* __restrict__ dna_len, uint32_t ahead) {
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t i = warp; i < m; i += warps) {
-        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0, 0, 0, 0, false, false};
+        DnaSink sink{graph, ix.offset + 1, nullptr, 0, 0, 0, 0, 0, false, false, ~0ull, ~0ull, ~0ull, 0, false};
         if (bytes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
             sink.out = bytes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t len = walk_sequence_warp<CHECKED>(ix, __ldg(ids + i), sink, ahead);
+        const uint64_t id = __ldg(ids + i);
+        const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
         if ((threadIdx.x & 31u) != 0) continue;
         if (len == ~0ull) {
             if (lengths != nullptr) lengths[i] = ~0ull;
@@ -954,6 +970,63 @@ __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView gra
         }
         if (sink.out != nullptr && sink.written < sink.cap) sink.out[sink.written] = static_cast<uint8_t>(endmarker);
         if (lengths != nullptr) lengths[i] = sink.written + 1;
+        seq_len[id] = len;               // remembered for k_extract_dna_split
+        dna_len[id] = sink.written + 1;
+    }
+}
+
+// K4, two-ended: as k_extract_split, for DNA. With the node count and the DNA length of a sequence known, the first
+// warp spells nodes [0, mid) from the front and the second walks the other strand and writes the rest downwards from
+// the end. Accepted only if the halves meet at the same node and their bytes add up to the known length.
+template <bool CHECKED>
+__global__ void __launch_bounds__(64) k_extract_dna_split(IndexView ix, GraphView graph, const uint64_t* __restrict__ ids, size_t m,
+                                                           const uint64_t* __restrict__ out_offsets, uint64_t base, uint32_t endmarker,
+                                                           uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths,
+                                                           uint64_t* __restrict__ seq_len, uint64_t* __restrict__ dna_len, uint32_t ahead) {
+    __shared__ uint64_t meet[2], spelled[2];
+    const uint32_t half = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (size_t i = blockIdx.x; i < m; i += gridDim.x) {
+        const uint64_t id = __ldg(ids + i);
+        const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+        const uint64_t cap = hi > lo ? hi - lo : 0;
+        const bool in_range = id < ix.sequences;
+        const uint64_t known = in_range ? seq_len[id] : SEQ_LEN_UNKNOWN, known_dna = in_range ? dna_len[id] : SEQ_LEN_UNKNOWN;
+        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128;
+        uint64_t result = known_dna;
+        for (;;) {
+            const uint64_t mid = known / 2;
+            DnaSink sink{graph, ix.offset + 1, bytes + (lo - base), cap, 0, 0, 0, 0, false, false, ~0ull, ~0ull, ~0ull, 0, false};
+            if (split) {
+                sink.probe = half == 0 ? mid : known - 1 - mid;
+                sink.node_limit = half == 0 ? mid : known - mid;
+                sink.mirror = half == 1;
+                sink.end = known_dna - 1;
+            }
+            if (split || half == 0) {
+                const uint64_t walked = walk_sequence_warp<CHECKED>(ix, split && half == 1 ? id ^ 1ull : id, sink, ahead,
+                                                                    !split ? ~0ull : (half == 0 ? mid + 1 : known - mid));
+                if (lane == 0) {
+                    if (!split) {
+                        result = walked == ~0ull ? ~0ull : sink.written + 1;
+                        if (walked != ~0ull) {
+                            if (sink.written < cap) sink.out[sink.written] = static_cast<uint8_t>(endmarker);
+                            seq_len[id] = walked;
+                            dna_len[id] = sink.written + 1;
+                        }
+                    } else {
+                        meet[half] = sink.value;
+                        spelled[half] = sink.written;
+                        if (half == 0 && known_dna - 1 < cap) sink.out[known_dna - 1] = static_cast<uint8_t>(endmarker);
+                    }
+                }
+            }
+            __syncthreads();
+            const bool agree = !split || (meet[0] == meet[1] && meet[0] != ~0ull && spelled[0] + spelled[1] == known_dna - 1);
+            __syncthreads();
+            if (agree) break;
+            split = false;
+        }
+        if (threadIdx.x == 0 && lengths != nullptr) lengths[i] = result;
     }
 }
 

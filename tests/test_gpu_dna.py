@@ -193,3 +193,51 @@ def test_no_graph_is_an_error(b200):
     # GBZ::load checks (src/gbz.rs:686-694)
     with pytest.raises(IOError, match="Mismatch between GBWT alphabet size and Graph sequence count"):
         e.attach_graph(np.array([0, 1], dtype=np.uint64), b"A")
+
+
+def test_two_ended_dna_extraction(b200, monkeypatch):
+    # Once the node count and DNA length of a sequence are known (dna_lengths), it is spelled from both ends by two
+    # warps: identical bytes to the one-ended walk and the oracle, also for slots shorter than the results.
+    import ctypes as C
+    S, H, seed = 900, 20, 13
+    img = synth.bubble_chain(S, H, seed)
+    starts, data = synth.node_labels(3 * S + 1, seed=21, max_anchor=70)
+    gbz = synth.gbz_image(img, starts, data, 3)
+    e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
+    ids = np.arange(2 * H + 1, dtype=np.uint64)
+    first = e.extract_dna(ids, ord("#"))     # lengths measured inside -> two-ended
+    again = e.extract_dna(ids, ord("#"))
+    monkeypatch.setenv("GBWT_B200_EXTRACT_SPLIT", "0")
+    plain = e.extract_dna(ids, ord("#"))
+    monkeypatch.delenv("GBWT_B200_EXTRACT_SPLIT")
+    want = g.extract_dna_batch(ids, ord("#"))
+    for got in (first, again, plain):
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    lib = b200.library()
+    for slot in (100, 4001, int(want[2][0]) - 1, int(want[2][0]) // 2, 0):
+        offsets = np.arange(len(ids) + 1, dtype=np.uint64) * np.uint64(slot)
+        out = np.full(int(offsets[-1]) + 16, 0xEE, dtype=np.uint8)
+        lengths = np.zeros(len(ids), dtype=np.uint64)
+        rc = lib.gbwt_b200_extract_dna(e._h, ids.ctypes.data_as(C.c_void_p), len(ids), ord("#"), offsets.ctypes.data_as(C.c_void_p),
+                                       out.ctypes.data_as(C.c_void_p), lengths.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.array_equal(lengths, want[2])
+        for i in range(2 * H):
+            full = want[1][int(want[0][i]):int(want[0][i + 1])]
+            assert np.array_equal(out[i * slot:i * slot + min(slot, len(full))], full[:slot])
+        assert np.all(out[int(offsets[-1]):] == 0xEE)
+
+
+def test_two_ended_dna_needs_mirror_strands(b200):
+    # flagged bidirectional, but the odd sequences are unrelated paths: the halves do not meet / do not add up, and
+    # every sequence is spelled from the front like the reference does
+    rng = random.Random(6)
+    paths = [[2 * rng.randint(1, 40) + rng.randint(0, 1) for _ in range(rng.choice([150, 200, 333]))] for _ in range(8)]
+    b = gb.build_bwt(paths)
+    img = synth.gbwt_image(**image_args(b))
+    n_labels = (b["alphabet_size"] - (b["offset"] + 1)) // 2
+    starts, data = random_labels(rng, n_labels, 9)
+    gbz = synth.gbz_image(img, starts, data, 4)
+    e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
+    for _ in range(2):
+        check_dna(e, g, endmarker=ord("$"), ids=np.arange(len(paths), dtype=np.uint64))
