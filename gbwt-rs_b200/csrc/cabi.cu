@@ -181,6 +181,11 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
             if (rc != GBWT_B200_OK) return rc;
         }
         if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+        else if (ix->view.edges_valid && env_int("GBWT_B200_FIND_LEAN", 1) != 0) {
+            // 5 resident CTAs per SM (48 registers): measured 3.06 G queries/s per step on config 4 against 2.85 with 4
+            // (53 registers, no spills), 2.69 with 6 and 1.66 with 8 (spills), 2.81 for the general loop
+            k_find_extend_lean<5><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+        }
         else k_find_extend<false><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
         int rc = launch_done("k_find_extend");
         if (perm != nullptr) cudaFreeAsync(perm, s);

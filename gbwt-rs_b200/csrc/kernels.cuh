@@ -95,6 +95,95 @@ struct ChunkReader {
     }
 };
 
+// rank1 of position r < 192 inside one dense block and the bit at r (layout.h: {ones_before, c0 | c1 << 8, 192 bits}).
+__device__ __forceinline__ uint32_t dense_block_rank_lean(const Quad& lo, const Quad& hi, uint32_t r, uint32_t& bit) {
+    const uint32_t j = r >> 6, p = r & 63u;
+    const uint32_t w_lo = j == 0 ? lo.z : (j == 1 ? hi.x : hi.z);
+    const uint32_t w_hi = j == 0 ? lo.w : (j == 1 ? hi.y : hi.w);
+    const uint64_t w = (static_cast<uint64_t>(w_hi) << 32) | w_lo;
+    const uint32_t sub = ((lo.y << 8) >> (8 * j)) & 0xFFu;  // 0, c0, c1
+    bit = static_cast<uint32_t>(w >> p) & 1u;
+    return lo.x + sub + static_cast<uint32_t>(__popcll(w & ((1ull << p) - 1ull)));
+}
+
+// GBWT::find + extends (src/gbwt.rs:269-304 over Record::follow, src/bwt.rs:595-616) on an index whose records are
+// all EMPTY, SINGLE or DENSE2 with validated edge targets (IndexView::edges_valid): same results as
+// query_find_extend_rounds<false>, written for the instruction count. ncu put the general loop at 165 instructions
+// per pattern node with the issue slots as the bound (53 % busy, 0.97 eligible warps per cycle); here a pattern node
+// must EQUAL an edge target of the current record to go on, so it needs no range checks of its own, the descriptor
+// is loaded without the empty-record preamble, and the two ranks of a dense step share one block whenever the
+// range lies inside it. Same rounds as the general loop (single-edge records, then one record with a body), so the
+// lanes of a warp meet at the rank step.
+template <class Reader>
+__device__ __forceinline__ void query_find_extend_lean(const IndexView& ix, Reader& rd, uint32_t k, gbwt_b200_state& out) {
+    set_none(out);
+    if (k == 0) return;
+    const RecordDesc* const descs = ix.desc;
+    const Unit16* const bodies = ix.bodies;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    uint32_t x;
+    // GBWT::find on pattern node 0 (src/gbwt.rs:269-281): a node of the alphabet with a non-empty record
+    if (records == 0 || !rd.node(0, x) || x - base - 1u >= records - 1u) return;
+    Desc d;
+    load_sector(reinterpret_cast<const Unit16*>(descs + (x - base)), d.a, d.b);
+    uint32_t start = 0, end = d.total_len(), node = x;
+    if (end == 0) return;
+    uint32_t i = 1;
+    while (i < k) {
+        // The single-edge loop has ONE exit (failures leave through a flag): the lanes of the warp reconverge behind
+        // it and take the rank step together. With returns inside, the compiler merges the two loops and lanes that
+        // started on different kinds of record stay out of phase for the whole pattern (14.8 of 32 lanes active).
+        bool dead = false;
+        uint32_t fmt = d.fmt();
+        while (i < k && fmt == FMT_SINGLE) {
+            // every position maps to edge 0 (follow_single); the endmarker (node 0) is below first_node
+            if (!rd.node(i, x) || x != d.node0() || x == 0) { dead = true; break; }
+            const uint32_t total = d.total_len();
+            start = d.offset0() + (start < total ? start : total);
+            end = d.offset0() + (end < total ? end : total);
+            if (start >= end) { dead = true; break; }
+            node = x;
+            i++;
+            if (i < k) {
+                load_sector(reinterpret_cast<const Unit16*>(descs + (x - base)), d.a, d.b);
+                fmt = d.fmt();
+            }
+        }
+        if (dead) return;
+        if (i >= k) break;
+        if (fmt != FMT_DENSE2 || !rd.node(i, x) || x == 0) return;  // EMPTY: BWT::record() is None
+        uint32_t symbol, edge_offset;
+        if (x == d.node0()) { symbol = 0; edge_offset = d.offset0(); }
+        else if (x == d.node1()) { symbol = 1; edge_offset = d.offset1(); }
+        else return;
+        const uint32_t total = d.total_len();
+        const uint32_t s = start < total ? start : total, e = end < total ? end : total;
+        if (s >= e) return;
+        // rank1(s) from the block of s; rank1(e) = rank1(e - 1) + bit(e - 1) from the block of e - 1 (e >= 1)
+        const uint32_t blk_s = __umulhi(s, 0xAAAAAAABu) >> 7, blk_e = __umulhi(e - 1u, 0xAAAAAAABu) >> 7;
+        const Unit16* body = bodies + d.body();
+        Quad lo, hi;
+        load_sector(body + 2u * blk_s, lo, hi);
+        uint32_t bit;
+        const uint32_t ones_s = dense_block_rank_lean(lo, hi, s - blk_s * DENSE_BITS, bit);
+        uint32_t ones_e;
+        if (blk_e == blk_s) {
+            ones_e = dense_block_rank_lean(lo, hi, e - 1u - blk_e * DENSE_BITS, bit) + bit;
+        } else {
+            Quad lo2, hi2;
+            load_sector(body + 2u * blk_e, lo2, hi2);
+            ones_e = dense_block_rank_lean(lo2, hi2, e - 1u - blk_e * DENSE_BITS, bit) + bit;
+        }
+        const uint32_t rs = symbol ? ones_s : s - ones_s, re = symbol ? ones_e : e - ones_e;
+        if (rs >= re) return;
+        start = edge_offset + rs; end = edge_offset + re;
+        node = x;
+        if (++i >= k) break;
+        load_sector(reinterpret_cast<const Unit16*>(descs + (x - base)), d.a, d.b);
+    }
+    out.node = node; out.start = start; out.end = end;
+}
+
 // K1: find(p[0]) + extends, one thread per pattern. With `perm` the threads take the queries in bucket order
 // (locality schedule below; results always go to out[q]). RUNS = false is the instantiation for indexes
 // without run-length bodies (record_scan.cuh: rank_pair).
@@ -106,6 +195,21 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend(IndexView ix, con
         gbwt_b200_state st;
         ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
         query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), st);
+        store_state(out + q, st);
+    }
+}
+
+// The same for an index that has only EMPTY / SINGLE / DENSE2 records and validated edges (query_find_extend_lean).
+// With the lean loop the issue slots are no longer the bound (38 % busy) and the kernel waits for its scattered
+// sector loads, so it is compiled for CTAS resident CTAs of 256 threads per SM (more warps to hide the latency).
+template <int CTAS>
+__global__ void __launch_bounds__(BLOCK_THREADS, CTAS) k_find_extend_lean(IndexView ix, const uint64_t* __restrict__ patterns,
+                                                                           const uint32_t* __restrict__ perm, size_t n, size_t k,
+                                                                           gbwt_b200_state* __restrict__ out) {
+    GBWT_FOR_EACH_QUERY(q, n, perm) {
+        gbwt_b200_state st;
+        ChunkReader rd(patterns + q * k, static_cast<uint32_t>(k));
+        query_find_extend_lean(ix, rd, static_cast<uint32_t>(k), st);
         store_state(out + q, st);
     }
 }
@@ -639,17 +743,6 @@ __device__ __forceinline__ uint64_t forward_slow(const IndexView& ix, uint32_t n
     cur.node = node; cur.offset = offset;
     if (!gbwt_forward(ix, cur, next)) return 0;
     return (static_cast<uint64_t>(next.offset) << 32) | static_cast<uint32_t>(next.node);
-}
-
-// rank1 of position r < 192 inside one dense block and the bit at r (layout.h: {ones_before, c0 | c1 << 8, 192 bits}).
-__device__ __forceinline__ uint32_t dense_block_rank_lean(const Quad& lo, const Quad& hi, uint32_t r, uint32_t& bit) {
-    const uint32_t j = r >> 6, p = r & 63u;
-    const uint32_t w_lo = j == 0 ? lo.z : (j == 1 ? hi.x : hi.z);
-    const uint32_t w_hi = j == 0 ? lo.w : (j == 1 ? hi.y : hi.w);
-    const uint64_t w = (static_cast<uint64_t>(w_hi) << 32) | w_lo;
-    const uint32_t sub = ((lo.y << 8) >> (8 * j)) & 0xFFu;  // 0, c0, c1
-    bit = static_cast<uint32_t>(w >> p) & 1u;
-    return lo.x + sub + static_cast<uint32_t>(__popcll(w & ((1ull << p) - 1ull)));
 }
 
 // Record index of node v for a load that must be safe but whose result is only used when v has a record: edge
