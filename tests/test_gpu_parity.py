@@ -404,3 +404,31 @@ def test_two_ended_extraction_checks_where_the_halves_meet(b200):
         offsets, nodes, lengths = e.extract(ids)
         for i, p in enumerate(paths):
             assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == p == [int(x) for x in g.sequence(i)]
+
+
+def test_lean_find_kernel_edge_cases(b200, monkeypatch):
+    # A dense-only index takes the lean find/extend kernel: every way a pattern can fail, pattern lengths around the
+    # 4-node sectors the reader works in, and the same answers from the general kernel.
+    S, H, seed = 300, 40, 17
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    assert e.device_bytes()["records_run8"] == 0
+    rng = np.random.default_rng(8)
+    for k in (1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 64):
+        pats = synth.patterns(S, H, seed, n=3000, k=k) if k <= 2 * S + 1 else None
+        bad = pats.copy()
+        rows = np.arange(len(bad))
+        cols = rng.integers(0, k, len(bad))
+        kind = rng.integers(0, 6, len(bad))
+        values = np.array([0, 1, 2**32, 2**63, g.alphabet_size(), g.alphabet_size() + 5], dtype=np.uint64)
+        bad[rows, cols] = values[kind]
+        swapped = pats.copy()
+        swapped[rows, cols] ^= np.uint64(1)          # the other strand of one node
+        skipped = pats.copy()
+        skipped[:, k // 2:] = np.roll(skipped[:, k // 2:], 1, axis=1)   # a valid node in the wrong place
+        for batch in (pats, bad, swapped, skipped):
+            want = g.find_extend_batch(batch)
+            assert pc.states_equal(e.find_extend(batch), want)
+            monkeypatch.setenv("GBWT_B200_FIND_LEAN", "0")
+            assert pc.states_equal(e.find_extend(batch), want)
+            monkeypatch.delenv("GBWT_B200_FIND_LEAN")
