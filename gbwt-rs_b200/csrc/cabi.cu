@@ -301,6 +301,11 @@ int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m,
     // sequences whose lengths are known are spelled from both ends by two warps (see launch_extract)
     if (bytes != nullptr && ix->view.bidirectional && env_int("GBWT_B200_EXTRACT_SPLIT", 1) != 0) {
         const unsigned pairs = static_cast<unsigned>(std::min<size_t>(m, size_t(1) << 30));
+        if (env_int("GBWT_B200_DNA_RELAY", 1) != 0) {
+            if (ix->view.edges_valid) k_extract_dna_relay<false><<<pairs, 96, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
+            else k_extract_dna_relay<true><<<pairs, 96, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
+            return launch_done("k_extract_dna_relay");
+        }
         if (ix->view.edges_valid) k_extract_dna_split<false><<<pairs, 64, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
         else k_extract_dna_split<true><<<pairs, 64, 0, s>>>(ix->view, ix->graph, ids, m, out_offsets, base, endmarker, bytes, lengths, seq_len, dna_len, ahead);
         return launch_done("k_extract_dna_split");

@@ -1123,6 +1123,140 @@ __global__ void __launch_bounds__(64) k_extract_dna_split(IndexView ix, GraphVie
     }
 }
 
+// ---- K4 with a spelling warp ---------------------------------------------------------------------------------------
+// The walk is a latency-bound dependent chain; spelling a group of nodes costs a few hundred instructions that have
+// nothing to do with it. In this variant the two walking warps of a CTA only park their nodes in a shared-memory ring
+// and a third warp does all the spelling (label ranges, scan, byte copy) for both: the walks run at the speed of plain
+// node extraction. Ring protocol per slot: the walker waits for full == 0, writes the 32 nodes + count + first index,
+// fences and sets full = 1; the speller waits for full == 1, spells, sets full = 0. count == RELAY_DONE ends a walk.
+constexpr uint32_t RELAY_SLOTS = 4, RELAY_DONE = 0xFFFFFFFFu;
+
+struct RelayRing {
+    uint32_t nodes[RELAY_SLOTS][32];
+    uint64_t first[RELAY_SLOTS];
+    uint32_t count[RELAY_SLOTS];
+    uint32_t full[RELAY_SLOTS];
+};
+
+__device__ __forceinline__ uint32_t relay_flag(const uint32_t* flag) { return *reinterpret_cast<const volatile uint32_t*>(flag); }
+__device__ __forceinline__ void relay_set(uint32_t* flag, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(flag) = v; }
+
+// The walker's side of the ring (also keeps the node at index `probe`, flipped on the mirrored strand).
+struct RelaySink {
+    RelayRing* ring;
+    uint32_t slot;
+    uint64_t probe, value;
+    bool mirror;
+    __device__ __forceinline__ void post(uint32_t node, uint32_t count, uint64_t first) {
+        const uint32_t lane = threadIdx.x & 31u;
+        while (relay_flag(&ring->full[slot]) != 0) __nanosleep(40);
+        ring->nodes[slot][lane] = node;
+        if (lane == 0) { ring->count[slot] = count; ring->first[slot] = first; }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) relay_set(&ring->full[slot], 1u);
+        slot = (slot + 1u) % RELAY_SLOTS;
+    }
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
+        const uint32_t lane = threadIdx.x & 31u;
+        const unsigned hit = __ballot_sync(0xFFFFFFFFu, lane < count && first + lane == probe);
+        if (hit != 0) value = __shfl_sync(0xFFFFFFFFu, mirror ? mine ^ 1ull : mine, __ffs(static_cast<int>(hit)) - 1);
+        post(static_cast<uint32_t>(mine), count, first);
+    }
+    __device__ __forceinline__ void finish() {}
+};
+
+// The speller's side: takes whatever is ready on the ring; returns true when the walk has ended.
+__device__ __forceinline__ bool relay_take(RelayRing* ring, uint32_t& slot, DnaSink& sink, bool& progressed) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (relay_flag(&ring->full[slot]) != 1u) return false;
+    __threadfence_block();
+    const uint32_t count = ring->count[slot];
+    const uint64_t first = ring->first[slot];
+    const uint32_t node = ring->nodes[slot][lane];
+    __syncwarp();
+    if (lane == 0) relay_set(&ring->full[slot], 0u);  // the values are in registers: the walker may reuse the slot
+    slot = (slot + 1u) % RELAY_SLOTS;
+    progressed = true;
+    if (count == RELAY_DONE) { sink.finish(); return true; }
+    sink.group(static_cast<uint64_t>(node), count, first);
+    return false;
+}
+
+template <bool CHECKED>
+__global__ void __launch_bounds__(96, 7) k_extract_dna_relay(IndexView ix, GraphView graph, const uint64_t* __restrict__ ids, size_t m,
+                                                              const uint64_t* __restrict__ out_offsets, uint64_t base, uint32_t endmarker,
+                                                              uint8_t* __restrict__ bytes, uint64_t* __restrict__ lengths,
+                                                              uint64_t* __restrict__ seq_len, uint64_t* __restrict__ dna_len, uint32_t ahead) {
+    __shared__ RelayRing rings[2];
+    __shared__ uint64_t meet[2], spelled[2], walked_nodes;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (size_t i = blockIdx.x; i < m; i += gridDim.x) {
+        const uint64_t id = __ldg(ids + i);
+        const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+        const uint64_t cap = hi > lo ? hi - lo : 0;
+        uint8_t* out = bytes + (lo - base);
+        const bool in_range = id < ix.sequences;
+        const uint64_t known = in_range ? seq_len[id] : SEQ_LEN_UNKNOWN, known_dna = in_range ? dna_len[id] : SEQ_LEN_UNKNOWN;
+        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128;
+        uint64_t result = known_dna;
+        for (;;) {
+            const uint64_t mid = known / 2;
+            if (threadIdx.x < 2 * RELAY_SLOTS) rings[threadIdx.x / RELAY_SLOTS].full[threadIdx.x % RELAY_SLOTS] = 0;
+            __syncthreads();
+            if (warp < 2) {
+                if (split || warp == 0) {
+                    RelaySink sink{&rings[warp], 0, ~0ull, ~0ull, split && warp == 1};
+                    if (split) sink.probe = warp == 0 ? mid : known - 1 - mid;
+                    const uint64_t walked = walk_sequence_warp<CHECKED>(ix, split && warp == 1 ? id ^ 1ull : id, sink, ahead,
+                                                                        !split ? ~0ull : (warp == 0 ? mid + 1 : known - mid));
+                    sink.post(0, RELAY_DONE, 0);
+                    if (lane == 0) {
+                        meet[warp] = sink.value;
+                        if (warp == 0) walked_nodes = walked;
+                    }
+                }
+            } else {
+                // the spelling warp: one DnaSink per walking warp
+                DnaSink front{graph, ix.offset + 1, out, cap, 0, 0, 0, 0, false, false, ~0ull, ~0ull, ~0ull, 0, false};
+                DnaSink back{graph, ix.offset + 1, out, cap, 0, 0, 0, 0, false, false, ~0ull, ~0ull, ~0ull, 0, false};
+                if (split) {
+                    front.node_limit = mid;
+                    back.node_limit = known - mid; back.mirror = true; back.end = known_dna - 1;
+                }
+                bool front_done = false, back_done = !split;
+                uint32_t front_slot = 0, back_slot = 0;
+                while (!(front_done && back_done)) {
+                    bool progressed = false;
+                    if (!front_done) front_done = relay_take(&rings[0], front_slot, front, progressed);
+                    if (!back_done) back_done = relay_take(&rings[1], back_slot, back, progressed);
+                    if (!progressed) __nanosleep(100);
+                }
+                if (lane == 0) { spelled[0] = front.written; spelled[1] = back.written; }
+            }
+            __syncthreads();
+            const bool ended = walked_nodes != ~0ull;  // (non-split) ~0: GBZ::path is None
+            const bool agree = !split || (meet[0] == meet[1] && meet[0] != ~0ull && spelled[0] + spelled[1] == known_dna - 1);
+            if (threadIdx.x == 0) {
+                if (!split) {
+                    result = ended ? spelled[0] + 1 : ~0ull;
+                    if (ended) {
+                        if (spelled[0] < cap) out[spelled[0]] = static_cast<uint8_t>(endmarker);
+                        seq_len[id] = walked_nodes;
+                        dna_len[id] = spelled[0] + 1;
+                    }
+                } else if (agree && known_dna - 1 < cap) {
+                    out[known_dna - 1] = static_cast<uint8_t>(endmarker);
+                }
+            }
+            __syncthreads();
+            if (agree) break;
+            split = false;
+        }
+        if (threadIdx.x == 0 && lengths != nullptr) lengths[i] = result;
+    }
+}
+
 // GBZ::sequence(node_id) for a batch of original-graph node identifiers (src/gbz.rs:286-298): lengths[i] = label
 // length, UINT64_MAX where the reference returns None (no such node: outside the alphabet or an empty record);
 // with `bytes`, label i is copied to bytes[out_offsets[i] - base ..), truncated to its slot. One warp per node.
