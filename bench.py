@@ -529,7 +529,7 @@ def bench_extract_dna(args, index, image, sites, haplotypes, rank, world, local_
                                    f"{total_bytes // max(1, m)} bases each) of the {3 * sites + 1}-node bubble-chain GBZ",
                        "paths_per_gpu": m, "layout": args.layout, "label_bytes": int(starts[-1]),
                        "note": "sequence and DNA lengths are known to the index from the dna_lengths call that sized the output, "
-                               "so every path is spelled from both ends (k_extract_dna_split)"},
+                               "so every path is walked from both ends by two warps that relay their nodes to a spelling warp (k_extract_dna_relay)"},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu_baseline,
             "extra": {"lf_steps_per_s": haplotypes * length * args.steps / (total_ms / 1e3), "lengths_only_ms": lengths_only_ms,
                       "index_device_bytes": stats,
