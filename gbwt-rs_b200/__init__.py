@@ -56,6 +56,9 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_index_from_bytes": (i, [p, sz, i, i, pp]),
         "gbwt_b200_index_from_parts": (i, [u64, u64, u64, u64, u64, p, u64, p, u64, i, i, pp]),
         "gbwt_b200_index_destroy": (None, [p]),
+        "gbwt_b200_index_serialize": (i, [p, pp, C.POINTER(sz)]),
+        "gbwt_b200_index_save_file": (i, [p, C.c_char_p]),
+        "gbwt_b200_free": (None, [p]),
         "gbwt_b200_last_error": (C.c_char_p, []),
         "gbwt_b200_len": (u64, [p]), "gbwt_b200_sequences": (u64, [p]), "gbwt_b200_alphabet_size": (u64, [p]),
         "gbwt_b200_alphabet_offset": (u64, [p]), "gbwt_b200_effective_size": (u64, [p]), "gbwt_b200_first_node": (u64, [p]),
@@ -250,6 +253,18 @@ class GBWT:
             raise ValueError("label_starts must hold one entry per label plus the total length")
         self._check(_lib.gbwt_b200_index_attach_graph(self._h, len(starts) - 1, _ptr(starts), _ptr(data)))
         return self
+
+    def serialize(self) -> bytes:
+        """GBWT::serialize (src/gbwt.rs:388-400): the index as a Simple-SDS GBWT image (no DA samples, no metadata)."""
+        image, n = C.c_void_p(), C.c_size_t(0)
+        self._check(_lib.gbwt_b200_index_serialize(self._h, C.byref(image), C.byref(n)))
+        try:
+            return bytes((C.c_uint8 * n.value).from_address(image.value)) if n.value else b""
+        finally:
+            _lib.gbwt_b200_free(image)
+
+    def save(self, path) -> None:
+        self._check(_lib.gbwt_b200_index_save_file(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None):

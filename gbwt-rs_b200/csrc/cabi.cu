@@ -17,6 +17,7 @@
 #include "../../include/gbwt_b200.h"
 #include "kernels.cuh"
 #include "layout_builder.h"
+#include "layout_writer.h"
 #include "sds_loader.h"
 
 using namespace gbwt_b200;
@@ -668,6 +669,49 @@ int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, uint64_t offse
     }
     return create_index(parsed, device, layout_policy, out);
 }
+
+int gbwt_b200_index_serialize(const gbwt_b200_index* ix, void** image, size_t* len) {
+    if (int rc = check_index(ix)) return rc;
+    if (image == nullptr || len == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    *image = nullptr; *len = 0;
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    // the layout comes back from HBM as it is; the encoder runs on the host
+    std::vector<RecordDesc> desc(ix->view.records);
+    std::vector<uint64_t> bodies(ix->bytes[1] / 8 + 2, 0);
+    std::vector<Edge> edges(ix->bytes[2] / sizeof(Edge) + 1, Edge{0, 0});
+    if (!desc.empty()) CUDA_TRY(cudaMemcpy(desc.data(), ix->d_desc, desc.size() * sizeof(RecordDesc), cudaMemcpyDeviceToHost));
+    if (ix->bytes[1] > 0) CUDA_TRY(cudaMemcpy(bodies.data(), ix->d_bodies, ix->bytes[1], cudaMemcpyDeviceToHost));
+    if (ix->bytes[2] > 0) CUDA_TRY(cudaMemcpy(edges.data(), ix->d_edges, ix->bytes[2], cudaMemcpyDeviceToHost));
+    LayoutArrays in;
+    in.desc = desc.data(); in.records = desc.size(); in.bodies = bodies.data(); in.edges = edges.data();
+    GBWTHeaderFields header;
+    header.sequences = ix->sequences; header.size = ix->size; header.offset = ix->offset;
+    header.alphabet_size = ix->alphabet_size; header.flags = ix->flags;
+    std::vector<uint8_t> bytes;
+    std::string err;
+    int rc = write_gbwt_image(header, in, bytes, err);
+    if (rc != GBWT_B200_OK) return fail(rc, err);
+    void* out = std::malloc(std::max<size_t>(bytes.size(), 1));
+    if (out == nullptr) return fail(GBWT_B200_E_IO, "out of memory");
+    std::memcpy(out, bytes.data(), bytes.size());
+    *image = out; *len = bytes.size();
+    return GBWT_B200_OK;
+}
+
+int gbwt_b200_index_save_file(const gbwt_b200_index* ix, const char* path) {
+    if (path == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null path");
+    void* image = nullptr;
+    size_t len = 0;
+    if (int rc = gbwt_b200_index_serialize(ix, &image, &len)) return rc;
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    bool ok = static_cast<bool>(f);
+    if (ok) { f.write(static_cast<const char*>(image), static_cast<std::streamsize>(len)); ok = static_cast<bool>(f); }
+    std::free(image);
+    return ok ? GBWT_B200_OK : fail(GBWT_B200_E_IO, std::string("cannot write ") + path);
+}
+
+void gbwt_b200_free(void* p) { std::free(p); }
 
 void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;

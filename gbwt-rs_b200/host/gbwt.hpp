@@ -58,6 +58,8 @@ public:
         check(gbwt_b200_index_from_bytes(bytes, len, device, layout, &h));
         return GBWT(h);
     }
+    // serialize::serialize_to (src/gbwt.rs:388-400): a Simple-SDS GBWT file without DA samples and metadata.
+    void save(const std::string& path) const { check(gbwt_b200_index_save_file(h_, path.c_str())); }
     GBWT(GBWT&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     GBWT& operator=(GBWT&& o) noexcept { if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; } return *this; }
     GBWT(const GBWT&) = delete;

@@ -86,6 +86,14 @@ GBWT_B200_API int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, 
  * against queries running on the same handle. Indexes loaded from a GBZ image have their graph already. */
 GBWT_B200_API int gbwt_b200_index_attach_graph(gbwt_b200_index* index, uint64_t sequences, const uint64_t* label_starts,
                                               const uint8_t* label_bytes);
+/* The way back (GBWT::serialize, src/gbwt.rs:388-400): the index as a Simple-SDS GBWT image that the reference
+ * crate and the C++ tools can load. Records are re-encoded from the device layout in the reference encoding with
+ * maximal runs (BWTBuilder::append, src/bwt.rs:241-253), so the BWT of a file written by the reference comes back
+ * byte for byte; tags are reduced to `source`, document-array samples and metadata are not carried (they never
+ * reach the device) and the metadata flag is cleared. `*image` is allocated by the library: gbwt_b200_free(). */
+GBWT_B200_API int gbwt_b200_index_serialize(const gbwt_b200_index* index, void** image, size_t* len);
+GBWT_B200_API int gbwt_b200_index_save_file(const gbwt_b200_index* index, const char* path);
+GBWT_B200_API void gbwt_b200_free(void* p);
 GBWT_B200_API void gbwt_b200_index_destroy(gbwt_b200_index* index);
 /* Message of the last failure on the calling thread (never NULL). */
 GBWT_B200_API const char* gbwt_b200_last_error(void);

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../gbwt-rs_b200/csrc/layout_builder.h"
+#include "../../gbwt-rs_b200/csrc/layout_writer.h"
 #include "../../gbwt-rs_b200/csrc/record_scan.cuh"
 #include "../../gbwt-rs_b200/csrc/sds_loader.h"
 
@@ -50,6 +51,21 @@ HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t
 }
 
 void hs_free(HostSim* h) { delete h; }
+
+// The layout written back as a GBWT image (layout_writer.cpp): returns the size; fills `out` when it is large enough.
+uint64_t hs_serialize(const HostSim* h, uint8_t* out, uint64_t cap) {
+    LayoutArrays in;
+    in.desc = h->layout.desc.data(); in.records = h->layout.desc.size();
+    in.bodies = h->layout.bodies.data(); in.edges = h->layout.edges.data();
+    GBWTHeaderFields header;
+    header.sequences = h->parsed.sequences; header.size = h->parsed.size; header.offset = h->parsed.offset;
+    header.alphabet_size = h->parsed.alphabet_size; header.flags = h->parsed.flags;
+    std::vector<uint8_t> image;
+    std::string err;
+    if (write_gbwt_image(header, in, image, err) != GBWT_B200_OK) return 0;
+    if (out != nullptr && cap >= image.size()) std::memcpy(out, image.data(), image.size());
+    return image.size();
+}
 
 // Path-walk shortcuts of K0 pass 3 (layout.h, IndexView::skips): 4 x u32 per record; and the descriptor words the
 // shortcuts are derived from: out[0..7] = {total_len, meta, w0, w1, body, body_len, w2, w3}.

@@ -15,9 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "hostsim", "hostsim.cpp"),
        os.path.join(ROOT, "gbwt-rs_b200", "csrc", "layout_builder.cpp"),
-       os.path.join(ROOT, "gbwt-rs_b200", "csrc", "sds_loader.cpp")]
+       os.path.join(ROOT, "gbwt-rs_b200", "csrc", "sds_loader.cpp"),
+       os.path.join(ROOT, "gbwt-rs_b200", "csrc", "layout_writer.cpp")]
 DEPS = SRC + [os.path.join(ROOT, "gbwt-rs_b200", "csrc", f) for f in
-              ("layout.h", "layout_builder.h", "sds_loader.h", "record_scan.cuh")] + \
+              ("layout.h", "layout_builder.h", "sds_loader.h", "layout_writer.h", "record_scan.cuh")] + \
        [os.path.join(ROOT, "include", "gbwt_b200.h")]
 OUT = os.path.join(HERE, "hostsim", "libgbwt_hostsim.so")
 
@@ -40,6 +41,8 @@ def lib():
         L.hs_load.restype = p
         L.hs_load.argtypes = [p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.hs_free.argtypes = [p]
+        L.hs_serialize.restype = u64
+        L.hs_serialize.argtypes = [p, p, u64]
         L.hs_skips.restype = p
         L.hs_skips.argtypes = [p]
         L.hs_edges_valid.argtypes = [p]
@@ -101,6 +104,13 @@ class HostSim:
                 self._h = None
         except Exception:
             pass
+
+    def serialize(self) -> bytes:
+        """The layout written back as a Simple-SDS GBWT image (csrc/layout_writer.cpp)."""
+        n = self._L.hs_serialize(self._h, None, 0)
+        buf = np.zeros(n, dtype=np.uint8)
+        assert self._L.hs_serialize(self._h, _p(buf), n) == n
+        return buf.tobytes()
 
     def records(self):
         return self._L.hs_records(self._h)

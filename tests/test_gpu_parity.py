@@ -432,3 +432,27 @@ def test_lean_find_kernel_edge_cases(b200, monkeypatch):
             monkeypatch.setenv("GBWT_B200_FIND_LEAN", "0")
             assert pc.states_equal(e.find_extend(batch), want)
             monkeypatch.delenv("GBWT_B200_FIND_LEAN")
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_serialize_round_trip(b200, layout, tmp_path):
+    # GBWT::serialize through the C ABI: the layout comes back from HBM and is re-encoded on the host. Same image as
+    # the CPU run of the writer (tests/test_layout_writer.py checks that one against the reference's files), loads in
+    # the oracle and in the product, and gives the same answers.
+    from hostsim_build import HostSim
+    for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        e = b200.GBWT.from_bytes(raw, layout=layout)
+        image = e.serialize()
+        assert image == HostSim(raw, 0 if layout == "auto" else 1).serialize()
+        src, back = orc.GBWT.load(raw), orc.GBWT.load(image)
+        assert back.bwt_data() == src.bwt_data() and np.array_equal(back.record_starts(), src.record_starts())
+        path = str(tmp_path / (name + ".out"))
+        e.save(path)
+        assert open(path, "rb").read() == image
+        pc.check_everything(b200.GBWT.load(path, layout=layout), src)
+    S, H, seed = 400, 100, 6
+    img = synth.bubble_chain(S, H, seed)
+    e = b200.GBWT.from_bytes(img.array, layout=layout)
+    back = orc.GBWT.load(e.serialize())
+    assert back.bwt_data() == orc.GBWT.load(img.array).bwt_data()
