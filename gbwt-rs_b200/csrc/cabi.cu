@@ -205,7 +205,10 @@ int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, 
         }, &perm);
         if (rc != GBWT_B200_OK) return rc;
     }
-    k_find_extend_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);
+    if (!has_run_records(ix) && ix->view.edges_valid && env_int("GBWT_B200_FIND_LEAN", 1) != 0)
+        k_find_extend_ragged<true><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);
+    else
+        k_find_extend_ragged<false><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);
     int rc = launch_done("k_find_extend_ragged");
     if (perm != nullptr) cudaFreeAsync(perm, s);
     return rc;

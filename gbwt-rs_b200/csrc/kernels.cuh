@@ -329,14 +329,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_scatter(const uint32_t
 }
 
 // `base` = offsets[0] of the chunk that `nodes` starts at (host entry points upload node chunks).
-__global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend_ragged(IndexView ix, const uint64_t* __restrict__ nodes,
-                                                                       const uint64_t* __restrict__ offsets, uint64_t base,
-                                                                       const uint32_t* __restrict__ perm, size_t n,
-                                                                       gbwt_b200_state* __restrict__ out) {
+// LEAN: the index qualifies for query_find_extend_lean (see k_find_extend_lean).
+template <bool LEAN>
+__global__ void __launch_bounds__(BLOCK_THREADS, LEAN ? 5 : 1) k_find_extend_ragged(IndexView ix, const uint64_t* __restrict__ nodes,
+                                                                                     const uint64_t* __restrict__ offsets, uint64_t base,
+                                                                                     const uint32_t* __restrict__ perm, size_t n,
+                                                                                     gbwt_b200_state* __restrict__ out) {
     GBWT_FOR_EACH_QUERY(q, n, perm) {
         const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
+        const uint64_t len = hi > lo ? hi - lo : 0;
         gbwt_b200_state st;
-        query_find_extend(ix, nodes + (lo - base), hi > lo ? hi - lo : 0, st);
+        if (LEAN && len <= 0xFFFFFFFFull) {
+            ChunkReader rd(nodes + (lo - base), static_cast<uint32_t>(len));
+            query_find_extend_lean(ix, rd, static_cast<uint32_t>(len), st);
+        } else {
+            query_find_extend(ix, nodes + (lo - base), len, st);
+        }
         store_state(out + q, st);
     }
 }

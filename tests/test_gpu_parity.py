@@ -429,8 +429,16 @@ def test_lean_find_kernel_edge_cases(b200, monkeypatch):
         for batch in (pats, bad, swapped, skipped):
             want = g.find_extend_batch(batch)
             assert pc.states_equal(e.find_extend(batch), want)
+            # the same rows as ragged patterns cut to assorted lengths (unaligned starts for the sector reader)
+            lens = rng.integers(0, k + 1, len(batch))
+            offsets = np.zeros(len(batch) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=offsets[1:])
+            flat = np.concatenate([batch[r, :lens[r]] for r in range(len(batch))]) if offsets[-1] else np.zeros(0, np.uint64)
+            want_ragged = g.find_extend_ragged(flat, offsets)
+            assert pc.states_equal(e.find_extend_ragged(flat, offsets), want_ragged)
             monkeypatch.setenv("GBWT_B200_FIND_LEAN", "0")
             assert pc.states_equal(e.find_extend(batch), want)
+            assert pc.states_equal(e.find_extend_ragged(flat, offsets), want_ragged)
             monkeypatch.delenv("GBWT_B200_FIND_LEAN")
 
 
