@@ -125,8 +125,8 @@ bool wants_locality(const gbwt_b200_index* ix, size_t n) {
     return locality == 1 || (locality != 0 && n >= LOCALITY_MIN_QUERIES && index_bytes >= LOCALITY_MIN_INDEX_BYTES);
 }
 
-// Locality schedule: counting sort of the batch by the record of each query's first node. `write_keys(shift, keys)`
-// launches the kernel that fills keys[q] = bucket of query q; on success *perm holds the sorted order and the
+// Locality schedule: counting sort of the batch by the record of each query's first node. `write_keys(shift, keys, counts)`
+// launches the kernel that fills keys[q] = bucket of query q and counts the buckets; on success *perm holds the sorted order and the
 // caller frees it with cudaFreeAsync on the same stream once the search kernel is enqueued.
 // About 256 queries per bucket and at most 2^18 buckets (GBWT_B200_BUCKETS overrides): measured on config 4,
 // a full sort (one bucket per record) makes the search kernel 11% faster but the sort itself twice as
@@ -146,10 +146,8 @@ int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, Wri
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&keys), n * sizeof(uint32_t), s));
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(perm), n * sizeof(uint32_t), s));
     CUDA_TRY(cudaMemsetAsync(counts, 0, m * sizeof(uint32_t), s));
-    write_keys(shift, keys);
+    write_keys(shift, keys, counts);  // keys[q] = bucket of query q, counts[bucket + 1] += 1
     launch_done("k_keys");
-    k_bucket_count<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts);
-    launch_done("k_bucket_count");
     k_scan_tiles<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
     launch_done("k_scan_tiles");
     if (tiles > 1) {
@@ -176,8 +174,8 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
         const uint64_t* part = patterns + begin * k;
         uint32_t* perm = nullptr;
         if (k >= 2 && wants_locality(ix, count)) {
-            int rc = build_locality_perm(ix, count, s, [&](uint32_t shift, uint32_t* keys) {
-                k_keys_fixed<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, keys);
+            int rc = build_locality_perm(ix, count, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
+                k_keys_fixed<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, keys, counts);
             }, &perm);
             if (rc != GBWT_B200_OK) return rc;
         }
@@ -200,8 +198,8 @@ int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, 
     if (n == 0) return GBWT_B200_OK;
     uint32_t* perm = nullptr;
     if (wants_locality(ix, n)) {
-        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys) {
-            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, nullptr, n, shift, keys);
+        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
+            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, nullptr, n, shift, keys, counts);
         }, &perm);
         if (rc != GBWT_B200_OK) return rc;
     }
@@ -230,8 +228,8 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
     if (n == 0) return GBWT_B200_OK;
     uint32_t* perm = nullptr;
     if (wants_locality(ix, n)) {
-        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys) {
-            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys);
+        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
+            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);
         }, &perm);
         if (rc != GBWT_B200_OK) return rc;
     }

@@ -235,26 +235,27 @@ __host__ __device__ inline uint64_t bucket_count(uint64_t records, uint32_t shif
 
 // keys[q] = bucket of query q: its first node is pattern row q, column 0 ...
 __global__ void __launch_bounds__(BLOCK_THREADS) k_keys_fixed(IndexView ix, const uint64_t* __restrict__ patterns, size_t n,
-                                                               size_t k, uint32_t shift, uint32_t* __restrict__ keys) {
-    GBWT_GRID_STRIDE(q, n) { keys[q] = bucket_of(ix, __ldg(patterns + q * k), shift); }
+                                                               size_t k, uint32_t shift, uint32_t* __restrict__ keys,
+                                                               uint32_t* __restrict__ counts) {
+    GBWT_GRID_STRIDE(q, n) {
+        const uint32_t b = bucket_of(ix, __ldg(patterns + q * k), shift);
+        keys[q] = b;
+        atomicAdd(counts + 1 + b, 1u);  // counts[0] stays 0 for the exclusive scan
+    }
 }
 
 // ... or nodes[offsets[q] - base + first[q]] for ragged batches (first == nullptr: the first node of the pattern).
 __global__ void __launch_bounds__(BLOCK_THREADS) k_keys_ragged(IndexView ix, const uint64_t* __restrict__ nodes,
                                                                 const uint64_t* __restrict__ offsets, uint64_t base,
                                                                 const uint64_t* __restrict__ first, size_t n, uint32_t shift,
-                                                                uint32_t* __restrict__ keys) {
+                                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ counts) {
     GBWT_GRID_STRIDE(q, n) {
         const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
         const uint64_t at = first != nullptr ? __ldg(first + q) : 0;
-        keys[q] = (hi > lo && at < hi - lo) ? bucket_of(ix, __ldg(nodes + (lo - base) + at), shift) : 0;
+        const uint32_t b = (hi > lo && at < hi - lo) ? bucket_of(ix, __ldg(nodes + (lo - base) + at), shift) : 0;
+        keys[q] = b;
+        atomicAdd(counts + 1 + b, 1u);
     }
-}
-
-// counts[b + 1] += 1 for the bucket b of every query (counts[0] stays 0 for the exclusive scan).
-__global__ void __launch_bounds__(BLOCK_THREADS) k_bucket_count(const uint32_t* __restrict__ keys, size_t n,
-                                                                 uint32_t* __restrict__ counts) {
-    GBWT_GRID_STRIDE(q, n) { atomicAdd(counts + 1 + __ldg(keys + q), 1u); }
 }
 
 // Inclusive scan of counts[0 .. m) in three launches: every CTA scans one tile of SCAN_TILE entries in place and
