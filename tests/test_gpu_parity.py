@@ -464,3 +464,24 @@ def test_serialize_round_trip(b200, layout, tmp_path):
     e = b200.GBWT.from_bytes(img.array, layout=layout)
     back = orc.GBWT.load(e.serialize())
     assert back.bwt_data() == orc.GBWT.load(img.array).bwt_data()
+
+
+def test_extraction_of_many_short_sequences(b200, monkeypatch):
+    # more sequences than warps worth running: one sequence per thread (k_extract_lanes), and the same batch with a
+    # forced thread stride; repeated ids are fine
+    rng = random.Random(3)
+    from test_hostsim_layout import random_paths
+    paths = random_paths(rng, n_nodes=9, n_paths=60, max_len=14)
+    img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths + [[2, 4]])))
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+    ids = np.array([rng.randrange(g.sequences() + 1) for _ in range(70_000)], dtype=np.uint64)
+    want_offsets, want_nodes = g.extract_batch(ids)
+    offsets, nodes, lengths = e.extract(ids)
+    assert np.array_equal(offsets, want_offsets) and np.array_equal(nodes, want_nodes)
+    assert np.array_equal(lengths == np.uint64(2**64 - 1), ids >= g.sequences())
+    for stride in ("1", "4", "32"):
+        monkeypatch.setenv("GBWT_B200_EXTRACT_STRIDE", stride)
+        offsets, nodes, _ = e.extract(ids[:5000])
+        monkeypatch.delenv("GBWT_B200_EXTRACT_STRIDE")
+        w_off, w_nodes = g.extract_batch(ids[:5000])
+        assert np.array_equal(offsets, w_off) and np.array_equal(nodes, w_nodes)
