@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/gbwt_b200.h"
+#include "find_mixed.h"
 #include "kernels.cuh"
 #include "layout_builder.h"
 #include "layout_writer.h"
@@ -117,6 +118,15 @@ bool has_run_records(const gbwt_b200_index* ix) {
     return ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64] != 0;
 }
 
+// The lean find/extend loop handles single-edge and dense records itself and calls out of line for the rest: it is
+// the kernel of choice when the rest is a minority (a pangenome index under the dense policy), not for a run-length
+// layout. Needs validated edge targets. GBWT_B200_FIND_LEAN=0 forces the general kernels.
+bool wants_lean_find(const gbwt_b200_index* ix) {
+    const uint64_t runs = ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64];
+    return ix->view.edges_valid && runs <= ix->format_counts[FMT_DENSE2] + ix->format_counts[FMT_SINGLE] / 4 &&
+           env_int("GBWT_B200_FIND_LEAN", 1) != 0;
+}
+
 // Whether a batch of n queries gets the locality schedule (GBWT_B200_LOCALITY overrides).
 bool wants_locality(const gbwt_b200_index* ix, size_t n) {
     const uint64_t index_bytes = ix->bytes[0] + ix->bytes[1] + ix->bytes[2];
@@ -179,12 +189,16 @@ int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size
             }, &perm);
             if (rc != GBWT_B200_OK) return rc;
         }
-        if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
-        else if (ix->view.edges_valid && env_int("GBWT_B200_FIND_LEAN", 1) != 0) {
+        const int force = env_int("GBWT_B200_FIND_LEAN", 1);  // development: 0 general, 2 general with runs, 3 lean mixed
+        if (force == 2) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+        else if (force == 3) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out + begin, grid_for(ix, count), s);
+        else if (wants_lean_find(ix)) {
             // 5 resident CTAs per SM (48 registers): measured 3.06 G queries/s per step on config 4 against 2.85 with 4
             // (53 registers, no spills), 2.69 with 6 and 1.66 with 8 (spills), 2.81 for the general loop
-            k_find_extend_lean<5><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+            if (has_run_records(ix)) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out + begin, grid_for(ix, count), s);
+            else k_find_extend_lean<5><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
         }
+        else if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
         else k_find_extend<false><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
         int rc = launch_done("k_find_extend");
         if (perm != nullptr) cudaFreeAsync(perm, s);
@@ -203,7 +217,9 @@ int launch_find_extend_ragged(const gbwt_b200_index* ix, const uint64_t* nodes, 
         }, &perm);
         if (rc != GBWT_B200_OK) return rc;
     }
-    if (!has_run_records(ix) && ix->view.edges_valid && env_int("GBWT_B200_FIND_LEAN", 1) != 0)
+    if (wants_lean_find(ix) && has_run_records(ix))
+        launch_find_extend_ragged_lean_mixed(ix->view, nodes, offsets, base, perm, n, out, grid_for(ix, n), s);
+    else if (wants_lean_find(ix))
         k_find_extend_ragged<true><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);
     else
         k_find_extend_ragged<false><<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, perm, n, out);

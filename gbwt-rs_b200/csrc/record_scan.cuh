@@ -275,8 +275,8 @@ GBWT_UNROLL
 // Not inlined on the device: the scan loops would otherwise set the register budget (and the occupancy) of
 // the kernels whose common case is the register-light dense / single-edge step.
 template <bool BD>
-GBWT_HD_NOINLINE void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
-                       uint32_t end, Ranks& r) {
+GBWT_HD void rank_runs_inline(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+                              uint32_t end, Ranks& r) {
     const Unit16* body = ix.bodies + d.body();
     const uint32_t n = d.body_len();
     const uint32_t fmt = d.fmt();
@@ -316,6 +316,12 @@ GBWT_UNROLL
             if (base + 1 < n) add_run<BD>(q.z, q.w, symbol, fs, start, end, off, r);
         }
     }
+}
+
+template <bool BD>
+GBWT_HD_NOINLINE void rank_runs(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+                                uint32_t end, Ranks& r) {
+    rank_runs_inline<BD>(ix, d, symbol, fs, start, end, r);
 }
 
 // Symbol at position i (< total_len) of a run body: the first pass of Record::lf (src/bwt.rs:483-484).
@@ -373,7 +379,8 @@ GBWT_UNROLL
 // `start` <= `end`; both are clamped to the record length (ranks saturate there).
 // RUNS = false compiles the run-length formats out: the host picks that instantiation for indexes that hold
 // none (IndexView::run_records == 0), so the scan loops do not set the register budget of the dense path.
-template <bool BD, bool RUNS = true>
+// INLINE_SCAN: the run scan is inlined into the caller (for callers that are themselves out of line).
+template <bool BD, bool RUNS = true, bool INLINE_SCAN = false>
 GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
                         uint32_t end) {
     Ranks r;
@@ -395,7 +402,8 @@ GBWT_HD Ranks rank_pair(const IndexView& ix, const Desc& d, uint32_t symbol, con
             r.flipped = (fs.has(0) ? zeros : 0) + (fs.has(1) ? ones : 0);
         }
     } else if (RUNS) {
-        rank_runs<BD>(ix, d, symbol, fs, start, end, r);
+        if (INLINE_SCAN) rank_runs_inline<BD>(ix, d, symbol, fs, start, end, r);
+        else rank_runs<BD>(ix, d, symbol, fs, start, end, r);
     }
     return r;
 }
@@ -746,13 +754,13 @@ GBWT_HD bool follow_single(const Desc& d, uint32_t next, uint32_t& start, uint32
 }
 
 // Step on a record with a body.
-template <bool RUNS>
+template <bool RUNS, bool INLINE_SCAN = false>
 GBWT_HD bool follow_body(const IndexView& ix, const Desc& d, uint32_t next, uint32_t& start, uint32_t& end) {
     uint32_t rank = 0, edge_offset = 0;
     FlipSet fs;
     fs.lt = 0; fs.extra = NO_SYMBOL;
     if (!find_edge<false>(ix, d, next, rank, edge_offset, fs)) return false;
-    const Ranks r = rank_pair<false, RUNS>(ix, d, rank, fs, start, end);
+    const Ranks r = rank_pair<false, RUNS, INLINE_SCAN>(ix, d, rank, fs, start, end);
     if (r.at_start >= r.at_end) return false;
     start = edge_offset + r.at_start; end = edge_offset + r.at_end;
     return true;

@@ -485,3 +485,34 @@ def test_extraction_of_many_short_sequences(b200, monkeypatch):
         monkeypatch.delenv("GBWT_B200_EXTRACT_STRIDE")
         w_off, w_nodes = g.extract_batch(ids[:5000])
         assert np.array_equal(offsets, w_off) and np.array_equal(nodes, w_nodes)
+
+
+@pytest.mark.parametrize("force", ["3", "2"])
+def test_forced_find_kernels_on_mixed_indexes(b200, force, monkeypatch):
+    # GBWT_B200_FIND_LEAN=3 forces the lean loop with its out-of-line step for run-length / high-outdegree records
+    # (find_mixed.cu), 2 the general kernel: both must agree with the oracle on indexes full of such records.
+    monkeypatch.setenv("GBWT_B200_FIND_LEAN", force)
+    from test_hostsim_layout import random_paths, wide_record_index, records_image
+    for name in FIXTURES:
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw)
+        pc.check_find_all_nodes(e, g)
+        pc.check_find_extend_random(e, g, n=3000, k=4, seed=11)
+    for seed in range(4):
+        rng = random.Random(300 + seed)
+        paths = random_paths(rng, n_nodes=rng.choice([3, 6, 12]), n_paths=rng.choice([10, 40]), max_len=rng.choice([8, 20]))
+        img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths + [[2, 4]])))
+        for layout in ("auto", "runs"):
+            g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, layout=layout)
+            pc.check_find_extend_random(e, g, n=4000, k=5, seed=seed)
+            seqs = [p for p in pc.all_sequences(g) if len(p) >= 3]
+            pats = np.array([p[j:j + 3] for p in seqs for j in range(len(p) - 2)], dtype=np.uint64)
+            if len(pats):
+                assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
+    for sigma, bits in [(3, (1, 4, 10)), (64, (1, 5)), (255, (1, 9)), (300, (1, 12))]:
+        rng = random.Random(sigma)
+        edges, runs, total = wide_record_index(sigma, rng, bits)
+        img, _ = records_image(edges, runs, sequences=total, size=3 * total, offset=0)
+        g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+        pats = np.array([[1, 2 + v] for v in range(sigma)] + [[1, 1], [1, 0], [1, sigma + 5]], dtype=np.uint64)
+        assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
