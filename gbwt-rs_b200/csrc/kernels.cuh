@@ -598,13 +598,28 @@ __device__ __forceinline__ uint64_t walk_sequence_lane(const IndexView& ix, uint
 // otherwise repeat lane 0's work: once per 32 steps the warp hands its 32 parked nodes to the sink and issues ONE
 // warp-wide round of prefetches for the records it is heading to (one address per lane).
 
-// A step on any other format, by value so that the caller's descriptor never has its address taken (which would
-// put it on the stack). Returns (offset << 32) | node, 0 = GBWT::forward is None.
-__device__ __forceinline__ uint64_t forward_slow(const IndexView& ix, uint32_t node, uint32_t offset) {
-    gbwt_b200_pos cur, next;
-    cur.node = node; cur.offset = offset;
-    if (!gbwt_forward(ix, cur, next)) return 0;
-    return (static_cast<uint64_t>(next.offset) << 32) | static_cast<uint32_t>(next.node);
+// Record::lf on a run-length body that the warp does not scan cooperatively (RUN32 / RUN64: rare), out of line so
+// that it does not weigh on the registers of the walk. The descriptor travels as scalars and the two arrays by
+// value: nothing of the caller has its address taken. (No 256-bit inline-asm load in here: inside a non-inlined
+// device function that crashes ptxas 12.9.) Returns (offset << 32) | node, 0 = GBWT::forward is None.
+__device__ __noinline__ uint64_t forward_other_record(const Unit16* bodies, const Edge* edges, uint32_t d0, uint32_t d1, uint32_t d2,
+                                                      uint32_t d3, uint32_t d4, uint32_t d5, uint32_t d6, uint32_t d7, uint32_t i) {
+    Desc d;
+    d.a.x = d0; d.a.y = d1; d.a.z = d2; d.a.w = d3; d.b.x = d4; d.b.y = d5; d.b.z = d6; d.b.w = d7;
+    IndexView view;  // the run scan only looks at the bodies and the edge lists
+    view.desc = nullptr; view.bodies = bodies; view.edges = edges; view.endmarker = nullptr;
+    view.records = 0; view.offset = 0; view.alphabet_size = 0; view.sequences = 0; view.endmarker_len = 0;
+    view.bidirectional = 0; view.skips = nullptr; view.edges_valid = 1;
+    const uint32_t symbol = symbol_at_runs(view, d, i);
+    if (symbol == NO_SYMBOL) return 0;
+    FlipSet fs;
+    fs.lt = 0; fs.extra = NO_SYMBOL;
+    Ranks r;
+    r.at_start = r.at_end = r.flipped = 0;
+    rank_runs_inline<false>(view, d, symbol, fs, i, i, r);
+    const Edge e = edge_at(view, d, symbol);
+    if (e.node == 0) return 0;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+    return (static_cast<uint64_t>(e.offset + r.at_start) << 32) | e.node;
 }
 
 // Record index of node v for a load that must be safe but whose result is only used when v has a record: edge
@@ -744,7 +759,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
                 const Edge e = edge_at(ix, d, symbol);
                 next_node = e.node; next_offset = e.offset + rank_i;
             } else {
-                const uint64_t next = forward_slow(ix, node, offset);
+                const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, i);
                 next_node = static_cast<uint32_t>(next); next_offset = static_cast<uint32_t>(next >> 32);
             }
             if (next_node == 0) break;
@@ -775,7 +790,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
                 warp_lf_runs8(ix, d, i, b, r);
                 if (b == NO_SYMBOL) break;
             } else {
-                const uint64_t next = forward_slow(ix, node, offset);
+                const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, i);
                 if (next == 0) break;
                 b = static_cast<uint32_t>(next) == d.node1() && d.node1() != d.node0() ? 1u : 0u;
                 r = static_cast<uint32_t>(next >> 32) - (b ? d.offset1() : d.offset0());
