@@ -71,3 +71,41 @@ def test_shard_range_partitions():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_sass_of_the_hot_kernels():
+    """The properties DESIGN.md claims for the hot kernels, read from the SASS of the built library: sector-sized
+    256-bit loads in the search and walk kernels, warp shuffles + L2 prefetches in the walks, and no local-memory
+    stack frame in the walk kernels (the descriptor must live in registers)."""
+    import re
+    import shutil
+    import subprocess
+    import gbwt_rs_b200 as gb
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", gb.LIBRARY], capture_output=True, text=True).stdout
+    kernels = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name is not None:
+            kernels[name].append(line)
+
+    def body(fragment):
+        hits = [k for k in kernels if fragment in k]
+        assert hits, f"no kernel matching {fragment}"
+        return "\n".join(kernels[hits[0]])
+
+    for fragment in ("k_find_extend_leanILi5", "k_find_extend_lean_mixed", "13k_find_extendILb0", "k_extract_splitILb0", "k_extract_dna_relayILb0"):
+        assert "LDG.E.ENL2.256" in body(fragment), f"{fragment}: no 256-bit sector loads"
+    for fragment in ("k_extractILb0", "k_extract_splitILb0", "k_extract_dna_relayILb0"):
+        text = body(fragment)
+        assert "SHFL" in text and "CCTL.E.PF2" in text, f"{fragment}: warp shuffles / L2 prefetches missing"
+    log = open(os.path.join(os.path.dirname(gb.LIBRARY), "build_ptxas.log")).read()
+    for fragment in ("k_extractILb0", "k_extract_splitILb0"):
+        m = re.search(r"Function properties for \S*" + fragment + r"\S*\n\s*(\d+) bytes stack frame", log)
+        assert m and int(m.group(1)) == 0, f"{fragment}: stack frame in the walk kernel"
