@@ -638,6 +638,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     v.bidirectional = (parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
     v.skips = static_cast<const Unit16*>(ix->d_skips);
     v.edges_valid = layout.edges_valid ? 1 : 0;
+    v.walk_limit = layout.total_length;
     if (parsed.has_graph) {
         rc = attach_graph(ix, parsed.label_starts.data(), parsed.label_starts.size() - 1, parsed.label_bytes.data());
         if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
@@ -652,12 +653,22 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
 
 extern "C" {
 
+// No exception crosses the C ABI: the sizes declared in a damaged image can make an allocation fail.
+#define GBWT_B200_GUARDED(body)                                                                        \
+    try { body } catch (const std::bad_alloc&) {                                                       \
+        return fail(GBWT_B200_E_INVALID_DATA, "invalid data (an allocation of the declared size failed)"); \
+    } catch (const std::exception& e) {                                                                \
+        return fail(GBWT_B200_E_INVALID_DATA, std::string("invalid data (") + e.what() + ")");        \
+    }
+
 int gbwt_b200_index_from_bytes(const void* bytes, size_t len, int device, int layout_policy, gbwt_b200_index** out) {
-    ParsedGBWT parsed;
-    std::string err;
-    int rc = parse_gbwt_image(static_cast<const uint8_t*>(bytes), len, parsed, err);
-    if (rc != GBWT_B200_OK) return fail(rc, err);
-    return create_index(parsed, device, layout_policy, out);
+    GBWT_B200_GUARDED(
+        ParsedGBWT parsed;
+        std::string err;
+        int rc = parse_gbwt_image(static_cast<const uint8_t*>(bytes), len, parsed, err);
+        if (rc != GBWT_B200_OK) return fail(rc, err);
+        return create_index(parsed, device, layout_policy, out);
+    )
 }
 
 int gbwt_b200_index_load_file(const char* path, int device, int layout_policy, gbwt_b200_index** out) {
@@ -666,25 +677,29 @@ int gbwt_b200_index_load_file(const char* path, int device, int layout_policy, g
     if (!f) return fail(GBWT_B200_E_IO, std::string("cannot open ") + path);
     std::streamsize n = f.tellg();
     f.seekg(0);
-    std::vector<uint8_t> buf(static_cast<size_t>(n));
-    if (n > 0 && !f.read(reinterpret_cast<char*>(buf.data()), n)) return fail(GBWT_B200_E_IO, std::string("cannot read ") + path);
-    return gbwt_b200_index_from_bytes(buf.data(), buf.size(), device, layout_policy, out);
+    GBWT_B200_GUARDED(
+        std::vector<uint8_t> buf(static_cast<size_t>(n));
+        if (n > 0 && !f.read(reinterpret_cast<char*>(buf.data()), n)) return fail(GBWT_B200_E_IO, std::string("cannot read ") + path);
+        return gbwt_b200_index_from_bytes(buf.data(), buf.size(), device, layout_policy, out);
+    )
 }
 
 int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, uint64_t offset, uint64_t alphabet_size, uint64_t flags,
                                const uint8_t* bwt_bytes, uint64_t bwt_len, const uint64_t* record_starts, uint64_t records,
                                int device, int layout_policy, gbwt_b200_index** out) {
     if ((bwt_len > 0 && bwt_bytes == nullptr) || (records > 0 && record_starts == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null input");
-    ParsedGBWT parsed;
-    parsed.sequences = sequences; parsed.size = size; parsed.offset = offset; parsed.alphabet_size = alphabet_size;
-    parsed.flags = flags | GBWT_FLAG_SIMPLE_SDS;
-    parsed.bwt = bwt_bytes; parsed.bwt_len = bwt_len;
-    parsed.record_starts.assign(record_starts, record_starts + records);
-    for (uint64_t i = 0; i < records; i++) {
-        if (record_starts[i] >= bwt_len || (i > 0 && record_starts[i] <= record_starts[i - 1]))
-            return fail(GBWT_B200_E_INVALID_DATA, "BWT: invalid index");
-    }
-    return create_index(parsed, device, layout_policy, out);
+    GBWT_B200_GUARDED(
+        ParsedGBWT parsed;
+        parsed.sequences = sequences; parsed.size = size; parsed.offset = offset; parsed.alphabet_size = alphabet_size;
+        parsed.flags = flags | GBWT_FLAG_SIMPLE_SDS;
+        parsed.bwt = bwt_bytes; parsed.bwt_len = bwt_len;
+        parsed.record_starts.assign(record_starts, record_starts + records);
+        for (uint64_t i = 0; i < records; i++) {
+            if (record_starts[i] >= bwt_len || (i > 0 && record_starts[i] <= record_starts[i - 1]))
+                return fail(GBWT_B200_E_INVALID_DATA, "BWT: invalid index");
+        }
+        return create_index(parsed, device, layout_policy, out);
+    )
 }
 
 int gbwt_b200_index_serialize(const gbwt_b200_index* ix, void** image, size_t* len) {

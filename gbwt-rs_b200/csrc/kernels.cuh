@@ -559,7 +559,7 @@ __device__ __forceinline__ uint64_t walk_sequence_lane(const IndexView& ix, uint
         if (n < cap) out[n] = node;
         n++;
         const uint32_t fmt = d.fmt();
-        if (fmt == FMT_EMPTY || offset >= d.total_len()) break;  // GBWT::forward -> None
+        if (fmt == FMT_EMPTY || offset >= d.total_len() || n > ix.walk_limit) break;  // GBWT::forward -> None
         const uint32_t i = static_cast<uint32_t>(offset);
         if (fmt == FMT_SINGLE) {
             if (d.node0() == 0) break;
@@ -709,7 +709,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
             sink.group(static_cast<uint64_t>(mine), in_group, flushed);
             flushed += in_group;
             in_group = 0;
-            if (flushed >= limit) break;
+            if (flushed >= limit || flushed > ix.walk_limit) break;  // (walk_limit: a damaged index with a cycle)
             if (ahead != 0) {
                 // Sequences that walk the graph together arrive at a record together and would all wait for the same
                 // HBM miss. Node ids follow the graph's topological order, so the records the walk needs next lie a

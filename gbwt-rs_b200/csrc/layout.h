@@ -86,6 +86,10 @@ struct IndexView {
     // so LF(LF(u, i)) = (n_b, o_b + rank_b(i)) without touching v_b's record; n_b = 0 where that does not apply.
     const Unit16* skips;
     uint32_t edges_valid;     // every edge of every record leads to the endmarker or to a node with a record
+    // Sum of Record::len() over all records: no sequence of a consistent index visits more nodes than that. Walks
+    // stop there, so that a damaged index with a cycle cannot keep a kernel running for ever (the reference's
+    // iterator would not terminate on such an index).
+    uint64_t walk_limit;
 };
 
 // Magic multiplier for q = b / sigma, 0 <= b < 256, 1 <= sigma <= 256: q = (b * magic) >> 16.

@@ -104,7 +104,8 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
     } else {
         best = ceil_div(pl.runs * 8, 16); pl.fmt = FMT_RUN64;
     }
-    if (pl.sigma == 2 && policy == GBWT_B200_LAYOUT_AUTO) {
+    // (a damaged file can hold a record with edges but no runs: it must not become a dense body of zero blocks)
+    if (pl.sigma == 2 && policy == GBWT_B200_LAYOUT_AUTO && pl.total > 0) {
         // A dense record answers rank with one 32-byte block however long it is, so it is preferred
         // unless it would more than double the footprint of a body that already spans several sectors.
         uint64_t dense = 2 * ceil_div(pl.total, DENSE_BITS);
@@ -260,6 +261,7 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
         body_at[i + 1] = body_at[i] + plans[i].units;
         edge_at[i + 1] = edge_at[i] + (plans[i].sigma > 2 ? plans[i].sigma : 0);
         out.format_counts[plans[i].fmt]++;
+        out.total_length += plans[i].total;
     }
     if (body_at[R] > 0xFFFFFFFFull || edge_at[R] > 0xFFFFFFFFull) {
         err = "index does not fit the 32-bit device layout"; return GBWT_B200_E_RANGE;

@@ -17,6 +17,7 @@ struct HostLayout {
     std::vector<Edge> endmarker;   // Record::decompress() of record 0 (src/gbwt.rs:413-414)
     std::vector<uint64_t> skips;   // two words per record (IndexView::skips)
     bool edges_valid = true;
+    uint64_t total_length = 0;    // sum of the record lengths (IndexView::walk_limit)
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 

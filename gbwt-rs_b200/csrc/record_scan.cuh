@@ -907,7 +907,7 @@ GBWT_HD uint64_t walk_sequence(const IndexView& ix, uint64_t id, uint64_t* out, 
     uint64_t n = 0;
     gbwt_b200_pos pos;
     bool some = gbwt_start(ix, id, pos);
-    while (some) {
+    while (some && n <= ix.walk_limit) {  // (the limit only ever matters for a damaged index with a cycle)
         if (n < cap) out[n] = pos.node;
         n++;
         gbwt_b200_pos next;

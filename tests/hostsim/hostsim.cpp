@@ -26,8 +26,14 @@ extern "C" {
 HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t errlen) {
     HostSim* h = new HostSim();
     std::string msg;
-    int rc = parse_gbwt_image(bytes, len, h->parsed, msg);
-    if (rc == GBWT_B200_OK) rc = build_layout(h->parsed, policy, h->layout, msg);
+    int rc;
+    try {
+        rc = parse_gbwt_image(bytes, len, h->parsed, msg);
+        if (rc == GBWT_B200_OK) rc = build_layout(h->parsed, policy, h->layout, msg);
+    } catch (const std::exception& e) {  // like the C ABI: sizes in a damaged image can be absurd
+        rc = GBWT_B200_E_INVALID_DATA;
+        msg = std::string("invalid data (") + e.what() + ")";
+    }
     if (rc != GBWT_B200_OK) {
         if (err && errlen) std::snprintf(err, errlen, "%d: %s", rc, msg.c_str());
         delete h;
@@ -46,6 +52,7 @@ HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t
     v.bidirectional = (h->parsed.flags & GBWT_FLAG_BIDIRECTIONAL) != 0;
     v.skips = reinterpret_cast<const Unit16*>(h->layout.skips.data());
     v.edges_valid = h->layout.edges_valid ? 1 : 0;
+    v.walk_limit = h->layout.total_length;
     h->parsed.bwt = nullptr;  // the image may go away
     return h;
 }

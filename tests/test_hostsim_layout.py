@@ -244,3 +244,31 @@ def test_invalid_edge_targets_are_flagged():
     img, _ = records_image([[(0, 0), (40, 0)], [(0, 0)], [(0, 0)]], [[(0, 1), (1, 1)], [(0, 1)], [(0, 1)]], sequences=2, size=4, offset=0)
     e = HostSim(img)
     assert not e.edges_valid() and not e.skips().any()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_records_with_edges_but_no_runs(layout):
+    # Only a damaged file has them (found by fuzzing the loader): Record::len() is 0, every query on them is None, and
+    # nothing may read a body that does not exist.
+    edges = [[(1, 0)], [(2, 0), (3, 0)], [(1, 0), (3, 0)], [(0, 0)]]
+    runs = [[(0, 3)], [(0, 2), (1, 1)], [], [(0, 1)]]
+    img, _ = records_image(edges, runs, sequences=3, size=8, offset=0, bidirectional=True)
+    g, e = orc.GBWT.load(img), HostSim(img, layout)
+    assert g.record_len(2) == 0 and e.record_format(2) not in (2,)   # never a dense body of zero blocks
+    states = np.array([(2, 0, 2), (2, 0, 0), (2, 1, 5)], dtype=orc.STATE_DTYPE)
+    for node in (1, 3, 0, 7):
+        nodes = np.full(len(states), node, dtype=np.uint64)
+        assert pc.states_equal(e.extend(states, nodes), g.extend_batch(states, nodes))
+    bd = np.zeros(2, dtype=e.bd_find(np.array([1], dtype=np.uint64)).dtype)
+    bd["forward"]["node"] = 3; bd["forward"]["end"] = 2; bd["reverse"]["node"] = 2; bd["reverse"]["end"] = 2
+    for backward in (False, True):
+        offsets, want, counts = g.follow_batch(bd, backward=backward)
+        got_offsets, got, got_counts = e.follow(bd, backward)
+        assert np.array_equal(got_counts, counts) and np.array_equal(got_offsets, offsets) and pc.states_equal(got, want)
+    # find() on the record without runs: the reference returns Some(empty range), which the ABI folds into None
+    nodes = np.arange(g.alphabet_size() + 2, dtype=np.uint64)
+    want = g.find_batch(nodes).copy()
+    want[want["end"] <= want["start"]] = (0, 0, 0)
+    assert pc.states_equal(e.find(nodes), want)
+    pos = np.array([(2, 0), (2, 1), (1, 0), (1, 2)], dtype=orc.POS_DTYPE)
+    assert pc.states_equal(e.forward(pos), g.forward_batch(pos))
