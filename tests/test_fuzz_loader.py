@@ -16,3 +16,12 @@ def test_damaged_images_are_rejected_or_harmless(seed):
     assert proc.returncode == 0, proc.stderr[-2000:]
     loaded, rejected = (int(x) for x in proc.stdout.split()[1::2])
     assert loaded + rejected == 300 and rejected > 50 and loaded > 20
+
+
+@pytest.mark.gpu
+def test_damaged_images_on_the_gpu():
+    # the same through the C ABI on cuda:0: every kernel family on whatever still loads (tests/fuzz_gpu.py)
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "fuzz_gpu.py"), "3", "200"], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    loaded, rejected = (int(x) for x in proc.stdout.split()[1::2])
+    assert loaded + rejected == 200 and loaded > 20
