@@ -2,8 +2,9 @@
  * gbwt_b200.h -- C ABI of the B200-native GBWT search / LF engine (libgbwt_b200.so).
  *
  * The reference (gbwt-rs, crate `gbz` 0.5.1) exposes no FFI; its boundary for this path is the
- * public Rust API of `GBWT` (src/gbwt.rs). Every entry point below is the batched form of one of
- * those methods and cites the method it replaces. A scalar crate call is a batch of one.
+ * public Rust API of `GBWT` (src/gbwt.rs), plus, for the rows next to the path, `GBZ::follow_*` and
+ * `GBZ::sequence` (src/gbz.rs) and `extract_sequence` (src/bin/gbz-extract.rs). Every entry point below is
+ * the batched form of one of those functions and cites the one it replaces. A scalar crate call is a batch of one.
  *
  * Conventions
  *  - All integers are 64-bit like the crate's `usize`; nothing is truncated at the boundary. The device
@@ -19,9 +20,12 @@
  *    asynchronously and overlapped with the kernels). `_device` entry points take device pointers valid
  *    on the index's device and a CUDA stream handle (cudaStream_t passed as void*, NULL = default
  *    stream); they only enqueue work.
- *  - An index handle is immutable after creation and may be used from many host threads at once, like
- *    the `Sync` reference type (src/gbwt.rs:95-102). There is no CPU fallback: every query entry point
- *    runs CUDA kernels on the device chosen at creation.
+ *  - An index handle is immutable after creation (gbwt_b200_index_attach_graph excepted) and may be used from
+ *    many host threads at once, like the `Sync` reference type (src/gbwt.rs:95-102). The only thing queries
+ *    leave behind is the length of the sequences they have walked, kept in device memory so that later
+ *    extractions can walk them from both ends. There is no CPU fallback: every query entry point runs CUDA
+ *    kernels on the device chosen at creation.
+ *  - Damaged input is rejected with GBWT_B200_E_INVALID_DATA; no C++ exception crosses this boundary.
  */
 #ifndef GBWT_B200_H
 #define GBWT_B200_H
