@@ -29,7 +29,14 @@ BDSTATE_DTYPE = np.dtype([("forward", STATE_DTYPE), ("reverse", STATE_DTYPE)])
 POS_DTYPE = np.dtype([("node", "<u8"), ("offset", "<u8")])
 
 LAYOUT_AUTO, LAYOUT_RUNS = 0, 1
+LAYOUT_CHECKPOINTS, LAYOUT_NO_CHECKPOINTS = 0x100, 0x200
 _LAYOUTS = {"auto": LAYOUT_AUTO, "runs": LAYOUT_RUNS, 0: LAYOUT_AUTO, 1: LAYOUT_RUNS}
+
+
+def _policy(layout, checkpoints) -> int:
+    """Layout policy word of the C ABI: body layout + the checkpoint flag (None = the library's default by size)."""
+    flag = 0 if checkpoints is None else (LAYOUT_CHECKPOINTS if checkpoints else LAYOUT_NO_CHECKPOINTS)
+    return _LAYOUTS[layout] | flag
 
 OK, E_INVALID_DATA, E_IO, E_RANGE, E_NOT_BIDIRECTIONAL, E_CUDA, E_ARGUMENT, E_NO_DEVICE = range(8)
 _U64MAX = np.uint64(2**64 - 1)
@@ -64,9 +71,12 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_alphabet_offset": (u64, [p]), "gbwt_b200_effective_size": (u64, [p]), "gbwt_b200_first_node": (u64, [p]),
         "gbwt_b200_has_node": (i, [p, u64]), "gbwt_b200_is_bidirectional": (i, [p]), "gbwt_b200_device": (i, [p]),
         "gbwt_b200_device_bytes": (u64, [p, p]),
+        "gbwt_b200_window_info": (None, [p, p]),
+        "gbwt_b200_checkpoint_info": (None, [p, p]),
         "gbwt_b200_find": (i, [p, p, sz, p]),
         "gbwt_b200_extend": (i, [p, p, p, sz, p]),
         "gbwt_b200_find_extend": (i, [p, p, sz, sz, p]),
+        "gbwt_b200_find_extend_u32": (i, [p, p, sz, sz, p]),
         "gbwt_b200_find_extend_ragged": (i, [p, p, p, sz, p]),
         "gbwt_b200_bd_find": (i, [p, p, sz, p]),
         "gbwt_b200_extend_forward": (i, [p, p, p, sz, p]),
@@ -80,6 +90,7 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_sequence_lengths": (i, [p, p, sz, p]),
         "gbwt_b200_extract": (i, [p, p, sz, p, p, p]),
         "gbwt_b200_find_extend_device": (i, [p, p, sz, sz, p, p]),
+        "gbwt_b200_find_extend_u32_device": (i, [p, p, sz, sz, p, p]),
         "gbwt_b200_find_extend_ragged_device": (i, [p, p, p, sz, p, p]),
         "gbwt_b200_find_device": (i, [p, p, sz, p, p]),
         "gbwt_b200_extend_device": (i, [p, p, p, sz, p, p]),
@@ -221,17 +232,17 @@ class GBWT:
             raise GBWTError(rc, msg)
 
     @classmethod
-    def load(cls, path, device: int = 0, layout="auto") -> "GBWT":
+    def load(cls, path, device: int = 0, layout="auto", checkpoints=None) -> "GBWT":
         h = C.c_void_p()
-        cls._check(_lib.gbwt_b200_index_load_file(os.fsencode(path), device, _LAYOUTS[layout], C.byref(h)))
+        cls._check(_lib.gbwt_b200_index_load_file(os.fsencode(path), device, _policy(layout, checkpoints), C.byref(h)))
         return cls(h.value)
 
     @classmethod
-    def from_bytes(cls, image, device: int = 0, layout="auto") -> "GBWT":
+    def from_bytes(cls, image, device: int = 0, layout="auto", checkpoints=None) -> "GBWT":
         arr = image if isinstance(image, np.ndarray) else np.frombuffer(image, dtype=np.uint8)
         arr = np.ascontiguousarray(arr)
         h = C.c_void_p()
-        cls._check(_lib.gbwt_b200_index_from_bytes(_ptr(arr), arr.nbytes, device, _LAYOUTS[layout], C.byref(h)))
+        cls._check(_lib.gbwt_b200_index_from_bytes(_ptr(arr), arr.nbytes, device, _policy(layout, checkpoints), C.byref(h)))
         return cls(h.value)
 
     @classmethod
@@ -329,6 +340,16 @@ class GBWT:
         n, k = patterns.shape
         out = np.zeros(n, STATE_DTYPE)
         self._check(_lib.gbwt_b200_find_extend(self._h, _ptr(patterns), n, k, _ptr(out)))
+        return out
+
+    def find_extend_u32(self, patterns) -> np.ndarray:
+        """find_extend for patterns held as 32-bit node identifiers (same results, half the bytes over PCIe)."""
+        patterns = np.ascontiguousarray(patterns, dtype=np.uint32)
+        if patterns.ndim == 1:
+            patterns = patterns.reshape(1, -1)
+        n, k = patterns.shape
+        out = np.zeros(n, STATE_DTYPE)
+        self._check(_lib.gbwt_b200_find_extend_u32(self._h, _ptr(patterns), n, k, _ptr(out)))
         return out
 
     def find_extend_ragged(self, nodes, offsets) -> np.ndarray:
@@ -512,9 +533,26 @@ class GBWT:
     def extract_dna_device(self, d_ids: int, m: int, endmarker: int, d_out_offsets: int, d_bytes: int, d_lengths: int, stream: int = 0):
         self._check(_lib.gbwt_b200_extract_dna_device(self._h, d_ids, m, endmarker, d_out_offsets, d_bytes, d_lengths, stream))
 
+    def checkpoint_info(self) -> dict:
+        raw = np.zeros(6, dtype=np.uint64)
+        _lib.gbwt_b200_checkpoint_info(self._h, _ptr(raw))
+        keys = ("present", "interval", "entries", "bytes", "build_us", "max_segments")
+        return {k: int(v) for k, v in zip(keys, raw)}
+
+    def window_info(self) -> dict:
+        """Plan and counters of the record-window search kernel (gbwt_b200_window_info)."""
+        raw = np.zeros(12, dtype=np.uint64)
+        _lib.gbwt_b200_window_info(self._h, _ptr(raw))
+        keys = ("can_run", "default", "window_records", "margin", "body_units", "threads", "smem_bytes", "windows",
+                "edges", "edges_local", "queries", "deferred")
+        return {k: int(v) for k, v in zip(keys, raw)}
+
     # -- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr(); stream = cudaStream_t) --
     def find_extend_device(self, d_patterns: int, n: int, k: int, d_out: int, stream: int = 0):
         self._check(_lib.gbwt_b200_find_extend_device(self._h, d_patterns, n, k, d_out, stream))
+
+    def find_extend_u32_device(self, d_patterns: int, n: int, k: int, d_out: int, stream: int = 0):
+        self._check(_lib.gbwt_b200_find_extend_u32_device(self._h, d_patterns, n, k, d_out, stream))
 
     def bd_search_device(self, d_nodes, d_offsets, d_first, d_start, d_end, n, d_out, stream: int = 0):
         self._check(_lib.gbwt_b200_bd_search_device(self._h, d_nodes, d_offsets, d_first, d_start, d_end, n, d_out, stream))

@@ -16,6 +16,7 @@
 
 #include "../../include/gbwt_b200.h"
 #include "find_mixed.h"
+#include "find_window.h"
 #include "kernels.cuh"
 #include "layout_builder.h"
 #include "layout_writer.h"
@@ -34,6 +35,20 @@ struct gbwt_b200_index {
     void* d_endmarker = nullptr;
     void* d_skips = nullptr;
     uint64_t skip_bytes = 0;
+    void* d_stage_body = nullptr;   // IndexView::stage_body (window kernels)
+    uint64_t edges_total = 0, edges_local = 0;
+    bool window_ok = false;         // the record-window search kernel can run on this index (validated edges, a plan)
+    bool window_suits = false;      // ... and is expected to pay: mostly single-edge / dense records, mostly local edges
+    WindowPlan window{};
+    // GBWT_B200_WINDOW_STATS=1 (tests, tools): queries that went through the window kernel and how many it deferred
+    mutable std::atomic<uint64_t> window_queries{0}, window_deferred{0};
+    // Path checkpoints (kernels.cuh, k_build_checkpoints): built once when the index is created, immutable afterwards.
+    void* d_ckpt_table = nullptr;
+    void* d_ckpt_first = nullptr;
+    CheckpointView ckpt{};
+    bool ckpt_ok = false;
+    uint32_t ckpt_shift = 0;
+    uint64_t ckpt_entries = 0, ckpt_bytes = 0, ckpt_build_us = 0;
     void* d_seq_len = nullptr;  // length of every sequence once some walk has measured it (SEQ_LEN_UNKNOWN before)
     void* d_dna_len = nullptr;  // the same for the DNA of every sequence (valid for the attached graph)
     void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
@@ -141,12 +156,16 @@ bool wants_locality(const gbwt_b200_index* ix, size_t n) {
 // About 256 queries per bucket and at most 2^18 buckets (GBWT_B200_BUCKETS overrides): measured on config 4,
 // a full sort (one bucket per record) makes the search kernel 11% faster but the sort itself twice as
 // expensive (20 M counters and fully scattered slot writes), a net loss.
+// `fixed_shift` >= 0: buckets of exactly 2^fixed_shift records (the record windows of find_window.cu). `bucket_end`, when
+// asked for, receives the array whose entry b is the end of bucket b's slots in perm (the caller frees it).
 template <class WriteKeys>
-int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, WriteKeys write_keys, uint32_t** perm) {
+int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, WriteKeys write_keys, uint32_t** perm,
+                        int fixed_shift = -1, uint32_t** bucket_end = nullptr, uint32_t** keys_out = nullptr) {
     const uint64_t max_buckets = static_cast<uint64_t>(std::max(1, env_int("GBWT_B200_BUCKETS", 1 << 18)));
     const uint64_t want_buckets = std::min<uint64_t>(max_buckets, std::max<uint64_t>(256, n / 256));
     uint32_t shift = 0;
-    while (bucket_count(ix->view.records, shift) > want_buckets) shift++;
+    if (fixed_shift >= 0) shift = static_cast<uint32_t>(fixed_shift);
+    else while (bucket_count(ix->view.records, shift) > want_buckets) shift++;
     const uint32_t buckets = static_cast<uint32_t>(bucket_count(ix->view.records, shift));
     const uint32_t m = buckets + 1, tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *tile_sums = nullptr, *keys = nullptr;
@@ -168,38 +187,101 @@ int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, Wri
     }
     k_bucket_scatter<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts, *perm);
     int rc = launch_done("k_bucket_scatter");
-    cudaFreeAsync(counts, s);
+    if (bucket_end != nullptr) *bucket_end = counts;  // after the scatter, counts[b] = end of bucket b
+    else cudaFreeAsync(counts, s);
     cudaFreeAsync(tile_sums, s);
-    cudaFreeAsync(keys, s);
+    if (keys_out != nullptr) *keys_out = keys;  // n words the caller may reuse (the keys are no longer needed)
+    else cudaFreeAsync(keys, s);
     return rc;
 }
 
-int launch_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, size_t n, size_t k, gbwt_b200_state* out,
-                       cudaStream_t s) {
+// keys[q] = bucket of query q for either pattern width (the 64-bit kernel of kernels.cuh, or find_window.cu's for 32 bits).
+void write_keys_fixed(const gbwt_b200_index* ix, const uint64_t* part, size_t count, size_t k, uint32_t shift, uint32_t* keys,
+                      uint32_t* counts, cudaStream_t s) {
+    k_keys_fixed<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, keys, counts);
+}
+void write_keys_fixed(const gbwt_b200_index* ix, const uint32_t* part, size_t count, size_t k, uint32_t shift, uint32_t* keys,
+                      uint32_t* counts, cudaStream_t s) {
+    WindowPlan plan{};
+    plan.wshift = shift;
+    launch_window_keys<uint32_t>(ix->view, plan, part, count, k, keys, counts, grid_for(ix, count), s);
+}
+
+// The search kernel for a batch without record windows (small batches, indexes the windows do not suit).
+void launch_find_extend_plain(const gbwt_b200_index* ix, const uint64_t* part, const uint32_t* perm, size_t count, size_t k,
+                              gbwt_b200_state* out, cudaStream_t s) {
+    // development: GBWT_B200_FIND_LEAN = 0 general, 2 general with runs, 3 lean mixed (only with validated edges)
+    const int force = env_int("GBWT_B200_FIND_LEAN", 1);
+    if (force == 2) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out);
+    else if (force == 3 && ix->view.edges_valid) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out, grid_for(ix, count), s);
+    else if (wants_lean_find(ix)) {
+        // 5 resident CTAs per SM (48 registers): measured 3.06 G queries/s per step on config 4 against 2.85 with 4
+        // (53 registers, no spills), 2.69 with 6 and 1.66 with 8 (spills), 2.81 for the general loop
+        if (has_run_records(ix)) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out, grid_for(ix, count), s);
+        else k_find_extend_lean<5><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out);
+    }
+    else if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out);
+    else k_find_extend<false><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out);
+}
+void launch_find_extend_plain(const gbwt_b200_index* ix, const uint32_t* part, const uint32_t* perm, size_t count, size_t k,
+                              gbwt_b200_state* out, cudaStream_t s) {
+    launch_find_extend_u32(ix->view, has_run_records(ix), part, perm, count, k, out, grid_for(ix, count), s);
+}
+
+// Whether a sorted batch goes through the record windows of find_window.cu (GBWT_B200_FIND_WINDOW=0 disables them).
+// GBWT_B200_FIND_WINDOW=2 forces them onto any index they can run on (tests).
+bool wants_windows(const gbwt_b200_index* ix) {
+    const int knob = env_int("GBWT_B200_FIND_WINDOW", 1);
+    if (!ix->window_ok || knob == 0 || env_int("GBWT_B200_FIND_LEAN", 1) != 1) return false;
+    return knob == 2 || ix->window_suits;
+}
+
+// T = uint64_t (the crate's usize nodes) or uint32_t (callers that hold 32-bit node identifiers).
+template <class T>
+int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, size_t k, gbwt_b200_state* out, cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
     if (k > 0xFFFFFFFFull) return fail(GBWT_B200_E_ARGUMENT, "pattern length must be below 2^32");
     const size_t max_part = 0xFFFFFFFFull;  // the permutation is 32-bit
     for (size_t begin = 0; begin < n; begin += max_part) {
         const size_t count = std::min(max_part, n - begin);
-        const uint64_t* part = patterns + begin * k;
+        const T* part = patterns + begin * k;
+        const bool sorted = k >= 2 && wants_locality(ix, count);
+        if (sorted && wants_windows(ix)) {
+            // Record windows: one bucket of the sort = one window; the window kernel answers from shared memory and
+            // lists what it could not decide, the general kernel finishes the list.
+            uint32_t *perm = nullptr, *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
+            int rc = build_locality_perm(ix, count, s, [&](uint32_t, uint32_t* keys, uint32_t* counts) {
+                launch_window_keys<T>(ix->view, ix->window, part, count, k, keys, counts, grid_for(ix, count), s);
+            }, &perm, static_cast<int>(ix->window.wshift), &bucket_end, &scratch);
+            if (rc != GBWT_B200_OK) return rc;
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+            const int e = launch_find_window<T>(ix->view, ix->window, part, perm, bucket_end, count, k, out + begin, scratch, counters, ix->sm_count, s);
+            if (e != 0) rc = cuda_fail(static_cast<cudaError_t>(e), "k_find_window");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (rc == GBWT_B200_OK) {
+                launch_find_deferred<T>(ix->view, part, scratch, counters, k, out + begin, static_cast<unsigned>(ix->sm_count) * 4, s);
+                rc = launch_done("k_find_deferred");
+            }
+            if (rc == GBWT_B200_OK && env_int("GBWT_B200_WINDOW_STATS", 0) != 0) {
+                uint32_t host[2] = {0, 0};
+                if (cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
+                    ix->window_queries.fetch_add(count);
+                    ix->window_deferred.fetch_add(host[1]);
+                }
+            }
+            cudaFreeAsync(perm, s); cudaFreeAsync(bucket_end, s); cudaFreeAsync(scratch, s); cudaFreeAsync(counters, s);
+            if (rc != GBWT_B200_OK) return rc;
+            continue;
+        }
         uint32_t* perm = nullptr;
-        if (k >= 2 && wants_locality(ix, count)) {
+        if (sorted) {
             int rc = build_locality_perm(ix, count, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
-                k_keys_fixed<<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, count, k, shift, keys, counts);
+                write_keys_fixed(ix, part, count, k, shift, keys, counts, s);
             }, &perm);
             if (rc != GBWT_B200_OK) return rc;
         }
-        const int force = env_int("GBWT_B200_FIND_LEAN", 1);  // development: 0 general, 2 general with runs, 3 lean mixed
-        if (force == 2) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
-        else if (force == 3) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out + begin, grid_for(ix, count), s);
-        else if (wants_lean_find(ix)) {
-            // 5 resident CTAs per SM (48 registers): measured 3.06 G queries/s per step on config 4 against 2.85 with 4
-            // (53 registers, no spills), 2.69 with 6 and 1.66 with 8 (spills), 2.81 for the general loop
-            if (has_run_records(ix)) launch_find_extend_lean_mixed(ix->view, part, perm, count, k, out + begin, grid_for(ix, count), s);
-            else k_find_extend_lean<5><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
-        }
-        else if (has_run_records(ix)) k_find_extend<true><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
-        else k_find_extend<false><<<grid_for(ix, count), BLOCK_THREADS, 0, s>>>(ix->view, part, perm, count, k, out + begin);
+        launch_find_extend_plain(ix, part, perm, count, k, out + begin, s);
         int rc = launch_done("k_find_extend");
         if (perm != nullptr) cudaFreeAsync(perm, s);
         if (rc != GBWT_B200_OK) return rc;
@@ -279,6 +361,20 @@ int launch_backward(const gbwt_b200_index* ix, const gbwt_b200_pos* pos, size_t 
 int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
                    uint64_t* nodes, uint64_t* lengths, cudaStream_t s) {
     if (m == 0) return GBWT_B200_OK;
+    // With checkpoints every sequence is a set of independent segments (GBWT_B200_EXTRACT_CHECKPOINTS=0: the chain walks below).
+    if (ix->ckpt_ok && env_int("GBWT_B200_EXTRACT_CHECKPOINTS", 1) != 0 && std::getenv("GBWT_B200_EXTRACT_STRIDE") == nullptr) {
+        if (nodes == nullptr) {
+            if (lengths != nullptr) k_lengths_from_table<<<grid_for(ix, m), BLOCK_THREADS, 0, s>>>(ix->view.sequences, ix->ckpt.seq_len, ids, m, lengths);
+            return launch_done("k_lengths_from_table");
+        }
+        const uint64_t items = ((m + 31) / 32) * static_cast<uint64_t>(std::max<uint32_t>(1, ix->ckpt.max_segments));
+        const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((items + 7) / 8, static_cast<uint64_t>(ix->sm_count) * 8)));
+        CheckpointView cv = ix->ckpt;
+        cv.max_segments = std::max<uint32_t>(1, cv.max_segments);
+        if (ix->view.edges_valid) k_extract_checkpointed<false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
+        else k_extract_checkpointed<true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
+        return launch_done("k_extract_checkpointed");
+    }
     // Up to 64 Ki sequences: one warp each (GBWT_B200_EXTRACT_STRIDE overrides: threads per sequence, 32 = warp mode).
     uint32_t stride = static_cast<uint32_t>(env_int("GBWT_B200_EXTRACT_STRIDE", m <= (size_t(1) << 16) ? 32 : 1));
     if (stride != 1 && stride != 2 && stride != 4 && stride != 8 && stride != 16 && stride != 32) stride = 1;
@@ -509,7 +605,9 @@ int run_ragged_output(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, 
         alloc(reinterpret_cast<void**>(&d_ids), count * 8); alloc(reinterpret_cast<void**>(&d_offsets), (count + 1) * 8);
         alloc(&d_out, cap * elem_bytes); alloc(reinterpret_cast<void**>(&d_lengths), count * 8);
         if (rc == GBWT_B200_OK) {
-            cudaError_t e = cudaMemcpyAsync(d_ids, ids + i0, count * 8, cudaMemcpyHostToDevice, s);
+            // slots may be larger than the results: the slack must not carry stale pool memory back to the caller
+            cudaError_t e = cap > 0 ? cudaMemsetAsync(d_out, 0, cap * elem_bytes, s) : cudaSuccess;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, ids + i0, count * 8, cudaMemcpyHostToDevice, s);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_offsets, out_offsets + i0, (count + 1) * 8, cudaMemcpyHostToDevice, s);
             if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
         }
@@ -577,6 +675,100 @@ int check_graph(const gbwt_b200_index* ix) {
     return GBWT_B200_OK;
 }
 
+// In-place inclusive scan of counts[0 .. m) on stream s (the three launches of kernels.cuh).
+int scan_counts(uint32_t* counts, uint32_t m, cudaStream_t s) {
+    const uint32_t tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t* tile_sums = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&tile_sums), tiles * sizeof(uint32_t), s));
+    k_scan_tiles<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+    launch_done("k_scan_tiles");
+    if (tiles > 1) {
+        k_scan_single<<<1, 1024, 0, s>>>(tile_sums, tiles);
+        launch_done("k_scan_single");
+        k_scan_add<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
+        launch_done("k_scan_add");
+    }
+    cudaFreeAsync(tile_sums, s);
+    return GBWT_B200_OK;
+}
+
+// Path checkpoints: one warp-mode walk over every sequence records its length and its position at about every
+// 2^shift-th node; afterwards a sequence can be extracted as independent segments (k_extract_checkpointed). The
+// interval is chosen so that the table holds at most ~16 M entries (GBWT_B200_CHECKPOINT_SHIFT overrides).
+int build_checkpoints(gbwt_b200_index* ix) {
+    const IndexView& v = ix->view;
+    if (v.sequences == 0 || v.sequences >= 0xFFFFFFFFull) return GBWT_B200_OK;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    uint32_t shift = 6;
+    while (shift < 30 && (v.walk_limit >> shift) > (uint64_t(16) << 20)) shift++;
+    shift = static_cast<uint32_t>(std::min(30, std::max(6, env_int("GBWT_B200_CHECKPOINT_SHIFT", static_cast<int>(shift)))));
+    const uint64_t pool_cap = (v.walk_limit >> shift) + v.sequences + 1024;
+    PoolEntry* pool = nullptr;
+    unsigned long long* used_dev = nullptr;
+    uint32_t* first = nullptr;
+    cudaStream_t s = nullptr;
+    CUDA_TRY(cudaEventRecord(e0, s));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&pool), pool_cap * sizeof(PoolEntry)));
+    int rc = GBWT_B200_OK;
+    auto cleanup = [&]() { cudaFree(pool); cudaFree(used_dev); cudaEventDestroy(e0); cudaEventDestroy(e1); };
+    if (cudaMalloc(reinterpret_cast<void**>(&used_dev), sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(used_dev, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&first), (v.sequences + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(first, 0, (v.sequences + 1) * sizeof(uint32_t)) != cudaSuccess) {
+        rc = cuda_fail(cudaGetLastError(), "cudaMalloc(checkpoints)");
+        cleanup(); cudaFree(first);
+        return rc;
+    }
+    const int block = 128;
+    const unsigned ctas = static_cast<unsigned>(std::min<uint64_t>((v.sequences * 32 + block - 1) / block, uint64_t(1) << 20));
+    const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
+    uint64_t* seq_len = static_cast<uint64_t*>(ix->d_seq_len);
+    if (v.edges_valid) k_build_checkpoints<false><<<ctas, block, 0, s>>>(v, shift, pool, used_dev, pool_cap, seq_len, ahead);
+    else k_build_checkpoints<true><<<ctas, block, 0, s>>>(v, shift, pool, used_dev, pool_cap, seq_len, ahead);
+    rc = launch_done("k_build_checkpoints");
+    unsigned long long used = 0;
+    if (rc == GBWT_B200_OK && cudaMemcpy(&used, used_dev, sizeof(used), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "k_build_checkpoints");
+    if (rc != GBWT_B200_OK || used > pool_cap || used > 0xFFFFFFF0ull) {  // (an overflowing pool: leave the index without checkpoints)
+        cleanup(); cudaFree(first);
+        return rc;
+    }
+    Checkpoint* table = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&table), std::max<size_t>(256, used * sizeof(Checkpoint))) != cudaSuccess) {
+        rc = cuda_fail(cudaGetLastError(), "cudaMalloc(checkpoint table)");
+        cleanup(); cudaFree(first);
+        return rc;
+    }
+    if (used > 0) {
+        k_checkpoint_count<<<grid_for(ix, used), BLOCK_THREADS, 0, s>>>(pool, used, first);
+        launch_done("k_checkpoint_count");
+        rc = scan_counts(first, static_cast<uint32_t>(v.sequences + 1), s);
+        if (rc == GBWT_B200_OK) {
+            k_checkpoint_scatter<<<grid_for(ix, used), BLOCK_THREADS, 0, s>>>(pool, used, shift, first, table);
+            rc = launch_done("k_checkpoint_scatter");
+        }
+    }
+    std::vector<uint32_t> host_first(v.sequences + 1, 0);
+    if (rc == GBWT_B200_OK && cudaMemcpy(host_first.data(), first, host_first.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = cuda_fail(cudaGetLastError(), "checkpoint table");
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cleanup();
+    if (rc != GBWT_B200_OK) { cudaFree(first); cudaFree(table); return rc; }
+    uint32_t max_segments = 0;
+    for (uint64_t i = 0; i < v.sequences; i++) max_segments = std::max(max_segments, host_first[i + 1] - host_first[i]);
+    ix->d_ckpt_table = table; ix->d_ckpt_first = first;
+    ix->ckpt.table = table; ix->ckpt.first = first; ix->ckpt.seq_len = seq_len; ix->ckpt.max_segments = max_segments;
+    ix->ckpt_shift = shift; ix->ckpt_entries = used;
+    ix->ckpt_bytes = used * sizeof(Checkpoint) + (v.sequences + 1) * sizeof(uint32_t);
+    ix->ckpt_build_us = static_cast<uint64_t>(ms * 1000.0f);
+    ix->ckpt_ok = true;
+    return GBWT_B200_OK;
+}
+
 int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_index** out) {
     if (out == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output handle");
     *out = nullptr;
@@ -586,6 +778,8 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
         return fail(GBWT_B200_E_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
     }
     if (device < 0 || device >= count) return fail(GBWT_B200_E_ARGUMENT, "invalid device ordinal");
+    const int checkpoint_policy = policy & (GBWT_B200_LAYOUT_CHECKPOINTS | GBWT_B200_LAYOUT_NO_CHECKPOINTS);
+    policy &= ~(GBWT_B200_LAYOUT_CHECKPOINTS | GBWT_B200_LAYOUT_NO_CHECKPOINTS);
     HostLayout layout;
     std::string err;
     int rc = build_layout(parsed, policy, layout, err);
@@ -604,6 +798,12 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_endmarker, layout.endmarker.data(), layout.endmarker.size() * sizeof(Edge), ix->bytes[3]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_skips, layout.skips.data(), layout.skips.size() * 8, ix->skip_bytes);
+    if (rc == GBWT_B200_OK) {
+        uint64_t stage_bytes = 0;
+        rc = upload(&ix->d_stage_body, layout.stage_body.data(), layout.stage_body.size() * sizeof(uint32_t), stage_bytes);
+        ix->skip_bytes += stage_bytes;
+    }
+    ix->edges_total = layout.edges_total; ix->edges_local = layout.edges_local;
     if (rc == GBWT_B200_OK) {
         const size_t bytes = std::max<size_t>(256, parsed.sequences * sizeof(uint64_t));
         if (cudaMalloc(&ix->d_seq_len, bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, bytes) != cudaSuccess ||
@@ -639,9 +839,32 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     v.skips = static_cast<const Unit16*>(ix->d_skips);
     v.edges_valid = layout.edges_valid ? 1 : 0;
     v.walk_limit = layout.total_length;
+    v.stage_body = static_cast<const uint32_t*>(ix->d_stage_body);
+    // Record windows (find_window.cu) suit an index whose records are mostly single-edge or dense and whose edges
+    // mostly lead to nearby records; everything else keeps the scattered-load kernels.
+    {
+        const uint64_t runs = layout.format_counts[FMT_RUN8] + layout.format_counts[FMT_RUN32] + layout.format_counts[FMT_RUN64];
+        const bool mostly_plain = runs * 8 <= layout.format_counts[FMT_DENSE2] + layout.format_counts[FMT_SINGLE];
+        const bool local = layout.edges_local * 10 >= layout.edges_total * 9;
+        ix->window_ok = plan_windows(v, layout.bodies.size() / 2, ix->window);
+        ix->window_suits = mostly_plain && local;
+    }
     if (parsed.has_graph) {
         rc = attach_graph(ix, parsed.label_starts.data(), parsed.label_starts.size() - 1, parsed.label_bytes.data());
         if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+    }
+    // Path checkpoints by default for indexes whose sequences are long enough to be worth cutting up
+    // (GBWT_B200_LAYOUT_CHECKPOINTS / _NO_CHECKPOINTS decide explicitly; GBWT_B200_CHECKPOINTS=0/1 overrides both).
+    {
+        bool want = layout.total_length >= (uint64_t(1) << 22);
+        if (checkpoint_policy & GBWT_B200_LAYOUT_CHECKPOINTS) want = true;
+        if (checkpoint_policy & GBWT_B200_LAYOUT_NO_CHECKPOINTS) want = false;
+        const int knob = env_int("GBWT_B200_CHECKPOINTS", -1);
+        if (knob >= 0) want = knob != 0;
+        if (want) {
+            rc = build_checkpoints(ix);
+            if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+        }
     }
     *out = ix;
     return GBWT_B200_OK;
@@ -749,7 +972,7 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;
     {
         DeviceScope scope(ix->device);
-        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_seq_len); cudaFree(ix->d_dna_len);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_stage_body); cudaFree(ix->d_ckpt_table); cudaFree(ix->d_ckpt_first); cudaFree(ix->d_seq_len); cudaFree(ix->d_dna_len);
         cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;
@@ -772,6 +995,20 @@ uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* ix) { return ix && ix-
 uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* ix) { return ix ? ix->graph_bytes : 0; }
 uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* ix) { return ix ? ix->skip_bytes : 0; }
 
+void gbwt_b200_checkpoint_info(const gbwt_b200_index* ix, uint64_t info[6]) {
+    if (ix == nullptr || info == nullptr) return;
+    const uint64_t values[6] = {ix->ckpt_ok, uint64_t(1) << ix->ckpt_shift, ix->ckpt_entries, ix->ckpt_bytes, ix->ckpt_build_us, ix->ckpt.max_segments};
+    for (int i = 0; i < 6; i++) info[i] = values[i];
+}
+
+void gbwt_b200_window_info(const gbwt_b200_index* ix, uint64_t info[12]) {
+    if (ix == nullptr || info == nullptr) return;
+    const WindowPlan& w = ix->window;
+    const uint64_t values[12] = {ix->window_ok, ix->window_suits, uint64_t(1) << w.wshift, w.margin, w.body_cap, w.threads, w.smem_bytes,
+                                 w.windows, ix->edges_total, ix->edges_local, ix->window_queries.load(), ix->window_deferred.load()};
+    for (int i = 0; i < 12; i++) info[i] = values[i];
+}
+
 const char* gbwt_b200_last_error(void) { return g_last_error.c_str(); }
 
 // ---- statistics (src/gbwt.rs:105-175) ----------------------------------------------------------------
@@ -792,7 +1029,7 @@ uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* ix, uint64_t breakdown[10
         for (int i = 0; i < 4; i++) breakdown[i] = ix->bytes[i];
         for (int i = 0; i < FMT_COUNT; i++) breakdown[4 + i] = ix->format_counts[i];
     }
-    return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3] + ix->skip_bytes + ix->graph_bytes;
+    return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3] + ix->skip_bytes + ix->graph_bytes + ix->ckpt_bytes;
 }
 
 // ---- device-pointer entry points ---------------------------------------------------------------------
@@ -813,6 +1050,11 @@ int gbwt_b200_extend_device(const gbwt_b200_index* ix, const gbwt_b200_state* d_
 }
 int gbwt_b200_find_extend_device(const gbwt_b200_index* ix, const uint64_t* d_patterns, size_t n, size_t k,
                                  gbwt_b200_state* d_out, void* stream) {
+    DEVICE_ENTRY_PROLOGUE(ix);
+    return launch_find_extend(ix, d_patterns, n, k, d_out, static_cast<cudaStream_t>(stream));
+}
+int gbwt_b200_find_extend_u32_device(const gbwt_b200_index* ix, const uint32_t* d_patterns, size_t n, size_t k,
+                                     gbwt_b200_state* d_out, void* stream) {
     DEVICE_ENTRY_PROLOGUE(ix);
     return launch_find_extend(ix, d_patterns, n, k, d_out, static_cast<cudaStream_t>(stream));
 }
@@ -902,6 +1144,16 @@ int gbwt_b200_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, s
     return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(8 * k, sizeof(gbwt_b200_state))),
                        [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
         return launch_find_extend(ix, static_cast<uint64_t*>(d[0]), count, k, static_cast<gbwt_b200_state*>(d[1]), s);
+    });
+}
+
+int gbwt_b200_find_extend_u32(const gbwt_b200_index* ix, const uint32_t* patterns, size_t n, size_t k, gbwt_b200_state* out) {
+    if (int rc = check_index(ix)) return rc;
+    if (n > 0 && ((k > 0 && patterns == nullptr) || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
+    std::vector<HostArray> arrays = {{k > 0 ? patterns : nullptr, nullptr, 4 * k}, {nullptr, out, sizeof(gbwt_b200_state)}};
+    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(4 * k, sizeof(gbwt_b200_state))),
+                       [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
+        return launch_find_extend(ix, static_cast<uint32_t*>(d[0]), count, k, static_cast<gbwt_b200_state*>(d[1]), s);
     });
 }
 

@@ -1,0 +1,50 @@
+// find_window.h -- host-side launchers of the record-window search kernels (find_window.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gbwt_b200.h"
+#include "layout.h"
+
+namespace gbwt_b200 {
+
+// How a batch is cut into record windows. One bucket of the locality sort = one window of 2^wshift records; a CTA
+// stages the window plus `margin` records either side (descriptors, two-hop shortcuts and the contiguous bodies)
+// into shared memory with bulk copies and resolves the window's queries from there.
+struct WindowPlan {
+    uint32_t wshift;       // log2(records per window)
+    uint32_t margin;       // records staged before and after the window (multiple of STAGE_GRANULE)
+    uint32_t windows;      // number of windows = buckets of the sort
+    uint32_t max_records;  // (1 << wshift) + 2 * margin
+    uint32_t body_cap;     // 16-byte units of shared memory set aside for bodies
+    uint32_t threads;      // CTA size: 256, 512 or 1024
+    uint32_t smem_bytes;   // dynamic shared memory per CTA
+};
+
+// Chooses the plan for an index (GBWT_B200_WINDOW / _MARGIN / _SMEM_KB / _THREADS override). False = do not use
+// the window kernel for this index.
+bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan);
+
+// keys[q] = window of query q's first node (0 when it has no record), counts[1 + window] += 1.
+// T = uint64_t or uint32_t pattern nodes.
+template <class T>
+void launch_window_keys(const IndexView& ix, const WindowPlan& plan, const T* patterns, size_t n, size_t k, uint32_t* keys,
+                        uint32_t* counts, unsigned grid, cudaStream_t stream);
+
+// The search itself. bucket_end[w] = end of window w's slots in perm (what the scatter leaves in the cursor array);
+// counters[0] = window ticket, counters[1] = number of deferred queries (both zero on entry); queries the window
+// kernel cannot finish from shared memory are listed in `deferred` and finished by launch_find_deferred.
+template <class T>
+int launch_find_window(const IndexView& ix, const WindowPlan& plan, const T* patterns, const uint32_t* perm,
+                       const uint32_t* bucket_end, size_t n, size_t k, gbwt_b200_state* out, uint32_t* deferred,
+                       uint32_t* counters, int sm_count, cudaStream_t stream);
+
+template <class T>
+void launch_find_deferred(const IndexView& ix, const T* patterns, const uint32_t* deferred, const uint32_t* counters, size_t k,
+                          gbwt_b200_state* out, unsigned grid, cudaStream_t stream);
+
+// Plain (no window) kernels for 32-bit patterns, same dispatch as the 64-bit ones of kernels.cuh.
+void launch_find_extend_u32(const IndexView& ix, bool runs, const uint32_t* patterns, const uint32_t* perm, size_t n, size_t k,
+                            gbwt_b200_state* out, unsigned grid, cudaStream_t stream);
+
+}  // namespace gbwt_b200

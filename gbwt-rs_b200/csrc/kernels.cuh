@@ -399,6 +399,7 @@ __device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d
 
 // GBWT::sequence(id): the node identifiers themselves, up to 256 contiguous bytes per group.
 struct NodeSink {
+    static constexpr bool CHECKPOINTS = false;
     uint64_t* out;
     uint64_t cap;
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
@@ -413,6 +414,7 @@ struct NodeSink {
 // len - 1 - j of sequence id (support::reverse_path, src/support.rs:310-314). Positions [lo, hi) are written; the
 // node at position `probe` is also kept in `value` (all lanes) so that the two halves can be compared where they meet.
 struct HalfSink {
+    static constexpr bool CHECKPOINTS = false;
     uint64_t* out;
     uint64_t cap, len, lo, hi, probe, value;
     bool reverse;
@@ -456,6 +458,7 @@ __device__ __forceinline__ uint32_t complement_base(uint32_t c) {
 // requested for one group are only consumed when the next group arrives (32 steps later, long since landed),
 // and label bytes are fetched eight rows (256 bytes, a typical group) at a time before any of them is stored.
 struct DnaSink {
+    static constexpr bool CHECKPOINTS = false;
     GraphView graph;
     uint64_t node_base;  // alphabet offset + 1: GBZ::gbwt_node_to_sequence, src/gbz.rs:253-255
     uint8_t* out;        // nullptr: count only
@@ -704,12 +707,15 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
     Desc d;
     Quad k;
     load_landing<true>(descs, skips, base, records, node, d, k);
+    if constexpr (Sink::CHECKPOINTS) sink.checkpoint(node, offset, 0);
     for (;;) {
         if (in_group >= 31) {  // an iteration parks up to two nodes
             sink.group(static_cast<uint64_t>(mine), in_group, flushed);
             flushed += in_group;
             in_group = 0;
             if (flushed >= limit || flushed > ix.walk_limit) break;  // (walk_limit: a damaged index with a cycle)
+            // (node, offset) is the position of node number `flushed` of the sequence: what a checkpoint records
+            if constexpr (Sink::CHECKPOINTS) sink.checkpoint(node, offset, flushed);
             if (ahead != 0) {
                 // Sequences that walk the graph together arrive at a record together and would all wait for the same
                 // HBM miss. Node ids follow the graph's topological order, so the records the walk needs next lie a
@@ -1020,6 +1026,7 @@ __device__ __forceinline__ void relay_set(uint32_t* flag, uint32_t v) { *reinter
 
 // The walker's side of the ring (also keeps the node at index `probe`, flipped on the mirrored strand).
 struct RelaySink {
+    static constexpr bool CHECKPOINTS = false;
     RelayRing* ring;
     uint32_t slot;
     uint64_t probe, value;
@@ -1161,6 +1168,175 @@ __global__ void k_node_sequences(IndexView ix, GraphView graph, const uint64_t* 
         const uint64_t cap = o_hi > o_lo ? o_hi - o_lo : 0;
         const uint64_t count = len < cap ? len : cap;
         for (uint64_t j = lane; j < count; j += 32) bytes[o_lo - base + j] = __ldg(graph.bytes + lo + j);
+    }
+}
+
+// ---- K3 with checkpoints: extraction that is parallel ALONG the paths ---------------------------------------------------
+// A path walk is a dependent chain (src/gbwt.rs:557-568): however many paths a batch has, nothing can make one chain
+// of 6.7 M LF steps take less than 6.7 M round trips. What breaks the chain is knowing positions in its middle. When
+// the index is created, one pass of the warp-mode walk over every sequence records the position (node, offset) at
+// about every `interval`-th node (k_build_checkpoints; like the DA samples of the reference's GBWT, but indexed by
+// sequence and rank instead of by BWT position). A sequence is then extracted as independent segments, each walked
+// from its checkpoint to the next by ONE lane: a batch of 1024 paths of 6.7 M nodes is 6.7 M independent walks of
+// ~1024 steps instead of 1024 chains, latency is hidden by occupancy like in the search kernels, and the 32 lanes of
+// a warp take the same segment number of 32 neighbouring sequences, which in a pangenome walk the same records at the
+// same time (their loads coalesce into a handful of sectors). Every node is still produced by an LF step.
+
+struct Checkpoint { uint32_t node, offset; uint64_t index; };            // position of node number `index` of a sequence
+struct PoolEntry { uint32_t seq, node, offset, pad; uint64_t index, pad2; };  // as the build walk emits them
+static_assert(sizeof(Checkpoint) == 16 && sizeof(PoolEntry) == 32, "checkpoint records are loaded with vector loads");
+
+struct CheckpointSink {
+    static constexpr bool CHECKPOINTS = true;
+    PoolEntry* pool;
+    unsigned long long* pool_used;
+    uint64_t pool_cap;
+    uint32_t seq, shift;
+    uint64_t next;  // first index that wants a checkpoint
+    __device__ __forceinline__ void group(uint64_t, uint32_t, uint64_t) {}
+    __device__ __forceinline__ void finish() {}
+    // called at every flush of the walk (at most 32 nodes apart), so every multiple of the interval gets the first
+    // flush at or after it
+    __device__ __forceinline__ void checkpoint(uint32_t node, uint32_t offset, uint64_t index) {
+        if (index < next) return;
+        next = ((index >> shift) + 1) << shift;
+        if ((threadIdx.x & 31u) != 0) return;
+        const unsigned long long slot = atomicAdd(pool_used, 1ull);
+        if (slot >= pool_cap) return;  // cannot happen on a consistent index (the pool holds total length / interval + sequences)
+        PoolEntry e;
+        e.seq = seq; e.node = node; e.offset = offset; e.pad = 0; e.index = index; e.pad2 = 0;
+        pool[slot] = e;
+    }
+};
+
+// One warp per sequence: walks it once, leaves its length in seq_len[] and its checkpoints in the pool.
+template <bool CHECKED>
+__global__ void __launch_bounds__(128) k_build_checkpoints(IndexView ix, uint32_t shift, PoolEntry* __restrict__ pool,
+                                                            unsigned long long* __restrict__ pool_used, uint64_t pool_cap,
+                                                            uint64_t* __restrict__ seq_len, uint32_t ahead) {
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
+    for (size_t id = warp; id < ix.sequences; id += warps) {
+        CheckpointSink sink{pool, pool_used, pool_cap, static_cast<uint32_t>(id), shift, 0};
+        const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
+        if ((threadIdx.x & 31u) == 0) seq_len[id] = len;
+    }
+}
+
+// counts[1 + seq] = checkpoints of the sequence (the exclusive scan of it gives every sequence's first slot).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_checkpoint_count(const PoolEntry* __restrict__ pool, uint64_t used,
+                                                                     uint32_t* __restrict__ counts) {
+    GBWT_GRID_STRIDE(i, used) atomicAdd(counts + 1 + pool[i].seq, 1u);
+}
+
+// table[first[seq] + index / interval] = the checkpoint (slots of a sequence are consecutive, see CheckpointSink).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_checkpoint_scatter(const PoolEntry* __restrict__ pool, uint64_t used, uint32_t shift,
+                                                                       const uint32_t* __restrict__ first, Checkpoint* __restrict__ table) {
+    GBWT_GRID_STRIDE(i, used) {
+        const PoolEntry e = pool[i];
+        Checkpoint c;
+        c.node = e.node; c.offset = e.offset; c.index = e.index;
+        table[first[e.seq] + static_cast<uint32_t>(e.index >> shift)] = c;
+    }
+}
+
+struct CheckpointView {
+    const Checkpoint* table;
+    const uint32_t* first;     // [sequences + 1]: slots of sequence s are table[first[s] .. first[s + 1])
+    const uint64_t* seq_len;   // [sequences]
+    uint32_t max_segments;     // most checkpoints any sequence has
+};
+
+// Nodes [index, end) of a sequence by one lane, starting from a known position: Record::lf (src/bwt.rs:480-496) per
+// step, two nodes per step where the two-hop shortcut applies (layout.h). Writes out[i] for i < cap.
+template <bool CHECKED>
+__device__ __forceinline__ void walk_segment_lane(const IndexView& ix, uint32_t node, uint32_t offset, uint64_t index, uint64_t end,
+                                                  uint64_t* __restrict__ out, uint64_t cap) {
+    const RecordDesc* const descs = ix.desc;
+    const Unit16* const bodies = ix.bodies;
+    const Unit16* const skips = ix.skips;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    while (index < end) {
+        if (index < cap) out[index] = node;
+        uint32_t rec = node - base;
+        if (CHECKED) { if (rec - 1u >= records - 1u) break; }
+        else rec = rec < records ? rec : records - 1u;
+        Desc d;
+        load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
+        const Quad k = load_quad(skips + rec);
+        const uint32_t fmt = d.fmt(), i = offset;
+        if (i >= d.total_len()) break;  // GBWT::forward -> None (an empty record has length 0)
+        uint32_t b = 0, r = i;
+        if (fmt == FMT_DENSE2) {
+            const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
+            Quad lo, hi;
+            load_sector(bodies + d.body() + 2u * blk, lo, hi);
+            const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, b);
+            r = b ? ones : i - ones;
+        } else if (fmt != FMT_SINGLE) {
+            const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, i);
+            if (next == 0) break;
+            node = static_cast<uint32_t>(next); offset = static_cast<uint32_t>(next >> 32);
+            index++;
+            continue;
+        }
+        const uint32_t v = b ? d.node1() : d.node0();
+        if (v == 0) break;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+        const uint32_t w = b ? k.z : k.x;
+        if (w != 0) {
+            if (index + 1 < end && index + 1 < cap) out[index + 1] = v;
+            node = w; offset = (b ? k.w : k.y) + r;
+            index += 2;
+        } else {
+            node = v; offset = (b ? d.offset1() : d.offset0()) + r;
+            index += 1;
+        }
+    }
+}
+
+// Work item (segment j, block of 32 batch entries): lane l walks segment j of sequence ids[32 * block + l]. Items are
+// ordered by segment number first, so the CTAs running at any moment are all in the same part of the graph.
+template <bool CHECKED>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
+                                                                         size_t m, const uint64_t* __restrict__ out_offsets, uint64_t base,
+                                                                         uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t blocks = (m + 31) / 32;
+    const uint64_t items = blocks * cv.max_segments;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) / 32;
+    for (uint64_t item = warp; item < items; item += warps) {
+        const uint64_t j = item / blocks, i = (item - j * blocks) * 32 + lane;
+        if (i >= m) continue;
+        const uint64_t id = __ldg(ids + i);
+        if (id >= ix.sequences) {
+            if (j == 0 && lengths != nullptr) lengths[i] = ~0ull;  // GBWT::sequence() is None
+            continue;
+        }
+        const uint64_t len = cv.seq_len[id];
+        if (j == 0 && lengths != nullptr) lengths[i] = len;
+        const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
+        if (j >= count) continue;
+        const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+        const uint64_t cap = hi > lo ? hi - lo : 0;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j));
+        const uint64_t index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
+        uint64_t end = len;
+        if (j + 1 < count) {
+            const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j + 1));
+            end = (static_cast<uint64_t>(next.w) << 32) | next.z;
+        }
+        if (index >= cap) continue;
+        walk_segment_lane<CHECKED>(ix, raw.x, raw.y, index, end, nodes + (lo - base), cap);
+    }
+}
+
+// GBWT::sequence(id).count() from the table the checkpoint build left.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_lengths_from_table(uint64_t sequences, const uint64_t* __restrict__ seq_len,
+                                                                       const uint64_t* __restrict__ ids, size_t m, uint64_t* __restrict__ lengths) {
+    GBWT_GRID_STRIDE(i, m) {
+        const uint64_t id = __ldg(ids + i);
+        lengths[i] = id < sequences ? seq_len[id] : ~0ull;
     }
 }
 

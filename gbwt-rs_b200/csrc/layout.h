@@ -46,6 +46,10 @@ constexpr uint32_t DENSE_WORDS = 6;
 constexpr uint8_t DESC_INLINE_EDGES = 1;    // w[] = {node0, offset0, node1, offset1}
 constexpr uint32_t RUN32_MAX_LEN = 1u << 24;
 constexpr uint32_t NO_SYMBOL = 0xFFFFFFFFu;
+// Window kernels (find_window.cuh): record windows are staged into shared memory in multiples of STAGE_GRANULE
+// records; STAGE_LOCAL is the distance (in records) within which an edge counts as local.
+constexpr uint32_t STAGE_GRANULE = 32;
+constexpr uint32_t STAGE_LOCAL = 128;
 
 // One record. 32 bytes, 32-byte aligned: a single sector, fetched with one 256-bit load, gives everything
 // but the body.
@@ -90,6 +94,10 @@ struct IndexView {
     // stop there, so that a damaged index with a cycle cannot keep a kernel running for ever (the reference's
     // iterator would not terminate on such an index).
     uint64_t walk_limit;
+    // Body offset (16-byte units) of record j * STAGE_GRANULE for j = 0 .. records / STAGE_GRANULE + 1 (the entries
+    // past the last record hold the total): bodies lie in record order, so the bodies of a record window are the
+    // contiguous range between two entries.
+    const uint32_t* stage_body;
 };
 
 // Magic multiplier for q = b / sigma, 0 <= b < 256, 1 <= sigma <= 256: q = (b * magic) >> 16.

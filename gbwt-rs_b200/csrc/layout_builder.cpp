@@ -24,11 +24,13 @@ struct RecordReader {
 
     RecordReader(const uint8_t* bytes, uint64_t len) : p(bytes), n(len) {}
 
+    // A varint of more than ten bytes, or one whose tenth byte does not fit 64 bits, is damaged input.
     bool varint(uint64_t& v) {
         v = 0;
         for (unsigned shift = 0; at < n; shift += 7) {
             uint8_t b = p[at++];
-            if (shift < 64) v += static_cast<uint64_t>(b & 0x7F) << shift;
+            if (shift >= 64 || (shift == 63 && (b & 0x7E) != 0)) { bad = true; return false; }
+            v += static_cast<uint64_t>(b & 0x7F) << shift;
             if (!(b & 0x80)) return true;
         }
         return false;
@@ -42,7 +44,7 @@ struct RecordReader {
         if (at >= n) return false;
         if (sigma >= 255) {
             uint64_t l;
-            if (!varint(value) || !varint(l)) { bad = true; return false; }
+            if (!varint(value) || !varint(l) || l == ~0ull) { bad = true; return false; }
             len = l + 1;
         } else {
             uint8_t b = p[at++];
@@ -50,7 +52,7 @@ struct RecordReader {
             len = b / sigma + 1;
             if (len == threshold) {
                 uint64_t extra;
-                if (!varint(extra)) { bad = true; return false; }
+                if (!varint(extra) || extra > ~0ull - len) { bad = true; return false; }
                 len += extra;
             }
         }
@@ -60,6 +62,7 @@ struct RecordReader {
 
 struct Plan {
     uint64_t sigma = 0, total = 0, runs = 0, run8 = 0, run32 = 0, header_end = 0;
+    uint64_t count01[2] = {0, 0};  // occurrences of symbols 0 and 1 (what the two-hop shortcuts are checked against)
     uint8_t fmt = FMT_EMPTY;
     uint32_t units = 0;   // body size in 16-byte units
     int status = GBWT_B200_OK;
@@ -88,7 +91,10 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
     uint64_t value, rl;
     while (rd.run(value, rl)) {
         if (value >= pl.sigma) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
+        // a run longer than the 32-bit layout (a crafted length near 2^64 would wrap the sums below)
+        if (rl == 0 || rl > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
         pl.total += rl;
+        if (value < 2) pl.count01[value] += rl;
         pl.runs++;
         if (max8) pl.run8 += ceil_div(rl, max8);
         pl.run32 += ceil_div(rl, RUN32_MAX_LEN);
@@ -164,7 +170,7 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
         uint64_t pos = 0;
         while (rd.run(value, rl)) {
             if (value == 1) {
-                for (uint64_t i = pos; i < pos + rl; i++) {
+                for (uint64_t i = pos; i < pos + rl && i < pl.total; i++) {
                     uint64_t blk = i / DENSE_BITS, bit = i % DENSE_BITS;
                     words[blk * 8 + 2 + bit / 32] |= 1u << (bit % 32);
                 }
@@ -185,8 +191,9 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
     case FMT_RUN8: {
         const uint64_t max8 = std::max<uint64_t>(1, 256 / sigma);
         uint64_t n = 0;
+        const uint64_t cap = static_cast<uint64_t>(pl.units) * 16;  // what pass 1 sized the body for
         while (rd.run(value, rl)) {
-            while (rl > 0) {
+            while (rl > 0 && n < cap) {
                 uint64_t piece = std::min(rl, max8);
                 body[n++] = static_cast<uint8_t>(value + sigma * (piece - 1));
                 rl -= piece;
@@ -198,8 +205,9 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
     case FMT_RUN32: {
         uint32_t* out = reinterpret_cast<uint32_t*>(body);
         uint64_t n = 0;
+        const uint64_t cap = static_cast<uint64_t>(pl.units) * 4;
         while (rd.run(value, rl)) {
-            while (rl > 0) {
+            while (rl > 0 && n < cap) {
                 uint64_t piece = std::min<uint64_t>(rl, RUN32_MAX_LEN);
                 out[n++] = static_cast<uint32_t>(value) | (static_cast<uint32_t>(piece - 1) << 8);
                 rl -= piece;
@@ -211,7 +219,8 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
     case FMT_RUN64: {
         uint32_t* out = reinterpret_cast<uint32_t*>(body);
         uint64_t n = 0;
-        while (rd.run(value, rl)) {
+        const uint64_t cap = static_cast<uint64_t>(pl.units) * 2;
+        while (n < cap && rd.run(value, rl)) {
             out[2 * n] = static_cast<uint32_t>(value);
             out[2 * n + 1] = static_cast<uint32_t>(rl);
             n++;
@@ -298,6 +307,10 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
             if (!has_record(w[0])) { edges_valid.store(false); continue; }
             const RecordDesc& v = out.desc[w[0] - in.offset];
             if (v.fmt != FMT_SINGLE || v.w01[0] == 0 || !has_record(v.w01[0])) continue;
+            // The shortcut replaces the step on v: Record::follow / lf there clamp to v's length (src/bwt.rs:605-607,
+            // 484), which only leaves the positions alone if everything u sends over this edge lies inside v. Always
+            // true in a consistent index; on a damaged one the shortcut is simply not made.
+            if (static_cast<uint64_t>(w[1]) + plans[i].count01[b] > v.total_len) continue;
             const uint64_t offset = static_cast<uint64_t>(w[1]) + v.w01[1];
             if (offset > 0xFFFFFFFFull) continue;
             skip[2 * b] = v.w01[0];
@@ -305,6 +318,39 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
         }
     }
     out.edges_valid = edges_valid.load();
+
+    // Staging table of the window kernels (layout.h, IndexView::stage_body): where the bodies of every
+    // STAGE_GRANULE-th record start, so that a CTA can size the bulk copy of a record window without reading
+    // descriptors first. Bodies lie in record order, so a window of records owns one contiguous range of units.
+    {
+        const uint64_t entries = R / STAGE_GRANULE + 2;
+        out.stage_body.assign(entries, static_cast<uint32_t>(body_at[R]));
+        for (uint64_t j = 0; j * STAGE_GRANULE <= R; j++) out.stage_body[j] = static_cast<uint32_t>(body_at[j * STAGE_GRANULE]);
+    }
+    // How local the graph is in record order: the share of edges whose target lies within STAGE_LOCAL records. The
+    // window kernels are only worth launching when a pattern mostly stays near its first record.
+    {
+        uint64_t edges_seen = 0, edges_near = 0;
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(+ : edges_seen, edges_near)
+        for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
+            const RecordDesc& d = out.desc[i];
+            if (d.fmt == FMT_EMPTY) continue;
+            auto tally = [&](uint32_t node) {
+                if (node == 0) return;
+                edges_seen++;
+                const int64_t delta = static_cast<int64_t>(node) - static_cast<int64_t>(in.offset) - i;
+                if (delta >= -static_cast<int64_t>(STAGE_LOCAL) && delta <= static_cast<int64_t>(STAGE_LOCAL)) edges_near++;
+            };
+            if (d.flags & DESC_INLINE_EDGES) {
+                tally(d.w01[0]);
+                if (plans[i].sigma == 2) tally(d.w23[0]);
+            } else {
+                for (uint64_t e = 0; e < plans[i].sigma; e++) tally(out.edges[edge_at[i] + e].node);
+            }
+        }
+        out.edges_total = edges_seen;
+        out.edges_local = edges_near;
+    }
 
     // Endmarker: Record::decompress of record 0 (src/bwt.rs:465-475, src/gbwt.rs:413-414).
     out.endmarker.clear();

@@ -16,6 +16,8 @@ struct HostLayout {
     std::vector<Edge> edges;       // edge lists of records with sigma > 2
     std::vector<Edge> endmarker;   // Record::decompress() of record 0 (src/gbwt.rs:413-414)
     std::vector<uint64_t> skips;   // two words per record (IndexView::skips)
+    std::vector<uint32_t> stage_body;  // body offset of every STAGE_GRANULE-th record (IndexView::stage_body)
+    uint64_t edges_total = 0, edges_local = 0;  // edges, and those whose target is within STAGE_LOCAL records
     bool edges_valid = true;
     uint64_t total_length = 0;    // sum of the record lengths (IndexView::walk_limit)
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};

@@ -137,17 +137,36 @@ int parse_gbwt(Cursor& c, ParsedGBWT& out, std::string& err) {
 struct ZstdApi {
     size_t (*decompress)(void*, size_t, const void*, size_t) = nullptr;
     unsigned (*is_error)(size_t) = nullptr;
+    unsigned long long (*frame_content_size)(const void*, size_t) = nullptr;
     ZstdApi() {
         void* lib = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
         if (lib == nullptr) lib = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
         if (lib == nullptr) return;
         decompress = reinterpret_cast<decltype(decompress)>(dlsym(lib, "ZSTD_decompress"));
         is_error = reinterpret_cast<decltype(is_error)>(dlsym(lib, "ZSTD_isError"));
+        frame_content_size = reinterpret_cast<decltype(frame_content_size)>(dlsym(lib, "ZSTD_getFrameContentSize"));
     }
 };
 
-bool zstd_decompress(uint8_t* dst, size_t dst_len, const uint8_t* src, size_t src_len, size_t& produced, std::string& err) {
+const ZstdApi& zstd_api() {
     static const ZstdApi api;  // resolved once (thread-safe initialisation)
+    return api;
+}
+
+// The decompressed size the frame itself declares, when it does (frames written by one-shot compression, which is
+// what the reference uses, always do): lets the loader reject a damaged `total` before it allocates that much.
+// Returns false when the frame declares a different size (or is not a frame at all).
+bool zstd_size_plausible(const uint8_t* src, size_t src_len, uint64_t total) {
+    const ZstdApi& api = zstd_api();
+    if (api.frame_content_size == nullptr) return true;
+    const unsigned long long declared = api.frame_content_size(src, src_len);
+    if (declared == 0ULL - 2) return total == 0 && src_len == 0;  // ZSTD_CONTENTSIZE_ERROR
+    if (declared == 0ULL - 1) return true;                        // ZSTD_CONTENTSIZE_UNKNOWN
+    return declared == total;
+}
+
+bool zstd_decompress(uint8_t* dst, size_t dst_len, const uint8_t* src, size_t src_len, size_t& produced, std::string& err) {
+    const ZstdApi& api = zstd_api();
     if (api.decompress == nullptr || api.is_error == nullptr) { err = "StringArray: libzstd is not available"; return false; }
     produced = api.decompress(dst, dst_len, src, src_len);
     if (api.is_error(produced)) { err = "StringArray: Zstandard decompression failed"; return false; }
@@ -176,6 +195,10 @@ int parse_graph(Cursor& c, ParsedGBWT& out, std::string& err) {
         const uint8_t* compressed = c.here();
         c.skip_words((compressed_len + 7) / 8);
         if (!c.ok() || total > (uint64_t(1) << 48)) { err = "StringArray: invalid data"; return GBWT_B200_E_INVALID_DATA; }
+        if (!zstd_size_plausible(compressed, compressed_len, total)) {
+            err = "StringArray: Decompressed string length does not match the expected length";
+            return GBWT_B200_E_INVALID_DATA;
+        }
         out.label_bytes.resize(total);
         size_t produced = 0;
         uint8_t scratch = 0;

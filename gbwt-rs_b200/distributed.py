@@ -23,12 +23,14 @@ def gather_states(local: np.ndarray, n_total: int, dst: int = 0, device=None):
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    words = local.view(np.uint64).reshape(len(local), -1).shape[1] if len(local) else 3
+    # words per row from the dtype (also right for a rank whose block is empty): SearchState = 3, BidirectionalState = 6
+    local = np.asarray(local)
+    words = max(1, local.dtype.itemsize // 8) * (int(np.prod(local.shape[1:])) if local.ndim > 1 else 1)
     sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
     width = max(sizes) if sizes else 0
     buf = torch.zeros((width, words), dtype=torch.int64, device=device)
     if len(local):
-        buf[: len(local)] = torch.from_numpy(local.view(np.int64).reshape(len(local), words)).to(buf.device)
+        buf[: len(local)] = torch.from_numpy(np.ascontiguousarray(local).view(np.int64).reshape(len(local), words)).to(buf.device)
     gathered = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(gathered, buf)
     if rank != dst:

@@ -69,7 +69,13 @@ typedef struct gbwt_b200_index gbwt_b200_index;
 /* How record bodies are laid out in HBM (see DESIGN.md "Device layout"). */
 enum {
     GBWT_B200_LAYOUT_AUTO = 0, /* per record: the format that touches the fewest bytes per query */
-    GBWT_B200_LAYOUT_RUNS = 1  /* run-length bodies only (the reference's runs, escape-free re-encoding) */
+    GBWT_B200_LAYOUT_RUNS = 1, /* run-length bodies only (the reference's runs, escape-free re-encoding) */
+    /* Flags, or-ed into the policy. Path checkpoints: while the index is created, one walk over every sequence records
+     * its length and its position at every few hundredth node, so that sequence()/extract afterwards run as
+     * independent segments instead of one dependent chain per sequence (results identical).
+     * Built by default for indexes of 4 Mi path nodes or more. */
+    GBWT_B200_LAYOUT_CHECKPOINTS = 0x100,    /* build them whatever the size */
+    GBWT_B200_LAYOUT_NO_CHECKPOINTS = 0x200  /* never build them (extraction walks whole chains) */
 };
 
 /* ---- construction (replaces GBWT::load / serialize::load_from, src/gbwt.rs:402-438; the embedded
@@ -119,6 +125,14 @@ GBWT_B200_API uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* index);      
 /* Bytes of HBM held by the index (including the path-walk shortcuts and node labels, reported separately
  * below), and a breakdown: [0] descriptors, [1] bodies, [2] edge lists, [3] endmarker; [4..9] number of records per body format (empty, single-edge, dense, run8, run32, run64). */
 GBWT_B200_API uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* index, uint64_t breakdown[10]);
+/* Path checkpoints of this index: [0] present, [1] interval (nodes), [2] entries, [3] bytes of HBM, [4] microseconds the
+ * build walk took on the device, [5] most segments any sequence has. */
+GBWT_B200_API void gbwt_b200_checkpoint_info(const gbwt_b200_index* index, uint64_t info[6]);
+/* The record-window search kernel's plan for this index and its counters (development / tests): [0] can run, [1] is
+ * the default for sorted batches, [2] records per window, [3] margin, [4] body units staged, [5] threads per CTA,
+ * [6] shared memory per CTA, [7] windows, [8] edges, [9] edges to nearby records, and -- only counted when
+ * GBWT_B200_WINDOW_STATS=1 -- [10] queries sent through windows, [11] queries the windows deferred to the general kernel. */
+GBWT_B200_API void gbwt_b200_window_info(const gbwt_b200_index* index, uint64_t info[12]);
 
 /* ---- unidirectional search -------------------------------------------------------------------- */
 /* GBWT::find (src/gbwt.rs:269-281) for n nodes. */
@@ -130,6 +144,11 @@ GBWT_B200_API int gbwt_b200_extend(const gbwt_b200_index* index, const gbwt_b200
  * k nodes each, row-major. k == 0 yields None. */
 GBWT_B200_API int gbwt_b200_find_extend(const gbwt_b200_index* index, const uint64_t* patterns, size_t n, size_t k,
                                        gbwt_b200_state* out);
+/* The same for callers that hold 32-bit node identifiers (every node of a loaded index is below 2^32, see
+ * GBWT_B200_E_RANGE): half the bytes over PCIe per query. Results are identical to gbwt_b200_find_extend on the
+ * widened patterns; a Rust caller with Vec<usize> paths (src/bin/benchmark.rs:155-169) narrows once on its side. */
+GBWT_B200_API int gbwt_b200_find_extend_u32(const gbwt_b200_index* index, const uint32_t* patterns, size_t n, size_t k,
+                                           gbwt_b200_state* out);
 /* Same for ragged patterns: pattern q = nodes[offsets[q] .. offsets[q+1]). */
 GBWT_B200_API int gbwt_b200_find_extend_ragged(const gbwt_b200_index* index, const uint64_t* nodes,
                                               const uint64_t* offsets, size_t n, gbwt_b200_state* out);
@@ -201,6 +220,8 @@ GBWT_B200_API int gbwt_b200_extract_dna(const gbwt_b200_index* index, const uint
 /* ---- device-pointer entry points (inputs and outputs already resident in HBM) ------------------- */
 GBWT_B200_API int gbwt_b200_find_extend_device(const gbwt_b200_index* index, const uint64_t* d_patterns, size_t n,
                                               size_t k, gbwt_b200_state* d_out, void* stream);
+GBWT_B200_API int gbwt_b200_find_extend_u32_device(const gbwt_b200_index* index, const uint32_t* d_patterns, size_t n,
+                                                  size_t k, gbwt_b200_state* d_out, void* stream);
 GBWT_B200_API int gbwt_b200_find_extend_ragged_device(const gbwt_b200_index* index, const uint64_t* d_nodes,
                                                      const uint64_t* d_offsets, size_t n, gbwt_b200_state* d_out,
                                                      void* stream);

@@ -1,0 +1,221 @@
+"""GPU parity tests for the round-2 kernels, through the C ABI against the CPU oracle, bit-exact:
+
+* the record-window search kernel (find_window.cu: records staged into shared memory with bulk copies, two-hop
+  steps) with windows small enough that queries leave them, bodies that do not fit, record formats it defers, every
+  way a pattern can fail, and 32-bit patterns;
+* checkpointed path extraction (k_build_checkpoints / k_extract_checkpointed) against the chain walks and the oracle.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import gbwt_builder as gb
+import parity_checks as pc
+from oracle import oracle as orc
+from synth import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import gbwt_rs_b200
+    return gbwt_rs_b200
+
+
+def image_of(b, bidirectional=True):
+    flags = 4 | (1 if bidirectional else 0)
+    return synth.gbwt_image(b["sequences"], b["size"], b["offset"], b["alphabet_size"], flags, b["starts"], b["data"])
+
+
+def force_windows(monkeypatch, **knobs):
+    monkeypatch.setenv("GBWT_B200_LOCALITY", "1")        # sort even tiny batches on tiny indexes
+    monkeypatch.setenv("GBWT_B200_FIND_WINDOW", "2")     # windows on any index they can run on
+    monkeypatch.setenv("GBWT_B200_WINDOW_STATS", "1")
+    for k, v in knobs.items():
+        monkeypatch.setenv("GBWT_B200_" + k, str(v))
+
+
+def damaged_batches(g, pats, rng):
+    """The ways a pattern can fail: a node that is no node, the other strand, a valid node in the wrong place."""
+    n, k = pats.shape
+    rows, cols = np.arange(n), rng.integers(0, k, n)
+    bad = pats.copy()
+    values = np.array([0, 1, 2**32, 2**63, g.alphabet_size(), g.alphabet_size() + 5], dtype=np.uint64)
+    bad[rows, cols] = values[rng.integers(0, 6, n)]
+    swapped = pats.copy()
+    swapped[rows, cols] ^= np.uint64(1)
+    skipped = pats.copy()
+    skipped[:, k // 2:] = np.roll(skipped[:, k // 2:], 1, axis=1)
+    return [pats, bad, swapped, skipped]
+
+
+@pytest.mark.parametrize("threads", [256, 512, 1024])
+def test_window_kernel_matches_oracle(b200, threads, monkeypatch):
+    force_windows(monkeypatch, WINDOW_THREADS=threads)
+    S, H, seed = 3000, 64, 42
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    info = e.window_info()
+    assert info["can_run"] and info["default"] and info["threads"] == threads
+    pats = synth.patterns(S, H, seed, n=200_000, k=32)
+    out = e.find_extend(pats)
+    assert pc.states_equal(out, g.find_extend_batch(pats))
+    assert np.all(out["end"] > out["start"]) and np.array_equal(out["node"], pats[:, -1])
+    info = e.window_info()
+    assert info["queries"] >= 200_000 and info["deferred"] * 100 < info["queries"], info   # answered from shared memory
+    assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), out)
+
+
+def test_window_kernel_edge_cases(b200, monkeypatch):
+    force_windows(monkeypatch)
+    S, H, seed = 400, 40, 17
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    rng = np.random.default_rng(8)
+    for k in (1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 64):
+        pats = synth.patterns(S, H, seed, n=3000, k=k)
+        for batch in damaged_batches(g, pats, rng):
+            want = g.find_extend_batch(batch)
+            assert pc.states_equal(e.find_extend(batch), want), k
+            narrow = batch[np.all(batch < 2**32, axis=1)]
+            assert pc.states_equal(e.find_extend_u32(narrow.astype(np.uint32)), g.find_extend_batch(narrow)), k
+    assert e.window_info()["queries"] > 0
+    pc.check_find_extend_random(e, g, n=30_000, k=7, seed=2)
+
+
+@pytest.mark.parametrize("knobs", [dict(WINDOW=32, WINDOW_MARGIN=32), dict(WINDOW=64, WINDOW_MARGIN=0),
+                                   dict(WINDOW_SMEM_KB=16, WINDOW=128, WINDOW_MARGIN=64)])
+def test_window_kernel_defers_what_it_cannot_answer(b200, knobs, monkeypatch):
+    # windows smaller than a pattern's reach, no margin at all, and too little shared memory for the 1024-haplotype
+    # bodies: the deferred list and the general kernel must give the same answers
+    force_windows(monkeypatch, **knobs)
+    S, H, seed = 500, 1024, 3
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    pats = synth.patterns(S, H, seed, n=60_000, k=32)
+    rng = np.random.default_rng(1)
+    for batch in damaged_batches(g, pats, rng):
+        assert pc.states_equal(e.find_extend(batch), g.find_extend_batch(batch))
+    info = e.window_info()
+    assert info["deferred"] > 0 and info["queries"] >= 4 * 60_000, info
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_window_kernel_on_fixtures_and_random_graphs(b200, layout, monkeypatch):
+    # indexes the windows are not meant for (run-length bodies, outdegree > 2, empty records, tiny): forced on, same answers
+    force_windows(monkeypatch)
+    for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw, layout=layout)
+        pc.check_find_extend_subpaths(e, g)
+        pc.check_find_extend_random(e, g, n=4001, k=4, seed=11)
+        pats = np.array([[2**40, 22], [0, 0], [22, 2**63]], dtype=np.uint64)
+        assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
+        assert e.window_info()["queries"] > 0
+    from test_hostsim_layout import random_paths
+    for seed in range(4):
+        rng = random.Random(seed)
+        paths = random_paths(rng, n_nodes=rng.choice([6, 12, 40]), n_paths=rng.choice([10, 40]), max_len=rng.choice([8, 20]))
+        if not any(paths):
+            paths.append([2, 4])
+        img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths)))
+        g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, layout=layout)
+        pc.check_find_extend_subpaths(e, g)
+        pc.check_find_extend_random(e, g, n=5000, k=5, seed=seed)
+
+
+def test_u32_patterns_without_windows(b200, monkeypatch):
+    # the 32-bit entry point on the plain kernels (small batch: no sort) and on the sorted general kernel
+    S, H, seed = 600, 64, 5
+    img = synth.bubble_chain(S, H, seed)
+    pats = synth.patterns(S, H, seed, n=50_000, k=32)
+    for layout in ("auto", "runs"):
+        g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)
+        want = g.find_extend_batch(pats)
+        assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), want)
+        monkeypatch.setenv("GBWT_B200_LOCALITY", "1")
+        monkeypatch.setenv("GBWT_B200_FIND_WINDOW", "0")
+        assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), want)
+        monkeypatch.delenv("GBWT_B200_LOCALITY")
+        monkeypatch.delenv("GBWT_B200_FIND_WINDOW")
+    assert len(e.find_extend_u32(np.zeros((0, 32), dtype=np.uint32))) == 0
+
+
+# ---- checkpointed extraction ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shift", [6, 8])
+def test_checkpointed_extraction_matches_chain_walks(b200, shift, monkeypatch):
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", str(shift))
+    S, H, seed = 1500, 48, 9
+    img = synth.bubble_chain(S, H, seed)
+    g = orc.GBWT.load(img.array)
+    e = b200.GBWT.from_bytes(img.array, checkpoints=True)
+    plain = b200.GBWT.from_bytes(img.array, checkpoints=False)
+    info = e.checkpoint_info()
+    assert info["present"] and info["interval"] == 1 << shift and info["max_segments"] >= (2 * S + 1) >> shift
+    assert not plain.checkpoint_info()["present"]
+    ids = np.concatenate([np.arange(2 * H, dtype=np.uint64), np.array([2 * H, 2**40, 3, 3], dtype=np.uint64)])
+    o_off, o_nodes = g.extract_batch(ids)
+    for engine in (e, plain):
+        offsets, nodes, lengths = engine.extract(ids)
+        assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+    assert np.array_equal(e.sequence_lengths(ids), plain.sequence_lengths(ids))
+    for i in (0, 1, 2 * H - 1):
+        assert np.array_equal(np.array(list(e.sequence(i)), dtype=np.uint64), synth.sequence(S, H, seed, i))
+    # slots shorter and longer than the sequences: truncated, and the slack comes back zeroed
+    lengths = e.sequence_lengths(ids[:6])
+    caps = np.array([0, 5, int(lengths[2]), int(lengths[3]) + 7, 1, 64], dtype=np.uint64)
+    offs = np.zeros(7, dtype=np.uint64)
+    np.cumsum(caps, out=offs[1:])
+    nodes = np.full(int(offs[-1]), 77, dtype=np.uint64)
+    got_len = np.zeros(6, dtype=np.uint64)
+    lib = b200.library()
+    rc = lib.gbwt_b200_extract(e._h, ids[:6].ctypes.data, 6, offs.ctypes.data, nodes.ctypes.data, got_len.ctypes.data)
+    assert rc == 0 and np.array_equal(got_len, lengths)
+    for i in range(6):
+        full = synth.sequence(S, H, seed, int(ids[i]))
+        a, b = int(offs[i]), int(offs[i + 1])
+        n = min(b - a, len(full))
+        assert np.array_equal(nodes[a:a + n], full[:n]) and np.all(nodes[a + n:b] == 0)
+
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_checkpointed_extraction_on_fixtures_and_random_graphs(b200, layout, monkeypatch):
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", "6")
+    for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw, layout=layout, checkpoints=True)
+        assert e.checkpoint_info()["present"]
+        pc.check_navigation(e, g)
+    from test_hostsim_layout import random_paths
+    for seed in range(4):
+        rng = random.Random(100 + seed)
+        paths = random_paths(rng, n_nodes=rng.choice([3, 12, 40]), n_paths=rng.choice([10, 40]), max_len=rng.choice([8, 200, 700]))
+        if not any(paths):
+            paths.append([2, 4])
+        img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths)))
+        g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, layout=layout, checkpoints=True)
+        ids = np.arange(g.sequences() + 2, dtype=np.uint64)
+        o_off, o_nodes = g.extract_batch(ids)
+        offsets, nodes, lengths = e.extract(ids)
+        assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+
+
+def test_checkpoints_on_an_index_with_invalid_edge_targets(b200):
+    # a damaged index (an edge to a node beyond the alphabet): the build walk and the segment walks take their
+    # bounds-checked instantiation and stop where the reference's iterator stops
+    edges = [[(1, 0)], [(2, 0), (40, 0)], [(0, 0)]]
+    runs = [[(0, 2)], [(1, 1), (0, 1)], [(0, 1)]]
+    g0 = orc.GBWT.from_records(edges, runs, sequences=2, size=6, offset=0)
+    img = synth.gbwt_image(2, 6, 0, 3, 4, g0.record_starts(), g0.bwt_data())
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, checkpoints=True)
+    assert e.checkpoint_info()["present"]
+    ids = np.arange(3, dtype=np.uint64)
+    o_off, o_nodes = g.extract_batch(ids)
+    offsets, nodes, lengths = e.extract(ids)
+    assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes) and lengths[2] == np.uint64(2**64 - 1)

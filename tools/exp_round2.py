@@ -1,0 +1,108 @@
+"""Development experiment (round 2): times the record-window search kernel against the scattered-load kernels, for
+both pattern widths and a few window shapes, and the checkpointed extraction against the chain walks, on one GPU.
+Usage (GPU box): python tools/exp_round2.py [--queries N] [--find VARIANTS] [--extract 0|1]
+A find variant is name[:KNOB=value[:KNOB=value...]] with GBWT_B200_ knobs read when the index is created."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import gbwt_rs_b200 as gb
+from synth import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--queries", type=int, default=1 << 26)
+ap.add_argument("--sites", type=int, default=3_333_333)
+ap.add_argument("--haplotypes", type=int, default=1024)
+ap.add_argument("--find", default="old:FIND_WINDOW=0,win512,win256:WINDOW_THREADS=256,win1024:WINDOW_THREADS=1024")
+ap.add_argument("--extract", type=int, default=1)
+ap.add_argument("--extract-plain", type=int, default=1)
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+S, H, Q = args.sites, args.haplotypes, args.queries
+t = time.time()
+img = synth.bubble_chain(S, H, 42)
+print(json.dumps({"image_s": time.time() - t}), flush=True)
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn, reps):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+if args.find:
+    d_pat = torch.empty((Q, 32), dtype=torch.int64, device=dev)
+    d_out = torch.empty((Q, 3), dtype=torch.int64, device=dev)
+    synth.patterns_device(S, H, 42, Q, d_pat.data_ptr(), stream=stream)
+    d_pat32 = d_pat.to(torch.int32)
+    torch.cuda.synchronize()
+    ref = None
+    for variant in args.find.split(","):
+        name, *knobs = variant.split(":")
+        set_knobs = []
+        for kv in knobs:
+            k, v = kv.split("=")
+            os.environ["GBWT_B200_" + k] = v
+            set_knobs.append("GBWT_B200_" + k)
+        os.environ["GBWT_B200_WINDOW_STATS"] = "0"
+        t = time.time()
+        index = gb.GBWT.from_bytes(img.array, checkpoints=False)
+        build_s = time.time() - t
+        row = {"variant": variant, "build_s": build_s, "window": index.window_info()}
+        for width, pat in (("u64", d_pat), ("u32", d_pat32)):
+            fn = (lambda: index.find_extend_device(pat.data_ptr(), Q, 32, d_out.data_ptr(), stream)) if width == "u64" else \
+                 (lambda: index.find_extend_u32_device(pat.data_ptr(), Q, 32, d_out.data_ptr(), stream))
+            ms = timed(fn, args.reps)
+            chk = int((d_out[:, 2] - d_out[:, 1]).sum().item())
+            ok = bool(torch.equal(d_out[:, 0], d_pat[:, 31]))
+            if ref is None:
+                ref = chk
+            row[width] = {"ms": ms, "gqps": Q / ms / 1e6, "checksum_ok": chk == ref and ok}
+        os.environ["GBWT_B200_WINDOW_STATS"] = "1"
+        index.find_extend_device(d_pat.data_ptr(), Q, 32, d_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        info = index.window_info()
+        row["deferred"] = info["deferred"]
+        print(json.dumps(row), flush=True)
+        del index
+        for k in set_knobs:
+            del os.environ[k]
+    del d_pat, d_out, d_pat32
+
+if args.extract:
+    t = time.time()
+    index = gb.GBWT.from_bytes(img.array, checkpoints=True)
+    print(json.dumps({"build_with_checkpoints_s": time.time() - t, "checkpoints": index.checkpoint_info()}), flush=True)
+    m, length = H, 2 * S + 1
+    ids = torch.arange(0, m, dtype=torch.int64, device=dev) * 2
+    offs = torch.arange(m + 1, dtype=torch.int64, device=dev) * length
+    nodes = torch.empty(m * length, dtype=torch.int64, device=dev)
+    lens = torch.empty(m, dtype=torch.int64, device=dev)
+    fn = lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
+    ms = timed(fn, args.reps)
+    ok = bool(torch.all(lens == length).item())
+    first = nodes[:length].cpu().numpy().view(np.uint64)
+    ok = ok and np.array_equal(first, synth.sequence(S, H, 42, 0))
+    last = nodes[(m - 1) * length:].cpu().numpy().view(np.uint64)
+    ok = ok and np.array_equal(last, synth.sequence(S, H, 42, 2 * (m - 1)))
+    checksum = int(nodes.sum().item())
+    print(json.dumps({"extract": "checkpointed", "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6, "ok": ok, "checksum": checksum}), flush=True)
+    if args.extract_plain:
+        os.environ["GBWT_B200_EXTRACT_CHECKPOINTS"] = "0"
+        nodes.zero_()
+        ms = timed(fn, 1)
+        print(json.dumps({"extract": "two-ended chains (lengths known)", "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6,
+                          "checksum_ok": int(nodes.sum().item()) == checksum}), flush=True)
+        os.environ["GBWT_B200_EXTRACT_SPLIT"] = "0"
+        ms = timed(fn, 1)
+        print(json.dumps({"extract": "one-ended chains", "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6,
+                          "checksum_ok": int(nodes.sum().item()) == checksum}), flush=True)
