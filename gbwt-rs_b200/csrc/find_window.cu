@@ -28,57 +28,51 @@ namespace gbwt_b200 {
 
 namespace {
 
-// ---- mbarrier / bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP) -------------------------------------------------
+// ---- shared-memory accessors (32-bit shared-space addresses: no generic-pointer arithmetic in the loop) --------------
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
 }
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
 }
-
-__device__ __forceinline__ void bulk_global_to_shared(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
 }
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done, tries = 0;
-    do {
-        // (a copy that never completes would otherwise hang the device: fail the launch instead)
-        if (++tries > (1u << 24)) __trap();
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (done == 0);
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 
 // ---- pattern rows -----------------------------------------------------------------------------------------------------
-// A thread reads its own pattern row a chunk of four nodes at a time and always has the next chunk in flight (the
-// rows of a sorted batch are scattered over HBM; this is the one load that pays DRAM latency, and nothing depends on
-// it for four nodes). The loads bypass L1 (every byte is used once) and ask L2 to fetch the whole row on first touch.
+// A thread reads its own pattern row one 32-byte sector at a time and always has the next sector in flight (the rows
+// of a sorted batch are scattered over HBM: this is the one load of the loop that pays DRAM latency, and nothing
+// depends on it for a whole chunk). The loads bypass L1 (every byte is used once) and ask L2 for the whole row on
+// first touch. The nodes of the current chunk live in the thread's own column of a small shared array (word j of
+// thread t at [j][t]: every lane always hits its own bank), so that node(i) is one conflict-free shared load however
+// i moves -- with the chunk in registers the select by i & 3 compiled to branches that split the warp.
 
 template <class T>
 struct RowReader;
 
+// 64-bit nodes: chunks of 4. A chunk with a node that does not fit 32 bits fails as a whole (the caller defers the query
+// to the general kernel, which looks at the nodes one by one).
 template <>
 struct RowReader<uint64_t> {
     const uint64_t* p;
-    uint32_t k, base;
-    uint32_t c0, c1, c2, c3, bad;
+    uint32_t k, base, slot, stride;  // slot: shared address of this thread's column, stride: bytes between its words
     uint64_t n0, n1, n2, n3;
-    bool vec;
+    bool bad, vec;
     __device__ __forceinline__ void fetch(uint32_t b) {
         n0 = n1 = n2 = n3 = 0;
         if (b >= k) return;
@@ -91,59 +85,81 @@ struct RowReader<uint64_t> {
             if (b + 3 < k) n3 = __ldg(p + b + 3);
         }
     }
-    __device__ __forceinline__ RowReader(const uint64_t* row, uint32_t len)
-        : p(row), k(len), base(0xFFFFFFFFu), c0(0), c1(0), c2(0), c3(0), bad(0), vec((reinterpret_cast<uintptr_t>(row) & 31) == 0) {
+    __device__ __forceinline__ RowReader(const uint64_t* row, uint32_t len, uint32_t slot_addr, uint32_t stride_bytes)
+        : p(row), k(len), base(0xFFFFFFFFu), slot(slot_addr), stride(stride_bytes), bad(false), vec((reinterpret_cast<uintptr_t>(row) & 31) == 0) {
         fetch(0);
     }
-    // nodes are asked for in increasing order of i; false = the node does not fit 32 bits (it cannot be in the index)
+    // nodes are asked for in non-decreasing chunk order; false = some node of the chunk does not fit 32 bits
     __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
         const uint32_t b = i & ~3u;
         if (b != base) {
             base = b;
-            c0 = static_cast<uint32_t>(n0); c1 = static_cast<uint32_t>(n1);
-            c2 = static_cast<uint32_t>(n2); c3 = static_cast<uint32_t>(n3);
-            bad = ((n0 >> 32) != 0 ? 1u : 0u) | ((n1 >> 32) != 0 ? 2u : 0u) | ((n2 >> 32) != 0 ? 4u : 0u) | ((n3 >> 32) != 0 ? 8u : 0u);
+            sts32(slot, static_cast<uint32_t>(n0)); sts32(slot + stride, static_cast<uint32_t>(n1));
+            sts32(slot + 2 * stride, static_cast<uint32_t>(n2)); sts32(slot + 3 * stride, static_cast<uint32_t>(n3));
+            bad = ((n0 | n1 | n2 | n3) >> 32) != 0;
             fetch(b + 4);
         }
-        const uint32_t j = i & 3u;
-        out = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
-        return ((bad >> j) & 1u) == 0;
+        out = lds32(slot + (i & 3u) * stride);
+        return !bad;
     }
 };
 
+// 32-bit nodes: one 32-byte sector (8 nodes) per load, handed to the shared column four at a time like the 64-bit
+// reader (a first version with 16-byte loads made L2 fetch every row several times: 27.6 GB of DRAM reads per 2^25
+// queries instead of 7.7).
 template <>
 struct RowReader<uint32_t> {
     const uint32_t* p;
-    uint32_t k, base;
-    uint32_t c0, c1, c2, c3;
-    uint32_t n0, n1, n2, n3;
+    uint32_t k, base, slot, stride;
+    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;  // the sector that holds chunk `base` (or, before the first call, node 0)
     bool vec;
     __device__ __forceinline__ void fetch(uint32_t b) {
-        n0 = n1 = n2 = n3 = 0;
+        n0 = n1 = n2 = n3 = n4 = n5 = n6 = n7 = 0;
         if (b >= k) return;
-        if (vec && k - b >= 4) {
-            asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3) : "l"(p + b));
+        if (vec && k - b >= 8) {
+            asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3), "=r"(n4), "=r"(n5), "=r"(n6), "=r"(n7) : "l"(p + b));
         } else {
             n0 = __ldg(p + b);
             if (b + 1 < k) n1 = __ldg(p + b + 1);
             if (b + 2 < k) n2 = __ldg(p + b + 2);
             if (b + 3 < k) n3 = __ldg(p + b + 3);
+            if (b + 4 < k) n4 = __ldg(p + b + 4);
+            if (b + 5 < k) n5 = __ldg(p + b + 5);
+            if (b + 6 < k) n6 = __ldg(p + b + 6);
+            if (b + 7 < k) n7 = __ldg(p + b + 7);
         }
     }
-    __device__ __forceinline__ RowReader(const uint32_t* row, uint32_t len)
-        : p(row), k(len), base(0xFFFFFFFFu), c0(0), c1(0), c2(0), c3(0), vec((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    __device__ __forceinline__ RowReader(const uint32_t* row, uint32_t len, uint32_t slot_addr, uint32_t stride_bytes)
+        : p(row), k(len), base(0xFFFFFFFFu), slot(slot_addr), stride(stride_bytes), vec((reinterpret_cast<uintptr_t>(row) & 31) == 0) {
         fetch(0);
     }
+    // chunks are visited in order, none skipped (the search loop advances by at most two nodes)
     __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
         const uint32_t b = i & ~3u;
         if (b != base) {
             base = b;
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-            fetch(b + 4);
+            if ((b & 4u) == 0) {
+                sts32(slot, n0); sts32(slot + stride, n1); sts32(slot + 2 * stride, n2); sts32(slot + 3 * stride, n3);
+            } else {
+                sts32(slot, n4); sts32(slot + stride, n5); sts32(slot + 2 * stride, n6); sts32(slot + 3 * stride, n7);
+                fetch(b + 4);  // the next sector, four nodes early
+            }
         }
-        const uint32_t j = i & 3u;
-        out = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+        out = lds32(slot + (i & 3u) * stride);
         return true;
+    }
+};
+
+// Pattern reader of the kernels that keep the chunk in registers (the general loop for deferred queries and the plain
+// 32-bit kernels): same interface, no shared memory.
+template <class T>
+struct PlainRowReader {
+    const T* p;
+    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
+        const uint64_t v = __ldg(p + i);
+        out = static_cast<uint32_t>(v);
+        return (v >> 32) == 0;
     }
 };
 
@@ -152,31 +168,32 @@ __device__ __forceinline__ uint64_t first_node(const uint64_t* patterns, size_t 
 __device__ __forceinline__ uint64_t first_node(const uint32_t* patterns, size_t q, size_t k) { return __ldg(patterns + q * k); }
 
 // ---- the staged window -----------------------------------------------------------------------------------------------
+// What a CTA decodes into shared memory for the records [lo, lo + count) -- once per window, used by ~3 queries per
+// record times 16 steps. Arranged for the loop, not like the global layout (reading the 32-byte global records in
+// place put every 16-byte access on one of four bank groups: 13 wavefronts per LDS.128 instead of 4, see
+// profiles/r2_find_window_v1_tma_raw_layout_ncu.txt):
+//   hot[r]   16 B  {node0, node1, total_len, kind}: kind = word index of the record's bitvector in `words` for a dense
+//                  record, or KIND_SINGLE / KIND_EMPTY / KIND_DEFER (run-length body, outdegree > 2, body not staged)
+//   pair[r]  16 B  the two-hop shortcut {landing node, offset} per edge (layout.h, IndexView::skips), as in HBM
+//   offs[r]   8 B  {offset0, offset1}: only read when a step cannot take the shortcut
+//   words[]   8 B  {ones before this word, 32 bits}: rank at position p of a record is ONE 8-byte load at kind + p / 32
+//                  (the 192-bit blocks of the global layout hold 6 such words each, so p / 32 needs no block arithmetic)
+constexpr uint32_t KIND_SINGLE = 0xFFFFFFFFu, KIND_EMPTY = 0xFFFFFFFEu, KIND_DEFER = 0xFFFFFFFDu;  // anything below: dense
 
 struct Staged {
-    const uint4* desc;   // two per record: {total_len, meta, node0, offset0}, {body, body_len, node1, offset1}
-    const uint2* skip;   // two per record: {landing node, offset} over edge 0 and over edge 1
-    const uint4* body;   // 16-byte units, the first one is unit `body_lo` of IndexView::bodies
-    uint32_t lo, count;  // staged records [lo, lo + count)
-    uint32_t body_lo, body_units;
+    uint32_t hot, pair, offs, words;  // shared-space addresses
+    uint32_t lo, count;               // staged records [lo, lo + count)
 };
 
-// rank1 of position p inside a dense body that starts at staged unit `unit0`, and the bit at p (layout.h: 32-byte
-// blocks {ones_before, c0 | c1 << 8, 192 bits}): the block header and ONE 64-bit word, both 8-byte shared loads.
-__device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t unit0, uint32_t p, uint32_t& bit) {
-    const uint32_t blk = __umulhi(p, 0xAAAAAAABu) >> 7;  // p / 192
-    const uint32_t r = p - blk * DENSE_BITS;
-    const uint32_t j = r >> 6, sh = r & 63u;
-    const uint2* block = reinterpret_cast<const uint2*>(st.body + unit0 + 2u * blk);
-    const uint2 hdr = block[0];
-    const uint2 w = block[1 + j];
-    const uint64_t word = (static_cast<uint64_t>(w.y) << 32) | w.x;
-    const uint32_t sub = ((hdr.y << 8) >> (8u * j)) & 0xFFu;  // 0, c0, c1
-    bit = static_cast<uint32_t>(word >> sh) & 1u;
-    return hdr.x + sub + static_cast<uint32_t>(__popcll(word & ((1ull << sh) - 1ull)));
-}
-
 enum : int { QUERY_DONE = 0, QUERY_DEFER = 1 };
+
+// rank1(p) and the bit at p of the dense record whose first word is `kind`
+__device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind, uint32_t p, uint32_t& bit) {
+    const uint2 w = lds64(st.words + 8u * (kind + (p >> 5)));
+    const uint32_t sh = p & 31u;
+    bit = (w.y >> sh) & 1u;
+    return w.x + static_cast<uint32_t>(__popc(w.y & ((1u << sh) - 1u)));
+}
 
 // One query against the staged window. QUERY_DONE: `out` holds the reference's answer. QUERY_DEFER: the window could
 // not decide; the general kernel redoes the query from the start.
@@ -185,71 +202,74 @@ __device__ __forceinline__ int window_query(const Staged& st, uint32_t base, Rea
     set_none(out);
     if (k == 0) return QUERY_DONE;
     uint32_t x;
-    if (!rd.node(0, x)) return QUERY_DONE;  // GBWT::find: not a node of the index
+    if (!rd.node(0, x)) return QUERY_DEFER;
     uint32_t idx = x - base - st.lo;
     if (idx >= st.count || idx + st.lo == 0) return QUERY_DEFER;  // (record 0 is the endmarker: find() is None; let the general code say so)
-    uint4 da = st.desc[2u * idx];
-    uint32_t start = 0, end = da.x, node = x;
-    uint32_t fmt = (da.y >> 16) & 0xFFu;
-    if (fmt == FMT_EMPTY || end == 0) return QUERY_DONE;
+    uint4 h = lds128(st.hot + 16u * idx);
+    uint32_t start = 0, end = h.z, node = x;
+    if (h.w == KIND_DEFER) return QUERY_DEFER;
+    if (h.w == KIND_EMPTY || end == 0) return QUERY_DONE;  // GBWT::find: no record
     uint32_t i = 1;
     while (i < k) {
         uint32_t x1;
-        if (!rd.node(i, x1) || x1 == 0) return QUERY_DONE;  // GBWT::extend: below first_node / not an edge target
-        const uint32_t total = da.x;
+        if (!rd.node(i, x1)) return QUERY_DEFER;
+        if (x1 == 0) return QUERY_DONE;  // GBWT::extend: below first_node
+        const uint32_t total = h.z, kind = h.w;
         const uint32_t s = start < total ? start : total, e = end < total ? end : total;
         if (s >= e) return QUERY_DONE;
-        uint32_t b, edge_offset, rs, re;
-        if (fmt == FMT_SINGLE) {
-            if (x1 != da.z) return QUERY_DONE;
-            b = 0; edge_offset = da.w; rs = s; re = e;
-        } else if (fmt == FMT_DENSE2) {
-            const uint4 db = st.desc[2u * idx + 1u];
-            if (x1 == da.z) { b = 0; edge_offset = da.w; }
-            else if (x1 == db.z) { b = 1; edge_offset = db.w; }
+        uint32_t b = 0, rs = s, re = e;
+        if (kind == KIND_SINGLE) {
+            if (x1 != h.x) return QUERY_DONE;
+        } else if (kind < KIND_DEFER) {
+            if (x1 == h.x) b = 0;
+            else if (x1 == h.y) b = 1;
             else return QUERY_DONE;
-            const uint32_t unit0 = db.x - st.body_lo;
-            const uint32_t last_blk = __umulhi(e - 1u, 0xAAAAAAABu) >> 7;
-            if (unit0 + 2u * last_blk + 2u > st.body_units) return QUERY_DEFER;  // the body did not fit the window
             // rank1(s), and rank1(e) = rank1(e - 1) + bit(e - 1); a range of one position needs one lookup
             uint32_t bit;
-            const uint32_t ones_s = staged_rank1(st, unit0, s, bit);
+            const uint32_t ones_s = staged_rank1(st, kind, s, bit);
             uint32_t ones_e = ones_s + bit;
-            if (e - 1u != s) { ones_e = staged_rank1(st, unit0, e - 1u, bit); ones_e += bit; }
+            if (e - 1u != s) { ones_e = staged_rank1(st, kind, e - 1u, bit); ones_e += bit; }
             rs = b ? ones_s : s - ones_s;
             re = b ? ones_e : e - ones_e;
             if (rs >= re) return QUERY_DONE;
-        } else if (fmt == FMT_EMPTY) {
+        } else if (kind == KIND_EMPTY) {
             return QUERY_DONE;  // BWT::record() is None
         } else {
-            return QUERY_DEFER;  // run-length body or outdegree > 2
+            return QUERY_DEFER;
         }
         // two hops at once when the successor is a single-edge record leading to the pattern node after x1
+        const uint2 hop = lds64(st.pair + 16u * idx + 8u * b);
         bool hopped = false;
-        if (i + 1 < k) {
-            const uint2 sk = st.skip[2u * idx + b];
+        if (i + 1 < k && hop.x != 0) {
             uint32_t x2;
-            if (sk.x != 0 && rd.node(i + 1, x2) && x2 == sk.x) {
-                start = sk.y + rs; end = sk.y + re;
+            if (!rd.node(i + 1, x2)) return QUERY_DEFER;
+            if (x2 == hop.x) {
+                start = hop.y + rs; end = hop.y + re;
                 node = x2; i += 2;
                 hopped = true;
             }
         }
         if (!hopped) {
+            const uint32_t edge_offset = lds32(st.offs + 8u * idx + 4u * b);
             start = edge_offset + rs; end = edge_offset + re;
             node = x1; i += 1;
         }
         if (i >= k) break;
         idx = node - base - st.lo;
         if (idx >= st.count) return QUERY_DEFER;
-        da = st.desc[2u * idx];
-        fmt = (da.y >> 16) & 0xFFu;
+        h = lds128(st.hot + 16u * idx);
     }
     out.node = node; out.start = start; out.end = end;
     return QUERY_DONE;
 }
 
-constexpr uint32_t SMEM_HEADER = 128;  // mbarrier + control words, keeps the staged arrays 128-byte aligned
+constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
+constexpr uint32_t PATTERN_WORDS = 4;  // words of the pattern column per thread (RowReader::CHUNK)
+
+// Bytes of shared memory a plan needs.
+__host__ __device__ inline uint32_t window_smem_bytes(uint32_t max_records, uint32_t body_cap, uint32_t threads) {
+    return SMEM_HEADER + max_records * 40u + (body_cap / 2u) * 48u + threads * PATTERN_WORDS * 4u;
+}
 
 template <class T, int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, WindowPlan wp, const T* __restrict__ patterns,
@@ -257,15 +277,15 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
                                                                 uint32_t k, gbwt_b200_state* __restrict__ out,
                                                                 uint32_t* __restrict__ deferred, uint32_t* __restrict__ counters) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem + 16);  // [0] window ticket, [1] next query slot
-    uint4* s_desc = reinterpret_cast<uint4*>(smem + SMEM_HEADER);
-    uint4* s_skip = s_desc + 2u * wp.max_records;
-    uint4* s_body = s_skip + wp.max_records;
+    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem);  // [0] window ticket, [1] next query slot
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
-    if (tid == 0) mbar_init(bar, 1);
-    uint32_t parity = 0;
+    Staged st;
+    st.hot = smem_addr(smem) + SMEM_HEADER;
+    st.pair = st.hot + 16u * wp.max_records;
+    st.offs = st.pair + 16u * wp.max_records;
+    st.words = st.offs + 8u * wp.max_records;
+    const uint32_t pattern_slot = st.words + (wp.body_cap / 2u) * 48u + 4u * tid;
     for (;;) {
         __syncthreads();  // everybody has left the previous window: its shared memory and ctrl[] may be reused
         if (tid == 0) ctrl[0] = atomicAdd(&counters[0], 1u);
@@ -275,25 +295,46 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1), q_end = __ldg(bucket_end + w);
         if (q_begin >= q_end) continue;
         const uint32_t r0 = w << wp.wshift;
-        Staged st;
         st.lo = r0 > wp.margin ? r0 - wp.margin : 0u;
         const uint32_t want_hi = r0 + (1u << wp.wshift) + wp.margin;
         const uint32_t hi = want_hi < records ? want_hi : records;
         st.count = hi - st.lo;
-        st.body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
+        const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
         const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
-        st.body_units = body_hi - st.body_lo < wp.body_cap ? body_hi - st.body_lo : wp.body_cap;
-        st.desc = s_desc; st.skip = reinterpret_cast<const uint2*>(s_skip); st.body = s_body;
-        if (tid == 0) {
-            ctrl[1] = q_begin;
-            mbar_expect_tx(bar, st.count * 48u + st.body_units * 16u);
-            bulk_global_to_shared(s_desc, ix.desc + st.lo, st.count * 32u, bar);
-            bulk_global_to_shared(s_skip, ix.skips + st.lo, st.count * 16u, bar);
-            if (st.body_units != 0) bulk_global_to_shared(s_body, ix.bodies + st.body_lo, st.body_units * 16u, bar);
+        const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
+        if (tid == 0) ctrl[1] = q_begin;
+        // decode the window into shared memory: descriptors + shortcuts ...
+        for (uint32_t r = tid; r < st.count; r += THREADS) {
+            Desc d;
+            load_sector(reinterpret_cast<const Unit16*>(ix.desc + st.lo + r), d.a, d.b);
+            const Quad skip = load_quad(ix.skips + st.lo + r);
+            const uint32_t fmt = d.fmt();
+            uint32_t kind = KIND_DEFER, node1 = 0;
+            if (fmt == FMT_SINGLE) kind = KIND_SINGLE;
+            else if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
+            else if (fmt == FMT_DENSE2) {
+                const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
+                if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units) { kind = (unit0 / 2u) * 6u; node1 = d.node1(); }
+            }
+            sts128(st.hot + 16u * r, d.node0(), node1, fmt == FMT_EMPTY ? 0u : d.total_len(), kind);
+            sts128(st.pair + 16u * r, skip.x, skip.y, skip.z, skip.w);
+            sts64(st.offs + 8u * r, d.offset0(), d.offset1());
         }
-        __syncthreads();  // ctrl[1] is set
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+        // ... and the dense blocks as {ones before, 32 bits} words
+        for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
+            Quad lo, hi;
+            load_sector(ix.bodies + body_lo + 2u * blk, lo, hi);
+            const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            uint32_t ones = lo.x;
+            const uint32_t at = st.words + 48u * blk;
+#pragma unroll
+            for (uint32_t j = 0; j < 6; j += 2) {
+                const uint32_t next = ones + static_cast<uint32_t>(__popc(bits[j]));
+                sts128(at + 8u * j, ones, bits[j], next, bits[j + 1]);
+                ones = next + static_cast<uint32_t>(__popc(bits[j + 1]));
+            }
+        }
+        __syncthreads();
         // the window's queries, 32 at a time per warp
         for (;;) {
             uint32_t slot = 0;
@@ -303,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
             const uint32_t at = slot + lane;
             if (at < q_end) {
                 const uint32_t q = __ldg(perm + at);
-                RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k);
+                RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k, pattern_slot, 4u * THREADS);
                 gbwt_b200_state result;
                 if (window_query(st, base, rd, k, result) == QUERY_DONE) store_state(out + q, result);
                 else deferred[atomicAdd(&counters[1], 1u)] = q;
@@ -320,7 +361,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_deferred(IndexView ix, c
     const uint32_t n = counters[1];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t q = __ldg(deferred + i);
-        RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k);
+        PlainRowReader<T> rd{patterns + static_cast<size_t>(q) * k};
         gbwt_b200_state result;
         query_find_extend_rounds<true>(ix, rd, k, result);
         store_state(out + q, result);
@@ -346,7 +387,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_extend_u32(IndexView ix,
                                                                     gbwt_b200_state* __restrict__ out) {
     GBWT_FOR_EACH_QUERY(q, n, perm) {
         gbwt_b200_state result;
-        RowReader<uint32_t> rd(patterns + q * k, static_cast<uint32_t>(k));
+        PlainRowReader<uint32_t> rd{patterns + q * k};
         query_find_extend_rounds<RUNS>(ix, rd, static_cast<uint32_t>(k), result);
         store_state(out + q, result);
     }
@@ -373,29 +414,29 @@ int launch_window_variant(const IndexView& ix, const WindowPlan& plan, const T* 
 
 bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
     if (!ix.edges_valid || ix.records < 2 || ix.stage_body == nullptr) return false;
-    // Shared memory per CTA (two CTAs of 512 threads per SM by default): what is left after descriptors and
-    // shortcuts (48 bytes per staged record) holds the bodies.
+    // Shared memory per CTA (two CTAs of 512 threads per SM by default): 40 bytes per staged record, the pattern
+    // columns, and what is left holds the bitvectors (48 bytes per 32-byte block of the global layout).
     const uint32_t threads = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_THREADS", 512));
-    const uint32_t smem_kb = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_SMEM_KB", threads >= 1024 ? 200 : (threads >= 512 ? 100 : 50)));
+    const uint32_t smem_kb = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_SMEM_KB", threads >= 1024 ? 224 : (threads >= 512 ? 112 : 55)));
     uint32_t window = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW", threads >= 1024 ? 1024 : (threads >= 512 ? 512 : 256)));
-    uint32_t margin = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_MARGIN", 128));
+    uint32_t margin = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_MARGIN", threads >= 1024 ? 128 : 96));
     if (threads != 256 && threads != 512 && threads != 1024) return false;
-    if (window < STAGE_GRANULE || (window & (window - 1)) != 0 || smem_kb > 227 || smem_kb < 16) return false;
+    if (window < STAGE_GRANULE || (window & (window - 1)) != 0 || smem_kb > 226 || smem_kb < 16) return false;
     margin = (margin + STAGE_GRANULE - 1) / STAGE_GRANULE * STAGE_GRANULE;
     plan.wshift = 0;
     while ((1u << plan.wshift) < window) plan.wshift++;
     plan.margin = margin;
     plan.max_records = window + 2 * margin;
-    const uint64_t fixed = SMEM_HEADER + static_cast<uint64_t>(plan.max_records) * 48;
+    const uint64_t fixed = window_smem_bytes(plan.max_records, 0, threads);
     const uint64_t budget = static_cast<uint64_t>(smem_kb) * 1024;
     if (fixed + 4096 > budget) return false;
-    plan.body_cap = static_cast<uint32_t>((budget - fixed) / 16);
+    plan.body_cap = static_cast<uint32_t>((budget - fixed) / 48) * 2;
     // no point in reserving more than the average window needs several times over
     const uint64_t avg_units = body_units * plan.max_records / std::max<uint64_t>(1, ix.records);
-    plan.body_cap = static_cast<uint32_t>(std::min<uint64_t>(plan.body_cap, std::max<uint64_t>(256, 4 * avg_units + 64)));
+    plan.body_cap = static_cast<uint32_t>(std::min<uint64_t>(plan.body_cap, std::max<uint64_t>(256, 4 * avg_units + 64))) & ~1u;
     plan.windows = static_cast<uint32_t>(((ix.records - 1) >> plan.wshift) + 1);
     plan.threads = threads;
-    plan.smem_bytes = static_cast<uint32_t>(fixed + static_cast<uint64_t>(plan.body_cap) * 16);
+    plan.smem_bytes = window_smem_bytes(plan.max_records, plan.body_cap, threads);
     return true;
 }
 

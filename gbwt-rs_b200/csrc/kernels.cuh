@@ -1247,87 +1247,132 @@ struct CheckpointView {
     uint32_t max_segments;     // most checkpoints any sequence has
 };
 
-// Nodes [index, end) of a sequence by one lane, starting from a known position: Record::lf (src/bwt.rs:480-496) per
-// step, two nodes per step where the two-hop shortcut applies (layout.h). Writes out[i] for i < cap.
+// Work item (segment j, block of 32 batch entries): lane l walks segment j of sequence ids[32 * block + l] from its
+// checkpoint to the next one (or to the end of the sequence): Record::lf (src/bwt.rs:480-496) per step, two nodes per
+// step where the two-hop shortcut applies (layout.h). Items are ordered by segment number first, so the CTAs running at
+// any moment are all in the same part of the graph.
+//
+// Output: a first version stored every node straight from its lane, 8 bytes to 32 different rows per instruction. ncu
+// (profiles/r2_extract_checkpointed_v1_ncu.txt): 1.7 G partial-sector writes churn through L2, evict the index (L2 read
+// hit rate 18 %) and the walks wait on DRAM for every record -- 39 G LF steps/s. Now every lane parks its nodes in a row
+// of a shared-memory tile, and when a row is nearly full the warp writes all rows out, half a warp per row: 128
+// contiguous bytes per row with streaming stores, so L2 sees whole sectors that it need not keep.
+constexpr uint32_t TILE_NODES = 16, TILE_STRIDE = 17;  // nodes per lane between flushes; row stride in 8-byte words
+
 template <bool CHECKED>
-__device__ __forceinline__ void walk_segment_lane(const IndexView& ix, uint32_t node, uint32_t offset, uint64_t index, uint64_t end,
-                                                  uint64_t* __restrict__ out, uint64_t cap) {
+__global__ void __launch_bounds__(BLOCK_THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
+                                                                         size_t m, const uint64_t* __restrict__ out_offsets, uint64_t base_offset,
+                                                                         uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ uint64_t tiles[BLOCK_THREADS / 32][32][TILE_STRIDE];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t (*tile)[TILE_STRIDE] = tiles[threadIdx.x >> 5];
     const RecordDesc* const descs = ix.desc;
     const Unit16* const bodies = ix.bodies;
     const Unit16* const skips = ix.skips;
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
-    while (index < end) {
-        if (index < cap) out[index] = node;
-        uint32_t rec = node - base;
-        if (CHECKED) { if (rec - 1u >= records - 1u) break; }
-        else rec = rec < records ? rec : records - 1u;
-        Desc d;
-        load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
-        const Quad k = load_quad(skips + rec);
-        const uint32_t fmt = d.fmt(), i = offset;
-        if (i >= d.total_len()) break;  // GBWT::forward -> None (an empty record has length 0)
-        uint32_t b = 0, r = i;
-        if (fmt == FMT_DENSE2) {
-            const uint32_t blk = __umulhi(i, 0xAAAAAAABu) >> 7;  // i / 192
-            Quad lo, hi;
-            load_sector(bodies + d.body() + 2u * blk, lo, hi);
-            const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, b);
-            r = b ? ones : i - ones;
-        } else if (fmt != FMT_SINGLE) {
-            const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, i);
-            if (next == 0) break;
-            node = static_cast<uint32_t>(next); offset = static_cast<uint32_t>(next >> 32);
-            index++;
-            continue;
-        }
-        const uint32_t v = b ? d.node1() : d.node0();
-        if (v == 0) break;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
-        const uint32_t w = b ? k.z : k.x;
-        if (w != 0) {
-            if (index + 1 < end && index + 1 < cap) out[index + 1] = v;
-            node = w; offset = (b ? k.w : k.y) + r;
-            index += 2;
-        } else {
-            node = v; offset = (b ? d.offset1() : d.offset0()) + r;
-            index += 1;
-        }
-    }
-}
-
-// Work item (segment j, block of 32 batch entries): lane l walks segment j of sequence ids[32 * block + l]. Items are
-// ordered by segment number first, so the CTAs running at any moment are all in the same part of the graph.
-template <bool CHECKED>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
-                                                                         size_t m, const uint64_t* __restrict__ out_offsets, uint64_t base,
-                                                                         uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
-    const uint32_t lane = threadIdx.x & 31u;
     const uint64_t blocks = (m + 31) / 32;
     const uint64_t items = blocks * cv.max_segments;
     const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) / 32;
     for (uint64_t item = warp; item < items; item += warps) {
         const uint64_t j = item / blocks, i = (item - j * blocks) * 32 + lane;
-        if (i >= m) continue;
-        const uint64_t id = __ldg(ids + i);
-        if (id >= ix.sequences) {
-            if (j == 0 && lengths != nullptr) lengths[i] = ~0ull;  // GBWT::sequence() is None
-            continue;
+        // this lane's segment, if it has one
+        bool active = false;
+        uint32_t node = 0, offset = 0;
+        uint64_t index = 0, end = 0, cap = 0;
+        uint64_t* dst = nodes;
+        if (i < m) {
+            const uint64_t id = __ldg(ids + i);
+            if (id >= ix.sequences) {
+                if (j == 0 && lengths != nullptr) lengths[i] = ~0ull;  // GBWT::sequence() is None
+            } else {
+                const uint64_t len = cv.seq_len[id];
+                if (j == 0 && lengths != nullptr) lengths[i] = len;
+                const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
+                if (j < count) {
+                    const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+                    cap = hi > lo ? hi - lo : 0;
+                    dst = nodes + (lo - base_offset);
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j));
+                    node = raw.x; offset = raw.y;
+                    index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
+                    end = len;
+                    if (j + 1 < count) {
+                        const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j + 1));
+                        end = (static_cast<uint64_t>(next.w) << 32) | next.z;
+                    }
+                    if (end > cap) end = cap;  // nothing beyond the caller's slot is written
+                    active = index < end;
+                }
+            }
         }
-        const uint64_t len = cv.seq_len[id];
-        if (j == 0 && lengths != nullptr) lengths[i] = len;
-        const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
-        if (j >= count) continue;
-        const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
-        const uint64_t cap = hi > lo ? hi - lo : 0;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j));
-        const uint64_t index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
-        uint64_t end = len;
-        if (j + 1 < count) {
-            const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j + 1));
-            end = (static_cast<uint64_t>(next.w) << 32) | next.z;
+        uint32_t parked = 0;          // nodes in this lane's row of the tile
+        uint64_t row_start = index;   // sequence index of the first of them
+        for (;;) {
+            if (active) {
+                tile[lane][parked++] = node;
+                uint32_t rec = node - base;
+                bool go = true;
+                if (CHECKED) go = rec - 1u < records - 1u;
+                else rec = rec < records ? rec : records - 1u;
+                if (go) {
+                    Desc d;
+                    load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
+                    const Quad k = load_quad(skips + rec);
+                    const uint32_t fmt = d.fmt(), at = offset;
+                    if (at >= d.total_len()) {
+                        go = false;  // GBWT::forward -> None (an empty record has length 0)
+                    } else if (fmt == FMT_SINGLE || fmt == FMT_DENSE2) {
+                        uint32_t b = 0, r = at;
+                        if (fmt == FMT_DENSE2) {
+                            const uint32_t blk = __umulhi(at, 0xAAAAAAABu) >> 7;  // at / 192
+                            Quad lo, hi;
+                            load_sector(bodies + d.body() + 2u * blk, lo, hi);
+                            const uint32_t ones = dense_block_rank_lean(lo, hi, at - blk * DENSE_BITS, b);
+                            r = b ? ones : at - ones;
+                        }
+                        const uint32_t v = b ? d.node1() : d.node0();
+                        const uint32_t w = b ? k.z : k.x;
+                        if (v == 0) {
+                            go = false;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+                        } else if (w != 0) {
+                            if (index + 1 < end) tile[lane][parked++] = v;
+                            node = w; offset = (b ? k.w : k.y) + r;
+                            index += 2;
+                        } else {
+                            node = v; offset = (b ? d.offset1() : d.offset0()) + r;
+                            index += 1;
+                        }
+                    } else {
+                        const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, at);
+                        if (next == 0) go = false;
+                        node = static_cast<uint32_t>(next); offset = static_cast<uint32_t>(next >> 32);
+                        index += 1;
+                    }
+                }
+                active = go && index < end;
+            }
+            const bool any_active = __any_sync(FULL, active);
+            if (__any_sync(FULL, parked + 2 > TILE_NODES) || !any_active) {
+                // all rows out, half a warp per row: lanes 0-15 row 2p, lanes 16-31 row 2p + 1
+                __syncwarp();
+                const uint64_t row_addr = reinterpret_cast<uint64_t>(dst + row_start);
+                const uint32_t t = lane & 15u;
+#pragma unroll 4
+                for (uint32_t p = 0; p < 16; p++) {
+                    const uint32_t row = 2u * p + (lane >> 4);
+                    const uint32_t n = __shfl_sync(FULL, parked, row);
+                    const uint32_t a_lo = __shfl_sync(FULL, static_cast<uint32_t>(row_addr), row);
+                    const uint32_t a_hi = __shfl_sync(FULL, static_cast<uint32_t>(row_addr >> 32), row);
+                    if (t < n) __stcs(reinterpret_cast<uint64_t*>((static_cast<uint64_t>(a_hi) << 32) | a_lo) + t, tile[row][t]);
+                }
+                __syncwarp();
+                row_start += parked;
+                parked = 0;
+                if (!any_active) break;
+            }
         }
-        if (index >= cap) continue;
-        walk_segment_lane<CHECKED>(ix, raw.x, raw.y, index, end, nodes + (lo - base), cap);
     }
 }
 
