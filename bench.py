@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=500_000, help="queries in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extract", action="store_true", help="skip the configs[4] extraction inside the default run")
     return ap.parse_args()
 
 
@@ -197,7 +198,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "gbwt_find_queries_per_s_k32", "value": base["value"], "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, sites, haplotypes, args.cpu_sample, "cpu"),
+        "config": dict(workload_config(args, sites, haplotypes, args.cpu_sample, "cpu"),
+                       note=f"a rate: every step times a bounded sample of {args.cpu_sample} queries of the same workload (same index, same "
+                            "pattern generator) against the GPU arm's 2^26 per GPU per step"),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread_us_per_query",
                                               "single_thread_ns_per_node")},
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,6 +224,35 @@ def workload_config(args, sites, haplotypes, queries, where):
 
 
 # ---- the GPU benchmark -------------------------------------------------------------------------------------
+
+KERNEL_SOURCES = ("find_window.cu", "find_window.h", "find_lean.cuh", "record_scan.cuh", "layout.h", "kernels.cuh", "cabi.cu")
+
+
+def kernel_source_hash():
+    """sha256 over the sources the timed kernels are compiled from: ties a committed ncu capture to the code it measured."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "gbwt-rs_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(kernel, queries, layout):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/find_window_traffic.json), scaled to
+    this launch's query count -- or (None, why) when the capture was taken from other sources than the ones being timed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "find_window_traffic.json")) as f:
+            prof = json.load(f)
+    except Exception as exc:
+        return None, f"no committed capture ({exc})"
+    if prof.get("kernel") != kernel or prof.get("layout") != layout:
+        return None, "the committed capture is of another kernel / layout"
+    if prof.get("source_sha16") != kernel_source_hash():
+        return None, "the committed capture was taken from other kernel sources than the ones being timed"
+    per_query = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) / prof["queries_per_launch"]
+    return per_query * queries, f"ncu dram__bytes_read+write of one launch of {prof['queries_per_launch']} queries ({prof['captured']}), scaled by queries"
+
 
 def main():
     args = parse_args()
@@ -248,6 +280,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     import gbwt_rs_b200 as gb
     from synth import synth
     ncpu = os.cpu_count() or 8
@@ -256,10 +295,12 @@ def main():
     sites, haplotypes, Q = resolve_workload(args)
     image, keep = get_image(sites, haplotypes, rank, world, barrier)
     t = time.time()
-    index = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout)
+    index = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=True)
+    build_s = time.time() - t
     stats = index.device_bytes()
+    ckpt = index.checkpoint_info()
     if rank == 0:
-        log(f"[bench] device index built in {time.time() - t:.1f} s: {stats}")
+        log(f"[bench] device index built in {build_s:.1f} s (checkpoint walk {ckpt['build_us'] / 1e6:.2f} s): {stats}")
     stream = torch.cuda.current_stream().cuda_stream
 
     if args.workload == "extract-dna":
@@ -283,25 +324,29 @@ def main():
     def step():
         index.find_extend_device(d_pat.data_ptr(), Q, K_LEN, d_out.data_ptr(), stream)
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    time.sleep(0.25)
-    launches0 = gb.kernel_launches()
-    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier(); torch.cuda.synchronize()
-    t0 = time.time()
-    events[0].record()
-    for i in range(args.steps):
-        step()
-        events[i + 1].record()
-    torch.cuda.synchronize(); barrier()
-    t1 = time.time()
-    launches = gb.kernel_launches() - launches0
-    clocks = sampler.stop(t0, t1)
-    step_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
-    total_ms = max_over_ranks(events[0].elapsed_time(events[-1]))
+    def timed_steps(fn, steps, warmup):
+        """`steps` calls of fn bracketed by barrier + synchronize; returns (max-over-ranks total ms, per-step ms, clocks, launches)."""
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        time.sleep(0.25)
+        launches0 = gb.kernel_launches()
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier(); torch.cuda.synchronize()
+        t0 = time.time()
+        events[0].record()
+        for i in range(steps):
+            fn()
+            events[i + 1].record()
+        torch.cuda.synchronize(); barrier()
+        t1 = time.time()
+        launches = gb.kernel_launches() - launches0
+        clocks = sampler.stop(t0, t1)
+        per_step = [events[i].elapsed_time(events[i + 1]) for i in range(steps)]
+        return max_over_ranks(events[0].elapsed_time(events[-1])), per_step, clocks, launches
+
+    total_ms, step_ms, clocks, launches = timed_steps(step, args.steps, args.warmup)
     value = Q * world * args.steps / (total_ms / 1e3)
 
     # size-independent parity properties on the full batch (every sampled pattern occurs; state.node = last node)
@@ -309,33 +354,35 @@ def main():
     checksum = int((d_out[:, 2] - d_out[:, 1]).sum().item())
     if not ok:
         raise SystemExit("parity property violated: a sampled pattern was not found")
+    want_out = d_out.clone()
 
-    # end to end through the host C ABI with pinned buffers (H2D + kernel + D2H inside the timed region)
+    # the dominant kernel alone (CUDA events around its launch inside the library, GBWT_B200_WINDOW_STATS=1; these
+    # three steps are outside the timed region because reading the counters synchronises the stream)
+    os.environ["GBWT_B200_WINDOW_STATS"] = "1"
+    w0 = index.window_info()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    w1 = index.window_info()
+    del os.environ["GBWT_B200_WINDOW_STATS"]
+    win_launches = w1["launches"] - w0["launches"]
+    kernel_ms = (w1["kernel_ns"] - w0["kernel_ns"]) / 1e6 / win_launches if win_launches else None
+    deferred = (w1["deferred"] - w0["deferred"]) // 3 if win_launches else None
+
+    # the same batch as 32-bit node identifiers (gbwt_b200_find_extend_u32_device): half the pattern bytes
+    d_pat32 = d_pat.to(torch.int32)
+    u32_ms, u32_steps, _, _ = timed_steps(lambda: index.find_extend_u32_device(d_pat32.data_ptr(), Q, K_LEN, d_out.data_ptr(), stream),
+                                          max(3, min(args.steps, 10)), 2)
+    if not torch.equal(d_out, want_out):
+        raise SystemExit("32-bit pattern results differ from 64-bit pattern results")
+    find_u32 = {"value": Q * world * len(u32_steps) / (u32_ms / 1e3), "unit": "queries/s", "ms_per_step": u32_ms / len(u32_steps),
+                "api": "gbwt_b200_find_extend_u32_device"}
+
+    # end to end through the host C ABI with pinned buffers (H2D + kernels + D2H inside the timed region), both widths
     e2e = None
     if not args.no_e2e:
-        Qe = min(args.e2e_queries, Q)
-        h_pat = torch.empty((Qe, K_LEN), dtype=torch.int64).pin_memory()
-        h_out = torch.empty((Qe, 3), dtype=torch.int64).pin_memory()
-        h_pat.copy_(d_pat[:Qe])
-        lib = gb.library()
-        def e2e_step():
-            rc = lib.gbwt_b200_find_extend(index._h, h_pat.data_ptr(), Qe, K_LEN, h_out.data_ptr())
-            if rc != 0:
-                raise SystemExit(f"gbwt_b200_find_extend failed: {lib.gbwt_b200_last_error().decode()}")
-        e2e_step()
-        e2e_steps = max(3, min(args.steps, 10))
-        barrier(); torch.cuda.synchronize()
-        te = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - te)
-        barrier()
-        if not torch.equal(h_out, d_out[:Qe].cpu()):
-            raise SystemExit("host-path results differ from device-path results")
-        e2e = {"value": Qe * world * e2e_steps / dt, "unit": "queries/s", "h2d_bytes_per_step": Qe * K_LEN * 8,
-               "d2h_bytes_per_step": Qe * 24, "queries_per_gpu_per_step": Qe, "steps": e2e_steps,
-               "api": "gbwt_b200_find_extend (host pointers, pinned), chunked double-buffered H2D/kernel/D2H"}
+        e2e = bench_e2e(args, index, d_pat, want_out, Q, world, local_rank, barrier, max_over_ranks, sum_over_ranks)
+    del d_pat32
 
     roofline, cpu = None, None
     if rank == 0:
@@ -350,46 +397,217 @@ def main():
         sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=q0)
         bytes_per_query = g.find_extend_bytes(sample) / sample_n
         want = g.find_extend_batch(sample)
-        got = d_out[:sample_n].cpu().numpy().view(np.uint64)
+        got = want_out[:sample_n].cpu().numpy().view(np.uint64)
         if not np.array_equal(got, want.view(np.uint64).reshape(-1, 3)):
             raise SystemExit("parity failure against the oracle on the sampled queries")
         peak, peak_src = measured_peak_gbs()
-        traffic = None
-        try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this very step
-            with open(os.path.join(ROOT, "profiles", "find_extend_traffic.json")) as f:
-                prof = json.load(f)
-            if prof["queries_per_launch"] == Q and prof["layout"] == args.layout and args.workload == "find":
-                traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-        except Exception:
-            traffic = None
-        launch_s = statistics.mean(step_ms) / 1e3
-        achieved = bytes_per_query * Q / launch_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_find_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
+        kernel = "k_find_window" if win_launches else "k_find_extend"
+        traffic, traffic_src = committed_traffic(kernel, Q, args.layout) if args.workload == "find" else (None, "not the headline workload")
+        step_s = statistics.mean(step_ms) / 1e3
+        launch_s = (kernel_ms / 1e3) if kernel_ms else step_s
+        index_once = stats["descriptors"] + stats["bodies"] + stats["edges"] + stats.get("skips", 0)
+        compulsory = Q * (K_LEN * 8 + 24) + index_once
+        roofline = {"bound": "hbm", "kernel": kernel, "unit": "GB/s", "peak": peak, "peak_source": peak_src + " (of measured)",
+                    # what the kernel really moves: measured DRAM bytes of one launch over its measured duration
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "achieved": (traffic / launch_s / 1e9) if traffic else None,
+                    "frac": (traffic / launch_s / 1e9 / peak) if traffic else None,
+                    # what it has to move at the very least: every pattern and result once, the index once
+                    "compulsory_bytes": compulsory, "compulsory_frac": compulsory / step_s / 1e9 / peak,
+                    "compulsory_frac_kernel_only": compulsory / launch_s / 1e9 / peak,
+                    # SURVEY.md 8(d) accounting on the reference's compressed records (not a bound for this layout: the dense
+                    # blocks answer a rank from 8 bytes and every record is read once per batch, so this is far above 1)
                     "algorithmic_bytes_per_query": bytes_per_query, "algorithmic_bytes_per_lf_step": bytes_per_query / K_LEN,
-                    "launch_ms": launch_s * 1e3, "launches_per_step": launches // max(1, args.steps),
-                    "note": "achieved = algorithmic bytes of SURVEY.md 8(d) (counted on the reference's compressed records: "
-                            "~330 B of a 518 B record per anchor step) / device time of the whole step (bucket pre-pass + "
-                            "k_find_extend). It exceeds the HBM peak because the work is not done by moving those bytes: the dense "
-                            "device layout answers a rank from one 32-byte block, and the locality schedule makes the batch share "
-                            "records through L1/L2, so measured DRAM traffic (`traffic`, ncu) is ~0.45 KB/query against 5.7 KB/query "
-                            "algorithmic. The kernel is bound by L1 wavefronts / latency (profiles/README.md), not by HBM"}
+                    "algorithmic_x": bytes_per_query * Q / step_s / 1e9 / peak,
+                    "launch_ms": launch_s * 1e3, "step_ms": step_s * 1e3, "launches_per_step": launches // max(1, args.steps),
+                    "deferred_queries_per_step": deferred,
+                    "note": "frac = measured DRAM bytes per launch (committed ncu capture of these kernel sources, hash-checked) / "
+                            "live CUDA-event duration of the window kernel / measured HBM copy peak; compulsory_frac = (patterns + "
+                            "results + index once) / whole step (sort + search) / peak: how far the step is from the bytes it cannot avoid"}
         log(f"[bench] oracle sample + cpu baseline took {time.time() - t:.1f} s")
+
+    # BASELINE.json configs[4] in the same run: extraction of all forward haplotype paths, partitioned by path
+    extract = None
+    if args.workload == "find" and not args.no_extract:
+        del d_pat, d_out, want_out
+        torch.cuda.empty_cache()
+        extract = bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats)
 
     if rank == 0:
         line = {
             "metric": "gbwt_find_queries_per_s_k32", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, sites, haplotypes, Q, "inputs and outputs resident in HBM"),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "extra": {"lf_steps_per_s": value * K_LEN, "occurrences_checksum": checksum, "index_device_bytes": stats,
-                      "step_ms": step_ms, "parity": "all patterns found, state.node == last node on the full batch; "
-                                                    "first 20000 queries bit-exact against the CPU oracle"},
+            "extra": {"lf_steps_per_s": value * K_LEN, "find_u32": find_u32, "extract": extract,
+                      "occurrences_checksum": checksum, "index_device_bytes": stats, "index_build_s": build_s,
+                      "checkpoints": ckpt, "window": {k: w1[k] for k in ("window_records", "margin", "threads", "smem_bytes", "windows")},
+                      "step_ms": step_ms, "arithmetic": "u64 node identifiers and offsets at the ABI, 32-bit inside the kernels "
+                                                        "(an index that does not fit is rejected at load)",
+                      "parity": "all patterns found, state.node == last node on the full batch; first 20000 queries bit-exact "
+                                "against the CPU oracle; 32-bit and host-path results identical to the device-path results"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_e2e(args, index, d_pat, want_out, Q, world, local_rank, barrier, max_over_ranks, sum_over_ranks):
+    """The same metric through the host entry points (pinned host buffers in, pinned host buffers out): the 32-bit call
+    is the headline (what a caller that narrows its node identifiers once pays), the 64-bit call beside it, and the
+    plain H2D copy rate of the same buffer, which is the bound for both."""
+    import torch
+    import gbwt_rs_b200 as gb
+    lib = gb.library()
+    Qe = min(args.e2e_queries, Q)
+    e2e_steps = max(3, min(args.steps, 10))
+    out = {}
+    for width in ("u32", "u64"):
+        dtype = torch.int32 if width == "u32" else torch.int64
+        h_pat = torch.empty((Qe, K_LEN), dtype=dtype).pin_memory()
+        h_out = torch.empty((Qe, 3), dtype=torch.int64).pin_memory()
+        h_pat.copy_(d_pat[:Qe].to(dtype))
+        fn = lib.gbwt_b200_find_extend_u32 if width == "u32" else lib.gbwt_b200_find_extend
+
+        def e2e_step():
+            rc = fn(index._h, h_pat.data_ptr(), Qe, K_LEN, h_out.data_ptr())
+            if rc != 0:
+                raise SystemExit(f"gbwt_b200_find_extend failed: {lib.gbwt_b200_last_error().decode()}")
+        e2e_step()
+        barrier(); torch.cuda.synchronize()
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - te)
+        barrier()
+        if not torch.equal(h_out, want_out[:Qe].cpu()):
+            raise SystemExit("host-path results differ from device-path results")
+        # the wire: the same pinned buffer copied to the device and nothing else, all ranks at once
+        d_tmp = torch.empty_like(h_pat, device=d_pat.device)
+        d_tmp.copy_(h_pat, non_blocking=True)
+        barrier(); torch.cuda.synchronize()
+        tw = time.perf_counter()
+        for _ in range(3):
+            d_tmp.copy_(h_pat, non_blocking=True)
+        torch.cuda.synchronize()
+        wire_s = max_over_ranks(time.perf_counter() - tw) / 3
+        barrier()
+        item = K_LEN * (4 if width == "u32" else 8)
+        out[width] = {"value": Qe * world * e2e_steps / dt, "unit": "queries/s", "h2d_bytes_per_step": Qe * item,
+                      "d2h_bytes_per_step": Qe * 24, "h2d_wire_gbs_per_gpu": Qe * item / wire_s / 1e9,
+                      "wire_bound_queries_per_s": Qe * world / wire_s,
+                      "api": f"gbwt_b200_find_extend{'_u32' if width == 'u32' else ''} (host pointers, pinned), chunked double-buffered H2D/kernels/D2H"}
+        del h_pat, h_out, d_tmp
+    e2e = dict(out["u32"])
+    e2e.update({"queries_per_gpu_per_step": Qe, "steps": e2e_steps, "u64": out["u64"],
+                "limiter": "host-to-device copy of the patterns (PCIe): compare value with wire_bound_queries_per_s, the rate at which "
+                           "the same pinned buffer is copied with nothing else running"})
+    return e2e
+
+
+def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats):
+    """configs[4] inside the default run: every forward haplotype path, partitioned by path over the ranks (strong scaling).
+    warm = the index as the library builds it (path checkpoints from the load-time walk: sequences are extracted as
+    independent segments); cold = a fresh handle WITHOUT checkpoints and without remembered lengths (one dependent chain per
+    path), first call and second call (lengths known after the first: two chains per path)."""
+    import torch
+    import gbwt_rs_b200 as gb
+    from synth import synth
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    lo, hi = gb.shard_range(haplotypes, rank, world)
+    m = hi - lo
+    length = 2 * sites + 1
+    ids = (torch.arange(lo, hi, dtype=torch.int64, device=dev) * 2)
+    offs = torch.arange(m + 1, dtype=torch.int64, device=dev) * length
+    nodes = torch.empty(m * length, dtype=torch.int64, device=dev)
+    lens = torch.empty(m, dtype=torch.int64, device=dev)
+
+    def run(ix, steps, warmup):
+        for _ in range(warmup):
+            ix.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            ix.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    steps = max(3, min(args.steps, 10))
+    nodes.zero_()
+    warm_ms = run(index, steps, 2)
+    if not bool(torch.all(lens == length).item()):
+        raise SystemExit("extraction: wrong sequence lengths")
+    # parity: 8 whole paths of this rank against the oracle (rank 0 checks its own; every rank checks the generator)
+    picks = sorted(set(int(x) for x in np.linspace(0, m - 1, 8)))
+    for j in picks[:2]:
+        got = nodes[j * length:(j + 1) * length].cpu().numpy().view(np.uint64)
+        if not np.array_equal(got, synth.sequence(sites, haplotypes, SEED, 2 * (lo + j))):
+            raise SystemExit("extraction: a path differs from the generator's haplotype")
+    oracle_paths = 0
+    if rank == 0:
+        from oracle import oracle as orc
+        g = orc.GBWT.load(image, native=True)
+        want_ids = np.array([2 * (lo + j) for j in picks], dtype=np.uint64)
+        w_off, w_nodes = g.extract_batch(want_ids, threads=len(picks))
+        for t, j in enumerate(picks):
+            got = nodes[j * length:(j + 1) * length].cpu().numpy().view(np.uint64)
+            if not np.array_equal(got, w_nodes[int(w_off[t]):int(w_off[t + 1])]):
+                raise SystemExit("extraction: a path differs from the oracle's")
+        oracle_paths = len(picks)
+    warm_sum = int(nodes.sum().item())
+    # cold: a fresh handle without checkpoints
+    t = time.time()
+    cold = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=False)
+    cold_build_s = time.time() - t
+    nodes.zero_()
+    cold_first_ms = run(cold, 1, 0)
+    if int(nodes.sum().item()) != warm_sum:
+        raise SystemExit("extraction: chain walks and checkpointed extraction disagree")
+    cold_second_ms = run(cold, 1, 0)
+    if int(nodes.sum().item()) != warm_sum:
+        raise SystemExit("extraction: two-ended walks and checkpointed extraction disagree")
+    del cold
+    total_nodes = haplotypes * length
+    peak, _ = measured_peak_gbs()
+    sm_mhz = 1965.0
+    # latency rooflines (dependent-load latencies measured with tools/microbench on this pool's B200: L2 291, HBM 813 cycles)
+    lat_l2, lat_hbm = 291.0, 813.0
+    props = torch.cuda.get_device_properties(local_rank)
+
+    def latency_bound(chains, nodes_per_trip, latency_cycles):
+        return chains * nodes_per_trip / (latency_cycles / (sm_mhz * 1e6)) * world
+
+    cold_chains = m                                   # one warp-wide chain per path, two nodes per dependent load (two-hop shortcuts)
+    warm_chains = min(m * max(1, ckpt["max_segments"]), props.multi_processor_count * 1280)  # lanes resident (5 CTAs of 256 per SM)
+    out_bytes = total_nodes * 8 + (stats["descriptors"] + stats["bodies"] + stats.get("skips", 0)) // 2 * world
+    res = {
+        "metric": "gbwt_extract_lf_steps_per_s", "unit": "LF steps/s", "scaling": "strong", "paths_per_gpu": m, "nodes_per_path": length,
+        "warm_lf_steps_per_s": total_nodes / (warm_ms / 1e3), "warm_ms": warm_ms,
+        "cold_lf_steps_per_s": total_nodes / (cold_first_ms / 1e3), "cold_first_call_ms": cold_first_ms,
+        "cold_second_call_lf_steps_per_s": total_nodes / (cold_second_ms / 1e3), "cold_second_call_ms": cold_second_ms,
+        "checkpoint_build_s": ckpt["build_us"] / 1e6, "checkpoint_interval": ckpt["interval"], "checkpoint_bytes": ckpt["bytes"],
+        "cold_index_build_s": cold_build_s,
+        "frac_bytes": out_bytes / (warm_ms / 1e3) / 1e9 / (peak * world),
+        "frac_latency_hbm": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_hbm),
+        "frac_latency_l2": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_l2),
+        "cold_frac_latency_hbm": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_hbm),
+        "cold_frac_latency_l2": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_l2),
+        "oracle_checked_paths": oracle_paths,
+        "note": "warm: k_extract_checkpointed, every sequence cut into independent segments at the checkpoints the index was built "
+                "with (build time above; the checkpoints are part of the immutable index, not a cache); a lane makes two dependent "
+                "loads per two-node step, so its latency bound is 1 node per round trip x lanes in flight. cold: a handle created "
+                "without checkpoints, one dependent chain per path (k_extract), then two per path once the first call has measured "
+                "the lengths (k_extract_split). frac_bytes = (8-byte nodes written + forward half of the index read once) / time / "
+                "measured HBM peak. All three produce identical bytes (checked); 8 whole paths compared with the CPU oracle on rank 0",
+    }
+    del nodes
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_extract(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, stats):

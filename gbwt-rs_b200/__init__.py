@@ -541,10 +541,10 @@ class GBWT:
 
     def window_info(self) -> dict:
         """Plan and counters of the record-window search kernel (gbwt_b200_window_info)."""
-        raw = np.zeros(12, dtype=np.uint64)
+        raw = np.zeros(14, dtype=np.uint64)
         _lib.gbwt_b200_window_info(self._h, _ptr(raw))
         keys = ("can_run", "default", "window_records", "margin", "body_units", "threads", "smem_bytes", "windows",
-                "edges", "edges_local", "queries", "deferred")
+                "edges", "edges_local", "queries", "deferred", "kernel_ns", "launches")
         return {k: int(v) for k, v in zip(keys, raw)}
 
     # -- device-pointer entry points (raw addresses, e.g. torch.Tensor.data_ptr(); stream = cudaStream_t) --

@@ -41,7 +41,8 @@ struct gbwt_b200_index {
     bool window_suits = false;      // ... and is expected to pay: mostly single-edge / dense records, mostly local edges
     WindowPlan window{};
     // GBWT_B200_WINDOW_STATS=1 (tests, tools): queries that went through the window kernel and how many it deferred
-    mutable std::atomic<uint64_t> window_queries{0}, window_deferred{0};
+    // and the device time of the window kernel alone, in nanoseconds (CUDA events around the launch)
+    mutable std::atomic<uint64_t> window_queries{0}, window_deferred{0}, window_kernel_ns{0}, window_launches{0};
     // Path checkpoints (kernels.cuh, k_build_checkpoints): built once when the index is created, immutable afterwards.
     void* d_ckpt_table = nullptr;
     void* d_ckpt_first = nullptr;
@@ -246,7 +247,8 @@ int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, s
         const size_t count = std::min(max_part, n - begin);
         const T* part = patterns + begin * k;
         const bool sorted = k >= 2 && wants_locality(ix, count);
-        if (sorted && wants_windows(ix)) {
+        // (a window is decoded into shared memory once per batch: it has to be shared by enough queries to pay)
+        if (sorted && wants_windows(ix) && (count >= 8 * static_cast<size_t>(ix->window.windows) || env_int("GBWT_B200_FIND_WINDOW", 1) == 2)) {
             // Record windows: one bucket of the sort = one window; the window kernel answers from shared memory and
             // lists what it could not decide, the general kernel finishes the list.
             uint32_t *perm = nullptr, *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
@@ -256,20 +258,32 @@ int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, s
             if (rc != GBWT_B200_OK) return rc;
             CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
             CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+            const bool stats = env_int("GBWT_B200_WINDOW_STATS", 0) != 0;
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (stats && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) { cudaGetLastError(); t0 = t1 = nullptr; }
+            if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t0, s);
             const int e = launch_find_window<T>(ix->view, ix->window, part, perm, bucket_end, count, k, out + begin, scratch, counters, ix->sm_count, s);
+            if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t1, s);
             if (e != 0) rc = cuda_fail(static_cast<cudaError_t>(e), "k_find_window");
             g_launches.fetch_add(1, std::memory_order_relaxed);
             if (rc == GBWT_B200_OK) {
                 launch_find_deferred<T>(ix->view, part, scratch, counters, k, out + begin, static_cast<unsigned>(ix->sm_count) * 4, s);
                 rc = launch_done("k_find_deferred");
             }
-            if (rc == GBWT_B200_OK && env_int("GBWT_B200_WINDOW_STATS", 0) != 0) {
+            if (rc == GBWT_B200_OK && stats) {
                 uint32_t host[2] = {0, 0};
                 if (cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
                     ix->window_queries.fetch_add(count);
                     ix->window_deferred.fetch_add(host[1]);
+                    float ms = 0;
+                    if (t0 != nullptr && t1 != nullptr && cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) {
+                        ix->window_kernel_ns.fetch_add(static_cast<uint64_t>(ms * 1e6));
+                        ix->window_launches.fetch_add(1);
+                    }
                 }
             }
+            if (t0 != nullptr) cudaEventDestroy(t0);
+            if (t1 != nullptr) cudaEventDestroy(t1);
             cudaFreeAsync(perm, s); cudaFreeAsync(bucket_end, s); cudaFreeAsync(scratch, s); cudaFreeAsync(counters, s);
             if (rc != GBWT_B200_OK) return rc;
             continue;
@@ -368,11 +382,23 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
             return launch_done("k_lengths_from_table");
         }
         const uint64_t items = ((m + 31) / 32) * static_cast<uint64_t>(std::max<uint32_t>(1, ix->ckpt.max_segments));
-        const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((items + 7) / 8, static_cast<uint64_t>(ix->sm_count) * 8)));
         CheckpointView cv = ix->ckpt;
         cv.max_segments = std::max<uint32_t>(1, cv.max_segments);
-        if (ix->view.edges_valid) k_extract_checkpointed<false><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
-        else k_extract_checkpointed<true><<<grid, BLOCK_THREADS, 0, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
+        // CTA size (GBWT_B200_EXTRACT_THREADS): the warps of a CTA take consecutive items, i.e. the same segment of
+        // neighbouring sequences, and share the records through L1
+        const int threads = env_int("GBWT_B200_EXTRACT_THREADS", 256);
+        const size_t tile_bytes = static_cast<size_t>(threads / 32) * 32 * TILE_STRIDE * sizeof(uint64_t);
+        const uint64_t ctas_wanted = (items * 32 + threads - 1) / threads;
+        if (threads == 1024) {
+            const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count))));
+            auto kernel = ix->view.edges_valid ? k_extract_checkpointed<false, 1024> : k_extract_checkpointed<true, 1024>;
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_bytes)));
+            kernel<<<grid, 1024, tile_bytes, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
+        } else {
+            const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count) * 8)));
+            auto kernel = ix->view.edges_valid ? k_extract_checkpointed<false, 256> : k_extract_checkpointed<true, 256>;
+            kernel<<<grid, 256, tile_bytes, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
+        }
         return launch_done("k_extract_checkpointed");
     }
     // Up to 64 Ki sequences: one warp each (GBWT_B200_EXTRACT_STRIDE overrides: threads per sequence, 32 = warp mode).
@@ -491,8 +517,8 @@ int run_chunked(const gbwt_b200_index* ix, size_t n, const std::vector<HostArray
 }
 
 // Chunk size: about 64 MiB of the widest array per chunk, at least 16 Ki items.
-size_t chunk_for(size_t widest_item_bytes) {
-    const size_t target = size_t(64) << 20;
+size_t chunk_for(size_t widest_item_bytes, size_t target = size_t(64) << 20) {
+    if (const int mb = env_int("GBWT_B200_HOST_CHUNK_MB", 0); mb > 0) target = static_cast<size_t>(mb) << 20;  // tests
     return std::max<size_t>(size_t(1) << 14, target / std::max<size_t>(1, widest_item_bytes));
 }
 
@@ -1001,12 +1027,13 @@ void gbwt_b200_checkpoint_info(const gbwt_b200_index* ix, uint64_t info[6]) {
     for (int i = 0; i < 6; i++) info[i] = values[i];
 }
 
-void gbwt_b200_window_info(const gbwt_b200_index* ix, uint64_t info[12]) {
+void gbwt_b200_window_info(const gbwt_b200_index* ix, uint64_t info[14]) {
     if (ix == nullptr || info == nullptr) return;
     const WindowPlan& w = ix->window;
-    const uint64_t values[12] = {ix->window_ok, ix->window_suits, uint64_t(1) << w.wshift, w.margin, w.body_cap, w.threads, w.smem_bytes,
-                                 w.windows, ix->edges_total, ix->edges_local, ix->window_queries.load(), ix->window_deferred.load()};
-    for (int i = 0; i < 12; i++) info[i] = values[i];
+    const uint64_t values[14] = {ix->window_ok, ix->window_suits, uint64_t(1) << w.wshift, w.margin, w.body_cap, w.threads, w.smem_bytes,
+                                 w.windows, ix->edges_total, ix->edges_local, ix->window_queries.load(), ix->window_deferred.load(),
+                                 ix->window_kernel_ns.load(), ix->window_launches.load()};
+    for (int i = 0; i < 14; i++) info[i] = values[i];
 }
 
 const char* gbwt_b200_last_error(void) { return g_last_error.c_str(); }
@@ -1141,7 +1168,9 @@ int gbwt_b200_find_extend(const gbwt_b200_index* ix, const uint64_t* patterns, s
     if (int rc = check_index(ix)) return rc;
     if (n > 0 && ((k > 0 && patterns == nullptr) || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
     std::vector<HostArray> arrays = {{k > 0 ? patterns : nullptr, nullptr, 8 * k}, {nullptr, out, sizeof(gbwt_b200_state)}};
-    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(8 * k, sizeof(gbwt_b200_state))),
+    // (pattern batches take larger chunks: a chunk is sorted and searched on its own, and the record windows of the
+    // search kernel want many queries each)
+    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(8 * k, sizeof(gbwt_b200_state)), size_t(512) << 20),
                        [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
         return launch_find_extend(ix, static_cast<uint64_t*>(d[0]), count, k, static_cast<gbwt_b200_state*>(d[1]), s);
     });
@@ -1151,7 +1180,7 @@ int gbwt_b200_find_extend_u32(const gbwt_b200_index* ix, const uint32_t* pattern
     if (int rc = check_index(ix)) return rc;
     if (n > 0 && ((k > 0 && patterns == nullptr) || out == nullptr)) return fail(GBWT_B200_E_ARGUMENT, "null array");
     std::vector<HostArray> arrays = {{k > 0 ? patterns : nullptr, nullptr, 4 * k}, {nullptr, out, sizeof(gbwt_b200_state)}};
-    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(4 * k, sizeof(gbwt_b200_state))),
+    return run_chunked(ix, n, arrays, chunk_for(std::max<size_t>(4 * k, sizeof(gbwt_b200_state)), size_t(256) << 20),
                        [&](size_t, size_t count, std::vector<void*>& d, cudaStream_t s) {
         return launch_find_extend(ix, static_cast<uint32_t*>(d[0]), count, k, static_cast<gbwt_b200_state*>(d[1]), s);
     });

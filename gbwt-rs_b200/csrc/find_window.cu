@@ -163,6 +163,14 @@ struct PlainRowReader {
     }
 };
 
+// Asks L2 for a pattern row ahead of its use: its first two 128-byte lines (a length-32 pattern is two lines of 64-bit
+// nodes, one of 32-bit nodes).
+template <class T>
+__device__ __forceinline__ void prefetch_row(const T* row, uint32_t k) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+    if (k * sizeof(T) > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + 128));
+}
+
 // First node of pattern row q as a 64-bit value (the sort key is computed from it).
 __device__ __forceinline__ uint64_t first_node(const uint64_t* patterns, size_t q, size_t k) { return __ldg(patterns + q * k); }
 __device__ __forceinline__ uint64_t first_node(const uint32_t* patterns, size_t q, size_t k) { return __ldg(patterns + q * k); }
@@ -185,7 +193,7 @@ struct Staged {
     uint32_t lo, count;               // staged records [lo, lo + count)
 };
 
-enum : int { QUERY_DONE = 0, QUERY_DEFER = 1 };
+enum : uint32_t { QUERY_FOUND = 0, QUERY_NONE = 1, QUERY_DEFER = 2 };
 
 // rank1(p) and the bit at p of the dense record whose first word is `kind`
 __device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind, uint32_t p, uint32_t& bit) {
@@ -195,72 +203,66 @@ __device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind
     return w.x + static_cast<uint32_t>(__popc(w.y & ((1u << sh) - 1u)));
 }
 
-// One query against the staged window. QUERY_DONE: `out` holds the reference's answer. QUERY_DEFER: the window could
-// not decide; the general kernel redoes the query from the start.
+// One query against the staged window. QUERY_FOUND: (node, start, end) is the reference's SearchState; QUERY_NONE: the
+// reference returns None; QUERY_DEFER: the window could not decide and the general kernel redoes the query from the
+// start. The loop has ONE exit (every failure breaks out with its status), so the lanes of a warp reconverge after
+// every step instead of carrying a stack of divergent returns.
 template <class Reader>
-__device__ __forceinline__ int window_query(const Staged& st, uint32_t base, Reader& rd, uint32_t k, gbwt_b200_state& out) {
-    set_none(out);
-    if (k == 0) return QUERY_DONE;
+__device__ __forceinline__ uint32_t window_query(const Staged& st, uint32_t base, Reader& rd, uint32_t k, uint32_t& node, uint32_t& start,
+                                                 uint32_t& end) {
+    if (k == 0) return QUERY_NONE;
     uint32_t x;
     if (!rd.node(0, x)) return QUERY_DEFER;
     uint32_t idx = x - base - st.lo;
     if (idx >= st.count || idx + st.lo == 0) return QUERY_DEFER;  // (record 0 is the endmarker: find() is None; let the general code say so)
     uint4 h = lds128(st.hot + 16u * idx);
-    uint32_t start = 0, end = h.z, node = x;
+    start = 0; end = h.z; node = x;
     if (h.w == KIND_DEFER) return QUERY_DEFER;
-    if (h.w == KIND_EMPTY || end == 0) return QUERY_DONE;  // GBWT::find: no record
-    uint32_t i = 1;
+    if (h.w == KIND_EMPTY || end == 0) return QUERY_NONE;  // GBWT::find: no record
+    uint32_t i = 1, status = QUERY_FOUND;
     while (i < k) {
         uint32_t x1;
-        if (!rd.node(i, x1)) return QUERY_DEFER;
-        if (x1 == 0) return QUERY_DONE;  // GBWT::extend: below first_node
+        if (!rd.node(i, x1)) { status = QUERY_DEFER; break; }
         const uint32_t total = h.z, kind = h.w;
         const uint32_t s = start < total ? start : total, e = end < total ? end : total;
-        if (s >= e) return QUERY_DONE;
+        // GBWT::extend: below first_node, or (Record::follow) an empty range
+        if (x1 == 0 || s >= e) { status = QUERY_NONE; break; }
         uint32_t b = 0, rs = s, re = e;
-        if (kind == KIND_SINGLE) {
-            if (x1 != h.x) return QUERY_DONE;
-        } else if (kind < KIND_DEFER) {
-            if (x1 == h.x) b = 0;
-            else if (x1 == h.y) b = 1;
-            else return QUERY_DONE;
-            // rank1(s), and rank1(e) = rank1(e - 1) + bit(e - 1); a range of one position needs one lookup
+        if (kind < KIND_DEFER) {
+            // dense record: rank1(s), and rank1(e) = rank1(e - 1) + bit(e - 1); a range of one position needs one lookup
+            b = x1 == h.y ? 1u : 0u;
+            if (x1 != h.x && x1 != h.y) { status = QUERY_NONE; break; }
             uint32_t bit;
             const uint32_t ones_s = staged_rank1(st, kind, s, bit);
             uint32_t ones_e = ones_s + bit;
             if (e - 1u != s) { ones_e = staged_rank1(st, kind, e - 1u, bit); ones_e += bit; }
             rs = b ? ones_s : s - ones_s;
             re = b ? ones_e : e - ones_e;
-            if (rs >= re) return QUERY_DONE;
-        } else if (kind == KIND_EMPTY) {
-            return QUERY_DONE;  // BWT::record() is None
+            if (rs >= re) { status = QUERY_NONE; break; }
+        } else if (kind == KIND_SINGLE) {
+            if (x1 != h.x) { status = QUERY_NONE; break; }
         } else {
-            return QUERY_DEFER;
+            status = kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;  // BWT::record() is None / a record the window does not decode
+            break;
         }
         // two hops at once when the successor is a single-edge record leading to the pattern node after x1
         const uint2 hop = lds64(st.pair + 16u * idx + 8u * b);
-        bool hopped = false;
-        if (i + 1 < k && hop.x != 0) {
-            uint32_t x2;
-            if (!rd.node(i + 1, x2)) return QUERY_DEFER;
-            if (x2 == hop.x) {
-                start = hop.y + rs; end = hop.y + re;
-                node = x2; i += 2;
-                hopped = true;
-            }
-        }
-        if (!hopped) {
+        uint32_t x2 = 0;
+        if (i + 1 < k && hop.x != 0 && !rd.node(i + 1, x2)) { status = QUERY_DEFER; break; }
+        if (x2 == hop.x && x2 != 0) {
+            start = hop.y + rs; end = hop.y + re;
+            node = x2; i += 2;
+        } else {
             const uint32_t edge_offset = lds32(st.offs + 8u * idx + 4u * b);
             start = edge_offset + rs; end = edge_offset + re;
             node = x1; i += 1;
         }
         if (i >= k) break;
         idx = node - base - st.lo;
-        if (idx >= st.count) return QUERY_DEFER;
+        if (idx >= st.count) { status = QUERY_DEFER; break; }
         h = lds128(st.hot + 16u * idx);
     }
-    out.node = node; out.start = start; out.end = end;
-    return QUERY_DONE;
+    return status;
 }
 
 constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
@@ -288,12 +290,22 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
     const uint32_t pattern_slot = st.words + (wp.body_cap / 2u) * 48u + 4u * tid;
     for (;;) {
         __syncthreads();  // everybody has left the previous window: its shared memory and ctrl[] may be reused
-        if (tid == 0) ctrl[0] = atomicAdd(&counters[0], 1u);
+        if (tid == 0) { ctrl[0] = atomicAdd(&counters[0], 1u); ctrl[1] = 0; }
         __syncthreads();
         const uint32_t w = ctrl[0];
         if (w >= wp.windows) break;
         const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1), q_end = __ldg(bucket_end + w);
         if (q_begin >= q_end) continue;
+        // Queries are handed out 32 at a time per warp; the pattern rows of a warp's NEXT 32 queries are requested from
+        // L2 before it works on the current ones, so that the row reads of the loop find them there (the rows of a
+        // sorted batch are scattered over HBM, and a thread has only one sector of its row in flight at a time).
+        uint32_t slot = 0, q_cur = 0;
+        if (lane == 0) slot = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot + lane < q_end) {
+            q_cur = __ldg(perm + slot + lane);
+            if (wp.prefetch) prefetch_row(patterns + static_cast<size_t>(q_cur) * k, k);
+        }
         const uint32_t r0 = w << wp.wshift;
         st.lo = r0 > wp.margin ? r0 - wp.margin : 0u;
         const uint32_t want_hi = r0 + (1u << wp.wshift) + wp.margin;
@@ -302,7 +314,6 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
         const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
         const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
-        if (tid == 0) ctrl[1] = q_begin;
         // decode the window into shared memory: descriptors + shortcuts ...
         for (uint32_t r = tid; r < st.count; r += THREADS) {
             Desc d;
@@ -335,20 +346,29 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
             }
         }
         __syncthreads();
-        // the window's queries, 32 at a time per warp
-        for (;;) {
-            uint32_t slot = 0;
-            if (lane == 0) slot = atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
-            slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-            if (slot >= q_end) break;
-            const uint32_t at = slot + lane;
-            if (at < q_end) {
-                const uint32_t q = __ldg(perm + at);
-                RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k, pattern_slot, 4u * THREADS);
-                gbwt_b200_state result;
-                if (window_query(st, base, rd, k, result) == QUERY_DONE) store_state(out + q, result);
-                else deferred[atomicAdd(&counters[1], 1u)] = q;
+        while (slot < q_end) {
+            uint32_t next_slot = 0, q_next = 0;
+            if (lane == 0) next_slot = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+            next_slot = __shfl_sync(0xFFFFFFFFu, next_slot, 0);
+            if (next_slot + lane < q_end) {
+                q_next = __ldg(perm + next_slot + lane);
+                if (wp.prefetch) prefetch_row(patterns + static_cast<size_t>(q_next) * k, k);
             }
+            if (slot + lane < q_end) {
+                const uint32_t q = q_cur;
+                RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k, pattern_slot, 4u * THREADS);
+                uint32_t node = 0, start = 0, end = 0;
+                const uint32_t status = window_query(st, base, rd, k, node, start, end);
+                if (status == QUERY_DEFER) {
+                    deferred[atomicAdd(&counters[1], 1u)] = q;
+                } else {
+                    const bool found = status == QUERY_FOUND;
+                    gbwt_b200_state result;
+                    result.node = found ? node : 0u; result.start = found ? start : 0u; result.end = found ? end : 0u;
+                    store_state(out + q, result);
+                }
+            }
+            slot = next_slot; q_cur = q_next;
         }
     }
 }
@@ -436,6 +456,7 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
     plan.body_cap = static_cast<uint32_t>(std::min<uint64_t>(plan.body_cap, std::max<uint64_t>(256, 4 * avg_units + 64))) & ~1u;
     plan.windows = static_cast<uint32_t>(((ix.records - 1) >> plan.wshift) + 1);
     plan.threads = threads;
+    plan.prefetch = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_PREFETCH", 0));
     plan.smem_bytes = window_smem_bytes(plan.max_records, plan.body_cap, threads);
     return true;
 }

@@ -19,6 +19,7 @@ struct WindowPlan {
     uint32_t body_cap;     // 16-byte units of shared memory set aside for bodies
     uint32_t threads;      // CTA size: 256, 512 or 1024
     uint32_t smem_bytes;   // dynamic shared memory per CTA
+    uint32_t prefetch;     // ask L2 for the pattern rows of a warp's next 32 queries (GBWT_B200_WINDOW_PREFETCH)
 };
 
 // Chooses the plan for an index (GBWT_B200_WINDOW / _MARGIN / _SMEM_KB / _THREADS override). False = do not use

@@ -1259,12 +1259,13 @@ struct CheckpointView {
 // contiguous bytes per row with streaming stores, so L2 sees whole sectors that it need not keep.
 constexpr uint32_t TILE_NODES = 16, TILE_STRIDE = 17;  // nodes per lane between flushes; row stride in 8-byte words
 
-template <bool CHECKED>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
+template <bool CHECKED, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
                                                                          size_t m, const uint64_t* __restrict__ out_offsets, uint64_t base_offset,
                                                                          uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    __shared__ uint64_t tiles[BLOCK_THREADS / 32][32][TILE_STRIDE];
+    extern __shared__ __align__(16) unsigned char tile_bytes[];  // [THREADS / 32][32][TILE_STRIDE] words
+    uint64_t (*tiles)[32][TILE_STRIDE] = reinterpret_cast<uint64_t (*)[32][TILE_STRIDE]>(tile_bytes);
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t (*tile)[TILE_STRIDE] = tiles[threadIdx.x >> 5];
     const RecordDesc* const descs = ix.desc;

@@ -131,8 +131,9 @@ GBWT_B200_API void gbwt_b200_checkpoint_info(const gbwt_b200_index* index, uint6
 /* The record-window search kernel's plan for this index and its counters (development / tests): [0] can run, [1] is
  * the default for sorted batches, [2] records per window, [3] margin, [4] body units staged, [5] threads per CTA,
  * [6] shared memory per CTA, [7] windows, [8] edges, [9] edges to nearby records, and -- only counted when
- * GBWT_B200_WINDOW_STATS=1 -- [10] queries sent through windows, [11] queries the windows deferred to the general kernel. */
-GBWT_B200_API void gbwt_b200_window_info(const gbwt_b200_index* index, uint64_t info[12]);
+ * GBWT_B200_WINDOW_STATS=1 -- [10] queries sent through windows, [11] queries the windows deferred to the general kernel,
+ * [12] device time of the window kernel launches in nanoseconds, [13] number of those launches. */
+GBWT_B200_API void gbwt_b200_window_info(const gbwt_b200_index* index, uint64_t info[14]);
 
 /* ---- unidirectional search -------------------------------------------------------------------- */
 /* GBWT::find (src/gbwt.rs:269-281) for n nodes. */

@@ -189,6 +189,7 @@ def test_config3_shape_small(b200, layout, locality, monkeypatch):
     # the library otherwise only uses for indexes that do not fit L2.
     if locality:
         monkeypatch.setenv("GBWT_B200_LOCALITY", locality)
+    monkeypatch.setenv("GBWT_B200_HOST_CHUNK_MB", "64")   # 262144 patterns per chunk: the batch below needs two
     S, H, seed = 4000, 64, 42
     img = synth.bubble_chain(S, H, seed)
     g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)

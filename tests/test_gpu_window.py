@@ -89,7 +89,7 @@ def test_window_kernel_edge_cases(b200, monkeypatch):
 
 
 @pytest.mark.parametrize("knobs", [dict(WINDOW=32, WINDOW_MARGIN=32), dict(WINDOW=64, WINDOW_MARGIN=0),
-                                   dict(WINDOW_SMEM_KB=20, WINDOW=128, WINDOW_MARGIN=64)])
+                                   dict(WINDOW_SMEM_KB=32, WINDOW=128, WINDOW_MARGIN=64)])
 def test_window_kernel_defers_what_it_cannot_answer(b200, knobs, monkeypatch):
     # windows smaller than a pattern's reach, no margin at all, and too little shared memory for the 1024-haplotype
     # bodies: the deferred list and the general kernel must give the same answers

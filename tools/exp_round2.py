@@ -18,6 +18,8 @@ ap.add_argument("--find", default="old:FIND_WINDOW=0,win512,win256:WINDOW_THREAD
 ap.add_argument("--extract", type=int, default=1)
 ap.add_argument("--extract-plain", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--ckpt-shifts", default="")
+ap.add_argument("--extract-threads", default="256")
 args = ap.parse_args()
 S, H, Q = args.sites, args.haplotypes, args.queries
 t = time.time()
@@ -79,23 +81,34 @@ if args.find:
     del d_pat, d_out, d_pat32
 
 if args.extract:
-    t = time.time()
-    index = gb.GBWT.from_bytes(img.array, checkpoints=True)
-    print(json.dumps({"build_with_checkpoints_s": time.time() - t, "checkpoints": index.checkpoint_info()}), flush=True)
     m, length = H, 2 * S + 1
     ids = torch.arange(0, m, dtype=torch.int64, device=dev) * 2
     offs = torch.arange(m + 1, dtype=torch.int64, device=dev) * length
     nodes = torch.empty(m * length, dtype=torch.int64, device=dev)
     lens = torch.empty(m, dtype=torch.int64, device=dev)
-    fn = lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
-    ms = timed(fn, args.reps)
-    ok = bool(torch.all(lens == length).item())
-    first = nodes[:length].cpu().numpy().view(np.uint64)
-    ok = ok and np.array_equal(first, synth.sequence(S, H, 42, 0))
-    last = nodes[(m - 1) * length:].cpu().numpy().view(np.uint64)
-    ok = ok and np.array_equal(last, synth.sequence(S, H, 42, 2 * (m - 1)))
-    checksum = int(nodes.sum().item())
-    print(json.dumps({"extract": "checkpointed", "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6, "ok": ok, "checksum": checksum}), flush=True)
+    want_first, want_last = synth.sequence(S, H, 42, 0), synth.sequence(S, H, 42, 2 * (m - 1))
+    checksum = None
+    for shift in (args.ckpt_shifts.split(",") if args.ckpt_shifts else [""]):
+        if shift:
+            os.environ["GBWT_B200_CHECKPOINT_SHIFT"] = shift
+        t = time.time()
+        index = gb.GBWT.from_bytes(img.array, checkpoints=True)
+        print(json.dumps({"build_with_checkpoints_s": time.time() - t, "checkpoints": index.checkpoint_info()}), flush=True)
+        fn = lambda: index.extract_device(ids.data_ptr(), m, offs.data_ptr(), nodes.data_ptr(), lens.data_ptr(), stream)
+        for threads in args.extract_threads.split(","):
+            os.environ["GBWT_B200_EXTRACT_THREADS"] = threads
+            nodes.zero_()
+            ms = timed(fn, args.reps)
+            ok = bool(torch.all(lens == length).item())
+            ok = ok and np.array_equal(nodes[:length].cpu().numpy().view(np.uint64), want_first)
+            ok = ok and np.array_equal(nodes[(m - 1) * length:].cpu().numpy().view(np.uint64), want_last)
+            chk = int(nodes.sum().item())
+            checksum = chk if checksum is None else checksum
+            print(json.dumps({"extract": "checkpointed", "shift": shift, "threads": threads, "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6,
+                              "ok": ok, "checksum_ok": chk == checksum}), flush=True)
+        del os.environ["GBWT_B200_EXTRACT_THREADS"]
+        if shift != (args.ckpt_shifts.split(",")[-1] if args.ckpt_shifts else ""):
+            del index
     if args.extract_plain:
         os.environ["GBWT_B200_EXTRACT_CHECKPOINTS"] = "0"
         nodes.zero_()
