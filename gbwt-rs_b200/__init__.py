@@ -65,6 +65,8 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_index_destroy": (None, [p]),
         "gbwt_b200_index_serialize": (i, [p, pp, C.POINTER(sz)]),
         "gbwt_b200_index_save_file": (i, [p, C.c_char_p]),
+        "gbwt_b200_index_serialize_gbz": (i, [p, pp, C.POINTER(sz)]),
+        "gbwt_b200_index_save_gbz_file": (i, [p, C.c_char_p]),
         "gbwt_b200_free": (None, [p]),
         "gbwt_b200_last_error": (C.c_char_p, []),
         "gbwt_b200_len": (u64, [p]), "gbwt_b200_sequences": (u64, [p]), "gbwt_b200_alphabet_size": (u64, [p]),
@@ -265,17 +267,20 @@ class GBWT:
         self._check(_lib.gbwt_b200_index_attach_graph(self._h, len(starts) - 1, _ptr(starts), _ptr(data)))
         return self
 
-    def serialize(self) -> bytes:
-        """GBWT::serialize (src/gbwt.rs:388-400): the index as a Simple-SDS GBWT image (no DA samples, no metadata)."""
+    def serialize(self, gbz: bool = False) -> bytes:
+        """GBWT::serialize (src/gbwt.rs:388-400) / GBZ::serialize (src/gbz.rs:662-671): the index as a Simple-SDS image,
+        with the tags, DA samples, metadata and (gbz=True) the Graph it was loaded with."""
         image, n = C.c_void_p(), C.c_size_t(0)
-        self._check(_lib.gbwt_b200_index_serialize(self._h, C.byref(image), C.byref(n)))
+        fn = _lib.gbwt_b200_index_serialize_gbz if gbz else _lib.gbwt_b200_index_serialize
+        self._check(fn(self._h, C.byref(image), C.byref(n)))
         try:
             return bytes((C.c_uint8 * n.value).from_address(image.value)) if n.value else b""
         finally:
             _lib.gbwt_b200_free(image)
 
-    def save(self, path) -> None:
-        self._check(_lib.gbwt_b200_index_save_file(self._h, os.fsencode(path)))
+    def save(self, path, gbz: bool = False) -> None:
+        fn = _lib.gbwt_b200_index_save_gbz_file if gbz else _lib.gbwt_b200_index_save_file
+        self._check(fn(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -59,6 +59,7 @@ struct gbwt_b200_index {
     uint64_t graph_bytes = 0;
     uint64_t bytes[4] = {0, 0, 0, 0};
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+    Carried carried;  // tags, DA samples, metadata, Graph section: host-side, written back by serialize
 };
 
 namespace {
@@ -682,6 +683,7 @@ int attach_graph(gbwt_b200_index* ix, const uint64_t* starts, uint64_t sequences
     cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     ix->d_label_starts = ix->d_label_bytes = nullptr;
     ix->has_graph = false;
+    ix->carried.graph_section.clear();  // (create_index restores the loaded one after attaching the loaded labels)
     // DNA lengths measured with another graph are void
     if (ix->d_dna_len != nullptr) CUDA_TRY(cudaMemset(ix->d_dna_len, 0xFE, std::max<size_t>(256, ix->sequences * sizeof(uint64_t))));
     uint64_t a = 0, b = 0;
@@ -819,6 +821,8 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     ix->sequences = parsed.sequences; ix->size = parsed.size; ix->offset = parsed.offset;
     ix->alphabet_size = parsed.alphabet_size; ix->flags = parsed.flags;
     std::memcpy(ix->format_counts, layout.format_counts, sizeof(layout.format_counts));
+    ix->carried.tags = parsed.tags; ix->carried.gbz_tags = parsed.gbz_tags;
+    ix->carried.da_samples = parsed.da_samples; ix->carried.metadata = parsed.metadata; ix->carried.graph_section = parsed.graph_section;
     rc = upload(&ix->d_desc, layout.desc.data(), layout.desc.size() * sizeof(RecordDesc), ix->bytes[0]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_bodies, layout.bodies.data(), layout.bodies.size() * 8, ix->bytes[1]);
     if (rc == GBWT_B200_OK) rc = upload(&ix->d_edges, layout.edges.data(), layout.edges.size() * sizeof(Edge), ix->bytes[2]);
@@ -878,6 +882,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     if (parsed.has_graph) {
         rc = attach_graph(ix, parsed.label_starts.data(), parsed.label_starts.size() - 1, parsed.label_bytes.data());
         if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+        ix->carried.graph_section = parsed.graph_section;
     }
     // Path checkpoints by default for indexes whose sequences are long enough to be worth cutting up
     // (GBWT_B200_LAYOUT_CHECKPOINTS / _NO_CHECKPOINTS decide explicitly; GBWT_B200_CHECKPOINTS=0/1 overrides both).
@@ -951,46 +956,70 @@ int gbwt_b200_index_from_parts(uint64_t sequences, uint64_t size, uint64_t offse
     )
 }
 
-int gbwt_b200_index_serialize(const gbwt_b200_index* ix, void** image, size_t* len) {
+// The layout comes back from HBM as it is; the encoder runs on the host. `gbz`: a GBZ image (needs node labels).
+static int serialize_index(const gbwt_b200_index* ix, bool gbz, void** image, size_t* len) {
     if (int rc = check_index(ix)) return rc;
     if (image == nullptr || len == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
     *image = nullptr; *len = 0;
+    if (gbz) { if (int rc = check_graph(ix)) return rc; }
     DeviceScope scope(ix->device);
     if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
-    // the layout comes back from HBM as it is; the encoder runs on the host
-    std::vector<RecordDesc> desc(ix->view.records);
-    std::vector<uint64_t> bodies(ix->bytes[1] / 8 + 2, 0);
-    std::vector<Edge> edges(ix->bytes[2] / sizeof(Edge) + 1, Edge{0, 0});
-    if (!desc.empty()) CUDA_TRY(cudaMemcpy(desc.data(), ix->d_desc, desc.size() * sizeof(RecordDesc), cudaMemcpyDeviceToHost));
-    if (ix->bytes[1] > 0) CUDA_TRY(cudaMemcpy(bodies.data(), ix->d_bodies, ix->bytes[1], cudaMemcpyDeviceToHost));
-    if (ix->bytes[2] > 0) CUDA_TRY(cudaMemcpy(edges.data(), ix->d_edges, ix->bytes[2], cudaMemcpyDeviceToHost));
-    LayoutArrays in;
-    in.desc = desc.data(); in.records = desc.size(); in.bodies = bodies.data(); in.edges = edges.data();
-    GBWTHeaderFields header;
-    header.sequences = ix->sequences; header.size = ix->size; header.offset = ix->offset;
-    header.alphabet_size = ix->alphabet_size; header.flags = ix->flags;
-    std::vector<uint8_t> bytes;
-    std::string err;
-    int rc = write_gbwt_image(header, in, bytes, err);
-    if (rc != GBWT_B200_OK) return fail(rc, err);
-    void* out = std::malloc(std::max<size_t>(bytes.size(), 1));
-    if (out == nullptr) return fail(GBWT_B200_E_IO, "out of memory");
-    std::memcpy(out, bytes.data(), bytes.size());
-    *image = out; *len = bytes.size();
-    return GBWT_B200_OK;
+    GBWT_B200_GUARDED(
+        std::vector<RecordDesc> desc(ix->view.records);
+        std::vector<uint64_t> bodies(ix->bytes[1] / 8 + 2, 0);
+        std::vector<Edge> edges(ix->bytes[2] / sizeof(Edge) + 1, Edge{0, 0});
+        if (!desc.empty()) CUDA_TRY(cudaMemcpy(desc.data(), ix->d_desc, desc.size() * sizeof(RecordDesc), cudaMemcpyDeviceToHost));
+        if (ix->bytes[1] > 0) CUDA_TRY(cudaMemcpy(bodies.data(), ix->d_bodies, ix->bytes[1], cudaMemcpyDeviceToHost));
+        if (ix->bytes[2] > 0) CUDA_TRY(cudaMemcpy(edges.data(), ix->d_edges, ix->bytes[2], cudaMemcpyDeviceToHost));
+        LayoutArrays in;
+        in.desc = desc.data(); in.records = desc.size(); in.bodies = bodies.data(); in.edges = edges.data();
+        GBWTHeaderFields header;
+        header.sequences = ix->sequences; header.size = ix->size; header.offset = ix->offset;
+        header.alphabet_size = ix->alphabet_size; header.flags = ix->flags;
+        std::vector<uint8_t> bytes;
+        std::string err;
+        int rc;
+        if (!gbz) {
+            rc = write_gbwt_image(header, in, ix->carried, bytes, err);
+        } else {
+            // labels attached by hand have no Graph section to pass through: they come back from HBM and are written as one
+            std::vector<uint64_t> starts;
+            std::vector<uint8_t> labels;
+            if (ix->carried.graph_section.empty()) {
+                starts.assign(ix->graph.sequences + 1, 0);
+                CUDA_TRY(cudaMemcpy(starts.data(), ix->d_label_starts, starts.size() * 8, cudaMemcpyDeviceToHost));
+                labels.assign(starts.back(), 0);
+                if (!labels.empty()) CUDA_TRY(cudaMemcpy(labels.data(), ix->d_label_bytes, labels.size(), cudaMemcpyDeviceToHost));
+            }
+            rc = write_gbz_image(header, in, ix->carried, starts.empty() ? nullptr : starts.data(), ix->graph.sequences,
+                                 labels.data(), bytes, err);
+        }
+        if (rc != GBWT_B200_OK) return fail(rc, err);
+        void* out = std::malloc(std::max<size_t>(bytes.size(), 1));
+        if (out == nullptr) return fail(GBWT_B200_E_IO, "out of memory");
+        std::memcpy(out, bytes.data(), bytes.size());
+        *image = out; *len = bytes.size();
+        return GBWT_B200_OK;
+    )
 }
 
-int gbwt_b200_index_save_file(const gbwt_b200_index* ix, const char* path) {
+static int save_index(const gbwt_b200_index* ix, bool gbz, const char* path) {
     if (path == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null path");
     void* image = nullptr;
     size_t len = 0;
-    if (int rc = gbwt_b200_index_serialize(ix, &image, &len)) return rc;
+    if (int rc = serialize_index(ix, gbz, &image, &len)) return rc;
     std::ofstream f(path, std::ios::binary | std::ios::trunc);
     bool ok = static_cast<bool>(f);
     if (ok) { f.write(static_cast<const char*>(image), static_cast<std::streamsize>(len)); ok = static_cast<bool>(f); }
     std::free(image);
     return ok ? GBWT_B200_OK : fail(GBWT_B200_E_IO, std::string("cannot write ") + path);
 }
+
+int gbwt_b200_index_serialize(const gbwt_b200_index* ix, void** image, size_t* len) { return serialize_index(ix, false, image, len); }
+int gbwt_b200_index_serialize_gbz(const gbwt_b200_index* ix, void** image, size_t* len) { return serialize_index(ix, true, image, len); }
+int gbwt_b200_index_save_gbz_file(const gbwt_b200_index* ix, const char* path) { return save_index(ix, true, path); }
+
+int gbwt_b200_index_save_file(const gbwt_b200_index* ix, const char* path) { return save_index(ix, false, path); }
 
 void gbwt_b200_free(void* p) { std::free(p); }
 

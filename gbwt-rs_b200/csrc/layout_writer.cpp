@@ -16,7 +16,8 @@ namespace gbwt_b200 {
 namespace {
 
 constexpr uint64_t GBWT_TAG = 0x6B376B37ull, GBWT_VERSION = 5;
-constexpr uint64_t FLAG_BIDIRECTIONAL = 1, FLAG_SIMPLE_SDS = 4;
+constexpr uint64_t FLAG_BIDIRECTIONAL = 1, FLAG_METADATA = 2, FLAG_SIMPLE_SDS = 4;
+constexpr uint64_t GBZ_TAG = 0x205A4247ull, GBZ_VERSION = 2, GRAPH_TAG = 0x6B3764AFull, FLAG_GRAPH_SIMPLE_SDS = 2;
 
 // Either counts or writes: the two passes of the encoder share one code path.
 struct ByteSink {
@@ -149,11 +150,9 @@ void put_sparse(WordSink& w, uint64_t universe, const std::vector<uint64_t>& val
     w.word(ones); w.word(width); w.word(ones * width); w.word(low.size()); w.words(low);
 }
 
-// Tags: a StringArray of [key, value, ...] = start offsets, alphabet, packed characters (src/support.rs:592-610).
-void put_tags(WordSink& w, const std::vector<std::string>& strings) {
-    std::vector<uint64_t> starts;
-    std::string all;
-    for (const std::string& s : strings) { starts.push_back(all.size()); all += s; }
+// StringArray::serialize (src/support.rs:601-622): start offsets (no sentinel), alphabet, packed characters.
+void put_string_array(WordSink& w, const std::vector<uint64_t>& starts, const uint8_t* bytes, uint64_t total) {
+    const std::basic_string<unsigned char> all(bytes, bytes + total);
     put_sparse(w, starts.empty() ? 0 : starts.back() + 1, starts);
     bool present[256] = {false};
     for (unsigned char c : all) present[c] = true;
@@ -170,6 +169,14 @@ void put_tags(WordSink& w, const std::vector<std::string>& strings) {
         if (bit % 64 + width > 64) packed[bit / 64 + 1] |= v >> (64 - bit % 64);
     }
     w.word(all.size()); w.word(width); w.word(all.size() * width); w.word(packed.size()); w.words(packed);
+}
+
+// Tags: a StringArray of [key, value, ...].
+void put_tags(WordSink& w, const std::vector<std::string>& strings) {
+    std::vector<uint64_t> starts;
+    std::string all;
+    for (const std::string& s : strings) { starts.push_back(all.size()); all += s; }
+    put_string_array(w, starts, reinterpret_cast<const uint8_t*>(all.data()), all.size());
 }
 
 }  // namespace
@@ -199,22 +206,70 @@ int encode_bwt(const LayoutArrays& in, std::vector<uint8_t>& data, std::vector<u
     return GBWT_B200_OK;
 }
 
-int write_gbwt_image(const GBWTHeaderFields& header, const LayoutArrays& in, std::vector<uint8_t>& image, std::string& err) {
+namespace {
+
+// Tags as the reference writes them after a load: `source` = "jltsiren/gbwt-rs", keys in order (a BTreeMap).
+std::vector<std::string> linearize_tags(std::vector<std::pair<std::string, std::string>> tags) {
+    bool have_source = false;
+    for (auto& kv : tags) if (kv.first == "source") { kv.second = "jltsiren/gbwt-rs"; have_source = true; }
+    if (!have_source) tags.emplace_back("source", "jltsiren/gbwt-rs");
+    std::sort(tags.begin(), tags.end());
+    std::vector<std::string> flat;
+    for (const auto& kv : tags) { flat.push_back(kv.first); flat.push_back(kv.second); }
+    return flat;
+}
+
+void append_bytes(std::vector<uint8_t>& out, const std::vector<uint8_t>& bytes) { out.insert(out.end(), bytes.begin(), bytes.end()); }
+
+}  // namespace
+
+int write_gbwt_image(const GBWTHeaderFields& header, const LayoutArrays& in, const Carried& carried, std::vector<uint8_t>& image,
+                     std::string& err) {
     std::vector<uint8_t> data;
     std::vector<uint64_t> starts;
     const int rc = encode_bwt(in, data, starts, err);
     if (rc != GBWT_B200_OK) return rc;
     image.clear();
-    image.reserve(data.size() + data.size() / 4 + 4096);
+    image.reserve(data.size() + data.size() / 4 + carried.da_samples.size() + carried.metadata.size() + 4096);
     WordSink w{image};
+    const bool has_metadata = carried.metadata.size() > 8;  // Option<Metadata>: more than the size word
     w.word(GBWT_TAG | (GBWT_VERSION << 32));
     w.word(header.sequences); w.word(header.size); w.word(header.offset); w.word(header.alphabet_size);
-    w.word((header.flags & FLAG_BIDIRECTIONAL) | FLAG_SIMPLE_SDS);  // no metadata in this image
-    put_tags(w, {"source", "jltsiren/gbwt-rs"});
+    w.word((header.flags & FLAG_BIDIRECTIONAL) | FLAG_SIMPLE_SDS | (has_metadata ? FLAG_METADATA : 0));
+    put_tags(w, linearize_tags(carried.tags));
     put_sparse(w, data.size(), starts);
     w.bytes(data.data(), data.size());
-    w.word(0);  // document-array samples: an empty Vec<u64>
-    w.word(0);  // Option<Metadata>: None
+    if (carried.da_samples.empty()) w.word(0);  // an empty Vec<u64>
+    else append_bytes(image, carried.da_samples);
+    if (!has_metadata) w.word(0);               // Option<Metadata>: None
+    else append_bytes(image, carried.metadata);
+    return GBWT_B200_OK;
+}
+
+int write_gbz_image(const GBWTHeaderFields& header, const LayoutArrays& in, const Carried& carried, const uint64_t* label_starts,
+                    uint64_t sequences, const uint8_t* label_bytes, std::vector<uint8_t>& image, std::string& err) {
+    std::vector<uint8_t> gbwt;
+    const int rc = write_gbwt_image(header, in, carried, gbwt, err);
+    if (rc != GBWT_B200_OK) return rc;
+    image.clear();
+    image.reserve(gbwt.size() + carried.graph_section.size() + 4096);
+    WordSink w{image};
+    w.word(GBZ_TAG | (GBZ_VERSION << 32));
+    w.word(0);  // GBZ flags
+    put_tags(w, linearize_tags(carried.gbz_tags));
+    append_bytes(image, gbwt);
+    if (!carried.graph_section.empty()) { append_bytes(image, carried.graph_section); return GBWT_B200_OK; }
+    if (label_starts == nullptr || (label_starts[sequences] > 0 && label_bytes == nullptr)) { err = "no node labels to write"; return GBWT_B200_E_NO_GRAPH; }
+    // Graph, version 3 (sequences as a plain StringArray), no translation
+    uint64_t nodes = 0;
+    for (uint64_t i = 0; i < sequences; i++) if (label_starts[i + 1] > label_starts[i]) nodes++;
+    w.word(GRAPH_TAG | (uint64_t(3) << 32));
+    w.word(nodes);
+    w.word(FLAG_GRAPH_SIMPLE_SDS);
+    std::vector<uint64_t> starts(label_starts, label_starts + sequences);
+    put_string_array(w, starts, label_bytes, label_starts[sequences]);
+    put_string_array(w, {}, nullptr, 0);  // segment names: none
+    put_sparse(w, 0, {});                 // node-to-segment mapping: empty
     return GBWT_B200_OK;
 }
 

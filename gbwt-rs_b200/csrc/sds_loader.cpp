@@ -92,6 +92,52 @@ bool read_sparse_values(Cursor& c, uint64_t& universe, std::vector<uint64_t>& va
     return j == ones;
 }
 
+// StringArray::load (src/support.rs:624-655) for small arrays (tags): start offsets, alphabet, packed characters.
+bool read_string_array(Cursor& c, std::vector<std::string>& strings) {
+    uint64_t universe = 0;
+    std::vector<uint64_t> starts;
+    if (!read_sparse_values(c, universe, starts)) return false;
+    const uint64_t alphabet_len = c.word();
+    const uint8_t* alphabet = c.here();
+    c.skip_words((alphabet_len + 7) / 8);
+    const uint64_t total = c.word(), width = c.word(), bits = c.word(), words = c.word();
+    const uint8_t* packed = c.here();
+    c.skip_words(words);
+    if (!c.ok() || width == 0 || width > 64 || words != (bits + 63) / 64 || bits != total * width || total > (uint64_t(1) << 32)) return false;
+    std::string all(total, '\0');
+    const uint64_t mask = width >= 64 ? ~0ull : ((1ull << width) - 1);
+    for (uint64_t i = 0; i < total; i++) {
+        const uint64_t bit = i * width, w = bit / 64, sh = bit % 64;
+        uint64_t v = load_word(packed, w) >> sh;
+        if (sh + width > 64) v |= load_word(packed, w + 1) << (64 - sh);
+        v &= mask;
+        if (v >= alphabet_len) return false;
+        all[i] = static_cast<char>(alphabet[v]);
+    }
+    strings.clear();
+    for (size_t i = 0; i < starts.size(); i++) {
+        const uint64_t lo = starts[i], hi = i + 1 < starts.size() ? starts[i + 1] : total;
+        if (lo > hi || hi > total || (i == 0 && lo != 0)) return false;
+        strings.push_back(all.substr(lo, hi - lo));
+    }
+    return true;
+}
+
+// Tags::load (src/support.rs:992-1007): [key, value, ...], keys lower-cased, no duplicates.
+bool read_tags(Cursor& c, std::vector<std::pair<std::string, std::string>>& tags, std::string& err) {
+    std::vector<std::string> strings;
+    if (!read_string_array(c, strings)) { err = "Tags: invalid data"; return false; }
+    if (strings.size() % 2 != 0) { err = "Tags: Key without a value"; return false; }
+    tags.clear();
+    for (size_t i = 0; i < strings.size(); i += 2) {
+        std::string key = strings[i];
+        for (char& ch : key) if (ch >= 'A' && ch <= 'Z') ch = static_cast<char>(ch - 'A' + 'a');
+        for (const auto& kv : tags) if (kv.first == key) { err = "Tags: Duplicate keys"; return false; }
+        tags.emplace_back(key, strings[i + 1]);
+    }
+    return true;
+}
+
 int parse_gbwt(Cursor& c, ParsedGBWT& out, std::string& err) {
     uint64_t tv = c.word();
     out.sequences = c.word(); out.size = c.word(); out.offset = c.word();
@@ -106,8 +152,7 @@ int parse_gbwt(Cursor& c, ParsedGBWT& out, std::string& err) {
     }
     if (!(out.flags & GBWT_FLAG_SIMPLE_SDS)) { err = "GBWTHeader: SDSL format is not supported"; return GBWT_B200_E_INVALID_DATA; }
     if (out.alphabet_size < out.offset) { err = "GBWTHeader: alphabet size below offset"; return GBWT_B200_E_INVALID_DATA; }
-    c.skip_tags();
-    if (!c.ok()) { err = "Tags: invalid data"; return GBWT_B200_E_INVALID_DATA; }
+    if (!read_tags(c, out.tags, err)) return GBWT_B200_E_INVALID_DATA;
     // BWT::load, src/bwt.rs:176-185
     uint64_t universe = 0;
     if (!read_sparse_values(c, universe, out.record_starts)) { err = "BWT: invalid index"; return GBWT_B200_E_INVALID_DATA; }
@@ -121,10 +166,14 @@ int parse_gbwt(Cursor& c, ParsedGBWT& out, std::string& err) {
         if (s >= out.bwt_len || (i > 0 && s <= out.record_starts[i - 1])) { err = "BWT: invalid index"; return GBWT_B200_E_INVALID_DATA; }
     }
     // DA samples pass through as Vec<u64> (src/gbwt.rs:417); Option<Metadata> must agree with the flag (:420-423).
+    const uint8_t* da_at = c.here();
     c.skip_words(c.word());
+    const uint8_t* meta_at = c.here();
     uint64_t meta_words = c.word();
     c.skip_words(meta_words);
     if (!c.ok()) { err = "GBWT: unexpected end of data"; return GBWT_B200_E_INVALID_DATA; }
+    out.da_samples.assign(da_at, meta_at);
+    out.metadata.assign(meta_at, c.here());
     if (((out.flags & GBWT_FLAG_METADATA) != 0) != (meta_words != 0)) {
         err = "GBWT: Invalid metadata flag in the header"; return GBWT_B200_E_INVALID_DATA;
     }
@@ -280,11 +329,16 @@ int parse_gbwt_image(const uint8_t* bytes, size_t len, ParsedGBWT& out, std::str
         uint32_t version = static_cast<uint32_t>(tv >> 32);
         if (version < 1 || version > 2) { err = "GBZHeader: Invalid version (expected 1 to 2)"; return GBWT_B200_E_INVALID_DATA; }
         if (flags != 0) { err = "GBZHeader: Invalid flags"; return GBWT_B200_E_INVALID_DATA; }
-        c.skip_tags();
+        if (!read_tags(c, out.gbz_tags, err)) return GBWT_B200_E_INVALID_DATA;
         int rc = parse_gbwt(c, out, err);
         if (rc != GBWT_B200_OK) return rc;
         if (!(out.flags & GBWT_FLAG_BIDIRECTIONAL)) { err = "GBZ: The GBWT index is not bidirectional"; return GBWT_B200_E_INVALID_DATA; }
-        return parse_graph(c, out, err);
+        const uint8_t* graph_at = c.here();
+        rc = parse_graph(c, out, err);
+        if (rc != GBWT_B200_OK) return rc;
+        out.graph_section.assign(graph_at, c.here());
+        out.from_gbz = true;
+        return GBWT_B200_OK;
     }
     return parse_gbwt(c, out, err);
 }

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace gbwt_b200 {
@@ -19,6 +20,13 @@ struct ParsedGBWT {
     bool has_graph = false;
     std::vector<uint64_t> label_starts;
     std::vector<uint8_t> label_bytes;
+    // What is not on the accelerated path is carried through as it is, so that an index can be written back whole
+    // (GBWT::serialize, src/gbwt.rs:388-400; GBZ::serialize, src/gbz.rs:662-671): the tags as key / value strings, and
+    // the serialized elements of the document-array samples (Vec<u64>, length word included), of Option<Metadata>
+    // (size word included) and, for a GBZ image, of the whole Graph section (header to end of image).
+    std::vector<std::pair<std::string, std::string>> tags, gbz_tags;
+    std::vector<uint8_t> da_samples, metadata, graph_section;
+    bool from_gbz = false;
 };
 
 constexpr uint64_t GBWT_FLAG_BIDIRECTIONAL = 1, GBWT_FLAG_METADATA = 2, GBWT_FLAG_SIMPLE_SDS = 4;

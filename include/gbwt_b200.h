@@ -99,10 +99,19 @@ GBWT_B200_API int gbwt_b200_index_attach_graph(gbwt_b200_index* index, uint64_t 
 /* The way back (GBWT::serialize, src/gbwt.rs:388-400): the index as a Simple-SDS GBWT image that the reference
  * crate and the C++ tools can load. Records are re-encoded from the device layout in the reference encoding with
  * maximal runs (BWTBuilder::append, src/bwt.rs:241-253), so the BWT of a file written by the reference comes back
- * byte for byte; tags are reduced to `source`, document-array samples and metadata are not carried (they never
- * reach the device) and the metadata flag is cleared. `*image` is allocated by the library: gbwt_b200_free(). */
+ * byte for byte. What is not on the accelerated path is kept on the host as it was loaded and written back whole: the
+ * tags (with `source` set to "jltsiren/gbwt-rs" and in key order, which is what the reference writes after a load,
+ * src/gbwt.rs:404-405), the document-array samples and the metadata. `*image` is allocated by the library:
+ * gbwt_b200_free(). */
 GBWT_B200_API int gbwt_b200_index_serialize(const gbwt_b200_index* index, void** image, size_t* len);
 GBWT_B200_API int gbwt_b200_index_save_file(const gbwt_b200_index* index, const char* path);
+/* GBZ::serialize (src/gbz.rs:662-671): GBZ header (version 2), tags, the GBWT image above, the Graph. The Graph section
+ * of an index loaded from a GBZ image is written back as it was read (node labels, segment names, node-to-segment
+ * mapping; the reference would re-compress the labels with Zstandard -- both forms load in the reference); labels given
+ * with gbwt_b200_index_attach_graph are written as a version-3 Graph without translation. GBWT_B200_E_NO_GRAPH
+ * without node labels. */
+GBWT_B200_API int gbwt_b200_index_serialize_gbz(const gbwt_b200_index* index, void** image, size_t* len);
+GBWT_B200_API int gbwt_b200_index_save_gbz_file(const gbwt_b200_index* index, const char* path);
 GBWT_B200_API void gbwt_b200_free(void* p);
 GBWT_B200_API void gbwt_b200_index_destroy(gbwt_b200_index* index);
 /* Message of the last failure on the calling thread (never NULL). */

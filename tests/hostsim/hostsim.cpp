@@ -60,7 +60,7 @@ HostSim* hs_load(const uint8_t* bytes, size_t len, int policy, char* err, size_t
 void hs_free(HostSim* h) { delete h; }
 
 // The layout written back as a GBWT image (layout_writer.cpp): returns the size; fills `out` when it is large enough.
-uint64_t hs_serialize(const HostSim* h, uint8_t* out, uint64_t cap) {
+uint64_t hs_serialize(const HostSim* h, int gbz, uint8_t* out, uint64_t cap) {
     LayoutArrays in;
     in.desc = h->layout.desc.data(); in.records = h->layout.desc.size();
     in.bodies = h->layout.bodies.data(); in.edges = h->layout.edges.data();
@@ -69,10 +69,20 @@ uint64_t hs_serialize(const HostSim* h, uint8_t* out, uint64_t cap) {
     header.alphabet_size = h->parsed.alphabet_size; header.flags = h->parsed.flags;
     std::vector<uint8_t> image;
     std::string err;
-    if (write_gbwt_image(header, in, image, err) != GBWT_B200_OK) return 0;
+    Carried carried;
+    carried.tags = h->parsed.tags; carried.gbz_tags = h->parsed.gbz_tags; carried.da_samples = h->parsed.da_samples;
+    carried.metadata = h->parsed.metadata; carried.graph_section = h->parsed.graph_section;
+    const int rc = gbz ? write_gbz_image(header, in, carried, h->parsed.has_graph ? h->parsed.label_starts.data() : nullptr,
+                                         h->parsed.has_graph ? h->parsed.label_starts.size() - 1 : 0, h->parsed.label_bytes.data(), image, err)
+                       : write_gbwt_image(header, in, carried, image, err);
+    if (rc != GBWT_B200_OK) return 0;
     if (out != nullptr && cap >= image.size()) std::memcpy(out, image.data(), image.size());
     return image.size();
 }
+
+// Forgets the Graph section the image came with, as if the node labels had been attached by hand: the GBZ writer then
+// writes a version-3 Graph from the labels.
+void hs_drop_graph_section(HostSim* h) { h->parsed.graph_section.clear(); }
 
 // Path-walk shortcuts of K0 pass 3 (layout.h, IndexView::skips): 4 x u32 per record; and the descriptor words the
 // shortcuts are derived from: out[0..7] = {total_len, meta, w0, w1, body, body_len, w2, w3}.

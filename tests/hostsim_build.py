@@ -42,7 +42,7 @@ def lib():
         L.hs_load.argtypes = [p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.hs_free.argtypes = [p]
         L.hs_serialize.restype = u64
-        L.hs_serialize.argtypes = [p, p, u64]
+        L.hs_serialize.argtypes = [p, C.c_int, p, u64]
         L.hs_skips.restype = p
         L.hs_skips.argtypes = [p]
         L.hs_edges_valid.argtypes = [p]
@@ -50,6 +50,7 @@ def lib():
         L.hs_records.argtypes = [p]
         L.hs_desc_words.argtypes = [p, u64, p]
         L.hs_has_graph.argtypes = [p]
+        L.hs_drop_graph_section.argtypes = [p]
         L.hs_label_count.restype = u64
         L.hs_label_count.argtypes = [p]
         L.hs_label_starts.restype = p
@@ -105,11 +106,12 @@ class HostSim:
         except Exception:
             pass
 
-    def serialize(self) -> bytes:
-        """The layout written back as a Simple-SDS GBWT image (csrc/layout_writer.cpp)."""
-        n = self._L.hs_serialize(self._h, None, 0)
+    def serialize(self, gbz: bool = False) -> bytes:
+        """The layout written back as a Simple-SDS GBWT (or GBZ) image (csrc/layout_writer.cpp)."""
+        n = self._L.hs_serialize(self._h, int(gbz), None, 0)
+        assert n > 0, "serialization failed"
         buf = np.zeros(n, dtype=np.uint8)
-        assert self._L.hs_serialize(self._h, _p(buf), n) == n
+        assert self._L.hs_serialize(self._h, int(gbz), _p(buf), n) == n
         return buf.tobytes()
 
     def records(self):
@@ -127,6 +129,9 @@ class HostSim:
         out = np.zeros(8, dtype=np.uint32)
         self._L.hs_desc_words(self._h, rec, _p(out))
         return out
+
+    def drop_graph_section(self):
+        self._L.hs_drop_graph_section(self._h)
 
     def labels(self):
         """(starts, bytes) of the node labels the product loader parsed from a GBZ image, or None for a plain GBWT."""

@@ -241,3 +241,43 @@ def test_two_ended_dna_needs_mirror_strands(b200):
     e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
     for _ in range(2):
         check_dna(e, g, endmarker=ord("$"), ids=np.arange(len(paths), dtype=np.uint64))
+
+
+def test_whole_object_serialization_through_the_c_abi(b200, tmp_path):
+    # GBWT::serialize / GBZ::serialize (src/gbwt.rs:388-400, src/gbz.rs:662-671) on the GPU-resident index: tags, BWT,
+    # DA samples, metadata and the Graph come back; the image loads again and answers like the original
+    from test_layout_writer import expected_tags, gbwt_sections, gbz_sections
+    for name in ("example.gbz", "translation.gbz", "translation-v1.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        e = b200.GBWT.from_bytes(raw)
+        image = e.serialize(gbz=True)
+        gh, gtags, header, tags, rest, graph = gbz_sections(raw)
+        oh, otags, oheader, otags_gbwt, orest, ograph = gbz_sections(image)
+        assert otags == expected_tags(gtags) and otags_gbwt == expected_tags(tags)
+        assert oheader == header and orest == rest and ograph == graph
+        path = tmp_path / name
+        e.save(path, gbz=True)
+        again = b200.GBWT.load(path)
+        g = orc.GBWT.load(raw)
+        ids = np.arange(g.sequences(), dtype=np.uint64)
+        a, b = e.extract_dna(ids, endmarker=ord("$")), again.extract_dna(ids, endmarker=ord("$"))
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        plain = e.serialize()
+        h2, t2, r2, end = gbwt_sections(plain)
+        assert end == len(plain) and h2 == header and r2 == rest and t2 == expected_tags(tags)
+    # labels attached by hand: written as a version-3 Graph, read back by the product and by the oracle
+    S, H, seed = 60, 8, 3
+    img = synth.bubble_chain(S, H, seed)
+    starts, labels = synth.node_labels(3 * S + 1, seed=5)
+    e = b200.GBWT.from_bytes(img.array)
+    with pytest.raises(b200.GBWTError):
+        e.serialize(gbz=True)                       # GBWT_B200_E_NO_GRAPH
+    e.attach_graph(starts, labels)
+    image = e.serialize(gbz=True)
+    again = b200.GBWT.from_bytes(image)
+    ids = np.arange(2 * H, dtype=np.uint64)
+    a, b = e.extract_dna(ids), again.extract_dna(ids)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    g = orc.GBWT.load(image)
+    w_off, w_bytes, _ = g.extract_dna_batch(ids, 0)
+    assert np.array_equal(a[0], w_off) and np.array_equal(a[1], w_bytes)

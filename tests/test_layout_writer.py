@@ -27,6 +27,86 @@ def same_index(a, b):
         assert a.record_decompress(rec) == b.record_decompress(rec)
 
 
+# ---- a minimal reader of the Simple-SDS container, to cut an image into its sections ----------------
+
+class Words:
+    def __init__(self, raw, at=0):
+        self.raw, self.at = raw, at
+
+    def word(self):
+        v = int.from_bytes(self.raw[self.at:self.at + 8], "little")
+        self.at += 8
+        return v
+
+    def skip(self, words):
+        self.at += 8 * words
+
+    def raw_vector(self):
+        self.word(); self.skip(self.word())
+
+    def int_vector(self):
+        self.word(); self.word(); self.raw_vector()
+
+    def sparse_vector(self):
+        self.word(); self.word(); self.raw_vector()
+        for _ in range(3):
+            self.skip(self.word())
+        self.int_vector()
+
+    def string_array(self):
+        """Returns the strings of a packed StringArray and leaves the cursor behind it."""
+        start = self.at
+        universe = self.word(); ones = self.word(); hbits = self.word(); hwords = self.word()
+        high = int.from_bytes(self.raw[self.at:self.at + 8 * hwords], "little"); self.skip(hwords)
+        for _ in range(3):
+            self.skip(self.word())
+        n, width, lbits, lwords = self.word(), self.word(), self.word(), self.word()
+        low = int.from_bytes(self.raw[self.at:self.at + 8 * lwords], "little"); self.skip(lwords)
+        starts, j, pos = [], 0, 0
+        while j < ones:
+            if (high >> pos) & 1:
+                starts.append(((pos - j) << width) | ((low >> (j * width)) & ((1 << width) - 1)))
+                j += 1
+            pos += 1
+        alen = self.word()
+        alphabet = self.raw[self.at:self.at + alen]; self.skip((alen + 7) // 8)
+        total, cw, cbits, cwords = self.word(), self.word(), self.word(), self.word()
+        packed = int.from_bytes(self.raw[self.at:self.at + 8 * cwords], "little"); self.skip(cwords)
+        text = bytes(alphabet[(packed >> (i * cw)) & ((1 << cw) - 1)] for i in range(total))
+        ends = starts[1:] + [total]
+        return [text[a:b].decode() for a, b in zip(starts, ends)]
+
+
+def gbwt_sections(raw, at=0):
+    """(header bytes, tags dict, bytes from the BWT to the end of the GBWT, offset behind the GBWT)."""
+    w = Words(raw, at)
+    w.skip(6)
+    header = raw[at:w.at]
+    strings = w.string_array()
+    tags = dict(zip(strings[0::2], strings[1::2]))
+    rest_at = w.at
+    w.sparse_vector()                       # BWT index
+    n = w.word(); w.skip((n + 7) // 8)      # BWT data
+    w.skip(w.word())                        # DA samples
+    w.skip(w.word())                        # Option<Metadata>
+    return header, tags, raw[rest_at:w.at], w.at
+
+
+def gbz_sections(raw):
+    w = Words(raw)
+    w.skip(2)
+    strings = w.string_array()
+    tags = dict(zip(strings[0::2], strings[1::2]))
+    header, gbwt_tags, rest, end = gbwt_sections(raw, w.at)
+    return raw[:16], tags, header, gbwt_tags, rest, raw[end:]
+
+
+def expected_tags(tags):
+    out = {k.lower(): v for k, v in tags.items()}
+    out["source"] = "jltsiren/gbwt-rs"      # Tags::insert(SOURCE_KEY, SOURCE_VALUE) at load, src/gbwt.rs:404-405
+    return out
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("name", FIXTURES)
 def test_fixtures_round_trip(name, layout):
@@ -36,9 +116,75 @@ def test_fixtures_round_trip(name, layout):
     same_index(src, back)
     # files written by the reference have maximal runs: the BWT comes back byte for byte
     assert back.bwt_data() == src.bwt_data() and np.array_equal(back.record_starts(), src.record_starts())
-    assert not (back.flags() & 2) and (back.flags() & 4)            # no metadata, Simple-SDS
+    assert back.flags() == src.flags()                               # the metadata travels with the index now
     pc.check_everything(HostSim(image, layout), src)                 # and the product loads its own output
     assert HostSim(image, layout).serialize() == image               # idempotent
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_whole_object_round_trip(name):
+    """serialize::test of the reference is a whole-object round trip (src/gbwt/tests.rs:72-84): tags, BWT, DA samples and
+    metadata. Everything behind the tags comes back byte for byte; the tags are the loaded ones with `source` replaced,
+    in key order, which is what the reference writes after a load."""
+    raw = open(os.path.join(GOLDEN, name), "rb").read()
+    if name.endswith(".gbz"):
+        _, _, header, tags, rest, _ = gbz_sections(raw)
+    else:
+        header, tags, rest, end = gbwt_sections(raw)
+        assert end == len(raw)
+    image = HostSim(raw, 0).serialize()
+    out_header, out_tags, out_rest, out_end = gbwt_sections(image)
+    assert out_end == len(image)
+    assert out_header == header and out_rest == rest and out_tags == expected_tags(tags)
+    assert list(out_tags) == sorted(out_tags)
+    if tags == expected_tags(tags) and list(tags) == sorted(tags) and not name.endswith(".gbz"):
+        assert image == raw                                          # a file the reference wrote: identical as a whole
+
+
+@pytest.mark.parametrize("name", [n for n in FIXTURES if n.endswith(".gbz")])
+def test_gbz_round_trip(name):
+    """GBZ::serialize (src/gbz.rs:662-671): header, tags, GBWT, Graph. The Graph section is the loaded one."""
+    raw = open(os.path.join(GOLDEN, name), "rb").read()
+    sim = HostSim(raw, 0)
+    image = sim.serialize(gbz=True)
+    gh, gtags, header, tags, rest, graph = gbz_sections(raw)
+    oh, otags, oheader, otags_gbwt, orest, ograph = gbz_sections(image)
+    assert oh[:4] == gh[:4] and int.from_bytes(oh[4:8], "little") == 2 and oh[8:] == gh[8:]   # written as version 2
+    assert otags == expected_tags(gtags) and otags_gbwt == expected_tags(tags)
+    assert oheader == header and orest == rest and ograph == graph
+    # the oracle (= the reference's loader restated) and the product load it: same index, same node labels
+    src, back = orc.GBWT.load(raw), orc.GBWT.load(image)
+    same_index(src, back)
+    again = HostSim(image, 0)
+    assert same_labels(again.labels(), sim.labels()) and again.serialize(gbz=True) == image
+    if gtags == expected_tags(gtags) and tags == expected_tags(tags) and int.from_bytes(gh[4:8], "little") == 2:
+        assert image == raw
+
+
+def same_labels(a, b):
+    return a is not None and b is not None and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("name", ["example.gbz", "translation-v1.gbz", None])
+def test_gbz_written_from_attached_labels(name):
+    """Labels that did not come with a Graph section (gbwt_b200_index_attach_graph) are written as a version-3 Graph:
+    plain StringArray, no translation. The product's loader and the oracle read it back."""
+    if name is None:
+        S, H, seed = 40, 6, 3
+        starts, labels = synth.node_labels(3 * S + 1, seed=5)
+        raw = synth.gbz_image(synth.bubble_chain(S, H, seed), starts, labels, 4)
+    else:
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+    sim = HostSim(raw, 0)
+    want = sim.labels()
+    sim.drop_graph_section()
+    image = sim.serialize(gbz=True)
+    back = HostSim(image, 0)
+    assert same_labels(back.labels(), want)
+    same_index(orc.GBWT.load(raw), orc.GBWT.load(image))
+    w = Words(image); w.skip(2); w.string_array()
+    _, _, _, end = gbwt_sections(image, w.at)
+    assert int.from_bytes(image[end + 4:end + 8], "little") == 3 and int.from_bytes(image[end + 16:end + 24], "little") == 2
 
 
 @pytest.mark.parametrize("layout", [0, 1])
