@@ -69,27 +69,15 @@ def dist_env():
 # ---- index image shared between the ranks of one box --------------------------------------------------
 
 def get_image(sites, haplotypes, rank, world, barrier):
-    """Rank 0 generates the Simple-SDS GBWT image (into /dev/shm when there are several ranks)."""
+    """The Simple-SDS GBWT image. With several ranks only rank 0 needs it (it builds the index the others import, and
+    runs the oracle); the others get None."""
     from synth import synth
-    if world == 1:
-        t = time.time()
-        img = synth.bubble_chain(sites, haplotypes, SEED)
-        log(f"[bench] generated index image: {img.nbytes / 1e9:.2f} GB in {time.time() - t:.1f} s")
-        return img.array, img
-    path = f"/dev/shm/gbwt_b200_bench_{sites}_{haplotypes}_{SEED}_{os.environ.get('MASTER_PORT', '0')}.gbwt"
-    if rank == 0:
-        t = time.time()
-        img = synth.bubble_chain(sites, haplotypes, SEED, threads=os.cpu_count() or 0)  # the other ranks wait
-        img.array.tofile(path + ".tmp")
-        os.replace(path + ".tmp", path)
-        log(f"[bench] generated index image: {img.nbytes / 1e9:.2f} GB in {time.time() - t:.1f} s")
-        img.free()
-    barrier()
-    arr = np.fromfile(path, dtype=np.uint8)
-    barrier()
-    if rank == 0:
-        os.unlink(path)
-    return arr, None
+    if rank != 0:
+        return None, None
+    t = time.time()
+    img = synth.bubble_chain(sites, haplotypes, SEED, threads=(os.cpu_count() or 0) if world > 1 else 0)
+    log(f"[bench] generated index image: {img.nbytes / 1e9:.2f} GB in {time.time() - t:.1f} s")
+    return img.array, img
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------
@@ -290,13 +278,28 @@ def main():
     import gbwt_rs_b200 as gb
     from synth import synth
     ncpu = os.cpu_count() or 8
-    os.environ["GBWT_B200_BUILD_THREADS"] = str(max(1, ncpu // max(1, world)))  # K0 runs on every rank at once
+    os.environ["GBWT_B200_BUILD_THREADS"] = str(ncpu)  # K0 runs on rank 0 only (the other ranks import its result)
 
     sites, haplotypes, Q = resolve_workload(args)
+
+    def replicated_index(checkpoints):
+        """The index on this rank's GPU: rank 0 parses the image, runs K0 and the checkpoint walk once, the other ranks
+        import its arrays device to device (CUDA IPC + peer copies over NVLink) instead of repeating the host work."""
+        t = time.time()
+        if world == 1:
+            return gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=checkpoints), time.time() - t
+        box = [None]
+        first = None
+        if rank == 0:
+            first = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=checkpoints)
+            box[0] = first.export_ipc()
+        dist.broadcast_object_list(box, src=0, device=dev)
+        ix = first if rank == 0 else gb.GBWT.import_ipc(box[0], device=local_rank)
+        barrier()  # rank 0 keeps its arrays alive until every rank has copied them
+        return ix, max_over_ranks(time.time() - t)
+
     image, keep = get_image(sites, haplotypes, rank, world, barrier)
-    t = time.time()
-    index = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=True)
-    build_s = time.time() - t
+    index, build_s = replicated_index(True)
     stats = index.device_bytes()
     ckpt = index.checkpoint_info()
     if rank == 0:
@@ -431,7 +434,8 @@ def main():
     if args.workload == "find" and not args.no_extract:
         del d_pat, d_out, want_out
         torch.cuda.empty_cache()
-        extract = bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats)
+        extract = bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats,
+                                       replicated_index)
 
     if rank == 0:
         line = {
@@ -507,7 +511,8 @@ def bench_e2e(args, index, d_pat, want_out, Q, world, local_rank, barrier, max_o
     return e2e
 
 
-def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats):
+def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats,
+                         replicated_index):
     """configs[4] inside the default run: every forward haplotype path, partitioned by path over the ranks (strong scaling).
     warm = the index as the library builds it (path checkpoints from the load-time walk: sequences are extracted as
     independent segments); cold = a fresh handle WITHOUT checkpoints and without remembered lengths (one dependent chain per
@@ -561,9 +566,7 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         oracle_paths = len(picks)
     warm_sum = int(nodes.sum().item())
     # cold: a fresh handle without checkpoints
-    t = time.time()
-    cold = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=False)
-    cold_build_s = time.time() - t
+    cold, cold_build_s = replicated_index(False)
     nodes.zero_()
     cold_first_ms = run(cold, 1, 0)
     if int(nodes.sum().item()) != warm_sum:

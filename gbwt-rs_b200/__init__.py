@@ -67,6 +67,8 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_index_save_file": (i, [p, C.c_char_p]),
         "gbwt_b200_index_serialize_gbz": (i, [p, pp, C.POINTER(sz)]),
         "gbwt_b200_index_save_gbz_file": (i, [p, C.c_char_p]),
+        "gbwt_b200_index_export_ipc": (i, [p, pp, C.POINTER(sz)]),
+        "gbwt_b200_index_import_ipc": (i, [p, sz, i, pp]),
         "gbwt_b200_free": (None, [p]),
         "gbwt_b200_last_error": (C.c_char_p, []),
         "gbwt_b200_len": (u64, [p]), "gbwt_b200_sequences": (u64, [p]), "gbwt_b200_alphabet_size": (u64, [p]),
@@ -277,6 +279,23 @@ class GBWT:
             return bytes((C.c_uint8 * n.value).from_address(image.value)) if n.value else b""
         finally:
             _lib.gbwt_b200_free(image)
+
+    def export_ipc(self) -> bytes:
+        """Describes this index for the other processes of the node (gbwt_b200_index_export_ipc): they get their own copy on
+        their own GPU with GBWT.import_ipc, copied device to device. Keep this index alive until they are done."""
+        blob, n = C.c_void_p(), C.c_size_t(0)
+        self._check(_lib.gbwt_b200_index_export_ipc(self._h, C.byref(blob), C.byref(n)))
+        try:
+            return bytes((C.c_uint8 * n.value).from_address(blob.value))
+        finally:
+            _lib.gbwt_b200_free(blob)
+
+    @classmethod
+    def import_ipc(cls, blob: bytes, device: int = 0) -> "GBWT":
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        cls._check(_lib.gbwt_b200_index_import_ipc(_ptr(buf), len(buf), device, C.byref(h)))
+        return cls(h.value)
 
     def save(self, path, gbz: bool = False) -> None:
         fn = _lib.gbwt_b200_index_save_gbz_file if gbz else _lib.gbwt_b200_index_save_file

@@ -908,8 +908,8 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
 extern "C" {
 
 // No exception crosses the C ABI: the sizes declared in a damaged image can make an allocation fail.
-#define GBWT_B200_GUARDED(body)                                                                        \
-    try { body } catch (const std::bad_alloc&) {                                                       \
+#define GBWT_B200_GUARDED(...)                                                                         \
+    try { __VA_ARGS__ } catch (const std::bad_alloc&) {                                                       \
         return fail(GBWT_B200_E_INVALID_DATA, "invalid data (an allocation of the declared size failed)"); \
     } catch (const std::exception& e) {                                                                \
         return fail(GBWT_B200_E_INVALID_DATA, std::string("invalid data (") + e.what() + ")");        \
@@ -1013,6 +1013,217 @@ static int save_index(const gbwt_b200_index* ix, bool gbz, const char* path) {
     if (ok) { f.write(static_cast<const char*>(image), static_cast<std::streamsize>(len)); ok = static_cast<bool>(f); }
     std::free(image);
     return ok ? GBWT_B200_OK : fail(GBWT_B200_E_IO, std::string("cannot write ") + path);
+}
+
+// ---- build once, replicate over NVLink -----------------------------------------------------------------------------
+// The index of a multi-GPU job is the same on every GPU. Instead of every rank parsing the image and running K0 and the
+// checkpoint walk, one rank builds it and exports a small blob: the scalars of the handle, what the loader carried, and
+// a CUDA IPC handle per device array. The other ranks (one process per GPU) open the handles and copy the arrays
+// device to device -- peer copies over NVLink / NVSwitch -- into allocations of their own.
+
+namespace {
+
+constexpr uint64_t IPC_MAGIC = 0x4350493030324247ull;  // "GB200IPC"
+constexpr int IPC_ARRAYS = 12;
+
+struct IpcArray { uint64_t bytes; cudaIpcMemHandle_t handle; };
+
+struct IpcHeader {
+    uint64_t magic, version;
+    uint64_t sequences, size, offset, alphabet_size, flags;
+    uint64_t records, endmarker_len, bidirectional, edges_valid, walk_limit;
+    uint64_t bytes[4], skip_bytes, format_counts[FMT_COUNT], edges_total, edges_local;
+    uint64_t window_ok, window_suits;
+    WindowPlan window;
+    uint64_t ckpt_ok, ckpt_shift, ckpt_entries, ckpt_bytes, ckpt_build_us, ckpt_max_segments;
+    uint64_t has_graph, graph_sequences, graph_bytes;
+    uint64_t source_device;
+    IpcArray arrays[IPC_ARRAYS];
+};
+
+void put_u64(std::vector<uint8_t>& out, uint64_t v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); out.insert(out.end(), p, p + 8); }
+void put_blob(std::vector<uint8_t>& out, const void* p, size_t n) {
+    put_u64(out, n);
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    out.insert(out.end(), b, b + n);
+}
+void put_tags_blob(std::vector<uint8_t>& out, const std::vector<std::pair<std::string, std::string>>& tags) {
+    put_u64(out, tags.size());
+    for (const auto& kv : tags) { put_blob(out, kv.first.data(), kv.first.size()); put_blob(out, kv.second.data(), kv.second.size()); }
+}
+
+struct BlobReader {
+    const uint8_t* p;
+    size_t n, at = 0;
+    bool ok = true;
+    uint64_t u64() {
+        if (!ok || n - at < 8) { ok = false; return 0; }
+        uint64_t v;
+        std::memcpy(&v, p + at, 8);
+        at += 8;
+        return v;
+    }
+    std::string str() {
+        const uint64_t len = u64();
+        if (!ok || len > n - at) { ok = false; return std::string(); }
+        std::string s(reinterpret_cast<const char*>(p + at), len);
+        at += len;
+        return s;
+    }
+    std::vector<uint8_t> bytes() { const std::string s = str(); return std::vector<uint8_t>(s.begin(), s.end()); }
+    void tags(std::vector<std::pair<std::string, std::string>>& out) {
+        const uint64_t count = u64();
+        out.clear();
+        for (uint64_t i = 0; i < count && ok; i++) { std::string k = str(); std::string v = str(); out.emplace_back(k, v); }
+    }
+};
+
+// The device arrays of a handle in export order, with their sizes in bytes.
+void ipc_arrays(const gbwt_b200_index* ix, void* ptrs[IPC_ARRAYS], uint64_t sizes[IPC_ARRAYS]) {
+    const uint64_t seq_bytes = std::max<uint64_t>(256, ix->sequences * sizeof(uint64_t));
+    void* p[IPC_ARRAYS] = {ix->d_desc, ix->d_bodies, ix->d_edges, ix->d_endmarker, ix->d_skips, ix->d_stage_body, ix->d_seq_len,
+                           ix->d_dna_len, ix->d_ckpt_table, ix->d_ckpt_first, ix->d_label_starts, ix->d_label_bytes};
+    const uint64_t b[IPC_ARRAYS] = {ix->bytes[0], ix->bytes[1], ix->bytes[2], ix->bytes[3],
+                                    (ix->view.records + 1) * 16, (ix->view.records / STAGE_GRANULE + 2) * sizeof(uint32_t), seq_bytes, seq_bytes,
+                                    ix->ckpt_ok ? ix->ckpt_entries * sizeof(Checkpoint) : 0,
+                                    ix->ckpt_ok ? (ix->view.sequences + 1) * sizeof(uint32_t) : 0,
+                                    ix->has_graph ? (ix->graph.sequences + 1) * 8 : 0,
+                                    ix->has_graph ? ix->graph_bytes - (ix->graph.sequences + 1) * 8 : 0};
+    for (int i = 0; i < IPC_ARRAYS; i++) { ptrs[i] = p[i]; sizes[i] = p[i] != nullptr ? b[i] : 0; }
+}
+
+}  // namespace
+
+int gbwt_b200_index_export_ipc(const gbwt_b200_index* ix, void** blob, size_t* len) {
+    if (int rc = check_index(ix)) return rc;
+    if (blob == nullptr || len == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null output");
+    *blob = nullptr; *len = 0;
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaDeviceSynchronize());  // everything the build enqueued has landed
+    IpcHeader h;
+    std::memset(&h, 0, sizeof(h));
+    h.magic = IPC_MAGIC; h.version = 1;
+    h.sequences = ix->sequences; h.size = ix->size; h.offset = ix->offset; h.alphabet_size = ix->alphabet_size; h.flags = ix->flags;
+    h.records = ix->view.records; h.endmarker_len = ix->view.endmarker_len; h.bidirectional = ix->view.bidirectional;
+    h.edges_valid = ix->view.edges_valid; h.walk_limit = ix->view.walk_limit;
+    for (int i = 0; i < 4; i++) h.bytes[i] = ix->bytes[i];
+    h.skip_bytes = ix->skip_bytes;
+    for (int i = 0; i < FMT_COUNT; i++) h.format_counts[i] = ix->format_counts[i];
+    h.edges_total = ix->edges_total; h.edges_local = ix->edges_local;
+    h.window_ok = ix->window_ok; h.window_suits = ix->window_suits; h.window = ix->window;
+    h.ckpt_ok = ix->ckpt_ok; h.ckpt_shift = ix->ckpt_shift; h.ckpt_entries = ix->ckpt_entries; h.ckpt_bytes = ix->ckpt_bytes;
+    h.ckpt_build_us = ix->ckpt_build_us; h.ckpt_max_segments = ix->ckpt.max_segments;
+    h.has_graph = ix->has_graph; h.graph_sequences = ix->graph.sequences; h.graph_bytes = ix->graph_bytes;
+    h.source_device = static_cast<uint64_t>(ix->device);
+    void* ptrs[IPC_ARRAYS];
+    uint64_t sizes[IPC_ARRAYS];
+    ipc_arrays(ix, ptrs, sizes);
+    for (int i = 0; i < IPC_ARRAYS; i++) {
+        h.arrays[i].bytes = sizes[i];
+        if (sizes[i] > 0) CUDA_TRY(cudaIpcGetMemHandle(&h.arrays[i].handle, ptrs[i]));
+    }
+    GBWT_B200_GUARDED(
+        std::vector<uint8_t> out(reinterpret_cast<const uint8_t*>(&h), reinterpret_cast<const uint8_t*>(&h) + sizeof(h));
+        put_tags_blob(out, ix->carried.tags); put_tags_blob(out, ix->carried.gbz_tags);
+        put_blob(out, ix->carried.da_samples.data(), ix->carried.da_samples.size());
+        put_blob(out, ix->carried.metadata.data(), ix->carried.metadata.size());
+        put_blob(out, ix->carried.graph_section.data(), ix->carried.graph_section.size());
+        void* mem = std::malloc(out.size());
+        if (mem == nullptr) return fail(GBWT_B200_E_IO, "out of memory");
+        std::memcpy(mem, out.data(), out.size());
+        *blob = mem; *len = out.size();
+        return GBWT_B200_OK;
+    )
+}
+
+int gbwt_b200_index_import_ipc(const void* blob, size_t len, int device, gbwt_b200_index** out) {
+    if (out == nullptr || blob == nullptr) return fail(GBWT_B200_E_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (len < sizeof(IpcHeader)) return fail(GBWT_B200_E_INVALID_DATA, "not an exported index");
+    IpcHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != IPC_MAGIC || h.version != 1) return fail(GBWT_B200_E_INVALID_DATA, "not an exported index");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(GBWT_B200_E_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return fail(GBWT_B200_E_ARGUMENT, "invalid device ordinal");
+    DeviceScope scope(device);
+    if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
+    GBWT_B200_GUARDED(
+        gbwt_b200_index* ix = new gbwt_b200_index();
+        ix->device = device;
+        cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device);
+        ix->sequences = h.sequences; ix->size = h.size; ix->offset = h.offset; ix->alphabet_size = h.alphabet_size; ix->flags = h.flags;
+        for (int i = 0; i < 4; i++) ix->bytes[i] = h.bytes[i];
+        ix->skip_bytes = h.skip_bytes;
+        for (int i = 0; i < FMT_COUNT; i++) ix->format_counts[i] = h.format_counts[i];
+        ix->edges_total = h.edges_total; ix->edges_local = h.edges_local;
+        ix->window_ok = h.window_ok != 0; ix->window_suits = h.window_suits != 0; ix->window = h.window;
+        BlobReader rd{static_cast<const uint8_t*>(blob), len, sizeof(IpcHeader)};
+        rd.tags(ix->carried.tags); rd.tags(ix->carried.gbz_tags);
+        ix->carried.da_samples = rd.bytes(); ix->carried.metadata = rd.bytes(); ix->carried.graph_section = rd.bytes();
+        if (!rd.ok) { delete ix; return fail(GBWT_B200_E_INVALID_DATA, "truncated exported index"); }
+        // the arrays: open the exporter's allocation, copy it device to device, close it
+        void** slots[IPC_ARRAYS] = {&ix->d_desc, &ix->d_bodies, &ix->d_edges, &ix->d_endmarker, &ix->d_skips, &ix->d_stage_body, &ix->d_seq_len,
+                                    &ix->d_dna_len, &ix->d_ckpt_table, &ix->d_ckpt_first, &ix->d_label_starts, &ix->d_label_bytes};
+        int rc = GBWT_B200_OK;
+        for (int i = 0; i < IPC_ARRAYS && rc == GBWT_B200_OK; i++) {
+            if (h.arrays[i].bytes == 0) continue;
+            void* remote = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&remote, h.arrays[i].handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaIpcOpenMemHandle"); break; }
+            e = cudaMalloc(slots[i], std::max<size_t>(h.arrays[i].bytes, 256));
+            if (e == cudaSuccess) e = cudaMemcpy(*slots[i], remote, h.arrays[i].bytes, cudaMemcpyDefault);
+            cudaIpcCloseMemHandle(remote);
+            if (e != cudaSuccess) rc = cuda_fail(e, "copy of an exported array");
+        }
+        if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+        // buffers that an exporter may lack (no checkpoints, no graph) but every handle owns
+        const size_t seq_bytes = std::max<size_t>(256, h.sequences * sizeof(uint64_t));
+        if (ix->d_seq_len == nullptr && (cudaMalloc(&ix->d_seq_len, seq_bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, seq_bytes) != cudaSuccess))
+            rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
+        if (rc == GBWT_B200_OK && ix->d_dna_len == nullptr &&
+            (cudaMalloc(&ix->d_dna_len, seq_bytes) != cudaSuccess || cudaMemset(ix->d_dna_len, 0xFE, seq_bytes) != cudaSuccess))
+            rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
+        if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        IndexView& v = ix->view;
+        v.desc = static_cast<const RecordDesc*>(ix->d_desc);
+        v.bodies = static_cast<const Unit16*>(ix->d_bodies);
+        v.edges = static_cast<const Edge*>(ix->d_edges);
+        v.endmarker = static_cast<const Edge*>(ix->d_endmarker);
+        v.records = h.records; v.offset = h.offset; v.alphabet_size = h.alphabet_size; v.sequences = h.sequences;
+        v.endmarker_len = h.endmarker_len; v.bidirectional = static_cast<uint32_t>(h.bidirectional);
+        v.skips = static_cast<const Unit16*>(ix->d_skips);
+        v.edges_valid = static_cast<uint32_t>(h.edges_valid);
+        v.walk_limit = h.walk_limit;
+        v.stage_body = static_cast<const uint32_t*>(ix->d_stage_body);
+        if (h.ckpt_ok) {
+            ix->ckpt.table = static_cast<const Checkpoint*>(ix->d_ckpt_table);
+            ix->ckpt.first = static_cast<const uint32_t*>(ix->d_ckpt_first);
+            ix->ckpt.seq_len = static_cast<const uint64_t*>(ix->d_seq_len);
+            ix->ckpt.max_segments = static_cast<uint32_t>(h.ckpt_max_segments);
+            ix->ckpt_shift = static_cast<uint32_t>(h.ckpt_shift); ix->ckpt_entries = h.ckpt_entries; ix->ckpt_bytes = h.ckpt_bytes;
+            ix->ckpt_build_us = h.ckpt_build_us;
+            ix->ckpt_ok = true;
+        }
+        if (h.has_graph) {
+            ix->graph.starts = static_cast<const uint64_t*>(ix->d_label_starts);
+            ix->graph.bytes = static_cast<const uint8_t*>(ix->d_label_bytes);
+            ix->graph.sequences = h.graph_sequences;
+            ix->graph_bytes = h.graph_bytes;
+            ix->has_graph = true;
+        }
+        *out = ix;
+        return GBWT_B200_OK;
+    )
 }
 
 int gbwt_b200_index_serialize(const gbwt_b200_index* ix, void** image, size_t* len) { return serialize_index(ix, false, image, len); }

@@ -112,6 +112,13 @@ GBWT_B200_API int gbwt_b200_index_save_file(const gbwt_b200_index* index, const 
  * without node labels. */
 GBWT_B200_API int gbwt_b200_index_serialize_gbz(const gbwt_b200_index* index, void** image, size_t* len);
 GBWT_B200_API int gbwt_b200_index_save_gbz_file(const gbwt_b200_index* index, const char* path);
+/* Build once, replicate over NVLink (multi-GPU jobs: one process per GPU, the same index on every GPU). The exporting
+ * process describes its index in a small blob (scalars, the carried tags / metadata, one CUDA IPC handle per device
+ * array; gbwt_b200_free() it); every other process of the node imports it: the arrays are copied device to device from
+ * the exporter's GPU into the importer's `device`. The exporter must keep its index alive until the imports are done.
+ * The imported handle is independent afterwards and answers exactly like one built from the same image. */
+GBWT_B200_API int gbwt_b200_index_export_ipc(const gbwt_b200_index* index, void** blob, size_t* len);
+GBWT_B200_API int gbwt_b200_index_import_ipc(const void* blob, size_t len, int device, gbwt_b200_index** out);
 GBWT_B200_API void gbwt_b200_free(void* p);
 GBWT_B200_API void gbwt_b200_index_destroy(gbwt_b200_index* index);
 /* Message of the last failure on the calling thread (never NULL). */

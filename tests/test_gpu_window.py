@@ -219,3 +219,44 @@ def test_checkpoints_on_an_index_with_invalid_edge_targets(b200):
     o_off, o_nodes = g.extract_batch(ids)
     offsets, nodes, lengths = e.extract(ids)
     assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes) and lengths[2] == np.uint64(2**64 - 1)
+
+
+# ---- build once, replicate (CUDA IPC export / import) ----------------------------------------------------------------
+
+def _ipc_child(blob, pats, ids, conn):
+    import numpy as np
+    import gbwt_rs_b200 as b200
+    try:
+        e = b200.GBWT.import_ipc(blob, device=0)
+        offsets, nodes, lengths = e.extract(ids)
+        conn.send(("ok", e.find_extend(pats), offsets, nodes, e.checkpoint_info(), e.window_info()["can_run"], e.serialize()))
+    except Exception as exc:  # pragma: no cover
+        conn.send(("error", repr(exc)))
+    conn.close()
+
+
+def test_exported_index_is_imported_by_another_process(b200, monkeypatch):
+    # rank 0 builds, the other ranks import: the arrays are copied device to device through CUDA IPC handles
+    import multiprocessing as mp
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", "6")
+    S, H, seed = 900, 32, 11
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, checkpoints=True)
+    pats = synth.patterns(S, H, seed, n=30_000, k=32)
+    ids = np.arange(2 * H, dtype=np.uint64)
+    blob = e.export_ipc()
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    proc = ctx.Process(target=_ipc_child, args=(blob, pats, ids, child))
+    proc.start()
+    msg = parent.recv()
+    proc.join(timeout=60)
+    assert msg[0] == "ok", msg
+    _, states, offsets, nodes, ckpt, can_run, image = msg
+    assert pc.states_equal(states, g.find_extend_batch(pats))
+    o_off, o_nodes = g.extract_batch(ids)
+    assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+    assert ckpt["present"] and ckpt["entries"] == e.checkpoint_info()["entries"] and can_run == 1
+    assert image == e.serialize()
+    with pytest.raises(b200.GBWTError):
+        b200.GBWT.import_ipc(b"not a blob" * 100)
