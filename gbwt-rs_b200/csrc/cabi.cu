@@ -385,21 +385,17 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
         const uint64_t items = ((m + 31) / 32) * static_cast<uint64_t>(std::max<uint32_t>(1, ix->ckpt.max_segments));
         CheckpointView cv = ix->ckpt;
         cv.max_segments = std::max<uint32_t>(1, cv.max_segments);
-        // CTA size (GBWT_B200_EXTRACT_THREADS): the warps of a CTA take consecutive items, i.e. the same segment of
-        // neighbouring sequences, and share the records through L1
-        const int threads = env_int("GBWT_B200_EXTRACT_THREADS", 256);
-        const size_t tile_bytes = static_cast<size_t>(threads / 32) * 32 * TILE_STRIDE * sizeof(uint64_t);
+        cv.discard = env_int("GBWT_B200_EXTRACT_DISCARD", 0) != 0 ? 1u : 0u;
+        cv.lookahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_LOOKAHEAD", 256)));  // measured: +4 % over none
+        // (the warps of a CTA take consecutive items, i.e. the same segment of neighbouring sequences; a 1024-thread CTA that
+        // holds one segment of 1024 sequences was measured 8 % slower than 256-thread CTAs)
+        constexpr int threads = BLOCK_THREADS;
+        const size_t tile_bytes = static_cast<size_t>(threads / 32) * 32 * TILE_STRIDE * sizeof(uint32_t);
         const uint64_t ctas_wanted = (items * 32 + threads - 1) / threads;
-        if (threads == 1024) {
-            const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count))));
-            auto kernel = ix->view.edges_valid ? k_extract_checkpointed<false, 1024> : k_extract_checkpointed<true, 1024>;
-            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_bytes)));
-            kernel<<<grid, 1024, tile_bytes, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
-        } else {
-            const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count) * 8)));
-            auto kernel = ix->view.edges_valid ? k_extract_checkpointed<false, 256> : k_extract_checkpointed<true, 256>;
-            kernel<<<grid, 256, tile_bytes, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
-        }
+        const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count) * 8)));
+        auto kernel = ix->view.edges_valid ? k_extract_checkpointed<false, threads> : k_extract_checkpointed<true, threads>;
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_bytes)));
+        kernel<<<grid, threads, tile_bytes, s>>>(ix->view, cv, ids, m, out_offsets, base, nodes, lengths);
         return launch_done("k_extract_checkpointed");
     }
     // Up to 64 Ki sequences: one warp each (GBWT_B200_EXTRACT_STRIDE overrides: threads per sequence, 32 = warp mode).
@@ -789,7 +785,7 @@ int build_checkpoints(gbwt_b200_index* ix) {
     uint32_t max_segments = 0;
     for (uint64_t i = 0; i < v.sequences; i++) max_segments = std::max(max_segments, host_first[i + 1] - host_first[i]);
     ix->d_ckpt_table = table; ix->d_ckpt_first = first;
-    ix->ckpt.table = table; ix->ckpt.first = first; ix->ckpt.seq_len = seq_len; ix->ckpt.max_segments = max_segments;
+    ix->ckpt.table = table; ix->ckpt.first = first; ix->ckpt.seq_len = seq_len; ix->ckpt.max_segments = max_segments; ix->ckpt.discard = 0; ix->ckpt.lookahead = 0;
     ix->ckpt_shift = shift; ix->ckpt_entries = used;
     ix->ckpt_bytes = used * sizeof(Checkpoint) + (v.sequences + 1) * sizeof(uint32_t);
     ix->ckpt_build_us = static_cast<uint64_t>(ms * 1000.0f);

@@ -1245,6 +1245,8 @@ struct CheckpointView {
     const uint32_t* first;     // [sequences + 1]: slots of sequence s are table[first[s] .. first[s + 1])
     const uint64_t* seq_len;   // [sequences]
     uint32_t max_segments;     // most checkpoints any sequence has
+    uint32_t discard;          // measurement only (GBWT_B200_EXTRACT_DISCARD=1): walk, but do not store the nodes
+    uint32_t lookahead;        // records ahead of the walks at which a warp touches the index once per round (0 = off)
 };
 
 // Work item (segment j, block of 32 batch entries): lane l walks segment j of sequence ids[32 * block + l] from its
@@ -1255,9 +1257,96 @@ struct CheckpointView {
 // Output: a first version stored every node straight from its lane, 8 bytes to 32 different rows per instruction. ncu
 // (profiles/r2_extract_checkpointed_v1_ncu.txt): 1.7 G partial-sector writes churn through L2, evict the index (L2 read
 // hit rate 18 %) and the walks wait on DRAM for every record -- 39 G LF steps/s. Now every lane parks its nodes in a row
-// of a shared-memory tile, and when a row is nearly full the warp writes all rows out, half a warp per row: 128
-// contiguous bytes per row with streaming stores, so L2 sees whole sectors that it need not keep.
-constexpr uint32_t TILE_NODES = 16, TILE_STRIDE = 17;  // nodes per lane between flushes; row stride in 8-byte words
+// of a shared-memory tile (as 32-bit values), and when a row is nearly full the warp writes all rows out, up to 512
+// contiguous bytes per row with streaming stores: whole sectors that L2 need not keep, in pieces long enough for DRAM
+// (with 128-byte pieces the 300 k concurrent output streams ran at 1.4 TB/s, every piece opening a DRAM page of its own).
+constexpr uint32_t TILE_NODES = 64, TILE_STRIDE = 65;  // nodes (32-bit) per lane between flushes; row stride in words
+
+// Index loads of the segment walks: the output of an extraction streams tens of GB through L2 and, even written with
+// evict-first stores, pushed the index out (L2 read hit rate 9 % in profiles/r2_extract_checkpointed_v2_ncu.txt: every
+// record fetch went to DRAM behind the writes). These loads ask L2 to keep what they touch (evict_last).
+__device__ __forceinline__ uint64_t keep_policy() {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+__device__ __forceinline__ void load_sector_keep(const Unit16* p, uint64_t policy, Quad& lo, Quad& hi) {
+    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ Quad load_quad_keep(const Unit16* p, uint64_t policy) {
+    Quad q;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p), "l"(policy));
+    return q;
+}
+
+// State of one lane's segment walk. `left` = nodes of the segment still to be emitted (0 = done).
+struct SegmentLane {
+    uint32_t node, offset, left, parked;
+};
+
+// Descriptor + shortcut of node v. A node without a record (only possible on an index with invalid edge targets) gets
+// an all-zero descriptor: length 0, so the walk emits the node and ends there, like GBWT::forward returning None.
+template <bool CHECKED>
+__device__ __forceinline__ void load_segment_record(const RecordDesc* descs, const Unit16* skips, uint32_t base, uint32_t records,
+                                                    uint64_t keep, uint32_t v, Desc& d, Quad& k) {
+    uint32_t rec = v - base;
+    if (CHECKED && rec - 1u >= records - 1u) {
+        d.a.x = d.a.y = d.a.z = d.a.w = d.b.x = d.b.y = d.b.z = d.b.w = 0;
+        k.x = k.y = k.z = k.w = 0;
+        return;
+    }
+    rec = rec < records ? rec : records - 1u;  // (v == 0, the endmarker as a successor: any valid address will do, the result is unused)
+    load_sector_keep(reinterpret_cast<const Unit16*>(descs + rec), keep, d.a, d.b);
+    k = load_quad_keep(skips + rec, keep);
+}
+
+// One step of a segment walk: emits the current node (whose record is in cur_d / cur_k) and, over a two-hop shortcut, its
+// successor; leaves the record of the node it lands on in nxt_d / nxt_k. The caller alternates the two register sets, so
+// no descriptor is ever copied. The landing record over edge 0 is requested BEFORE the block that decides the edge is
+// looked at: in a bubble both edges land on the same node and a step is one memory round trip; otherwise edge 1 pays a
+// second one.
+template <bool CHECKED>
+__device__ __forceinline__ void segment_step(SegmentLane& st, const Desc& cur_d, const Quad& cur_k, Desc& nxt_d, Quad& nxt_k, uint32_t* row,
+                                             const RecordDesc* descs, const Unit16* bodies, const Unit16* skips, const Edge* edges,
+                                             uint32_t base, uint32_t records, uint64_t keep) {
+    row[st.parked++] = st.node;
+    const uint32_t fmt = cur_d.fmt(), at = st.offset;
+    if (at >= cur_d.total_len()) { st.left = 0; return; }  // GBWT::forward -> None (an empty record has length 0)
+    if (fmt == FMT_SINGLE || fmt == FMT_DENSE2) {
+        const uint32_t land0 = cur_k.x != 0 ? cur_k.x : cur_d.node0();
+        load_segment_record<CHECKED>(descs, skips, base, records, keep, land0, nxt_d, nxt_k);  // (node 0: the endmarker's record, unused)
+        uint32_t b = 0, r = at;
+        if (fmt == FMT_DENSE2) {
+            const uint32_t blk = __umulhi(at, 0xAAAAAAABu) >> 7;  // at / 192
+            Quad lo, hi;
+            load_sector_keep(bodies + cur_d.body() + 2u * blk, keep, lo, hi);
+            const uint32_t ones = dense_block_rank_lean(lo, hi, at - blk * DENSE_BITS, b);
+            r = b ? ones : at - ones;
+        }
+        const uint32_t v = b ? cur_d.node1() : cur_d.node0();
+        const uint32_t w = b ? cur_k.z : cur_k.x;
+        if (v == 0) { st.left = 0; return; }  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+        uint32_t advance = 1;
+        if (w != 0) {
+            if (st.left > 1) row[st.parked++] = v;
+            st.node = w; st.offset = (b ? cur_k.w : cur_k.y) + r;
+            advance = 2;
+        } else {
+            st.node = v; st.offset = (b ? cur_d.offset1() : cur_d.offset0()) + r;
+        }
+        st.left = st.left > advance ? st.left - advance : 0;
+        if (st.left != 0 && st.node != land0) load_segment_record<CHECKED>(descs, skips, base, records, keep, st.node, nxt_d, nxt_k);
+    } else {
+        const uint64_t next = forward_other_record(bodies, edges, cur_d.a.x, cur_d.a.y, cur_d.a.z, cur_d.a.w, cur_d.b.x, cur_d.b.y, cur_d.b.z,
+                                                   cur_d.b.w, at);
+        if (next == 0) { st.left = 0; return; }
+        st.node = static_cast<uint32_t>(next); st.offset = static_cast<uint32_t>(next >> 32);
+        st.left -= 1;
+        if (st.left != 0) load_segment_record<CHECKED>(descs, skips, base, records, keep, st.node, nxt_d, nxt_k);
+    }
+}
 
 template <bool CHECKED, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, CheckpointView cv, const uint64_t* __restrict__ ids,
@@ -1265,12 +1354,15 @@ __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, 
                                                                          uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     extern __shared__ __align__(16) unsigned char tile_bytes[];  // [THREADS / 32][32][TILE_STRIDE] words
-    uint64_t (*tiles)[32][TILE_STRIDE] = reinterpret_cast<uint64_t (*)[32][TILE_STRIDE]>(tile_bytes);
+    uint32_t (*tiles)[32][TILE_STRIDE] = reinterpret_cast<uint32_t (*)[32][TILE_STRIDE]>(tile_bytes);
     const uint32_t lane = threadIdx.x & 31u;
-    uint64_t (*tile)[TILE_STRIDE] = tiles[threadIdx.x >> 5];
+    uint32_t (*tile)[TILE_STRIDE] = tiles[threadIdx.x >> 5];
+    uint32_t* const row = tile[lane];
+    const uint64_t keep = keep_policy();
     const RecordDesc* const descs = ix.desc;
     const Unit16* const bodies = ix.bodies;
     const Unit16* const skips = ix.skips;
+    const Edge* const edges = ix.edges;
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
     const uint64_t blocks = (m + 31) / 32;
     const uint64_t items = blocks * cv.max_segments;
@@ -1279,10 +1371,9 @@ __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, 
     for (uint64_t item = warp; item < items; item += warps) {
         const uint64_t j = item / blocks, i = (item - j * blocks) * 32 + lane;
         // this lane's segment, if it has one
-        bool active = false;
-        uint32_t node = 0, offset = 0;
-        uint64_t index = 0, end = 0, cap = 0;
-        uint64_t* dst = nodes;
+        SegmentLane st;
+        st.node = 0; st.offset = 0; st.left = 0; st.parked = 0;
+        uint64_t* dst = nodes;  // where node number `parked` of the tile row goes
         if (i < m) {
             const uint64_t id = __ldg(ids + i);
             if (id >= ix.sequences) {
@@ -1293,87 +1384,92 @@ __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, 
                 const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
                 if (j < count) {
                     const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
-                    cap = hi > lo ? hi - lo : 0;
-                    dst = nodes + (lo - base_offset);
+                    const uint64_t cap = hi > lo ? hi - lo : 0;
                     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j));
-                    node = raw.x; offset = raw.y;
-                    index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
-                    end = len;
+                    st.node = raw.x; st.offset = raw.y;
+                    const uint64_t index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
+                    uint64_t end = len;
                     if (j + 1 < count) {
                         const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j + 1));
                         end = (static_cast<uint64_t>(next.w) << 32) | next.z;
                     }
                     if (end > cap) end = cap;  // nothing beyond the caller's slot is written
-                    active = index < end;
+                    const uint64_t todo = end > index ? end - index : 0;
+                    st.left = todo < 0xFFFFFFFFull ? static_cast<uint32_t>(todo) : 0xFFFFFFFFu;
+                    dst = nodes + (lo - base_offset) + index;
                 }
             }
         }
-        uint32_t parked = 0;          // nodes in this lane's row of the tile
-        uint64_t row_start = index;   // sequence index of the first of them
+        Desc d0, d1;
+        Quad k0, k1;
+        if (st.left != 0) load_segment_record<CHECKED>(descs, skips, base, records, keep, st.node, d0, k0);
+        // Look-ahead (see the round loop): where the warp was a round ago, the bodies it has yet to touch, and the words
+        // its touches returned (folded into `sink` a round later, so that nothing ever waits for them).
+        uint32_t prev_rec = 0xFFFFFFFFu, ahead_body = 0, ahead_span = 0;
+        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, sink = 0;
         for (;;) {
-            if (active) {
-                tile[lane][parked++] = node;
-                uint32_t rec = node - base;
-                bool go = true;
-                if (CHECKED) go = rec - 1u < records - 1u;
-                else rec = rec < records ? rec : records - 1u;
-                if (go) {
-                    Desc d;
-                    load_sector(reinterpret_cast<const Unit16*>(descs + rec), d.a, d.b);
-                    const Quad k = load_quad(skips + rec);
-                    const uint32_t fmt = d.fmt(), at = offset;
-                    if (at >= d.total_len()) {
-                        go = false;  // GBWT::forward -> None (an empty record has length 0)
-                    } else if (fmt == FMT_SINGLE || fmt == FMT_DENSE2) {
-                        uint32_t b = 0, r = at;
-                        if (fmt == FMT_DENSE2) {
-                            const uint32_t blk = __umulhi(at, 0xAAAAAAABu) >> 7;  // at / 192
-                            Quad lo, hi;
-                            load_sector(bodies + d.body() + 2u * blk, lo, hi);
-                            const uint32_t ones = dense_block_rank_lean(lo, hi, at - blk * DENSE_BITS, b);
-                            r = b ? ones : at - ones;
-                        }
-                        const uint32_t v = b ? d.node1() : d.node0();
-                        const uint32_t w = b ? k.z : k.x;
-                        if (v == 0) {
-                            go = false;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
-                        } else if (w != 0) {
-                            if (index + 1 < end) tile[lane][parked++] = v;
-                            node = w; offset = (b ? k.w : k.y) + r;
-                            index += 2;
-                        } else {
-                            node = v; offset = (b ? d.offset1() : d.offset0()) + r;
-                            index += 1;
-                        }
-                    } else {
-                        const uint64_t next = forward_other_record(bodies, ix.edges, d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w, at);
-                        if (next == 0) go = false;
-                        node = static_cast<uint32_t>(next); offset = static_cast<uint32_t>(next >> 32);
-                        index += 1;
+            // The 32 lanes walk the same stretch of the graph (the same segment of 32 sequences), and so do the other
+            // warps of the CTA and the CTAs next to it: whoever gets to a record first waits for DRAM, and everybody
+            // else then waits with it. Node identifiers follow the graph's topological order, so once per round the
+            // warp touches the records it is heading for -- lane l the descriptors and shortcuts of 8 records
+            // `lookahead + 8 l` records further on, and the bodies of the 8 records it touched a round ago (their
+            // offset comes from the descriptor that touch returned) -- and the walks find them in L2 / L1.
+            if (cv.lookahead != 0) {
+                sink ^= t0 ^ t1 ^ t2 ^ t3 ^ t4 ^ t5;
+                const unsigned walking = __ballot_sync(FULL, st.left != 0);
+                if (walking != 0) {
+                    const uint32_t here = __shfl_sync(FULL, st.node, __ffs(static_cast<int>(walking)) - 1) - base;
+                    const bool up = prev_rec == 0xFFFFFFFFu ? (here & 1u) == ((base & 1u) ^ 0u) : here >= prev_rec;
+                    prev_rec = here;
+                    for (uint32_t u = 0; u < ahead_span; u += 8) {  // bodies: 128-byte lines, at most four per lane
+                        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(t5) : "l"(bodies + ahead_body + u), "l"(keep));
+                    }
+                    const uint32_t step = cv.lookahead + 8u * lane;
+                    uint32_t target = up ? here + step : here - step - 7u;
+                    if (up ? (target < here || target + 8u > records) : (target > here)) target = up ? (records > 8u ? records - 8u : 0u) : 0u;
+                    if (records >= 8u) {
+                        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(t0) : "l"(&descs[target].body), "l"(keep));
+                        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(t1) : "l"(&descs[target + 4u].body), "l"(keep));
+                        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(t2) : "l"(skips + target), "l"(keep));
+                        asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(t3) : "l"(&descs[target + 7u].body), "l"(keep));
+                        t4 = target;
                     }
                 }
-                active = go && index < end;
             }
-            const bool any_active = __any_sync(FULL, active);
-            if (__any_sync(FULL, parked + 2 > TILE_NODES) || !any_active) {
-                // all rows out, half a warp per row: lanes 0-15 row 2p, lanes 16-31 row 2p + 1
-                __syncwarp();
-                const uint64_t row_addr = reinterpret_cast<uint64_t>(dst + row_start);
-                const uint32_t t = lane & 15u;
+
+            // A round: as many steps as fit the tile rows whatever the lanes do (a step parks at most two nodes), two
+            // per iteration on alternating register sets. No votes inside: lanes that are done just sit the round out.
+#pragma unroll 1
+            for (uint32_t step = 0; step < TILE_NODES / 4; step++) {
+                if (st.left != 0) segment_step<CHECKED>(st, d0, k0, d1, k1, row, descs, bodies, skips, edges, base, records, keep);
+                if (st.left != 0) segment_step<CHECKED>(st, d1, k1, d0, k0, row, descs, bodies, skips, edges, base, records, keep);
+            }
+            // all rows out, one after the other: up to 512 contiguous bytes per row, 256 per store instruction
+            __syncwarp();
+            const uint64_t row_addr = reinterpret_cast<uint64_t>(dst);
 #pragma unroll 4
-                for (uint32_t p = 0; p < 16; p++) {
-                    const uint32_t row = 2u * p + (lane >> 4);
-                    const uint32_t n = __shfl_sync(FULL, parked, row);
-                    const uint32_t a_lo = __shfl_sync(FULL, static_cast<uint32_t>(row_addr), row);
-                    const uint32_t a_hi = __shfl_sync(FULL, static_cast<uint32_t>(row_addr >> 32), row);
-                    if (t < n) __stcs(reinterpret_cast<uint64_t*>((static_cast<uint64_t>(a_hi) << 32) | a_lo) + t, tile[row][t]);
-                }
-                __syncwarp();
-                row_start += parked;
-                parked = 0;
-                if (!any_active) break;
+            for (uint32_t r = 0; r < 32; r++) {
+                const uint32_t n = __shfl_sync(FULL, st.parked, r);
+                const uint32_t a_lo = __shfl_sync(FULL, static_cast<uint32_t>(row_addr), r);
+                const uint32_t a_hi = __shfl_sync(FULL, static_cast<uint32_t>(row_addr >> 32), r);
+                uint64_t* to = reinterpret_cast<uint64_t*>((static_cast<uint64_t>(a_hi) << 32) | a_lo);
+                if (cv.discard) continue;
+                if (lane < n) __stcs(to + lane, static_cast<uint64_t>(tile[r][lane]));
+                if (lane + 32 < n) __stcs(to + lane + 32, static_cast<uint64_t>(tile[r][lane + 32]));
             }
+            __syncwarp();
+            dst += st.parked;
+            st.parked = 0;
+            if (cv.lookahead != 0) {
+                // by now (a round later) the touched descriptors have arrived: the bodies of this lane's 8 records lie between
+                // the body offset of its first record and that of its last (bodies lie in record order)
+                const uint32_t lo = t0 < t3 ? t0 : t3, hi = t0 < t3 ? t3 : t0;
+                ahead_body = lo;
+                ahead_span = hi - lo < 32u ? hi - lo + 8u : 32u;
+            }
+            if (!__any_sync(FULL, st.left != 0)) break;
         }
+        if (sink == 0x9E3779B9u && lengths != nullptr && m == ~size_t(0)) lengths[0] = sink;  // (keeps the touches alive; never true)
     }
 }
 

@@ -107,6 +107,13 @@ if args.extract:
             print(json.dumps({"extract": "checkpointed", "shift": shift, "threads": threads, "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6,
                               "ok": ok, "checksum_ok": chk == checksum}), flush=True)
         del os.environ["GBWT_B200_EXTRACT_THREADS"]
+        os.environ["GBWT_B200_EXTRACT_DISCARD"] = "1"
+        ms = timed(fn, args.reps)
+        del os.environ["GBWT_B200_EXTRACT_DISCARD"]
+        print(json.dumps({"extract": "checkpointed, walks only (nodes not stored)", "ms": ms, "g_lf_steps_per_s": m * length / ms / 1e6}), flush=True)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(); nodes.fill_(1); t1.record(); torch.cuda.synchronize()
+        print(json.dumps({"plain fill of the output buffer, ms": t0.elapsed_time(t1), "GB/s": nodes.numel() * 8 / t0.elapsed_time(t1) / 1e6}), flush=True)
         if shift != (args.ckpt_shifts.split(",")[-1] if args.ckpt_shifts else ""):
             del index
     if args.extract_plain:
