@@ -831,8 +831,9 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     }
     ix->edges_total = layout.edges_total; ix->edges_local = layout.edges_local;
     if (rc == GBWT_B200_OK) {
+        // per sequence: its length, then (behind all lengths) the three words of its signature (kernels.cuh, SigAcc)
         const size_t bytes = std::max<size_t>(256, parsed.sequences * sizeof(uint64_t));
-        if (cudaMalloc(&ix->d_seq_len, bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, bytes) != cudaSuccess ||
+        if (cudaMalloc(&ix->d_seq_len, 4 * bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, 4 * bytes) != cudaSuccess ||
             cudaMalloc(&ix->d_dna_len, bytes) != cudaSuccess || cudaMemset(ix->d_dna_len, 0xFE, bytes) != cudaSuccess) {
             rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
         }
@@ -1080,7 +1081,7 @@ void ipc_arrays(const gbwt_b200_index* ix, void* ptrs[IPC_ARRAYS], uint64_t size
     void* p[IPC_ARRAYS] = {ix->d_desc, ix->d_bodies, ix->d_edges, ix->d_endmarker, ix->d_skips, ix->d_stage_body, ix->d_seq_len,
                            ix->d_dna_len, ix->d_ckpt_table, ix->d_ckpt_first, ix->d_label_starts, ix->d_label_bytes};
     const uint64_t b[IPC_ARRAYS] = {ix->bytes[0], ix->bytes[1], ix->bytes[2], ix->bytes[3],
-                                    (ix->view.records + 1) * 16, (ix->view.records / STAGE_GRANULE + 2) * sizeof(uint32_t), seq_bytes, seq_bytes,
+                                    (ix->view.records + 1) * 16, (ix->view.records / STAGE_GRANULE + 2) * sizeof(uint32_t), 4 * seq_bytes, seq_bytes,
                                     ix->ckpt_ok ? ix->ckpt_entries * sizeof(Checkpoint) : 0,
                                     ix->ckpt_ok ? (ix->view.sequences + 1) * sizeof(uint32_t) : 0,
                                     ix->has_graph ? (ix->graph.sequences + 1) * 8 : 0,
@@ -1179,7 +1180,7 @@ int gbwt_b200_index_import_ipc(const void* blob, size_t len, int device, gbwt_b2
         if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
         // buffers that an exporter may lack (no checkpoints, no graph) but every handle owns
         const size_t seq_bytes = std::max<size_t>(256, h.sequences * sizeof(uint64_t));
-        if (ix->d_seq_len == nullptr && (cudaMalloc(&ix->d_seq_len, seq_bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, seq_bytes) != cudaSuccess))
+        if (ix->d_seq_len == nullptr && (cudaMalloc(&ix->d_seq_len, 4 * seq_bytes) != cudaSuccess || cudaMemset(ix->d_seq_len, 0xFE, 4 * seq_bytes) != cudaSuccess))
             rc = cuda_fail(cudaGetLastError(), "cudaMalloc(sequence lengths)");
         if (rc == GBWT_B200_OK && ix->d_dna_len == nullptr &&
             (cudaMalloc(&ix->d_dna_len, seq_bytes) != cudaSuccess || cudaMemset(ix->d_dna_len, 0xFE, seq_bytes) != cudaSuccess))

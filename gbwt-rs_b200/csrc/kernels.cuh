@@ -397,14 +397,79 @@ __device__ __forceinline__ void warp_lf_runs8(const IndexView& ix, const Desc& d
 // A warp-mode walk parks the nodes it visits one per lane and hands the sink a group of up to 32 of them at a
 // time: `count` nodes, the first of which is number `first` of the sequence.
 
+// ---- are the two strands of a path mirror images? -----------------------------------------------------------------------
+// The two-ended walks rest on sequence id ^ 1 being sequence id reversed and flipped (support::reverse_path,
+// src/support.rs:310-314). That is what "bidirectional" promises, but the flag is only a flag: on an index whose strands
+// differ somewhere a two-ended walk would splice two different paths. (Comparing the halves where they meet, as the first
+// version did, only proves that they agree THERE.) So every whole-sequence walk also leaves a signature of the sequence,
+// three 64-bit sums over its nodes n_j (flipped when the walk is on an odd, i.e. reverse, sequence id):
+//     A = sum a(n_j),   B = sum a(n_j) * j,   C = sum b(n_j)          (a, b: two 64-bit mixers)
+// If sequence o = id ^ 1 is the mirror image of sequence id, its node j is the flip of node len - 1 - j, hence
+//     A_o = A_id,   C_o = C_id,   B_o = (len - 1) * A_id - B_id       (mod 2^64)
+// and any difference in a node or in a position breaks one of the three with probability 1 - 2^-64. A sequence is walked
+// from both ends only when both strands have signatures and they agree; otherwise it is walked like the reference does.
+struct SeqSignature { uint64_t a, b, c; };
+
+__device__ __forceinline__ uint64_t sig_mix(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+struct SigAcc {
+    uint64_t a = 0, b = 0, c = 0;  // this lane's share
+    // the lane's node of a group: node number first + lane of the walk, if lane < count
+    __device__ __forceinline__ void add(uint64_t mine, uint32_t count, uint64_t first, uint64_t flip) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (lane >= count) return;
+        const uint64_t n = mine ^ flip, wa = sig_mix(n + 0x9E3779B97F4A7C15ull);
+        a += wa; b += wa * (first + lane); c += sig_mix(n ^ 0xD6E8FEB86659FD93ull);
+    }
+    __device__ __forceinline__ SeqSignature total() const {
+        SeqSignature s{a, b, c};
+#pragma unroll
+        for (uint32_t d = 16; d != 0; d >>= 1) {
+            s.a += __shfl_xor_sync(0xFFFFFFFFu, s.a, d);
+            s.b += __shfl_xor_sync(0xFFFFFFFFu, s.b, d);
+            s.c += __shfl_xor_sync(0xFFFFFFFFu, s.c, d);
+        }
+        return s;
+    }
+};
+
+// The signatures live behind the lengths in one allocation: seq_len[0 .. sequences), then three words per sequence.
+__device__ __forceinline__ uint64_t* signatures_of(uint64_t* seq_len, uint64_t sequences) { return seq_len + sequences; }
+__device__ __forceinline__ const uint64_t* signatures_of(const uint64_t* seq_len, uint64_t sequences) { return seq_len + sequences; }
+
+constexpr uint64_t SIG_UNKNOWN = 0xFEFEFEFEFEFEFEFEull;  // what cudaMemset(0xFE) leaves (as for the length cache below)
+
+__device__ __forceinline__ void store_signature(uint64_t* seq_sig, uint64_t id, const SeqSignature& s) {
+    seq_sig[3 * id] = s.a; seq_sig[3 * id + 1] = s.b; seq_sig[3 * id + 2] = s.c == SIG_UNKNOWN ? s.c + 1 : s.c;
+}
+
+// Both strands of sequence `id` have been walked and they are mirror images of each other.
+__device__ __forceinline__ bool strands_mirror(const uint64_t* seq_len, const uint64_t* seq_sig, uint64_t id, uint64_t sequences) {
+    const uint64_t other = id ^ 1ull;
+    if (id >= sequences || other >= sequences || seq_sig == nullptr) return false;
+    const uint64_t len = seq_len[id];
+    if (len == SIG_UNKNOWN || seq_len[other] != len) return false;
+    const uint64_t a = seq_sig[3 * id], b = seq_sig[3 * id + 1], c = seq_sig[3 * id + 2];
+    const uint64_t oa = seq_sig[3 * other], ob = seq_sig[3 * other + 1], oc = seq_sig[3 * other + 2];
+    if (c == SIG_UNKNOWN || oc == SIG_UNKNOWN) return false;
+    return a == oa && c == oc && ob == (len - 1) * a - b;
+}
+
 // GBWT::sequence(id): the node identifiers themselves, up to 256 contiguous bytes per group.
 struct NodeSink {
     static constexpr bool CHECKPOINTS = false;
     uint64_t* out;
     uint64_t cap;
+    uint64_t flip;  // 1 on a reverse (odd) sequence id: the signature is taken over the flipped nodes
+    SigAcc sig;
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
         if (lane < count && first + lane < cap) out[first + lane] = mine;
+        sig.add(mine, count, first, flip);
     }
     __device__ __forceinline__ void finish() {}
 };
@@ -418,9 +483,12 @@ struct HalfSink {
     uint64_t* out;
     uint64_t cap, len, lo, hi, probe, value;
     bool reverse;
+    uint64_t flip;  // signature of a whole-sequence walk (see SigAcc): 1 on an odd sequence id
+    SigAcc sig;
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
         const uint64_t j = first + lane;
+        sig.add(mine, count, first, flip);
         const uint64_t p = reverse ? len - 1 - j : j, node = reverse ? mine ^ 1ull : mine;
         const bool valid = lane < count && (!reverse || j < len);
         if (valid && p >= lo && p < hi && p < cap) out[p] = node;
@@ -475,6 +543,8 @@ struct DnaSink {
     // forward on the walked strand (= reverse on the requested one).
     uint64_t node_limit, probe, value, end;
     bool mirror;
+    uint64_t flip = 0;  // signature of a whole-sequence walk (SigAcc): 1 on an odd sequence id
+    SigAcc sig;
 
     __device__ __forceinline__ void copy_pending() {
         constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -529,6 +599,7 @@ struct DnaSink {
     }
     __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
+        sig.add(mine, count, first, flip);
         if (pending) copy_pending();
         const unsigned hit = __ballot_sync(0xFFFFFFFFu, lane < count && first + lane == probe);
         if (hit != 0) value = __shfl_sync(0xFFFFFFFFu, mirror ? mine ^ 1ull : mine, __ffs(static_cast<int>(hit)) - 1);
@@ -834,17 +905,21 @@ __global__ void __launch_bounds__(128) k_extract(IndexView ix, const uint64_t* _
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t i = warp; i < m; i += warps) {
-        NodeSink sink{nullptr, 0};
+        const uint64_t id = __ldg(ids + i);
+        NodeSink sink{nullptr, 0, id & 1ull, SigAcc{}};
         if (nodes != nullptr) {
             const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
             sink.out = nodes + (lo - base);
             sink.cap = hi > lo ? hi - lo : 0;
         }
-        const uint64_t id = __ldg(ids + i);
         const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
+        const SeqSignature signature = sink.sig.total();
         if ((threadIdx.x & 31u) == 0) {
             if (lengths != nullptr) lengths[i] = len;
-            if (seq_len != nullptr && id < ix.sequences) seq_len[id] = len;  // remembered for k_extract_split
+            if (seq_len != nullptr && id < ix.sequences) {  // remembered for k_extract_split
+                store_signature(signatures_of(seq_len, ix.sequences), id, signature);
+                seq_len[id] = len;
+            }
         }
     }
 }
@@ -855,9 +930,10 @@ constexpr uint64_t SEQ_LEN_UNKNOWN = 0xFEFEFEFEFEFEFEFEull;  // what cudaMemset(
 // the same path on the other strand, so it starts where sequence id ends. Once the length of a sequence is known
 // (any earlier k_extract, e.g. the sequence_lengths call that sized the output, leaves it in `seq_len`), two warps
 // of one CTA walk it from both ends and meet in the middle: twice the chains in flight, half the chain length.
-// Both produce the node at the meeting position; if they disagree (an index whose strands are not mirror images),
-// the first warp redoes the sequence from the front alone, which is what the reference does. One call site of the
-// walk serves all three cases, so the kernel stays at the register count of the plain one.
+// A sequence is only split when both of its strands have been walked whole before and their signatures say that they
+// are mirror images (strands_mirror above); the halves are still compared where they meet, and if they disagree the
+// first warp redoes the sequence from the front alone, which is what the reference does. One call site of the walk
+// serves all three cases, so the kernel stays at the register count of the plain one.
 template <bool CHECKED>
 __global__ void __launch_bounds__(64) k_extract_split(IndexView ix, const uint64_t* __restrict__ ids, size_t m,
                                                        const uint64_t* __restrict__ out_offsets, uint64_t base,
@@ -870,13 +946,14 @@ __global__ void __launch_bounds__(64) k_extract_split(IndexView ix, const uint64
         const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
         const uint64_t cap = hi > lo ? hi - lo : 0;
         const uint64_t known = id < ix.sequences ? seq_len[id] : SEQ_LEN_UNKNOWN;
-        bool split = known != SEQ_LEN_UNKNOWN && known >= 128;  // a short sequence is not worth two warps
+        // (a short sequence is not worth two warps)
+        bool split = known != SEQ_LEN_UNKNOWN && known >= 128 && strands_mirror(seq_len, signatures_of(seq_len, ix.sequences), id, ix.sequences);
         uint64_t len = known;
         // at most two rounds: the halves, then (only if they disagree where they meet) the whole sequence from the front
         for (;;) {
             const uint64_t mid = known / 2;  // both halves produce position `mid`; the far half writes it
             HalfSink sink;
-            sink.out = nodes + (lo - base); sink.cap = cap; sink.value = ~0ull;
+            sink.out = nodes + (lo - base); sink.cap = cap; sink.value = ~0ull; sink.flip = id & 1ull;
             if (!split) { sink.len = 0; sink.lo = 0; sink.hi = ~0ull; sink.probe = ~0ull; sink.reverse = false; }
             else if (half == 0) { sink.len = known; sink.lo = 0; sink.hi = mid; sink.probe = mid; sink.reverse = false; }
             else { sink.len = known; sink.lo = mid; sink.hi = known; sink.probe = mid; sink.reverse = true; }
@@ -885,7 +962,11 @@ __global__ void __launch_bounds__(64) k_extract_split(IndexView ix, const uint64
                                                                     !split ? ~0ull : (half == 0 ? mid + 1 : known - mid));
                 if (!split) {
                     len = walked;
-                    if (lane == 0 && id < ix.sequences) seq_len[id] = walked;
+                    const SeqSignature signature = sink.sig.total();
+                    if (lane == 0 && id < ix.sequences) {
+                        store_signature(signatures_of(seq_len, ix.sequences), id, signature);
+                        seq_len[id] = walked;
+                    }
                 } else if (lane == 0) {
                     meet[half] = sink.value;
                 }
@@ -938,7 +1019,9 @@ __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView gra
             sink.cap = hi > lo ? hi - lo : 0;
         }
         const uint64_t id = __ldg(ids + i);
+        sink.flip = id & 1ull;
         const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
+        const SeqSignature signature = sink.sig.total();
         if ((threadIdx.x & 31u) != 0) continue;
         if (len == ~0ull) {
             if (lengths != nullptr) lengths[i] = ~0ull;
@@ -946,6 +1029,7 @@ __global__ void __launch_bounds__(128) k_extract_dna(IndexView ix, GraphView gra
         }
         if (sink.out != nullptr && sink.written < sink.cap) sink.out[sink.written] = static_cast<uint8_t>(endmarker);
         if (lengths != nullptr) lengths[i] = sink.written + 1;
+        store_signature(signatures_of(seq_len, ix.sequences), id, signature);
         seq_len[id] = len;               // remembered for k_extract_dna_split
         dna_len[id] = sink.written + 1;
     }
@@ -967,7 +1051,8 @@ __global__ void __launch_bounds__(64) k_extract_dna_split(IndexView ix, GraphVie
         const uint64_t cap = hi > lo ? hi - lo : 0;
         const bool in_range = id < ix.sequences;
         const uint64_t known = in_range ? seq_len[id] : SEQ_LEN_UNKNOWN, known_dna = in_range ? dna_len[id] : SEQ_LEN_UNKNOWN;
-        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128;
+        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128 &&
+                     strands_mirror(seq_len, signatures_of(seq_len, ix.sequences), id, ix.sequences);
         uint64_t result = known_dna;
         for (;;) {
             const uint64_t mid = known / 2;
@@ -979,13 +1064,16 @@ __global__ void __launch_bounds__(64) k_extract_dna_split(IndexView ix, GraphVie
                 sink.end = known_dna - 1;
             }
             if (split || half == 0) {
+                sink.flip = id & 1ull;
                 const uint64_t walked = walk_sequence_warp<CHECKED>(ix, split && half == 1 ? id ^ 1ull : id, sink, ahead,
                                                                     !split ? ~0ull : (half == 0 ? mid + 1 : known - mid));
+                const SeqSignature signature = sink.sig.total();
                 if (lane == 0) {
                     if (!split) {
                         result = walked == ~0ull ? ~0ull : sink.written + 1;
                         if (walked != ~0ull) {
                             if (sink.written < cap) sink.out[sink.written] = static_cast<uint8_t>(endmarker);
+                            store_signature(signatures_of(seq_len, ix.sequences), id, signature);
                             seq_len[id] = walked;
                             dna_len[id] = sink.written + 1;
                         }
@@ -1031,6 +1119,8 @@ struct RelaySink {
     uint32_t slot;
     uint64_t probe, value;
     bool mirror;
+    uint64_t flip = 0;
+    SigAcc sig;
     __device__ __forceinline__ void post(uint32_t node, uint32_t count, uint64_t first) {
         const uint32_t lane = threadIdx.x & 31u;
         while (relay_flag(&ring->full[slot]) != 0) __nanosleep(40);
@@ -1045,6 +1135,7 @@ struct RelaySink {
         const uint32_t lane = threadIdx.x & 31u;
         const unsigned hit = __ballot_sync(0xFFFFFFFFu, lane < count && first + lane == probe);
         if (hit != 0) value = __shfl_sync(0xFFFFFFFFu, mirror ? mine ^ 1ull : mine, __ffs(static_cast<int>(hit)) - 1);
+        sig.add(mine, count, first, flip);
         post(static_cast<uint32_t>(mine), count, first);
     }
     __device__ __forceinline__ void finish() {}
@@ -1082,7 +1173,8 @@ __global__ void __launch_bounds__(96, 7) k_extract_dna_relay(IndexView ix, Graph
         uint8_t* out = bytes + (lo - base);
         const bool in_range = id < ix.sequences;
         const uint64_t known = in_range ? seq_len[id] : SEQ_LEN_UNKNOWN, known_dna = in_range ? dna_len[id] : SEQ_LEN_UNKNOWN;
-        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128;
+        bool split = known != SEQ_LEN_UNKNOWN && known_dna != SEQ_LEN_UNKNOWN && known >= 128 &&
+                     strands_mirror(seq_len, signatures_of(seq_len, ix.sequences), id, ix.sequences);
         uint64_t result = known_dna;
         for (;;) {
             const uint64_t mid = known / 2;
@@ -1091,13 +1183,17 @@ __global__ void __launch_bounds__(96, 7) k_extract_dna_relay(IndexView ix, Graph
             if (warp < 2) {
                 if (split || warp == 0) {
                     RelaySink sink{&rings[warp], 0, ~0ull, ~0ull, split && warp == 1};
+                    sink.flip = id & 1ull;
                     if (split) sink.probe = warp == 0 ? mid : known - 1 - mid;
                     const uint64_t walked = walk_sequence_warp<CHECKED>(ix, split && warp == 1 ? id ^ 1ull : id, sink, ahead,
                                                                         !split ? ~0ull : (warp == 0 ? mid + 1 : known - mid));
                     sink.post(0, RELAY_DONE, 0);
+                    const SeqSignature signature = sink.sig.total();
                     if (lane == 0) {
                         meet[warp] = sink.value;
                         if (warp == 0) walked_nodes = walked;
+                        // (a whole walk; its length is stored below by thread 0 once the speller is done)
+                        if (!split && walked != ~0ull) store_signature(signatures_of(seq_len, ix.sequences), id, signature);
                     }
                 }
             } else {
@@ -1193,7 +1289,8 @@ struct CheckpointSink {
     uint64_t pool_cap;
     uint32_t seq, shift;
     uint64_t next;  // first index that wants a checkpoint
-    __device__ __forceinline__ void group(uint64_t, uint32_t, uint64_t) {}
+    SigAcc sig;
+    __device__ __forceinline__ void group(uint64_t mine, uint32_t count, uint64_t first) { sig.add(mine, count, first, seq & 1u); }
     __device__ __forceinline__ void finish() {}
     // called at every flush of the walk (at most 32 nodes apart), so every multiple of the interval gets the first
     // flush at or after it
@@ -1217,9 +1314,13 @@ __global__ void __launch_bounds__(128) k_build_checkpoints(IndexView ix, uint32_
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) / 32;
     for (size_t id = warp; id < ix.sequences; id += warps) {
-        CheckpointSink sink{pool, pool_used, pool_cap, static_cast<uint32_t>(id), shift, 0};
+        CheckpointSink sink{pool, pool_used, pool_cap, static_cast<uint32_t>(id), shift, 0, SigAcc{}};
         const uint64_t len = walk_sequence_warp<CHECKED>(ix, id, sink, ahead);
-        if ((threadIdx.x & 31u) == 0) seq_len[id] = len;
+        const SeqSignature signature = sink.sig.total();
+        if ((threadIdx.x & 31u) == 0) {
+            store_signature(signatures_of(seq_len, ix.sequences), id, signature);
+            seq_len[id] = len;
+        }
     }
 }
 
@@ -1463,9 +1564,10 @@ __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, 
             if (cv.lookahead != 0) {
                 // by now (a round later) the touched descriptors have arrived: the bodies of this lane's 8 records lie between
                 // the body offset of its first record and that of its last (bodies lie in record order)
+                // (up to the START of the last one's body: whatever lies in between is inside the array)
                 const uint32_t lo = t0 < t3 ? t0 : t3, hi = t0 < t3 ? t3 : t0;
                 ahead_body = lo;
-                ahead_span = hi - lo < 32u ? hi - lo + 8u : 32u;
+                ahead_span = hi - lo < 32u ? hi - lo : 32u;
             }
             if (!__any_sync(FULL, st.left != 0)) break;
         }

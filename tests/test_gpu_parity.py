@@ -389,22 +389,44 @@ def test_two_ended_extraction(b200, monkeypatch):
         assert np.all(nodes[int(offsets[-1]):] == 0xABCD)
 
 
-def test_two_ended_extraction_checks_where_the_halves_meet(b200):
-    # An index flagged bidirectional whose odd sequences are NOT the reverse strands of the even ones: the halves
-    # disagree at the meeting node and every sequence is redone from the front, like the reference walks it.
+def test_two_ended_extraction_needs_mirror_image_strands(b200, monkeypatch):
+    # An index flagged bidirectional whose odd sequences are NOT the reverse strands of the even ones. Sequences are only
+    # walked from both ends when the signatures of both strands (taken by earlier whole walks) say that they are mirror
+    # images; everything else is walked from the front, like the reference walks it. Three kinds of pairs:
+    # unrelated strands, strands of equal length that agree around the middle (where the halves would meet) but differ
+    # in ONE node elsewhere, and true mirror images.
     rng = random.Random(6)
-    paths = [[2 * rng.randint(1, 40) + rng.randint(0, 1) for _ in range(rng.choice([150, 200, 333]))] for _ in range(8)]
-    for i, p in enumerate(paths):  # the check is one node: make sure no pair agrees there by chance
-        other, at = paths[i ^ 1], len(p) - 1 - len(p) // 2
-        assert at >= len(other) or other[at] ^ 1 != p[len(p) // 2]
-    b = gb.build_bwt(paths)
-    img = image_of(b, bidirectional=True)
-    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+
+    def mirror(p):
+        return [x ^ 1 for x in reversed(p)]
+
+    paths = []
+    for kind in ("unrelated", "one node", "one node", "mirror", "one node near an end", "mirror"):
+        p = [2 * rng.randint(1, 40) + rng.randint(0, 1) for _ in range(rng.choice([150, 200, 333]))]
+        q = mirror(p)
+        if kind == "unrelated":
+            q = [2 * rng.randint(1, 40) + rng.randint(0, 1) for _ in range(len(p))]
+        elif kind == "one node":
+            at = len(q) // 5
+            q[at] = q[at] ^ 2 if (q[at] ^ 2) >= 2 else q[at] + 2
+        elif kind == "one node near an end":
+            q[-2] = q[-2] + 2
+        paths += [p, q]
+    for i in range(2, 10, 2):   # the one-node pairs agree where the halves would meet
+        p, q = paths[i], paths[i + 1]
+        if i != 6:
+            assert q[len(p) - 1 - len(p) // 2] ^ 1 == p[len(p) // 2] and q != mirror(p)
+    img = image_of(gb.build_bwt(paths), bidirectional=True)
+    g = orc.GBWT.load(img)
     ids = np.arange(len(paths), dtype=np.uint64)
-    for _ in range(2):
-        offsets, nodes, lengths = e.extract(ids)
-        for i, p in enumerate(paths):
-            assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == p == [int(x) for x in g.sequence(i)]
+    for checkpoints in (False, True):
+        if checkpoints:
+            monkeypatch.setenv("GBWT_B200_EXTRACT_CHECKPOINTS", "0")   # built (signatures of every sequence), but walk the chains
+        e = b200.GBWT.from_bytes(img, checkpoints=checkpoints)
+        for _ in range(3):          # lengths + signatures, then (where allowed) two-ended, and again
+            offsets, nodes, lengths = e.extract(ids)
+            for i, p in enumerate(paths):
+                assert [int(x) for x in nodes[int(offsets[i]):int(offsets[i + 1])]] == p == [int(x) for x in g.sequence(i)]
 
 
 def test_lean_find_kernel_edge_cases(b200, monkeypatch):
