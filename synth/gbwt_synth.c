@@ -15,6 +15,11 @@
  * A_S = 3S+1. Haplotype h visits A_0, x_0, A_1, ..., x_{S-1}, A_S with x_s = C_s if allele(h, s)
  * else B_s; allele(h, s) = mix64(seed + h*S + s) >> 63. GBWT node = 2*id + orientation; sequence 2h is
  * the forward path, 2h+1 its reverse (support.rs:155, 310-314). offset = 1, alphabet_size = 2(3S+2).
+ *
+ * Variant model (the *_v entry points, alt_ppm > 0): nodes A_s = 4s+1, B_s, C_s, D_s = 4s+2..4, final anchor 4S+1;
+ * allele 1 (C_s) with probability alt_ppm / 10^6, and at every site with mix64(31 seed + 0x5BD1E995 + s) % tri_mod == 0
+ * a third allele (D_s) with the same probability: low-frequency variants give the anchor records long runs, the
+ * tri-allelic sites give them outdegree 3 (run-length bodies on the device). D_s has an empty record elsewhere.
  */
 #include <math.h>
 #include <stdint.h>
@@ -34,11 +39,40 @@ static inline uint64_t mix64(uint64_t x) {
 
 uint64_t synth_mix64(uint64_t x) { return mix64(x); }
 
-static inline unsigned allele(uint64_t seed, uint64_t S, uint64_t h, uint64_t s) {
-    return (unsigned)(mix64(seed + h * S + s) >> 63);
+/* The allele model. Legacy (thr == 0): two equally likely alleles per site, three node ids per site. Variant model
+ * (thr > 0): the alternative allele has probability thr / 2^32; every tri_mod-th site (chosen by a hash of the site) has a
+ * second alternative allele of the same probability; four node ids per site (the fourth has an empty record at a
+ * bi-allelic site). */
+typedef struct { uint64_t seed, S; uint32_t thr, tri_mod, stride; } model_t;
+
+static inline model_t make_model(uint64_t seed, uint64_t S, uint64_t alt_ppm, uint64_t tri_mod) {
+    model_t m;
+    m.seed = seed; m.S = S;
+    m.thr = alt_ppm == 0 ? 0 : (uint32_t)((alt_ppm * 4294967296.0) / 1e6);
+    if (alt_ppm != 0 && m.thr == 0) m.thr = 1;
+    m.tri_mod = alt_ppm == 0 ? 0 : (uint32_t)tri_mod;
+    m.stride = alt_ppm == 0 ? 3 : 4;
+    return m;
 }
 
-unsigned synth_allele(uint64_t seed, uint64_t S, uint64_t h, uint64_t s) { return allele(seed, S, h, s); }
+static inline int site_is_tri(const model_t* m, uint64_t s) {
+    return m->tri_mod != 0 && mix64(m->seed * 31 + 0x5BD1E995ULL + s) % m->tri_mod == 0;
+}
+
+static inline unsigned allele(const model_t* m, uint64_t h, uint64_t s) {
+    uint64_t r = mix64(m->seed + h * m->S + s);
+    if (m->thr == 0) return (unsigned)(r >> 63);
+    uint64_t u = r >> 32;
+    if (u < m->thr) return 1;
+    if (u < 2 * (uint64_t)m->thr && site_is_tri(m, s)) return 2;
+    return 0;
+}
+
+unsigned synth_allele(uint64_t seed, uint64_t S, uint64_t h, uint64_t s) { model_t m = make_model(seed, S, 0, 0); return allele(&m, h, s); }
+unsigned synth_allele_v(uint64_t seed, uint64_t S, uint64_t alt_ppm, uint64_t tri_mod, uint64_t h, uint64_t s) {
+    model_t m = make_model(seed, S, alt_ppm, tri_mod);
+    return allele(&m, h, s);
+}
 
 static inline size_t put_varint(uint8_t* p, uint64_t v) {
     size_t n = 0;
@@ -259,9 +293,11 @@ void synth_free(void* p) { free(p); }
 /* Order of the haplotypes when they arrive at the anchor of site `s` on one strand: sorted by the
  * alleles of the previously visited sites (most recent first), ties by haplotype id. Computed exactly
  * by replaying the stable partitions of the last K sites and extending K while ties remain. */
-static void order_at(uint64_t seed, uint64_t S, uint64_t H, int reverse, uint64_t s, uint32_t* order, uint32_t* tmp, uint64_t* key) {
+static void order_at(const model_t* m, uint64_t H, int reverse, uint64_t s, uint32_t* order, uint32_t* tmp, uint64_t* key) {
+    uint64_t S = m->S;
     uint64_t avail = reverse ? (S - 1 - s) : s; /* number of sites already visited */
-    uint64_t K = 64;
+    uint64_t K = m->thr == 0 ? 64 : 32;
+    const unsigned classes = m->thr == 0 ? 2 : 3, key_bits = m->thr == 0 ? 1 : 2;
     for (;;) {
         if (K > avail) K = avail;
         for (uint64_t i = 0; i < H; i++) order[i] = (uint32_t)i;
@@ -269,17 +305,17 @@ static void order_at(uint64_t seed, uint64_t S, uint64_t H, int reverse, uint64_
         for (uint64_t j = K; j >= 1; j--) {
             uint64_t site = reverse ? (s + j) : (s - j);
             uint64_t nb = 0;
-            for (uint64_t i = 0; i < H; i++) if (!allele(seed, S, order[i], site)) tmp[nb++] = order[i];
-            for (uint64_t i = 0; i < H; i++) if (allele(seed, S, order[i], site)) tmp[nb++] = order[i];
+            for (unsigned c = 0; c < classes; c++)
+                for (uint64_t i = 0; i < H; i++) if (allele(m, order[i], site) == c) tmp[nb++] = order[i];
             memcpy(order, tmp, H * sizeof(uint32_t));
         }
         if (K == avail) return;
         /* exact iff no two neighbours share all K window alleles */
         int tie = 0;
-        if (K <= 64) {
+        if (K * key_bits <= 64) {
             for (uint64_t i = 0; i < H; i++) {
                 uint64_t k = 0;
-                for (uint64_t j = 1; j <= K; j++) k = (k << 1) | allele(seed, S, order[i], reverse ? (s + j) : (s - j));
+                for (uint64_t j = 1; j <= K; j++) k = (k << key_bits) | allele(m, order[i], reverse ? (s + j) : (s - j));
                 key[i] = k;
             }
             for (uint64_t i = 1; i < H && !tie; i++) tie = (key[i] == key[i - 1]);
@@ -288,7 +324,7 @@ static void order_at(uint64_t seed, uint64_t S, uint64_t H, int reverse, uint64_
                 int same = 1;
                 for (uint64_t j = 1; j <= K && same; j++) {
                     uint64_t site = reverse ? (s + j) : (s - j);
-                    same = allele(seed, S, order[i], site) == allele(seed, S, order[i - 1], site);
+                    same = allele(m, order[i], site) == allele(m, order[i - 1], site);
                 }
                 tie = same;
             }
@@ -312,64 +348,59 @@ static inline uint8_t* cb_reserve(chunk_buf* c, size_t extra) {
     return c->buf + c->len;
 }
 
-/* Emits the three records of one site on one strand and advances the order.
- * b_node / c_node / next_anchor are GBWT node ids. */
-static void emit_site(chunk_buf* cb, uint64_t seed, uint64_t S, uint64_t H, uint64_t site,
-                      uint64_t b_node, uint64_t c_node, uint64_t next_anchor,
-                      uint32_t* order, uint32_t* tmp, uint8_t* bits, uint32_t* rec_len /* [3]: anchor, B, C */) {
-    uint64_t nb = 0, nc = 0;
+/* Emits the records of one site on one strand (anchor, then one per allele node) and advances the order.
+ * alt_nodes[] / next_anchor are GBWT node ids; rec_len[0] = anchor, rec_len[1 + a] = node of allele a. */
+static void emit_site(chunk_buf* cb, const model_t* m, uint64_t H, uint64_t site, const uint64_t* alt_nodes, uint64_t next_anchor,
+                      uint32_t* order, uint32_t* tmp, uint8_t* bits, uint32_t* rec_len) {
+    const unsigned alleles = m->stride - 1;
+    uint64_t cnt[3] = {0, 0, 0};
+    unsigned rank_of[3] = {0, 0, 0};
     for (uint64_t i = 0; i < H; i++) {
-        unsigned a = allele(seed, S, order[i], site);
+        unsigned a = allele(m, order[i], site);
         bits[i] = (uint8_t)a;
-        nc += a;
+        cnt[a]++;
     }
-    nb = H - nc;
     /* anchor record */
     uint8_t* p = cb_reserve(cb, 64 + 3 * H);
     size_t n = 0;
-    uint64_t sigma = (nb > 0) + (nc > 0);
+    uint64_t sigma = 0;
+    for (unsigned a = 0; a < alleles; a++) { rank_of[a] = (unsigned)sigma; sigma += cnt[a] > 0; }
     n += put_varint(p + n, sigma);
     uint64_t prev = 0;
-    if (nb > 0) { n += put_varint(p + n, b_node - prev); n += put_varint(p + n, 0); prev = b_node; }
-    if (nc > 0) { n += put_varint(p + n, c_node - prev); n += put_varint(p + n, 0); prev = c_node; }
+    for (unsigned a = 0; a < alleles; a++)
+        if (cnt[a] > 0) { n += put_varint(p + n, alt_nodes[a] - prev); n += put_varint(p + n, 0); prev = alt_nodes[a]; }
     uint64_t i = 0;
     while (i < H) {
         uint64_t j = i + 1;
         while (j < H && bits[j] == bits[i]) j++;
-        uint64_t value = (sigma == 2) ? bits[i] : 0;
-        n += put_run(p + n, sigma, value, j - i);
+        n += put_run(p + n, sigma, rank_of[bits[i]], j - i);
         i = j;
     }
     cb->len += n; rec_len[0] = (uint32_t)n;
-    /* B record: all B-takers continue to the next anchor at offsets 0.. */
-    p = cb_reserve(cb, 64);
-    n = 0;
-    if (nb > 0) {
-        n += put_varint(p + n, 1); n += put_varint(p + n, next_anchor); n += put_varint(p + n, 0);
-        n += put_run(p + n, 1, 0, nb);
-    } else {
-        p[n++] = 0;
+    /* allele records: the takers of allele a continue to the next anchor, after the takers of the smaller alleles */
+    uint64_t before = 0;
+    for (unsigned a = 0; a < alleles; a++) {
+        p = cb_reserve(cb, 64);
+        n = 0;
+        if (cnt[a] > 0) {
+            n += put_varint(p + n, 1); n += put_varint(p + n, next_anchor); n += put_varint(p + n, before);
+            n += put_run(p + n, 1, 0, cnt[a]);
+        } else {
+            p[n++] = 0;
+        }
+        cb->len += n; rec_len[1 + a] = (uint32_t)n;
+        before += cnt[a];
     }
-    cb->len += n; rec_len[1] = (uint32_t)n;
-    /* C record: C-takers follow the B-takers in the next anchor */
-    p = cb_reserve(cb, 64);
-    n = 0;
-    if (nc > 0) {
-        n += put_varint(p + n, 1); n += put_varint(p + n, next_anchor); n += put_varint(p + n, nb);
-        n += put_run(p + n, 1, 0, nc);
-    } else {
-        p[n++] = 0;
-    }
-    cb->len += n; rec_len[2] = (uint32_t)n;
     /* stable partition */
     uint64_t k = 0;
-    for (uint64_t q = 0; q < H; q++) if (!bits[q]) tmp[k++] = order[q];
-    for (uint64_t q = 0; q < H; q++) if (bits[q]) tmp[k++] = order[q];
+    for (unsigned a = 0; a < alleles; a++)
+        for (uint64_t q = 0; q < H; q++) if (bits[q] == a) tmp[k++] = order[q];
     memcpy(order, tmp, H * sizeof(uint32_t));
 }
 
 /* Returns a malloc'd Simple-SDS GBWT image (free with synth_free). */
-uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int threads, uint64_t* out_len) {
+static uint8_t* bubble_chain_image(const model_t* m, uint64_t H, int threads, uint64_t* out_len) {
+    const uint64_t S = m->S, T = m->stride;
     if (S == 0 || H == 0 || H > 0xFFFFFFFFULL) return NULL;
 #ifdef _OPENMP
     /* all processors unless told otherwise: launchers such as torchrun export OMP_NUM_THREADS=1 */
@@ -379,13 +410,13 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
 #endif
     const uint64_t CH = 2048; /* sites per chunk */
     uint64_t n_chunks = (S + CH - 1) / CH;
-    uint64_t n_ids = 3 * S + 1; /* original node ids 1..3S+1 */
+    uint64_t n_ids = T * S + 1; /* original node ids 1..T*S+1 */
     chunk_buf* fwd = (chunk_buf*)calloc(n_chunks, sizeof(chunk_buf));
     chunk_buf* rev = (chunk_buf*)calloc(n_chunks, sizeof(chunk_buf));
     /* per-record lengths, indexed by original node id (1-based) */
     uint32_t* len_f = (uint32_t*)calloc(n_ids + 2, sizeof(uint32_t));
     uint32_t* len_r = (uint32_t*)calloc(n_ids + 2, sizeof(uint32_t));
-    uint64_t NEXT_LAST_F = 2 * (3 * S + 1); /* A_S forward */
+    uint64_t NEXT_LAST_F = 2 * (T * S + 1); /* A_S forward */
 
 #pragma omp parallel num_threads(threads)
     {
@@ -398,23 +429,26 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
             uint64_t c = (uint64_t)job / 2;
             int reverse = (int)(job & 1);
             uint64_t s0 = c * CH, s1 = s0 + CH < S ? s0 + CH : S;
-            uint32_t rl[3];
+            uint32_t rl[4];
+            uint64_t alts[3];
             if (!reverse) {
-                order_at(seed, S, H, 0, s0, order, tmp, key);
+                order_at(m, H, 0, s0, order, tmp, key);
                 for (uint64_t s = s0; s < s1; s++) {
-                    uint64_t a = 3 * s + 1;
-                    uint64_t next = (s + 1 == S) ? NEXT_LAST_F : 2 * (3 * (s + 1) + 1);
-                    emit_site(&fwd[c], seed, S, H, s, 2 * (a + 1), 2 * (a + 2), next, order, tmp, bits, rl);
-                    len_f[a] = rl[0]; len_f[a + 1] = rl[1]; len_f[a + 2] = rl[2];
+                    uint64_t a = T * s + 1;
+                    uint64_t next = (s + 1 == S) ? NEXT_LAST_F : 2 * (T * (s + 1) + 1);
+                    for (uint64_t d = 1; d < T; d++) alts[d - 1] = 2 * (a + d);
+                    emit_site(&fwd[c], m, H, s, alts, next, order, tmp, bits, rl);
+                    for (uint64_t d = 0; d < T; d++) len_f[a + d] = rl[d];
                 }
             } else {
-                /* reverse strand visits sites in descending order: anchor A_{s+1} rev -> B_s/C_s rev -> A_s rev */
-                order_at(seed, S, H, 1, s1 - 1, order, tmp, key);
+                /* reverse strand visits sites in descending order: anchor A_{s+1} rev -> allele nodes of s rev -> A_s rev */
+                order_at(m, H, 1, s1 - 1, order, tmp, key);
                 for (uint64_t s = s1; s-- > s0;) {
-                    uint64_t a = 3 * s + 1;
-                    emit_site(&rev[c], seed, S, H, s, 2 * (a + 1) + 1, 2 * (a + 2) + 1, 2 * a + 1,
-                              order, tmp, bits, rl);
-                    len_r[a + 3] = rl[0]; len_r[a + 1] = rl[1]; len_r[a + 2] = rl[2];
+                    uint64_t a = T * s + 1;
+                    for (uint64_t d = 1; d < T; d++) alts[d - 1] = 2 * (a + d) + 1;
+                    emit_site(&rev[c], m, H, s, alts, 2 * a + 1, order, tmp, bits, rl);
+                    len_r[a + T] = rl[0];
+                    for (uint64_t d = 1; d < T; d++) len_r[a + d] = rl[d];
                 }
             }
         }
@@ -426,7 +460,7 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
     size_t term_len = 0;
     term_len += put_varint(term + term_len, 1); term_len += put_varint(term + term_len, 0); term_len += put_varint(term + term_len, 0);
     term_len += put_run(term + term_len, 1, 0, H);
-    len_f[3 * S + 1] = (uint32_t)term_len;
+    len_f[T * S + 1] = (uint32_t)term_len;
     len_r[1] = (uint32_t)term_len;
 
     /* endmarker record: sequences alternate forward (starts at A_0 fwd = 2) and reverse (A_S rev) */
@@ -435,10 +469,10 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
     size_t em_len = 0;
     em_len += put_varint(em + em_len, 2);
     em_len += put_varint(em + em_len, 2); em_len += put_varint(em + em_len, 0);
-    em_len += put_varint(em + em_len, (2 * (3 * S + 1) + 1) - 2); em_len += put_varint(em + em_len, 0);
+    em_len += put_varint(em + em_len, (2 * (T * S + 1) + 1) - 2); em_len += put_varint(em + em_len, 0);
     for (uint64_t h = 0; h < H; h++) { em[em_len++] = 0; em[em_len++] = 1; } /* runs (0,1),(1,1) with sigma 2 */
 
-    /* record starts: record 0 = endmarker, then for id = 1..3S+1: forward, reverse */
+    /* record starts: record 0 = endmarker, then for id = 1..T*S+1: forward, reverse */
     uint64_t records = 2 * n_ids + 1;
     uint64_t* starts = (uint64_t*)malloc(records * sizeof(uint64_t));
     uint64_t pos = 0;
@@ -451,10 +485,10 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
     uint64_t sequences = 2 * H;
     uint64_t size = sequences * (2 * S + 2);
     uint64_t data_at = 0;
-    uint8_t* image = assemble_image(sequences, size, 1, 2 * (3 * S + 2), 1 | 4, starts, records, NULL, data_len, out_len, &data_at);
+    uint8_t* image = assemble_image(sequences, size, 1, 2 * (T * S + 2), 1 | 4, starts, records, NULL, data_len, out_len, &data_at);
     uint8_t* data = image + data_at;
     memcpy(data, em, em_len);
-    memcpy(data + starts[2 * (3 * S + 1) - 1], term, term_len);
+    memcpy(data + starts[2 * (T * S + 1) - 1], term, term_len);
     memcpy(data + starts[2], term, term_len);
 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
@@ -465,8 +499,8 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
         if (!reverse) {
             const uint8_t* src = fwd[c].buf;
             for (uint64_t s = s0; s < s1; s++) {
-                uint64_t a = 3 * s + 1;
-                for (uint64_t d = 0; d < 3; d++) {
+                uint64_t a = T * s + 1;
+                for (uint64_t d = 0; d < T; d++) {
                     memcpy(data + starts[2 * (a + d) - 1], src, len_f[a + d]);
                     src += len_f[a + d];
                 }
@@ -474,11 +508,11 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
         } else {
             const uint8_t* src = rev[c].buf;
             for (uint64_t s = s1; s-- > s0;) {
-                uint64_t a = 3 * s + 1;
-                uint64_t ids[3] = {a + 3, a + 1, a + 2};
-                for (uint64_t d = 0; d < 3; d++) {
-                    memcpy(data + starts[2 * ids[d]], src, len_r[ids[d]]);
-                    src += len_r[ids[d]];
+                uint64_t a = T * s + 1;
+                for (uint64_t d = 0; d < T; d++) {
+                    uint64_t id = d == 0 ? a + T : a + d;
+                    memcpy(data + starts[2 * id], src, len_r[id]);
+                    src += len_r[id];
                 }
             }
         }
@@ -488,37 +522,53 @@ uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int thre
     return image;
 }
 
+uint8_t* synth_bubble_chain_gbwt(uint64_t S, uint64_t H, uint64_t seed, int threads, uint64_t* out_len) {
+    model_t m = make_model(seed, S, 0, 0);
+    return bubble_chain_image(&m, H, threads, out_len);
+}
+
+/* The variant model: alternative alleles with probability alt_ppm / 10^6, every tri_mod-th site tri-allelic (0: none),
+ * N = 4 S + 1 node ids. */
+uint8_t* synth_bubble_chain_gbwt_v(uint64_t S, uint64_t H, uint64_t seed, uint64_t alt_ppm, uint64_t tri_mod, int threads,
+                                   uint64_t* out_len) {
+    model_t m = make_model(seed, S, alt_ppm, tri_mod);
+    return bubble_chain_image(&m, H, threads, out_len);
+}
+
 /* ---- haplotype paths and query patterns ----------------------------------------- */
 
 /* Node at position p (0..2S) of forward sequence 2h. */
-static inline uint64_t fwd_node(uint64_t seed, uint64_t S, uint64_t h, uint64_t p) {
+static inline uint64_t fwd_node(const model_t* m, uint64_t h, uint64_t p) {
     uint64_t s = p >> 1;
-    if ((p & 1) == 0) return 2 * (3 * s + 1);
-    return 2 * (3 * s + 2 + allele(seed, S, h, s));
+    if ((p & 1) == 0) return 2 * (m->stride * s + 1);
+    return 2 * (m->stride * s + 2 + allele(m, h, s));
 }
 
-static inline uint64_t seq_node(uint64_t seed, uint64_t S, uint64_t seq, uint64_t p) {
+static inline uint64_t seq_node(const model_t* m, uint64_t seq, uint64_t p) {
     uint64_t h = seq >> 1;
-    if ((seq & 1) == 0) return fwd_node(seed, S, h, p);
-    return fwd_node(seed, S, h, 2 * S - p) ^ 1;
+    if ((seq & 1) == 0) return fwd_node(m, h, p);
+    return fwd_node(m, h, 2 * m->S - p) ^ 1;
 }
 
 /* Full sequence `seq` (2S+1 nodes). */
-void synth_sequence(uint64_t S, uint64_t H, uint64_t seed, uint64_t seq, uint64_t* out) {
+void synth_sequence_v(uint64_t S, uint64_t H, uint64_t seed, uint64_t alt_ppm, uint64_t tri_mod, uint64_t seq, uint64_t* out) {
     (void)H;
-    for (uint64_t p = 0; p <= 2 * S; p++) out[p] = seq_node(seed, S, seq, p);
+    model_t m = make_model(seed, S, alt_ppm, tri_mod);
+    for (uint64_t p = 0; p <= 2 * S; p++) out[p] = seq_node(&m, seq, p);
 }
+void synth_sequence(uint64_t S, uint64_t H, uint64_t seed, uint64_t seq, uint64_t* out) { synth_sequence_v(S, H, seed, 0, 0, seq, out); }
 
 /* Queries q0 .. q0+n: h = mix64(seed_q + 3q) % H, o = mix64(seed_q + 3q + 1) & 1,
  * t = mix64(seed_q + 3q + 2) % (2S + 1 - (k - 1)); pattern = sequence 2h+o positions [t, t+k). */
-void synth_patterns(uint64_t S, uint64_t H, uint64_t seed, uint64_t seed_q, uint64_t q0, uint64_t n, uint64_t k,
-                    uint64_t* out, int threads) {
+void synth_patterns_v(uint64_t S, uint64_t H, uint64_t seed, uint64_t alt_ppm, uint64_t tri_mod, uint64_t seed_q, uint64_t q0,
+                      uint64_t n, uint64_t k, uint64_t* out, int threads) {
 #ifdef _OPENMP
     /* all processors unless told otherwise: launchers such as torchrun export OMP_NUM_THREADS=1 */
     if (threads <= 0) threads = omp_get_num_procs();
 #else
     threads = 1;
 #endif
+    const model_t m = make_model(seed, S, alt_ppm, tri_mod);
     uint64_t span = 2 * S + 1 - (k - 1);
 #pragma omp parallel for schedule(static) num_threads(threads)
     for (int64_t i = 0; i < (int64_t)n; i++) {
@@ -527,6 +577,10 @@ void synth_patterns(uint64_t S, uint64_t H, uint64_t seed, uint64_t seed_q, uint
         uint64_t o = mix64(seed_q + 3 * q + 1) & 1;
         uint64_t t = mix64(seed_q + 3 * q + 2) % span;
         uint64_t* dst = out + (uint64_t)i * k;
-        for (uint64_t j = 0; j < k; j++) dst[j] = seq_node(seed, S, 2 * h + o, t + j);
+        for (uint64_t j = 0; j < k; j++) dst[j] = seq_node(&m, 2 * h + o, t + j);
     }
+}
+void synth_patterns(uint64_t S, uint64_t H, uint64_t seed, uint64_t seed_q, uint64_t q0, uint64_t n, uint64_t k,
+                    uint64_t* out, int threads) {
+    synth_patterns_v(S, H, seed, 0, 0, seed_q, q0, n, k, out, threads);
 }

@@ -35,6 +35,12 @@ def lib() -> C.CDLL:
         L.synth_allele.argtypes = [u64, u64, u64, u64]
         L.synth_bubble_chain_gbwt.restype = p
         L.synth_bubble_chain_gbwt.argtypes = [u64, u64, u64, C.c_int, C.POINTER(u64)]
+        L.synth_bubble_chain_gbwt_v.restype = p
+        L.synth_bubble_chain_gbwt_v.argtypes = [u64, u64, u64, u64, u64, C.c_int, C.POINTER(u64)]
+        L.synth_allele_v.restype = C.c_uint
+        L.synth_allele_v.argtypes = [u64, u64, u64, u64, u64, u64]
+        L.synth_sequence_v.argtypes = [u64, u64, u64, u64, u64, u64, p]
+        L.synth_patterns_v.argtypes = [u64, u64, u64, u64, u64, u64, u64, u64, u64, p, C.c_int]
         L.synth_gbwt_image.restype = p
         L.synth_gbwt_image.argtypes = [u64, u64, u64, u64, u64, p, u64, p, u64, C.POINTER(u64)]
         L.synth_bwt_section.restype = p
@@ -71,10 +77,15 @@ class Image:
             pass
 
 
-def bubble_chain(sites: int, haplotypes: int, seed: int = 42, threads: int = 0) -> Image:
-    """Bubble chain with `sites` sites (N = 3*sites + 1 nodes) and `haplotypes` haplotypes."""
+def bubble_chain(sites: int, haplotypes: int, seed: int = 42, threads: int = 0, alt_ppm: int = 0, tri_mod: int = 0) -> Image:
+    """Bubble chain with `sites` sites and `haplotypes` haplotypes. Default model: N = 3*sites + 1 nodes, two equally
+    likely alleles. alt_ppm > 0 selects the variant model: N = 4*sites + 1 node ids, alternative alleles with
+    probability alt_ppm / 10^6, every tri_mod-th site (by hash) tri-allelic."""
     n = C.c_uint64(0)
-    ptr = lib().synth_bubble_chain_gbwt(sites, haplotypes, seed, threads, C.byref(n))
+    if alt_ppm:
+        ptr = lib().synth_bubble_chain_gbwt_v(sites, haplotypes, seed, alt_ppm, tri_mod, threads, C.byref(n))
+    else:
+        ptr = lib().synth_bubble_chain_gbwt(sites, haplotypes, seed, threads, C.byref(n))
     if not ptr:
         raise ValueError("invalid bubble-chain parameters")
     return Image(ptr, n.value)
@@ -144,18 +155,19 @@ def bwt_section(rec_starts, data: bytes) -> bytes:
     return out
 
 
-def sequence(sites: int, haplotypes: int, seed: int, seq_id: int) -> np.ndarray:
+def sequence(sites: int, haplotypes: int, seed: int, seq_id: int, alt_ppm: int = 0, tri_mod: int = 0) -> np.ndarray:
     out = np.zeros(2 * sites + 1, dtype=np.uint64)
-    lib().synth_sequence(sites, haplotypes, seed, seq_id, out.ctypes.data_as(C.c_void_p))
+    lib().synth_sequence_v(sites, haplotypes, seed, alt_ppm, tri_mod if alt_ppm else 0, seq_id, out.ctypes.data_as(C.c_void_p))
     return out
 
 
 def patterns(sites: int, haplotypes: int, seed: int, n: int, k: int = 32, seed_q: int = 7, q0: int = 0,
-             threads: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+             threads: int = 0, out: np.ndarray | None = None, alt_ppm: int = 0, tri_mod: int = 0) -> np.ndarray:
     if out is None:
         out = np.empty((n, k), dtype=np.uint64)
     assert out.dtype == np.uint64 and out.flags.c_contiguous and out.size == n * k
-    lib().synth_patterns(sites, haplotypes, seed, seed_q, q0, n, k, out.ctypes.data_as(C.c_void_p), threads)
+    lib().synth_patterns_v(sites, haplotypes, seed, alt_ppm, tri_mod if alt_ppm else 0, seed_q, q0, n, k,
+                           out.ctypes.data_as(C.c_void_p), threads)
     return out
 
 
@@ -173,14 +185,15 @@ def build_cuda(force: bool = False) -> str:
 
 
 def patterns_device(sites: int, haplotypes: int, seed: int, n: int, d_out: int, k: int = 32, seed_q: int = 7,
-                    q0: int = 0, stream: int = 0) -> None:
+                    q0: int = 0, stream: int = 0, alt_ppm: int = 0, tri_mod: int = 0) -> None:
     """Writes patterns q0 .. q0+n (row-major, k u64 each) to the device address `d_out`."""
     global _CUDA_LIB
     if _CUDA_LIB is None:
         L = C.CDLL(build_cuda())
         u64 = C.c_uint64
         L.synth_patterns_device.argtypes = [u64, u64, u64, u64, u64, u64, u64, C.c_void_p, C.c_void_p]
+        L.synth_patterns_device_v.argtypes = [u64, u64, u64, u64, u64, u64, u64, u64, u64, C.c_void_p, C.c_void_p]
         _CUDA_LIB = L
-    rc = _CUDA_LIB.synth_patterns_device(sites, haplotypes, seed, seed_q, q0, n, k, d_out, stream)
+    rc = _CUDA_LIB.synth_patterns_device_v(sites, haplotypes, seed, alt_ppm, tri_mod if alt_ppm else 0, seed_q, q0, n, k, d_out, stream)
     if rc != 0:
         raise RuntimeError(f"synth_patterns_device failed with CUDA error {rc}")
