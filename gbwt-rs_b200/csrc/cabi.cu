@@ -255,7 +255,7 @@ int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, s
             uint32_t *perm = nullptr, *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
             int rc = build_locality_perm(ix, count, s, [&](uint32_t, uint32_t* keys, uint32_t* counts) {
                 launch_window_keys<T>(ix->view, ix->window, part, count, k, keys, counts, grid_for(ix, count), s);
-            }, &perm, static_cast<int>(ix->window.wshift), &bucket_end, &scratch);
+            }, &perm, static_cast<int>(ix->window.wshift - ix->window.fine), &bucket_end, &scratch);
             if (rc != GBWT_B200_OK) return rc;
             CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
             CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));

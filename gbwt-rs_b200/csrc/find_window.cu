@@ -31,11 +31,6 @@ namespace {
 // ---- shared-memory accessors (32-bit shared-space addresses: no generic-pointer arithmetic in the loop) --------------
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -55,113 +50,84 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 
 // ---- pattern rows -----------------------------------------------------------------------------------------------------
-// A thread reads its own pattern row one 32-byte sector at a time and always has the next sector in flight (the rows
-// of a sorted batch are scattered over HBM: this is the one load of the loop that pays DRAM latency, and nothing
-// depends on it for a whole chunk). The loads bypass L1 (every byte is used once) and ask L2 for the whole row on
-// first touch. The nodes of the current chunk live in the thread's own column of a small shared array (word j of
-// thread t at [j][t]: every lane always hits its own bank), so that node(i) is one conflict-free shared load however
-// i moves -- with the chunk in registers the select by i & 3 compiled to branches that split the warp.
+// A warp takes 32 queries at a time and reads their pattern rows TOGETHER, one segment of 16 nodes per round: the lanes
+// that share a row read consecutive 32-byte sectors of it, so a load instruction moves whole 128-byte lines (64-bit
+// nodes: 4 lanes per row, 8 rows per instruction, 4 instructions per segment) instead of 32 isolated sectors. (The
+// first versions had every thread read its own row sector by sector: one L1 wavefront per 32 bytes, 3.9 M of the
+// 12.2 M data-stage wavefronts per SM, and the consumer waited for DRAM eight times per query -- 21 % of the stall
+// samples in profiles/r2_find_window_v2_ncu.txt.) Each node is narrowed on the spot to a 16-bit index into the staged
+// window (NODE_OUTSIDE if it is not in there) and stored in the warp's tile, node-major: tile[t][row], so that in the
+// search loop a lane reads node t of its own row with one conflict-free 16-bit load however t moves.
+constexpr uint32_t SEGMENT = 16;            // pattern nodes per round
+constexpr uint32_t TILE_PITCH = 34;         // 16-bit slots per tile line: 32 rows + 2 (the lanes that share a row store 4 lines apart: 16 distinct banks)
+constexpr uint32_t TILE_BYTES = SEGMENT * TILE_PITCH * 2u;
+constexpr uint32_t NODE_OUTSIDE = 0xFFFFu;  // not a record of the staged window (or node 0, the endmarker)
 
+__device__ __forceinline__ uint32_t window_index(uint64_t node, uint32_t origin, uint32_t count) {
+    const uint64_t rel = node - origin;
+    return node != 0 && rel < count ? static_cast<uint32_t>(rel) : NODE_OUTSIDE;
+}
+__device__ __forceinline__ uint32_t window_index(uint32_t node, uint32_t origin, uint32_t count) {
+    const uint32_t rel = node - origin;
+    return node != 0 && rel < count ? rel : NODE_OUTSIDE;
+}
+
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t x) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(x)) : "memory"); }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+
+// One 32-byte sector of pattern nodes, bypassing L1 (every byte is used once).
+__device__ __forceinline__ void load_nodes(const uint64_t* p, uint64_t (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void load_nodes(const uint32_t* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
+// Fills the warp's tile with nodes [seg, seg + n_seg) of its 32 rows. `row` is this lane's own row (nullptr: no query).
+// Sector loads when every row segment starts on a 32-byte boundary and n_seg is a whole number of sectors, else node
+// by node.
 template <class T>
-struct RowReader;
-
-// 64-bit nodes: chunks of 4. A chunk with a node that does not fit 32 bits fails as a whole (the caller defers the query
-// to the general kernel, which looks at the nodes one by one).
-template <>
-struct RowReader<uint64_t> {
-    const uint64_t* p;
-    uint32_t k, base, slot, stride;  // slot: shared address of this thread's column, stride: bytes between its words
-    uint64_t n0, n1, n2, n3;
-    bool bad, vec;
-    __device__ __forceinline__ void fetch(uint32_t b) {
-        n0 = n1 = n2 = n3 = 0;
-        if (b >= k) return;
-        if (vec && k - b >= 4) {
-            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(n0), "=l"(n1), "=l"(n2), "=l"(n3) : "l"(p + b));
-        } else {
-            n0 = __ldg(p + b);
-            if (b + 1 < k) n1 = __ldg(p + b + 1);
-            if (b + 2 < k) n2 = __ldg(p + b + 2);
-            if (b + 3 < k) n3 = __ldg(p + b + 3);
+__device__ __forceinline__ void load_tile(const T* row, uint32_t seg, uint32_t n_seg, bool sectors, uint32_t tile, uint32_t origin,
+                                          uint32_t count, uint32_t lane) {
+    constexpr uint32_t PER_SECTOR = 32u / sizeof(T);          // nodes per 32-byte sector: 4 or 8
+    constexpr uint32_t MAX_LANES_PER_ROW = SEGMENT / PER_SECTOR;  // 4 or 2
+    const unsigned long long mine = reinterpret_cast<unsigned long long>(row);
+    if (sectors) {
+        const uint32_t per_row = n_seg / PER_SECTOR;  // sectors per row segment: 1 .. MAX_LANES_PER_ROW (whole lanes only when a power of two)
+        // lanes_per_row = MAX_LANES_PER_ROW always (a shorter segment leaves the extra lanes idle: only the last round of a pattern)
+        const uint32_t sub = lane % MAX_LANES_PER_ROW, first = lane / MAX_LANES_PER_ROW;
+        constexpr uint32_t ROWS_PER_LOAD = 32u / MAX_LANES_PER_ROW;  // 8 or 16
+        T v[32u / ROWS_PER_LOAD][PER_SECTOR];
+        bool have[32u / ROWS_PER_LOAD];
+#pragma unroll
+        for (uint32_t j = 0; j < 32u / ROWS_PER_LOAD; j++) {
+            const uint32_t r = j * ROWS_PER_LOAD + first;
+            const T* p = reinterpret_cast<const T*>(__shfl_sync(0xFFFFFFFFu, mine, r));
+            have[j] = p != nullptr && sub < per_row;
+            if (have[j]) load_nodes(p + seg + sub * PER_SECTOR, v[j]);
         }
-    }
-    __device__ __forceinline__ RowReader(const uint64_t* row, uint32_t len, uint32_t slot_addr, uint32_t stride_bytes)
-        : p(row), k(len), base(0xFFFFFFFFu), slot(slot_addr), stride(stride_bytes), bad(false), vec((reinterpret_cast<uintptr_t>(row) & 31) == 0) {
-        fetch(0);
-    }
-    // nodes are asked for in non-decreasing chunk order; false = some node of the chunk does not fit 32 bits
-    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
-        const uint32_t b = i & ~3u;
-        if (b != base) {
-            base = b;
-            sts32(slot, static_cast<uint32_t>(n0)); sts32(slot + stride, static_cast<uint32_t>(n1));
-            sts32(slot + 2 * stride, static_cast<uint32_t>(n2)); sts32(slot + 3 * stride, static_cast<uint32_t>(n3));
-            bad = ((n0 | n1 | n2 | n3) >> 32) != 0;
-            fetch(b + 4);
-        }
-        out = lds32(slot + (i & 3u) * stride);
-        return !bad;
-    }
-};
-
-// 32-bit nodes: one 32-byte sector (8 nodes) per load, handed to the shared column four at a time like the 64-bit
-// reader (a first version with 16-byte loads made L2 fetch every row several times: 27.6 GB of DRAM reads per 2^25
-// queries instead of 7.7).
-template <>
-struct RowReader<uint32_t> {
-    const uint32_t* p;
-    uint32_t k, base, slot, stride;
-    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;  // the sector that holds chunk `base` (or, before the first call, node 0)
-    bool vec;
-    __device__ __forceinline__ void fetch(uint32_t b) {
-        n0 = n1 = n2 = n3 = n4 = n5 = n6 = n7 = 0;
-        if (b >= k) return;
-        if (vec && k - b >= 8) {
-            asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3), "=r"(n4), "=r"(n5), "=r"(n6), "=r"(n7) : "l"(p + b));
-        } else {
-            n0 = __ldg(p + b);
-            if (b + 1 < k) n1 = __ldg(p + b + 1);
-            if (b + 2 < k) n2 = __ldg(p + b + 2);
-            if (b + 3 < k) n3 = __ldg(p + b + 3);
-            if (b + 4 < k) n4 = __ldg(p + b + 4);
-            if (b + 5 < k) n5 = __ldg(p + b + 5);
-            if (b + 6 < k) n6 = __ldg(p + b + 6);
-            if (b + 7 < k) n7 = __ldg(p + b + 7);
-        }
-    }
-    __device__ __forceinline__ RowReader(const uint32_t* row, uint32_t len, uint32_t slot_addr, uint32_t stride_bytes)
-        : p(row), k(len), base(0xFFFFFFFFu), slot(slot_addr), stride(stride_bytes), vec((reinterpret_cast<uintptr_t>(row) & 31) == 0) {
-        fetch(0);
-    }
-    // chunks are visited in order, none skipped (the search loop advances by at most two nodes)
-    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
-        const uint32_t b = i & ~3u;
-        if (b != base) {
-            base = b;
-            if ((b & 4u) == 0) {
-                sts32(slot, n0); sts32(slot + stride, n1); sts32(slot + 2 * stride, n2); sts32(slot + 3 * stride, n3);
-            } else {
-                sts32(slot, n4); sts32(slot + stride, n5); sts32(slot + 2 * stride, n6); sts32(slot + 3 * stride, n7);
-                fetch(b + 4);  // the next sector, four nodes early
+#pragma unroll
+        for (uint32_t j = 0; j < 32u / ROWS_PER_LOAD; j++) {
+            const uint32_t r = j * ROWS_PER_LOAD + first;
+            if (have[j]) {
+#pragma unroll
+                for (uint32_t t = 0; t < PER_SECTOR; t++)
+                    sts16(tile + ((sub * PER_SECTOR + t) * TILE_PITCH + r) * 2u, window_index(v[j][t], origin, count));
             }
         }
-        out = lds32(slot + (i & 3u) * stride);
-        return true;
+    } else {
+        for (uint32_t e = lane; e < 32u * n_seg; e += 32u) {
+            const uint32_t r = e / n_seg, t = e - r * n_seg;
+            const T* p = reinterpret_cast<const T*>(__shfl_sync(0xFFFFFFFFu, mine, r));
+            if (p != nullptr) sts16(tile + (t * TILE_PITCH + r) * 2u, window_index(__ldg(p + seg + t), origin, count));
+        }
     }
-};
-
-// Pattern reader of the kernels that keep the chunk in registers (the general loop for deferred queries and the plain
-// 32-bit kernels): same interface, no shared memory.
-template <class T>
-struct PlainRowReader {
-    const T* p;
-    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
-        const uint64_t v = __ldg(p + i);
-        out = static_cast<uint32_t>(v);
-        return (v >> 32) == 0;
-    }
-};
+}
 
 // Asks L2 for a pattern row ahead of its use: its first two 128-byte lines (a length-32 pattern is two lines of 64-bit
 // nodes, one of 32-bit nodes).
@@ -177,100 +143,107 @@ __device__ __forceinline__ uint64_t first_node(const uint32_t* patterns, size_t 
 
 // ---- the staged window -----------------------------------------------------------------------------------------------
 // What a CTA decodes into shared memory for the records [lo, lo + count) -- once per window, used by ~3 queries per
-// record times 16 steps. Arranged for the loop, not like the global layout (reading the 32-byte global records in
-// place put every 16-byte access on one of four bank groups: 13 wavefronts per LDS.128 instead of 4, see
-// profiles/r2_find_window_v1_tma_raw_layout_ncu.txt):
-//   hot[r]   16 B  {node0, node1, total_len, kind}: kind = word index of the record's bitvector in `words` for a dense
-//                  record, or KIND_SINGLE / KIND_EMPTY / KIND_DEFER (run-length body, outdegree > 2, body not staged)
-//   pair[r]  16 B  the two-hop shortcut {landing node, offset} per edge (layout.h, IndexView::skips), as in HBM
-//   offs[r]   8 B  {offset0, offset1}: only read when a step cannot take the shortcut
-//   words[]   8 B  {ones before this word, 32 bits}: rank at position p of a record is ONE 8-byte load at kind + p / 32
-//                  (the 192-bit blocks of the global layout hold 6 such words each, so p / 32 needs no block arithmetic)
-constexpr uint32_t KIND_SINGLE = 0xFFFFFFFFu, KIND_EMPTY = 0xFFFFFFFEu, KIND_DEFER = 0xFFFFFFFDu;  // anything below: dense
+// record times 16 steps. Arranged for the loop, not like the global layout, and in 16-bit fields: the data stage of
+// L1 was the busiest unit of the first versions (78 % with 32-bit patterns), half of its shared-memory wavefronts
+// being bank conflicts of 8- and 16-byte loads at random records, so every table entry is as narrow as it can be.
+// Nodes are indexes into the window (NODE_OUTSIDE when the node is not staged); a record with a field that does not
+// fit 16 bits is marked KIND_DEFER.
+//   hot[r]    8 B  {target0 | target1 << 16, total_len | kind << 16}: kind = index of the record's first rank entry for a
+//                  dense record, or KIND_SINGLE / KIND_EMPTY / KIND_DEFER (run-length body, outdegree > 2, body not staged)
+//   pair[r]   8 B  per edge the two-hop shortcut {landing node | offset << 16} (layout.h, IndexView::skips)
+//   offs[r]   4 B  {offset0 | offset1 << 16}: only read when a step cannot take the shortcut
+//   ranks[]   4 B  {ones before | 16 bits << 16}: rank at position p of a record is ONE 4-byte load at kind + p / 16
+constexpr uint32_t KIND_SINGLE = 0xFFFFu, KIND_EMPTY = 0xFFFEu, KIND_DEFER = 0xFFFDu;  // anything below: dense
+constexpr uint32_t RECORD_BYTES = 20;  // hot + pair + offs
 
 struct Staged {
-    uint32_t hot, pair, offs, words;  // shared-space addresses
+    uint32_t hot, pair, offs, ranks;  // shared-space addresses
     uint32_t lo, count;               // staged records [lo, lo + count)
 };
 
-enum : uint32_t { QUERY_FOUND = 0, QUERY_NONE = 1, QUERY_DEFER = 2 };
+enum : uint32_t { QUERY_ACTIVE = 0, QUERY_FOUND = 1, QUERY_NONE = 2, QUERY_DEFER = 3 };
 
-// rank1(p) and the bit at p of the dense record whose first word is `kind`
-__device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind, uint32_t p, uint32_t& bit) {
-    const uint2 w = lds64(st.words + 8u * (kind + (p >> 5)));
-    const uint32_t sh = p & 31u;
-    bit = (w.y >> sh) & 1u;
-    return w.x + static_cast<uint32_t>(__popc(w.y & ((1u << sh) - 1u)));
+// ones in [0, p) of the dense record whose first rank entry is `kind`; with INCLUSIVE the bit at p counts too
+template <bool INCLUSIVE>
+__device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind, uint32_t p) {
+    const uint32_t w = lds32(st.ranks + 4u * (kind + (p >> 4)));
+    const uint32_t sh = p & 15u;
+    const uint32_t mask = INCLUSIVE ? ((2u << sh) - 1u) : ((1u << sh) - 1u);
+    return (w & 0xFFFFu) + static_cast<uint32_t>(__popc((w >> 16) & mask));
 }
 
-// One query against the staged window. QUERY_FOUND: (node, start, end) is the reference's SearchState; QUERY_NONE: the
-// reference returns None; QUERY_DEFER: the window could not decide and the general kernel redoes the query from the
-// start. The loop has ONE exit (every failure breaks out with its status), so the lanes of a warp reconverge after
-// every step instead of carrying a stack of divergent returns.
-template <class Reader>
-__device__ __forceinline__ uint32_t window_query(const Staged& st, uint32_t base, Reader& rd, uint32_t k, uint32_t& node, uint32_t& start,
-                                                 uint32_t& end) {
-    if (k == 0) return QUERY_NONE;
-    uint32_t x;
-    if (!rd.node(0, x)) return QUERY_DEFER;
-    uint32_t idx = x - base - st.lo;
-    if (idx >= st.count || idx + st.lo == 0) return QUERY_DEFER;  // (record 0 is the endmarker: find() is None; let the general code say so)
-    uint4 h = lds128(st.hot + 16u * idx);
-    start = 0; end = h.z; node = x;
-    if (h.w == KIND_DEFER) return QUERY_DEFER;
-    if (h.w == KIND_EMPTY || end == 0) return QUERY_NONE;  // GBWT::find: no record
-    uint32_t i = 1, status = QUERY_FOUND;
-    while (i < k) {
-        uint32_t x1;
-        if (!rd.node(i, x1)) { status = QUERY_DEFER; break; }
-        const uint32_t total = h.z, kind = h.w;
+// The state of one query between rounds.
+struct WindowQuery {
+    uint32_t idx;         // window index of the current node
+    uint32_t start, end;  // the range in its record
+    uint32_t i;           // next pattern position
+    uint32_t status;
+};
+
+// GBWT::find on the first pattern node (window index x, NODE_OUTSIDE if it is not staged).
+__device__ __forceinline__ void window_find(const Staged& st, uint32_t x, uint32_t k, WindowQuery& q) {
+    q.idx = x; q.start = 0; q.end = 0; q.i = 1; q.status = QUERY_ACTIVE;
+    if (x == NODE_OUTSIDE || x + st.lo == 0) { q.status = QUERY_DEFER; return; }  // (record 0 is the endmarker: find() is None; let the general code say so)
+    const uint2 h = lds64(st.hot + 8u * x);
+    const uint32_t kind = h.y >> 16;
+    q.end = h.y & 0xFFFFu;
+    if (kind == KIND_DEFER) q.status = QUERY_DEFER;
+    else if (kind == KIND_EMPTY || q.end == 0) q.status = QUERY_NONE;  // GBWT::find: no record
+    else if (k == 1) q.status = QUERY_FOUND;
+}
+
+// Extends an active query through the pattern nodes [q.i, seg_end) that the warp's tile holds (tile line t = node
+// seg + t of every row; `slot` = this lane's column). QUERY_FOUND: (idx, start, end) is the reference's SearchState;
+// QUERY_NONE: the reference returns None; QUERY_DEFER: the window could not decide and the general kernel redoes the
+// query from the start. The loop has ONE exit (every failure breaks out with its status), so the lanes of a warp
+// reconverge after every step instead of carrying a stack of divergent returns.
+__device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, uint32_t seg, uint32_t seg_end, uint32_t k, WindowQuery& q) {
+    uint32_t idx = q.idx, start = q.start, end = q.end, i = q.i, status = QUERY_ACTIVE;
+    uint2 h = lds64(st.hot + 8u * idx);
+    while (i < seg_end) {
+        const uint32_t x1 = lds16(slot + (i - seg) * (TILE_PITCH * 2u));
+        if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }  // (also pattern node 0: GBWT::extend is None below first_node)
+        const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
         const uint32_t s = start < total ? start : total, e = end < total ? end : total;
-        // GBWT::extend: below first_node, or (Record::follow) an empty range
-        if (x1 == 0 || s >= e) { status = QUERY_NONE; break; }
+        if (s >= e) { status = QUERY_NONE; break; }  // Record::follow on an empty range
         uint32_t b = 0, rs = s, re = e;
         if (kind < KIND_DEFER) {
-            // dense record: rank1(s), and rank1(e) = rank1(e - 1) + bit(e - 1); a range of one position needs one lookup
-            b = x1 == h.y ? 1u : 0u;
-            if (x1 != h.x && x1 != h.y) { status = QUERY_NONE; break; }
-            uint32_t bit;
-            const uint32_t ones_s = staged_rank1(st, kind, s, bit);
-            uint32_t ones_e = ones_s + bit;
-            if (e - 1u != s) { ones_e = staged_rank1(st, kind, e - 1u, bit); ones_e += bit; }
+            // dense record: rank1(s), and rank1(e) = ones up to and including position e - 1
+            b = x1 == (h.x >> 16) ? 1u : 0u;
+            if (x1 != (h.x & 0xFFFFu) && b == 0) { status = QUERY_NONE; break; }
+            const uint32_t ones_s = staged_rank1<false>(st, kind, s);
+            const uint32_t ones_e = staged_rank1<true>(st, kind, e - 1u);
             rs = b ? ones_s : s - ones_s;
             re = b ? ones_e : e - ones_e;
             if (rs >= re) { status = QUERY_NONE; break; }
         } else if (kind == KIND_SINGLE) {
-            if (x1 != h.x) { status = QUERY_NONE; break; }
+            if (x1 != (h.x & 0xFFFFu)) { status = QUERY_NONE; break; }
         } else {
             status = kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;  // BWT::record() is None / a record the window does not decode
             break;
         }
         // two hops at once when the successor is a single-edge record leading to the pattern node after x1
-        const uint2 hop = lds64(st.pair + 16u * idx + 8u * b);
-        uint32_t x2 = 0;
-        if (i + 1 < k && hop.x != 0 && !rd.node(i + 1, x2)) { status = QUERY_DEFER; break; }
-        if (x2 == hop.x && x2 != 0) {
-            start = hop.y + rs; end = hop.y + re;
-            node = x2; i += 2;
+        const uint32_t hop = lds32(st.pair + 8u * idx + 4u * b);
+        const uint32_t x2 = i + 1 < seg_end ? lds16(slot + (i + 1 - seg) * (TILE_PITCH * 2u)) : NODE_OUTSIDE;
+        if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
+            start = (hop >> 16) + rs; end = (hop >> 16) + re;
+            idx = x2; i += 2;
         } else {
-            const uint32_t edge_offset = lds32(st.offs + 8u * idx + 4u * b);
+            const uint32_t edge_offset = lds16(st.offs + 4u * idx + 2u * b);
             start = edge_offset + rs; end = edge_offset + re;
-            node = x1; i += 1;
+            idx = x1; i += 1;
         }
-        if (i >= k) break;
-        idx = node - base - st.lo;
-        if (idx >= st.count) { status = QUERY_DEFER; break; }
-        h = lds128(st.hot + 16u * idx);
+        if (i >= k) { status = QUERY_FOUND; break; }
+        h = lds64(st.hot + 8u * idx);
     }
-    return status;
+    q.idx = idx; q.start = start; q.end = end; q.i = i; q.status = status;
 }
 
 constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
-constexpr uint32_t PATTERN_WORDS = 4;  // words of the pattern column per thread (RowReader::CHUNK)
 
 // Bytes of shared memory a plan needs.
 __host__ __device__ inline uint32_t window_smem_bytes(uint32_t max_records, uint32_t body_cap, uint32_t threads) {
-    return SMEM_HEADER + max_records * 40u + (body_cap / 2u) * 48u + threads * PATTERN_WORDS * 4u;
+    return SMEM_HEADER + max_records * RECORD_BYTES + (body_cap / 2u) * 48u + (threads / 32u) * TILE_BYTES;
 }
 
 template <class T, int THREADS, int CTAS>
@@ -284,26 +257,30 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
     Staged st;
     st.hot = smem_addr(smem) + SMEM_HEADER;
-    st.pair = st.hot + 16u * wp.max_records;
-    st.offs = st.pair + 16u * wp.max_records;
-    st.words = st.offs + 8u * wp.max_records;
-    const uint32_t pattern_slot = st.words + (wp.body_cap / 2u) * 48u + 4u * tid;
+    st.pair = st.hot + 8u * wp.max_records;
+    st.offs = st.pair + 8u * wp.max_records;
+    st.ranks = st.offs + 4u * wp.max_records;
+    const uint32_t tile = st.ranks + (wp.body_cap / 2u) * 48u + (tid >> 5) * TILE_BYTES, slot = tile + 2u * lane;
+    // sector loads need every row segment on a 32-byte boundary
+    const bool aligned = (reinterpret_cast<uintptr_t>(patterns) & 31u) == 0 && (k * sizeof(T)) % 32u == 0;
     for (;;) {
         __syncthreads();  // everybody has left the previous window: its shared memory and ctrl[] may be reused
         if (tid == 0) { ctrl[0] = atomicAdd(&counters[0], 1u); ctrl[1] = 0; }
         __syncthreads();
         const uint32_t w = ctrl[0];
         if (w >= wp.windows) break;
-        const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1), q_end = __ldg(bucket_end + w);
+        // (bucket_end[] has one entry per sort bucket, 2^fine of them per window)
+        const uint32_t fine_buckets = ((records - 1u) >> (wp.wshift - wp.fine)) + 1u, after = (w + 1u) << wp.fine;
+        const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + (w << wp.fine) - 1u);
+        const uint32_t q_end = __ldg(bucket_end + (after < fine_buckets ? after : fine_buckets) - 1u);
         if (q_begin >= q_end) continue;
-        // Queries are handed out 32 at a time per warp; the pattern rows of a warp's NEXT 32 queries are requested from
-        // L2 before it works on the current ones, so that the row reads of the loop find them there (the rows of a
-        // sorted batch are scattered over HBM, and a thread has only one sector of its row in flight at a time).
-        uint32_t slot = 0, q_cur = 0;
-        if (lane == 0) slot = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
-        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-        if (slot + lane < q_end) {
-            q_cur = __ldg(perm + slot + lane);
+        // Queries are handed out 32 at a time per warp; with wp.prefetch the pattern rows of a warp's NEXT 32 queries are
+        // requested from L2 before it works on the current ones.
+        uint32_t at = 0, q_cur = 0;
+        if (lane == 0) at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        if (at + lane < q_end) {
+            q_cur = __ldg(perm + at + lane);
             if (wp.prefetch) prefetch_row(patterns + static_cast<size_t>(q_cur) * k, k);
         }
         const uint32_t r0 = w << wp.wshift;
@@ -311,6 +288,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         const uint32_t want_hi = r0 + (1u << wp.wshift) + wp.margin;
         const uint32_t hi = want_hi < records ? want_hi : records;
         st.count = hi - st.lo;
+        const uint32_t origin = base + st.lo;
         const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
         const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
         const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
@@ -320,58 +298,94 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
             load_sector(reinterpret_cast<const Unit16*>(ix.desc + st.lo + r), d.a, d.b);
             const Quad skip = load_quad(ix.skips + st.lo + r);
             const uint32_t fmt = d.fmt();
-            uint32_t kind = KIND_DEFER, node1 = 0;
-            if (fmt == FMT_SINGLE) kind = KIND_SINGLE;
-            else if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
-            else if (fmt == FMT_DENSE2) {
-                const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
-                if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units) { kind = (unit0 / 2u) * 6u; node1 = d.node1(); }
+            uint32_t kind = KIND_DEFER, target0 = NODE_OUTSIDE, target1 = NODE_OUTSIDE, total = 0, offset0 = 0, offset1 = 0;
+            if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
+            else if (d.total_len() < 0xFFFFu) {
+                total = d.total_len();
+                if (fmt == FMT_SINGLE && d.offset0() <= 0xFFFFu) {
+                    kind = KIND_SINGLE; target0 = window_index(d.node0(), origin, st.count); offset0 = d.offset0();
+                } else if (fmt == FMT_DENSE2 && d.offset0() <= 0xFFFFu && d.offset1() <= 0xFFFFu) {
+                    const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
+                    if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units && (unit0 / 2u) * 12u < KIND_DEFER) {
+                        kind = (unit0 / 2u) * 12u;
+                        target0 = window_index(d.node0(), origin, st.count); target1 = window_index(d.node1(), origin, st.count);
+                        offset0 = d.offset0(); offset1 = d.offset1();
+                    }
+                }
             }
-            sts128(st.hot + 16u * r, d.node0(), node1, fmt == FMT_EMPTY ? 0u : d.total_len(), kind);
-            sts128(st.pair + 16u * r, skip.x, skip.y, skip.z, skip.w);
-            sts64(st.offs + 8u * r, d.offset0(), d.offset1());
+            // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
+            const uint32_t land0 = skip.y <= 0xFFFFu ? window_index(skip.x, origin, st.count) : NODE_OUTSIDE;
+            const uint32_t land1 = skip.w <= 0xFFFFu ? window_index(skip.z, origin, st.count) : NODE_OUTSIDE;
+            sts64(st.hot + 8u * r, target0 | (target1 << 16), total | (kind << 16));
+            sts64(st.pair + 8u * r, land0 | (skip.y << 16), land1 | (skip.w << 16));
+            sts32(st.offs + 4u * r, offset0 | (offset1 << 16));
         }
-        // ... and the dense blocks as {ones before, 32 bits} words
+        // ... and the dense blocks as {ones before, 16 bits} entries
         for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
             Quad lo, hi;
             load_sector(ix.bodies + body_lo + 2u * blk, lo, hi);
             const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
             uint32_t ones = lo.x;
-            const uint32_t at = st.words + 48u * blk;
+            const uint32_t at_block = st.ranks + 48u * blk;
 #pragma unroll
             for (uint32_t j = 0; j < 6; j += 2) {
-                const uint32_t next = ones + static_cast<uint32_t>(__popc(bits[j]));
-                sts128(at + 8u * j, ones, bits[j], next, bits[j + 1]);
-                ones = next + static_cast<uint32_t>(__popc(bits[j + 1]));
+                const uint32_t a0 = bits[j] & 0xFFFFu, a1 = bits[j] >> 16, b0 = bits[j + 1] & 0xFFFFu, b1 = bits[j + 1] >> 16;
+                const uint32_t o1 = ones + static_cast<uint32_t>(__popc(a0)), o2 = o1 + static_cast<uint32_t>(__popc(a1));
+                const uint32_t o3 = o2 + static_cast<uint32_t>(__popc(b0));
+                sts128(at_block + 8u * j, (ones & 0xFFFFu) | (a0 << 16), (o1 & 0xFFFFu) | (a1 << 16), (o2 & 0xFFFFu) | (b0 << 16), (o3 & 0xFFFFu) | (b1 << 16));
+                ones = o3 + static_cast<uint32_t>(__popc(b1));
             }
         }
         __syncthreads();
-        while (slot < q_end) {
-            uint32_t next_slot = 0, q_next = 0;
-            if (lane == 0) next_slot = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
-            next_slot = __shfl_sync(0xFFFFFFFFu, next_slot, 0);
-            if (next_slot + lane < q_end) {
-                q_next = __ldg(perm + next_slot + lane);
+        while (at < q_end) {
+            uint32_t next_at = 0, q_next = 0;
+            if (lane == 0) next_at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+            next_at = __shfl_sync(0xFFFFFFFFu, next_at, 0);
+            if (next_at + lane < q_end) {
+                q_next = __ldg(perm + next_at + lane);
                 if (wp.prefetch) prefetch_row(patterns + static_cast<size_t>(q_next) * k, k);
             }
-            if (slot + lane < q_end) {
-                const uint32_t q = q_cur;
-                RowReader<T> rd(patterns + static_cast<size_t>(q) * k, k, pattern_slot, 4u * THREADS);
-                uint32_t node = 0, start = 0, end = 0;
-                const uint32_t status = window_query(st, base, rd, k, node, start, end);
-                if (status == QUERY_DEFER) {
-                    deferred[atomicAdd(&counters[1], 1u)] = q;
+            const bool mine = at + lane < q_end;
+            const T* row = mine ? patterns + static_cast<size_t>(q_cur) * k : nullptr;
+            WindowQuery q;
+            q.idx = 0; q.start = 0; q.end = 0; q.i = 0; q.status = mine && k != 0 ? QUERY_ACTIVE : QUERY_NONE;
+            for (uint32_t seg = 0; seg < k; seg += SEGMENT) {
+                if (!__any_sync(0xFFFFFFFFu, q.status == QUERY_ACTIVE)) break;
+                const uint32_t n_seg = k - seg < SEGMENT ? k - seg : SEGMENT;
+                load_tile<T>(q.status == QUERY_ACTIVE ? row : nullptr, seg, n_seg, aligned && n_seg % (32u / sizeof(T)) == 0, tile, origin, st.count, lane);
+                __syncwarp();
+                if (q.status == QUERY_ACTIVE) {
+                    if (seg == 0) window_find(st, lds16(slot), k, q);
+                    if (q.status == QUERY_ACTIVE) window_extend(st, slot, seg, seg + n_seg, k, q);
+                }
+                __syncwarp();  // the tile is rewritten in the next round
+            }
+            if (mine) {
+                if (q.status == QUERY_DEFER || q.status == QUERY_ACTIVE) {
+                    deferred[atomicAdd(&counters[1], 1u)] = q_cur;
                 } else {
-                    const bool found = status == QUERY_FOUND;
+                    const bool found = q.status == QUERY_FOUND;
                     gbwt_b200_state result;
-                    result.node = found ? node : 0u; result.start = found ? start : 0u; result.end = found ? end : 0u;
-                    store_state(out + q, result);
+                    result.node = found ? q.idx + origin : 0u; result.start = found ? q.start : 0u; result.end = found ? q.end : 0u;
+                    store_state(out + q_cur, result);
                 }
             }
-            slot = next_slot; q_cur = q_next;
+            at = next_at; q_cur = q_next;
         }
     }
 }
+
+// Pattern reader of the kernels that keep the chunk in registers (the general loop for deferred queries and the plain
+// 32-bit kernels): same interface, no shared memory.
+template <class T>
+struct PlainRowReader {
+    const T* p;
+    __device__ __forceinline__ bool node(uint32_t i, uint32_t& out) {
+        const uint64_t v = __ldg(p + i);
+        out = static_cast<uint32_t>(v);
+        return (v >> 32) == 0;
+    }
+};
 
 // The deferred queries, by the general rounds loop (every record format, every edge case).
 template <class T>
@@ -457,6 +471,7 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
     plan.windows = static_cast<uint32_t>(((ix.records - 1) >> plan.wshift) + 1);
     plan.threads = threads;
     plan.prefetch = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_PREFETCH", 0));
+    plan.fine = static_cast<uint32_t>(std::min<int>(std::max(0, env_or("GBWT_B200_WINDOW_FINE", 0)), static_cast<int>(plan.wshift)));
     plan.smem_bytes = window_smem_bytes(plan.max_records, plan.body_cap, threads);
     return true;
 }
@@ -464,7 +479,7 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
 template <class T>
 void launch_window_keys(const IndexView& ix, const WindowPlan& plan, const T* patterns, size_t n, size_t k, uint32_t* keys,
                         uint32_t* counts, unsigned grid, cudaStream_t stream) {
-    k_window_keys<T><<<grid, BLOCK_THREADS, 0, stream>>>(ix, plan.wshift, patterns, n, k, keys, counts);
+    k_window_keys<T><<<grid, BLOCK_THREADS, 0, stream>>>(ix, plan.wshift - plan.fine, patterns, n, k, keys, counts);
 }
 
 template <class T>

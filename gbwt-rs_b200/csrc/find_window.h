@@ -20,6 +20,8 @@ struct WindowPlan {
     uint32_t threads;      // CTA size: 256, 512 or 1024
     uint32_t smem_bytes;   // dynamic shared memory per CTA
     uint32_t prefetch;     // ask L2 for the pattern rows of a warp's next 32 queries (GBWT_B200_WINDOW_PREFETCH)
+    uint32_t fine;         // the sort's buckets are 2^(wshift - fine) records: 2^fine buckets per window, so that the queries a
+                           // warp takes together start within a few records of each other (GBWT_B200_WINDOW_FINE)
 };
 
 // Chooses the plan for an index (GBWT_B200_WINDOW / _MARGIN / _SMEM_KB / _THREADS override). False = do not use
