@@ -31,6 +31,11 @@ namespace {
 // ---- shared-memory accessors (32-bit shared-space addresses: no generic-pointer arithmetic in the loop) --------------
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -43,9 +48,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 
@@ -60,16 +62,24 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st
 // search loop a lane reads node t of its own row with one conflict-free 16-bit load however t moves.
 constexpr uint32_t SEGMENT = 16;            // pattern nodes per round
 constexpr uint32_t TILE_PITCH = 34;         // 16-bit slots per tile line: 32 rows + 2 (the lanes that share a row store 4 lines apart: 16 distinct banks)
-constexpr uint32_t TILE_BYTES = SEGMENT * TILE_PITCH * 2u;
+constexpr uint32_t TILE_LINE = TILE_PITCH * 2u;  // bytes from node t to node t + 1 of a row
+constexpr uint32_t TILE_BYTES = (SEGMENT + 1u) * TILE_LINE;  // one line more than a segment: the line after the last node always reads NODE_OUTSIDE
 constexpr uint32_t NODE_OUTSIDE = 0xFFFFu;  // not a record of the staged window (or node 0, the endmarker)
 
-__device__ __forceinline__ uint32_t window_index(uint64_t node, uint32_t origin, uint32_t count) {
-    const uint64_t rel = node - origin;
-    return node != 0 && rel < count ? static_cast<uint32_t>(rel) : NODE_OUTSIDE;
-}
+// Window index of an edge target (node 0, the endmarker, is never a record to go on with).
 __device__ __forceinline__ uint32_t window_index(uint32_t node, uint32_t origin, uint32_t count) {
     const uint32_t rel = node - origin;
     return node != 0 && rel < count ? rel : NODE_OUTSIDE;
+}
+// Window index of a pattern node. No test for node 0: if record 0 is staged at all (origin == 0) it is the endmarker's,
+// which window_find defers and which no table entry names as a target, so a pattern node 0 never matches anything.
+__device__ __forceinline__ uint32_t pattern_index(uint64_t node, uint32_t origin, uint32_t count) {
+    const uint64_t rel = node - origin;
+    return rel < count ? static_cast<uint32_t>(rel) : NODE_OUTSIDE;
+}
+__device__ __forceinline__ uint32_t pattern_index(uint32_t node, uint32_t origin, uint32_t count) {
+    const uint32_t rel = node - origin;
+    return rel < count ? rel : NODE_OUTSIDE;
 }
 
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t x) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(x)) : "memory"); }
@@ -117,14 +127,14 @@ __device__ __forceinline__ void load_tile(const T* row, uint32_t seg, uint32_t n
             if (have[j]) {
 #pragma unroll
                 for (uint32_t t = 0; t < PER_SECTOR; t++)
-                    sts16(tile + ((sub * PER_SECTOR + t) * TILE_PITCH + r) * 2u, window_index(v[j][t], origin, count));
+                    sts16(tile + ((sub * PER_SECTOR + t) * TILE_PITCH + r) * 2u, pattern_index(v[j][t], origin, count));
             }
         }
     } else {
         for (uint32_t e = lane; e < 32u * n_seg; e += 32u) {
             const uint32_t r = e / n_seg, t = e - r * n_seg;
             const T* p = reinterpret_cast<const T*>(__shfl_sync(0xFFFFFFFFu, mine, r));
-            if (p != nullptr) sts16(tile + (t * TILE_PITCH + r) * 2u, window_index(__ldg(p + seg + t), origin, count));
+            if (p != nullptr) sts16(tile + (t * TILE_PITCH + r) * 2u, pattern_index(__ldg(p + seg + t), origin, count));
         }
     }
 }
@@ -148,29 +158,21 @@ __device__ __forceinline__ uint64_t first_node(const uint32_t* patterns, size_t 
 // being bank conflicts of 8- and 16-byte loads at random records, so every table entry is as narrow as it can be.
 // Nodes are indexes into the window (NODE_OUTSIDE when the node is not staged); a record with a field that does not
 // fit 16 bits is marked KIND_DEFER.
-//   hot[r]    8 B  {target0 | target1 << 16, total_len | kind << 16}: kind = index of the record's first rank entry for a
-//                  dense record, or KIND_SINGLE / KIND_EMPTY / KIND_DEFER (run-length body, outdegree > 2, body not staged)
-//   pair[r]   8 B  per edge the two-hop shortcut {landing node | offset << 16} (layout.h, IndexView::skips)
+//   rec[r]   16 B  {target0 | target1 << 16, total_len | kind << 16, shortcut0, shortcut1}: kind = index of the record's
+//                  first rank entry for a dense record, or KIND_SINGLE / KIND_EMPTY / KIND_DEFER (run-length body,
+//                  outdegree > 2, body not staged); shortcut = the two-hop shortcut of the edge {landing node | offset << 16}
+//                  (layout.h, IndexView::skips). One 16-byte load per step.
 //   offs[r]   4 B  {offset0 | offset1 << 16}: only read when a step cannot take the shortcut
 //   ranks[]   4 B  {ones before | 16 bits << 16}: rank at position p of a record is ONE 4-byte load at kind + p / 16
 constexpr uint32_t KIND_SINGLE = 0xFFFFu, KIND_EMPTY = 0xFFFEu, KIND_DEFER = 0xFFFDu;  // anything below: dense
-constexpr uint32_t RECORD_BYTES = 20;  // hot + pair + offs
+constexpr uint32_t RECORD_BYTES = 20;  // rec + offs
 
 struct Staged {
-    uint32_t hot, pair, offs, ranks;  // shared-space addresses
-    uint32_t lo, count;               // staged records [lo, lo + count)
+    uint32_t rec, offs, ranks;  // shared-space addresses
+    uint32_t lo, count;         // staged records [lo, lo + count)
 };
 
 enum : uint32_t { QUERY_ACTIVE = 0, QUERY_FOUND = 1, QUERY_NONE = 2, QUERY_DEFER = 3 };
-
-// ones in [0, p) of the dense record whose first rank entry is `kind`; with INCLUSIVE the bit at p counts too
-template <bool INCLUSIVE>
-__device__ __forceinline__ uint32_t staged_rank1(const Staged& st, uint32_t kind, uint32_t p) {
-    const uint32_t w = lds32(st.ranks + 4u * (kind + (p >> 4)));
-    const uint32_t sh = p & 15u;
-    const uint32_t mask = INCLUSIVE ? ((2u << sh) - 1u) : ((1u << sh) - 1u);
-    return (w & 0xFFFFu) + static_cast<uint32_t>(__popc((w >> 16) & mask));
-}
 
 // The state of one query between rounds.
 struct WindowQuery {
@@ -184,7 +186,7 @@ struct WindowQuery {
 __device__ __forceinline__ void window_find(const Staged& st, uint32_t x, uint32_t k, WindowQuery& q) {
     q.idx = x; q.start = 0; q.end = 0; q.i = 1; q.status = QUERY_ACTIVE;
     if (x == NODE_OUTSIDE || x + st.lo == 0) { q.status = QUERY_DEFER; return; }  // (record 0 is the endmarker: find() is None; let the general code say so)
-    const uint2 h = lds64(st.hot + 8u * x);
+    const uint2 h = lds64(st.rec + 16u * x);
     const uint32_t kind = h.y >> 16;
     q.end = h.y & 0xFFFFu;
     if (kind == KIND_DEFER) q.status = QUERY_DEFER;
@@ -192,27 +194,32 @@ __device__ __forceinline__ void window_find(const Staged& st, uint32_t x, uint32
     else if (k == 1) q.status = QUERY_FOUND;
 }
 
-// Extends an active query through the pattern nodes [q.i, seg_end) that the warp's tile holds (tile line t = node
-// seg + t of every row; `slot` = this lane's column). QUERY_FOUND: (idx, start, end) is the reference's SearchState;
-// QUERY_NONE: the reference returns None; QUERY_DEFER: the window could not decide and the general kernel redoes the
-// query from the start. The loop has ONE exit (every failure breaks out with its status), so the lanes of a warp
-// reconverge after every step instead of carrying a stack of divergent returns.
-__device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, uint32_t seg, uint32_t seg_end, uint32_t k, WindowQuery& q) {
-    uint32_t idx = q.idx, start = q.start, end = q.end, i = q.i, status = QUERY_ACTIVE;
-    uint2 h = lds64(st.hot + 8u * idx);
-    while (i < seg_end) {
-        const uint32_t x1 = lds16(slot + (i - seg) * (TILE_PITCH * 2u));
-        if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }  // (also pattern node 0: GBWT::extend is None below first_node)
+// Extends an active query through the pattern nodes [q.i, seg + n_seg) that the warp's tile holds (tile line t = node
+// seg + t of every row, the line after the last node reads NODE_OUTSIDE; `slot` = this lane's column). QUERY_FOUND:
+// (idx, start, end) is the reference's SearchState; QUERY_NONE: the reference returns None; QUERY_DEFER: the window
+// could not decide and the general kernel redoes the query from the start. The loop has ONE exit (every failure
+// breaks out with its status), so the lanes of a warp reconverge after every step instead of carrying a stack of
+// divergent returns. Per step: the two pattern nodes, one 16-byte record entry, one or two rank entries.
+__device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, uint32_t seg, uint32_t n_seg, uint32_t k, WindowQuery& q) {
+    uint32_t idx = q.idx, start = q.start, end = q.end, status = QUERY_ACTIVE;
+    uint32_t pat = slot + (q.i - seg) * TILE_LINE;
+    const uint32_t pat_end = slot + n_seg * TILE_LINE;
+    uint4 h = lds128(st.rec + 16u * idx);
+    while (pat < pat_end) {
+        const uint32_t x1 = lds16(pat), x2 = lds16(pat + TILE_LINE);
         const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
         const uint32_t s = start < total ? start : total, e = end < total ? end : total;
+        if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }
         if (s >= e) { status = QUERY_NONE; break; }  // Record::follow on an empty range
-        uint32_t b = 0, rs = s, re = e;
+        const uint32_t b = x1 == (h.x >> 16) ? 1u : 0u;
+        uint32_t rs = s, re = e;
         if (kind < KIND_DEFER) {
             // dense record: rank1(s), and rank1(e) = ones up to and including position e - 1
-            b = x1 == (h.x >> 16) ? 1u : 0u;
             if (x1 != (h.x & 0xFFFFu) && b == 0) { status = QUERY_NONE; break; }
-            const uint32_t ones_s = staged_rank1<false>(st, kind, s);
-            const uint32_t ones_e = staged_rank1<true>(st, kind, e - 1u);
+            const uint32_t last = e - 1u;
+            const uint32_t ws = lds32(st.ranks + 4u * (kind + (s >> 4))), we = lds32(st.ranks + 4u * (kind + (last >> 4)));
+            const uint32_t ones_s = (ws & 0xFFFFu) + static_cast<uint32_t>(__popc((ws >> 16) & ~(0xFFFFFFFFu << (s & 15u))));
+            const uint32_t ones_e = (we & 0xFFFFu) + static_cast<uint32_t>(__popc((we >> 16) & ~(0xFFFFFFFEu << (last & 15u))));
             rs = b ? ones_s : s - ones_s;
             re = b ? ones_e : e - ones_e;
             if (rs >= re) { status = QUERY_NONE; break; }
@@ -223,20 +230,19 @@ __device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, u
             break;
         }
         // two hops at once when the successor is a single-edge record leading to the pattern node after x1
-        const uint32_t hop = lds32(st.pair + 8u * idx + 4u * b);
-        const uint32_t x2 = i + 1 < seg_end ? lds16(slot + (i + 1 - seg) * (TILE_PITCH * 2u)) : NODE_OUTSIDE;
+        const uint32_t hop = b ? h.w : h.z;
+        uint32_t offset;
         if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
-            start = (hop >> 16) + rs; end = (hop >> 16) + re;
-            idx = x2; i += 2;
+            offset = hop >> 16; idx = x2; pat += 2u * TILE_LINE;
         } else {
-            const uint32_t edge_offset = lds16(st.offs + 4u * idx + 2u * b);
-            start = edge_offset + rs; end = edge_offset + re;
-            idx = x1; i += 1;
+            offset = lds16(st.offs + 4u * idx + 2u * b); idx = x1; pat += TILE_LINE;
         }
-        if (i >= k) { status = QUERY_FOUND; break; }
-        h = lds64(st.hot + 8u * idx);
+        start = offset + rs; end = offset + re;
+        if (pat >= pat_end) break;
+        h = lds128(st.rec + 16u * idx);
     }
-    q.idx = idx; q.start = start; q.end = end; q.i = i; q.status = status;
+    q.idx = idx; q.start = start; q.end = end; q.i = seg + (pat - slot) / TILE_LINE;
+    q.status = status == QUERY_ACTIVE && q.i >= k ? QUERY_FOUND : status;
 }
 
 constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
@@ -256,11 +262,14 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
     Staged st;
-    st.hot = smem_addr(smem) + SMEM_HEADER;
-    st.pair = st.hot + 8u * wp.max_records;
-    st.offs = st.pair + 8u * wp.max_records;
+    st.rec = smem_addr(smem) + SMEM_HEADER;
+    st.offs = st.rec + 16u * wp.max_records;
     st.ranks = st.offs + 4u * wp.max_records;
-    const uint32_t tile = st.ranks + (wp.body_cap / 2u) * 48u + (tid >> 5) * TILE_BYTES, slot = tile + 2u * lane;
+    uint32_t tile = st.ranks + (wp.body_cap / 2u) * 48u + (tid >> 5) * TILE_BYTES;
+    // (opaque to the compiler: it would otherwise recompute the shared-window addresses from special registers in every step)
+    asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(tile));
+    const uint32_t slot = tile + 2u * lane;
+    sts16(slot + SEGMENT * TILE_LINE, NODE_OUTSIDE);  // the line after a full segment
     // sector loads need every row segment on a 32-byte boundary
     const bool aligned = (reinterpret_cast<uintptr_t>(patterns) & 31u) == 0 && (k * sizeof(T)) % 32u == 0;
     for (;;) {
@@ -316,8 +325,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
             // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
             const uint32_t land0 = skip.y <= 0xFFFFu ? window_index(skip.x, origin, st.count) : NODE_OUTSIDE;
             const uint32_t land1 = skip.w <= 0xFFFFu ? window_index(skip.z, origin, st.count) : NODE_OUTSIDE;
-            sts64(st.hot + 8u * r, target0 | (target1 << 16), total | (kind << 16));
-            sts64(st.pair + 8u * r, land0 | (skip.y << 16), land1 | (skip.w << 16));
+            sts128(st.rec + 16u * r, target0 | (target1 << 16), total | (kind << 16), land0 | (skip.y << 16), land1 | (skip.w << 16));
             sts32(st.offs + 4u * r, offset0 | (offset1 << 16));
         }
         // ... and the dense blocks as {ones before, 16 bits} entries
@@ -353,10 +361,11 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
                 if (!__any_sync(0xFFFFFFFFu, q.status == QUERY_ACTIVE)) break;
                 const uint32_t n_seg = k - seg < SEGMENT ? k - seg : SEGMENT;
                 load_tile<T>(q.status == QUERY_ACTIVE ? row : nullptr, seg, n_seg, aligned && n_seg % (32u / sizeof(T)) == 0, tile, origin, st.count, lane);
+                if (n_seg < SEGMENT) sts16(slot + n_seg * TILE_LINE, NODE_OUTSIDE);  // the line after a short segment
                 __syncwarp();
                 if (q.status == QUERY_ACTIVE) {
                     if (seg == 0) window_find(st, lds16(slot), k, q);
-                    if (q.status == QUERY_ACTIVE) window_extend(st, slot, seg, seg + n_seg, k, q);
+                    if (q.status == QUERY_ACTIVE) window_extend(st, slot, seg, n_seg, k, q);
                 }
                 __syncwarp();  // the tile is rewritten in the next round
             }
