@@ -82,10 +82,11 @@ __device__ __forceinline__ uint32_t pattern_index(uint32_t node, uint32_t origin
     return rel < count ? rel : NODE_OUTSIDE;
 }
 
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t x) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(x)) : "memory"); }
+// (16-bit shared accesses on 32-bit registers: the load zero-extends, the store writes the low half)
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t x) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 
@@ -245,6 +246,47 @@ __device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, u
     q.status = status == QUERY_ACTIVE && q.i >= k ? QUERY_FOUND : status;
 }
 
+// One record of the window, from its descriptor and shortcuts to its table entries.
+__device__ __forceinline__ void stage_record(const Staged& st, uint32_t r, const Desc& d, const Quad& skip, uint32_t origin, uint32_t body_lo,
+                                             uint32_t body_units) {
+    const uint32_t fmt = d.fmt();
+    uint32_t kind = KIND_DEFER, target0 = NODE_OUTSIDE, target1 = NODE_OUTSIDE, total = 0, offset0 = 0, offset1 = 0;
+    if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
+    else if (d.total_len() < 0xFFFFu) {
+        total = d.total_len();
+        if (fmt == FMT_SINGLE && d.offset0() <= 0xFFFFu) {
+            kind = KIND_SINGLE; target0 = window_index(d.node0(), origin, st.count); offset0 = d.offset0();
+        } else if (fmt == FMT_DENSE2 && d.offset0() <= 0xFFFFu && d.offset1() <= 0xFFFFu) {
+            const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
+            if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units && (unit0 / 2u) * 12u < KIND_DEFER) {
+                kind = (unit0 / 2u) * 12u;
+                target0 = window_index(d.node0(), origin, st.count); target1 = window_index(d.node1(), origin, st.count);
+                offset0 = d.offset0(); offset1 = d.offset1();
+            }
+        }
+    }
+    // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
+    const uint32_t land0 = skip.y <= 0xFFFFu ? window_index(skip.x, origin, st.count) : NODE_OUTSIDE;
+    const uint32_t land1 = skip.w <= 0xFFFFu ? window_index(skip.z, origin, st.count) : NODE_OUTSIDE;
+    sts128(st.rec + 16u * r, target0 | (target1 << 16), total | (kind << 16), land0 | (skip.y << 16), land1 | (skip.w << 16));
+    sts32(st.offs + 4u * r, offset0 | (offset1 << 16));
+}
+
+// One 192-bit dense block (layout.h) as twelve rank entries.
+__device__ __forceinline__ void stage_block(const Staged& st, uint32_t blk, const Quad& lo, const Quad& hi) {
+    const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t ones = lo.x;
+    const uint32_t at_block = st.ranks + 48u * blk;
+#pragma unroll
+    for (uint32_t j = 0; j < 6; j += 2) {
+        const uint32_t a0 = bits[j] & 0xFFFFu, a1 = bits[j] >> 16, b0 = bits[j + 1] & 0xFFFFu, b1 = bits[j + 1] >> 16;
+        const uint32_t o1 = ones + static_cast<uint32_t>(__popc(a0)), o2 = o1 + static_cast<uint32_t>(__popc(a1));
+        const uint32_t o3 = o2 + static_cast<uint32_t>(__popc(b0));
+        sts128(at_block + 8u * j, (ones & 0xFFFFu) | (a0 << 16), (o1 & 0xFFFFu) | (a1 << 16), (o2 & 0xFFFFu) | (b0 << 16), (o3 & 0xFFFFu) | (b1 << 16));
+        ones = o3 + static_cast<uint32_t>(__popc(b1));
+    }
+}
+
 constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
 
 // Bytes of shared memory a plan needs.
@@ -301,48 +343,19 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
         const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
         const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
-        // decode the window into shared memory: descriptors + shortcuts ...
+        // decode the window into shared memory: descriptors + shortcuts, then the dense blocks as {ones before, 16 bits}
+        // entries (requesting two records or blocks per thread before decoding either was measured: the extra live
+        // registers spill under the 64-register budget of two 512-thread CTAs per SM, 6.2 -> 5.0 G queries/s)
         for (uint32_t r = tid; r < st.count; r += THREADS) {
             Desc d;
             load_sector(reinterpret_cast<const Unit16*>(ix.desc + st.lo + r), d.a, d.b);
             const Quad skip = load_quad(ix.skips + st.lo + r);
-            const uint32_t fmt = d.fmt();
-            uint32_t kind = KIND_DEFER, target0 = NODE_OUTSIDE, target1 = NODE_OUTSIDE, total = 0, offset0 = 0, offset1 = 0;
-            if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
-            else if (d.total_len() < 0xFFFFu) {
-                total = d.total_len();
-                if (fmt == FMT_SINGLE && d.offset0() <= 0xFFFFu) {
-                    kind = KIND_SINGLE; target0 = window_index(d.node0(), origin, st.count); offset0 = d.offset0();
-                } else if (fmt == FMT_DENSE2 && d.offset0() <= 0xFFFFu && d.offset1() <= 0xFFFFu) {
-                    const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
-                    if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units && (unit0 / 2u) * 12u < KIND_DEFER) {
-                        kind = (unit0 / 2u) * 12u;
-                        target0 = window_index(d.node0(), origin, st.count); target1 = window_index(d.node1(), origin, st.count);
-                        offset0 = d.offset0(); offset1 = d.offset1();
-                    }
-                }
-            }
-            // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
-            const uint32_t land0 = skip.y <= 0xFFFFu ? window_index(skip.x, origin, st.count) : NODE_OUTSIDE;
-            const uint32_t land1 = skip.w <= 0xFFFFu ? window_index(skip.z, origin, st.count) : NODE_OUTSIDE;
-            sts128(st.rec + 16u * r, target0 | (target1 << 16), total | (kind << 16), land0 | (skip.y << 16), land1 | (skip.w << 16));
-            sts32(st.offs + 4u * r, offset0 | (offset1 << 16));
+            stage_record(st, r, d, skip, origin, body_lo, body_units);
         }
-        // ... and the dense blocks as {ones before, 16 bits} entries
         for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
             Quad lo, hi;
             load_sector(ix.bodies + body_lo + 2u * blk, lo, hi);
-            const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            uint32_t ones = lo.x;
-            const uint32_t at_block = st.ranks + 48u * blk;
-#pragma unroll
-            for (uint32_t j = 0; j < 6; j += 2) {
-                const uint32_t a0 = bits[j] & 0xFFFFu, a1 = bits[j] >> 16, b0 = bits[j + 1] & 0xFFFFu, b1 = bits[j + 1] >> 16;
-                const uint32_t o1 = ones + static_cast<uint32_t>(__popc(a0)), o2 = o1 + static_cast<uint32_t>(__popc(a1));
-                const uint32_t o3 = o2 + static_cast<uint32_t>(__popc(b0));
-                sts128(at_block + 8u * j, (ones & 0xFFFFu) | (a0 << 16), (o1 & 0xFFFFu) | (a1 << 16), (o2 & 0xFFFFu) | (b0 << 16), (o3 & 0xFFFFu) | (b1 << 16));
-                ones = o3 + static_cast<uint32_t>(__popc(b1));
-            }
+            stage_block(st, blk, lo, hi);
         }
         __syncthreads();
         while (at < q_end) {
