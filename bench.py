@@ -35,8 +35,17 @@ WORKLOADS = {
     "find-c3": (33_333, 64, 10_000_000),
     "extract": (3_333_333, 1024, 0),
     "extract-dna": (3_333_333, 1024, 0),
+    # the run-length workload: 10 M node ids x 1024 haplotypes with alternative alleles of frequency 0.05 and every tenth
+    # site tri-allelic (synth variant model): anchors with three edges keep run-length bodies (records_run8 > 0)
+    "find-runs": (2_500_000, 1024, 1 << 26),
 }
 SEED, SEED_Q, K_LEN = 42, 7, 32
+# allele model per workload (synth.bubble_chain): alt_ppm = 0 is the default model (two equally likely alleles)
+MODELS = {"find-runs": {"alt_ppm": 50_000, "tri_mod": 10}}
+
+
+def model_of(args):
+    return MODELS.get(args.workload, {"alt_ppm": 0, "tri_mod": 0})
 
 
 def log(*a):
@@ -68,14 +77,14 @@ def dist_env():
 
 # ---- index image shared between the ranks of one box --------------------------------------------------
 
-def get_image(sites, haplotypes, rank, world, barrier):
+def get_image(sites, haplotypes, rank, world, barrier, model):
     """The Simple-SDS GBWT image. With several ranks only rank 0 needs it (it builds the index the others import, and
     runs the oracle); the others get None."""
     from synth import synth
     if rank != 0:
         return None, None
     t = time.time()
-    img = synth.bubble_chain(sites, haplotypes, SEED, threads=(os.cpu_count() or 0) if world > 1 else 0)
+    img = synth.bubble_chain(sites, haplotypes, SEED, threads=(os.cpu_count() or 0) if world > 1 else 0, **model)
     log(f"[bench] generated index image: {img.nbytes / 1e9:.2f} GB in {time.time() - t:.1f} s")
     return img.array, img
 
@@ -150,13 +159,13 @@ def measured_peak_gbs():
 
 # ---- CPU side (oracle = C restatement of the reference path) ------------------------------------------
 
-def cpu_find_baseline(image, sites, haplotypes, sample, steps=1, warmup=0):
+def cpu_find_baseline(image, sites, haplotypes, sample, steps=1, warmup=0, model=None):
     """Times the oracle (kind "port") on all host threads over `sample` queries per step."""
     from oracle import oracle as orc
     from synth import synth
     g = orc.GBWT.load(image, native=True)
     threads = orc.max_threads()
-    pats = synth.patterns(sites, haplotypes, SEED, n=sample, k=K_LEN, seed_q=SEED_Q, q0=1 << 40)
+    pats = synth.patterns(sites, haplotypes, SEED, n=sample, k=K_LEN, seed_q=SEED_Q, q0=1 << 40, **(model or {}))
     for _ in range(warmup):
         g.find_extend_batch(pats, threads=threads)
     t = time.perf_counter()
@@ -180,8 +189,8 @@ def run_reference(args, rank, world):
         return
     sites, haplotypes, _ = resolve_workload(args)
     from synth import synth
-    img = synth.bubble_chain(sites, haplotypes, SEED)
-    base, _ = cpu_find_baseline(img.array, sites, haplotypes, args.cpu_sample, steps=args.steps, warmup=args.warmup)
+    img = synth.bubble_chain(sites, haplotypes, SEED, **model_of(args))
+    base, _ = cpu_find_baseline(img.array, sites, haplotypes, args.cpu_sample, steps=args.steps, warmup=args.warmup, model=model_of(args))
     line = {
         "impl": "reference", "metric": "gbwt_find_queries_per_s_k32", "value": base["value"], "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
@@ -203,8 +212,13 @@ def resolve_workload(args):
 
 
 def workload_config(args, sites, haplotypes, queries, where):
-    return {"workload": f"synthetic bubble-chain GBWT, {3 * sites + 1} nodes x {haplotypes} haplotypes ({sites} sites, iid alleles, "
-                        f"seed {SEED}), length-{K_LEN} find/extend patterns sampled from the haplotypes (seed {SEED_Q})",
+    model = model_of(args)
+    if model["alt_ppm"]:
+        what = (f"synthetic bubble-chain GBWT, {4 * sites + 1} node ids x {haplotypes} haplotypes ({sites} sites, alternative alleles of "
+                f"frequency {model['alt_ppm'] / 1e6:g}, every {model['tri_mod']}th site tri-allelic, seed {SEED})")
+    else:
+        what = f"synthetic bubble-chain GBWT, {3 * sites + 1} nodes x {haplotypes} haplotypes ({sites} sites, iid alleles, seed {SEED})"
+    return {"workload": what + f", length-{K_LEN} find/extend patterns sampled from the haplotypes (seed {SEED_Q})",
             "baseline_config": "BASELINE.json configs[3]" if args.workload == "find" else args.workload,
             "queries_per_gpu_per_step": queries, "pattern_len": K_LEN, "layout": args.layout, "where": where,
             "l2": "inputs larger than L2 (index + pattern batch >> 126 MB), no flush needed",
@@ -298,7 +312,8 @@ def main():
         barrier()  # rank 0 keeps its arrays alive until every rank has copied them
         return ix, max_over_ranks(time.time() - t)
 
-    image, keep = get_image(sites, haplotypes, rank, world, barrier)
+    model = model_of(args)
+    image, keep = get_image(sites, haplotypes, rank, world, barrier, model)
     index, build_s = replicated_index(True)
     stats = index.device_bytes()
     ckpt = index.checkpoint_info()
@@ -321,7 +336,7 @@ def main():
     q0 = rank * Q
     d_pat = torch.empty((Q, K_LEN), dtype=torch.int64, device=dev)
     d_out = torch.empty((Q, 3), dtype=torch.int64, device=dev)
-    synth.patterns_device(sites, haplotypes, SEED, Q, d_pat.data_ptr(), k=K_LEN, seed_q=SEED_Q, q0=q0, stream=stream)
+    synth.patterns_device(sites, haplotypes, SEED, Q, d_pat.data_ptr(), k=K_LEN, seed_q=SEED_Q, q0=q0, stream=stream, **model)
     torch.cuda.synchronize()
 
     def step():
@@ -396,8 +411,8 @@ def main():
         if args.no_cpu_baseline or world > 1:
             g = orc.GBWT.load(image, native=True)
         else:
-            cpu, g = cpu_find_baseline(image, sites, haplotypes, args.cpu_sample)
-        sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=q0)
+            cpu, g = cpu_find_baseline(image, sites, haplotypes, args.cpu_sample, model=model)
+        sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=q0, **model)
         bytes_per_query = g.find_extend_bytes(sample) / sample_n
         want = g.find_extend_batch(sample)
         got = want_out[:sample_n].cpu().numpy().view(np.uint64)

@@ -59,6 +59,7 @@ struct gbwt_b200_index {
     uint64_t graph_bytes = 0;
     uint64_t bytes[4] = {0, 0, 0, 0};
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t checkpointed_records = 0;
     Carried carried;  // tags, DA samples, metadata, Graph section: host-side, written back by serialize
 };
 
@@ -817,6 +818,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
     ix->sequences = parsed.sequences; ix->size = parsed.size; ix->offset = parsed.offset;
     ix->alphabet_size = parsed.alphabet_size; ix->flags = parsed.flags;
     std::memcpy(ix->format_counts, layout.format_counts, sizeof(layout.format_counts));
+    ix->checkpointed_records = layout.checkpointed_records;
     ix->carried.tags = parsed.tags; ix->carried.gbz_tags = parsed.gbz_tags;
     ix->carried.da_samples = parsed.da_samples; ix->carried.metadata = parsed.metadata; ix->carried.graph_section = parsed.graph_section;
     rc = upload(&ix->d_desc, layout.desc.data(), layout.desc.size() * sizeof(RecordDesc), ix->bytes[0]);
@@ -1029,7 +1031,7 @@ struct IpcHeader {
     uint64_t magic, version;
     uint64_t sequences, size, offset, alphabet_size, flags;
     uint64_t records, endmarker_len, bidirectional, edges_valid, walk_limit;
-    uint64_t bytes[4], skip_bytes, format_counts[FMT_COUNT], edges_total, edges_local;
+    uint64_t bytes[4], skip_bytes, format_counts[FMT_COUNT], checkpointed_records, edges_total, edges_local;
     uint64_t window_ok, window_suits;
     WindowPlan window;
     uint64_t ckpt_ok, ckpt_shift, ckpt_entries, ckpt_bytes, ckpt_build_us, ckpt_max_segments;
@@ -1107,6 +1109,7 @@ int gbwt_b200_index_export_ipc(const gbwt_b200_index* ix, void** blob, size_t* l
     for (int i = 0; i < 4; i++) h.bytes[i] = ix->bytes[i];
     h.skip_bytes = ix->skip_bytes;
     for (int i = 0; i < FMT_COUNT; i++) h.format_counts[i] = ix->format_counts[i];
+    h.checkpointed_records = ix->checkpointed_records;
     h.edges_total = ix->edges_total; h.edges_local = ix->edges_local;
     h.window_ok = ix->window_ok; h.window_suits = ix->window_suits; h.window = ix->window;
     h.ckpt_ok = ix->ckpt_ok; h.ckpt_shift = ix->ckpt_shift; h.ckpt_entries = ix->ckpt_entries; h.ckpt_bytes = ix->ckpt_bytes;
@@ -1157,6 +1160,7 @@ int gbwt_b200_index_import_ipc(const void* blob, size_t len, int device, gbwt_b2
         for (int i = 0; i < 4; i++) ix->bytes[i] = h.bytes[i];
         ix->skip_bytes = h.skip_bytes;
         for (int i = 0; i < FMT_COUNT; i++) ix->format_counts[i] = h.format_counts[i];
+        ix->checkpointed_records = h.checkpointed_records;
         ix->edges_total = h.edges_total; ix->edges_local = h.edges_local;
         ix->window_ok = h.window_ok != 0; ix->window_suits = h.window_suits != 0; ix->window = h.window;
         BlobReader rd{static_cast<const uint8_t*>(blob), len, sizeof(IpcHeader)};
@@ -1257,6 +1261,7 @@ int gbwt_b200_has_graph(const gbwt_b200_index* ix) { return ix && ix->has_graph;
 uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* ix) { return ix && ix->has_graph ? ix->graph.sequences : 0; }
 uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* ix) { return ix ? ix->graph_bytes : 0; }
 uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* ix) { return ix ? ix->skip_bytes : 0; }
+uint64_t gbwt_b200_run_checkpoint_records(const gbwt_b200_index* ix) { return ix ? ix->checkpointed_records : 0; }
 
 void gbwt_b200_checkpoint_info(const gbwt_b200_index* ix, uint64_t info[6]) {
     if (ix == nullptr || info == nullptr) return;

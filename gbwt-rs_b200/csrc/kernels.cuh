@@ -829,7 +829,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
         if (!d.inline_edges()) {
             // outdegree > 2: the warp scans a byte-per-run body, anything else takes the general one-lane step
             uint32_t next_node, next_offset;
-            if (fmt == FMT_RUN8) {
+            if (fmt == FMT_RUN8 && d.checkpoints() == 0) {  // (a checkpointed body is a short scan for one lane)
                 uint32_t symbol, rank_i;
                 warp_lf_runs8(ix, d, i, symbol, rank_i);
                 if (symbol == NO_SYMBOL) break;
@@ -863,7 +863,7 @@ __device__ __forceinline__ uint64_t walk_sequence_warp(const IndexView& ix, uint
                 load_sector(bodies + d.body() + 2u * blk, lo, hi);
                 const uint32_t ones = dense_block_rank_lean(lo, hi, i - blk * DENSE_BITS, b);
                 r = b ? ones : i - ones;
-            } else if (fmt == FMT_RUN8) {
+            } else if (fmt == FMT_RUN8 && d.checkpoints() == 0) {
                 warp_lf_runs8(ix, d, i, b, r);
                 if (b == NO_SYMBOL) break;
             } else {

@@ -44,6 +44,13 @@ enum BodyFormat : uint8_t {
 constexpr uint32_t DENSE_BITS = 192;
 constexpr uint32_t DENSE_WORDS = 6;
 constexpr uint8_t DESC_INLINE_EDGES = 1;    // w[] = {node0, offset0, node1, offset1}
+// Checkpointed run bodies: flags bits 1-5 hold log2(P) + 1 when a table of checkpoints follows the runs of a RUN8 /
+// RUN32 / RUN64 body (0: none). The table starts on the next 32-byte boundary after the runs; entry j - 1 describes
+// position j P (j = 1 .. (total_len - 1) / P), in (sigma + 3) / 4 * 4 words: words 0 .. sigma - 2 = the number of
+// positions before j P with a symbol <= v, word sigma - 1 = the index of the run that starts at j P (the builder
+// splits runs at multiples of P). Only for records with at most CKPT_MAX_SIGMA edges and more than CKPT_MIN_RUNS runs.
+constexpr uint32_t DESC_CKPT_SHIFT = 1, DESC_CKPT_MASK = 31;
+constexpr uint32_t CKPT_MAX_SIGMA = 64, CKPT_MIN_RUNS = 32, CKPT_RUNS_PER_INTERVAL = 32;
 constexpr uint32_t RUN32_MAX_LEN = 1u << 24;
 constexpr uint32_t NO_SYMBOL = 0xFFFFFFFFu;
 // Window kernels (find_window.cuh): record windows are staged into shared memory in multiples of STAGE_GRANULE

@@ -64,14 +64,31 @@ struct Plan {
     uint64_t sigma = 0, total = 0, runs = 0, run8 = 0, run32 = 0, header_end = 0;
     uint64_t count01[2] = {0, 0};  // occurrences of symbols 0 and 1 (what the two-hop shortcuts are checked against)
     uint8_t fmt = FMT_EMPTY;
+    uint8_t ckpt = 0;     // 0, or log2(positions per checkpoint) + 1 for a run body with a checkpoint table (layout.h)
     uint32_t units = 0;   // body size in 16-byte units
     int status = GBWT_B200_OK;
 };
 
+// Tuning / test knobs for the checkpoint tables (layout.h): GBWT_B200_CKPT=0 disables them, GBWT_B200_CKPT_MIN_RUNS and
+// GBWT_B200_CKPT_INTERVAL_RUNS override when a body gets one and how many runs lie between two checkpoints.
+struct CheckpointPolicy {
+    uint64_t min_runs = CKPT_MIN_RUNS, interval_runs = CKPT_RUNS_PER_INTERVAL;
+    bool enabled = true;
+    CheckpointPolicy() {
+        if (const char* e = std::getenv("GBWT_B200_CKPT")) enabled = std::atoi(e) != 0;
+        if (const char* e = std::getenv("GBWT_B200_CKPT_MIN_RUNS")) min_runs = static_cast<uint64_t>(std::max(0, std::atoi(e)));
+        if (const char* e = std::getenv("GBWT_B200_CKPT_INTERVAL_RUNS")) interval_runs = static_cast<uint64_t>(std::max(1, std::atoi(e)));
+    }
+};
+
+inline uint64_t run_units_of(uint8_t fmt, uint64_t n) {
+    return fmt == FMT_RUN8 ? (n + 15) / 16 : (fmt == FMT_RUN32 ? (n + 3) / 4 : (n + 1) / 2);
+}
+
 inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // Pass 1: size every candidate format and pick one.
-Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
+Plan plan_record(const uint8_t* bytes, uint64_t len, int policy, const CheckpointPolicy& cp) {
     Plan pl;
     if (len == 0) return pl;  // Record::new: empty slice -> None (src/bwt.rs:342)
     RecordReader rd(bytes, len);
@@ -118,6 +135,21 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy) {
         if (dense <= std::max<uint64_t>(4, 2 * best)) { best = dense; pl.fmt = FMT_DENSE2; }
     }
     best = (best + 1) & ~1ull;  // every body starts on a 32-byte sector boundary (256-bit loads)
+    // Checkpoints for a long run body: one every P positions with about interval_runs runs in between, P a power of two
+    // doubled until the table is no larger than the runs themselves. Runs are split at the checkpoints, at most one
+    // more run each, which the body is sized for.
+    const uint64_t fmt_runs = pl.fmt == FMT_RUN8 ? pl.run8 : (pl.fmt == FMT_RUN32 ? pl.run32 : pl.runs);
+    if (cp.enabled && pl.fmt >= FMT_RUN8 && pl.sigma <= CKPT_MAX_SIGMA && fmt_runs > cp.min_runs && pl.total > 1) {
+        const uint64_t stride_units = (pl.sigma + 3) / 4;
+        uint32_t shift = 1;
+        while (shift < 30 && (uint64_t(1) << shift) * fmt_runs < cp.interval_runs * pl.total) shift++;
+        uint64_t entries = (pl.total - 1) >> shift;
+        while (shift < 30 && entries * stride_units > run_units_of(pl.fmt, fmt_runs + entries)) { shift++; entries = (pl.total - 1) >> shift; }
+        if (entries > 0) {
+            pl.ckpt = static_cast<uint8_t>(shift + 1);
+            best = ((run_units_of(pl.fmt, fmt_runs + entries) + 1) & ~1ull) + ((entries * stride_units + 1) & ~1ull);
+        }
+    }
     if (best > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
     pl.units = static_cast<uint32_t>(best);
     return pl;
@@ -188,44 +220,50 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
         }
         break;
     }
-    case FMT_RUN8: {
-        const uint64_t max8 = std::max<uint64_t>(1, 256 / sigma);
-        uint64_t n = 0;
-        const uint64_t cap = static_cast<uint64_t>(pl.units) * 16;  // what pass 1 sized the body for
-        while (rd.run(value, rl)) {
-            while (rl > 0 && n < cap) {
-                uint64_t piece = std::min(rl, max8);
-                body[n++] = static_cast<uint8_t>(value + sigma * (piece - 1));
-                rl -= piece;
-            }
-        }
-        d.body_len = static_cast<uint32_t>(n);
-        break;
-    }
-    case FMT_RUN32: {
-        uint32_t* out = reinterpret_cast<uint32_t*>(body);
-        uint64_t n = 0;
-        const uint64_t cap = static_cast<uint64_t>(pl.units) * 4;
-        while (rd.run(value, rl)) {
-            while (rl > 0 && n < cap) {
-                uint64_t piece = std::min<uint64_t>(rl, RUN32_MAX_LEN);
-                out[n++] = static_cast<uint32_t>(value) | (static_cast<uint32_t>(piece - 1) << 8);
-                rl -= piece;
-            }
-        }
-        d.body_len = static_cast<uint32_t>(n);
-        break;
-    }
+    case FMT_RUN8:
+    case FMT_RUN32:
     case FMT_RUN64: {
-        uint32_t* out = reinterpret_cast<uint32_t*>(body);
-        uint64_t n = 0;
-        const uint64_t cap = static_cast<uint64_t>(pl.units) * 2;
-        while (n < cap && rd.run(value, rl)) {
-            out[2 * n] = static_cast<uint32_t>(value);
-            out[2 * n + 1] = static_cast<uint32_t>(rl);
-            n++;
+        // The reference's run sequence, re-encoded: runs are split at the format's maximal length and, with a
+        // checkpoint table, at every multiple of P (a rank only depends on the sums of |run ∩ range| per symbol, which
+        // splitting a run does not change).
+        const uint64_t max_len = pl.fmt == FMT_RUN8 ? std::max<uint64_t>(1, 256 / sigma) : (pl.fmt == FMT_RUN32 ? RUN32_MAX_LEN : 0xFFFFFFFFull);
+        const uint64_t per_unit = pl.fmt == FMT_RUN8 ? 16 : (pl.fmt == FMT_RUN32 ? 4 : 2);
+        const uint32_t shift = pl.ckpt ? pl.ckpt - 1u : 0;
+        const uint64_t interval = pl.ckpt ? (uint64_t(1) << shift) : ~0ull;
+        const uint64_t entries = pl.ckpt ? (pl.total - 1) >> shift : 0;
+        const uint64_t stride = (sigma + 3) / 4 * 4;
+        const uint64_t table_units = (entries * stride / 4 + 1) & ~1ull;
+        const uint64_t cap = (static_cast<uint64_t>(pl.units) - table_units) * per_unit;  // runs the body was sized for
+        std::vector<uint32_t> counts(pl.ckpt ? sigma : 0, 0), table(entries * stride, 0);
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(body);
+        uint64_t n = 0, pos = 0, next_checkpoint = interval, written = 0;
+        while (rd.run(value, rl)) {
+            while (rl > 0 && n < cap) {
+                const uint64_t piece = std::min(std::min(rl, max_len), next_checkpoint - pos);
+                if (pl.fmt == FMT_RUN8) body[n] = static_cast<uint8_t>(value + sigma * (piece - 1));
+                else if (pl.fmt == FMT_RUN32) out32[n] = static_cast<uint32_t>(value) | (static_cast<uint32_t>(piece - 1) << 8);
+                else { out32[2 * n] = static_cast<uint32_t>(value); out32[2 * n + 1] = static_cast<uint32_t>(piece); }
+                n++;
+                rl -= piece; pos += piece;
+                if (pl.ckpt) {
+                    counts[value] += static_cast<uint32_t>(piece);
+                    if (pos == next_checkpoint && written < entries) {
+                        uint32_t* e = table.data() + written * stride;
+                        uint32_t upto = 0;
+                        for (uint64_t v = 0; v + 1 < sigma; v++) { upto += counts[v]; e[v] = upto; }
+                        e[sigma - 1] = static_cast<uint32_t>(n);  // the next run starts at this checkpoint
+                        written++;
+                        next_checkpoint += interval;
+                    }
+                }
+            }
         }
         d.body_len = static_cast<uint32_t>(n);
+        if (pl.ckpt && written == entries) {
+            d.flags |= static_cast<uint8_t>(pl.ckpt << DESC_CKPT_SHIFT);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(body) + 4 * ((run_units_of(pl.fmt, n) + 1) & ~1ull);
+            std::memcpy(dst, table.data(), table.size() * sizeof(uint32_t));
+        }
         break;
     }
     default:
@@ -255,10 +293,11 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
     if (const char* e = std::getenv("GBWT_B200_BUILD_THREADS")) threads = std::max(1, std::atoi(e));
     (void)threads;
     std::vector<Plan> plans(R);
+    const CheckpointPolicy checkpoint_policy;
     std::atomic<int> status{GBWT_B200_OK};
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
     for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
-        plans[i] = plan_record(in.bwt + in.record_starts[i], rec_len(i), policy);
+        plans[i] = plan_record(in.bwt + in.record_starts[i], rec_len(i), policy, checkpoint_policy);
         if (plans[i].status != GBWT_B200_OK) status.store(plans[i].status);
     }
     if (status.load() != GBWT_B200_OK) {
@@ -270,6 +309,7 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
         body_at[i + 1] = body_at[i] + plans[i].units;
         edge_at[i + 1] = edge_at[i] + (plans[i].sigma > 2 ? plans[i].sigma : 0);
         out.format_counts[plans[i].fmt]++;
+        if (plans[i].ckpt != 0) out.checkpointed_records++;
         out.total_length += plans[i].total;
     }
     if (body_at[R] > 0xFFFFFFFFull || edge_at[R] > 0xFFFFFFFFull) {

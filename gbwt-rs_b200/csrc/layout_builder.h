@@ -21,6 +21,7 @@ struct HostLayout {
     bool edges_valid = true;
     uint64_t total_length = 0;    // sum of the record lengths (IndexView::walk_limit)
     uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t checkpointed_records = 0;  // run bodies that carry a checkpoint table (layout.h)
 };
 
 // `policy` is GBWT_B200_LAYOUT_AUTO or GBWT_B200_LAYOUT_RUNS. Returns a GBWT_B200_* status.

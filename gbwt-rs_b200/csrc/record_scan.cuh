@@ -61,6 +61,8 @@ struct Desc {
     GBWT_HD uint32_t total_len() const { return a.x; }
     GBWT_HD uint32_t fmt() const { return (a.y >> 16) & 0xFF; }
     GBWT_HD bool inline_edges() const { return ((a.y >> 24) & DESC_INLINE_EDGES) != 0; }
+    // 0 = the run body has no checkpoints, else log2(positions per checkpoint) + 1 (layout.h)
+    GBWT_HD uint32_t checkpoints() const { return (a.y >> (24 + DESC_CKPT_SHIFT)) & DESC_CKPT_MASK; }
     GBWT_HD uint32_t sigma() const { return inline_edges() ? (a.y & 0xFFFF) : a.w; }
     GBWT_HD uint32_t edge_base() const { return a.z; }
     GBWT_HD uint32_t node0() const { return a.z; }
@@ -271,12 +273,122 @@ GBWT_UNROLL
     }
 }
 
+// ---- checkpointed run bodies (layout.h) ---------------------------------------------------------------
+// A long run body carries a table of checkpoints behind its runs: one every P = 2^shift positions, runs split there
+// at load time so that a run starts exactly at the checkpoint. Entry j - 1 (position j P) holds, in `stride` words,
+// C_v = the number of positions before j P with a symbol <= v for v = 0 .. sigma - 2 and, in word sigma - 1, the
+// index of the run that starts at j P. A rank is then one table entry plus a scan of at most one interval's runs
+// instead of a scan from the start of the body (the reference scans from the start: src/bwt.rs:603-613 over
+// RLEIter, src/support.rs:1413-1430).
+struct RunCheckpoint {
+    uint32_t run, offset;   // where the scan starts: run index and the position that run starts at
+    uint32_t count, flip;   // occurrences of the symbol / of the FlipSet symbols before `offset`
+};
+
+GBWT_HD uint32_t run_units(uint32_t fmt, uint32_t n) {
+    return fmt == FMT_RUN8 ? (n + 15u) >> 4 : (fmt == FMT_RUN32 ? (n + 3u) >> 2 : (n + 1u) >> 1);
+}
+
+template <bool BD>
+GBWT_HD RunCheckpoint load_checkpoint(const Unit16* body, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t pos) {
+    RunCheckpoint c;
+    c.run = 0; c.offset = 0; c.count = 0; c.flip = 0;
+    const uint32_t shift = d.checkpoints() - 1u;
+    const uint32_t last = (d.total_len() - 1u) >> shift;  // checkpoints 1 .. last exist
+    uint32_t j = pos >> shift;
+    if (j > last) j = last;
+    if (j == 0) return c;
+    const uint32_t sigma = d.sigma(), stride = (sigma + 3u) & ~3u;
+    const uint32_t* table = reinterpret_cast<const uint32_t*>(body + ((run_units(d.fmt(), d.body_len()) + 1u) & ~1u)) + static_cast<size_t>(j - 1u) * stride;
+    c.offset = j << shift;
+    c.run = GBWT_LDG(table + sigma - 1u);
+    // C_{sigma - 1} is the position itself
+    const uint32_t upto = symbol + 1u < sigma ? GBWT_LDG(table + symbol) : c.offset;
+    const uint32_t below = symbol > 0 ? GBWT_LDG(table + symbol - 1u) : 0u;
+    c.count = upto - below;
+    if (BD) {
+        if (fs.lt > 0) c.flip = fs.lt < sigma ? GBWT_LDG(table + fs.lt - 1u) : c.offset;
+        if (fs.extra < sigma) {
+            const uint32_t e_upto = fs.extra + 1u < sigma ? GBWT_LDG(table + fs.extra) : c.offset;
+            c.flip += e_upto - (fs.extra > 0 ? GBWT_LDG(table + fs.extra - 1u) : 0u);
+        }
+    }
+    return c;
+}
+
+// Adds to c.count / c.flip the occurrences in [c.offset, pos), scanning from run c.run.
+template <bool BD>
+GBWT_HD void scan_runs_to(const Unit16* body, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t pos, RunCheckpoint& c) {
+    const uint32_t n = d.body_len(), fmt = d.fmt();
+    uint32_t off = c.offset;
+    if (fmt == FMT_RUN8) {
+        const uint32_t sigma = d.sigma();
+        const uint32_t magic = d.inline_edges() ? 32769u : d.magic();  // inline edges + runs => sigma == 2
+        for (uint32_t base = c.run & ~15u; base < n && off < pos; base += 16) {
+            const Quad q = load_quad(body + (base >> 4));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 16; j++) {
+                if (base + j >= c.run && base + j < n && off < pos) {
+                    const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                    const uint32_t quot = (b * magic) >> 16, value = b - quot * sigma;
+                    const uint32_t part = pos - off < quot + 1 ? pos - off : quot + 1;
+                    if (value == symbol) c.count += part;
+                    if (BD) { if (fs.has(value)) c.flip += part; }
+                    off += quot + 1;
+                }
+            }
+        }
+    } else if (fmt == FMT_RUN32) {
+        for (uint32_t base = c.run & ~3u; base < n && off < pos; base += 4) {
+            const Quad q = load_quad(body + (base >> 2));
+            const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+GBWT_UNROLL
+            for (uint32_t j = 0; j < 4; j++) {
+                if (base + j >= c.run && base + j < n && off < pos) {
+                    const uint32_t value = words[j] & 0xFF, len = (words[j] >> 8) + 1;
+                    const uint32_t part = pos - off < len ? pos - off : len;
+                    if (value == symbol) c.count += part;
+                    if (BD) { if (fs.has(value)) c.flip += part; }
+                    off += len;
+                }
+            }
+        }
+    } else {  // FMT_RUN64
+        for (uint32_t run = c.run; run < n && off < pos; run++) {
+            const Quad q = load_quad(body + (run >> 1));
+            const uint32_t value = (run & 1) ? q.z : q.x, len = (run & 1) ? q.w : q.y;
+            const uint32_t part = pos - off < len ? pos - off : len;
+            if (value == symbol) c.count += part;
+            if (BD) { if (fs.has(value)) c.flip += part; }
+            off += len;
+        }
+    }
+}
+
+// rank(start), rank(end) and the flipped count of [start, end) on a checkpointed body.
+template <bool BD>
+GBWT_HD void rank_runs_checkpointed(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
+                                    uint32_t end, Ranks& r) {
+    const Unit16* body = ix.bodies + d.body();
+    RunCheckpoint cs = load_checkpoint<BD>(body, d, symbol, fs, start);
+    scan_runs_to<BD>(body, d, symbol, fs, start, cs);
+    r.at_start = r.at_end = cs.count;
+    if (end != start) {
+        RunCheckpoint ce = load_checkpoint<BD>(body, d, symbol, fs, end);
+        scan_runs_to<BD>(body, d, symbol, fs, end, ce);
+        r.at_end = ce.count;
+        if (BD) r.flipped = ce.flip - cs.flip;
+    }
+}
+
 // Scans the runs of a RUN8 / RUN32 / RUN64 body up to `end` (the reference's early exit, src/bwt.rs:610-612).
 // Not inlined on the device: the scan loops would otherwise set the register budget (and the occupancy) of
 // the kernels whose common case is the register-light dense / single-edge step.
 template <bool BD>
 GBWT_HD void rank_runs_inline(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
                               uint32_t end, Ranks& r) {
+    if (d.checkpoints() != 0) { rank_runs_checkpointed<BD>(ix, d, symbol, fs, start, end, r); return; }
     const Unit16* body = ix.bodies + d.body();
     const uint32_t n = d.body_len();
     const uint32_t fmt = d.fmt();
@@ -329,17 +441,27 @@ GBWT_HD uint32_t symbol_at_runs(const IndexView& ix, const Desc& d, uint32_t i) 
     const Unit16* body = ix.bodies + d.body();
     const uint32_t n = d.body_len();
     const uint32_t fmt = d.fmt();
-    uint32_t off = 0, symbol = NO_SYMBOL;
+    uint32_t off = 0, symbol = NO_SYMBOL, first = 0;
+    if (d.checkpoints() != 0 && i < d.total_len()) {
+        // start at the checkpoint before position i (word sigma - 1 of its entry: the run that starts there)
+        const uint32_t shift = d.checkpoints() - 1u, j = i >> shift;
+        if (j > 0) {
+            const uint32_t sigma = d.sigma(), stride = (sigma + 3u) & ~3u;
+            const uint32_t* table = reinterpret_cast<const uint32_t*>(body + ((run_units(fmt, n) + 1u) & ~1u)) + static_cast<size_t>(j - 1u) * stride;
+            first = GBWT_LDG(table + sigma - 1u);
+            off = j << shift;
+        }
+    }
     if (fmt == FMT_RUN8) {
         const uint32_t sigma = d.sigma();
         const uint32_t magic = d.inline_edges() ? 32769u : d.magic();  // inline edges + runs => sigma == 2
-        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 16) {
+        for (uint32_t base = first & ~15u; base < n && symbol == NO_SYMBOL; base += 16) {
             const Quad q = load_quad(body + (base >> 4));
             const uint32_t words[4] = {q.x, q.y, q.z, q.w};
             const uint32_t nb = n - base < 16 ? n - base : 16;
 GBWT_UNROLL
             for (uint32_t j = 0; j < 16; j++) {
-                if (j < nb) {
+                if (j < nb && base + j >= first) {
                     const uint32_t b = (words[j >> 2] >> (8 * (j & 3))) & 0xFF;
                     const uint32_t quot = (b * magic) >> 16;
                     if (symbol == NO_SYMBOL && i - off < quot + 1) symbol = b - quot * sigma;
@@ -348,13 +470,13 @@ GBWT_UNROLL
             }
         }
     } else if (fmt == FMT_RUN32) {
-        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 4) {
+        for (uint32_t base = first & ~3u; base < n && symbol == NO_SYMBOL; base += 4) {
             const Quad q = load_quad(body + (base >> 2));
             const uint32_t words[4] = {q.x, q.y, q.z, q.w};
             const uint32_t nb = n - base < 4 ? n - base : 4;
 GBWT_UNROLL
             for (uint32_t j = 0; j < 4; j++) {
-                if (j < nb) {
+                if (j < nb && base + j >= first) {
                     const uint32_t len = (words[j] >> 8) + 1;
                     if (symbol == NO_SYMBOL && i - off < len) symbol = words[j] & 0xFF;
                     off += len;
@@ -362,14 +484,11 @@ GBWT_UNROLL
             }
         }
     } else {
-        for (uint32_t base = 0; base < n && symbol == NO_SYMBOL; base += 2) {
-            const Quad q = load_quad(body + (base >> 1));
-            if (i - off < q.y) symbol = q.x;
-            off += q.y;
-            if (symbol == NO_SYMBOL && base + 1 < n) {
-                if (i - off < q.w) symbol = q.z;
-                off += q.w;
-            }
+        for (uint32_t run = first; run < n && symbol == NO_SYMBOL; run++) {
+            const Quad q = load_quad(body + (run >> 1));
+            const uint32_t value = (run & 1) ? q.z : q.x, len = (run & 1) ? q.w : q.y;
+            if (i - off < len) symbol = value;
+            off += len;
         }
     }
     return symbol;

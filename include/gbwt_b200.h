@@ -138,6 +138,10 @@ GBWT_B200_API int gbwt_b200_has_graph(const gbwt_b200_index* index);            
 GBWT_B200_API uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* index); /* Graph::sequences, src/graph.rs:112-114 */
 GBWT_B200_API uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* index);     /* HBM held by the node labels */
 GBWT_B200_API uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* index);      /* HBM held by the path-walk shortcuts */
+/* Records whose run-length body carries a checkpoint table: a rank on them reads one table entry and scans one interval
+ * of runs, where RLEIter (src/support.rs:1413-1430, used by Record::follow / lf, src/bwt.rs:480-496, 595-656) scans from
+ * the start of the record. */
+GBWT_B200_API uint64_t gbwt_b200_run_checkpoint_records(const gbwt_b200_index* index);
 /* Bytes of HBM held by the index (including the path-walk shortcuts and node labels, reported separately
  * below), and a breakdown: [0] descriptors, [1] bodies, [2] edge lists, [3] endmarker; [4..9] number of records per body format (empty, single-edge, dense, run8, run32, run64). */
 GBWT_B200_API uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* index, uint64_t breakdown[10]);

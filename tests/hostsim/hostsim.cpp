@@ -99,6 +99,7 @@ const uint8_t* hs_label_bytes(const HostSim* h) { return h->parsed.label_bytes.d
 
 void hs_format_counts(const HostSim* h, uint64_t* out) { std::memcpy(out, h->layout.format_counts, sizeof(h->layout.format_counts)); }
 uint64_t hs_body_bytes(const HostSim* h) { return h->layout.bodies.size() * 8; }
+uint64_t hs_checkpointed_records(const HostSim* h) { return h->layout.checkpointed_records; }
 int hs_record_format(const HostSim* h, uint64_t rec) { return h->layout.desc[rec].fmt; }
 
 void hs_find(const HostSim* h, const uint64_t* nodes, size_t n, gbwt_b200_state* out) {

@@ -60,6 +60,8 @@ def lib():
         L.hs_format_counts.argtypes = [p, p]
         L.hs_body_bytes.restype = u64
         L.hs_body_bytes.argtypes = [p]
+        L.hs_checkpointed_records.restype = u64
+        L.hs_checkpointed_records.argtypes = [p]
         L.hs_record_format.argtypes = [p, u64]
         L.hs_find.argtypes = [p, p, C.c_size_t, p]
         L.hs_extend.argtypes = [p, p, p, C.c_size_t, p]
@@ -143,6 +145,10 @@ class HostSim:
         data = np.ctypeslib.as_array(C.cast(self._L.hs_label_bytes(self._h), C.POINTER(C.c_uint8)), (total,)).copy() \
             if total else np.zeros(0, np.uint8)
         return starts, data
+
+    def checkpointed_records(self):
+        """Run bodies that carry a checkpoint table (layout.h)."""
+        return int(self._L.hs_checkpointed_records(self._h))
 
     def format_counts(self):
         out = np.zeros(6, dtype=np.uint64)
