@@ -105,7 +105,7 @@ def _load_library() -> C.CDLL:
         "gbwt_b200_sequence_lengths_device": (i, [p, p, sz, p, p]),
         "gbwt_b200_extract_device": (i, [p, p, sz, p, p, p, p]),
         "gbwt_b200_index_attach_graph": (i, [p, u64, p, p]),
-        "gbwt_b200_has_graph": (i, [p]), "gbwt_b200_graph_sequences": (u64, [p]), "gbwt_b200_graph_bytes": (u64, [p]), "gbwt_b200_skip_bytes": (u64, [p]), "gbwt_b200_run_checkpoint_records": (u64, [p]),
+        "gbwt_b200_has_graph": (i, [p]), "gbwt_b200_graph_sequences": (u64, [p]), "gbwt_b200_graph_bytes": (u64, [p]), "gbwt_b200_skip_bytes": (u64, [p]), "gbwt_b200_run_checkpoint_records": (u64, [p]), "gbwt_b200_dense4_records": (u64, [p]),
         "gbwt_b200_node_sequence_lengths": (i, [p, p, sz, p]),
         "gbwt_b200_node_sequences": (i, [p, p, sz, p, p, p]),
         "gbwt_b200_dna_lengths": (i, [p, p, sz, p]),
@@ -334,6 +334,7 @@ class GBWT:
         out = {k: int(v) for k, v in zip(keys, b)}
         out["skips"] = int(_lib.gbwt_b200_skip_bytes(self._h))
         out["records_run_checkpointed"] = int(_lib.gbwt_b200_run_checkpoint_records(self._h))
+        out["records_dense4"] = int(_lib.gbwt_b200_dense4_records(self._h))
         out["labels"] = int(_lib.gbwt_b200_graph_bytes(self._h))
         out["total"] = int(total)
         return out

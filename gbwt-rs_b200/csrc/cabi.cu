@@ -58,7 +58,7 @@ struct gbwt_b200_index {
     GraphView graph{};
     uint64_t graph_bytes = 0;
     uint64_t bytes[4] = {0, 0, 0, 0};
-    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t checkpointed_records = 0;
     Carried carried;  // tags, DA samples, metadata, Graph section: host-side, written back by serialize
 };
@@ -133,7 +133,8 @@ constexpr size_t LOCALITY_MIN_QUERIES = size_t(1) << 16;  // below this the sort
 constexpr uint64_t LOCALITY_MIN_INDEX_BYTES = uint64_t(48) << 20;  // an index that lives in L2 gains nothing
 
 bool has_run_records(const gbwt_b200_index* ix) {
-    return ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64] != 0;
+    // (DENSE4 bodies go through the same out-of-line step as the run-length formats)
+    return ix->format_counts[FMT_RUN8] + ix->format_counts[FMT_RUN32] + ix->format_counts[FMT_RUN64] + ix->format_counts[FMT_DENSE4] != 0;
 }
 
 // The lean find/extend loop handles single-edge and dense records itself and calls out of line for the rest: it is
@@ -875,7 +876,9 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
         const uint64_t runs = layout.format_counts[FMT_RUN8] + layout.format_counts[FMT_RUN32] + layout.format_counts[FMT_RUN64];
         const bool mostly_plain = runs * 8 <= layout.format_counts[FMT_DENSE2] + layout.format_counts[FMT_SINGLE];
         const bool local = layout.edges_local * 10 >= layout.edges_total * 9;
-        ix->window_ok = plan_windows(v, layout.bodies.size() / 2, ix->window);
+        const double edge_span = layout.edges_local != 0 ? static_cast<double>(layout.edges_local_span) / static_cast<double>(layout.edges_local) : 3.0;
+        const bool wide = layout.format_counts[FMT_DENSE4] + layout.format_counts[FMT_RUN8] != 0;
+        ix->window_ok = plan_windows(v, layout.bodies.size() / 2, edge_span, wide, ix->window);
         ix->window_suits = mostly_plain && local;
     }
     if (parsed.has_graph) {
@@ -1262,6 +1265,7 @@ uint64_t gbwt_b200_graph_sequences(const gbwt_b200_index* ix) { return ix && ix-
 uint64_t gbwt_b200_graph_bytes(const gbwt_b200_index* ix) { return ix ? ix->graph_bytes : 0; }
 uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* ix) { return ix ? ix->skip_bytes : 0; }
 uint64_t gbwt_b200_run_checkpoint_records(const gbwt_b200_index* ix) { return ix ? ix->checkpointed_records : 0; }
+uint64_t gbwt_b200_dense4_records(const gbwt_b200_index* ix) { return ix ? ix->format_counts[FMT_DENSE4] : 0; }
 
 void gbwt_b200_checkpoint_info(const gbwt_b200_index* ix, uint64_t info[6]) {
     if (ix == nullptr || info == nullptr) return;
@@ -1296,7 +1300,8 @@ uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* ix, uint64_t breakdown[10
     if (ix == nullptr) return 0;
     if (breakdown != nullptr) {
         for (int i = 0; i < 4; i++) breakdown[i] = ix->bytes[i];
-        for (int i = 0; i < FMT_COUNT; i++) breakdown[4 + i] = ix->format_counts[i];
+        for (int i = 0; i < 6; i++) breakdown[4 + i] = ix->format_counts[i];
+        breakdown[4 + FMT_DENSE2] += ix->format_counts[FMT_DENSE4];  // both dense formats in one slot (gbwt_b200_dense4_records tells them apart)
     }
     return ix->bytes[0] + ix->bytes[1] + ix->bytes[2] + ix->bytes[3] + ix->skip_bytes + ix->graph_bytes + ix->ckpt_bytes;
 }

@@ -49,6 +49,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 
 // ---- pattern rows -----------------------------------------------------------------------------------------------------
@@ -99,43 +102,49 @@ __device__ __forceinline__ void load_nodes(const uint32_t* p, uint32_t (&v)[8]) 
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
 
-// Fills the warp's tile with nodes [seg, seg + n_seg) of its 32 rows. `row` is this lane's own row (nullptr: no query).
-// Sector loads when every row segment starts on a 32-byte boundary and n_seg is a whole number of sectors, else node
-// by node.
+// Fills the warp's tile with nodes [seg, seg + n_seg) of its 32 rows. `q` is this lane's own query (NO_QUERY: none);
+// row r is the row of lane r's query. Sector loads when every row segment starts on a 32-byte boundary and n_seg is a
+// whole number of sectors, else node by node.
+constexpr uint32_t NO_QUERY = 0xFFFFFFFFu;
+
 template <class T>
-__device__ __forceinline__ void load_tile(const T* row, uint32_t seg, uint32_t n_seg, bool sectors, uint32_t tile, uint32_t origin,
-                                          uint32_t count, uint32_t lane) {
+__device__ __forceinline__ void load_tile(const T* __restrict__ patterns, uint32_t q, uint32_t k, uint32_t seg, uint32_t n_seg, bool sectors,
+                                          uint32_t tile, uint32_t origin, uint32_t count, uint32_t lane) {
     constexpr uint32_t PER_SECTOR = 32u / sizeof(T);          // nodes per 32-byte sector: 4 or 8
     constexpr uint32_t MAX_LANES_PER_ROW = SEGMENT / PER_SECTOR;  // 4 or 2
-    const unsigned long long mine = reinterpret_cast<unsigned long long>(row);
     if (sectors) {
         const uint32_t per_row = n_seg / PER_SECTOR;  // sectors per row segment: 1 .. MAX_LANES_PER_ROW (whole lanes only when a power of two)
         // lanes_per_row = MAX_LANES_PER_ROW always (a shorter segment leaves the extra lanes idle: only the last round of a pattern)
         const uint32_t sub = lane % MAX_LANES_PER_ROW, first = lane / MAX_LANES_PER_ROW;
         constexpr uint32_t ROWS_PER_LOAD = 32u / MAX_LANES_PER_ROW;  // 8 or 16
-        T v[32u / ROWS_PER_LOAD][PER_SECTOR];
-        bool have[32u / ROWS_PER_LOAD];
+        constexpr uint32_t LOADS = 32u / ROWS_PER_LOAD;  // 4 or 2 load instructions per segment
+        // (64-bit nodes: two loads = 16 registers in flight at a time; all four at once spill under the 64-register budget)
+        constexpr uint32_t GROUP = 2;
+        const uint32_t at = tile + (sub * PER_SECTOR * TILE_PITCH + first) * 2u;
 #pragma unroll
-        for (uint32_t j = 0; j < 32u / ROWS_PER_LOAD; j++) {
-            const uint32_t r = j * ROWS_PER_LOAD + first;
-            const T* p = reinterpret_cast<const T*>(__shfl_sync(0xFFFFFFFFu, mine, r));
-            have[j] = p != nullptr && sub < per_row;
-            if (have[j]) load_nodes(p + seg + sub * PER_SECTOR, v[j]);
-        }
+        for (uint32_t g = 0; g < LOADS; g += GROUP) {
+            T v[GROUP][PER_SECTOR];
+            bool have[GROUP];
 #pragma unroll
-        for (uint32_t j = 0; j < 32u / ROWS_PER_LOAD; j++) {
-            const uint32_t r = j * ROWS_PER_LOAD + first;
-            if (have[j]) {
+            for (uint32_t j = 0; j < GROUP; j++) {
+                const uint32_t owner = __shfl_sync(0xFFFFFFFFu, q, (g + j) * ROWS_PER_LOAD + first);
+                have[j] = owner != NO_QUERY && sub < per_row;
+                if (have[j]) load_nodes(patterns + static_cast<size_t>(owner) * k + seg + sub * PER_SECTOR, v[j]);
+            }
 #pragma unroll
-                for (uint32_t t = 0; t < PER_SECTOR; t++)
-                    sts16(tile + ((sub * PER_SECTOR + t) * TILE_PITCH + r) * 2u, pattern_index(v[j][t], origin, count));
+            for (uint32_t j = 0; j < GROUP; j++) {
+                if (have[j]) {
+#pragma unroll
+                    for (uint32_t t = 0; t < PER_SECTOR; t++)
+                        sts16(at + (t * TILE_PITCH + (g + j) * ROWS_PER_LOAD) * 2u, pattern_index(v[j][t], origin, count));
+                }
             }
         }
     } else {
         for (uint32_t e = lane; e < 32u * n_seg; e += 32u) {
             const uint32_t r = e / n_seg, t = e - r * n_seg;
-            const T* p = reinterpret_cast<const T*>(__shfl_sync(0xFFFFFFFFu, mine, r));
-            if (p != nullptr) sts16(tile + (t * TILE_PITCH + r) * 2u, pattern_index(__ldg(p + seg + t), origin, count));
+            const uint32_t owner = __shfl_sync(0xFFFFFFFFu, q, r);
+            if (owner != NO_QUERY) sts16(tile + (t * TILE_PITCH + r) * 2u, pattern_index(__ldg(patterns + static_cast<size_t>(owner) * k + seg + t), origin, count));
         }
     }
 }
@@ -165,15 +174,109 @@ __device__ __forceinline__ uint64_t first_node(const uint32_t* patterns, size_t 
 //                  (layout.h, IndexView::skips). One 16-byte load per step.
 //   offs[r]   4 B  {offset0 | offset1 << 16}: only read when a step cannot take the shortcut
 //   ranks[]   4 B  {ones before | 16 bits << 16}: rank at position p of a record is ONE 4-byte load at kind + p / 16
-constexpr uint32_t KIND_SINGLE = 0xFFFFu, KIND_EMPTY = 0xFFFEu, KIND_DEFER = 0xFFFDu;  // anything below: dense
+//   wide records (up to four edges with a DENSE4 or byte-per-run body, or two edges with a byte-per-run body: what a
+//   multi-allelic site or a record with few runs looks like) take the slower path of wide_follow():
+//   rec[r]         {aux index | sigma << 16, total_len | KIND_WIDE << 16, body slot | body_len << 16, format | checkpoints << 8}
+//   aux[a]   32 B  {target0 | target1 << 16, target2 | target3 << 16, shortcut0 .. shortcut3, offset0 | offset1 << 16,
+//                  offset2 | offset3 << 16}: handed out from a small pool while the records are decoded
+//   body slots: every 32-byte block of the staged body range owns 48 bytes of `ranks`; a DENSE2 block fills them with its
+//   twelve rank entries, a DENSE4 block with two 16-byte entries {64 bits of codes, count1 | count2 << 16, count3} of 32
+//   positions each, a run-length body (with its checkpoint table) is copied as it is, 32 bytes per slot. kinds[] says
+//   which (one byte per block, written by the record's thread before the blocks are decoded).
+constexpr uint32_t KIND_SINGLE = 0xFFFFu, KIND_EMPTY = 0xFFFEu, KIND_DEFER = 0xFFFDu, KIND_WIDE = 0xFFFCu;  // anything below: dense
 constexpr uint32_t RECORD_BYTES = 20;  // rec + offs
+constexpr uint32_t AUX_BYTES = 32;
+constexpr uint32_t NO_SHORTCUT = 0xFFFFu;  // (its node half is NODE_OUTSIDE: never equal to a pattern node that passed the x2 test)
+enum : uint32_t { BLOCK_UNUSED = 0, BLOCK_DENSE2 = 1, BLOCK_DENSE4 = 2, BLOCK_RAW = 3 };
 
 struct Staged {
     uint32_t rec, offs, ranks;  // shared-space addresses
     uint32_t lo, count;         // staged records [lo, lo + count)
+    uint32_t aux, kinds;        // wide records: edge tables, and what each body block holds
 };
 
-enum : uint32_t { QUERY_ACTIVE = 0, QUERY_FOUND = 1, QUERY_NONE = 2, QUERY_DEFER = 3 };
+// Shared address of 16-byte unit u of a body copied as it is into the slots from `slot` on.
+__device__ __forceinline__ uint32_t raw_unit(uint32_t ranks, uint32_t slot, uint32_t u) { return ranks + 48u * (slot + (u >> 1)) + 16u * (u & 1u); }
+
+// Occurrences of `symbol` in [0, pos) of a byte-per-run body (layout.h: FMT_RUN8, sigma 2 .. 4) held in the slots from
+// `slot` on, starting at the checkpoint before pos when the body has a table (record_scan.cuh: load_checkpoint /
+// scan_runs_to, here on the shared-memory copy; a table entry of a record with at most four edges is one 16-byte unit).
+__device__ __forceinline__ uint32_t staged_rank_runs8(uint32_t ranks, uint32_t slot, uint32_t n, uint32_t sigma, uint32_t checkpoints,
+                                                      uint32_t total, uint32_t symbol, uint32_t pos) {
+    uint32_t run = 0, off = 0, count = 0;
+    if (checkpoints != 0) {
+        const uint32_t shift = checkpoints - 1u, last = (total - 1u) >> shift;
+        uint32_t j = pos >> shift;
+        if (j > last) j = last;
+        if (j != 0) {
+            const uint4 e = lds128(raw_unit(ranks, slot, ((((n + 15u) >> 4) + 1u) & ~1u) + j - 1u));
+            off = j << shift;
+            run = sigma == 2 ? e.y : (sigma == 3 ? e.z : e.w);
+            const uint32_t upto = symbol + 1u < sigma ? (symbol == 0 ? e.x : (symbol == 1 ? e.y : e.z)) : off;
+            const uint32_t below = symbol == 0 ? 0u : (symbol == 1 ? e.x : (symbol == 2 ? e.y : e.z));
+            count = upto - below;
+        }
+    }
+    const uint32_t magic = sigma == 2 ? 32769u : (sigma == 3 ? 21846u : 16385u);  // div_magic(sigma)
+    for (uint32_t base = run & ~15u; base < n && off < pos; base += 16) {
+        const uint4 q = lds128(raw_unit(ranks, slot, base >> 4));
+        const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+            if (base + j >= run && base + j < n && off < pos) {
+                const uint32_t byte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                const uint32_t quot = (byte * magic) >> 16, len = quot + 1u;
+                if (byte - quot * sigma == symbol) count += pos - off < len ? pos - off : len;
+                off += len;
+            }
+        }
+    }
+    return count;
+}
+
+// Occurrences of `symbol` in [0, pos) of a DENSE4 body held as 16-byte entries of 32 positions (two per slot).
+__device__ __forceinline__ uint32_t staged_rank_dense4(uint32_t ranks, uint32_t slot, uint32_t blocks, uint32_t symbol, uint32_t pos) {
+    uint32_t half = pos >> 5;
+    if (half >= 2u * blocks) half = 2u * blocks - 1u;  // pos == total_len on a block boundary
+    const uint32_t r = pos - 32u * half;               // 0 .. 32 fields of this entry
+    const uint4 e = lds128(ranks + 48u * (slot + (half >> 1)) + 16u * (half & 1u));
+    const uint32_t c1 = e.z & 0xFFFFu, c2 = e.z >> 16, c3 = e.w;
+    const uint32_t before = symbol == 0 ? 32u * half - c1 - c2 - c3 : (symbol == 1 ? c1 : (symbol == 2 ? c2 : c3));
+    const unsigned long long codes = (static_cast<unsigned long long>(e.y) << 32) | e.x;
+    const unsigned long long y = codes ^ (symbol * 0x5555555555555555ull);
+    unsigned long long t = ~(y | (y >> 1)) & 0x5555555555555555ull;
+    if (r < 32u) t &= (1ull << (2u * r)) - 1ull;
+    return before + static_cast<uint32_t>(__popcll(t));
+}
+
+// Record::follow on a wide record (src/bwt.rs:595-616): {rank(s), rank(e), shortcut, shared address of the edge offset}
+// for the edge to window index x1; rank(s) == rank(e) == 0 when x1 is not a successor. Out of line: it is the rare case,
+// and inlined it would set the register budget of the whole search loop.
+__device__ __noinline__ uint4 wide_follow(uint32_t ranks, uint32_t aux, uint32_t h_z, uint32_t h_w, uint32_t sigma, uint32_t total,
+                                          uint32_t x1, uint32_t s, uint32_t e) {
+    const uint4 a0 = lds128(aux), a1 = lds128(aux + 16u);
+    uint32_t b = 4;
+    if (x1 == (a0.x & 0xFFFFu)) b = 0;
+    else if (x1 == (a0.x >> 16)) b = 1;
+    else if (x1 == (a0.y & 0xFFFFu)) b = 2;
+    else if (x1 == (a0.y >> 16)) b = 3;
+    uint4 out;
+    out.x = 0; out.y = 0; out.z = NO_SHORTCUT; out.w = aux + 24u;
+    if (b >= sigma) return out;
+    const uint32_t slot = h_z & 0xFFFFu, n = h_z >> 16, fmt = h_w & 0xFFu, checkpoints = (h_w >> 8) & 0xFFu;
+    if (fmt == FMT_DENSE4) {
+        out.x = staged_rank_dense4(ranks, slot, n, b, s);
+        out.y = staged_rank_dense4(ranks, slot, n, b, e);
+    } else {
+        out.x = staged_rank_runs8(ranks, slot, n, sigma, checkpoints, total, b, s);
+        out.y = staged_rank_runs8(ranks, slot, n, sigma, checkpoints, total, b, e);
+    }
+    out.z = b == 0 ? a0.z : (b == 1 ? a0.w : (b == 2 ? a1.x : a1.y));
+    out.w = aux + 24u + 2u * b;
+    return out;
+}
+
+enum : uint32_t { QUERY_ACTIVE = 0, QUERY_FOUND = 1, QUERY_NONE = 2, QUERY_DEFER = 3, QUERY_WIDE = 4 };
 
 // The state of one query between rounds.
 struct WindowQuery {
@@ -198,103 +301,221 @@ __device__ __forceinline__ void window_find(const Staged& st, uint32_t x, uint32
 // Extends an active query through the pattern nodes [q.i, seg + n_seg) that the warp's tile holds (tile line t = node
 // seg + t of every row, the line after the last node reads NODE_OUTSIDE; `slot` = this lane's column). QUERY_FOUND:
 // (idx, start, end) is the reference's SearchState; QUERY_NONE: the reference returns None; QUERY_DEFER: the window
-// could not decide and the general kernel redoes the query from the start. The loop has ONE exit (every failure
+// could not decide and the general kernel redoes the query from the start. The inner loop has ONE exit (every failure
 // breaks out with its status), so the lanes of a warp reconverge after every step instead of carrying a stack of
 // divergent returns. Per step: the two pattern nodes, one 16-byte record entry, one or two rank entries.
+// A wide record ends the inner loop as well: the lanes that met one take that step together (wide_follow, out of
+// line) once every lane has left the loop, and go back in -- the common records never pay for the rare ones, and the
+// rare steps of different lanes run side by side instead of one after the other.
+template <bool WIDE>
 __device__ __forceinline__ void window_extend(const Staged& st, uint32_t slot, uint32_t seg, uint32_t n_seg, uint32_t k, WindowQuery& q) {
     uint32_t idx = q.idx, start = q.start, end = q.end, status = QUERY_ACTIVE;
     uint32_t pat = slot + (q.i - seg) * TILE_LINE;
     const uint32_t pat_end = slot + n_seg * TILE_LINE;
     uint4 h = lds128(st.rec + 16u * idx);
-    while (pat < pat_end) {
-        const uint32_t x1 = lds16(pat), x2 = lds16(pat + TILE_LINE);
-        const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
-        const uint32_t s = start < total ? start : total, e = end < total ? end : total;
-        if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }
-        if (s >= e) { status = QUERY_NONE; break; }  // Record::follow on an empty range
-        const uint32_t b = x1 == (h.x >> 16) ? 1u : 0u;
-        uint32_t rs = s, re = e;
-        if (kind < KIND_DEFER) {
-            // dense record: rank1(s), and rank1(e) = ones up to and including position e - 1
-            if (x1 != (h.x & 0xFFFFu) && b == 0) { status = QUERY_NONE; break; }
-            const uint32_t last = e - 1u;
-            const uint32_t ws = lds32(st.ranks + 4u * (kind + (s >> 4))), we = lds32(st.ranks + 4u * (kind + (last >> 4)));
-            const uint32_t ones_s = (ws & 0xFFFFu) + static_cast<uint32_t>(__popc((ws >> 16) & ~(0xFFFFFFFFu << (s & 15u))));
-            const uint32_t ones_e = (we & 0xFFFFu) + static_cast<uint32_t>(__popc((we >> 16) & ~(0xFFFFFFFEu << (last & 15u))));
-            rs = b ? ones_s : s - ones_s;
-            re = b ? ones_e : e - ones_e;
-            if (rs >= re) { status = QUERY_NONE; break; }
-        } else if (kind == KIND_SINGLE) {
-            if (x1 != (h.x & 0xFFFFu)) { status = QUERY_NONE; break; }
-        } else {
-            status = kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;  // BWT::record() is None / a record the window does not decode
-            break;
+    for (;;) {
+        while (pat < pat_end) {
+            const uint32_t x1 = lds16(pat), x2 = lds16(pat + TILE_LINE);
+            const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
+            const uint32_t s = start < total ? start : total, e = end < total ? end : total;
+            if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }
+            if (s >= e) { status = QUERY_NONE; break; }  // Record::follow on an empty range
+            const uint32_t b = x1 == (h.x >> 16) ? 1u : 0u;
+            uint32_t rs = s, re = e;
+            if (kind < KIND_WIDE) {
+                // dense record: rank1(s), and rank1(e) = ones up to and including position e - 1
+                if (x1 != (h.x & 0xFFFFu) && b == 0) { status = QUERY_NONE; break; }
+                const uint32_t last = e - 1u;
+                const uint32_t ws = lds32(st.ranks + 4u * (kind + (s >> 4))), we = lds32(st.ranks + 4u * (kind + (last >> 4)));
+                const uint32_t ones_s = (ws & 0xFFFFu) + static_cast<uint32_t>(__popc((ws >> 16) & ~(0xFFFFFFFFu << (s & 15u))));
+                const uint32_t ones_e = (we & 0xFFFFu) + static_cast<uint32_t>(__popc((we >> 16) & ~(0xFFFFFFFEu << (last & 15u))));
+                rs = b ? ones_s : s - ones_s;
+                re = b ? ones_e : e - ones_e;
+                if (rs >= re) { status = QUERY_NONE; break; }
+            } else if (kind == KIND_SINGLE) {
+                if (x1 != (h.x & 0xFFFFu)) { status = QUERY_NONE; break; }
+            } else {
+                // a wide record (below), BWT::record() is None, or a record the window does not decode
+                status = WIDE && kind == KIND_WIDE ? QUERY_WIDE : (kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER);
+                break;
+            }
+            // two hops at once when the successor is a single-edge record leading to the pattern node after x1
+            const uint32_t hop = b ? h.w : h.z;
+            uint32_t offset;
+            if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
+                offset = hop >> 16; idx = x2; pat += 2u * TILE_LINE;
+            } else {
+                offset = lds16(st.offs + 4u * idx + 2u * b); idx = x1; pat += TILE_LINE;
+            }
+            start = offset + rs; end = offset + re;
+            if (pat >= pat_end) break;
+            h = lds128(st.rec + 16u * idx);
         }
-        // two hops at once when the successor is a single-edge record leading to the pattern node after x1
-        const uint32_t hop = b ? h.w : h.z;
-        uint32_t offset;
-        if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
-            offset = hop >> 16; idx = x2; pat += 2u * TILE_LINE;
-        } else {
-            offset = lds16(st.offs + 4u * idx + 2u * b); idx = x1; pat += TILE_LINE;
+        if (!WIDE || status != QUERY_WIDE) break;
+        // the same step on a wide record (the tests on x1 and on the range have passed)
+        {
+            const uint32_t x1 = lds16(pat), x2 = lds16(pat + TILE_LINE);
+            const uint32_t total = h.y & 0xFFFFu;
+            const uint32_t s = start < total ? start : total, e = end < total ? end : total;
+            const uint4 f = wide_follow(st.ranks, st.aux + AUX_BYTES * (h.x & 0xFFFFu), h.z, h.w, h.x >> 16, total, x1, s, e);
+            if (f.x >= f.y) { status = QUERY_NONE; break; }
+            uint32_t offset;
+            if (x2 == (f.z & 0xFFFFu) && x2 != NODE_OUTSIDE) {
+                offset = f.z >> 16; idx = x2; pat += 2u * TILE_LINE;
+            } else {
+                offset = lds16(f.w); idx = x1; pat += TILE_LINE;
+            }
+            start = offset + f.x; end = offset + f.y;
+            status = QUERY_ACTIVE;
+            if (pat >= pat_end) break;
+            h = lds128(st.rec + 16u * idx);
         }
-        start = offset + rs; end = offset + re;
-        if (pat >= pat_end) break;
-        h = lds128(st.rec + 16u * idx);
     }
     q.idx = idx; q.start = start; q.end = end; q.i = seg + (pat - slot) / TILE_LINE;
     q.status = status == QUERY_ACTIVE && q.i >= k ? QUERY_FOUND : status;
 }
 
-// One record of the window, from its descriptor and shortcuts to its table entries.
-__device__ __forceinline__ void stage_record(const Staged& st, uint32_t r, const Desc& d, const Quad& skip, uint32_t origin, uint32_t body_lo,
-                                             uint32_t body_units) {
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t x) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// One record of the window, from its descriptor and shortcuts to its table entries. `aux_counter` = shared address of
+// the pool counter, aux_cap = entries in the pool.
+template <bool WIDE>
+__device__ __forceinline__ void stage_record(const Staged& st, const IndexView& ix, uint32_t r, const Desc& d, const Quad& skip, uint32_t origin,
+                                             uint32_t body_lo, uint32_t body_units, uint32_t* aux_counter, uint32_t aux_cap) {
     const uint32_t fmt = d.fmt();
-    uint32_t kind = KIND_DEFER, target0 = NODE_OUTSIDE, target1 = NODE_OUTSIDE, total = 0, offset0 = 0, offset1 = 0;
+    uint32_t kind = KIND_DEFER, x = NODE_OUTSIDE | (NODE_OUTSIDE << 16), total = 0, offsets = 0;
+    uint32_t z = NO_SHORTCUT, w = NO_SHORTCUT;  // inline records: the two-hop shortcuts of the two edges
+    const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
     if (fmt == FMT_EMPTY) kind = KIND_EMPTY;
     else if (d.total_len() < 0xFFFFu) {
         total = d.total_len();
+        const uint32_t sigma = d.sigma();
         if (fmt == FMT_SINGLE && d.offset0() <= 0xFFFFu) {
-            kind = KIND_SINGLE; target0 = window_index(d.node0(), origin, st.count); offset0 = d.offset0();
+            kind = KIND_SINGLE; x = window_index(d.node0(), origin, st.count) | (NODE_OUTSIDE << 16); offsets = d.offset0();
         } else if (fmt == FMT_DENSE2 && d.offset0() <= 0xFFFFu && d.offset1() <= 0xFFFFu) {
-            const uint32_t unit0 = d.body() - body_lo;  // bodies are 32-byte aligned and lie in record order
-            if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units && (unit0 / 2u) * 12u < KIND_DEFER) {
+            if (d.body() >= body_lo && unit0 + 2u * d.body_len() <= body_units && (unit0 / 2u) * 12u < KIND_WIDE) {
                 kind = (unit0 / 2u) * 12u;
-                target0 = window_index(d.node0(), origin, st.count); target1 = window_index(d.node1(), origin, st.count);
-                offset0 = d.offset0(); offset1 = d.offset1();
+                x = window_index(d.node0(), origin, st.count) | (window_index(d.node1(), origin, st.count) << 16);
+                offsets = d.offset0() | (d.offset1() << 16);
+                if (WIDE) { for (uint32_t j = 0; j < d.body_len(); j++) sts8(st.kinds + unit0 / 2u + j, BLOCK_DENSE2); }
+            }
+        } else if (WIDE && (fmt == FMT_DENSE4 || fmt == FMT_RUN8) && sigma >= 2 && sigma <= 4 && d.body_len() <= 0xFFFFu) {
+            // a wide record: its whole body (runs and checkpoint table) has to be staged, and the pool must have an entry left
+            uint32_t units = 2u * d.body_len();
+            if (fmt == FMT_RUN8) {
+                units = (((d.body_len() + 15u) >> 4) + 1u) & ~1u;
+                if (d.checkpoints() != 0) units += ((((total - 1u) >> (d.checkpoints() - 1u)) + 1u) & ~1u);  // one unit per entry (sigma <= 4)
+            }
+            uint32_t targets[4] = {0, 0, 0, 0}, edge_offsets[4] = {0, 0, 0, 0};
+            bool fits = d.body() >= body_lo && unit0 + units <= body_units;
+            if (fits) {
+                if (d.inline_edges()) {
+                    targets[0] = d.node0(); edge_offsets[0] = d.offset0(); targets[1] = d.node1(); edge_offsets[1] = d.offset1();
+                } else {
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; e++) {
+                        if (e < sigma) {
+                            targets[e] = __ldg(&ix.edges[d.edge_base() + e].node);
+                            edge_offsets[e] = __ldg(&ix.edges[d.edge_base() + e].offset);
+                        }
+                    }
+                }
+                fits = fits && (edge_offsets[0] | edge_offsets[1] | edge_offsets[2] | edge_offsets[3]) <= 0xFFFFu;
+            }
+            uint32_t a = aux_cap;
+            if (fits) a = atomicAdd(aux_counter, 1u);
+            if (a < aux_cap) {
+                uint32_t t[4];
+#pragma unroll
+                for (uint32_t e = 0; e < 4; e++) t[e] = e < sigma ? window_index(targets[e], origin, st.count) : NODE_OUTSIDE;
+                const uint32_t at = st.aux + AUX_BYTES * a;
+                sts128(at, t[0] | (t[1] << 16), t[2] | (t[3] << 16), NO_SHORTCUT, NO_SHORTCUT);
+                sts128(at + 16u, NO_SHORTCUT, NO_SHORTCUT, edge_offsets[0] | (edge_offsets[1] << 16), edge_offsets[2] | (edge_offsets[3] << 16));
+                kind = KIND_WIDE;
+                x = a | (sigma << 16); z = (unit0 / 2u) | (d.body_len() << 16); w = fmt | (d.checkpoints() << 8);
+                for (uint32_t j = 0; j < units / 2u; j++) sts8(st.kinds + unit0 / 2u + j, fmt == FMT_DENSE4 ? BLOCK_DENSE4 : BLOCK_RAW);
             }
         }
     }
-    // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
-    const uint32_t land0 = skip.y <= 0xFFFFu ? window_index(skip.x, origin, st.count) : NODE_OUTSIDE;
-    const uint32_t land1 = skip.w <= 0xFFFFu ? window_index(skip.z, origin, st.count) : NODE_OUTSIDE;
-    sts128(st.rec + 16u * r, target0 | (target1 << 16), total | (kind << 16), land0 | (skip.y << 16), land1 | (skip.w << 16));
-    sts32(st.offs + 4u * r, offset0 | (offset1 << 16));
+    if (kind != KIND_WIDE) {
+        // a shortcut whose landing node is not staged or whose offset does not fit is left out (the step then takes one hop)
+        z = skip.y <= 0xFFFFu ? (window_index(skip.x, origin, st.count) | (skip.y << 16)) : NO_SHORTCUT;
+        w = skip.w <= 0xFFFFu ? (window_index(skip.z, origin, st.count) | (skip.w << 16)) : NO_SHORTCUT;
+    }
+    sts128(st.rec + 16u * r, x, total | (kind << 16), z, w);
+    sts32(st.offs + 4u * r, offsets);
 }
 
-// One 192-bit dense block (layout.h) as twelve rank entries.
-__device__ __forceinline__ void stage_block(const Staged& st, uint32_t blk, const Quad& lo, const Quad& hi) {
-    const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    uint32_t ones = lo.x;
-    const uint32_t at_block = st.ranks + 48u * blk;
+// The two-hop shortcuts of a wide record's edges, from the staged tables (the global shortcut array only covers records
+// with inline edges): edge b leads to a single-edge record -> {that record's target, offset_b + its edge offset}.
+__device__ __forceinline__ void stage_wide_shortcuts(const Staged& st, uint32_t a) {
+    const uint32_t at = st.aux + AUX_BYTES * a;
+    const uint2 targets = lds64(at);
+    const uint2 offsets = lds64(at + 24u);
+    uint32_t hops[4];
 #pragma unroll
-    for (uint32_t j = 0; j < 6; j += 2) {
-        const uint32_t a0 = bits[j] & 0xFFFFu, a1 = bits[j] >> 16, b0 = bits[j + 1] & 0xFFFFu, b1 = bits[j + 1] >> 16;
-        const uint32_t o1 = ones + static_cast<uint32_t>(__popc(a0)), o2 = o1 + static_cast<uint32_t>(__popc(a1));
-        const uint32_t o3 = o2 + static_cast<uint32_t>(__popc(b0));
-        sts128(at_block + 8u * j, (ones & 0xFFFFu) | (a0 << 16), (o1 & 0xFFFFu) | (a1 << 16), (o2 & 0xFFFFu) | (b0 << 16), (o3 & 0xFFFFu) | (b1 << 16));
-        ones = o3 + static_cast<uint32_t>(__popc(b1));
+    for (uint32_t b = 0; b < 4; b++) {
+        const uint32_t target = ((b < 2 ? targets.x : targets.y) >> (16u * (b & 1u))) & 0xFFFFu;
+        const uint32_t offset = ((b < 2 ? offsets.x : offsets.y) >> (16u * (b & 1u))) & 0xFFFFu;
+        hops[b] = NO_SHORTCUT;
+        if (target != NODE_OUTSIDE) {
+            const uint2 next = lds64(st.rec + 16u * target);
+            const uint32_t through = offset + (lds32(st.offs + 4u * target) & 0xFFFFu);
+            if ((next.y >> 16) == KIND_SINGLE && (next.x & 0xFFFFu) != NODE_OUTSIDE && through <= 0xFFFFu) hops[b] = (next.x & 0xFFFFu) | (through << 16);
+        }
+    }
+    sts64(at + 8u, hops[0], hops[1]);
+    sts64(at + 16u, hops[2], hops[3]);
+}
+
+// One 32-byte block of the staged body range, according to what its record said it holds.
+__device__ __forceinline__ void stage_block(const Staged& st, uint32_t what, uint32_t blk, const Quad& lo, const Quad& hi) {
+    const uint32_t at_block = st.ranks + 48u * blk;
+    if (what == BLOCK_DENSE2) {
+        // a 192-bit dense block (layout.h) as twelve rank entries
+        const uint32_t bits[6] = {lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint32_t ones = lo.x;
+#pragma unroll
+        for (uint32_t j = 0; j < 6; j += 2) {
+            const uint32_t a0 = bits[j] & 0xFFFFu, a1 = bits[j] >> 16, b0 = bits[j + 1] & 0xFFFFu, b1 = bits[j + 1] >> 16;
+            const uint32_t o1 = ones + static_cast<uint32_t>(__popc(a0)), o2 = o1 + static_cast<uint32_t>(__popc(a1));
+            const uint32_t o3 = o2 + static_cast<uint32_t>(__popc(b0));
+            sts128(at_block + 8u * j, (ones & 0xFFFFu) | (a0 << 16), (o1 & 0xFFFFu) | (a1 << 16), (o2 & 0xFFFFu) | (b0 << 16), (o3 & 0xFFFFu) | (b1 << 16));
+            ones = o3 + static_cast<uint32_t>(__popc(b1));
+        }
+    } else if (what == BLOCK_DENSE4) {
+        // 64 positions of two bits: two entries of 32 positions, the second with the counts of the first half added
+        uint32_t c[3] = {lo.x, lo.y & ~DENSE4_TAG, lo.z};
+        sts128(at_block, hi.x, hi.y, c[0] | (c[1] << 16), c[2]);
+#pragma unroll
+        for (uint32_t v = 1; v <= 3; v++) {
+            const uint32_t y0 = hi.x ^ (v * 0x55555555u), y1 = hi.y ^ (v * 0x55555555u);
+            c[v - 1] += static_cast<uint32_t>(__popc(~(y0 | (y0 >> 1)) & 0x55555555u) + __popc(~(y1 | (y1 >> 1)) & 0x55555555u));
+        }
+        sts128(at_block + 16u, hi.z, hi.w, c[0] | (c[1] << 16), c[2]);
+    } else if (what == BLOCK_RAW) {
+        sts128(at_block, lo.x, lo.y, lo.z, lo.w);
+        sts128(at_block + 16u, hi.x, hi.y, hi.z, hi.w);
     }
 }
 
 constexpr uint32_t SMEM_HEADER = 128;  // control words, keeps the staged arrays 128-byte aligned
 
 // Bytes of shared memory a plan needs.
-__host__ __device__ inline uint32_t window_smem_bytes(uint32_t max_records, uint32_t body_cap, uint32_t threads) {
-    return SMEM_HEADER + max_records * RECORD_BYTES + (body_cap / 2u) * 48u + (threads / 32u) * TILE_BYTES;
+__host__ __device__ inline uint32_t window_kinds_bytes(uint32_t body_cap) { return (body_cap / 2u + 15u) & ~15u; }
+__host__ __device__ inline uint32_t window_smem_bytes(uint32_t max_records, uint32_t body_cap, uint32_t threads, uint32_t aux_cap) {
+    return SMEM_HEADER + max_records * RECORD_BYTES + aux_cap * AUX_BYTES + (aux_cap != 0 ? window_kinds_bytes(body_cap) : 0u) +
+           (body_cap / 2u) * 48u + (threads / 32u) * TILE_BYTES;
 }
 
-template <class T, int THREADS, int CTAS>
+// WIDE = false: the instantiation for an index without DENSE4 / byte-per-run records (every staged body block is a
+// DENSE2 block: no block kinds, no pool, one barrier less per window).
+template <class T, int THREADS, int CTAS, bool WIDE>
 __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, WindowPlan wp, const T* __restrict__ patterns,
                                                                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ bucket_end,
                                                                 uint32_t k, gbwt_b200_state* __restrict__ out,
@@ -306,17 +527,21 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
     Staged st;
     st.rec = smem_addr(smem) + SMEM_HEADER;
     st.offs = st.rec + 16u * wp.max_records;
-    st.ranks = st.offs + 4u * wp.max_records;
+    st.aux = st.offs + 4u * wp.max_records;
+    st.kinds = st.aux + AUX_BYTES * wp.aux_cap;
+    st.ranks = st.kinds + (WIDE ? window_kinds_bytes(wp.body_cap) : 0u);
     uint32_t tile = st.ranks + (wp.body_cap / 2u) * 48u + (tid >> 5) * TILE_BYTES;
     // (opaque to the compiler: it would otherwise recompute the shared-window addresses from special registers in every step)
-    asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(tile));
+    if (WIDE) asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(st.aux), "+r"(tile));
+    else asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(tile));
     const uint32_t slot = tile + 2u * lane;
     sts16(slot + SEGMENT * TILE_LINE, NODE_OUTSIDE);  // the line after a full segment
     // sector loads need every row segment on a 32-byte boundary
     const bool aligned = (reinterpret_cast<uintptr_t>(patterns) & 31u) == 0 && (k * sizeof(T)) % 32u == 0;
     for (;;) {
         __syncthreads();  // everybody has left the previous window: its shared memory and ctrl[] may be reused
-        if (tid == 0) { ctrl[0] = atomicAdd(&counters[0], 1u); ctrl[1] = 0; }
+        if (tid == 0) { ctrl[0] = atomicAdd(&counters[0], 1u); ctrl[1] = 0; ctrl[2] = 0; }
+        if (WIDE) { for (uint32_t i = tid; i < window_kinds_bytes(wp.body_cap) / 4u; i += THREADS) sts32(st.kinds + 4u * i, 0u); }  // BLOCK_UNUSED
         __syncthreads();
         const uint32_t w = ctrl[0];
         if (w >= wp.windows) break;
@@ -343,19 +568,27 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
         const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
         const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
-        // decode the window into shared memory: descriptors + shortcuts, then the dense blocks as {ones before, 16 bits}
-        // entries (requesting two records or blocks per thread before decoding either was measured: the extra live
-        // registers spill under the 64-register budget of two 512-thread CTAs per SM, 6.2 -> 5.0 G queries/s)
+        // decode the window into shared memory: descriptors + shortcuts first (a record also says what its body blocks
+        // hold), then the body blocks and, from the finished record table, the shortcuts of the wide records. (Requesting
+        // two records or blocks per thread before decoding either was measured: the extra live registers spill under the
+        // 64-register budget of two 512-thread CTAs per SM, 6.2 -> 5.0 G queries/s.)
         for (uint32_t r = tid; r < st.count; r += THREADS) {
             Desc d;
             load_sector(reinterpret_cast<const Unit16*>(ix.desc + st.lo + r), d.a, d.b);
             const Quad skip = load_quad(ix.skips + st.lo + r);
-            stage_record(st, r, d, skip, origin, body_lo, body_units);
+            stage_record<WIDE>(st, ix, r, d, skip, origin, body_lo, body_units, const_cast<uint32_t*>(&ctrl[2]), wp.aux_cap);
         }
+        if (WIDE) __syncthreads();
         for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
+            const uint32_t what = WIDE ? lds8(st.kinds + blk) : static_cast<uint32_t>(BLOCK_DENSE2);
+            if (what == BLOCK_UNUSED) continue;
             Quad lo, hi;
             load_sector(ix.bodies + body_lo + 2u * blk, lo, hi);
-            stage_block(st, blk, lo, hi);
+            stage_block(st, what, blk, lo, hi);
+        }
+        if (WIDE) {
+            const uint32_t wide = ctrl[2] < wp.aux_cap ? ctrl[2] : wp.aux_cap;
+            for (uint32_t a = tid; a < wide; a += THREADS) stage_wide_shortcuts(st, a);
         }
         __syncthreads();
         while (at < q_end) {
@@ -367,18 +600,18 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
                 if (wp.prefetch) prefetch_row(patterns + static_cast<size_t>(q_next) * k, k);
             }
             const bool mine = at + lane < q_end;
-            const T* row = mine ? patterns + static_cast<size_t>(q_cur) * k : nullptr;
             WindowQuery q;
             q.idx = 0; q.start = 0; q.end = 0; q.i = 0; q.status = mine && k != 0 ? QUERY_ACTIVE : QUERY_NONE;
             for (uint32_t seg = 0; seg < k; seg += SEGMENT) {
                 if (!__any_sync(0xFFFFFFFFu, q.status == QUERY_ACTIVE)) break;
                 const uint32_t n_seg = k - seg < SEGMENT ? k - seg : SEGMENT;
-                load_tile<T>(q.status == QUERY_ACTIVE ? row : nullptr, seg, n_seg, aligned && n_seg % (32u / sizeof(T)) == 0, tile, origin, st.count, lane);
+                load_tile<T>(patterns, q.status == QUERY_ACTIVE ? q_cur : NO_QUERY, k, seg, n_seg, aligned && n_seg % (32u / sizeof(T)) == 0, tile, origin,
+                             st.count, lane);
                 if (n_seg < SEGMENT) sts16(slot + n_seg * TILE_LINE, NODE_OUTSIDE);  // the line after a short segment
                 __syncwarp();
                 if (q.status == QUERY_ACTIVE) {
                     if (seg == 0) window_find(st, lds16(slot), k, q);
-                    if (q.status == QUERY_ACTIVE) window_extend(st, slot, seg, n_seg, k, q);
+                    if (q.status == QUERY_ACTIVE) window_extend<WIDE>(st, slot, seg, n_seg, k, q);
                 }
                 __syncwarp();  // the tile is rewritten in the next round
             }
@@ -458,7 +691,7 @@ template <class T, int THREADS, int CTAS>
 int launch_window_variant(const IndexView& ix, const WindowPlan& plan, const T* patterns, const uint32_t* perm,
                           const uint32_t* bucket_end, size_t k, gbwt_b200_state* out, uint32_t* deferred, uint32_t* counters,
                           int sm_count, cudaStream_t stream) {
-    auto kernel = k_find_window<T, THREADS, CTAS>;
+    auto kernel = plan.wide ? k_find_window<T, THREADS, CTAS, true> : k_find_window<T, THREADS, CTAS, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes));
     if (e != cudaSuccess) return static_cast<int>(e);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(plan.windows, static_cast<uint64_t>(sm_count) * CTAS));
@@ -468,14 +701,17 @@ int launch_window_variant(const IndexView& ix, const WindowPlan& plan, const T* 
 
 }  // namespace
 
-bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
+bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, WindowPlan& plan) {
+    plan.wide = wide ? 1u : 0u;
     if (!ix.edges_valid || ix.records < 2 || ix.stage_body == nullptr) return false;
     // Shared memory per CTA (two CTAs of 512 threads per SM by default): 40 bytes per staged record, the pattern
     // columns, and what is left holds the bitvectors (48 bytes per 32-byte block of the global layout).
     const uint32_t threads = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_THREADS", 512));
     const uint32_t smem_kb = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_SMEM_KB", threads >= 1024 ? 224 : (threads >= 512 ? 112 : 55)));
     uint32_t window = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW", threads >= 1024 ? 1024 : (threads >= 512 ? 512 : 256)));
-    uint32_t margin = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_MARGIN", threads >= 1024 ? 128 : 96));
+    // the records a pattern of 32 nodes moves away from its first one (3 records per edge on a chain of bi-allelic sites: 96)
+    const uint32_t travelled = static_cast<uint32_t>(std::min(256.0, std::max(64.0, 32.0 * edge_span)));
+    uint32_t margin = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_MARGIN", static_cast<int>(travelled)));
     if (threads != 256 && threads != 512 && threads != 1024) return false;
     if (window < STAGE_GRANULE || (window & (window - 1)) != 0 || smem_kb > 226 || smem_kb < 16) return false;
     margin = (margin + STAGE_GRANULE - 1) / STAGE_GRANULE * STAGE_GRANULE;
@@ -483,10 +719,11 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
     while ((1u << plan.wshift) < window) plan.wshift++;
     plan.margin = margin;
     plan.max_records = window + 2 * margin;
-    const uint64_t fixed = window_smem_bytes(plan.max_records, 0, threads);
+    plan.aux_cap = plan.wide ? plan.max_records / 4 : 0;  // wide records the window can hold (32 bytes each); the rest are deferred
+    const uint64_t fixed = window_smem_bytes(plan.max_records, 0, threads, plan.aux_cap);
     const uint64_t budget = static_cast<uint64_t>(smem_kb) * 1024;
     if (fixed + 4096 > budget) return false;
-    plan.body_cap = static_cast<uint32_t>((budget - fixed) / 48) * 2;
+    plan.body_cap = static_cast<uint32_t>((budget - fixed - 16) / 49) * 2;  // 48 bytes of entries + one kind byte per block
     // no point in reserving more than the average window needs several times over
     const uint64_t avg_units = body_units * plan.max_records / std::max<uint64_t>(1, ix.records);
     plan.body_cap = static_cast<uint32_t>(std::min<uint64_t>(plan.body_cap, std::max<uint64_t>(256, 4 * avg_units + 64))) & ~1u;
@@ -494,7 +731,7 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan) {
     plan.threads = threads;
     plan.prefetch = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_PREFETCH", 0));
     plan.fine = static_cast<uint32_t>(std::min<int>(std::max(0, env_or("GBWT_B200_WINDOW_FINE", 0)), static_cast<int>(plan.wshift)));
-    plan.smem_bytes = window_smem_bytes(plan.max_records, plan.body_cap, threads);
+    plan.smem_bytes = window_smem_bytes(plan.max_records, plan.body_cap, threads, plan.aux_cap);
     return true;
 }
 

@@ -20,13 +20,18 @@ struct WindowPlan {
     uint32_t threads;      // CTA size: 256, 512 or 1024
     uint32_t smem_bytes;   // dynamic shared memory per CTA
     uint32_t prefetch;     // ask L2 for the pattern rows of a warp's next 32 queries (GBWT_B200_WINDOW_PREFETCH)
+    uint32_t wide;         // 1: the instantiation that also decodes DENSE4 / byte-per-run records
+    uint32_t aux_cap;      // wide records (up to four edges, DENSE4 or byte-per-run body) a window can hold
     uint32_t fine;         // the sort's buckets are 2^(wshift - fine) records: 2^fine buckets per window, so that the queries a
                            // warp takes together start within a few records of each other (GBWT_B200_WINDOW_FINE)
 };
 
 // Chooses the plan for an index (GBWT_B200_WINDOW / _MARGIN / _SMEM_KB / _THREADS override). False = do not use
 // the window kernel for this index.
-bool plan_windows(const IndexView& ix, uint64_t body_units, WindowPlan& plan);
+// `edge_span` = mean distance, in records, from a record to the targets of its edges (the margin is what a pattern of 32
+// nodes travels at that rate).
+// `wide`: the index has DENSE4 or byte-per-run records, which the kernel answers from shared memory on a slower path.
+bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, WindowPlan& plan);
 
 // keys[q] = window of query q's first node (0 when it has no record), counts[1 + window] += 1.
 // T = uint64_t or uint32_t pattern nodes.

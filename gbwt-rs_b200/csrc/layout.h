@@ -35,8 +35,16 @@ enum BodyFormat : uint8_t {
     FMT_RUN8 = 3,    // one byte per run: value + sigma * (len - 1), len <= max(1, 256 / sigma); no escapes
     FMT_RUN32 = 4,   // one u32 per run: value | (len - 1) << 8, sigma <= 256, len <= 2^24
     FMT_RUN64 = 5,   // two u32 per run: value, len
-    FMT_COUNT = 6
+    FMT_DENSE4 = 6,  // sigma == 3 or 4: two bits per position, 32-byte blocks {counts of symbols 1, 2, 3 before the block, -, 64 positions}
+    FMT_COUNT = 7
 };
+
+// Dense block for three or four symbols = one 32-byte sector: words 0-2 = occurrences of symbols 1, 2, 3 before the
+// block (word 1 has bit 31 set, which tells a staged DENSE4 block from a DENSE2 block; the format is only used for records
+// shorter than 2^31), word 3 unused, words 4-7 = 64 positions of two bits each (position p -> word 4 + p / 16, bits
+// 2 (p % 16)). A rank is one block and at most four masked 32-bit match counts.
+constexpr uint32_t DENSE4_POSITIONS = 64;
+constexpr uint32_t DENSE4_TAG = 0x80000000u;
 
 // Dense block = one 32-byte sector: word 0 = ones before the block, word 1 = ones in payload bits [0, 64) in
 // bits 0-7 and ones in [0, 128) in bits 8-15, words 2-7 = 192 payload bits (position p -> word 2 + p / 32,

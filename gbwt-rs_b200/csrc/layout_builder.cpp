@@ -130,11 +130,16 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy, const Checkpoin
     // (a damaged file can hold a record with edges but no runs: it must not become a dense body of zero blocks)
     if (pl.sigma == 2 && policy == GBWT_B200_LAYOUT_AUTO && pl.total > 0) {
         // A dense record answers rank with one 32-byte block however long it is, so it is preferred
-        // unless it would more than double the footprint of a body that already spans several sectors.
+        // unless it would more than triple the footprint of a body that already spans several sectors. (A body of a
+        // few dozen runs is a short scan and stays as it is; it is the body of a hundred runs -- low-frequency alleles
+        // over a thousand haplotypes -- that would otherwise cost every rank a table entry and a scan.)
         uint64_t dense = 2 * ceil_div(pl.total, DENSE_BITS);
-        if (dense <= std::max<uint64_t>(4, 2 * best)) { best = dense; pl.fmt = FMT_DENSE2; }
+        if (dense <= std::max<uint64_t>(4, 3 * best)) { best = dense; pl.fmt = FMT_DENSE2; }
     }
     best = (best + 1) & ~1ull;  // every body starts on a 32-byte sector boundary (256-bit loads)
+    uint64_t dense4_units = 0;
+    if ((pl.sigma == 3 || pl.sigma == 4) && policy == GBWT_B200_LAYOUT_AUTO && pl.total > 0 && pl.total < (uint64_t(1) << 31))
+        dense4_units = 2 * ceil_div(pl.total, DENSE4_POSITIONS);
     // Checkpoints for a long run body: one every P positions with about interval_runs runs in between, P a power of two
     // doubled until the table is no larger than the runs themselves. Runs are split at the checkpoints, at most one
     // more run each, which the body is sized for.
@@ -150,6 +155,9 @@ Plan plan_record(const uint8_t* bytes, uint64_t len, int policy, const Checkpoin
             best = ((run_units_of(pl.fmt, fmt_runs + entries) + 1) & ~1ull) + ((entries * stride_units + 1) & ~1ull);
         }
     }
+    // Three or four symbols: two bits per position answer a rank from one 32-byte block, preferred under the same rule
+    // as the bitvector of a two-symbol record (unless it more than triples a body that already spans several sectors).
+    if (dense4_units != 0 && dense4_units <= std::max<uint64_t>(4, 3 * best)) { best = dense4_units; pl.fmt = FMT_DENSE4; pl.ckpt = 0; }
     if (best > 0xFFFFFFFFull) { pl.status = GBWT_B200_E_RANGE; return pl; }
     pl.units = static_cast<uint32_t>(best);
     return pl;
@@ -217,6 +225,27 @@ void emit_record(const uint8_t* bytes, uint64_t len, const Plan& pl, uint64_t bo
             const uint32_t c1 = c0 + static_cast<uint32_t>(__builtin_popcount(w[4]) + __builtin_popcount(w[5]));
             w[1] = c0 | (c1 << 8);
             ones += c1 + static_cast<uint32_t>(__builtin_popcount(w[6]) + __builtin_popcount(w[7]));
+        }
+        break;
+    }
+    case FMT_DENSE4: {
+        const uint64_t blocks = ceil_div(pl.total, DENSE4_POSITIONS);
+        d.body_len = static_cast<uint32_t>(blocks);
+        uint32_t* words = reinterpret_cast<uint32_t*>(body);
+        uint64_t pos = 0;
+        while (rd.run(value, rl)) {
+            for (uint64_t i = pos; i < pos + rl && i < pl.total; i++) {
+                const uint64_t blk = i / DENSE4_POSITIONS, at = i % DENSE4_POSITIONS;
+                words[blk * 8 + 4 + at / 16] |= static_cast<uint32_t>(value) << (2 * (at % 16));
+            }
+            pos += rl;
+        }
+        uint32_t before[4] = {0, 0, 0, 0};
+        for (uint64_t b = 0; b < blocks; b++) {
+            uint32_t* w = words + b * 8;
+            w[0] = before[1]; w[1] = before[2] | DENSE4_TAG; w[2] = before[3];
+            const uint64_t here = std::min<uint64_t>(DENSE4_POSITIONS, pl.total - b * DENSE4_POSITIONS);
+            for (uint64_t at = 0; at < here; at++) before[(w[4 + at / 16] >> (2 * (at % 16))) & 3u]++;
         }
         break;
     }
@@ -370,8 +399,8 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
     // How local the graph is in record order: the share of edges whose target lies within STAGE_LOCAL records. The
     // window kernels are only worth launching when a pattern mostly stays near its first record.
     {
-        uint64_t edges_seen = 0, edges_near = 0;
-#pragma omp parallel for schedule(static) num_threads(threads) reduction(+ : edges_seen, edges_near)
+        uint64_t edges_seen = 0, edges_near = 0, span = 0;
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(+ : edges_seen, edges_near, span)
         for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
             const RecordDesc& d = out.desc[i];
             if (d.fmt == FMT_EMPTY) continue;
@@ -379,7 +408,7 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
                 if (node == 0) return;
                 edges_seen++;
                 const int64_t delta = static_cast<int64_t>(node) - static_cast<int64_t>(in.offset) - i;
-                if (delta >= -static_cast<int64_t>(STAGE_LOCAL) && delta <= static_cast<int64_t>(STAGE_LOCAL)) edges_near++;
+                if (delta >= -static_cast<int64_t>(STAGE_LOCAL) && delta <= static_cast<int64_t>(STAGE_LOCAL)) { edges_near++; span += static_cast<uint64_t>(delta < 0 ? -delta : delta); }
             };
             if (d.flags & DESC_INLINE_EDGES) {
                 tally(d.w01[0]);
@@ -390,6 +419,7 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
         }
         out.edges_total = edges_seen;
         out.edges_local = edges_near;
+        out.edges_local_span = span;
     }
 
     // Endmarker: Record::decompress of record 0 (src/bwt.rs:465-475, src/gbwt.rs:413-414).

@@ -18,9 +18,10 @@ struct HostLayout {
     std::vector<uint64_t> skips;   // two words per record (IndexView::skips)
     std::vector<uint32_t> stage_body;  // body offset of every STAGE_GRANULE-th record (IndexView::stage_body)
     uint64_t edges_total = 0, edges_local = 0;  // edges, and those whose target is within STAGE_LOCAL records
+    uint64_t edges_local_span = 0;              // sum over the local edges of the distance to the target, in records
     bool edges_valid = true;
     uint64_t total_length = 0;    // sum of the record lengths (IndexView::walk_limit)
-    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t format_counts[FMT_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t checkpointed_records = 0;  // run bodies that carry a checkpoint table (layout.h)
 };
 

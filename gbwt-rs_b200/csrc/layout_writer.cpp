@@ -59,6 +59,18 @@ void for_each_run(const RecordDesc& d, const LayoutArrays& in, Emit emit) {
         if (run_len > 0) emit(run_value, run_len);
         break;
     }
+    case FMT_DENSE4: {
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(body);
+        uint64_t run_value = 0, run_len = 0;
+        for (uint64_t i = 0; i < d.total_len; i++) {
+            const uint64_t blk = i / DENSE4_POSITIONS, at = i % DENSE4_POSITIONS;
+            const uint64_t v = (words[blk * 8 + 4 + at / 16] >> (2 * (at % 16))) & 3u;
+            if (run_len > 0 && v != run_value) { emit(run_value, run_len); run_len = 0; }
+            run_value = v; run_len++;
+        }
+        if (run_len > 0) emit(run_value, run_len);
+        break;
+    }
     case FMT_RUN8: {
         const uint64_t sigma = (d.flags & DESC_INLINE_EDGES) ? d.sigma16 : d.w01[1];
         for (uint64_t i = 0; i < d.body_len; i++) emit(body[i] % sigma, body[i] / sigma + 1);

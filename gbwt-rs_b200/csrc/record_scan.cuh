@@ -273,6 +273,38 @@ GBWT_UNROLL
     }
 }
 
+// ---- FMT_DENSE4 (layout.h): two bits per position ---------------------------------------------------------
+// Occurrences of `symbol` among the first r (<= 16) two-bit fields of w.
+GBWT_HD uint32_t dense4_matches(uint32_t w, uint32_t symbol, uint32_t r) {
+    const uint32_t y = w ^ (symbol * 0x55555555u);
+    uint32_t t = ~(y | (y >> 1)) & 0x55555555u;
+    t = r >= 16 ? t : (t & ((1u << (2 * r)) - 1u));
+    return GBWT_POPC(t);
+}
+
+// Occurrences of `symbol` in [0, i) of a DENSE4 body, i <= total_len.
+GBWT_HD uint32_t dense4_rank(const Unit16* body, uint32_t blocks, uint32_t symbol, uint32_t i) {
+    uint32_t blk = i / DENSE4_POSITIONS;
+    if (blk >= blocks) blk = blocks - 1;
+    const uint32_t r = i - blk * DENSE4_POSITIONS;  // 0 .. 64
+    const Quad head = load_quad(body + 2 * blk), codes = load_quad(body + 2 * blk + 1);
+    const uint32_t c1 = head.x, c2 = head.y & ~DENSE4_TAG, c3 = head.z;
+    uint32_t count = symbol == 0 ? blk * DENSE4_POSITIONS - c1 - c2 - c3 : (symbol == 1 ? c1 : (symbol == 2 ? c2 : c3));
+    const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
+GBWT_UNROLL
+    for (uint32_t j = 0; j < 4; j++) {
+        if (r > 16 * j) count += dense4_matches(w[j], symbol, r - 16 * j);
+    }
+    return count;
+}
+
+GBWT_HD uint32_t dense4_symbol(const Unit16* body, uint32_t i) {
+    const uint32_t blk = i / DENSE4_POSITIONS, at = i % DENSE4_POSITIONS;
+    const Quad codes = load_quad(body + 2 * blk + 1);
+    const uint32_t w = (at >> 4) == 0 ? codes.x : ((at >> 4) == 1 ? codes.y : ((at >> 4) == 2 ? codes.z : codes.w));
+    return (w >> (2 * (at & 15u))) & 3u;
+}
+
 // ---- checkpointed run bodies (layout.h) ---------------------------------------------------------------
 // A long run body carries a table of checkpoints behind its runs: one every P = 2^shift positions, runs split there
 // at load time so that a run starts exactly at the checkpoint. Entry j - 1 (position j P) holds, in `stride` words,
@@ -388,6 +420,17 @@ GBWT_HD void rank_runs_checkpointed(const IndexView& ix, const Desc& d, uint32_t
 template <bool BD>
 GBWT_HD void rank_runs_inline(const IndexView& ix, const Desc& d, uint32_t symbol, const FlipSet& fs, uint32_t start,
                               uint32_t end, Ranks& r) {
+    if (d.fmt() == FMT_DENSE4) {
+        const Unit16* body4 = ix.bodies + d.body();
+        const uint32_t blocks = d.body_len();
+        r.at_start = dense4_rank(body4, blocks, symbol, start);
+        r.at_end = end != start ? dense4_rank(body4, blocks, symbol, end) : r.at_start;
+        if (BD && end != start) {
+            for (uint32_t v = 0; v < d.sigma(); v++)
+                if (fs.has(v)) r.flipped += dense4_rank(body4, blocks, v, end) - dense4_rank(body4, blocks, v, start);
+        }
+        return;
+    }
     if (d.checkpoints() != 0) { rank_runs_checkpointed<BD>(ix, d, symbol, fs, start, end, r); return; }
     const Unit16* body = ix.bodies + d.body();
     const uint32_t n = d.body_len();
@@ -442,6 +485,7 @@ GBWT_HD uint32_t symbol_at_runs(const IndexView& ix, const Desc& d, uint32_t i) 
     const uint32_t n = d.body_len();
     const uint32_t fmt = d.fmt();
     uint32_t off = 0, symbol = NO_SYMBOL, first = 0;
+    if (fmt == FMT_DENSE4) return i < d.total_len() ? dense4_symbol(body, i) : NO_SYMBOL;
     if (d.checkpoints() != 0 && i < d.total_len()) {
         // start at the checkpoint before position i (word sigma - 1 of its entry: the run that starts there)
         const uint32_t shift = d.checkpoints() - 1u, j = i >> shift;
@@ -699,6 +743,22 @@ GBWT_HD bool select_symbol(const IndexView& ix, const Desc& d, uint32_t symbol, 
                 return pos < total;
             }
             need -= c;
+        }
+        return false;
+    }
+    if (fmt == FMT_DENSE4) {
+        // last block whose prefix count of `symbol` is <= k, then position by position
+        uint32_t lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (dense4_rank(body, n, symbol, mid * DENSE4_POSITIONS) <= k) lo = mid; else hi = mid;
+        }
+        uint32_t seen4 = dense4_rank(body, n, symbol, lo * DENSE4_POSITIONS);
+        for (uint32_t p = lo * DENSE4_POSITIONS; p < total && p < (lo + 1) * DENSE4_POSITIONS; p++) {
+            if (dense4_symbol(body, p) == symbol) {
+                if (seen4 == k) { pos = p; return true; }
+                seen4++;
+            }
         }
         return false;
     }

@@ -142,6 +142,9 @@ GBWT_B200_API uint64_t gbwt_b200_skip_bytes(const gbwt_b200_index* index);      
  * of runs, where RLEIter (src/support.rs:1413-1430, used by Record::follow / lf, src/bwt.rs:480-496, 595-656) scans from
  * the start of the record. */
 GBWT_B200_API uint64_t gbwt_b200_run_checkpoint_records(const gbwt_b200_index* index);
+/* Records with three or four edges held as two bits per position (counted with the dense records in the breakdown of
+ * gbwt_b200_device_bytes). */
+GBWT_B200_API uint64_t gbwt_b200_dense4_records(const gbwt_b200_index* index);
 /* Bytes of HBM held by the index (including the path-walk shortcuts and node labels, reported separately
  * below), and a breakdown: [0] descriptors, [1] bodies, [2] edge lists, [3] endmarker; [4..9] number of records per body format (empty, single-edge, dense, run8, run32, run64). */
 GBWT_B200_API uint64_t gbwt_b200_device_bytes(const gbwt_b200_index* index, uint64_t breakdown[10]);

@@ -151,7 +151,7 @@ class HostSim:
         return int(self._L.hs_checkpointed_records(self._h))
 
     def format_counts(self):
-        out = np.zeros(6, dtype=np.uint64)
+        out = np.zeros(7, dtype=np.uint64)
         self._L.hs_format_counts(self._h, _p(out))
         return [int(x) for x in out]
 

@@ -82,18 +82,24 @@ def test_wide_records_default_thresholds(b200, sigma, bits):
 
 
 @pytest.mark.parametrize("layout", ["auto", "runs"])
-@pytest.mark.parametrize("lean", [None, "0", "3"])
+@pytest.mark.parametrize("lean", [None, "0", "3", "window"])
 def test_run_length_workload(b200, layout, lean, monkeypatch):
     """The benchmark's run-length workload (bench.py --workload find-runs) at test size, through the default dispatch,
-    the general kernels (GBWT_B200_FIND_LEAN=0) and the lean loop with the out-of-line step (=3)."""
-    if lean is not None:
+    the general kernels (GBWT_B200_FIND_LEAN=0), the lean loop with the out-of-line step (=3), and with the record-window
+    kernel forced (wide records: DENSE4 and byte-per-run bodies answered from shared memory)."""
+    if lean == "window":
+        monkeypatch.setenv("GBWT_B200_FIND_WINDOW", "2")
+    elif lean is not None:
         monkeypatch.setenv("GBWT_B200_FIND_LEAN", lean)
     monkeypatch.setenv("GBWT_B200_LOCALITY", "1")
     S, H, seed, ppm, tri = 3000, 1024, 42, 50_000, 10
     img = synth.bubble_chain(S, H, seed, alt_ppm=ppm, tri_mod=tri)
     g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, layout=layout)
     stats = e.device_bytes()
-    assert stats["records_run8"] + stats["records_run32"] > 0 and stats["records_run_checkpointed"] > 0
+    if layout == "runs":
+        assert stats["records_run8"] + stats["records_run32"] > 0 and stats["records_run_checkpointed"] > 0
+    else:
+        assert stats["records_dense4"] > 0
     pats = synth.patterns(S, H, seed, n=100_000, k=32, alt_ppm=ppm, tri_mod=tri)
     got = e.find_extend(pats)
     assert pc.states_equal(got, g.find_extend_batch(pats))
@@ -107,3 +113,29 @@ def test_run_length_workload(b200, layout, lean, monkeypatch):
     seq = [int(x) for x in synth.sequence(S, H, seed, 1, ppm, tri)][:40]
     nodes_, offs, first, start, end = pc.bd_triples([seq[:12]])
     assert pc.states_equal(e.bd_search(nodes_, offs, first, start, end), g.bd_search_batch(nodes_, offs, first, start, end))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_window_kernel_on_wide_records(b200, seed, monkeypatch):
+    """Graphs whose records mostly have three or four successors in both orientations, record-window kernel forced, with
+    and without forced checkpoint tables on the byte-per-run bodies: find/extend of every subpath against the oracle."""
+    from test_run_checkpoints import sparse_paths
+    monkeypatch.setenv("GBWT_B200_FIND_WINDOW", "2")
+    monkeypatch.setenv("GBWT_B200_LOCALITY", "1")
+    if seed % 2 == 1:
+        monkeypatch.setenv("GBWT_B200_CKPT_MIN_RUNS", "1")
+        monkeypatch.setenv("GBWT_B200_CKPT_INTERVAL_RUNS", "2")
+    rng = random.Random(700 + seed)
+    paths = sparse_paths(rng, rng.choice([6, 10, 40]), rng.choice([150, 400, 900]))
+    img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths)))
+    g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img)
+    w0 = e.window_info()
+    pc.check_find_extend_subpaths(e, g)
+    pc.check_find_extend_random(e, g, n=20000, k=7, seed=seed)
+    seqs = [g.sequence(i) for i in range(g.sequences())]
+    for k in (2, 3, 5, 16, 17, 33):
+        pats = pc.subpath_patterns(seqs, k)
+        if pats:
+            pats = np.array(pats, dtype=np.uint64)
+            assert pc.states_equal(e.find_extend(pats), g.find_extend_batch(pats))
+            assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), g.find_extend_batch(pats))
