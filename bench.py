@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extract", action="store_true", help="skip the configs[4] extraction inside the default run")
+    ap.add_argument("--no-runs", action="store_true", help="skip the run-length workload inside the default run")
     return ap.parse_args()
 
 
@@ -296,16 +297,17 @@ def main():
 
     sites, haplotypes, Q = resolve_workload(args)
 
-    def replicated_index(checkpoints):
+    def replicated_index(checkpoints, image_bytes=None):
         """The index on this rank's GPU: rank 0 parses the image, runs K0 and the checkpoint walk once, the other ranks
         import its arrays device to device (CUDA IPC + peer copies over NVLink) instead of repeating the host work."""
         t = time.time()
+        src = image if image_bytes is None else image_bytes
         if world == 1:
-            return gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=checkpoints), time.time() - t
+            return gb.GBWT.from_bytes(src, device=local_rank, layout=args.layout, checkpoints=checkpoints), time.time() - t
         box = [None]
         first = None
         if rank == 0:
-            first = gb.GBWT.from_bytes(image, device=local_rank, layout=args.layout, checkpoints=checkpoints)
+            first = gb.GBWT.from_bytes(src, device=local_rank, layout=args.layout, checkpoints=checkpoints)
             box[0] = first.export_ipc()
         dist.broadcast_object_list(box, src=0, device=dev)
         ix = first if rank == 0 else gb.GBWT.import_ipc(box[0], device=local_rank)
@@ -452,6 +454,13 @@ def main():
         extract = bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats,
                                        replicated_index)
 
+    # the run-length workload in the same run (low-frequency alleles, tri-allelic sites: records the dense bitvector does not cover)
+    find_runs = None
+    if args.workload == "find" and not args.no_runs:
+        del index
+        torch.cuda.empty_cache()
+        find_runs = bench_find_runs(args, rank, world, local_rank, barrier, max_over_ranks, replicated_index)
+
     if rank == 0:
         line = {
             "metric": "gbwt_find_queries_per_s_k32", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -459,7 +468,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, sites, haplotypes, Q, "inputs and outputs resident in HBM"),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "extra": {"lf_steps_per_s": value * K_LEN, "find_u32": find_u32, "extract": extract,
+            "extra": {"lf_steps_per_s": value * K_LEN, "find_u32": find_u32, "extract": extract, "find_runs": find_runs,
                       "occurrences_checksum": checksum, "index_device_bytes": stats, "index_build_s": build_s,
                       "checkpoints": ckpt, "window": {k: w1[k] for k in ("window_records", "margin", "threads", "smem_bytes", "windows")},
                       "step_ms": step_ms, "arithmetic": "u64 node identifiers and offsets at the ABI, 32-bit inside the kernels "
@@ -526,12 +535,75 @@ def bench_e2e(args, index, d_pat, want_out, Q, world, local_rank, barrier, max_o
     return e2e
 
 
+def bench_find_runs(args, rank, world, local_rank, barrier, max_over_ranks, replicated_index):
+    """The same metric on the run-length workload (WORKLOADS["find-runs"]): alternative alleles of frequency 0.05 and every
+    tenth site tri-allelic, so that the anchors are not all plain bitvectors -- three-edge records (DENSE4), byte-per-run
+    bodies and their checkpoint tables are on the path. Device-resident patterns, weak scaling like the headline."""
+    import torch
+    import gbwt_rs_b200 as gb
+    from synth import synth
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    sites, haplotypes, Q = WORKLOADS["find-runs"]
+    model = MODELS["find-runs"]
+    Q = min(Q, args.queries) if args.queries else Q
+    img = None
+    if rank == 0:
+        img = synth.bubble_chain(sites, haplotypes, SEED, threads=(os.cpu_count() or 0) if world > 1 else 0, **model)
+    index, build_s = replicated_index(False, img.array if img is not None else None)
+    stats = index.device_bytes()
+    d_pat = torch.empty((Q, K_LEN), dtype=torch.int64, device=dev)
+    d_out = torch.empty((Q, 3), dtype=torch.int64, device=dev)
+    synth.patterns_device(sites, haplotypes, SEED, Q, d_pat.data_ptr(), k=K_LEN, seed_q=SEED_Q, q0=rank * Q, stream=stream, **model)
+    torch.cuda.synchronize()
+    steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        index.find_extend_device(d_pat.data_ptr(), Q, K_LEN, d_out.data_ptr(), stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        index.find_extend_device(d_pat.data_ptr(), Q, K_LEN, d_out.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    if not (bool(torch.all(d_out[:, 2] > d_out[:, 1]).item()) and bool(torch.equal(d_out[:, 0], d_pat[:, K_LEN - 1]))):
+        raise SystemExit("run-length workload: a sampled pattern was not found")
+    os.environ["GBWT_B200_WINDOW_STATS"] = "1"
+    w0 = index.window_info()
+    index.find_extend_device(d_pat.data_ptr(), Q, K_LEN, d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    w1 = index.window_info()
+    del os.environ["GBWT_B200_WINDOW_STATS"]
+    checked = 0
+    if rank == 0:
+        from oracle import oracle as orc
+        g = orc.GBWT.load(img.array, native=True)
+        sample_n = 20_000
+        sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=0, **model)
+        want = g.find_extend_batch(sample)
+        if not np.array_equal(d_out[:sample_n].cpu().numpy().view(np.uint64), want.view(np.uint64).reshape(-1, 3)):
+            raise SystemExit("run-length workload: parity failure against the oracle")
+        checked = sample_n
+    res = {"metric": "gbwt_find_queries_per_s_k32", "value": Q * world / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+           "queries_per_gpu_per_step": Q,
+           "workload": f"{4 * sites + 1} node ids x {haplotypes} haplotypes, alternative alleles of frequency {model['alt_ppm'] / 1e6:g}, every "
+                       f"{model['tri_mod']}th site tri-allelic; length-{K_LEN} patterns sampled from the haplotypes",
+           "index_device_bytes": stats, "index_build_s": build_s,
+           "window_kernel_ms": (w1["kernel_ns"] - w0["kernel_ns"]) / 1e6 if w1["launches"] > w0["launches"] else None,
+           "deferred_queries_per_step": w1["deferred"] - w0["deferred"],
+           "parity": f"all patterns found, state.node == last node on the full batch; first {checked} queries bit-exact against the CPU oracle"}
+    del d_pat, d_out, index
+    torch.cuda.empty_cache()
+    return res
+
+
 def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, local_rank, barrier, max_over_ranks, ckpt, stats,
                          replicated_index):
     """configs[4] inside the default run: every forward haplotype path, partitioned by path over the ranks (strong scaling).
     warm = the index as the library builds it (path checkpoints from the load-time walk: sequences are extracted as
     independent segments); cold = a fresh handle WITHOUT checkpoints and without remembered lengths (one dependent chain per
-    path), first call and second call (lengths known after the first: two chains per path)."""
+    path), first call and second call."""
     import torch
     import gbwt_rs_b200 as gb
     from synth import synth
@@ -619,9 +691,11 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         "note": "warm: k_extract_checkpointed, every sequence cut into independent segments at the checkpoints the index was built "
                 "with (build time above; the checkpoints are part of the immutable index, not a cache); a lane makes two dependent "
                 "loads per two-node step, so its latency bound is 1 node per round trip x lanes in flight. cold: a handle created "
-                "without checkpoints, one dependent chain per path (k_extract), then two per path once the first call has measured "
-                "the lengths (k_extract_split). frac_bytes = (8-byte nodes written + forward half of the index read once) / time / "
-                "measured HBM peak. All three produce identical bytes (checked); 8 whole paths compared with the CPU oracle on rank 0",
+                "without checkpoints, one dependent chain per path (two-hop steps). A path is only walked from both ends once BOTH "
+                "of its strands have been walked whole and their signatures agree; this run extracts the forward strands only, so "
+                "the second cold call repeats the first. frac_bytes = (8-byte nodes written + forward half of the index read once) "
+                "/ time / measured HBM peak. Cold and warm produce identical bytes (checked); 8 whole paths compared with the CPU "
+                "oracle on rank 0",
     }
     del nodes
     torch.cuda.empty_cache()
