@@ -1364,8 +1364,8 @@ struct CheckpointView {
 constexpr uint32_t TILE_NODES = 64, TILE_STRIDE = 65;  // nodes (32-bit) per lane between flushes; row stride in words
 
 // Index loads of the segment walks: the output of an extraction streams tens of GB through L2 and, even written with
-// evict-first stores, pushed the index out (L2 read hit rate 9 % in profiles/r2_extract_checkpointed_v2_ncu.txt: every
-// record fetch went to DRAM behind the writes). These loads ask L2 to keep what they touch (evict_last).
+// evict-first stores, pushed the index out (L2 read hit rate 9 % in the capture of that version: every record fetch went to DRAM
+// behind the writes; the shipped kernel's capture is profiles/r2_extract_checkpointed_v3_ncu.txt). These loads ask L2 to keep what they touch (evict_last).
 __device__ __forceinline__ uint64_t keep_policy() {
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
