@@ -300,6 +300,7 @@ def main():
     def replicated_index(checkpoints, image_bytes=None):
         """The index on this rank's GPU: rank 0 parses the image, runs K0 and the checkpoint walk once, the other ranks
         import its arrays device to device (CUDA IPC + peer copies over NVLink) instead of repeating the host work."""
+        barrier()  # (the first collective also sets up the NCCL communicator: keep that out of the build time)
         t = time.time()
         src = image if image_bytes is None else image_bytes
         if world == 1:
@@ -308,6 +309,7 @@ def main():
         first = None
         if rank == 0:
             first = gb.GBWT.from_bytes(src, device=local_rank, layout=args.layout, checkpoints=checkpoints)
+            log(f"[bench] rank 0 built the index in {time.time() - t:.1f} s; the other ranks copy it device to device")
             box[0] = first.export_ipc()
         dist.broadcast_object_list(box, src=0, device=dev)
         ix = first if rank == 0 else gb.GBWT.import_ipc(box[0], device=local_rank)
