@@ -411,14 +411,14 @@ def main():
         # algorithmic bytes per query of SURVEY.md 8(d), on the reference's compressed records, from a sample
         from oracle import oracle as orc
         t = time.time()
-        sample_n = 20_000
+        sample_n = 1 << 18
         if args.no_cpu_baseline or world > 1:
             g = orc.GBWT.load(image, native=True)
         else:
             cpu, g = cpu_find_baseline(image, sites, haplotypes, args.cpu_sample, model=model)
         sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=q0, **model)
-        bytes_per_query = g.find_extend_bytes(sample) / sample_n
-        want = g.find_extend_batch(sample)
+        bytes_per_query = g.find_extend_bytes(sample[:20_000]) / 20_000
+        want = g.find_extend_batch(sample, threads=orc.max_threads())
         got = want_out[:sample_n].cpu().numpy().view(np.uint64)
         if not np.array_equal(got, want.view(np.uint64).reshape(-1, 3)):
             raise SystemExit("parity failure against the oracle on the sampled queries")
@@ -475,7 +475,7 @@ def main():
                       "checkpoints": ckpt, "window": {k: w1[k] for k in ("window_records", "margin", "threads", "smem_bytes", "windows")},
                       "step_ms": step_ms, "arithmetic": "u64 node identifiers and offsets at the ABI, 32-bit inside the kernels "
                                                         "(an index that does not fit is rejected at load)",
-                      "parity": "all patterns found, state.node == last node on the full batch; first 20000 queries bit-exact "
+                      "parity": f"all patterns found, state.node == last node on the full batch; first {1 << 18} queries bit-exact "
                                 "against the CPU oracle; 32-bit and host-path results identical to the device-path results"},
         }
         print(json.dumps(line), flush=True)
@@ -581,9 +581,9 @@ def bench_find_runs(args, rank, world, local_rank, barrier, max_over_ranks, repl
     if rank == 0:
         from oracle import oracle as orc
         g = orc.GBWT.load(img.array, native=True)
-        sample_n = 20_000
+        sample_n = 1 << 18
         sample = synth.patterns(sites, haplotypes, SEED, n=sample_n, k=K_LEN, seed_q=SEED_Q, q0=0, **model)
-        want = g.find_extend_batch(sample)
+        want = g.find_extend_batch(sample, threads=orc.max_threads())
         if not np.array_equal(d_out[:sample_n].cpu().numpy().view(np.uint64), want.view(np.uint64).reshape(-1, 3)):
             raise SystemExit("run-length workload: parity failure against the oracle")
         checked = sample_n

@@ -75,3 +75,31 @@ def test_full_size_extraction_against_oracle(world, monkeypatch):
     assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
     for j, i in enumerate(ids[:3]):
         assert np.array_equal(nodes[int(offsets[j]):int(offsets[j + 1])], synth.sequence(S, H, SEED, int(i)))
+
+
+def test_full_size_run_length_workload_against_oracle():
+    """The run-length workload of bench.py (10 M node ids, alternative alleles of frequency 0.05, every tenth site
+    tri-allelic) at full size: DENSE4 anchors and wide records in the window kernel, 1 M queries against the oracle."""
+    import gbwt_rs_b200 as b200
+    sites, ppm, tri = 2_500_000, 50_000, 10
+    img = synth.bubble_chain(sites, H, SEED, alt_ppm=ppm, tri_mod=tri)
+    e = b200.GBWT.from_bytes(img.array, checkpoints=False)
+    g = orc.GBWT.load(img.array, native=True)
+    stats = e.device_bytes()
+    assert stats["records_dense4"] > 400_000 and e.window_info()["default"] == 1
+    n = 1 << 20
+    pats = synth.patterns(sites, H, SEED, n=n, k=32, seed_q=7, q0=987_654_321, alt_ppm=ppm, tri_mod=tri)
+    want = g.find_extend_batch(pats, threads=orc.max_threads())
+    got = e.find_extend(pats)
+    assert pc.states_equal(got, want)
+    assert np.all(got["end"] > got["start"]) and np.array_equal(got["node"], pats[:, -1])
+    assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), want)
+    bad = pats[: 1 << 18].copy()
+    rng = np.random.default_rng(6)
+    bad[np.arange(len(bad)), rng.integers(0, 32, len(bad))] ^= np.uint64(1)
+    assert pc.states_equal(e.find_extend(bad), g.find_extend_batch(bad, threads=orc.max_threads()))
+    ids = np.array([0, 1, 2 * H - 1], dtype=np.uint64)
+    offsets, nodes, lengths = e.extract(ids)
+    o_off, o_nodes = g.extract_batch(ids, threads=3)
+    assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+    e.close()
