@@ -265,7 +265,11 @@ int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, s
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (stats && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) { cudaGetLastError(); t0 = t1 = nullptr; }
             if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t0, s);
-            const int e = launch_find_window<T>(ix->view, ix->window, part, perm, bucket_end, count, k, out + begin, scratch, counters, ix->sm_count, s);
+            // margins for this batch's pattern length (the windows themselves, and with them the sort, stay the same)
+            WindowPlan plan = ix->window;
+            if (k != 32 && !plan_windows(ix->view, plan.body_units, plan.edge_span, plan.wide != 0, static_cast<uint32_t>(std::min<size_t>(k, 4096)), plan))
+                plan = ix->window;
+            const int e = launch_find_window<T>(ix->view, plan, part, perm, bucket_end, count, k, out + begin, scratch, counters, ix->sm_count, s);
             if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t1, s);
             if (e != 0) rc = cuda_fail(static_cast<cudaError_t>(e), "k_find_window");
             g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -878,7 +882,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
         const bool local = layout.edges_local * 10 >= layout.edges_total * 9;
         const double edge_span = layout.edges_local != 0 ? static_cast<double>(layout.edges_local_span) / static_cast<double>(layout.edges_local) : 3.0;
         const bool wide = layout.format_counts[FMT_DENSE4] + layout.format_counts[FMT_RUN8] != 0;
-        ix->window_ok = plan_windows(v, layout.bodies.size() / 2, edge_span, wide, ix->window);
+        ix->window_ok = plan_windows(v, layout.bodies.size() / 2, edge_span, wide, 32, ix->window);
         ix->window_suits = mostly_plain && local;
     }
     if (parsed.has_graph) {

@@ -701,7 +701,7 @@ int launch_window_variant(const IndexView& ix, const WindowPlan& plan, const T* 
 
 }  // namespace
 
-bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, WindowPlan& plan) {
+bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, uint32_t pattern_len, WindowPlan& plan) {
     plan.wide = wide ? 1u : 0u;
     if (!ix.edges_valid || ix.records < 2 || ix.stage_body == nullptr) return false;
     // Shared memory per CTA (two CTAs of 512 threads per SM by default): 40 bytes per staged record, the pattern
@@ -709,8 +709,10 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bo
     const uint32_t threads = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_THREADS", 512));
     const uint32_t smem_kb = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_SMEM_KB", threads >= 1024 ? 224 : (threads >= 512 ? 112 : 55)));
     uint32_t window = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW", threads >= 1024 ? 1024 : (threads >= 512 ? 512 : 256)));
-    // the records a pattern of 32 nodes moves away from its first one (3 records per edge on a chain of bi-allelic sites: 96)
-    const uint32_t travelled = static_cast<uint32_t>(std::min(256.0, std::max(64.0, 32.0 * edge_span)));
+    // the records a pattern moves away from its first one (3 records per edge on a chain of bi-allelic sites: 96 for 32 nodes)
+    plan.edge_span = static_cast<float>(edge_span);
+    plan.body_units = body_units;
+    const uint32_t travelled = static_cast<uint32_t>(std::min(256.0, std::max(64.0, std::max<uint32_t>(pattern_len, 16) * edge_span)));
     uint32_t margin = static_cast<uint32_t>(env_or("GBWT_B200_WINDOW_MARGIN", static_cast<int>(travelled)));
     if (threads != 256 && threads != 512 && threads != 1024) return false;
     if (window < STAGE_GRANULE || (window & (window - 1)) != 0 || smem_kb > 226 || smem_kb < 16) return false;

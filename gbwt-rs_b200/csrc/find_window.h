@@ -20,6 +20,8 @@ struct WindowPlan {
     uint32_t threads;      // CTA size: 256, 512 or 1024
     uint32_t smem_bytes;   // dynamic shared memory per CTA
     uint32_t prefetch;     // ask L2 for the pattern rows of a warp's next 32 queries (GBWT_B200_WINDOW_PREFETCH)
+    float edge_span;       // what the plan was made from (a batch of patterns of another length is planned again)
+    uint64_t body_units;
     uint32_t wide;         // 1: the instantiation that also decodes DENSE4 / byte-per-run records
     uint32_t aux_cap;      // wide records (up to four edges, DENSE4 or byte-per-run body) a window can hold
     uint32_t fine;         // the sort's buckets are 2^(wshift - fine) records: 2^fine buckets per window, so that the queries a
@@ -31,7 +33,9 @@ struct WindowPlan {
 // `edge_span` = mean distance, in records, from a record to the targets of its edges (the margin is what a pattern of 32
 // nodes travels at that rate).
 // `wide`: the index has DENSE4 or byte-per-run records, which the kernel answers from shared memory on a slower path.
-bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, WindowPlan& plan);
+// `pattern_len`: the plan of an index is made for patterns of 32 nodes; a batch of longer or shorter patterns gets its own
+// (same windows, other margins).
+bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bool wide, uint32_t pattern_len, WindowPlan& plan);
 
 // keys[q] = window of query q's first node (0 when it has no record), counts[1 + window] += 1.
 // T = uint64_t or uint32_t pattern nodes.

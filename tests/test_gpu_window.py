@@ -71,6 +71,28 @@ def test_window_kernel_matches_oracle(b200, threads, monkeypatch):
     assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), out)
 
 
+@pytest.mark.parametrize("k", [2, 7, 16, 17, 40, 64, 100])
+def test_window_kernel_pattern_lengths(b200, k, monkeypatch):
+    """Patterns shorter and longer than the 32 nodes an index's windows are planned for (a batch gets margins for its own
+    length), lengths that are not a whole number of 16-node segments or 32-byte sectors, 64- and 32-bit nodes."""
+    force_windows(monkeypatch)
+    S, H, seed = 4000, 64, 5
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    pats = synth.patterns(S, H, seed, n=30_000, k=k)
+    rng = np.random.default_rng(k)
+    if k > 1:
+        rows = rng.integers(0, len(pats), 3000)
+        pats[rows, rng.integers(1, k, 3000)] ^= np.uint64(1)  # a third of the damaged ones fail somewhere in the middle
+    want = g.find_extend_batch(pats)
+    w0 = e.window_info()
+    assert pc.states_equal(e.find_extend(pats), want)
+    assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), want)
+    w1 = e.window_info()
+    assert w1["queries"] - w0["queries"] == 2 * len(pats)      # both went through the windows ...
+    assert w1["deferred"] - w0["deferred"] < len(pats) // 4    # ... and mostly stayed there
+
+
 def test_window_kernel_edge_cases(b200, monkeypatch):
     force_windows(monkeypatch)
     S, H, seed = 400, 40, 17
