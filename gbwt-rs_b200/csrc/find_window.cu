@@ -630,6 +630,260 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
     }
 }
 
+// ---- path extraction from record windows ----------------------------------------------------------------------------
+// Checkpointed extraction (kernels.cuh: k_extract_checkpointed) walks segment j of every sequence with one lane, each
+// lane loading the records it meets from L1 / L2 / HBM: 62 instructions per node at 24 warps per SM, a third of the issue
+// slots busy, every step an L2 round trip. But the lanes that walk segment j of neighbouring sequences walk the SAME
+// records -- that is what a pangenome is. Here a CTA takes segment j of 512 sequences, stages the window of records its
+// lanes are in (the staging of the search kernel above: one 16-byte entry per record, one 4-byte entry per 16 positions
+// of a bitvector) and every lane steps through it from shared memory; when most lanes have left the window the CTA
+// stages the next one. A lane that cannot take a step from the window (its node is not staged, a record format the
+// window does not decode, the end of a sequence) takes that step from the global layout instead, so the result never
+// depends on where the windows fall. Every node is still produced by an LF step (Record::lf, src/bwt.rs:480-496).
+constexpr uint32_t EXTRACT_TILE_NODES = 32, EXTRACT_TILE_STRIDE = 33;  // nodes a lane parks between flushes; row stride in words
+
+// One LF step from the global layout: GBWT::forward (src/gbwt.rs:222-229). (offset << 32) | node, 0 = None. Out of line
+// (and therefore without the 256-bit inline-asm load): the rare step must not weigh on the walk's registers.
+__device__ __noinline__ uint64_t global_forward(const RecordDesc* descs, const Unit16* bodies, const Edge* edges, uint32_t base, uint32_t records,
+                                                uint32_t node, uint32_t offset) {
+    const uint32_t rec = node - base;
+    if (node < base + 1u || rec >= records) return 0;
+    Desc d;
+    d.a = load_quad(reinterpret_cast<const Unit16*>(descs + rec));
+    d.b = load_quad(reinterpret_cast<const Unit16*>(descs + rec) + 1);
+    const uint32_t fmt = d.fmt();
+    if (fmt == FMT_EMPTY || offset >= d.total_len()) return 0;
+    IndexView view;  // the scans only look at the bodies and the edge lists
+    view.desc = descs; view.bodies = bodies; view.edges = edges; view.endmarker = nullptr;
+    view.records = records; view.offset = base; view.alphabet_size = 0; view.sequences = 0; view.endmarker_len = 0;
+    view.bidirectional = 0; view.skips = nullptr; view.edges_valid = 1; view.walk_limit = 0; view.stage_body = nullptr;
+    uint32_t symbol, rank_i;
+    if (fmt == FMT_SINGLE) {
+        symbol = 0; rank_i = offset;
+    } else if (fmt == FMT_DENSE2) {
+        // (the block with two 128-bit loads: the 256-bit inline-asm load must not appear in a function that is not inlined)
+        uint32_t blk = offset / DENSE_BITS;
+        if (blk >= d.body_len()) blk = d.body_len() - 1;
+        DenseBlock block;
+        block.lo = load_quad(bodies + d.body() + 2 * blk);
+        block.hi = load_quad(bodies + d.body() + 2 * blk + 1);
+        const uint32_t ones = dense_block_rank1(block, offset - blk * DENSE_BITS, symbol);
+        rank_i = symbol ? ones : offset - ones;
+    } else {
+        symbol = symbol_at_runs(view, d, offset);
+        if (symbol == NO_SYMBOL) return 0;
+        FlipSet fs;
+        fs.lt = 0; fs.extra = NO_SYMBOL;
+        Ranks r;
+        r.at_start = r.at_end = r.flipped = 0;
+        rank_runs_inline<false>(view, d, symbol, fs, offset, offset, r);
+        rank_i = r.at_start;
+    }
+    const Edge e = edge_at(view, d, symbol);
+    if (e.node == 0) return 0;  // successor is the endmarker: the sequence ends (src/bwt.rs:485-486)
+    return (static_cast<uint64_t>(e.offset + rank_i) << 32) | e.node;
+}
+
+struct ExtractLane {
+    uint32_t node, offset;  // current position
+    uint32_t left;          // nodes of the segment still to be emitted (0 = done)
+    uint32_t parked;        // nodes in the tile row
+    bool moved;             // has taken a step from this window
+};
+
+// As many steps as the tile row has room for. A lane that cannot take its next step from the window (its node is not
+// staged, or leads out of the staged range) waits for the next window if it has moved in this one, and otherwise takes
+// the step from the global layout: every window moves every lane. Returns true if the lane is waiting.
+__device__ __forceinline__ bool extract_round(const Staged& st, uint32_t origin, ExtractLane& ln, uint32_t row, const RecordDesc* descs,
+                                              const Unit16* bodies, const Edge* edges, uint32_t base, uint32_t records) {
+    while (ln.left != 0 && ln.parked + 2u <= EXTRACT_TILE_NODES) {
+        const uint32_t idx = ln.node - origin;
+        if (idx >= st.count && ln.moved) return true;
+        bool stepped = false, ended = false, leaves = false;  // leaves: the record is staged, the one it leads to is not
+        uint32_t v = 0, next_node = 0, next_offset = 0;  // fast step: the second node of a two-hop step (0: none), the landing position
+        if (idx < st.count) {
+            const uint4 h = lds128(st.rec + 16u * idx);
+            const uint32_t kind = h.y >> 16, total = h.y & 0xFFFFu, at = ln.offset;
+            if (kind < KIND_WIDE || kind == KIND_SINGLE) {
+                if (at >= total) {
+                    ended = true;  // GBWT::forward -> None
+                } else {
+                    uint32_t b = 0, r = at;
+                    if (kind != KIND_SINGLE) {
+                        const uint32_t w = lds32(st.ranks + 4u * (kind + (at >> 4)));
+                        const uint32_t sh = at & 15u;
+                        b = (w >> (16u + sh)) & 1u;
+                        const uint32_t ones = (w & 0xFFFFu) + static_cast<uint32_t>(__popc((w >> 16) & ~(0xFFFFFFFFu << sh)));
+                        r = b ? ones : at - ones;
+                    }
+                    const uint32_t target = b ? h.x >> 16 : h.x & 0xFFFFu, hop = b ? h.w : h.z;
+                    if (target != NODE_OUTSIDE) {
+                        if ((hop & 0xFFFFu) != NODE_OUTSIDE) {
+                            // two nodes: the successor is a single-edge record (layout.h, IndexView::skips)
+                            v = target + origin; next_node = (hop & 0xFFFFu) + origin; next_offset = (hop >> 16) + r;
+                        } else {
+                            next_node = target + origin; next_offset = lds16(st.offs + 4u * idx + 2u * b) + r;
+                        }
+                        stepped = true;
+                    } else {
+                        leaves = true;
+                    }
+                }
+            }
+        }
+        if (leaves && ln.moved) return true;  // (the next window will hold the landing record)
+        sts32(row + 4u * ln.parked, ln.node);
+        ln.parked++;
+        if (ended) { ln.left = 0; break; }
+        if (stepped) {
+            if (v != 0) {
+                if (ln.left > 1) { sts32(row + 4u * ln.parked, v); ln.parked++; }
+                ln.left = ln.left > 2 ? ln.left - 2 : 0;
+            } else {
+                ln.left -= 1;
+            }
+            ln.node = next_node; ln.offset = next_offset;
+            ln.moved = true;
+        } else {
+            const uint64_t next = global_forward(descs, bodies, edges, base, records, ln.node, ln.offset);
+            if (next == 0) { ln.left = 0; break; }
+            ln.node = static_cast<uint32_t>(next); ln.offset = static_cast<uint32_t>(next >> 32);
+            ln.left -= 1;
+            ln.moved = true;
+        }
+    }
+    return false;
+}
+
+template <int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_extract_window(IndexView ix, CheckpointView cv, WindowPlan wp, const uint64_t* __restrict__ ids, size_t m,
+                                                                const uint64_t* __restrict__ out_offsets, uint64_t base_offset,
+                                                                uint64_t* __restrict__ nodes, uint64_t* __restrict__ lengths,
+                                                                uint32_t* __restrict__ counters) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    extern __shared__ __align__(128) unsigned char smem[];
+    // ctrl: [0] work ticket, [2] lowest record of an active lane, [3] highest, [4] lanes walking towards higher records
+    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    Staged st;
+    st.rec = smem_addr(smem) + SMEM_HEADER;
+    st.offs = st.rec + 16u * wp.max_records;
+    st.aux = st.offs + 4u * wp.max_records;
+    st.kinds = st.aux;
+    st.ranks = st.aux;
+    uint32_t tiles = st.ranks + (wp.body_cap / 2u) * 48u;
+    asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(tiles));
+    const uint32_t tile = tiles + (tid >> 5) * (32u * EXTRACT_TILE_STRIDE * 4u), row = tile + lane * (EXTRACT_TILE_STRIDE * 4u);
+    const RecordDesc* const descs = ix.desc;
+    const Unit16* const bodies = ix.bodies;
+    const Edge* const edges = ix.edges;
+    const uint64_t blocks = (m + THREADS - 1) / THREADS;
+    const uint64_t items = blocks * cv.max_segments;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) ctrl[0] = atomicAdd(&counters[0], 1u);
+        __syncthreads();
+        const uint64_t item = ctrl[0];
+        if (item >= items) break;
+        const uint64_t j = item / blocks, i = (item - j * blocks) * THREADS + tid;
+        // this lane's segment, if it has one (as in k_extract_checkpointed)
+        ExtractLane ln;
+        ln.node = 0; ln.offset = 0; ln.left = 0; ln.parked = 0; ln.moved = false;
+        uint64_t* dst = nodes;
+        if (i < m) {
+            const uint64_t id = __ldg(ids + i);
+            if (id >= ix.sequences) {
+                if (j == 0 && lengths != nullptr) lengths[i] = ~0ull;  // GBWT::sequence() is None
+            } else {
+                const uint64_t len = cv.seq_len[id];
+                if (j == 0 && lengths != nullptr) lengths[i] = len;
+                const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
+                if (j < count) {
+                    const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+                    const uint64_t cap = hi > lo ? hi - lo : 0;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j));
+                    ln.node = raw.x; ln.offset = raw.y;
+                    const uint64_t index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
+                    uint64_t end = len;
+                    if (j + 1 < count) {
+                        const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + first + j + 1));
+                        end = (static_cast<uint64_t>(next.w) << 32) | next.z;
+                    }
+                    if (end > cap) end = cap;  // nothing beyond the caller's slot is written
+                    const uint64_t todo = end > index ? end - index : 0;
+                    ln.left = todo < 0xFFFFFFFFull ? static_cast<uint32_t>(todo) : 0xFFFFFFFFu;
+                    dst = nodes + (lo - base_offset) + index;
+                }
+            }
+        }
+        // windows until every lane is done
+        for (;;) {
+            // where the active lanes are, and which way they walk (node identifiers follow the graph's topological order:
+            // a forward node leads to higher records, a reverse node to lower ones; only a matter of speed if not)
+            __syncthreads();
+            if (tid == 0) { ctrl[2] = 0xFFFFFFFFu; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; }
+            __syncthreads();
+            if (ln.left != 0) {
+                const uint32_t rec = ln.node - base;
+                atomicMin(const_cast<uint32_t*>(&ctrl[2]), rec);
+                atomicMax(const_cast<uint32_t*>(&ctrl[3]), rec);
+                atomicAdd(const_cast<uint32_t*>(&ctrl[(ln.node & 1u) == 0 ? 4 : 5]), 1u);
+            }
+            __syncthreads();
+            const uint32_t lowest = ctrl[2], highest = ctrl[3], up = ctrl[4], down = ctrl[5];
+            if (up + down == 0) break;
+            const uint32_t behind = STAGE_GRANULE;  // records kept behind the slowest lane
+            uint32_t lo;
+            if (up >= down) lo = lowest > behind ? lowest - behind : 0u;
+            else lo = highest + behind + 1u > wp.max_records ? highest + behind + 1u - wp.max_records : 0u;
+            lo &= ~(STAGE_GRANULE - 1u);
+            st.lo = lo;
+            const uint32_t hi = lo + wp.max_records < records ? lo + wp.max_records : records;
+            st.count = hi - lo;
+            const uint32_t origin = base + lo;
+            const uint32_t body_lo = __ldg(ix.stage_body + lo / STAGE_GRANULE);
+            const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
+            const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
+            for (uint32_t r = tid; r < st.count; r += THREADS) {
+                Desc d;
+                load_sector(reinterpret_cast<const Unit16*>(ix.desc + lo + r), d.a, d.b);
+                const Quad skip = load_quad(ix.skips + lo + r);
+                stage_record<false>(st, ix, r, d, skip, origin, body_lo, body_units, nullptr, 0);
+            }
+            for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
+                Quad blo, bhi;
+                load_sector(ix.bodies + body_lo + 2u * blk, blo, bhi);
+                stage_block(st, BLOCK_DENSE2, blk, blo, bhi);
+            }
+            __syncthreads();
+            ln.moved = false;
+            // rounds in this window: walk, write the tile out, until too many lanes are waiting for the next one
+            for (;;) {
+                const bool waiting = extract_round(st, origin, ln, row, descs, bodies, edges, base, records);
+                __syncwarp();
+                // all rows of the warp out, one after the other: up to 256 contiguous bytes per row and store instruction
+                const uint64_t row_addr = reinterpret_cast<uint64_t>(dst);
+#pragma unroll 4
+                for (uint32_t r = 0; r < 32; r++) {
+                    const uint32_t n = __shfl_sync(FULL, ln.parked, r);
+                    const uint32_t a_lo = __shfl_sync(FULL, static_cast<uint32_t>(row_addr), r);
+                    const uint32_t a_hi = __shfl_sync(FULL, static_cast<uint32_t>(row_addr >> 32), r);
+                    uint64_t* to = reinterpret_cast<uint64_t*>((static_cast<uint64_t>(a_hi) << 32) | a_lo);
+                    if (cv.discard) continue;
+                    if (lane < n) __stcs(to + lane, static_cast<uint64_t>(lds32(tile + (r * EXTRACT_TILE_STRIDE + lane) * 4u)));
+                }
+                __syncwarp();
+                dst += ln.parked;
+                ln.parked = 0;
+                const int walking = __syncthreads_count(ln.left != 0);
+                const int stalled = __syncthreads_count(ln.left != 0 && waiting);
+                if (walking == 0 || 8 * stalled >= walking) break;  // next window once an eighth of the walkers wait for it
+            }
+        }
+    }
+}
+
 // Pattern reader of the kernels that keep the chunk in registers (the general loop for deferred queries and the plain
 // 32-bit kernels): same interface, no shared memory.
 template <class T>
@@ -757,6 +1011,42 @@ template <class T>
 void launch_find_deferred(const IndexView& ix, const T* patterns, const uint32_t* deferred, const uint32_t* counters, size_t k,
                           gbwt_b200_state* out, unsigned grid, cudaStream_t stream) {
     k_find_deferred<T><<<grid, BLOCK_THREADS, 0, stream>>>(ix, patterns, deferred, counters, static_cast<uint32_t>(k), out);
+}
+
+// Checkpointed extraction from record windows (k_extract_window): the search plan's window with the margins dropped (the
+// walks only move one way) and a tile of output rows. False: the plan does not fit this index / GPU.
+bool plan_extract_windows(const WindowPlan& search, size_t sequences, WindowPlan& plan) {
+    plan = search;
+    // one CTA of 1024 lanes per SM when the batch has that many sequences (a staged window then serves twice the lanes and is
+    // twice as long), else two CTAs of 512
+    plan.threads = sequences >= 768 && env_or("GBWT_B200_EXTRACT_WINDOW_THREADS", 1024) == 1024 ? 1024u : 512u;
+    plan.aux_cap = 0; plan.wide = 0;
+    const uint32_t tile_bytes = (plan.threads / 32u) * 32u * EXTRACT_TILE_STRIDE * 4u;
+    const uint32_t budget = plan.threads == 1024 ? 224u * 1024u : 112u * 1024u;
+    // records per window: what is left after the tile, at ~(20 + 48 * bodies per record) bytes per record
+    const double per_record = RECORD_BYTES + 48.0 * 0.5 * static_cast<double>(search.body_units) / std::max<double>(1.0, static_cast<double>(search.windows) * (1u << search.wshift));
+    uint32_t max_records = static_cast<uint32_t>((budget - SMEM_HEADER - tile_bytes) / (per_record * 1.15));
+    max_records &= ~(STAGE_GRANULE - 1u);
+    if (max_records < 4 * STAGE_GRANULE) return false;
+    plan.max_records = max_records;
+    plan.margin = 0;
+    const uint32_t fixed = SMEM_HEADER + max_records * RECORD_BYTES + tile_bytes;
+    plan.body_cap = ((budget - fixed) / 48u) * 2u;
+    plan.smem_bytes = fixed + (plan.body_cap / 2u) * 48u;
+    return true;
+}
+
+int launch_extract_window(const IndexView& ix, const CheckpointView& cv, const WindowPlan& plan, const uint64_t* ids, size_t m,
+                          const uint64_t* out_offsets, uint64_t base_offset, uint64_t* nodes, uint64_t* lengths, uint32_t* counters, int sm_count,
+                          cudaStream_t stream) {
+    const bool big = plan.threads == 1024;
+    auto kernel = big ? k_extract_window<1024, 1> : k_extract_window<512, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const uint64_t items = ((m + plan.threads - 1) / plan.threads) * static_cast<uint64_t>(cv.max_segments);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(sm_count) * (big ? 1 : 2)));
+    kernel<<<grid, plan.threads, plan.smem_bytes, stream>>>(ix, cv, plan, ids, m, out_offsets, base_offset, nodes, lengths, counters);
+    return static_cast<int>(cudaGetLastError());
 }
 
 void launch_find_extend_u32(const IndexView& ix, bool runs, const uint32_t* patterns, const uint32_t* perm, size_t n, size_t k,

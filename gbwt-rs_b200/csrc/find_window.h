@@ -55,6 +55,13 @@ template <class T>
 void launch_find_deferred(const IndexView& ix, const T* patterns, const uint32_t* deferred, const uint32_t* counters, size_t k,
                           gbwt_b200_state* out, unsigned grid, cudaStream_t stream);
 
+// Checkpointed path extraction from record windows (find_window.cu: k_extract_window). plan_extract_windows derives its
+// plan from the search plan; counters[0] = work ticket (zero on entry).
+bool plan_extract_windows(const WindowPlan& search, size_t sequences, WindowPlan& plan);
+int launch_extract_window(const IndexView& ix, const CheckpointView& cv, const WindowPlan& plan, const uint64_t* ids, size_t m,
+                          const uint64_t* out_offsets, uint64_t base_offset, uint64_t* nodes, uint64_t* lengths, uint32_t* counters, int sm_count,
+                          cudaStream_t stream);
+
 // Plain (no window) kernels for 32-bit patterns, same dispatch as the 64-bit ones of kernels.cuh.
 void launch_find_extend_u32(const IndexView& ix, bool runs, const uint32_t* patterns, const uint32_t* perm, size_t n, size_t k,
                             gbwt_b200_state* out, unsigned grid, cudaStream_t stream);

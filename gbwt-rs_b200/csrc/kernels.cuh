@@ -1278,7 +1278,7 @@ __global__ void k_node_sequences(IndexView ix, GraphView graph, const uint64_t* 
 // a warp take the same segment number of 32 neighbouring sequences, which in a pangenome walk the same records at the
 // same time (their loads coalesce into a handful of sectors). Every node is still produced by an LF step.
 
-struct Checkpoint { uint32_t node, offset; uint64_t index; };            // position of node number `index` of a sequence
+// (struct Checkpoint and CheckpointView: layout.h)
 struct PoolEntry { uint32_t seq, node, offset, pad; uint64_t index, pad2; };  // as the build walk emits them
 static_assert(sizeof(Checkpoint) == 16 && sizeof(PoolEntry) == 32, "checkpoint records are loaded with vector loads");
 
@@ -1341,14 +1341,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_checkpoint_scatter(const Pool
     }
 }
 
-struct CheckpointView {
-    const Checkpoint* table;
-    const uint32_t* first;     // [sequences + 1]: slots of sequence s are table[first[s] .. first[s + 1])
-    const uint64_t* seq_len;   // [sequences]
-    uint32_t max_segments;     // most checkpoints any sequence has
-    uint32_t discard;          // measurement only (GBWT_B200_EXTRACT_DISCARD=1): walk, but do not store the nodes
-    uint32_t lookahead;        // records ahead of the walks at which a warp touches the index once per round (0 = off)
-};
 
 // Work item (segment j, block of 32 batch entries): lane l walks segment j of sequence ids[32 * block + l] from its
 // checkpoint to the next one (or to the end of the sequence): Record::lf (src/bwt.rs:480-496) per step, two nodes per

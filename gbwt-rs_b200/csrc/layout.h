@@ -115,6 +115,19 @@ struct IndexView {
     const uint32_t* stage_body;
 };
 
+// Path checkpoints (kernels.cuh: k_build_checkpoints): the position of about every `interval`-th node of every sequence,
+// so that a sequence can be extracted as independent segments.
+struct Checkpoint { uint32_t node, offset; uint64_t index; };  // position of node number `index` of a sequence
+static_assert(sizeof(Checkpoint) == 16, "checkpoints are loaded with one vector load");
+struct CheckpointView {
+    const Checkpoint* table;
+    const uint32_t* first;     // [sequences + 1]: slots of sequence s are table[first[s] .. first[s + 1])
+    const uint64_t* seq_len;   // [sequences]
+    uint32_t max_segments;     // most checkpoints any sequence has
+    uint32_t discard;          // measurement only (GBWT_B200_EXTRACT_DISCARD=1): walk, but do not store the nodes
+    uint32_t lookahead;        // records ahead of the walks at which a warp touches the index once per round (0 = off)
+};
+
 // Magic multiplier for q = b / sigma, 0 <= b < 256, 1 <= sigma <= 256: q = (b * magic) >> 16.
 GBWT_HD uint32_t div_magic(uint32_t sigma) { return 65536u / sigma + 1u; }
 

@@ -170,9 +170,11 @@ def test_u32_patterns_without_windows(b200, monkeypatch):
 
 # ---- checkpointed extraction ------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("window", ["0", "2"])   # one-lane walks from global memory / CTAs walking staged record windows
 @pytest.mark.parametrize("shift", [6, 8])
-def test_checkpointed_extraction_matches_chain_walks(b200, shift, monkeypatch):
+def test_checkpointed_extraction_matches_chain_walks(b200, shift, window, monkeypatch):
     monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", str(shift))
+    monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", window)
     S, H, seed = 1500, 48, 9
     img = synth.bubble_chain(S, H, seed)
     g = orc.GBWT.load(img.array)
@@ -206,9 +208,11 @@ def test_checkpointed_extraction_matches_chain_walks(b200, shift, monkeypatch):
         assert np.array_equal(nodes[a:a + n], full[:n]) and np.all(nodes[a + n:b] == 0)
 
 
+@pytest.mark.parametrize("window", ["0", "2"])
 @pytest.mark.parametrize("layout", ["auto", "runs"])
-def test_checkpointed_extraction_on_fixtures_and_random_graphs(b200, layout, monkeypatch):
+def test_checkpointed_extraction_on_fixtures_and_random_graphs(b200, layout, window, monkeypatch):
     monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", "6")
+    monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", window)
     for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
         raw = open(os.path.join(GOLDEN, name), "rb").read()
         g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw, layout=layout, checkpoints=True)
@@ -228,7 +232,9 @@ def test_checkpointed_extraction_on_fixtures_and_random_graphs(b200, layout, mon
         assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
 
 
-def test_checkpoints_on_an_index_with_invalid_edge_targets(b200):
+@pytest.mark.parametrize("window", ["0", "2"])
+def test_checkpoints_on_an_index_with_invalid_edge_targets(b200, window, monkeypatch):
+    monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", window)
     # a damaged index (an edge to a node beyond the alphabet): the build walk and the segment walks take their
     # bounds-checked instantiation and stop where the reference's iterator stops
     edges = [[(1, 0)], [(2, 0), (40, 0)], [(0, 0)]]
@@ -241,6 +247,27 @@ def test_checkpoints_on_an_index_with_invalid_edge_targets(b200):
     o_off, o_nodes = g.extract_batch(ids)
     offsets, nodes, lengths = e.extract(ids)
     assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes) and lengths[2] == np.uint64(2**64 - 1)
+
+
+def test_window_extraction_of_many_sequences(b200, monkeypatch):
+    """Enough sequences for several 512-lane CTAs per segment (the default dispatch), both strands mixed in one batch,
+    tri-allelic sites (records the windows do not decode: those steps come from global memory), slots of every length."""
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", "7")
+    for model in (dict(), dict(alt_ppm=50_000, tri_mod=4)):
+        S, H, seed = 700, 700, 21
+        img = synth.bubble_chain(S, H, seed, **model)
+        g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array, checkpoints=True)
+        assert e.checkpoint_info()["present"]
+        rng = np.random.default_rng(4)
+        ids = rng.permutation(2 * H).astype(np.uint64)
+        ids[5] = np.uint64(2 * H + 3)   # not a sequence
+        o_off, o_nodes = g.extract_batch(ids)
+        offsets, nodes, lengths = e.extract(ids)
+        assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+        monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", "0")
+        offsets0, nodes0, lengths0 = e.extract(ids)
+        monkeypatch.delenv("GBWT_B200_EXTRACT_WINDOW")
+        assert np.array_equal(nodes, nodes0) and np.array_equal(lengths, lengths0)
 
 
 # ---- build once, replicate (CUDA IPC export / import) ----------------------------------------------------------------
