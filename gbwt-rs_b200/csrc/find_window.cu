@@ -640,7 +640,11 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
 // stages the next one. A lane that cannot take a step from the window (its node is not staged, a record format the
 // window does not decode, the end of a sequence) takes that step from the global layout instead, so the result never
 // depends on where the windows fall. Every node is still produced by an LF step (Record::lf, src/bwt.rs:480-496).
-constexpr uint32_t EXTRACT_TILE_NODES = 32, EXTRACT_TILE_STRIDE = 33;  // nodes a lane parks between flushes; row stride in words
+// A lane parks up to 64 nodes between flushes, as 16-bit differences from the first node of the row (a walk stays near
+// where it is; a node that does not fit ends the round early): rows of 64 nodes leave as 512 contiguous bytes, and 256-byte
+// pieces from 150 k rows at a time were what bound the first version (DRAM wrote 54.6 GB at 2.6 TB/s, every piece a page
+// of its own). Row stride: 33 words.
+constexpr uint32_t EXTRACT_TILE_NODES = 64, EXTRACT_TILE_STRIDE = 33;
 
 // One LF step from the global layout: GBWT::forward (src/gbwt.rs:222-229). (offset << 32) | node, 0 = None. Out of line
 // (and therefore without the 256-bit inline-asm load): the rare step must not weigh on the walk's registers.
@@ -688,71 +692,77 @@ struct ExtractLane {
     uint32_t node, offset;  // current position
     uint32_t left;          // nodes of the segment still to be emitted (0 = done)
     uint32_t parked;        // nodes in the tile row
+    uint32_t row_base;      // the tile row holds node - row_base
     bool moved;             // has taken a step from this window
 };
 
-// As many steps as the tile row has room for. A lane that cannot take its next step from the window (its node is not
-// staged, or leads out of the staged range) waits for the next window if it has moved in this one, and otherwise takes
-// the step from the global layout: every window moves every lane. Returns true if the lane is waiting.
+__device__ __forceinline__ bool fits_row(uint32_t node, uint32_t row_base) { return node - row_base + 0x8000u < 0x10000u; }
+__device__ __forceinline__ int32_t lds16_signed(uint32_t a) {
+    int32_t v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// As many steps as the tile row has room for. The inner loop only knows the common step (the node's record is staged
+// and decoded, and so is the record it leads to) and leaves for anything else, which is sorted out per lane below: a
+// lane whose step leads out of the staged range waits for the next window if it has moved in this one, and otherwise
+// takes the step from the global layout, as it does for records the window does not decode and at the end of a
+// sequence -- every window moves every lane. Returns true if the lane is waiting.
 __device__ __forceinline__ bool extract_round(const Staged& st, uint32_t origin, ExtractLane& ln, uint32_t row, const RecordDesc* descs,
                                               const Unit16* bodies, const Edge* edges, uint32_t base, uint32_t records) {
-    while (ln.left != 0 && ln.parked + 2u <= EXTRACT_TILE_NODES) {
-        const uint32_t idx = ln.node - origin;
-        if (idx >= st.count && ln.moved) return true;
-        bool stepped = false, ended = false, leaves = false;  // leaves: the record is staged, the one it leads to is not
-        uint32_t v = 0, next_node = 0, next_offset = 0;  // fast step: the second node of a two-hop step (0: none), the landing position
-        if (idx < st.count) {
+    uint32_t node = ln.node, offset = ln.offset, left = ln.left, at_row = row + 2u * ln.parked;
+    const uint32_t row_end = row + 2u * (EXTRACT_TILE_NODES - 1u);  // room for two nodes below this address
+    if (ln.parked == 0) ln.row_base = node;
+    const uint32_t row_base = ln.row_base;
+    bool waiting = false, moved = ln.moved, full = false;  // full: a node does not fit the row (16-bit differences)
+    for (;;) {
+        bool leaves = false;  // the inner loop left because the step leads out of the staged range (or the node is not staged)
+        while (left != 0 && at_row < row_end) {
+            const uint32_t idx = node - origin;
+            if (idx >= st.count) { leaves = true; break; }
             const uint4 h = lds128(st.rec + 16u * idx);
-            const uint32_t kind = h.y >> 16, total = h.y & 0xFFFFu, at = ln.offset;
-            if (kind < KIND_WIDE || kind == KIND_SINGLE) {
-                if (at >= total) {
-                    ended = true;  // GBWT::forward -> None
-                } else {
-                    uint32_t b = 0, r = at;
-                    if (kind != KIND_SINGLE) {
-                        const uint32_t w = lds32(st.ranks + 4u * (kind + (at >> 4)));
-                        const uint32_t sh = at & 15u;
-                        b = (w >> (16u + sh)) & 1u;
-                        const uint32_t ones = (w & 0xFFFFu) + static_cast<uint32_t>(__popc((w >> 16) & ~(0xFFFFFFFFu << sh)));
-                        r = b ? ones : at - ones;
-                    }
-                    const uint32_t target = b ? h.x >> 16 : h.x & 0xFFFFu, hop = b ? h.w : h.z;
-                    if (target != NODE_OUTSIDE) {
-                        if ((hop & 0xFFFFu) != NODE_OUTSIDE) {
-                            // two nodes: the successor is a single-edge record (layout.h, IndexView::skips)
-                            v = target + origin; next_node = (hop & 0xFFFFu) + origin; next_offset = (hop >> 16) + r;
-                        } else {
-                            next_node = target + origin; next_offset = lds16(st.offs + 4u * idx + 2u * b) + r;
-                        }
-                        stepped = true;
-                    } else {
-                        leaves = true;
-                    }
-                }
+            const uint32_t kind = h.y >> 16, total = h.y & 0xFFFFu;
+            if ((kind >= KIND_WIDE && kind != KIND_SINGLE) || offset >= total) break;  // not decoded here / GBWT::forward -> None
+            uint32_t b = 0, r = offset;
+            if (kind != KIND_SINGLE) {
+                const uint32_t w = lds32(st.ranks + 4u * (kind + (offset >> 4)));
+                const uint32_t sh = offset & 15u;
+                b = (w >> (16u + sh)) & 1u;
+                const uint32_t ones = (w & 0xFFFFu) + static_cast<uint32_t>(__popc((w >> 16) & ~(0xFFFFFFFFu << sh)));
+                r = b ? ones : offset - ones;
             }
-        }
-        if (leaves && ln.moved) return true;  // (the next window will hold the landing record)
-        sts32(row + 4u * ln.parked, ln.node);
-        ln.parked++;
-        if (ended) { ln.left = 0; break; }
-        if (stepped) {
-            if (v != 0) {
-                if (ln.left > 1) { sts32(row + 4u * ln.parked, v); ln.parked++; }
-                ln.left = ln.left > 2 ? ln.left - 2 : 0;
+            const uint32_t target = b ? h.x >> 16 : h.x & 0xFFFFu, hop = b ? h.w : h.z;
+            if (target == NODE_OUTSIDE) { leaves = true; break; }
+            if (!fits_row(node, row_base)) { full = true; break; }  // (only with nodes parked before it: the row starts again here)
+            if (!fits_row(target + origin, row_base)) break;        // (a far jump: one node at a time, below)
+            sts16(at_row, node - row_base);
+            if ((hop & 0xFFFFu) != NODE_OUTSIDE) {
+                // two nodes: the successor is a single-edge record (layout.h, IndexView::skips)
+                if (left > 1) sts16(at_row + 2u, target + origin - row_base);
+                at_row += left > 1 ? 4u : 2u;
+                node = (hop & 0xFFFFu) + origin; offset = (hop >> 16) + r;
+                left = left > 2 ? left - 2 : 0;
             } else {
-                ln.left -= 1;
+                at_row += 2u;
+                node = target + origin; offset = lds16(st.offs + 4u * idx + 2u * b) + r;
+                left -= 1;
             }
-            ln.node = next_node; ln.offset = next_offset;
-            ln.moved = true;
-        } else {
-            const uint64_t next = global_forward(descs, bodies, edges, base, records, ln.node, ln.offset);
-            if (next == 0) { ln.left = 0; break; }
-            ln.node = static_cast<uint32_t>(next); ln.offset = static_cast<uint32_t>(next >> 32);
-            ln.left -= 1;
-            ln.moved = true;
+            moved = true;
         }
+        if (left == 0 || at_row >= row_end || full) break;
+        if (leaves && moved) { waiting = true; break; }
+        // one step from the global layout
+        if (!fits_row(node, row_base)) break;  // (the row is written out and starts again at this node)
+        sts16(at_row, node - row_base);
+        at_row += 2u;
+        const uint64_t next = global_forward(descs, bodies, edges, base, records, node, offset);
+        if (next == 0) { left = 0; break; }
+        node = static_cast<uint32_t>(next); offset = static_cast<uint32_t>(next >> 32);
+        left -= 1;
+        moved = true;
     }
-    return false;
+    ln.node = node; ln.offset = offset; ln.left = left; ln.parked = (at_row - row) / 2u; ln.moved = moved;
+    return waiting;
 }
 
 template <int THREADS, int CTAS>
@@ -789,7 +799,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_extract_window(IndexView ix, 
         const uint64_t j = item / blocks, i = (item - j * blocks) * THREADS + tid;
         // this lane's segment, if it has one (as in k_extract_checkpointed)
         ExtractLane ln;
-        ln.node = 0; ln.offset = 0; ln.left = 0; ln.parked = 0; ln.moved = false;
+        ln.node = 0; ln.offset = 0; ln.left = 0; ln.parked = 0; ln.row_base = 0; ln.moved = false;
         uint64_t* dst = nodes;
         if (i < m) {
             const uint64_t id = __ldg(ids + i);
@@ -822,7 +832,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_extract_window(IndexView ix, 
             // where the active lanes are, and which way they walk (node identifiers follow the graph's topological order:
             // a forward node leads to higher records, a reverse node to lower ones; only a matter of speed if not)
             __syncthreads();
-            if (tid == 0) { ctrl[2] = 0xFFFFFFFFu; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; }
+            if (tid == 0) { ctrl[2] = 0xFFFFFFFFu; ctrl[3] = 0; ctrl[4] = 0; ctrl[5] = 0; ctrl[6] = 0; }
             __syncthreads();
             if (ln.left != 0) {
                 const uint32_t rec = ln.node - base;
@@ -858,27 +868,36 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_extract_window(IndexView ix, 
             }
             __syncthreads();
             ln.moved = false;
-            // rounds in this window: walk, write the tile out, until too many lanes are waiting for the next one
+            // rounds in this window: walk, write the tile out. No barrier between rounds (the warps of a CTA would otherwise
+            // all walk and then all write): a warp leaves for the next window when all of its walkers wait for it, or when an
+            // eighth of the CTA's walkers do (ctrl[6], which only grows while a window lasts).
+            uint32_t reported = 0;
             for (;;) {
                 const bool waiting = extract_round(st, origin, ln, row, descs, bodies, edges, base, records);
                 __syncwarp();
-                // all rows of the warp out, one after the other: up to 256 contiguous bytes per row and store instruction
+                // all rows of the warp out, one after the other: up to 512 contiguous bytes per row, 256 per store instruction
                 const uint64_t row_addr = reinterpret_cast<uint64_t>(dst);
 #pragma unroll 4
                 for (uint32_t r = 0; r < 32; r++) {
                     const uint32_t n = __shfl_sync(FULL, ln.parked, r);
+                    const uint32_t first = __shfl_sync(FULL, ln.row_base, r);
                     const uint32_t a_lo = __shfl_sync(FULL, static_cast<uint32_t>(row_addr), r);
                     const uint32_t a_hi = __shfl_sync(FULL, static_cast<uint32_t>(row_addr >> 32), r);
                     uint64_t* to = reinterpret_cast<uint64_t*>((static_cast<uint64_t>(a_hi) << 32) | a_lo);
                     if (cv.discard) continue;
-                    if (lane < n) __stcs(to + lane, static_cast<uint64_t>(lds32(tile + (r * EXTRACT_TILE_STRIDE + lane) * 4u)));
+                    const uint32_t at = tile + r * (EXTRACT_TILE_STRIDE * 4u) + 2u * lane;
+                    if (lane < n) __stcs(to + lane, static_cast<uint64_t>(first + static_cast<uint32_t>(lds16_signed(at))));
+                    if (lane + 32u < n) __stcs(to + lane + 32u, static_cast<uint64_t>(first + static_cast<uint32_t>(lds16_signed(at + 64u))));
                 }
                 __syncwarp();
                 dst += ln.parked;
                 ln.parked = 0;
-                const int walking = __syncthreads_count(ln.left != 0);
-                const int stalled = __syncthreads_count(ln.left != 0 && waiting);
-                if (walking == 0 || 8 * stalled >= walking) break;  // next window once an eighth of the walkers wait for it
+                const unsigned walkers = __ballot_sync(FULL, ln.left != 0), waiters = __ballot_sync(FULL, ln.left != 0 && waiting);
+                if (walkers == waiters) break;  // (nobody left who could move in this window)
+                const uint32_t stalled = static_cast<uint32_t>(__popc(waiters));
+                if (lane == 0 && stalled > reported) atomicAdd(const_cast<uint32_t*>(&ctrl[6]), stalled - reported);
+                reported = stalled > reported ? stalled : reported;
+                if (8u * ctrl[6] >= up + down) break;
             }
         }
     }
