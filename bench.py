@@ -690,9 +690,11 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         "cold_frac_latency_hbm": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_hbm),
         "cold_frac_latency_l2": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_l2),
         "oracle_checked_paths": oracle_paths,
-        "note": "warm: k_extract_checkpointed, every sequence cut into independent segments at the checkpoints the index was built "
-                "with (build time above; the checkpoints are part of the immutable index, not a cache); a lane makes two dependent "
-                "loads per two-node step, so its latency bound is 1 node per round trip x lanes in flight. cold: a handle created "
+        "note": "warm: every sequence cut into independent segments at the checkpoints the index was built with (build time above; "
+                "the checkpoints are part of the immutable index, not a cache). With 256 or more paths per GPU a CTA takes one "
+                "segment of 512 / 1024 sequences, stages the records they walk in shared memory and the lanes step from there "
+                "(k_extract_window); with fewer, one lane per segment walks from global memory (k_extract_checkpointed: two "
+                "dependent loads per two-node step, latency bound = 1 node per round trip x lanes in flight). cold: a handle created "
                 "without checkpoints, one dependent chain per path (two-hop steps). A path is only walked from both ends once BOTH "
                 "of its strands have been walked whole and their signatures agree; this run extracts the forward strands only, so "
                 "the second cold call repeats the first. frac_bytes = (8-byte nodes written + forward half of the index read once) "

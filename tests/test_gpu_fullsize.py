@@ -64,9 +64,27 @@ def test_full_size_extraction_against_oracle(world, monkeypatch):
     ids = np.array(sorted(set(int(x) for x in np.linspace(0, 2 * H - 1, 16))), dtype=np.uint64)   # both strands
     o_off, o_nodes = g.extract_batch(ids, threads=len(ids))
     assert np.all(np.diff(o_off.astype(np.int64)) == 2 * S + 1)
-    offsets, nodes, lengths = e.extract(ids)                       # checkpointed segments
+    offsets, nodes, lengths = e.extract(ids)                       # checkpointed segments, one lane each from global memory
     assert e.checkpoint_info()["present"]
     assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+    monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", "2")            # checkpointed segments from staged record windows
+    offsets, nodes, lengths = e.extract(ids)
+    assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
+    # ... and the way a large batch takes by default (256 sequences: one CTA per segment): identical to the one-lane walks,
+    # four of the paths compared with the oracle
+    many = np.arange(0, 2 * H, 8, dtype=np.uint64)
+    monkeypatch.delenv("GBWT_B200_EXTRACT_WINDOW")
+    offs_w, nodes_w, _ = e.extract(many)
+    monkeypatch.setenv("GBWT_B200_EXTRACT_WINDOW", "0")
+    offs_0, nodes_0, _ = e.extract(many)
+    monkeypatch.delenv("GBWT_B200_EXTRACT_WINDOW")
+    assert np.array_equal(offs_w, offs_0) and np.array_equal(nodes_w, nodes_0)
+    del nodes_0
+    picks = np.array([0, 85, 170, 255])
+    p_off, p_nodes = g.extract_batch(many[picks], threads=4)
+    for t, k in enumerate(picks):
+        assert np.array_equal(nodes_w[int(offs_w[k]):int(offs_w[k + 1])], p_nodes[int(p_off[t]):int(p_off[t + 1])])
+    del nodes_w
     monkeypatch.setenv("GBWT_B200_EXTRACT_CHECKPOINTS", "0")       # two chains per path (lengths are known to the index)
     offsets, nodes, lengths = e.extract(ids)
     assert np.array_equal(offsets, o_off) and np.array_equal(nodes, o_nodes)
