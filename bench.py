@@ -675,11 +675,13 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         return chains * nodes_per_trip / (latency_cycles / (sm_mhz * 1e6)) * world
 
     cold_chains = m                                   # one warp-wide chain per path, two nodes per dependent load (two-hop shortcuts)
-    warm_chains = min(m * max(1, ckpt["max_segments"]), props.multi_processor_count * 1280)  # lanes resident (5 CTAs of 256 per SM)
+    # lanes resident: 1024 per SM in the window kernel (256 or more paths per GPU), 5 CTAs of 256 in the one-lane kernel
+    warm_chains = min(m * max(1, ckpt["max_segments"]), props.multi_processor_count * (1024 if m >= 256 else 1280))
     out_bytes = total_nodes * 8 + (stats["descriptors"] + stats["bodies"] + stats.get("skips", 0)) // 2 * world
     res = {
         "metric": "gbwt_extract_lf_steps_per_s", "unit": "LF steps/s", "scaling": "strong", "paths_per_gpu": m, "nodes_per_path": length,
         "warm_lf_steps_per_s": total_nodes / (warm_ms / 1e3), "warm_ms": warm_ms,
+        "warm_kernel": "k_extract_window" if m >= 256 else "k_extract_checkpointed",
         "cold_lf_steps_per_s": total_nodes / (cold_first_ms / 1e3), "cold_first_call_ms": cold_first_ms,
         "cold_second_call_lf_steps_per_s": total_nodes / (cold_second_ms / 1e3), "cold_second_call_ms": cold_second_ms,
         "checkpoint_build_s": ckpt["build_us"] / 1e6, "checkpoint_interval": ckpt["interval"], "checkpoint_bytes": ckpt["bytes"],
