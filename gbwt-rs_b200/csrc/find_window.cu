@@ -1036,9 +1036,9 @@ void launch_find_deferred(const IndexView& ix, const T* patterns, const uint32_t
 // walks only move one way) and a tile of output rows. False: the plan does not fit this index / GPU.
 bool plan_extract_windows(const WindowPlan& search, size_t sequences, WindowPlan& plan) {
     plan = search;
-    // one CTA of 1024 lanes per SM when the batch has that many sequences (a staged window then serves twice the lanes and is
-    // twice as long), else two CTAs of 512
-    plan.threads = sequences >= 768 && env_or("GBWT_B200_EXTRACT_WINDOW_THREADS", 1024) == 1024 ? 1024u : 512u;
+    // two CTAs of 512 lanes per SM (measured on config 5: 18.2 ms against 19.3 for one CTA of 1024 lanes, whose window is
+    // twice as long but whose warps all restage at the same time; GBWT_B200_EXTRACT_WINDOW_THREADS=1024 selects it)
+    plan.threads = sequences >= 768 && env_or("GBWT_B200_EXTRACT_WINDOW_THREADS", 512) == 1024 ? 1024u : 512u;
     plan.aux_cap = 0; plan.wide = 0;
     const uint32_t tile_bytes = (plan.threads / 32u) * 32u * EXTRACT_TILE_STRIDE * 4u;
     const uint32_t budget = plan.threads == 1024 ? 224u * 1024u : 112u * 1024u;
