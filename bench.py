@@ -687,8 +687,10 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         "checkpoint_build_s": ckpt["build_us"] / 1e6, "checkpoint_interval": ckpt["interval"], "checkpoint_bytes": ckpt["bytes"],
         "cold_index_build_s": cold_build_s,
         "frac_bytes": out_bytes / (warm_ms / 1e3) / 1e9 / (peak * world),
-        "frac_latency_hbm": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_hbm),
-        "frac_latency_l2": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_l2),
+        # (latency rooflines of the one-lane kernel only: a step of the window kernel is a shared-memory round trip, its bounds
+        # are the bytes it writes and its issue slots)
+        "frac_latency_hbm": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_hbm) if m < 256 else None,
+        "frac_latency_l2": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_l2) if m < 256 else None,
         "cold_frac_latency_hbm": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_hbm),
         "cold_frac_latency_l2": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_l2),
         "oracle_checked_paths": oracle_paths,
