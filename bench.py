@@ -676,12 +676,12 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
 
     cold_chains = m                                   # one warp-wide chain per path, two nodes per dependent load (two-hop shortcuts)
     # lanes resident: 1024 per SM in the window kernel (256 or more paths per GPU), 5 CTAs of 256 in the one-lane kernel
-    warm_chains = min(m * max(1, ckpt["max_segments"]), props.multi_processor_count * (1024 if m >= 256 else 1280))
+    warm_chains = min(m * max(1, ckpt["max_segments"]), props.multi_processor_count * (1024 if m >= 96 else 1280))
     out_bytes = total_nodes * 8 + (stats["descriptors"] + stats["bodies"] + stats.get("skips", 0)) // 2 * world
     res = {
         "metric": "gbwt_extract_lf_steps_per_s", "unit": "LF steps/s", "scaling": "strong", "paths_per_gpu": m, "nodes_per_path": length,
         "warm_lf_steps_per_s": total_nodes / (warm_ms / 1e3), "warm_ms": warm_ms,
-        "warm_kernel": "k_extract_window" if m >= 256 else "k_extract_checkpointed",
+        "warm_kernel": "k_extract_window" if m >= 96 else "k_extract_checkpointed",
         "cold_lf_steps_per_s": total_nodes / (cold_first_ms / 1e3), "cold_first_call_ms": cold_first_ms,
         "cold_second_call_lf_steps_per_s": total_nodes / (cold_second_ms / 1e3), "cold_second_call_ms": cold_second_ms,
         "checkpoint_build_s": ckpt["build_us"] / 1e6, "checkpoint_interval": ckpt["interval"], "checkpoint_bytes": ckpt["bytes"],
@@ -689,14 +689,14 @@ def bench_extract_inline(args, index, image, sites, haplotypes, rank, world, loc
         "frac_bytes": out_bytes / (warm_ms / 1e3) / 1e9 / (peak * world),
         # (latency rooflines of the one-lane kernel only: a step of the window kernel is a shared-memory round trip, its bounds
         # are the bytes it writes and its issue slots)
-        "frac_latency_hbm": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_hbm) if m < 256 else None,
-        "frac_latency_l2": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_l2) if m < 256 else None,
+        "frac_latency_hbm": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_hbm) if m < 96 else None,
+        "frac_latency_l2": total_nodes / (warm_ms / 1e3) / latency_bound(warm_chains, 1.0, lat_l2) if m < 96 else None,
         "cold_frac_latency_hbm": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_hbm),
         "cold_frac_latency_l2": total_nodes / (cold_first_ms / 1e3) / latency_bound(cold_chains, 2.0, lat_l2),
         "oracle_checked_paths": oracle_paths,
         "note": "warm: every sequence cut into independent segments at the checkpoints the index was built with (build time above; "
-                "the checkpoints are part of the immutable index, not a cache). With 256 or more paths per GPU a CTA takes one "
-                "segment of 512 / 1024 sequences, stages the records they walk in shared memory and the lanes step from there "
+                "the checkpoints are part of the immutable index, not a cache). With 96 or more paths per GPU a CTA takes one "
+                "segment of up to 512 sequences, stages the records they walk in shared memory and the lanes step from there "
                 "(k_extract_window); with fewer, one lane per segment walks from global memory (k_extract_checkpointed: two "
                 "dependent loads per two-node step, latency bound = 1 node per round trip x lanes in flight). cold: a handle created "
                 "without checkpoints, one dependent chain per path (two-hop steps). A path is only walked from both ends once BOTH "

@@ -392,13 +392,13 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
         CheckpointView cv = ix->ckpt;
         cv.max_segments = std::max<uint32_t>(1, cv.max_segments);
         cv.discard = env_int("GBWT_B200_EXTRACT_DISCARD", 0) != 0 ? 1u : 0u;
-        // Enough sequences to fill CTAs of 512 lanes on an index that suits record windows: the lanes of a CTA walk the same
+        // Enough sequences to fill CTAs of 128 to 512 lanes on an index that suits record windows: the lanes of a CTA walk the same
         // records, so the CTA stages them in shared memory (find_window.cu: k_extract_window; GBWT_B200_EXTRACT_WINDOW=0
         // keeps the one-lane walks from global memory, =2 forces the windows).
         {
             const int knob = env_int("GBWT_B200_EXTRACT_WINDOW", 1);
             WindowPlan plan;
-            if (knob != 0 && ix->window_ok && (knob == 2 || (ix->window_suits && m >= 256)) && plan_extract_windows(ix->window, m, plan)) {
+            if (knob != 0 && ix->window_ok && (knob == 2 || (ix->window_suits && m >= 96)) && plan_extract_windows(ix->window, m, plan)) {
                 uint32_t* counters = nullptr;
                 CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), sizeof(uint32_t), s));
                 CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t), s));

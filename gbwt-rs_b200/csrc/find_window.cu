@@ -1036,12 +1036,18 @@ void launch_find_deferred(const IndexView& ix, const T* patterns, const uint32_t
 // walks only move one way) and a tile of output rows. False: the plan does not fit this index / GPU.
 bool plan_extract_windows(const WindowPlan& search, size_t sequences, WindowPlan& plan) {
     plan = search;
-    // two CTAs of 512 lanes per SM (measured on config 5: 18.2 ms against 19.3 for one CTA of 1024 lanes, whose window is
-    // twice as long but whose warps all restage at the same time; GBWT_B200_EXTRACT_WINDOW_THREADS=1024 selects it)
-    plan.threads = sequences >= 768 && env_or("GBWT_B200_EXTRACT_WINDOW_THREADS", 512) == 1024 ? 1024u : 512u;
+    // 1024 lanes per SM: two CTAs of 512 lanes (measured on config 5: 18.2 ms against 19.3 for one CTA of 1024 lanes, whose
+    // window is twice as long but whose warps all restage at the same time), and smaller CTAs for smaller batches, so that the
+    // lanes of a CTA are all at work (128 sequences, the share of one of 8 GPUs on config 5: 225 G LF steps/s with four CTAs
+    // of 128 lanes per SM, 210 with CTAs of 256, 195 with a quarter-full CTA of 512, 168 for the one-lane walks; 256
+    // sequences: 283 with half-full CTAs of 512, 277 with CTAs of 256). GBWT_B200_EXTRACT_WINDOW_THREADS overrides.
+    uint32_t threads = sequences >= 192 ? 512u : 128u;
+    const int knob = env_or("GBWT_B200_EXTRACT_WINDOW_THREADS", 0);
+    if (knob == 128 || knob == 256 || knob == 512 || knob == 1024) threads = static_cast<uint32_t>(knob);
+    plan.threads = threads;
     plan.aux_cap = 0; plan.wide = 0;
     const uint32_t tile_bytes = (plan.threads / 32u) * 32u * EXTRACT_TILE_STRIDE * 4u;
-    const uint32_t budget = plan.threads == 1024 ? 224u * 1024u : 112u * 1024u;
+    const uint32_t budget = plan.threads >= 256 ? 224u * plan.threads : 56u * 1024u;  // (four CTAs of 128 lanes per SM: a window needs room)
     // records per window: what is left after the tile, at ~(20 + 48 * bodies per record) bytes per record
     const double per_record = RECORD_BYTES + 48.0 * 0.5 * static_cast<double>(search.body_units) / std::max<double>(1.0, static_cast<double>(search.windows) * (1u << search.wshift));
     uint32_t max_records = static_cast<uint32_t>((budget - SMEM_HEADER - tile_bytes) / (per_record * 1.15));
@@ -1058,12 +1064,12 @@ bool plan_extract_windows(const WindowPlan& search, size_t sequences, WindowPlan
 int launch_extract_window(const IndexView& ix, const CheckpointView& cv, const WindowPlan& plan, const uint64_t* ids, size_t m,
                           const uint64_t* out_offsets, uint64_t base_offset, uint64_t* nodes, uint64_t* lengths, uint32_t* counters, int sm_count,
                           cudaStream_t stream) {
-    const bool big = plan.threads == 1024;
-    auto kernel = big ? k_extract_window<1024, 1> : k_extract_window<512, 2>;
+    auto kernel = plan.threads == 1024 ? k_extract_window<1024, 1> : (plan.threads == 512 ? k_extract_window<512, 2> :
+                  (plan.threads == 256 ? k_extract_window<256, 4> : k_extract_window<128, 4>));
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes));
     if (e != cudaSuccess) return static_cast<int>(e);
     const uint64_t items = ((m + plan.threads - 1) / plan.threads) * static_cast<uint64_t>(cv.max_segments);
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(sm_count) * (big ? 1 : 2)));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(sm_count) * (plan.threads >= 256 ? 1024u / plan.threads : 4u)));
     kernel<<<grid, plan.threads, plan.smem_bytes, stream>>>(ix, cv, plan, ids, m, out_offsets, base_offset, nodes, lengths, counters);
     return static_cast<int>(cudaGetLastError());
 }

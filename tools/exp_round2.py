@@ -20,6 +20,7 @@ ap.add_argument("--extract-plain", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ckpt-shifts", default="")
 ap.add_argument("--extract-threads", default="256")
+ap.add_argument("--paths", type=int, default=0, help="forward paths to extract (default: all)")
 args = ap.parse_args()
 S, H, Q = args.sites, args.haplotypes, args.queries
 t = time.time()
@@ -81,7 +82,7 @@ if args.find:
     del d_pat, d_out, d_pat32
 
 if args.extract:
-    m, length = H, 2 * S + 1
+    m, length = (args.paths or H), 2 * S + 1
     ids = torch.arange(0, m, dtype=torch.int64, device=dev) * 2
     offs = torch.arange(m + 1, dtype=torch.int64, device=dev) * length
     nodes = torch.empty(m * length, dtype=torch.int64, device=dev)
