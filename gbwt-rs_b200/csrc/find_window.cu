@@ -93,12 +93,14 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
     return v;
 }
 
-// One 32-byte sector of pattern nodes, bypassing L1 (every byte is used once).
+// One 32-byte sector of pattern nodes, bypassing L1 (every byte is used once). The loads ask L2 for the whole row (256
+// bytes of 64-bit nodes, 128 of 32-bit nodes: two 16-node segments), so that the second segment's loads find it there
+// instead of paying DRAM latency again (6.34 -> 6.84 G queries/s; prefetching the NEXT 32 rows on top of that is slower).
 __device__ __forceinline__ void load_nodes(const uint64_t* p, uint64_t (&v)[4]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
 }
 __device__ __forceinline__ void load_nodes(const uint32_t* p, uint32_t (&v)[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
 
