@@ -400,6 +400,41 @@ def main():
     find_u32 = {"value": Q * world * len(u32_steps) / (u32_ms / 1e3), "unit": "queries/s", "ms_per_step": u32_ms / len(u32_steps),
                 "api": "gbwt_b200_find_extend_u32_device"}
 
+    # bidirectional searches on the same patterns (config 2's operation at config 4's size): bd_find of a random node of the
+    # pattern, forward extensions to a random end, backward extensions to a random start, fused in one kernel
+    bd = None
+    if args.workload == "find":
+        Qb = min(Q, 1 << 24)
+        gen = torch.Generator(device=dev); gen.manual_seed(11 + rank)
+        first = torch.randint(0, K_LEN, (Qb,), device=dev, generator=gen, dtype=torch.int64)
+        start = (first.double() * torch.rand(Qb, device=dev, generator=gen, dtype=torch.float64)).long()
+        end = first + 1 + ((K_LEN - 1 - first).double() * torch.rand(Qb, device=dev, generator=gen, dtype=torch.float64)).long()
+        offs = torch.arange(Qb + 1, dtype=torch.int64, device=dev) * K_LEN
+        d_bd = torch.empty((Qb, 6), dtype=torch.int64, device=dev)
+        bd_ms, bd_steps, _, _ = timed_steps(lambda: index.bd_search_device(d_pat.data_ptr(), offs.data_ptr(), first.data_ptr(), start.data_ptr(),
+                                                                           end.data_ptr(), Qb, d_bd.data_ptr(), stream), 3, 2)
+        sizes_ok = bool(torch.all(d_bd[:, 2] > d_bd[:, 1]).item()) and bool(torch.equal(d_bd[:, 2] - d_bd[:, 1], d_bd[:, 5] - d_bd[:, 4]))
+        if not sizes_ok:
+            raise SystemExit("bidirectional search: a sampled subpath was not found, or forward and reverse ranges differ in size")
+        bd_checked = 0
+        if rank == 0:
+            from oracle import oracle as orc
+            nb = 20_000
+            gb_oracle = orc.GBWT.load(image, native=True)
+            want_bd = gb_oracle.bd_search_batch(d_pat[:nb].reshape(-1).cpu().numpy().view(np.uint64), (np.arange(nb + 1, dtype=np.uint64) * K_LEN),
+                                                first[:nb].cpu().numpy().view(np.uint64), start[:nb].cpu().numpy().view(np.uint64),
+                                                end[:nb].cpu().numpy().view(np.uint64))
+            if not np.array_equal(d_bd[:nb].cpu().numpy().view(np.uint64).reshape(-1), want_bd.view(np.uint64).reshape(-1)):
+                raise SystemExit("bidirectional search: parity failure against the oracle")
+            bd_checked = nb
+            del gb_oracle
+        extensions = float((end - start - 1).sum().item())
+        bd = {"value": Qb * world * len(bd_steps) / (bd_ms / 1e3), "unit": "searches/s", "ms_per_step": bd_ms / len(bd_steps),
+              "searches_per_gpu_per_step": Qb, "lf_steps_per_s": extensions * world * len(bd_steps) / (bd_ms / 1e3),
+              "api": "gbwt_b200_bd_search_device (bd_find + extend_forward* + extend_backward*, src/gbwt.rs:311-384)",
+              "parity": f"every range non-empty and forward / reverse sizes equal on the full batch; first {bd_checked} searches bit-exact against the CPU oracle"}
+        del first, start, end, offs, d_bd
+
     # end to end through the host C ABI with pinned buffers (H2D + kernels + D2H inside the timed region), both widths
     e2e = None
     if not args.no_e2e:
@@ -470,7 +505,7 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, sites, haplotypes, Q, "inputs and outputs resident in HBM"),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "extra": {"lf_steps_per_s": value * K_LEN, "find_u32": find_u32, "extract": extract, "find_runs": find_runs,
+            "extra": {"lf_steps_per_s": value * K_LEN, "find_u32": find_u32, "bd_search": bd, "extract": extract, "find_runs": find_runs,
                       "occurrences_checksum": checksum, "index_device_bytes": stats, "index_build_s": build_s,
                       "checkpoints": ckpt, "window": {k: w1[k] for k in ("window_records", "margin", "threads", "smem_bytes", "windows")},
                       "step_ms": step_ms, "arithmetic": "u64 node identifiers and offsets at the ABI, 32-bit inside the kernels "

@@ -346,6 +346,24 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
                      cudaStream_t s) {
     if (n == 0) return GBWT_B200_OK;
     uint32_t* perm = nullptr;
+    // Record windows (find_window.cu: k_bd_window): the batch sorted by the window of path[first], the searches answered from
+    // shared memory, what a window cannot decide finished by the general loop.
+    WindowPlan plan;
+    if (wants_locality(ix, n) && wants_windows(ix) && (n >= 8 * static_cast<size_t>(ix->window.windows) || env_int("GBWT_B200_FIND_WINDOW", 1) == 2) &&
+        env_int("GBWT_B200_BD_WINDOW", 1) != 0 && plan_bd_windows(ix->window, plan)) {
+        uint32_t *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
+        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
+            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);
+        }, &perm, static_cast<int>(plan.wshift), &bucket_end, &scratch);
+        if (rc != GBWT_B200_OK) return rc;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+        const int e = launch_bd_window(ix->view, plan, nodes, offsets, base, first, start, end, perm, bucket_end, out, scratch, counters, ix->sm_count, s);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        cudaFreeAsync(perm, s); cudaFreeAsync(bucket_end, s); cudaFreeAsync(scratch, s); cudaFreeAsync(counters, s);
+        if (e != 0) return cuda_fail(static_cast<cudaError_t>(e), "k_bd_window");
+        return GBWT_B200_OK;
+    }
     if (wants_locality(ix, n)) {
         int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
             k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);

@@ -917,6 +917,236 @@ struct PlainRowReader {
     }
 };
 
+// ---- bidirectional search from record windows ------------------------------------------------------------------------
+// bd_find(path[first]) + extend_forward over path(first, end) + extend_backward over path[start, first) (the driver of
+// src/gbwt/tests.rs:352-361 over src/gbwt.rs:311-384), with the records in shared memory like the search above. The batch
+// is sorted by the window of path[first]; a warp takes 32 searches, reads the nodes path[start, end) of each into a tile of
+// 32 lines (window indexes, one line per position; longer subpaths go to the general kernel) and every lane runs the two
+// phases on it: forward extensions up the tile, then -- a backward extension by x is a forward extension of the flipped
+// state by flip(x), src/gbwt.rs:362-367 -- the same loop down the tile on the other strand's records, which lie next to
+// this strand's in record order. Per step the half being extended moves like GBWT::extend, the other half's range start
+// moves by the number of positions of the range whose successor precedes the extension in the reverse order
+// (Record::bd_follow, src/bwt.rs:621-656): for a record with two edges that is all the ones, all the zeros or nothing,
+// depending on the edge taken and on whether the two successors are the two orientations of one node. Records the window
+// does not decode, nodes it does not hold and subpaths longer than the tile put the search on the deferred list.
+constexpr uint32_t BD_TILE_LINES = 32, BD_TILE_BYTES = (BD_TILE_LINES + 2u) * TILE_LINE;  // one sentinel line either side
+
+// One phase: extends half `a` (at window index idx, record entry h) by the tile lines from `pat` in direction `dir` (+1 /
+// -1 lines) for `count` nodes, flipping each node when `flip` (the backward phase); `b_start` is the other half's start.
+// Returns QUERY_ACTIVE when all extensions were made.
+__device__ __forceinline__ uint32_t bd_window_phase(const Staged& st, uint32_t origin, uint32_t pat, int32_t dir, uint32_t count, bool flip,
+                                                    uint32_t& idx, uint32_t& a_start, uint32_t& a_end, uint32_t& b_start) {
+    const uint32_t parity = origin & 1u;
+    const int32_t line = dir * static_cast<int32_t>(TILE_LINE);
+    uint32_t left = count;
+    if (left == 0) return QUERY_ACTIVE;
+    uint4 h = lds128(st.rec + 16u * idx);
+    while (left != 0) {
+        uint32_t x1 = lds16(pat), x2 = left > 1 ? lds16(pat + line) : NODE_OUTSIDE;
+        if (flip) {
+            // flip(node) as a window index: the other orientation's record is the neighbour (node ^ 1)
+            x1 = x1 == NODE_OUTSIDE ? x1 : ((x1 + parity) ^ 1u) - parity;
+            x2 = x2 == NODE_OUTSIDE ? x2 : ((x2 + parity) ^ 1u) - parity;
+            if (x1 >= st.count) x1 = NODE_OUTSIDE;
+            if (x2 >= st.count) x2 = NODE_OUTSIDE;
+        }
+        if (x1 == NODE_OUTSIDE) return QUERY_DEFER;
+        const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
+        const uint32_t s = a_start < total ? a_start : total, e = a_end < total ? a_end : total;
+        if (s >= e) return QUERY_NONE;
+        const uint32_t t0 = h.x & 0xFFFFu, t1 = h.x >> 16;
+        uint32_t b = 0, rs = s, re = e, flipped = 0;
+        if (kind < KIND_WIDE) {
+            b = x1 == t1 ? 1u : 0u;
+            if (x1 != t0 && b == 0) return QUERY_NONE;
+            if (t0 == NODE_OUTSIDE || t1 == NODE_OUTSIDE) return QUERY_DEFER;  // (cannot tell whether the successors are one node's two orientations)
+            const uint32_t last = e - 1u;
+            const uint32_t ws = lds32(st.ranks + 4u * (kind + (s >> 4))), we = lds32(st.ranks + 4u * (kind + (last >> 4)));
+            const uint32_t ones_s = (ws & 0xFFFFu) + static_cast<uint32_t>(__popc((ws >> 16) & ~(0xFFFFFFFFu << (s & 15u))));
+            const uint32_t ones_e = (we & 0xFFFFu) + static_cast<uint32_t>(__popc((we >> 16) & ~(0xFFFFFFFEu << (last & 15u))));
+            rs = b ? ones_s : s - ones_s;
+            re = b ? ones_e : e - ones_e;
+            if (rs >= re) return QUERY_NONE;
+            // Record::bd_follow's second value: edge 0 is preceded (in the reverse order) by edge 1 only when both lead to the
+            // same node and edge 0 to its forward orientation; edge 1 by edge 0 unless that is the case
+            const bool paired = t1 == t0 + 1u && ((t0 + origin) & 1u) == 0;
+            const uint32_t ones = ones_e - ones_s, zeros = (e - s) - ones;
+            flipped = b == 0 ? (paired ? ones : 0u) : (paired ? 0u : zeros);
+        } else if (kind == KIND_SINGLE) {
+            if (x1 != t0) return QUERY_NONE;
+        } else {
+            return kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;
+        }
+        b_start += flipped;
+        const uint32_t hop = b ? h.w : h.z;
+        uint32_t offset;
+        if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
+            // two extensions at once: the second one is over a single-edge record, which moves neither range start
+            offset = hop >> 16; idx = x2; pat += 2 * line; left -= 2;
+        } else {
+            offset = lds16(st.offs + 4u * idx + 2u * b); idx = x1; pat += line; left -= 1;
+        }
+        a_start = offset + rs; a_end = offset + re;
+        if (left == 0) break;
+        h = lds128(st.rec + 16u * idx);
+    }
+    return QUERY_ACTIVE;
+}
+
+template <int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, WindowPlan wp, const uint64_t* __restrict__ nodes,
+                                                              const uint64_t* __restrict__ offsets, uint64_t base_offset,
+                                                              const uint64_t* __restrict__ first, const uint64_t* __restrict__ start,
+                                                              const uint64_t* __restrict__ end, const uint32_t* __restrict__ perm,
+                                                              const uint32_t* __restrict__ bucket_end, gbwt_b200_bdstate* __restrict__ out,
+                                                              uint32_t* __restrict__ deferred, uint32_t* __restrict__ counters) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    extern __shared__ __align__(128) unsigned char smem[];
+    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem);  // [0] window ticket, [1] next query slot
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    Staged st;
+    st.rec = smem_addr(smem) + SMEM_HEADER;
+    st.offs = st.rec + 16u * wp.max_records;
+    st.aux = st.offs + 4u * wp.max_records;
+    st.kinds = st.aux;
+    st.ranks = st.aux;
+    uint32_t tile = st.ranks + (wp.body_cap / 2u) * 48u + (tid >> 5) * BD_TILE_BYTES;
+    asm volatile("" : "+r"(st.rec), "+r"(st.offs), "+r"(st.ranks), "+r"(tile));
+    const uint32_t slot = tile + 2u * lane;  // line 0 is the sentinel below the first node, data in lines 1 .. 32
+    sts16(slot, NODE_OUTSIDE);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { ctrl[0] = atomicAdd(&counters[0], 1u); ctrl[1] = 0; }
+        __syncthreads();
+        const uint32_t w = ctrl[0];
+        if (w >= wp.windows) break;
+        const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1u), q_end = __ldg(bucket_end + w);
+        if (q_begin >= q_end) continue;
+        uint32_t at = 0;
+        if (lane == 0) at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+        at = __shfl_sync(FULL, at, 0);
+        const uint32_t r0 = w << wp.wshift;
+        st.lo = r0 > wp.margin ? r0 - wp.margin : 0u;
+        const uint32_t want_hi = r0 + (1u << wp.wshift) + wp.margin;
+        const uint32_t hi = want_hi < records ? want_hi : records;
+        st.count = hi - st.lo;
+        const uint32_t origin = base + st.lo;
+        const uint32_t body_lo = __ldg(ix.stage_body + st.lo / STAGE_GRANULE);
+        const uint32_t body_hi = __ldg(ix.stage_body + (hi + STAGE_GRANULE - 1u) / STAGE_GRANULE);
+        const uint32_t body_units = body_hi - body_lo < wp.body_cap ? body_hi - body_lo : wp.body_cap;
+        for (uint32_t r = tid; r < st.count; r += THREADS) {
+            Desc d;
+            load_sector(reinterpret_cast<const Unit16*>(ix.desc + st.lo + r), d.a, d.b);
+            const Quad skip = load_quad(ix.skips + st.lo + r);
+            stage_record<false>(st, ix, r, d, skip, origin, body_lo, body_units, nullptr, 0);
+        }
+        for (uint32_t blk = tid; blk < body_units / 2u; blk += THREADS) {
+            Quad blo, bhi;
+            load_sector(ix.bodies + body_lo + 2u * blk, blo, bhi);
+            stage_block(st, BLOCK_DENSE2, blk, blo, bhi);
+        }
+        __syncthreads();
+        while (at < q_end) {
+            const bool mine = at + lane < q_end;
+            const uint32_t q = mine ? __ldg(perm + at + lane) : 0u;
+            // this lane's search: nodes path[begin, finish) of its path, bd_find at `anchor`
+            uint32_t status = QUERY_NONE, begin = 0, length = 0, anchor = 0;
+            const uint64_t* row = nullptr;
+            if (mine) {
+                const uint64_t lo = __ldg(offsets + q), hi_off = __ldg(offsets + q + 1);
+                const uint64_t len = hi_off > lo ? hi_off - lo : 0;
+                const uint64_t f = __ldg(first + q), s = __ldg(start + q), e = __ldg(end + q);
+                if (s <= f && f < e && e <= len && len <= 0xFFFFFFFFull) {  // (else None, like query_bd_search_fast)
+                    status = e - s <= BD_TILE_LINES ? QUERY_ACTIVE : QUERY_DEFER;
+                    begin = static_cast<uint32_t>(s); length = static_cast<uint32_t>(e - s); anchor = static_cast<uint32_t>(f - s);
+                    row = nodes + (lo - base_offset) + s;
+                }
+            }
+            // the tile: line 1 + t = node t of every row's subpath, NODE_OUTSIDE beyond its end; one row per iteration, lanes = positions
+            const unsigned long long my_row = reinterpret_cast<unsigned long long>(status == QUERY_ACTIVE ? row : nullptr);
+            // (eight rows requested before the first one is narrowed: the rows of a sorted batch are scattered over HBM)
+#pragma unroll 1
+            for (uint32_t r0 = 0; r0 < 32; r0 += 8) {
+                uint64_t loaded[8];
+                bool have[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) {
+                    const uint64_t* p = reinterpret_cast<const uint64_t*>(__shfl_sync(FULL, my_row, r0 + j));
+                    const uint32_t n = __shfl_sync(FULL, length, r0 + j);
+                    have[j] = p != nullptr;
+                    loaded[j] = 0;
+                    if (have[j] && lane < n) loaded[j] = __ldg(p + lane);
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) {
+                    // (beyond the end of a subpath `loaded` is node 0, which is no record of any window: NODE_OUTSIDE)
+                    if (have[j]) sts16(tile + ((1u + lane) * TILE_PITCH + r0 + j) * 2u, loaded[j] == 0 ? NODE_OUTSIDE : pattern_index(loaded[j], origin, st.count));
+                }
+            }
+            if (status == QUERY_ACTIVE) sts16(slot + (1u + BD_TILE_LINES) * TILE_LINE, NODE_OUTSIDE);
+            __syncwarp();
+            (void)begin;
+            uint32_t f_idx = 0, f_start = 0, f_end = 0, r_idx = 0, r_start = 0, r_end = 0;
+            if (status == QUERY_ACTIVE) {
+                // bd_find (src/gbwt.rs:311-324)
+                const uint32_t at_anchor = slot + (1u + anchor) * TILE_LINE;
+                const uint32_t x0 = lds16(at_anchor);
+                const uint32_t parity = origin & 1u;
+                const uint32_t x0_flip = x0 == NODE_OUTSIDE ? x0 : ((x0 + parity) ^ 1u) - parity;
+                if (x0 == NODE_OUTSIDE || x0 + st.lo == 0 || x0_flip >= st.count) status = QUERY_DEFER;
+                else {
+                    const uint2 h = lds64(st.rec + 16u * x0);
+                    const uint32_t kind = h.y >> 16, total = h.y & 0xFFFFu;
+                    if (kind == KIND_DEFER) status = QUERY_DEFER;
+                    else if (kind == KIND_EMPTY || total == 0) status = QUERY_NONE;
+                    else {
+                        f_idx = x0; f_start = 0; f_end = total; r_idx = x0_flip; r_start = 0; r_end = total;
+                        // forward extensions by path(first, end): `a` = forward half, `b` = reverse half
+                        status = bd_window_phase(st, origin, at_anchor + TILE_LINE, 1, length - anchor - 1u, false, f_idx, f_start, f_end, r_start);
+                        r_end = r_start + (f_end - f_start);
+                        if (status == QUERY_ACTIVE && anchor > 0) {
+                            // backward extensions by path[start, first) in descending order: forward extensions of the flipped state
+                            status = bd_window_phase(st, origin, at_anchor - TILE_LINE, -1, anchor, true, r_idx, r_start, r_end, f_start);
+                            f_end = f_start + (r_end - r_start);
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // the tile is rewritten for the next 32 searches
+            if (mine) {
+                if (status == QUERY_DEFER) {
+                    deferred[atomicAdd(&counters[1], 1u)] = q;
+                } else {
+                    const bool found = status == QUERY_ACTIVE;
+                    gbwt_b200_bdstate result;
+                    result.forward.node = found ? f_idx + origin : 0u; result.forward.start = found ? f_start : 0u; result.forward.end = found ? f_end : 0u;
+                    result.reverse.node = found ? r_idx + origin : 0u; result.reverse.start = found ? r_start : 0u; result.reverse.end = found ? r_end : 0u;
+                    out[q] = result;
+                }
+            }
+            if (lane == 0) at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
+            at = __shfl_sync(FULL, at, 0);
+        }
+    }
+}
+
+// The deferred searches, by the general loop.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bd_deferred(IndexView ix, const uint64_t* __restrict__ nodes, const uint64_t* __restrict__ offsets,
+                                                                uint64_t base_offset, const uint64_t* __restrict__ first,
+                                                                const uint64_t* __restrict__ start, const uint64_t* __restrict__ end,
+                                                                const uint32_t* __restrict__ deferred, const uint32_t* __restrict__ counters,
+                                                                gbwt_b200_bdstate* __restrict__ out) {
+    const uint32_t n = counters[1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t q = __ldg(deferred + i);
+        const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
+        gbwt_b200_bdstate result;
+        query_bd_search_fast<true>(ix, nodes + (lo - base_offset), hi > lo ? hi - lo : 0, __ldg(first + q), __ldg(start + q), __ldg(end + q), result);
+        out[q] = result;
+    }
+}
+
 // The deferred queries, by the general rounds loop (every record format, every edge case).
 template <class T>
 __global__ void __launch_bounds__(BLOCK_THREADS) k_find_deferred(IndexView ix, const T* __restrict__ patterns,
@@ -1073,6 +1303,34 @@ int launch_extract_window(const IndexView& ix, const CheckpointView& cv, const W
     const uint64_t items = ((m + plan.threads - 1) / plan.threads) * static_cast<uint64_t>(cv.max_segments);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(sm_count) * (plan.threads >= 256 ? 1024u / plan.threads : 4u)));
     kernel<<<grid, plan.threads, plan.smem_bytes, stream>>>(ix, cv, plan, ids, m, out_offsets, base_offset, nodes, lengths, counters);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// Bidirectional searches from record windows (k_bd_window) + the deferred ones by the general loop. The plan is the search
+// plan with a tile of 34 lines per warp; false from plan_bd_windows: it does not fit.
+bool plan_bd_windows(const WindowPlan& search, WindowPlan& plan) {
+    plan = search;
+    if (plan.threads != 512) return false;
+    plan.aux_cap = 0; plan.wide = 0;
+    const uint32_t fixed = SMEM_HEADER + plan.max_records * RECORD_BYTES + (plan.threads / 32u) * BD_TILE_BYTES;
+    const uint32_t budget = 112u * 1024u;
+    if (fixed + 8192u > budget) return false;
+    plan.body_cap = std::min<uint32_t>(search.body_cap, ((budget - fixed) / 48u) * 2u);
+    plan.smem_bytes = fixed + (plan.body_cap / 2u) * 48u;
+    return true;
+}
+
+int launch_bd_window(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, const uint64_t* offsets, uint64_t base_offset,
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint32_t* bucket_end,
+                     gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count, cudaStream_t stream) {
+    auto kernel = k_bd_window<512, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(plan.windows, static_cast<uint64_t>(sm_count) * 2));
+    kernel<<<grid, 512, plan.smem_bytes, stream>>>(ix, plan, nodes, offsets, base_offset, first, start, end, perm, bucket_end, out, deferred, counters);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    k_bd_deferred<<<static_cast<unsigned>(sm_count) * 4, BLOCK_THREADS, 0, stream>>>(ix, nodes, offsets, base_offset, first, start, end, deferred, counters, out);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -93,6 +93,55 @@ def test_window_kernel_pattern_lengths(b200, k, monkeypatch):
     assert w1["deferred"] - w0["deferred"] < len(pats) // 4    # ... and mostly stayed there
 
 
+# ---- bidirectional searches from record windows (k_bd_window) ---------------------------------------------------------
+
+@pytest.mark.parametrize("layout", ["auto", "runs"])
+def test_bd_window_kernel_on_fixtures_and_random_graphs(b200, layout, monkeypatch):
+    """Every (first, start, end) of every sequence (src/gbwt/tests.rs:365-462) with the window kernel forced: fixtures (two
+    orientations of a node among a record's successors, empty records), random graphs with high outdegrees (deferred)."""
+    force_windows(monkeypatch)
+    for name in ("example.gbwt", "with-empty.gbwt", "translation.gbz"):
+        raw = open(os.path.join(GOLDEN, name), "rb").read()
+        g, e = orc.GBWT.load(raw), b200.GBWT.from_bytes(raw, layout=layout)
+        assert pc.check_bd(e, g) > 0
+    from test_hostsim_layout import random_paths
+    from test_run_checkpoints import sparse_paths
+    for seed in range(6):
+        rng = random.Random(300 + seed)
+        paths = sparse_paths(rng, rng.choice([6, 10, 40]), rng.choice([50, 200])) if seed % 2 else \
+            random_paths(rng, n_nodes=rng.choice([3, 12, 40]), n_paths=rng.choice([10, 40]), max_len=rng.choice([8, 40, 70]))
+        if not any(paths):
+            paths.append([2, 4])
+        img = image_of(gb.build_bwt(gb.bidirectional_sequences(paths)))
+        g, e = orc.GBWT.load(img), b200.GBWT.from_bytes(img, layout=layout)
+        pc.check_bd(e, g)
+
+
+@pytest.mark.parametrize("model", [dict(), dict(alt_ppm=50_000, tri_mod=4)])
+def test_bd_window_kernel_on_bubble_chains(b200, model, monkeypatch):
+    """Random (first, start, end) on sampled subpaths of a bubble chain: paired successors never occur here, plain bubbles
+    always; subpaths longer than the tile and tri-allelic sites (records the window does not decode) are deferred; damaged
+    paths fail where the oracle fails."""
+    force_windows(monkeypatch)
+    S, H, seed = 3000, 64, 17
+    img = synth.bubble_chain(S, H, seed, **model)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    rng = np.random.default_rng(8)
+    for k in (32, 9, 40):
+        n = 40_000
+        pats = synth.patterns(S, H, seed, n=n, k=k, **model)
+        bad = rng.integers(0, n, n // 10)
+        pats[bad, rng.integers(0, k, len(bad))] ^= np.uint64(1)
+        first = rng.integers(0, k, size=n).astype(np.uint64)
+        start = (first * rng.random(n)).astype(np.uint64)
+        end = (first + 1 + ((k - first - 1) * rng.random(n)).astype(np.uint64)).astype(np.uint64)
+        offs = np.arange(n + 1, dtype=np.uint64) * k
+        flat = pats.reshape(-1)
+        want = g.bd_search_batch(flat, offs, first, start, end)
+        assert pc.states_equal(e.bd_search(flat, offs, first, start, end), want)
+        assert np.count_nonzero(want["forward"]["end"] > want["forward"]["start"]) > n // 2
+
+
 def test_window_kernel_edge_cases(b200, monkeypatch):
     force_windows(monkeypatch)
     S, H, seed = 400, 40, 17

@@ -10,7 +10,7 @@ python - <<PY
 import json
 d=json.loads(open("gpurun_out/r2_bench_n$N.json").read().strip().splitlines()[-1])
 print("value", d["value"]/1e9, "ms", d["ms_per_step"], "e2e", d["e2e"]["value"]/1e9, "u64 e2e", d["e2e"]["u64"]["value"]/1e9, "wire", d["e2e"]["wire_bound_queries_per_s"]/1e9)
-print("u32", d["extra"]["find_u32"]["value"]/1e9, "build_s", d["extra"]["index_build_s"])
+print("u32", d["extra"]["find_u32"]["value"]/1e9, "build_s", d["extra"]["index_build_s"], "bd", d["extra"]["bd_search"] and (d["extra"]["bd_search"]["value"]/1e9, d["extra"]["bd_search"]["lf_steps_per_s"]/1e9))
 x=d["extra"]["extract"]; print("extract warm", x["warm_lf_steps_per_s"]/1e9, "cold", x["cold_lf_steps_per_s"]/1e9, x["frac_bytes"], x["frac_latency_hbm"])
 r=d["extra"]["find_runs"]; print("runs", r["value"]/1e9, r["ms_per_step"], r["deferred_queries_per_step"], r["window_kernel_ms"])
 print("roofline", {k:v for k,v in (d["roofline"] or {}).items() if k in ("traffic","frac","compulsory_frac","compulsory_frac_kernel_only","launch_ms","step_ms")})
