@@ -404,7 +404,7 @@ def main():
     # pattern, forward extensions to a random end, backward extensions to a random start, fused in one kernel
     bd = None
     if args.workload == "find":
-        Qb = min(Q, 1 << 24)
+        Qb = Q
         gen = torch.Generator(device=dev); gen.manual_seed(11 + rank)
         first = torch.randint(0, K_LEN, (Qb,), device=dev, generator=gen, dtype=torch.int64)
         start = (first.double() * torch.rand(Qb, device=dev, generator=gen, dtype=torch.float64)).long()

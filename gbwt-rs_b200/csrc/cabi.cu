@@ -12,6 +12,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/gbwt_b200.h"
@@ -162,9 +163,10 @@ bool wants_locality(const gbwt_b200_index* ix, size_t n) {
 // expensive (20 M counters and fully scattered slot writes), a net loss.
 // `fixed_shift` >= 0: buckets of exactly 2^fixed_shift records (the record windows of find_window.cu). `bucket_end`, when
 // asked for, receives the array whose entry b is the end of bucket b's slots in perm (the caller frees it).
-template <class WriteKeys>
+struct DefaultScatter {};
+template <class WriteKeys, class Scatter = DefaultScatter>
 int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, WriteKeys write_keys, uint32_t** perm,
-                        int fixed_shift = -1, uint32_t** bucket_end = nullptr, uint32_t** keys_out = nullptr) {
+                        int fixed_shift = -1, uint32_t** bucket_end = nullptr, uint32_t** keys_out = nullptr, Scatter* scatter = nullptr) {
     const uint64_t max_buckets = static_cast<uint64_t>(std::max(1, env_int("GBWT_B200_BUCKETS", 1 << 18)));
     const uint64_t want_buckets = std::min<uint64_t>(max_buckets, std::max<uint64_t>(256, n / 256));
     uint32_t shift = 0;
@@ -189,7 +191,9 @@ int build_locality_perm(const gbwt_b200_index* ix, size_t n, cudaStream_t s, Wri
         k_scan_add<<<tiles, 1024, 0, s>>>(counts, m, tile_sums);
         launch_done("k_scan_add");
     }
-    k_bucket_scatter<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts, *perm);
+    // (`scatter`: the caller's own placement kernel, which writes more than the permutation)
+    if constexpr (std::is_same<Scatter, DefaultScatter>::value) k_bucket_scatter<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(keys, n, counts, *perm);
+    else (*scatter)(keys, counts, *perm);
     int rc = launch_done("k_bucket_scatter");
     if (bucket_end != nullptr) *bucket_end = counts;  // after the scatter, counts[b] = end of bucket b
     else cudaFreeAsync(counts, s);
@@ -352,15 +356,21 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
     if (wants_locality(ix, n) && wants_windows(ix) && (n >= 8 * static_cast<size_t>(ix->window.windows) || env_int("GBWT_B200_FIND_WINDOW", 1) == 2) &&
         env_int("GBWT_B200_BD_WINDOW", 1) != 0 && plan_bd_windows(ix->window, plan)) {
         uint32_t *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
+        uint4* packed = nullptr;  // per search, in sorted order: where its subpath starts, its length, the position of `first` in it
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&packed), n * sizeof(uint4), s));
+        auto place = [&](const uint32_t* keys, uint32_t* cursor, uint32_t* perm_out) {
+            launch_bd_place(keys, n, cursor, perm_out, offsets, base, first, start, end, packed, grid_for(ix, n), s);
+        };
         int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
             k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);
-        }, &perm, static_cast<int>(plan.wshift), &bucket_end, &scratch);
-        if (rc != GBWT_B200_OK) return rc;
+        }, &perm, static_cast<int>(plan.wshift), &bucket_end, &scratch, &place);
+        if (rc != GBWT_B200_OK) { cudaFreeAsync(packed, s); return rc; }
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
         CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-        const int e = launch_bd_window(ix->view, plan, nodes, offsets, base, first, start, end, perm, bucket_end, out, scratch, counters, ix->sm_count, s);
+        const int e = launch_bd_window(ix->view, plan, nodes, offsets, base, first, start, end, perm, packed, bucket_end, out, scratch, counters,
+                                       ix->sm_count, s);
         g_launches.fetch_add(2, std::memory_order_relaxed);
-        cudaFreeAsync(perm, s); cudaFreeAsync(bucket_end, s); cudaFreeAsync(scratch, s); cudaFreeAsync(counters, s);
+        cudaFreeAsync(perm, s); cudaFreeAsync(bucket_end, s); cudaFreeAsync(scratch, s); cudaFreeAsync(counters, s); cudaFreeAsync(packed, s);
         if (e != 0) return cuda_fail(static_cast<cudaError_t>(e), "k_bd_window");
         return GBWT_B200_OK;
     }

@@ -998,9 +998,11 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
                                                               const uint64_t* __restrict__ offsets, uint64_t base_offset,
                                                               const uint64_t* __restrict__ first, const uint64_t* __restrict__ start,
                                                               const uint64_t* __restrict__ end, const uint32_t* __restrict__ perm,
-                                                              const uint32_t* __restrict__ bucket_end, gbwt_b200_bdstate* __restrict__ out,
-                                                              uint32_t* __restrict__ deferred, uint32_t* __restrict__ counters) {
+                                                              const uint4* __restrict__ packed, const uint32_t* __restrict__ bucket_end,
+                                                              gbwt_b200_bdstate* __restrict__ out, uint32_t* __restrict__ deferred,
+                                                              uint32_t* __restrict__ counters) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    (void)offsets; (void)first; (void)start; (void)end;  // (read by the placement step, which left what is needed in `packed`)
     extern __shared__ __align__(128) unsigned char smem[];
     volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem);  // [0] window ticket, [1] next query slot
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -1051,16 +1053,14 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
             const bool mine = at + lane < q_end;
             const uint32_t q = mine ? __ldg(perm + at + lane) : 0u;
             // this lane's search: nodes path[begin, finish) of its path, bd_find at `anchor`
-            uint32_t status = QUERY_NONE, begin = 0, length = 0, anchor = 0;
+            uint32_t status = QUERY_NONE, length = 0, anchor = 0;
             const uint64_t* row = nullptr;
             if (mine) {
-                const uint64_t lo = __ldg(offsets + q), hi_off = __ldg(offsets + q + 1);
-                const uint64_t len = hi_off > lo ? hi_off - lo : 0;
-                const uint64_t f = __ldg(first + q), s = __ldg(start + q), e = __ldg(end + q);
-                if (s <= f && f < e && e <= len && len <= 0xFFFFFFFFull) {  // (else None, like query_bd_search_fast)
-                    status = e - s <= BD_TILE_LINES ? QUERY_ACTIVE : QUERY_DEFER;
-                    begin = static_cast<uint32_t>(s); length = static_cast<uint32_t>(e - s); anchor = static_cast<uint32_t>(f - s);
-                    row = nodes + (lo - base_offset) + s;
+                const uint4 rec = __ldg(packed + at + lane);
+                if (rec.z != 0) {  // (else None, like query_bd_search_fast)
+                    status = rec.z <= BD_TILE_LINES ? QUERY_ACTIVE : QUERY_DEFER;
+                    length = rec.z; anchor = rec.w;
+                    row = nodes + ((static_cast<uint64_t>(rec.y) << 32) | rec.x);
                 }
             }
             // the tile: line 1 + t = node t of every row's subpath, NODE_OUTSIDE beyond its end; one row per iteration, lanes = positions
@@ -1086,7 +1086,6 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
             }
             if (status == QUERY_ACTIVE) sts16(slot + (1u + BD_TILE_LINES) * TILE_LINE, NODE_OUTSIDE);
             __syncwarp();
-            (void)begin;
             uint32_t f_idx = 0, f_start = 0, f_end = 0, r_idx = 0, r_start = 0, r_end = 0;
             if (status == QUERY_ACTIVE) {
                 // bd_find (src/gbwt.rs:311-324)
@@ -1128,6 +1127,26 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
             if (lane == 0) at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
             at = __shfl_sync(FULL, at, 0);
         }
+    }
+}
+
+// The placement step of the sort for bidirectional searches (see find_window.h).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bd_place(const uint32_t* __restrict__ keys, size_t n, uint32_t* __restrict__ cursor,
+                                                             uint32_t* __restrict__ perm, const uint64_t* __restrict__ offsets, uint64_t base_offset,
+                                                             const uint64_t* __restrict__ first, const uint64_t* __restrict__ start,
+                                                             const uint64_t* __restrict__ end, uint4* __restrict__ packed) {
+    for (size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
+        const uint64_t len = hi > lo ? hi - lo : 0;
+        const uint64_t f = __ldg(first + q), s = __ldg(start + q), e = __ldg(end + q);
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (s <= f && f < e && e <= len && len <= 0xFFFFFFFFull) {
+            const uint64_t at = (lo - base_offset) + s;
+            rec = make_uint4(static_cast<uint32_t>(at), static_cast<uint32_t>(at >> 32), static_cast<uint32_t>(e - s), static_cast<uint32_t>(f - s));
+        }
+        const uint32_t slot = atomicAdd(cursor + __ldg(keys + q), 1u);
+        perm[slot] = static_cast<uint32_t>(q);
+        packed[slot] = rec;
     }
 }
 
@@ -1320,14 +1339,21 @@ bool plan_bd_windows(const WindowPlan& search, WindowPlan& plan) {
     return true;
 }
 
+void launch_bd_place(const uint32_t* keys, size_t n, uint32_t* cursor, uint32_t* perm, const uint64_t* offsets, uint64_t base_offset,
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, uint4* packed, unsigned grid, cudaStream_t stream) {
+    k_bd_place<<<grid, BLOCK_THREADS, 0, stream>>>(keys, n, cursor, perm, offsets, base_offset, first, start, end, packed);
+}
+
 int launch_bd_window(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, const uint64_t* offsets, uint64_t base_offset,
-                     const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint32_t* bucket_end,
-                     gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count, cudaStream_t stream) {
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint4* packed,
+                     const uint32_t* bucket_end, gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count,
+                     cudaStream_t stream) {
     auto kernel = k_bd_window<512, 2>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes));
     if (e != cudaSuccess) return static_cast<int>(e);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(plan.windows, static_cast<uint64_t>(sm_count) * 2));
-    kernel<<<grid, 512, plan.smem_bytes, stream>>>(ix, plan, nodes, offsets, base_offset, first, start, end, perm, bucket_end, out, deferred, counters);
+    kernel<<<grid, 512, plan.smem_bytes, stream>>>(ix, plan, nodes, offsets, base_offset, first, start, end, perm, packed, bucket_end, out, deferred,
+                                                   counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     k_bd_deferred<<<static_cast<unsigned>(sm_count) * 4, BLOCK_THREADS, 0, stream>>>(ix, nodes, offsets, base_offset, first, start, end, deferred, counters, out);

@@ -65,9 +65,15 @@ int launch_extract_window(const IndexView& ix, const CheckpointView& cv, const W
 // Bidirectional searches from record windows (find_window.cu: k_bd_window, then k_bd_deferred for what it could not
 // decide). perm / bucket_end: the batch sorted by the window of path[first]; counters as for launch_find_window.
 bool plan_bd_windows(const WindowPlan& search, WindowPlan& plan);
+// launch_bd_place is the placement step of the sort for these batches: besides perm[slot] = q it writes packed[slot] =
+// {element offset of path[start] in `nodes` (two words), end - start, first - start} (length 0: the search is None), so that
+// the window kernel reads one coalesced 16-byte record per search instead of five scattered 8-byte values.
+void launch_bd_place(const uint32_t* keys, size_t n, uint32_t* cursor, uint32_t* perm, const uint64_t* offsets, uint64_t base_offset,
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, uint4* packed, unsigned grid, cudaStream_t stream);
 int launch_bd_window(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, const uint64_t* offsets, uint64_t base_offset,
-                     const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint32_t* bucket_end,
-                     gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count, cudaStream_t stream);
+                     const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint4* packed,
+                     const uint32_t* bucket_end, gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count,
+                     cudaStream_t stream);
 
 // Plain (no window) kernels for 32-bit patterns, same dispatch as the 64-bit ones of kernels.cuh.
 void launch_find_extend_u32(const IndexView& ix, bool runs, const uint32_t* patterns, const uint32_t* perm, size_t n, size_t k,
