@@ -1,22 +1,26 @@
-// find_window.cu -- GBWT::find + extends (src/gbwt.rs:269-304 over Record::follow, src/bwt.rs:595-616) with the
-// records in shared memory.
+// find_window.cu -- the record-window kernels: GBWT::find + extends (src/gbwt.rs:269-304 over Record::follow,
+// src/bwt.rs:595-616), bidirectional searches (src/gbwt.rs:311-384) and checkpointed path extraction (Record::lf,
+// src/bwt.rs:480-496) with the records in shared memory.
 //
 // After the locality sort the queries of one bucket all start inside one window of consecutive records, and a
 // pattern stays close to its first record (node identifiers follow the graph's topological order). So a CTA takes a
-// window, stages the window plus a margin either side -- descriptors, two-hop shortcuts and the contiguous range of
-// bodies, three cp.async.bulk copies completing on one mbarrier -- and its threads resolve the window's queries from
-// shared memory: a dependent step costs a shared-memory round trip (~30 cycles) instead of an L2 / HBM one
-// (300 / 800), the index is read from HBM once per batch in large sequential pieces, and the only scattered global
-// accesses left are each query's own pattern row and its 24-byte result.
+// window, decodes the window plus a margin either side -- descriptors, two-hop shortcuts and the contiguous range of
+// bodies -- into tables laid out for the search loop (16-bit window-relative fields, one 4-byte entry per 16 positions
+// of a bitvector), and its warps resolve the window's queries from shared memory: a dependent step costs a
+// shared-memory round trip (~30 cycles) instead of an L2 / HBM one (300 / 800), the index is read from HBM once per
+// batch in large sequential pieces, and the only scattered global accesses left are the pattern rows (read by a warp
+// together, whole lines at a time) and the results. (The first version staged the raw records with cp.async.bulk and an
+// mbarrier and read them in their global layout; the bank conflicts of that layout are why the window is decoded
+// instead: profiles/r2_find_window_v1_tma_raw_layout_ncu.txt.)
 //
 // Per step: the record u of the current node, the pattern node x1 (which must equal one of u's edge targets), and --
 // the two-hop shortcut of layout.h -- if the successor over that edge is a single-edge record whose only target is the
 // pattern node after x1, both nodes are consumed at once without looking at the successor's record. A bubble
-// (SNP / indel site) is therefore ONE step: descriptor + shortcut + one or two 64-bit words of the bitvector.
+// (SNP / indel site) is therefore ONE step: one 16-byte record entry and one or two 4-byte rank entries.
 //
 // Anything the window cannot answer exactly -- a record outside the staged range, a body that did not fit, a record
-// that is neither single-edge nor dense -- puts the query on a deferred list, and the general kernel finishes the
-// list afterwards. Results are therefore always those of the general kernel; the window only makes the common case fast.
+// format it does not decode -- puts the query on a deferred list, and the general kernel finishes the list
+// afterwards. Results are therefore always those of the general kernel; the window only makes the common case fast.
 #include "find_window.h"
 
 #include <algorithm>

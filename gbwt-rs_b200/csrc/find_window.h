@@ -9,8 +9,8 @@
 namespace gbwt_b200 {
 
 // How a batch is cut into record windows. One bucket of the locality sort = one window of 2^wshift records; a CTA
-// stages the window plus `margin` records either side (descriptors, two-hop shortcuts and the contiguous bodies)
-// into shared memory with bulk copies and resolves the window's queries from there.
+// decodes the window plus `margin` records either side (descriptors, two-hop shortcuts and the contiguous bodies)
+// into shared memory and resolves the window's queries from there.
 struct WindowPlan {
     uint32_t wshift;       // log2(records per window)
     uint32_t margin;       // records staged before and after the window (multiple of STAGE_GRANULE)
