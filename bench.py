@@ -792,17 +792,20 @@ def bench_extract(args, index, image, sites, haplotypes, rank, world, local_rank
         per_step = g.extract_bytes(sample_ids) / (len(sample_ids) * length)
         peak, src = measured_peak_gbs()
         achieved = per_step * haplotypes * length / world / (total_ms / args.steps / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_extract_split", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": src, "algorithmic_bytes_per_lf_step": per_step,
-                    "note": "a path walk is a dependent chain: the bound that matters is chains in flight / access latency"}
+        kernel = ("k_extract_window" if m >= 96 else "k_extract_checkpointed") if index.checkpoint_info()["present"] else "k_extract"
+        written = haplotypes * length * 8 / world / (total_ms / args.steps / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": written, "peak": peak, "unit": "GB/s", "frac": written / peak,
+                    "traffic": None, "peak_source": src, "algorithmic_bytes_per_lf_step": per_step, "algorithmic_x": achieved / peak,
+                    "note": "achieved = 8-byte nodes written / time (what the checkpointed kernels are bound by); algorithmic_x = SURVEY.md "
+                            "8(d)'s bytes on the reference's compressed records / time / peak. A walk without checkpoints is a dependent "
+                            "chain: its bound is chains in flight / access latency (extra.extract of the default run)"}
     return {"metric": "gbwt_extract_lf_steps_per_s", "value": value, "unit": "LF steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"extraction of all {haplotypes} forward haplotype paths ({length} nodes each) of the "
                                    f"{3 * sites + 1}-node bubble-chain GBWT", "baseline_config": "BASELINE.json configs[4]",
                        "paths_per_gpu": m, "layout": args.layout,
-                       "note": "path lengths are known to the index after the first (warm-up) extraction, so every path is "
-                               "walked from both ends (k_extract_split)"},
+                       "note": "the index carries path checkpoints (built at load): every sequence is extracted as independent segments"},
             "gpu_launches": gb.kernel_launches() - launches0, "roofline": roofline, "clocks": clocks,
             "extra": {"index_device_bytes": stats}}
 
