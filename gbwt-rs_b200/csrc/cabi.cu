@@ -259,20 +259,34 @@ int launch_find_extend(const gbwt_b200_index* ix, const T* patterns, size_t n, s
             // Record windows: one bucket of the sort = one window; the window kernel answers from shared memory and
             // lists what it could not decide, the general kernel finishes the list.
             uint32_t *perm = nullptr, *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
-            int rc = build_locality_perm(ix, count, s, [&](uint32_t, uint32_t* keys, uint32_t* counts) {
-                launch_window_keys<T>(ix->view, ix->window, part, count, k, keys, counts, grid_for(ix, count), s);
-            }, &perm, static_cast<int>(ix->window.wshift - ix->window.fine), &bucket_end, &scratch);
-            if (rc != GBWT_B200_OK) return rc;
-            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
-            CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-            const bool stats = env_int("GBWT_B200_WINDOW_STATS", 0) != 0;
-            cudaEvent_t t0 = nullptr, t1 = nullptr;
-            if (stats && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) { cudaGetLastError(); t0 = t1 = nullptr; }
-            if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t0, s);
             // margins for this batch's pattern length (the windows themselves, and with them the sort, stay the same)
             WindowPlan plan = ix->window;
             if (k != 32 && !plan_windows(ix->view, plan.body_units, plan.edge_span, plan.wide != 0, static_cast<uint32_t>(std::min<size_t>(k, 4096)), plan))
                 plan = ix->window;
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+            int rc = GBWT_B200_OK;
+            const uint64_t cap = std::max<uint64_t>(64, 2 * ((count + plan.windows - 1) / plan.windows));
+            if (env_int("GBWT_B200_WINDOW_DIRECT", 1) != 0 && cap * plan.windows <= 0xFFFFFFFFull) {
+                // one pass: every window owns `cap` slots, a query takes the next free one of its window (or is deferred)
+                plan.direct_cap = static_cast<uint32_t>(cap);
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&bucket_end), plan.windows * sizeof(uint32_t), s));
+                CUDA_TRY(cudaMemsetAsync(bucket_end, 0, plan.windows * sizeof(uint32_t), s));
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm), cap * plan.windows * sizeof(uint32_t), s));
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), count * sizeof(uint32_t), s));
+                launch_window_place_direct<T>(ix->view, plan, part, count, k, bucket_end, perm, scratch, counters, grid_for(ix, count), s);
+                rc = launch_done("k_window_place_direct");
+            } else {
+                plan.direct_cap = 0;
+                rc = build_locality_perm(ix, count, s, [&](uint32_t, uint32_t* keys, uint32_t* counts) {
+                    launch_window_keys<T>(ix->view, ix->window, part, count, k, keys, counts, grid_for(ix, count), s);
+                }, &perm, static_cast<int>(ix->window.wshift - ix->window.fine), &bucket_end, &scratch);
+            }
+            if (rc != GBWT_B200_OK) return rc;
+            const bool stats = env_int("GBWT_B200_WINDOW_STATS", 0) != 0;
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (stats && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) { cudaGetLastError(); t0 = t1 = nullptr; }
+            if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t0, s);
             const int e = launch_find_window<T>(ix->view, plan, part, perm, bucket_end, count, k, out + begin, scratch, counters, ix->sm_count, s);
             if (t0 != nullptr && t1 != nullptr) cudaEventRecord(t1, s);
             if (e != 0) rc = cuda_fail(static_cast<cudaError_t>(e), "k_find_window");
@@ -357,16 +371,31 @@ int launch_bd_search(const gbwt_b200_index* ix, const uint64_t* nodes, const uin
         env_int("GBWT_B200_BD_WINDOW", 1) != 0 && plan_bd_windows(ix->window, plan)) {
         uint32_t *bucket_end = nullptr, *scratch = nullptr, *counters = nullptr;
         uint4* packed = nullptr;  // per search, in sorted order: where its subpath starts, its length, the position of `first` in it
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&packed), n * sizeof(uint4), s));
-        auto place = [&](const uint32_t* keys, uint32_t* cursor, uint32_t* perm_out) {
-            launch_bd_place(keys, n, cursor, perm_out, offsets, base, first, start, end, packed, grid_for(ix, n), s);
-        };
-        int rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
-            k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);
-        }, &perm, static_cast<int>(plan.wshift), &bucket_end, &scratch, &place);
-        if (rc != GBWT_B200_OK) { cudaFreeAsync(packed, s); return rc; }
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&counters), 2 * sizeof(uint32_t), s));
         CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+        const uint64_t cap = std::max<uint64_t>(64, 2 * ((n + plan.windows - 1) / plan.windows));
+        int rc = GBWT_B200_OK;
+        if (env_int("GBWT_B200_WINDOW_DIRECT", 1) != 0 && cap * plan.windows <= 0xFFFFFFFFull) {
+            // one pass: every window owns `cap` slots, a search takes the next free one of its window (or is deferred)
+            plan.direct_cap = static_cast<uint32_t>(cap);
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&bucket_end), plan.windows * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMemsetAsync(bucket_end, 0, plan.windows * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&perm), cap * plan.windows * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&packed), cap * plan.windows * sizeof(uint4), s));
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n * sizeof(uint32_t), s));
+            launch_bd_place_direct(ix->view, plan, nodes, n, bucket_end, perm, offsets, base, first, start, end, packed, scratch, counters, grid_for(ix, n), s);
+            rc = launch_done("k_bd_place_direct");
+        } else {
+            plan.direct_cap = 0;
+            CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&packed), n * sizeof(uint4), s));
+            auto place = [&](const uint32_t* keys, uint32_t* cursor, uint32_t* perm_out) {
+                launch_bd_place(keys, n, cursor, perm_out, offsets, base, first, start, end, packed, grid_for(ix, n), s);
+            };
+            rc = build_locality_perm(ix, n, s, [&](uint32_t shift, uint32_t* keys, uint32_t* counts) {
+                k_keys_ragged<<<grid_for(ix, n), BLOCK_THREADS, 0, s>>>(ix->view, nodes, offsets, base, first, n, shift, keys, counts);
+            }, &perm, static_cast<int>(plan.wshift), &bucket_end, &scratch, &place);
+        }
+        if (rc != GBWT_B200_OK) { cudaFreeAsync(packed, s); cudaFreeAsync(counters, s); return rc; }
         const int e = launch_bd_window(ix->view, plan, nodes, offsets, base, first, start, end, perm, packed, bucket_end, out, scratch, counters,
                                        ix->sm_count, s);
         g_launches.fetch_add(2, std::memory_order_relaxed);

@@ -551,10 +551,18 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_find_window(IndexView ix, Win
         __syncthreads();
         const uint32_t w = ctrl[0];
         if (w >= wp.windows) break;
-        // (bucket_end[] has one entry per sort bucket, 2^fine of them per window)
-        const uint32_t fine_buckets = ((records - 1u) >> (wp.wshift - wp.fine)) + 1u, after = (w + 1u) << wp.fine;
-        const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + (w << wp.fine) - 1u);
-        const uint32_t q_end = __ldg(bucket_end + (after < fine_buckets ? after : fine_buckets) - 1u);
+        uint32_t q_begin, q_end;
+        if (wp.direct_cap != 0) {
+            // one-pass placement (k_window_place_direct): window w owns the slots [w cap, (w + 1) cap) of perm, bucket_end[w] = its count
+            const uint32_t filled = __ldg(bucket_end + w);
+            q_begin = w * wp.direct_cap;
+            q_end = q_begin + (filled < wp.direct_cap ? filled : wp.direct_cap);
+        } else {
+            // (bucket_end[] has one entry per sort bucket, 2^fine of them per window)
+            const uint32_t fine_buckets = ((records - 1u) >> (wp.wshift - wp.fine)) + 1u, after = (w + 1u) << wp.fine;
+            q_begin = w == 0 ? 0u : __ldg(bucket_end + (w << wp.fine) - 1u);
+            q_end = __ldg(bucket_end + (after < fine_buckets ? after : fine_buckets) - 1u);
+        }
         if (q_begin >= q_end) continue;
         // Queries are handed out 32 at a time per warp; with wp.prefetch the pattern rows of a warp's NEXT 32 queries are
         // requested from L2 before it works on the current ones.
@@ -1027,7 +1035,15 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
         __syncthreads();
         const uint32_t w = ctrl[0];
         if (w >= wp.windows) break;
-        const uint32_t q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1u), q_end = __ldg(bucket_end + w);
+        uint32_t q_begin, q_end;
+        if (wp.direct_cap != 0) {  // (one-pass placement: window w owns perm / packed [w cap, (w + 1) cap), bucket_end[w] = its count)
+            const uint32_t filled = __ldg(bucket_end + w);
+            q_begin = w * wp.direct_cap;
+            q_end = q_begin + (filled < wp.direct_cap ? filled : wp.direct_cap);
+        } else {
+            q_begin = w == 0 ? 0u : __ldg(bucket_end + w - 1u);
+            q_end = __ldg(bucket_end + w);
+        }
         if (q_begin >= q_end) continue;
         uint32_t at = 0;
         if (lane == 0) at = q_begin + atomicAdd(const_cast<uint32_t*>(&ctrl[1]), 32u);
@@ -1154,6 +1170,36 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_place(const uint32_t* __re
     }
 }
 
+// The same in one pass (see k_window_place_direct): the window of path[first] is computed here, every window owns `cap`
+// slots, a search that finds its window full goes to the deferred list.
+__global__ void __launch_bounds__(BLOCK_THREADS) k_bd_place_direct(IndexView ix, uint32_t wshift, const uint64_t* __restrict__ nodes, size_t n,
+                                                                    uint32_t cap, uint32_t* __restrict__ filled, uint32_t* __restrict__ perm,
+                                                                    const uint64_t* __restrict__ offsets, uint64_t base_offset,
+                                                                    const uint64_t* __restrict__ first, const uint64_t* __restrict__ start,
+                                                                    const uint64_t* __restrict__ end, uint4* __restrict__ packed,
+                                                                    uint32_t* __restrict__ deferred, uint32_t* __restrict__ counters) {
+    for (size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint64_t lo = __ldg(offsets + q), hi = __ldg(offsets + q + 1);
+        const uint64_t len = hi > lo ? hi - lo : 0;
+        const uint64_t f = __ldg(first + q), s = __ldg(start + q), e = __ldg(end + q);
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t b = 0;
+        if (s <= f && f < e && e <= len && len <= 0xFFFFFFFFull) {
+            const uint64_t at = (lo - base_offset) + s;
+            rec = make_uint4(static_cast<uint32_t>(at), static_cast<uint32_t>(at >> 32), static_cast<uint32_t>(e - s), static_cast<uint32_t>(f - s));
+            uint64_t record;
+            if (record_of(ix, __ldg(nodes + (lo - base_offset) + f), record)) b = static_cast<uint32_t>(record >> wshift);
+        }
+        const uint32_t slot = atomicAdd(filled + b, 1u);
+        if (slot < cap) {
+            perm[static_cast<size_t>(b) * cap + slot] = static_cast<uint32_t>(q);
+            packed[static_cast<size_t>(b) * cap + slot] = rec;
+        } else {
+            deferred[atomicAdd(&counters[1], 1u)] = static_cast<uint32_t>(q);
+        }
+    }
+}
+
 // The deferred searches, by the general loop.
 __global__ void __launch_bounds__(BLOCK_THREADS) k_bd_deferred(IndexView ix, const uint64_t* __restrict__ nodes, const uint64_t* __restrict__ offsets,
                                                                 uint64_t base_offset, const uint64_t* __restrict__ first,
@@ -1182,6 +1228,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS) k_find_deferred(IndexView ix, c
         gbwt_b200_state result;
         query_find_extend_rounds<true>(ix, rd, k, result);
         store_state(out + q, result);
+    }
+}
+
+// One-pass placement: the batch is not sorted exactly; every window owns `cap` slots (twice its share of the batch) and a
+// query takes the next free slot of the window of its first node -- one pass over the first nodes, one returning atomic,
+// no keys array, no scan. A query that finds its window full goes to the deferred list (a batch that crowds one part of
+// the graph is then mostly answered by the general kernel, as it would be without windows).
+template <class T>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_window_place_direct(IndexView ix, uint32_t wshift, const T* __restrict__ patterns, size_t n, size_t k,
+                                                                        uint32_t cap, uint32_t* __restrict__ filled, uint32_t* __restrict__ slots,
+                                                                        uint32_t* __restrict__ deferred, uint32_t* __restrict__ counters) {
+    for (size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint64_t node = first_node(patterns, q, k);
+        uint64_t rec;
+        const uint32_t b = record_of(ix, node, rec) ? static_cast<uint32_t>(rec >> wshift) : 0u;
+        const uint32_t at = atomicAdd(filled + b, 1u);
+        if (at < cap) slots[static_cast<size_t>(b) * cap + at] = static_cast<uint32_t>(q);
+        else deferred[atomicAdd(&counters[1], 1u)] = static_cast<uint32_t>(q);
     }
 }
 
@@ -1272,6 +1336,12 @@ void launch_window_keys(const IndexView& ix, const WindowPlan& plan, const T* pa
 }
 
 template <class T>
+void launch_window_place_direct(const IndexView& ix, const WindowPlan& plan, const T* patterns, size_t n, size_t k, uint32_t* filled,
+                                uint32_t* slots, uint32_t* deferred, uint32_t* counters, unsigned grid, cudaStream_t stream) {
+    k_window_place_direct<T><<<grid, BLOCK_THREADS, 0, stream>>>(ix, plan.wshift, patterns, n, k, plan.direct_cap, filled, slots, deferred, counters);
+}
+
+template <class T>
 int launch_find_window(const IndexView& ix, const WindowPlan& plan, const T* patterns, const uint32_t* perm,
                        const uint32_t* bucket_end, size_t n, size_t k, gbwt_b200_state* out, uint32_t* deferred,
                        uint32_t* counters, int sm_count, cudaStream_t stream) {
@@ -1348,6 +1418,13 @@ void launch_bd_place(const uint32_t* keys, size_t n, uint32_t* cursor, uint32_t*
     k_bd_place<<<grid, BLOCK_THREADS, 0, stream>>>(keys, n, cursor, perm, offsets, base_offset, first, start, end, packed);
 }
 
+void launch_bd_place_direct(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, size_t n, uint32_t* filled, uint32_t* perm,
+                            const uint64_t* offsets, uint64_t base_offset, const uint64_t* first, const uint64_t* start, const uint64_t* end,
+                            uint4* packed, uint32_t* deferred, uint32_t* counters, unsigned grid, cudaStream_t stream) {
+    k_bd_place_direct<<<grid, BLOCK_THREADS, 0, stream>>>(ix, plan.wshift, nodes, n, plan.direct_cap, filled, perm, offsets, base_offset, first, start, end,
+                                                          packed, deferred, counters);
+}
+
 int launch_bd_window(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, const uint64_t* offsets, uint64_t base_offset,
                      const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint4* packed,
                      const uint32_t* bucket_end, gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count,
@@ -1370,6 +1447,10 @@ void launch_find_extend_u32(const IndexView& ix, bool runs, const uint32_t* patt
     else k_find_extend_u32<false><<<grid, BLOCK_THREADS, 0, stream>>>(ix, patterns, perm, n, k, out);
 }
 
+template void launch_window_place_direct<uint64_t>(const IndexView&, const WindowPlan&, const uint64_t*, size_t, size_t, uint32_t*, uint32_t*, uint32_t*,
+                                                   uint32_t*, unsigned, cudaStream_t);
+template void launch_window_place_direct<uint32_t>(const IndexView&, const WindowPlan&, const uint32_t*, size_t, size_t, uint32_t*, uint32_t*, uint32_t*,
+                                                   uint32_t*, unsigned, cudaStream_t);
 template void launch_window_keys<uint64_t>(const IndexView&, const WindowPlan&, const uint64_t*, size_t, size_t, uint32_t*, uint32_t*, unsigned, cudaStream_t);
 template void launch_window_keys<uint32_t>(const IndexView&, const WindowPlan&, const uint32_t*, size_t, size_t, uint32_t*, uint32_t*, unsigned, cudaStream_t);
 template int launch_find_window<uint64_t>(const IndexView&, const WindowPlan&, const uint64_t*, const uint32_t*, const uint32_t*, size_t, size_t,

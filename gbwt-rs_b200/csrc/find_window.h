@@ -22,6 +22,7 @@ struct WindowPlan {
     uint32_t prefetch;     // ask L2 for the pattern rows of a warp's next 32 queries (GBWT_B200_WINDOW_PREFETCH)
     float edge_span;       // what the plan was made from (a batch of patterns of another length is planned again)
     uint64_t body_units;
+    uint32_t direct_cap;   // 0: perm is sorted exactly; else window w owns perm[w cap .. (w + 1) cap) (one-pass placement, set per launch)
     uint32_t wide;         // 1: the instantiation that also decodes DENSE4 / byte-per-run records
     uint32_t aux_cap;      // wide records (up to four edges, DENSE4 or byte-per-run body) a window can hold
     uint32_t fine;         // the sort's buckets are 2^(wshift - fine) records: 2^fine buckets per window, so that the queries a
@@ -42,6 +43,12 @@ bool plan_windows(const IndexView& ix, uint64_t body_units, double edge_span, bo
 template <class T>
 void launch_window_keys(const IndexView& ix, const WindowPlan& plan, const T* patterns, size_t n, size_t k, uint32_t* keys,
                         uint32_t* counts, unsigned grid, cudaStream_t stream);
+
+// One-pass placement for the window search (plan.direct_cap slots per window, filled[w] = queries that asked for window w,
+// zero on entry): see k_window_place_direct. Queries that find their window full are appended to `deferred` (counters[1]).
+template <class T>
+void launch_window_place_direct(const IndexView& ix, const WindowPlan& plan, const T* patterns, size_t n, size_t k, uint32_t* filled,
+                                uint32_t* slots, uint32_t* deferred, uint32_t* counters, unsigned grid, cudaStream_t stream);
 
 // The search itself. bucket_end[w] = end of window w's slots in perm (what the scatter leaves in the cursor array);
 // counters[0] = window ticket, counters[1] = number of deferred queries (both zero on entry); queries the window
@@ -70,6 +77,10 @@ bool plan_bd_windows(const WindowPlan& search, WindowPlan& plan);
 // the window kernel reads one coalesced 16-byte record per search instead of five scattered 8-byte values.
 void launch_bd_place(const uint32_t* keys, size_t n, uint32_t* cursor, uint32_t* perm, const uint64_t* offsets, uint64_t base_offset,
                      const uint64_t* first, const uint64_t* start, const uint64_t* end, uint4* packed, unsigned grid, cudaStream_t stream);
+// The same as a one-pass placement with plan.direct_cap slots per window (see launch_window_place_direct).
+void launch_bd_place_direct(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, size_t n, uint32_t* filled, uint32_t* perm,
+                            const uint64_t* offsets, uint64_t base_offset, const uint64_t* first, const uint64_t* start, const uint64_t* end,
+                            uint4* packed, uint32_t* deferred, uint32_t* counters, unsigned grid, cudaStream_t stream);
 int launch_bd_window(const IndexView& ix, const WindowPlan& plan, const uint64_t* nodes, const uint64_t* offsets, uint64_t base_offset,
                      const uint64_t* first, const uint64_t* start, const uint64_t* end, const uint32_t* perm, const uint4* packed,
                      const uint32_t* bucket_end, gbwt_b200_bdstate* out, uint32_t* deferred, uint32_t* counters, int sm_count,

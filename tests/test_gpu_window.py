@@ -142,6 +142,40 @@ def test_bd_window_kernel_on_bubble_chains(b200, model, monkeypatch):
         assert np.count_nonzero(want["forward"]["end"] > want["forward"]["start"]) > n // 2
 
 
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_window_placement_of_a_crowded_batch(b200, direct, monkeypatch):
+    """A batch whose queries all start in a few windows: with the one-pass placement (every window owns twice its share of
+    the batch) most of them find their window full and are finished by the general kernels; with the exact sort they all
+    fit. Same results either way, for find/extend and for bidirectional searches."""
+    force_windows(monkeypatch)
+    monkeypatch.setenv("GBWT_B200_WINDOW_DIRECT", direct)
+    S, H, seed = 6000, 64, 31
+    img = synth.bubble_chain(S, H, seed)
+    g, e = orc.GBWT.load(img.array), b200.GBWT.from_bytes(img.array)
+    assert e.window_info()["windows"] >= 32
+    n, k = 60_000, 32
+    rng = np.random.default_rng(12)
+    seqs = [synth.sequence(S, H, seed, i) for i in range(8)]
+    pats = np.empty((n, k), dtype=np.uint64)
+    for q in range(n):
+        p = seqs[q % 8]
+        t = int(rng.integers(0, 300)) if q % 8 % 2 == 0 else int(rng.integers(len(p) - 300 - k, len(p) - k))  # (both strands start near record 0)
+        pats[q] = p[t:t + k]
+    want = g.find_extend_batch(pats)
+    w0 = e.window_info()
+    assert pc.states_equal(e.find_extend(pats), want)
+    assert pc.states_equal(e.find_extend_u32(pats.astype(np.uint32)), want)
+    w1 = e.window_info()
+    if direct == "1":
+        assert w1["deferred"] - w0["deferred"] > n      # (most of both batches overflowed)
+    first = rng.integers(0, k, size=n).astype(np.uint64)
+    start = (first * rng.random(n)).astype(np.uint64)
+    end = (first + 1 + ((k - first - 1) * rng.random(n)).astype(np.uint64)).astype(np.uint64)
+    offs = np.arange(n + 1, dtype=np.uint64) * k
+    flat = pats.reshape(-1)
+    assert pc.states_equal(e.bd_search(flat, offs, first, start, end), g.bd_search_batch(flat, offs, first, start, end))
+
+
 def test_window_kernel_edge_cases(b200, monkeypatch):
     force_windows(monkeypatch)
     S, H, seed = 400, 40, 17
