@@ -943,66 +943,80 @@ struct PlainRowReader {
 // does not decode, nodes it does not hold and subpaths longer than the tile put the search on the deferred list.
 constexpr uint32_t BD_TILE_LINES = 32, BD_TILE_BYTES = (BD_TILE_LINES + 2u) * TILE_LINE;  // one sentinel line either side
 
-// One phase: extends half `a` (at window index idx, record entry h) by the tile lines from `pat` in direction `dir` (+1 /
-// -1 lines) for `count` nodes, flipping each node when `flip` (the backward phase); `b_start` is the other half's start.
-// Returns QUERY_ACTIVE when all extensions were made.
-__device__ __forceinline__ uint32_t bd_window_phase(const Staged& st, uint32_t origin, uint32_t pat, int32_t dir, uint32_t count, bool flip,
-                                                    uint32_t& idx, uint32_t& a_start, uint32_t& a_end, uint32_t& b_start) {
+// The extensions of one search in ONE loop: `fwd` forward extensions by the tile lines above the anchor, then `bwd` backward
+// extensions by the lines below it, which are forward extensions of the flipped state by the flipped nodes
+// (src/gbwt.rs:362-367). Half `a` is the one being extended (at window index a_idx), `b` the other one: when a lane has
+// made its forward extensions it swaps the halves and walks down. The lanes of a warp share the loop whatever phase each
+// is in, so a warp spends max(fwd + bwd) iterations on its 32 searches; as two loops, one per phase, it spent
+// max(fwd) + max(bwd), nearly twice that on subpaths with the anchor anywhere (profiles/r2_bd_window_ncu.txt: 10 of
+// 32 lanes active in the loops). Returns QUERY_ACTIVE when all extensions were made; `flipped` says which half `a` is then.
+__device__ __forceinline__ uint32_t bd_window_extend(const Staged& st, uint32_t origin, uint32_t at_anchor, uint32_t fwd, uint32_t bwd,
+                                                     uint32_t& a_idx, uint32_t& a_start, uint32_t& a_end, uint32_t& b_idx, uint32_t& b_start,
+                                                     bool& flipped) {
     const uint32_t parity = origin & 1u;
-    const int32_t line = dir * static_cast<int32_t>(TILE_LINE);
-    uint32_t left = count;
-    if (left == 0) return QUERY_ACTIVE;
-    uint4 h = lds128(st.rec + 16u * idx);
-    while (left != 0) {
+    uint32_t left = fwd, later = bwd, pat = at_anchor + TILE_LINE;
+    int32_t line = static_cast<int32_t>(TILE_LINE);
+    uint32_t flip = 0;  // 1 in the backward phase
+    uint32_t status = QUERY_ACTIVE;
+    for (;;) {
+        // (selects, not branches: the lanes of a warp are in different phases and must not part ways over this)
+        const bool turn = left == 0;
+        if (turn && later == 0) break;
+        // a lane that has made its forward extensions: the other half's range has the same size; it becomes the half to extend
+        const uint32_t size = a_end - a_start, o_idx = a_idx, o_start = a_start;
+        a_idx = turn ? b_idx : a_idx; b_idx = turn ? o_idx : b_idx;
+        a_start = turn ? b_start : a_start; b_start = turn ? o_start : b_start;
+        a_end = a_start + size;
+        left = turn ? later : left; later = turn ? 0u : later; flip = turn ? 1u : flip;
+        line = turn ? -static_cast<int32_t>(TILE_LINE) : line; pat = turn ? at_anchor - TILE_LINE : pat;
+        const uint4 h = lds128(st.rec + 16u * a_idx);
         uint32_t x1 = lds16(pat), x2 = left > 1 ? lds16(pat + line) : NODE_OUTSIDE;
-        if (flip) {
-            // flip(node) as a window index: the other orientation's record is the neighbour (node ^ 1)
-            x1 = x1 == NODE_OUTSIDE ? x1 : ((x1 + parity) ^ 1u) - parity;
-            x2 = x2 == NODE_OUTSIDE ? x2 : ((x2 + parity) ^ 1u) - parity;
-            if (x1 >= st.count) x1 = NODE_OUTSIDE;
-            if (x2 >= st.count) x2 = NODE_OUTSIDE;
-        }
-        if (x1 == NODE_OUTSIDE) return QUERY_DEFER;
+        // backward: flip(node) as a window index -- the other orientation's record is the neighbour (node ^ 1); forward: as it is
+        x1 = x1 == NODE_OUTSIDE ? x1 : ((x1 + parity) ^ flip) - parity;
+        x2 = x2 == NODE_OUTSIDE ? x2 : ((x2 + parity) ^ flip) - parity;
+        if (x1 >= st.count) x1 = NODE_OUTSIDE;
+        if (x2 >= st.count) x2 = NODE_OUTSIDE;
+        if (x1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }
         const uint32_t total = h.y & 0xFFFFu, kind = h.y >> 16;
         const uint32_t s = a_start < total ? a_start : total, e = a_end < total ? a_end : total;
-        if (s >= e) return QUERY_NONE;
+        if (s >= e) { status = QUERY_NONE; break; }
         const uint32_t t0 = h.x & 0xFFFFu, t1 = h.x >> 16;
-        uint32_t b = 0, rs = s, re = e, flipped = 0;
+        uint32_t b = 0, rs = s, re = e, moved = 0;
         if (kind < KIND_WIDE) {
             b = x1 == t1 ? 1u : 0u;
-            if (x1 != t0 && b == 0) return QUERY_NONE;
-            if (t0 == NODE_OUTSIDE || t1 == NODE_OUTSIDE) return QUERY_DEFER;  // (cannot tell whether the successors are one node's two orientations)
+            if (x1 != t0 && b == 0) { status = QUERY_NONE; break; }
+            if (t0 == NODE_OUTSIDE || t1 == NODE_OUTSIDE) { status = QUERY_DEFER; break; }  // (cannot tell whether the successors are one node's two orientations)
             const uint32_t last = e - 1u;
             const uint32_t ws = lds32(st.ranks + 4u * (kind + (s >> 4))), we = lds32(st.ranks + 4u * (kind + (last >> 4)));
             const uint32_t ones_s = (ws & 0xFFFFu) + static_cast<uint32_t>(__popc((ws >> 16) & ~(0xFFFFFFFFu << (s & 15u))));
             const uint32_t ones_e = (we & 0xFFFFu) + static_cast<uint32_t>(__popc((we >> 16) & ~(0xFFFFFFFEu << (last & 15u))));
             rs = b ? ones_s : s - ones_s;
             re = b ? ones_e : e - ones_e;
-            if (rs >= re) return QUERY_NONE;
+            if (rs >= re) { status = QUERY_NONE; break; }
             // Record::bd_follow's second value: edge 0 is preceded (in the reverse order) by edge 1 only when both lead to the
             // same node and edge 0 to its forward orientation; edge 1 by edge 0 unless that is the case
             const bool paired = t1 == t0 + 1u && ((t0 + origin) & 1u) == 0;
             const uint32_t ones = ones_e - ones_s, zeros = (e - s) - ones;
-            flipped = b == 0 ? (paired ? ones : 0u) : (paired ? 0u : zeros);
+            moved = b == 0 ? (paired ? ones : 0u) : (paired ? 0u : zeros);
         } else if (kind == KIND_SINGLE) {
-            if (x1 != t0) return QUERY_NONE;
+            if (x1 != t0) { status = QUERY_NONE; break; }
         } else {
-            return kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;
+            status = kind == KIND_EMPTY ? QUERY_NONE : QUERY_DEFER;
+            break;
         }
-        b_start += flipped;
+        b_start += moved;
         const uint32_t hop = b ? h.w : h.z;
         uint32_t offset;
         if (x2 == (hop & 0xFFFFu) && x2 != NODE_OUTSIDE) {
             // two extensions at once: the second one is over a single-edge record, which moves neither range start
-            offset = hop >> 16; idx = x2; pat += 2 * line; left -= 2;
+            offset = hop >> 16; a_idx = x2; pat += 2 * line; left -= 2;
         } else {
-            offset = lds16(st.offs + 4u * idx + 2u * b); idx = x1; pat += line; left -= 1;
+            offset = lds16(st.offs + 4u * a_idx + 2u * b); a_idx = x1; pat += line; left -= 1;
         }
         a_start = offset + rs; a_end = offset + re;
-        if (left == 0) break;
-        h = lds128(st.rec + 16u * idx);
     }
-    return QUERY_ACTIVE;
+    flipped = flip != 0;
+    return status;
 }
 
 template <int THREADS, int CTAS>
@@ -1120,15 +1134,13 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_bd_window(IndexView ix, Windo
                     if (kind == KIND_DEFER) status = QUERY_DEFER;
                     else if (kind == KIND_EMPTY || total == 0) status = QUERY_NONE;
                     else {
-                        f_idx = x0; f_start = 0; f_end = total; r_idx = x0_flip; r_start = 0; r_end = total;
-                        // forward extensions by path(first, end): `a` = forward half, `b` = reverse half
-                        status = bd_window_phase(st, origin, at_anchor + TILE_LINE, 1, length - anchor - 1u, false, f_idx, f_start, f_end, r_start);
-                        r_end = r_start + (f_end - f_start);
-                        if (status == QUERY_ACTIVE && anchor > 0) {
-                            // backward extensions by path[start, first) in descending order: forward extensions of the flipped state
-                            status = bd_window_phase(st, origin, at_anchor - TILE_LINE, -1, anchor, true, r_idx, r_start, r_end, f_start);
-                            f_end = f_start + (r_end - r_start);
-                        }
+                        // `a` starts as the forward half, `b` as the reverse half
+                        uint32_t a_idx = x0, a_start = 0, a_end = total, b_idx = x0_flip, b_start = 0;
+                        bool flipped = false;
+                        status = bd_window_extend(st, origin, at_anchor, length - anchor - 1u, anchor, a_idx, a_start, a_end, b_idx, b_start, flipped);
+                        const uint32_t b_end = b_start + (a_end - a_start);
+                        f_idx = flipped ? b_idx : a_idx; f_start = flipped ? b_start : a_start; f_end = flipped ? b_end : a_end;
+                        r_idx = flipped ? a_idx : b_idx; r_start = flipped ? a_start : b_start; r_end = flipped ? a_end : b_end;
                     }
                 }
             }

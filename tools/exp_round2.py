@@ -16,6 +16,7 @@ ap.add_argument("--sites", type=int, default=3_333_333)
 ap.add_argument("--haplotypes", type=int, default=1024)
 ap.add_argument("--find", default="old:FIND_WINDOW=0,win512,win256:WINDOW_THREADS=256,win1024:WINDOW_THREADS=1024")
 ap.add_argument("--extract", type=int, default=1)
+ap.add_argument("--bd", type=int, default=0, help="also time the bench's bidirectional searches with every find variant")
 ap.add_argument("--extract-plain", type=int, default=1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ckpt-shifts", default="")
@@ -75,6 +76,18 @@ if args.find:
         torch.cuda.synchronize()
         info = index.window_info()
         row["deferred"] = info["deferred"]
+        if args.bd:
+            gen = torch.Generator(device=dev); gen.manual_seed(11)
+            first = torch.randint(0, 32, (Q,), device=dev, generator=gen, dtype=torch.int64)
+            start = (first.double() * torch.rand(Q, device=dev, generator=gen, dtype=torch.float64)).long()
+            end = first + 1 + ((31 - first).double() * torch.rand(Q, device=dev, generator=gen, dtype=torch.float64)).long()
+            offs = torch.arange(Q + 1, dtype=torch.int64, device=dev) * 32
+            d_bd = torch.empty((Q, 6), dtype=torch.int64, device=dev)
+            ms = timed(lambda: index.bd_search_device(d_pat.data_ptr(), offs.data_ptr(), first.data_ptr(), start.data_ptr(), end.data_ptr(), Q,
+                                                      d_bd.data_ptr(), stream), args.reps)
+            ok = bool(torch.all(d_bd[:, 2] > d_bd[:, 1]).item()) and bool(torch.equal(d_bd[:, 2] - d_bd[:, 1], d_bd[:, 5] - d_bd[:, 4]))
+            row["bd"] = {"ms": ms, "g_searches_per_s": Q / ms / 1e6, "sizes_ok": ok, "checksum": int(d_bd.sum().item())}
+            del first, start, end, offs, d_bd
         print(json.dumps(row), flush=True)
         del index
         for k in set_knobs:
