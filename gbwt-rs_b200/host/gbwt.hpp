@@ -58,8 +58,32 @@ public:
         check(gbwt_b200_index_from_bytes(bytes, len, device, layout, &h));
         return GBWT(h);
     }
-    // serialize::serialize_to (src/gbwt.rs:388-400): a Simple-SDS GBWT file without DA samples and metadata.
+    // From the parts GBWT::load assembles (src/gbwt.rs:402-438; BWT::load, src/bwt.rs:176-185): header fields, the
+    // concatenated record bytes and the start offset of every record.
+    static GBWT from_parts(std::size_t sequences, std::size_t size, std::size_t offset, std::size_t alphabet_size, uint64_t flags,
+                           const std::vector<uint8_t>& bwt, const std::vector<uint64_t>& record_starts, int device = 0,
+                           int layout = GBWT_B200_LAYOUT_AUTO) {
+        gbwt_b200_index* h = nullptr;
+        check(gbwt_b200_index_from_parts(sequences, size, offset, alphabet_size, flags, bwt.data(), bwt.size(), record_starts.data(),
+                                         record_starts.size(), device, layout, &h));
+        return GBWT(h);
+    }
+    // serialize::serialize_to (src/gbwt.rs:388-400): the Simple-SDS GBWT file, tags, DA samples and metadata as loaded.
     void save(const std::string& path) const { check(gbwt_b200_index_save_file(h_, path.c_str())); }
+    std::vector<uint8_t> serialize() const {
+        void* image = nullptr;
+        std::size_t len = 0;
+        check(gbwt_b200_index_serialize(h_, &image, &len));
+        return take(image, len);
+    }
+    // GBZ::serialize (src/gbz.rs:662-671); throws std::runtime_error for an index without node labels.
+    void save_gbz(const std::string& path) const { check(gbwt_b200_index_save_gbz_file(h_, path.c_str())); }
+    std::vector<uint8_t> serialize_gbz() const {
+        void* image = nullptr;
+        std::size_t len = 0;
+        check(gbwt_b200_index_serialize_gbz(h_, &image, &len));
+        return take(image, len);
+    }
     GBWT(GBWT&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     GBWT& operator=(GBWT&& o) noexcept { if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; } return *this; }
     GBWT(const GBWT&) = delete;
@@ -79,6 +103,11 @@ public:
     std::size_t record_to_node(std::size_t record) const { return record + alphabet_offset(); }
     bool has_node(std::size_t id) const { return gbwt_b200_has_node(h_, id) != 0; }
     bool is_bidirectional() const { return gbwt_b200_is_bidirectional(h_) != 0; }
+    // Where the index lives and what it holds there (no counterpart in the crate).
+    int device() const { return gbwt_b200_device(h_); }
+    std::size_t device_bytes() const { uint64_t breakdown[10]; return gbwt_b200_device_bytes(h_, breakdown); }
+    bool has_checkpoints() const { uint64_t info[6]; gbwt_b200_checkpoint_info(h_, info); return info[0] != 0; }
+    static std::string version() { return gbwt_b200_version(); }
 
     // Sequence navigation, src/gbwt.rs:213-261.
     std::optional<Pos> start(std::size_t id) const {
@@ -183,6 +212,19 @@ public:
         check(gbwt_b200_find_extend(h_, patterns.data(), n, k, out.data()));
         return out;
     }
+    // The same with 32-bit node identifiers (half the bytes over PCIe; a node >= 2^32 has no record in an index that loads).
+    std::vector<gbwt_b200_state> find_extend_batch(const std::vector<uint32_t>& patterns, std::size_t k) const {
+        std::size_t n = k ? patterns.size() / k : 0;
+        std::vector<gbwt_b200_state> out(n);
+        check(gbwt_b200_find_extend_u32(h_, patterns.data(), n, k, out.data()));
+        return out;
+    }
+    // Patterns of different lengths: pattern q = nodes[offsets[q] .. offsets[q + 1]).
+    std::vector<gbwt_b200_state> find_extend_ragged(const std::vector<uint64_t>& nodes, const std::vector<uint64_t>& offsets) const {
+        std::vector<gbwt_b200_state> out(offsets.empty() ? 0 : offsets.size() - 1);
+        check(gbwt_b200_find_extend_ragged(h_, nodes.data(), offsets.data(), out.size(), out.data()));
+        return out;
+    }
     std::vector<gbwt_b200_bdstate> bd_search_batch(const std::vector<uint64_t>& nodes, const std::vector<uint64_t>& offsets,
                                                    const std::vector<uint64_t>& first, const std::vector<uint64_t>& start,
                                                    const std::vector<uint64_t>& end) const {
@@ -211,6 +253,12 @@ private:
         check(gbwt_b200_follow(h_, &in, 1, backward, offsets, raw.data(), &count));
         std::vector<BidirectionalState> out;
         for (const auto& r : raw) out.push_back(*to_bd(r));
+        return out;
+    }
+    static std::vector<uint8_t> take(void* image, std::size_t len) {
+        const uint8_t* p = static_cast<const uint8_t*>(image);
+        std::vector<uint8_t> out(p, p + len);
+        gbwt_b200_free(image);
         return out;
     }
     explicit GBWT(gbwt_b200_index* h) : h_(h) {}

@@ -75,6 +75,26 @@ int main(int argc, char** argv) {
         std::size_t occ = 0;
         for (auto& s : out) occ += s.end - s.start;
         CHECK(out.size() == 20 && occ == 32);
+        // the same batch with 32-bit nodes and as ragged patterns; a ragged batch with an empty and a one-node pattern
+        std::vector<uint32_t> narrow(patterns.begin(), patterns.end());
+        auto out32 = index.find_extend_batch(narrow, 4);
+        std::vector<uint64_t> offsets;
+        for (std::size_t q = 0; q <= out.size(); q++) offsets.push_back(4 * q);
+        auto ragged = index.find_extend_ragged(patterns, offsets);
+        CHECK(out32.size() == out.size() && ragged.size() == out.size());
+        for (std::size_t q = 0; q < out.size(); q++) {
+            CHECK(out32[q].node == out[q].node && out32[q].start == out[q].start && out32[q].end == out[q].end);
+            CHECK(ragged[q].node == out[q].node && ragged[q].start == out[q].start && ragged[q].end == out[q].end);
+        }
+        auto odd = index.find_extend_ragged({encode_node(12, false), encode_node(12, false), encode_node(14, false)}, {0, 0, 1, 3});
+        CHECK(odd.size() == 3 && odd[0].end <= odd[0].start && odd[1].node == encode_node(12, false) && odd[2].node == encode_node(14, false));
+        CHECK(index.device() == 0 && index.device_bytes() > 0 && !GBWT::version().empty());
+        // serialize::test (src/gbwt/tests.rs:72-84): the image loads again and answers alike
+        auto image = index.serialize();
+        GBWT again = GBWT::from_bytes(image.data(), image.size());
+        CHECK(again.len() == index.len() && again.sequences() == index.sequences() && again.sequence(7) == index.sequence(7));
+        auto out_again = again.find_extend_batch(patterns, 4);
+        for (std::size_t q = 0; q < out.size(); q++) CHECK(out_again[q].start == out[q].start && out_again[q].end == out[q].end);
         // node sequences and DNA of a GBZ (src/gbz/tests.rs:237-247; extract_sequence, src/bin/gbz-extract.rs:173-189)
         CHECK(!index.has_graph());
         GBWT gbz = GBWT::load(dir + "/example.gbz");
@@ -85,6 +105,13 @@ int main(int argc, char** argv) {
         CHECK(dna.second == "GATAA$TTATC$GATA$TATC$" && dna.first == (std::vector<uint64_t>{0, 6, 12, 17, 22}));
         bool refused = false;
         try { index.path_dna(0); } catch (const std::runtime_error&) { refused = true; }
+        CHECK(refused);
+        // GBZ::serialize (src/gbz.rs:662-671): round trip with the node labels; a GBWT alone has no GBZ form
+        auto gbz_image = gbz.serialize_gbz();
+        GBWT gbz_again = GBWT::from_bytes(gbz_image.data(), gbz_image.size());
+        CHECK(gbz_again.has_graph() && gbz_again.path_dna(0, '$') == std::string("GATAA$") && gbz_again.node_sequence(16) == std::string("C"));
+        refused = false;
+        try { index.serialize_gbz(); } catch (const std::runtime_error&) { refused = true; }
         CHECK(refused);
     } catch (const std::runtime_error& e) {
         if (std::string(e.what()).find("error 7") != std::string::npos) { std::fprintf(stderr, "%s\n", e.what()); return 77; }
