@@ -547,22 +547,32 @@ struct HostArray {
     size_t item_bytes;
 };
 
-// Processes items [0, n) in chunks on two alternating streams: H2D of the chunk's inputs, the kernel(s), D2H
-// of its outputs. With page-locked host memory the copies of one chunk overlap the kernel of the other.
+// Processes items [0, n) in chunks on alternating streams: H2D of the chunk's inputs, the kernel(s), D2H of its outputs.
+// With page-locked host memory the copies of one chunk overlap the kernels of the others, and the host-to-device copies
+// follow each other without a gap: the call takes the time of its input copies plus whatever is left to do when the last
+// byte has arrived. That tail is the last chunk's kernels and output copy, so the last chunk's worth of items is cut into
+// halves (1/2, 1/4, ... of a chunk, down to 1/16): the kernels of each piece run under the copy of the next, and what
+// follows the last copy is the work of a sixteenth of a chunk. (Four streams: a piece must not wait for the output copy of
+// the piece two before it.)
 // `launch(begin, count, device_ptrs, stream)` receives one device pointer per HostArray.
 template <class Launch>
 int run_chunked(const gbwt_b200_index* ix, size_t n, const std::vector<HostArray>& arrays, size_t chunk_items, Launch launch) {
     if (n == 0) return GBWT_B200_OK;
     DeviceScope scope(ix->device);
     if (!scope.ok) return fail(GBWT_B200_E_CUDA, "cudaSetDevice failed");
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    const int n_streams = n > chunk_items ? 2 : 1;
+    constexpr int MAX_STREAMS = 4;
+    cudaStream_t streams[MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    const bool taper = n > chunk_items && env_int("GBWT_B200_HOST_TAPER", 1) != 0;
+    const size_t min_items = std::max<size_t>(size_t(1) << 14, chunk_items / 16);
+    const int n_streams = n > chunk_items ? (taper ? MAX_STREAMS : 2) : 1;
     for (int i = 0; i < n_streams; i++) CUDA_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
     int rc = GBWT_B200_OK;
     std::vector<void*> dptr(arrays.size(), nullptr);
     size_t chunk_index = 0;
-    for (size_t begin = 0; begin < n && rc == GBWT_B200_OK; begin += chunk_items, chunk_index++) {
-        const size_t count = std::min(chunk_items, n - begin);
+    for (size_t begin = 0, count = 0; begin < n && rc == GBWT_B200_OK; begin += count, chunk_index++) {
+        const size_t left = n - begin;
+        count = std::min(chunk_items, left);
+        if (taper && left <= chunk_items && left / 2 >= min_items) count = left / 2;
         cudaStream_t s = streams[chunk_index % n_streams];
         for (size_t a = 0; a < arrays.size() && rc == GBWT_B200_OK; a++) {
             cudaError_t e = cudaMallocAsync(&dptr[a], std::max<size_t>(16, count * arrays[a].item_bytes), s);
