@@ -563,7 +563,7 @@ def bench_e2e(args, index, d_pat, want_out, Q, world, local_rank, barrier, max_o
         out[width] = {"value": Qe * world * e2e_steps / dt, "unit": "queries/s", "h2d_bytes_per_step": Qe * item,
                       "d2h_bytes_per_step": Qe * 24, "h2d_wire_gbs_per_gpu": Qe * item / wire_s / 1e9,
                       "wire_bound_queries_per_s": Qe * world / wire_s,
-                      "api": f"gbwt_b200_find_extend{'_u32' if width == 'u32' else ''} (host pointers, pinned), chunked double-buffered H2D/kernels/D2H"}
+                      "api": f"gbwt_b200_find_extend{'_u32' if width == 'u32' else ''} (host pointers, pinned), chunked H2D/kernels/D2H on alternating streams"}
         del h_pat, h_out, d_tmp
     e2e = dict(out["u32"])
     e2e.update({"queries_per_gpu_per_step": Qe, "steps": e2e_steps, "u64": out["u64"],
