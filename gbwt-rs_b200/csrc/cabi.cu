@@ -51,6 +51,10 @@ struct gbwt_b200_index {
     bool ckpt_ok = false;
     uint32_t ckpt_shift = 0;
     uint64_t ckpt_entries = 0, ckpt_bytes = 0, ckpt_build_us = 0;
+    // DNA bytes of every sequence before each of its checkpoints (k_extract_dna_checkpointed), made when checkpoints and
+    // node labels are both there; follows the checkpoint table entry by entry.
+    void* d_ckpt_dna = nullptr;
+    bool dna_ckpt_ok = false;
     void* d_seq_len = nullptr;  // length of every sequence once some walk has measured it (SEQ_LEN_UNKNOWN before)
     void* d_dna_len = nullptr;  // the same for the DNA of every sequence (valid for the attached graph)
     void* d_label_starts = nullptr;  // node labels of a GBZ file (Graph::sequences), absent for a plain GBWT
@@ -505,6 +509,51 @@ int launch_extract(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, con
     k_extract_lanes<<<static_cast<unsigned>((threads + block - 1) / block), block, 0, s>>>(ix->view, ids, m, out_offsets, base, nodes, lengths, stride);
     return launch_done("k_extract_lanes");
 }
+// K4 from checkpoints (kernels.cuh: k_extract_dna_checkpointed). seg_bytes != nullptr: the count pass over all sequences.
+int launch_extract_dna_checkpointed(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
+                                    uint8_t endmarker, uint8_t* bytes, uint64_t* lengths, uint64_t* seg_bytes, cudaStream_t s) {
+    if (m == 0) return GBWT_B200_OK;
+    constexpr int threads = BLOCK_THREADS;
+    const size_t tile_bytes = static_cast<size_t>(threads / 32) * 32 * DNA_TILE_STRIDE * sizeof(uint32_t);
+    const uint64_t items = ((m + 31) / 32) * ix->ckpt.max_segments;
+    const uint64_t ctas_wanted = (items * 32 + threads - 1) / threads;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, static_cast<uint64_t>(ix->sm_count) * 8)));
+    // CTAs per SM the kernel is compiled for (GBWT_B200_DNA_CTAS: 4 = 64 registers, 3 = 85, anything else = what the compiler takes)
+    const int ctas = env_int("GBWT_B200_DNA_CTAS", 4);
+    auto kernel = k_extract_dna_checkpointed<false, threads, 1>;
+    if (ix->view.edges_valid) kernel = ctas >= 4 ? k_extract_dna_checkpointed<false, threads, 4> : (ctas == 3 ? k_extract_dna_checkpointed<false, threads, 3> : k_extract_dna_checkpointed<false, threads, 1>);
+    else kernel = ctas >= 4 ? k_extract_dna_checkpointed<true, threads, 4> : (ctas == 3 ? k_extract_dna_checkpointed<true, threads, 3> : k_extract_dna_checkpointed<true, threads, 1>);
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_bytes)));
+    kernel<<<grid, threads, tile_bytes, s>>>(ix->view, ix->graph, ix->ckpt, static_cast<const uint64_t*>(ix->d_ckpt_dna), seg_bytes,
+                                             static_cast<const uint64_t*>(ix->d_dna_len), ids, m, out_offsets, base, endmarker, bytes, lengths);
+    return launch_done("k_extract_dna_checkpointed");
+}
+
+// Where the DNA of every sequence stands at each of its checkpoints: one count pass over all segments (every node's label
+// length, no bytes moved), then a scan per sequence; leaves the DNA length of every sequence in d_dna_len. Called when an
+// index has both checkpoints and node labels (at creation, when labels are attached, after an import). Without it DNA is
+// extracted by whole-sequence walks; a failure here only means that.
+void build_dna_checkpoints(gbwt_b200_index* ix) {
+    cudaFree(ix->d_ckpt_dna);
+    ix->d_ckpt_dna = nullptr;
+    ix->dna_ckpt_ok = false;
+    if (!ix->ckpt_ok || !ix->has_graph || ix->d_dna_len == nullptr || ix->ckpt.max_segments == 0 || env_int("GBWT_B200_DNA_CHECKPOINTS", 1) == 0) return;
+    DeviceScope scope(ix->device);
+    if (!scope.ok) return;
+    uint64_t* seg = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&seg), std::max<size_t>(256, ix->ckpt_entries * sizeof(uint64_t))) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStream_t s = nullptr;
+    int rc = launch_extract_dna_checkpointed(ix, nullptr, ix->view.sequences, nullptr, 0, 0, nullptr, nullptr, seg, s);
+    if (rc == GBWT_B200_OK) {
+        k_dna_checkpoint_scan<<<grid_for(ix, ix->view.sequences), BLOCK_THREADS, 0, s>>>(ix->view.sequences, ix->ckpt.first, seg,
+                                                                                         static_cast<uint64_t*>(ix->d_dna_len));
+        rc = launch_done("k_dna_checkpoint_scan");
+    }
+    if (rc != GBWT_B200_OK || cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); cudaFree(seg); return; }
+    ix->d_ckpt_dna = seg;
+    ix->dna_ckpt_ok = true;
+}
+
 int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m, const uint64_t* out_offsets, uint64_t base,
                        uint8_t endmarker, uint8_t* bytes, uint64_t* lengths, cudaStream_t s) {
     if (m == 0) return GBWT_B200_OK;
@@ -515,6 +564,15 @@ int launch_extract_dna(const gbwt_b200_index* ix, const uint64_t* ids, size_t m,
     const uint32_t ahead = static_cast<uint32_t>(std::max(0, env_int("GBWT_B200_EXTRACT_AHEAD", 48)));
     const unsigned grid = static_cast<unsigned>(std::min<size_t>(ctas, size_t(1) << 30));
     uint64_t *seq_len = static_cast<uint64_t*>(ix->d_seq_len), *dna_len = static_cast<uint64_t*>(ix->d_dna_len);
+    // With path checkpoints and their DNA positions every sequence is spelled as independent segments, one lane each
+    // (GBWT_B200_DNA_CHECKPOINTS=0: whole-sequence walks), and the lengths are a table lookup.
+    if (ix->dna_ckpt_ok && env_int("GBWT_B200_DNA_CHECKPOINTS", 1) != 0) {
+        if (bytes == nullptr) {
+            if (lengths != nullptr) k_lengths_from_table<<<grid_for(ix, m), BLOCK_THREADS, 0, s>>>(ix->view.sequences, dna_len, ids, m, lengths);
+            return launch_done("k_lengths_from_table");
+        }
+        return launch_extract_dna_checkpointed(ix, ids, m, out_offsets, base, endmarker, bytes, lengths, nullptr, s);
+    }
     // sequences whose lengths are known are spelled from both ends by two warps (see launch_extract)
     if (bytes != nullptr && ix->view.bidirectional && env_int("GBWT_B200_EXTRACT_SPLIT", 1) != 0) {
         const unsigned pairs = static_cast<unsigned>(std::min<size_t>(m, size_t(1) << 30));
@@ -769,6 +827,7 @@ int attach_graph(gbwt_b200_index* ix, const uint64_t* starts, uint64_t sequences
     cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     ix->d_label_starts = ix->d_label_bytes = nullptr;
     ix->has_graph = false;
+    ix->dna_ckpt_ok = false;
     ix->carried.graph_section.clear();  // (create_index restores the loaded one after attaching the loaded labels)
     // DNA lengths measured with another graph are void
     if (ix->d_dna_len != nullptr) CUDA_TRY(cudaMemset(ix->d_dna_len, 0xFE, std::max<size_t>(256, ix->sequences * sizeof(uint64_t))));
@@ -781,6 +840,7 @@ int attach_graph(gbwt_b200_index* ix, const uint64_t* starts, uint64_t sequences
     ix->graph.sequences = sequences;
     ix->graph_bytes = a + b;
     ix->has_graph = true;
+    build_dna_checkpoints(ix);
     return GBWT_B200_OK;
 }
 
@@ -985,6 +1045,7 @@ int create_index(const ParsedGBWT& parsed, int device, int policy, gbwt_b200_ind
         if (want) {
             rc = build_checkpoints(ix);
             if (rc != GBWT_B200_OK) { gbwt_b200_index_destroy(ix); return rc; }
+            build_dna_checkpoints(ix);
         }
     }
     *out = ix;
@@ -1313,6 +1374,7 @@ int gbwt_b200_index_import_ipc(const void* blob, size_t len, int device, gbwt_b2
             ix->graph_bytes = h.graph_bytes;
             ix->has_graph = true;
         }
+        build_dna_checkpoints(ix);  // (a table of the importer's own: a short count pass, not worth a handle in the blob)
         *out = ix;
         return GBWT_B200_OK;
     )
@@ -1330,7 +1392,7 @@ void gbwt_b200_index_destroy(gbwt_b200_index* ix) {
     if (ix == nullptr) return;
     {
         DeviceScope scope(ix->device);
-        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_stage_body); cudaFree(ix->d_ckpt_table); cudaFree(ix->d_ckpt_first); cudaFree(ix->d_seq_len); cudaFree(ix->d_dna_len);
+        cudaFree(ix->d_desc); cudaFree(ix->d_bodies); cudaFree(ix->d_edges); cudaFree(ix->d_endmarker); cudaFree(ix->d_skips); cudaFree(ix->d_stage_body); cudaFree(ix->d_ckpt_table); cudaFree(ix->d_ckpt_first); cudaFree(ix->d_seq_len); cudaFree(ix->d_dna_len); cudaFree(ix->d_ckpt_dna);
         cudaFree(ix->d_label_starts); cudaFree(ix->d_label_bytes);
     }
     delete ix;

@@ -1567,6 +1567,194 @@ __global__ void __launch_bounds__(THREADS) k_extract_checkpointed(IndexView ix, 
     }
 }
 
+// ---- K4 with checkpoints: DNA extraction that is parallel ALONG the paths ----------------------------------------------
+// One group of up to 32 consecutive nodes of a path (lane l holds node l of the group, l < count) spelled at byte `at` of
+// the path's DNA: the stateless form of DnaSink (extract_sequence, src/bin/gbz-extract.rs:173-189; reverse-oriented nodes
+// reverse-complemented, support::reverse_complement, src/support.rs:104-110). Every lane fetches the label range of its
+// node, a warp scan turns the lengths into offsets, and the warp writes the group's bytes as consecutive 32-byte rows,
+// each lane finding the node that owns its byte by a 5-step search over the scanned lengths. out == nullptr only counts.
+// Returns the bytes of the group, written or not (nothing beyond out[cap) is written).
+__device__ __forceinline__ uint32_t spell_group(const GraphView& graph, uint64_t node_base, uint32_t mine, uint32_t count,
+                                                uint8_t* out, uint64_t cap, uint64_t at) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr uint32_t ROWS = 8;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t sid = ((static_cast<uint64_t>(mine) & ~1ull) - node_base) >> 1;  // GBZ::gbwt_node_to_sequence, src/gbz.rs:253-255
+    const bool valid = lane < count && sid < graph.sequences;
+    const uint64_t idx = valid ? sid : 0;
+    const uint64_t lo = __ldg(graph.starts + idx), hi = __ldg(graph.starts + idx + 1);
+    const uint32_t rev = mine & 1u;
+    const uint32_t len = valid ? static_cast<uint32_t>(hi - lo) : 0u;
+    uint32_t incl = len;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (out != nullptr) {
+        // byte b of the group comes from label byte key + b (forward node) or key - b (reverse node); the keys carry a bias
+        // of 2^32 so that they stay positive (bit 63 is the orientation)
+        constexpr uint64_t BIAS = 1ull << 32;
+        const uint32_t excl = incl - len;
+        const uint64_t key = BIAS + (rev ? lo + len - 1 + excl : lo - excl);
+        const uint32_t key_lo = static_cast<uint32_t>(key), key_hi = static_cast<uint32_t>(key >> 32) | (rev << 31);
+        for (uint32_t row = 0; row < total; row += 32 * ROWS) {
+            uint32_t c[ROWS], flip[ROWS];
+#pragma unroll
+            for (uint32_t j = 0; j < ROWS; j++) {
+                const uint32_t b = row + 32 * j + lane;
+                uint32_t owner = 0;  // number of nodes that end at or before byte b (incl is non-decreasing over the lanes)
+#pragma unroll
+                for (uint32_t step = 16; step != 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, incl, (owner + step - 1) & 31u);
+                    if (v <= b) owner += step;
+                }
+                const uint32_t k_lo = __shfl_sync(FULL, key_lo, owner & 31u), k_hi = __shfl_sync(FULL, key_hi, owner & 31u);
+                const uint64_t k = (static_cast<uint64_t>(k_hi & 0x7FFFFFFFu) << 32) | k_lo;
+                flip[j] = k_hi >> 31;
+                c[j] = 0;
+                if (b < total && at + b < cap) c[j] = __ldg(graph.bytes + ((flip[j] ? k - b : k + b) - BIAS));
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < ROWS; j++) {
+                const uint32_t b = row + 32 * j + lane;
+                if (b < total && at + b < cap) out[at + b] = static_cast<uint8_t>(flip[j] ? complement_base(c[j]) : c[j]);
+            }
+        }
+    }
+    return total;
+}
+
+// Work item (segment j, block of 32 sequences) as in k_extract_checkpointed: lane l walks segment j of its sequence from
+// the checkpoint, parks the nodes in its row of the tile, and once per round the warp spells the rows one after the
+// other (spell_group) at each lane's own byte position, which starts at dna_at[checkpoint] = the DNA bytes of the
+// sequence before the checkpoint's node.
+// Count mode (bytes == nullptr, seg_bytes != nullptr, ids == nullptr: all sequences): seg_bytes[checkpoint] = DNA bytes of
+// the segment -- the pass that dna_at[] is made from when a graph and checkpoints are both there.
+// (Rounds of 32 nodes per lane: spelling a row is two memory round trips however long it is, so what counts is how many
+// warps an SM holds, and the tile is what limits that.)
+constexpr uint32_t DNA_TILE_NODES = 32, DNA_TILE_STRIDE = 33;
+
+template <bool CHECKED, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_extract_dna_checkpointed(IndexView ix, GraphView graph, CheckpointView cv,
+                                                                             const uint64_t* __restrict__ dna_at, uint64_t* __restrict__ seg_bytes,
+                                                                             const uint64_t* __restrict__ dna_len, const uint64_t* __restrict__ ids,
+                                                                             size_t m, const uint64_t* __restrict__ out_offsets, uint64_t base_offset,
+                                                                             uint32_t endmarker, uint8_t* __restrict__ bytes,
+                                                                             uint64_t* __restrict__ lengths) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    extern __shared__ __align__(16) unsigned char tile_bytes[];  // [THREADS / 32][32][DNA_TILE_STRIDE] words
+    uint32_t (*tiles)[32][DNA_TILE_STRIDE] = reinterpret_cast<uint32_t (*)[32][DNA_TILE_STRIDE]>(tile_bytes);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t (*tile)[DNA_TILE_STRIDE] = tiles[threadIdx.x >> 5];
+    uint32_t* const row = tile[lane];
+    const uint64_t keep = keep_policy();
+    const RecordDesc* const descs = ix.desc;
+    const Unit16* const bodies = ix.bodies;
+    const Unit16* const skips = ix.skips;
+    const Edge* const edges = ix.edges;
+    const uint32_t base = static_cast<uint32_t>(ix.offset), records = static_cast<uint32_t>(ix.records);
+    const uint64_t node_base = ix.offset + 1;
+    const bool counting = bytes == nullptr;
+    const uint64_t blocks = (m + 31) / 32;
+    const uint64_t items = blocks * cv.max_segments;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) / 32;
+    for (uint64_t item = warp; item < items; item += warps) {
+        const uint64_t j = item / blocks, i = (item - j * blocks) * 32 + lane;
+        SegmentLane st;
+        st.node = 0; st.offset = 0; st.left = 0; st.parked = 0;
+        uint8_t* out = nullptr;  // this lane's sequence slot
+        uint64_t cap = 0, cursor = 0;
+        uint64_t slot = ~0ull;   // the checkpoint this lane walks from
+        bool last = false;       // ... is the last one of its sequence: the endmarker byte follows
+        if (i < m) {
+            const uint64_t id = ids != nullptr ? __ldg(ids + i) : i;
+            if (id >= ix.sequences) {
+                if (j == 0 && lengths != nullptr) lengths[i] = ~0ull;  // GBZ::path() is None
+            } else {
+                if (j == 0 && lengths != nullptr) lengths[i] = dna_len[id];
+                const uint32_t first = __ldg(cv.first + id), count = __ldg(cv.first + id + 1) - first;
+                if (!counting) {
+                    const uint64_t lo = __ldg(out_offsets + i), hi = __ldg(out_offsets + i + 1);
+                    out = bytes + (lo - base_offset);
+                    cap = hi > lo ? hi - lo : 0;
+                    if (j == 0 && count == 0 && cap > 0) out[0] = static_cast<uint8_t>(endmarker);  // an empty path: the endmarker alone
+                }
+                if (j < count) {
+                    slot = first + j;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(cv.table + slot));
+                    st.node = raw.x; st.offset = raw.y;
+                    const uint64_t index = (static_cast<uint64_t>(raw.w) << 32) | raw.z;
+                    uint64_t end = cv.seq_len[id];
+                    if (j + 1 < count) {
+                        const uint4 next = __ldg(reinterpret_cast<const uint4*>(cv.table + slot + 1));
+                        end = (static_cast<uint64_t>(next.w) << 32) | next.z;
+                    } else {
+                        last = true;
+                    }
+                    const uint64_t todo = end > index ? end - index : 0;
+                    st.left = todo < 0xFFFFFFFFull ? static_cast<uint32_t>(todo) : 0xFFFFFFFFu;
+                    if (!counting) cursor = __ldg(dna_at + slot);
+                }
+            }
+        }
+        Desc d0, d1;
+        Quad k0, k1;
+        if (st.left != 0) load_segment_record<CHECKED>(descs, skips, base, records, keep, st.node, d0, k0);
+        for (;;) {
+#pragma unroll 1
+            for (uint32_t step = 0; step < DNA_TILE_NODES / 4; step++) {
+                if (st.left != 0) segment_step<CHECKED>(st, d0, k0, d1, k1, row, descs, bodies, skips, edges, base, records, keep);
+                if (st.left != 0) segment_step<CHECKED>(st, d1, k1, d0, k0, row, descs, bodies, skips, edges, base, records, keep);
+            }
+            // every lane asks L1 for the label ranges of the nodes it parked (neighbouring lanes walk neighbouring haplotypes:
+            // a few lines), so that the warp's loads of them below do not each wait for L2 / DRAM
+            for (uint32_t p = 0; p < st.parked; p++) {
+                const uint64_t sid = ((static_cast<uint64_t>(row[p]) & ~1ull) - node_base) >> 1;
+                if (sid < graph.sequences) asm volatile("prefetch.global.L1 [%0];" ::"l"(graph.starts + sid));
+            }
+            // the rows one after the other, each at its lane's own position in its own sequence
+            __syncwarp();
+#pragma unroll 1
+            for (uint32_t r = 0; r < 32; r++) {
+                const uint32_t n = __shfl_sync(FULL, st.parked, r);
+                if (n == 0) continue;
+                uint64_t at = __shfl_sync(FULL, cursor, r);
+                const uint64_t to = __shfl_sync(FULL, reinterpret_cast<uint64_t>(out), r), limit = __shfl_sync(FULL, cap, r);
+                for (uint32_t g = 0; g < n; g += 32) {
+                    const uint32_t mine = g + lane < n ? tile[r][g + lane] : 0u;
+                    at += spell_group(graph, node_base, mine, n - g < 32u ? n - g : 32u, reinterpret_cast<uint8_t*>(to), limit, at);
+                }
+                if (lane == r) cursor = at;
+            }
+            __syncwarp();
+            st.parked = 0;
+            if (!__any_sync(FULL, st.left != 0)) break;
+        }
+        if (slot != ~0ull) {
+            if (counting) seg_bytes[slot] = cursor;
+            else if (last && cursor < cap) out[cursor] = static_cast<uint8_t>(endmarker);
+        }
+    }
+}
+
+// dna_at[checkpoint] = DNA bytes of the sequence before the checkpoint's node (exclusive scan of the segment sizes the
+// count pass left there); dna_len[id] = bytes of the whole result, endmarker included (1 for an empty path).
+__global__ void __launch_bounds__(BLOCK_THREADS) k_dna_checkpoint_scan(uint64_t sequences, const uint32_t* __restrict__ first,
+                                                                        uint64_t* __restrict__ seg, uint64_t* __restrict__ dna_len) {
+    GBWT_GRID_STRIDE(id, sequences) {
+        uint64_t total = 0;
+        for (uint32_t s = first[id]; s < first[id + 1]; s++) {
+            const uint64_t t = seg[s];
+            seg[s] = total;
+            total += t;
+        }
+        dna_len[id] = total + 1;
+    }
+}
+
 // GBWT::sequence(id).count() from the table the checkpoint build left.
 __global__ void __launch_bounds__(BLOCK_THREADS) k_lengths_from_table(uint64_t sequences, const uint64_t* __restrict__ seq_len,
                                                                        const uint64_t* __restrict__ ids, size_t m, uint64_t* __restrict__ lengths) {

@@ -235,7 +235,8 @@ GBWT_B200_API int gbwt_b200_node_sequences(const gbwt_b200_index* index, const u
  * (= support::encode_path(path_id, orientation), src/support.rs:247-249): the labels of the nodes on the path,
  * reverse-complemented for reverse-oriented nodes (support::reverse_complement, src/support.rs:104-110), then
  * the `endmarker` byte. lengths[i] = length of the full result including the endmarker, UINT64_MAX where
- * GBZ::path is None (id >= sequences()). */
+ * GBZ::path is None (id >= sequences()). An index with path checkpoints (GBWT_B200_LAYOUT_CHECKPOINTS, the default for long
+ * sequences) and node labels spells every sequence as independent segments and answers the lengths from a table. */
 GBWT_B200_API int gbwt_b200_dna_lengths(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m, uint64_t* lengths);
 /* Result i is written to bytes[out_offsets[i] ..], at most out_offsets[i+1] - out_offsets[i] bytes. */
 GBWT_B200_API int gbwt_b200_extract_dna(const gbwt_b200_index* index, const uint64_t* seq_ids, size_t m, uint8_t endmarker,

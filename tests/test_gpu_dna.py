@@ -289,3 +289,84 @@ def test_whole_object_serialization_through_the_c_abi(b200, tmp_path):
     g = orc.GBWT.load(image)
     w_off, w_bytes, _ = g.extract_dna_batch(ids, 0)
     assert np.array_equal(a[0], w_off) and np.array_equal(a[1], w_bytes)
+
+
+@pytest.mark.parametrize("shift", [6, 8])
+def test_checkpointed_dna_extraction(b200, shift, monkeypatch):
+    # With path checkpoints AND node labels the index also knows where the DNA of every sequence stands at each checkpoint
+    # (one count pass when both are there), and a sequence is spelled as independent segments, one lane each
+    # (k_extract_dna_checkpointed): identical bytes to the whole-sequence walks and the oracle.
+    import torch
+    monkeypatch.setenv("GBWT_B200_CHECKPOINTS", "1")
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", str(shift))
+    S, H, seed = 2000, 48, 11   # 4001 nodes per path: 63 segments of 64 nodes, 16 of 256
+    img = synth.bubble_chain(S, H, seed)
+    starts, data = synth.node_labels(3 * S + 1, seed=5, max_anchor=48)
+    gbz = synth.gbz_image(img, starts, data, 4)
+    e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
+    info = e.checkpoint_info()
+    assert info["present"] == 1 and info["max_segments"] >= 4001 >> shift
+    ids = np.arange(2 * H + 1, dtype=np.uint64)   # all sequences and one past the end (None)
+    want_offsets, want, want_lengths = g.extract_dna_batch(ids, ord("\n"))
+    before = b200.kernel_launches()
+    assert np.array_equal(e.dna_lengths(ids), want_lengths)       # a table lookup now
+    offsets, got, lengths = e.extract_dna(ids, ord("\n"))
+    assert np.array_equal(offsets, want_offsets) and np.array_equal(lengths, want_lengths) and np.array_equal(got, want)
+    assert b200.kernel_launches() == before + 3   # lengths; lengths again inside extract_dna; the segments
+    # slots shorter than the results: each result is cut to its slot, lengths still report the full size
+    n = 2 * H
+    cut = np.minimum(want_lengths[:n], np.uint64(1500)) - np.arange(n, dtype=np.uint64) % np.uint64(3)
+    slots = np.zeros(n + 1, np.uint64)
+    np.cumsum(cut, out=slots[1:])
+    d_ids = torch.from_numpy(ids[:n].view(np.int64)).cuda()
+    d_offsets = torch.from_numpy(slots.view(np.int64)).cuda()
+    d_bytes = torch.full((int(slots[-1]) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    d_lengths = torch.zeros(n, dtype=torch.int64, device="cuda")
+    e.extract_dna_device(d_ids.data_ptr(), n, 7, d_offsets.data_ptr(), d_bytes.data_ptr(), d_lengths.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out = d_bytes.cpu().numpy()
+    assert np.array_equal(d_lengths.cpu().numpy().view(np.uint64), want_lengths[:n])
+    for i in range(n):
+        lo, hi = int(slots[i]), int(slots[i + 1])
+        ref = want[int(want_offsets[i]):int(want_offsets[i]) + hi - lo].copy()
+        if hi - lo == int(want_lengths[i]):
+            ref[-1] = 7   # (the endmarker of this call)
+        assert np.array_equal(out[lo:hi], ref), i
+    assert np.all(out[int(slots[-1]):] == 0xEE)   # nothing written past the last slot
+    # the same index without the table walks whole sequences: same bytes
+    monkeypatch.setenv("GBWT_B200_DNA_CHECKPOINTS", "0")
+    _, plain, _ = e.extract_dna(ids, ord("\n"))
+    assert np.array_equal(plain, want)
+    monkeypatch.delenv("GBWT_B200_DNA_CHECKPOINTS")
+    # labels attached to an index that already has its checkpoints; other labels replace the table
+    e2 = b200.GBWT.from_bytes(img.array).attach_graph(starts, data)
+    _, got2, lengths2 = e2.extract_dna(ids, ord("\n"))
+    assert np.array_equal(got2, want) and np.array_equal(lengths2, want_lengths)
+    starts3, data3 = synth.node_labels(3 * S + 1, seed=6, max_anchor=20)
+    g3 = orc.GBWT.load(synth.gbz_image(img, starts3, data3, 3))
+    e2.attach_graph(starts3, data3)
+    check_dna(e2, g3, endmarker=ord("$"))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_checkpointed_dna_on_random_graphs_and_fixtures(b200, seed, monkeypatch):
+    # short and empty paths, labels of 0 to 700 bytes, nodes on both strands: one segment per path or a few
+    from test_hostsim_layout import random_paths
+    monkeypatch.setenv("GBWT_B200_CHECKPOINTS", "1")
+    monkeypatch.setenv("GBWT_B200_CHECKPOINT_SHIFT", "6")
+    rng = random.Random(300 + seed)
+    paths = random_paths(rng, n_nodes=rng.choice([3, 6, 12]), n_paths=rng.choice([3, 10, 40]), max_len=rng.choice([8, 90, 300]))
+    paths.append([])
+    paths.append([2, 4])
+    b = gb.build_bwt(gb.bidirectional_sequences(paths))
+    img = synth.gbwt_image(**image_args(b))
+    n_labels = (b["alphabet_size"] - (b["offset"] + 1)) // 2
+    starts, data = random_labels(rng, n_labels, rng.choice([3, 40, 700]))
+    gbz = synth.gbz_image(img, starts, data, rng.choice([3, 4]))
+    e, g = b200.GBWT.from_bytes(gbz), orc.GBWT.load(gbz)
+    assert e.checkpoint_info()["present"] == 1
+    check_dna(e, g, endmarker=rng.choice([0, ord("$"), 255]))
+    if seed == 0:
+        for name in ("example.gbz", "example-v1.gbz", "translation.gbz", "translation-v1.gbz"):
+            path = os.path.join(GOLDEN, name)
+            check_dna(b200.GBWT.load(path), orc.GBWT.load(path), endmarker=ord("$"))
