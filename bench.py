@@ -884,8 +884,11 @@ def bench_extract_dna(args, index, image, sites, haplotypes, rank, world, local_
             "config": {"workload": f"DNA sequences of all {haplotypes} forward haplotype paths ({length} nodes, "
                                    f"{total_bytes // max(1, m)} bases each) of the {3 * sites + 1}-node bubble-chain GBZ",
                        "paths_per_gpu": m, "layout": args.layout, "label_bytes": int(starts[-1]),
-                       "note": "sequence and DNA lengths are known to the index from the dna_lengths call that sized the output, "
-                               "so every path is walked from both ends by two warps that relay their nodes to a spelling warp (k_extract_dna_relay)"},
+                       "kernel": "k_extract_dna_checkpointed" if index.checkpoint_info()["present"] else "k_extract_dna_relay",
+                       "note": "with path checkpoints (the default for an index of this size) the DNA position of every checkpoint is counted "
+                               "when the labels are attached and every segment is spelled independently (k_extract_dna_checkpointed); "
+                               "without them sequence and DNA lengths are known from the dna_lengths call that sized the output and every "
+                               "path is walked from both ends by two warps that relay their nodes to a spelling warp (k_extract_dna_relay)"},
             "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu_baseline,
             "extra": {"lf_steps_per_s": haplotypes * length * args.steps / (total_ms / 1e3), "lengths_only_ms": lengths_only_ms,
                       "index_device_bytes": stats,
