@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -20,6 +21,7 @@ struct RecordReader {
     const uint8_t* p;
     uint64_t n, at = 0;
     uint64_t sigma = 0, threshold = 0;
+    uint32_t sigma32 = 0, magic = 0;  // byte / sigma by multiplication (layout.h: div_magic), not by a 64-bit division per run
     bool bad = false;
 
     RecordReader(const uint8_t* bytes, uint64_t len) : p(bytes), n(len) {}
@@ -38,6 +40,7 @@ struct RecordReader {
     void begin_runs(uint64_t s) {
         sigma = s;
         threshold = (s < 255) ? 256 / s : 0;
+        if (s >= 1 && s < 255) { sigma32 = static_cast<uint32_t>(s); magic = div_magic(sigma32); }
     }
     // One run of the reference's sequence; false at the end of the record (or on a truncated run).
     bool run(uint64_t& value, uint64_t& len) {
@@ -47,9 +50,9 @@ struct RecordReader {
             if (!varint(value) || !varint(l) || l == ~0ull) { bad = true; return false; }
             len = l + 1;
         } else {
-            uint8_t b = p[at++];
-            value = b % sigma;
-            len = b / sigma + 1;
+            const uint32_t b = p[at++], q = (b * magic) >> 16;  // q = b / sigma for b < 256, sigma <= 256
+            value = b - q * sigma32;
+            len = q + 1;
             if (len == threshold) {
                 uint64_t extra;
                 if (!varint(extra) || extra > ~0ull - len) { bad = true; return false; }
@@ -60,14 +63,17 @@ struct RecordReader {
     }
 };
 
+// (no default member initialisers: an array of plans is sized without being cleared, plan_record() starts from Plan{} = all
+// zero = an empty record, status OK)
 struct Plan {
-    uint64_t sigma = 0, total = 0, runs = 0, run8 = 0, run32 = 0, header_end = 0;
-    uint64_t count01[2] = {0, 0};  // occurrences of symbols 0 and 1 (what the two-hop shortcuts are checked against)
-    uint8_t fmt = FMT_EMPTY;
-    uint8_t ckpt = 0;     // 0, or log2(positions per checkpoint) + 1 for a run body with a checkpoint table (layout.h)
-    uint32_t units = 0;   // body size in 16-byte units
-    int status = GBWT_B200_OK;
+    uint64_t sigma, total, runs, run8, run32, header_end;
+    uint64_t count01[2];  // occurrences of symbols 0 and 1 (what the two-hop shortcuts are checked against)
+    uint8_t fmt;
+    uint8_t ckpt;         // 0, or log2(positions per checkpoint) + 1 for a run body with a checkpoint table (layout.h)
+    uint32_t units;       // body size in 16-byte units
+    int status;
 };
+static_assert(std::is_trivially_default_constructible<Plan>::value && FMT_EMPTY == 0 && GBWT_B200_OK == 0, "Plan{} is the plan of an empty record");
 
 // Tuning / test knobs for the checkpoint tables (layout.h): GBWT_B200_CKPT=0 disables them, GBWT_B200_CKPT_MIN_RUNS and
 // GBWT_B200_CKPT_INTERVAL_RUNS override when a body gets one and how many runs lie between two checkpoints.
@@ -89,7 +95,7 @@ inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // Pass 1: size every candidate format and pick one.
 Plan plan_record(const uint8_t* bytes, uint64_t len, int policy, const CheckpointPolicy& cp) {
-    Plan pl;
+    Plan pl{};
     if (len == 0) return pl;  // Record::new: empty slice -> None (src/bwt.rs:342)
     RecordReader rd(bytes, len);
     if (!rd.varint(pl.sigma)) { pl.status = GBWT_B200_E_INVALID_DATA; return pl; }
@@ -321,7 +327,9 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
 #endif
     if (const char* e = std::getenv("GBWT_B200_BUILD_THREADS")) threads = std::max(1, std::atoi(e));
     (void)threads;
-    std::vector<Plan> plans(R);
+    // (80 bytes per record, every one of them written by the pass below: no point in one thread clearing them first)
+    BigVector<Plan> plans;
+    plans.resize(R);
     const CheckpointPolicy checkpoint_policy;
     std::atomic<int> status{GBWT_B200_OK};
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
@@ -333,19 +341,56 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
         err = status.load() == GBWT_B200_E_RANGE ? "a record does not fit the 32-bit device layout" : "BWT: malformed record";
         return status.load();
     }
-    std::vector<uint64_t> body_at(R + 1, 0), edge_at(R + 1, 0);
-    for (uint64_t i = 0; i < R; i++) {
-        body_at[i + 1] = body_at[i] + plans[i].units;
-        edge_at[i + 1] = edge_at[i] + (plans[i].sigma > 2 ? plans[i].sigma : 0);
-        out.format_counts[plans[i].fmt]++;
-        if (plans[i].ckpt != 0) out.checkpointed_records++;
-        out.total_length += plans[i].total;
+    // Where every record's body and edge list go: prefix sums over the plans, by blocks of records (sums of the blocks in
+    // parallel, a scan over the few block sums, then the prefixes inside every block in parallel).
+    BigVector<uint64_t> body_at, edge_at;
+    body_at.resize(R + 1); edge_at.resize(R + 1);
+    {
+        const uint64_t block = uint64_t(1) << 16, blocks = (R + block - 1) / block;
+        std::vector<uint64_t> block_body(blocks + 1, 0), block_edge(blocks + 1, 0), block_total(blocks, 0), block_ckpt(blocks, 0);
+        std::vector<uint64_t> block_fmt(blocks * FMT_COUNT, 0);
+#pragma omp parallel for schedule(static) num_threads(threads)
+        for (int64_t b = 0; b < static_cast<int64_t>(blocks); b++) {
+            uint64_t body = 0, edge = 0, total = 0, ckpt = 0;
+            for (uint64_t i = b * block; i < std::min(R, (b + 1) * block); i++) {
+                body += plans[i].units;
+                edge += plans[i].sigma > 2 ? plans[i].sigma : 0;
+                block_fmt[b * FMT_COUNT + plans[i].fmt]++;
+                if (plans[i].ckpt != 0) ckpt++;
+                total += plans[i].total;
+            }
+            block_body[b + 1] = body; block_edge[b + 1] = edge; block_total[b] = total; block_ckpt[b] = ckpt;
+        }
+        for (uint64_t b = 0; b < blocks; b++) {
+            block_body[b + 1] += block_body[b]; block_edge[b + 1] += block_edge[b];
+            out.total_length += block_total[b]; out.checkpointed_records += block_ckpt[b];
+            for (int f = 0; f < FMT_COUNT; f++) out.format_counts[f] += block_fmt[b * FMT_COUNT + f];
+        }
+#pragma omp parallel for schedule(static) num_threads(threads)
+        for (int64_t b = 0; b < static_cast<int64_t>(blocks); b++) {
+            uint64_t body = block_body[b], edge = block_edge[b];
+            for (uint64_t i = b * block; i < std::min(R, (b + 1) * block); i++) {
+                body_at[i] = body; edge_at[i] = edge;
+                body += plans[i].units;
+                edge += plans[i].sigma > 2 ? plans[i].sigma : 0;
+            }
+        }
+        body_at[R] = block_body[blocks]; edge_at[R] = block_edge[blocks];
     }
     if (body_at[R] > 0xFFFFFFFFull || edge_at[R] > 0xFFFFFFFFull) {
         err = "index does not fit the 32-bit device layout"; return GBWT_B200_E_RANGE;
     }
-    out.desc.assign(R, RecordDesc{});
-    out.bodies.assign(2 * body_at[R] + 2, 0);
+    // (sized without clearing -- see UninitAllocator -- and cleared by all threads: whoever clears a page also maps it)
+    auto clear_all = [&](void* p, size_t bytes) {
+        const size_t piece = size_t(1) << 22, pieces = (bytes + piece - 1) / piece;
+        unsigned char* at = static_cast<unsigned char*>(p);
+#pragma omp parallel for schedule(static) num_threads(threads)
+        for (int64_t j = 0; j < static_cast<int64_t>(pieces); j++) std::memset(at + j * piece, 0, std::min(piece, bytes - j * piece));
+    };
+    out.desc.resize(R);
+    clear_all(out.desc.data(), R * sizeof(RecordDesc));
+    out.bodies.resize(2 * body_at[R] + 2);
+    clear_all(out.bodies.data(), out.bodies.size() * sizeof(uint64_t));
     out.edges.assign(edge_at[R] + 1, Edge{0, 0});
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
     for (int64_t i = 0; i < static_cast<int64_t>(R); i++) {
@@ -355,7 +400,8 @@ int build_layout(const ParsedGBWT& in, int policy, HostLayout& out, std::string&
 
     // Pass 3: edge targets are checked once here so that a path walk can follow them without bounds tests, and the
     // two-hop shortcuts over single-edge successors are filled in (layout.h, IndexView::skips).
-    out.skips.assign(2 * R + 2, 0);
+    out.skips.resize(2 * R + 2);
+    clear_all(out.skips.data(), out.skips.size() * sizeof(uint64_t));
     std::atomic<bool> edges_valid{true};
     auto has_record = [&](uint64_t node) { return node > in.offset && node - in.offset < R; };
 #pragma omp parallel for schedule(dynamic, 4096) num_threads(threads)
